@@ -1,0 +1,170 @@
+/*
+ * ssrlcv_b200.h -- C ABI of libssrlcv_match_b200.so
+ *
+ * B200-native (sm_100a) replacement for the SIFT descriptor matching path of
+ * uga-ssrl/SSRLCV: the kernels behind ssrlcv::MatchFactory<SIFT_Descriptor>
+ * (reference: include/MatchFactory.cuh:131-311, src/MatchFactory.cu).
+ * The reference has no FFI layer; its "operator API" is that C++ class.  The
+ * drop-in is therefore a replacement MatchFactory.cu
+ * whose methods marshal Unity<> device pointers into the entry points below.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary
+ *   - every function returns 0 on success, a negative SSRLCV_B200_E* code on
+ *     error, or a positive cudaError_t; nothing in the library calls exit()
+ *     (the reference's CudaSafeCall does, include/Memory.cuh:33-40 -- the shim
+ *     maps a non-zero return to that behaviour)
+ *   - "dev" pointers are device memory of the context's device; "host" are host
+ *   - record layouts are the reference's (sizes in bytes):
+ *       Feature<SIFT_Descriptor> 152 (include/Feature.cuh:30-38,68-94)
+ *       Image::Camera 80            (include/Image.cuh:41-57)
+ *       Match 40, DMatch 48, FeatureMatch<SIFT> 320, uint2_pair 16,
+ *       KeyPoint 16, MultiMatch 8   (include/MatchFactory.cuh:23-72)
+ *   - all work is enqueued on the context's stream; functions that return a
+ *     count to the host synchronise that stream before returning, mirroring the
+ *     reference's cudaDeviceSynchronize() after each kernel
+ *     (src/MatchFactory.cu:383-384)
+ */
+#ifndef SSRLCV_B200_H
+#define SSRLCV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSRLCV_B200_ABI_VERSION 1
+
+enum {
+  SSRLCV_B200_EINVAL = -1,      /* bad argument (NULL, size mismatch, unknown kind) */
+  SSRLCV_B200_ENODEVICE = -2,   /* no sm_100 device / driver entry point missing    */
+  SSRLCV_B200_ESEEDSIZE = -3,   /* seed distances do not belong to the query set (src/MatchFactory.cu:370-373) */
+  SSRLCV_B200_ETHRESHOLD = -4,  /* refine threshold == 0 (src/MatchFactory.cu:138-141) */
+  SSRLCV_B200_ENOMEM = -5
+};
+
+/* output record selected by the reference method family */
+enum {
+  SSRLCV_B200_OUT_MATCH = 0,        /* generateMatches*            -> Match        */
+  SSRLCV_B200_OUT_DMATCH = 1,       /* generateDistanceMatches*    -> DMatch       */
+  SSRLCV_B200_OUT_PAIR = 2,         /* generateMatches*IndexOnly   -> uint2_pair   */
+  SSRLCV_B200_OUT_FEATUREMATCH = 3  /* generateFeatureMatches*     -> FeatureMatch */
+};
+/* epipolar mask applied to the candidate targets of each query */
+enum {
+  SSRLCV_B200_MASK_NONE = 0,        /* matchFeaturesBruteForce        */
+  SSRLCV_B200_MASK_FUNDAMENTAL = 1, /* matchFeaturesConstrained       (F matrix, src/MatchFactory.cu:1598-1657) */
+  SSRLCV_B200_MASK_DOUBLE = 2       /* matchFeaturesDoubleConstrained (GEO_ORBIT=1, src/MatchFactory.cu:1507-1597) */
+};
+/* distance engine; TCGEN05 is the product path, SIMT exists to cross-check it on device */
+enum { SSRLCV_B200_ENGINE_TCGEN05 = 0, SSRLCV_B200_ENGINE_SIMT = 1 };
+
+typedef struct ssrlcv_b200_ctx ssrlcv_b200_ctx;   /* device, stream, workspaces */
+typedef struct ssrlcv_b200_set ssrlcv_b200_set;   /* a feature set repacked for TMA / tcgen05 */
+
+/* replaces: the arguments every matchFeatures* kernel receives (src/MatchFactory.cu:1463-1466,
+ * 1659-1662, 1599-1601, 2195-2198) plus MatchFactory::{absolute,relative}Threshold */
+typedef struct {
+  int32_t  out_kind;            /* SSRLCV_B200_OUT_*  */
+  int32_t  mask_kind;           /* SSRLCV_B200_MASK_* */
+  float    absolute_threshold;  /* MatchFactory::absoluteThreshold (FLT_MAX by default) */
+  float    relative_threshold;  /* MatchFactory::relativeThreshold; the library applies rel or rel*rel
+                                   exactly as the reference kernel of (out_kind, mask_kind) does */
+  uint32_t query_image_id;      /* query->id  */
+  uint32_t target_image_id;     /* target->id */
+  float    epsilon;             /* px; Constrained / DoubleConstrained */
+  float    delta;               /* km; DoubleConstrained */
+  float    fundamental[9];      /* row-major float[3][3]; Constrained */
+  uint8_t  query_camera[80];    /* Image::Camera of the query image; DoubleConstrained */
+  uint8_t  target_camera[80];   /* Image::Camera of the target image; the library derives the 3x4
+                                   projection on the host like getProjectionMatrix (src/Image.cu:498-539) */
+  int32_t  compact;             /* 1: stable-compact valid entries (validateMatches, src/MatchFactory.cu:31-135);
+                                   0: keep all numQuery entries, invalid ones flagged (generateFeatureMatches
+                                   quirk, src/MatchFactory.cu:674-696) */
+  int32_t  engine;              /* SSRLCV_B200_ENGINE_* */
+} ssrlcv_b200_match_params;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int  ssrlcv_b200_abi_version(void);
+/* stream: a cudaStream_t to enqueue on, or NULL to let the library create its own. */
+int  ssrlcv_b200_create(ssrlcv_b200_ctx** ctx, int device, void* stream);
+void ssrlcv_b200_destroy(ssrlcv_b200_ctx* ctx);
+const char* ssrlcv_b200_last_error(const ssrlcv_b200_ctx* ctx);
+int  ssrlcv_b200_synchronize(ssrlcv_b200_ctx* ctx);
+/* number of kernels this library has launched on the context so far (bench bookkeeping) */
+uint64_t ssrlcv_b200_launch_count(const ssrlcv_b200_ctx* ctx);
+
+/* ---- feature sets -------------------------------------------------------------------------
+ * replaces: Unity<Feature<SIFT_Descriptor>>::device as consumed by the matching kernels.  The
+ * 152-byte AoS records cannot be read by TMA (stride 152 = 8 mod 16); pack() repacks them once
+ * into dense uint8[n][128] rows (+ norms, locations, sigma/theta). */
+int  ssrlcv_b200_pack(ssrlcv_b200_ctx* ctx, const void* features_dev, uint64_t n, ssrlcv_b200_set** out);
+int  ssrlcv_b200_pack_host(ssrlcv_b200_ctx* ctx, const void* features_host, uint64_t n, ssrlcv_b200_set** out);
+uint64_t ssrlcv_b200_set_size(const ssrlcv_b200_set* s);
+void ssrlcv_b200_set_free(ssrlcv_b200_set* s);
+
+/* ---- matching -----------------------------------------------------------------------------
+ * replaces: MatchFactory<T>::getSeedDistances (src/MatchFactory.cu:315-346) + getSeedMatchDistances
+ * (:1433-1460).  out_dev: float[size(query)]; FLT_MAX when the seed set is empty. */
+int  ssrlcv_b200_seed_distances(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* query, const ssrlcv_b200_set* seed,
+                                float* out_dev, int engine);
+
+/* replaces: generateMatches / generateDistanceMatches / generateMatchesIndexOnly / generateFeatureMatches
+ * and their Constrained / DoubleConstrained forms (src/MatchFactory.cu:349-905) including the
+ * validateMatches compaction.  seed_dist_dev: float[size(query)] from seed_distances, or NULL.
+ * out_dev: capacity size(query) records of params->out_kind.  *n_out: number of records written
+ * (ascending query index).  Synchronises. */
+int  ssrlcv_b200_match(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* params,
+                       const ssrlcv_b200_set* query, const ssrlcv_b200_set* target,
+                       const float* seed_dist_dev, uint64_t n_seed_dist, void* out_dev, uint64_t* n_out);
+
+/* Whole reference call sequence with HOST buffers (what MatchFactory does when the Unity arrays are in
+ * state `cpu`): H2D of both feature sets (+ seed set if seed_host != NULL), pack, seed distances, match,
+ * D2H of the result.  out_host: capacity n_query records. */
+int  ssrlcv_b200_match_host(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* params,
+                            const void* query_host, uint64_t n_query, const void* target_host, uint64_t n_target,
+                            const void* seed_host, uint64_t n_seed, void* out_host, uint64_t* n_out);
+
+/* Sharded reference set (multi-GPU): each rank matches the queries against its shard of the
+ * target set and emits one 64-bit candidate per query, key = d2 << 37 | (f mod 32) << 32 | f with f the
+ * GLOBAL target index (all-ones = no candidate); the minimum over shards is the reference's winner.
+ * target_offset must be a multiple of 32. */
+int  ssrlcv_b200_match_candidates(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* params,
+                                  const ssrlcv_b200_set* query, const ssrlcv_b200_set* target_shard,
+                                  uint64_t target_offset, uint64_t* keys_dev);
+/* Merge n_shards candidate arrays (keys_dev: [n_shards][size(query)], e.g. the output of an all-gather),
+ * then thresholds / ratio test / writers / compaction exactly as ssrlcv_b200_match.
+ * target_loc_dev: float2[n_target_total] locations of the whole target set (index = global f);
+ * needed for Match/DMatch outputs, may be NULL for SSRLCV_B200_OUT_PAIR. */
+int  ssrlcv_b200_finalize_candidates(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* params,
+                                     const ssrlcv_b200_set* query, const uint64_t* keys_dev, uint32_t n_shards,
+                                     const float* target_loc_dev, const float* seed_dist_dev,
+                                     void* out_dev, uint64_t* n_out);
+/* device pointer to the float2[n] locations of a packed set (borrowed) */
+const float* ssrlcv_b200_set_loc(const ssrlcv_b200_set* s);
+
+/* ---- post-processing ------------------------------------------------------------------------
+ * replaces: validateMatches (src/MatchFactory.cu:31-135): stable removal of invalid entries, in place. */
+int  ssrlcv_b200_validate(ssrlcv_b200_ctx* ctx, int out_kind, void* matches_dev, uint64_t n, uint64_t* n_out);
+/* replaces: refineMatches (src/MatchFactory.cu:137-160): keep distance <= threshold, stable, in place. */
+int  ssrlcv_b200_refine(ssrlcv_b200_ctx* ctx, void* dmatches_dev, uint64_t n, float threshold, uint64_t* n_out);
+/* replaces: sortMatches (src/MatchFactory.cu:191-222): ascending distance; equal distances keep their
+ * input order (deterministic; one valid outcome of the reference's unstable thrust::sort). */
+int  ssrlcv_b200_sort(ssrlcv_b200_ctx* ctx, void* dmatches_dev, uint64_t n);
+/* replaces: getRawMatches + convertMatchToRaw (src/MatchFactory.cu:257-280, :2921-2926). */
+int  ssrlcv_b200_raw_matches(ssrlcv_b200_ctx* ctx, const void* dmatches_dev, uint64_t n, void* matches_dev);
+
+/* ---- diagnostics used by the parity tests ----------------------------------------------------
+ * per-query epipolar segment end points (p1.x,p1.y,p2.x,p2.y) as the DoubleConstrained prologue
+ * computes them (replaces getEpipolarEndpoints, src/MatchFactory.cu:1241-1277). out_dev: float4[n]. */
+int  ssrlcv_b200_epipolar_endpoints(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* params,
+                                    const ssrlcv_b200_set* query, float* out_dev);
+/* sinf/cosf of x[n] computed on the device (validates the oracle's libdevice restatement) */
+int  ssrlcv_b200_device_sincos(ssrlcv_b200_ctx* ctx, const float* x_dev, uint64_t n, float* sin_dev, float* cos_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSRLCV_B200_H */

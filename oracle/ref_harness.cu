@@ -1,0 +1,143 @@
+/*
+ * ref_harness.cu -- TEST/BASELINE INFRASTRUCTURE ONLY.
+ *
+ * A thin extern "C" face over the UNMODIFIED reference MatchFactory<SIFT_Descriptor>
+ * (compiled from the sources where they lie under /root/reference by build_ref.sh;
+ * no reference source is copied into this repository).  It lets the parity tests
+ * and bench.py call the reference's own CUDA kernels on the B200 box with plain
+ * host buffers, through the reference's public API (ref: include/MatchFactory.cuh:131-311).
+ *
+ * Everything in this file is our code; it only *uses* the reference's classes.
+ */
+#include "MatchFactory.cuh"
+
+#include <chrono>
+#include <cstring>
+#include <sys/stat.h>
+
+using namespace ssrlcv;
+typedef Feature<SIFT_Descriptor> Feat;
+typedef ptr::value<Unity<Feat>> FeatSet;
+
+/* ---- the five io_util symbols Image.cu references (ref: src/io_util.cpp:27-70), so that
+ *      libpng/libjpeg/libtiff are not needed ---- */
+namespace ssrlcv {
+bool fileExists(std::string fileName) { std::ifstream f(fileName.c_str()); return f.good(); }
+std::string getFileExtension(std::string path) {
+  size_t p = path.find_last_of('.');
+  return p == std::string::npos ? std::string() : path.substr(p + 1);
+}
+std::string getFolderFromFilePath(std::string path) {
+  size_t p = path.find_last_of('/');
+  return p == std::string::npos ? std::string(".") : path.substr(0, p);
+}
+std::string getFileFromFilePath(std::string path) {
+  size_t p = path.find_last_of('/');
+  return p == std::string::npos ? path : path.substr(p + 1);
+}
+ptr::host<unsigned char> readImage(const char*, unsigned int&, unsigned int&, unsigned int&) {
+  fprintf(stderr, "ref_harness: readImage is not available (no image codecs linked)\n");
+  abort();
+}
+}  // namespace ssrlcv
+
+static FeatSet make_set(const void* host, unsigned long n, int state) {
+  FeatSet u(nullptr, n, cpu);
+  memcpy((void*)u->host.get(), host, n * sizeof(Feat));
+  if (state == 2) u->setMemoryState(gpu);
+  else if (state == 3) u->setMemoryState(both);
+  return u;
+}
+
+static ptr::value<Image> make_image(int id, const void* camera80) {
+  ptr::value<Image> img;
+  img.construct();
+  img->id = id;
+  if (camera80) memcpy((void*)&img->camera, camera80, sizeof(Image::Camera));
+  img->size = img->camera.size;
+  return img;
+}
+
+template <typename U>
+static unsigned long copy_out(U m, void* out_host, size_t elt) {
+  if (m == nullptr) return 0;
+  unsigned long n = m->size();
+  if (m->getMemoryState() == gpu) m->transferMemoryTo(cpu);
+  memcpy(out_host, (void*)m->host.get(), n * elt);
+  return n;
+}
+
+extern "C" {
+
+int ref_sizes(int* feat, int* camera, int* match, int* dmatch, int* pair, int* fmatch) {
+  *feat = sizeof(Feat); *camera = sizeof(Image::Camera); *match = sizeof(Match); *dmatch = sizeof(DMatch);
+  *pair = sizeof(uint2_pair); *fmatch = sizeof(FeatureMatch<SIFT_Descriptor>);
+  return 0;
+}
+
+/* getSeedDistances (ref: src/MatchFactory.cu:315-346).  state: 1 cpu, 2 gpu, 3 both. */
+int ref_seed_distances(const void* q, unsigned long nq, const void* seed, unsigned long ns, int state,
+                       float* out, double* ms) {
+  mkdir("out", 0755);
+  FeatSet qs = make_set(q, nq, state), ss = make_set(seed, ns, state);
+  MatchFactory<SIFT_Descriptor> mf(1.0f, FLT_MAX);
+  mf.setSeedFeatures(ss);
+  cudaDeviceSynchronize();
+  auto t0 = std::chrono::steady_clock::now();
+  ptr::value<Unity<float>> d = mf.getSeedDistances(qs);
+  cudaDeviceSynchronize();
+  if (ms) *ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  d->transferMemoryTo(cpu);
+  memcpy(out, d->host.get(), nq * sizeof(float));
+  return 0;
+}
+
+/* out_kind: 0 Match, 1 DMatch, 2 uint2_pair.  mask_kind: 0 none, 1 fundamental, 2 double constrained.
+ * seed_dist may be NULL.  Returns the number of entries the reference returned (after its own
+ * validateMatches), copied to out_host.  ms = wall time of the API call (inputs already in `state`). */
+long ref_match(int out_kind, int mask_kind, float abs_thr, float rel_thr, int qid, int tid,
+               const void* q, unsigned long nq, const void* t, unsigned long nt, const float* seed_dist, int state,
+               float eps, float delta, const float* F9, const void* qcam80, const void* tcam80,
+               void* out_host, double* ms) {
+  mkdir("out", 0755);
+  FeatSet qs = make_set(q, nq, state), ts = make_set(t, nt, state);
+  ptr::value<Image> qi = make_image(qid, qcam80), ti = make_image(tid, tcam80);
+  MatchFactory<SIFT_Descriptor> mf(rel_thr, abs_thr);
+  ptr::value<Unity<float>> sd = nullptr;
+  if (seed_dist) {
+    sd = ptr::value<Unity<float>>(nullptr, nq, cpu);
+    memcpy(sd->host.get(), seed_dist, nq * sizeof(float));
+    if (state != 1) sd->setMemoryState(gpu);
+  }
+  float F[3][3];
+  if (F9) memcpy(F, F9, sizeof F);
+  cudaDeviceSynchronize();
+  auto t0 = std::chrono::steady_clock::now();
+  long n = -1;
+  ptr::value<Unity<Match>> m0 = nullptr;
+  ptr::value<Unity<DMatch>> m1 = nullptr;
+  ptr::value<Unity<uint2_pair>> m2 = nullptr;
+  if (out_kind == 0) {
+    if (mask_kind == 0) m0 = mf.generateMatches(qi, qs, ti, ts, sd);
+    else if (mask_kind == 1) m0 = mf.generateMatchesConstrained(qi, qs, ti, ts, eps, F, sd);
+    else m0 = mf.generateMatchesDoubleConstrained(qi, qs, ti, ts, eps, delta, sd);
+  } else if (out_kind == 1) {
+    if (mask_kind == 0) m1 = mf.generateDistanceMatches(qi, qs, ti, ts, sd);
+    else if (mask_kind == 1) m1 = mf.generateDistanceMatchesConstrained(qi, qs, ti, ts, eps, F, sd);
+    else m1 = mf.generateDistanceMatchesDoubleConstrained(qi, qs, ti, ts, eps, delta, sd);
+  } else if (out_kind == 2) {
+    if (mask_kind == 0) m2 = mf.generateMatchesIndexOnly(qi, qs, ti, ts, sd);
+    else if (mask_kind == 1) m2 = mf.generateMatchesConstrainedIndexOnly(qi, qs, ti, ts, eps, F, sd);
+    else m2 = mf.generateMatchesDoubleConstrainedIndexOnly(qi, qs, ti, ts, eps, delta, sd);
+  } else {
+    return -2;
+  }
+  cudaDeviceSynchronize();
+  if (ms) *ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (out_kind == 0) n = (long)copy_out(m0, out_host, sizeof(Match));
+  else if (out_kind == 1) n = (long)copy_out(m1, out_host, sizeof(DMatch));
+  else n = (long)copy_out(m2, out_host, sizeof(uint2_pair));
+  return n;
+}
+
+}  // extern "C"

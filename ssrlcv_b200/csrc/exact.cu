@@ -1,0 +1,92 @@
+// exact.cu -- exact SIMT evaluation of one query against a target range.
+// Two uses:
+//   * tie resolution: queries whose maximum score occurred in more than one 32-target window of the
+//     tensor-core kernel (rare: needs equal squared distances up to parity) are re-evaluated here;
+//   * SSRLCV_B200_ENGINE_SIMT: the whole problem, to cross-check the tcgen05 path on the device.
+// One warp per (split, query): lane l owns targets l, l+32, ... exactly like one block of the reference's
+// matchFeatures* kernels (ref: src/MatchFactory.cu:1466-1492), so the key (d2, f%32, f) falls out naturally.
+#include "geometry.cuh"
+#include "matcher.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const uint32_t lo = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v), o);
+    const uint32_t hi = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), o);
+    const uint64_t w = (static_cast<uint64_t>(hi) << 32) | lo;
+    v = w < v ? w : v;
+  }
+  return v;
+}
+
+template <int kMask>
+__global__ void __launch_bounds__(256) exact_kernel(SmaxArgs a, MaskParams mp, int use_list) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t total = use_list ? *a.n_flagged : a.n_splits * a.nq;
+  for (uint32_t item = warp; item < total; item += n_warps) {
+    uint32_t split, row;
+    if (use_list) { const uint32_t e = a.flagged[item]; split = e / a.nq_pad; row = e % a.nq_pad; }
+    else { split = item / a.nq; row = item % a.nq; }
+    const uint4* qd = reinterpret_cast<const uint4*>(a.q_desc + static_cast<uint64_t>(row) * kDescBytes);
+    uint4 q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = __ldg(qd + i);
+    const int32_t qn = a.q_norm[row];
+    QueryMask qm;
+    if (kMask != SSRLCV_B200_MASK_NONE) qm = make_query_mask<kMask>(mp, a.q_loc[row]);
+    const uint64_t f_begin = static_cast<uint64_t>(split) * a.tiles_per_split * kBN;
+    uint64_t f_end = f_begin + static_cast<uint64_t>(a.tiles_per_split) * kBN;
+    if (f_end > a.nt) f_end = a.nt;
+    uint64_t best = kKeyNone;
+    for (uint64_t f = f_begin + lane; f < f_end; f += 32) {
+      if (kMask != SSRLCV_B200_MASK_NONE) {
+        const float2 tl = a.t_loc[f];
+        if (mask_skips<kMask>(qm, tl.x, tl.y, mp.eps)) continue;
+      }
+      const uint4* td = reinterpret_cast<const uint4*>(a.t_desc + f * kDescBytes);
+      uint32_t dot = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 t = __ldg(td + i);
+        dot = __dp4a(q[i].x, t.x, dot); dot = __dp4a(q[i].y, t.y, dot);
+        dot = __dp4a(q[i].z, t.z, dot); dot = __dp4a(q[i].w, t.w, dot);
+      }
+      const uint32_t d2 = static_cast<uint32_t>(qn + a.t_norm[f] - 2 * static_cast<int32_t>(dot));
+      const uint64_t key = make_key(d2, f + a.target_offset);
+      best = key < best ? key : best;
+    }
+    best = warp_min_u64(best);
+    if (lane == 0) a.keys[static_cast<uint64_t>(split) * a.nq_pad + row] = best;
+  }
+}
+
+void launch_exact(cudaStream_t st, const SmaxArgs& a, const MaskParams& mp, int use_list, int sm_count) {
+  const int blocks = sm_count * 8;
+  switch (mp.kind) {
+    case SSRLCV_B200_MASK_NONE: exact_kernel<SSRLCV_B200_MASK_NONE><<<blocks, 256, 0, st>>>(a, mp, use_list); break;
+    case SSRLCV_B200_MASK_FUNDAMENTAL: exact_kernel<SSRLCV_B200_MASK_FUNDAMENTAL><<<blocks, 256, 0, st>>>(a, mp, use_list); break;
+    default: exact_kernel<SSRLCV_B200_MASK_DOUBLE><<<blocks, 256, 0, st>>>(a, mp, use_list); break;
+  }
+}
+
+// ---- small diagnostics kernels -----------------------------------------------------------------
+__global__ void endpoints_kernel(MaskParams mp, const float2* loc, uint64_t n, float4* out) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = epipolar_endpoints_ref(mp, loc[i]);
+}
+void launch_endpoints(cudaStream_t st, const MaskParams& mp, const float2* loc, uint64_t n, float4* out) {
+  if (n) endpoints_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(mp, loc, n, out);
+}
+__global__ void sincos_kernel(const float* x, uint64_t n, float* s, float* c) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) { s[i] = sinf(x[i]); c[i] = cosf(x[i]); }
+}
+void launch_sincos(cudaStream_t st, const float* x, uint64_t n, float* s, float* c) {
+  if (n) sincos_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, n, s, c);
+}
+
+}  // namespace b200

@@ -1,0 +1,112 @@
+// matcher.cuh -- internal types shared by the kernels and the C-ABI layer.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/ssrlcv_b200.h"
+
+namespace b200 {
+
+// ----- reference record layouts (byte-compatible, see include/ssrlcv_b200.h) -----
+struct alignas(8) RefFeature {   // Feature<SIFT_Descriptor>, include/Feature.cuh:30-38,68-94
+  int32_t parent;
+  int32_t pad_;
+  float2  loc;
+  float   sigma, theta;
+  uint8_t values[128];
+};
+static_assert(sizeof(RefFeature) == 152, "Feature<SIFT_Descriptor> is 152 bytes");
+
+struct RefCamera {               // Image::Camera, include/Image.cuh:41-57
+  float    cam_pos[3];
+  float    cam_rot[3];
+  float    fov[2];
+  float    foc;
+  float    pad0_;
+  float    dpix[2];
+  long long timeStamp;
+  float    ecef_offset[3];
+  uint8_t  no_rot;
+  uint8_t  pad1_[3];
+  uint32_t size[2];
+};
+static_assert(sizeof(RefCamera) == 80, "Image::Camera is 80 bytes");
+
+struct alignas(8) RefKeyPoint { int32_t parentId; int32_t pad_; float2 loc; };                         // 16
+struct alignas(8) RefMatch { uint8_t invalid; uint8_t pad_[7]; RefKeyPoint kp[2]; };                  // 40
+struct alignas(8) RefDMatch { uint8_t invalid; uint8_t pad_[7]; RefKeyPoint kp[2]; float distance; float pad2_; };  // 48
+struct RefSift { float sigma, theta; uint8_t values[128]; };                                          // 136
+struct alignas(8) RefFeatureMatch {                                                                   // 320
+  uint8_t invalid; uint8_t pad_[7]; RefKeyPoint kp[2]; float distance; RefSift desc[2]; float pad2_;
+};
+struct alignas(8) RefPair { uint32_t a[2]; uint32_t b[2]; };                                          // 16
+static_assert(sizeof(RefKeyPoint) == 16 && sizeof(RefMatch) == 40 && sizeof(RefDMatch) == 48, "match layouts");
+static_assert(sizeof(RefFeatureMatch) == 320 && offsetof(RefFeatureMatch, desc) == 44, "FeatureMatch layout");
+static_assert(sizeof(RefPair) == 16, "uint2_pair layout");
+
+// ----- tiling -----
+constexpr int kBM = 128;          // query rows per CTA tile  (UMMA M, cta_group::1)
+constexpr int kBN = 256;          // target rows per pipeline stage (UMMA N)
+constexpr int kDescBytes = 128;   // SIFT descriptor length = K of the main contraction
+constexpr int kExtBytes = 32;     // extra K block carrying the folded -|b|^2/2 term
+constexpr int kRowPad = 256;      // packed sets are padded to a multiple of this many rows
+constexpr int kChunk = 32;        // candidate window (targets) resolved exactly per query
+
+// Fold constants: the extra K block multiplies the constant vector c = [1, 255 x 31] (u8) with
+// per-target digits so that c . digits = W = hmax - (|b|^2 >> 1) + 2  (>= 2 for every real target,
+// 0 for padding rows).  Representable range of W: [0, 255 + 255*31*255].
+constexpr int32_t kFoldMaxW = 255 + 255 * 31 * 255;   // 2 016 030
+
+// 64-bit candidate key: d2 << 37 | (f & 31) << 32 | f   (min == the reference's winner rule)
+constexpr uint64_t kKeyNone = ~0ull;                 // no candidate
+constexpr uint64_t kKeyNeedsExact = ~0ull - 1;       // tie between windows: resolve by the exact kernel
+__host__ __device__ __forceinline__ uint64_t make_key(uint32_t d2, uint64_t f) {
+  return (static_cast<uint64_t>(d2) << 37) | ((f & 31ull) << 32) | (f & 0xFFFFFFFFull);
+}
+
+// ----- per-query epipolar mask state -----
+struct MaskParams {
+  int32_t kind;            // SSRLCV_B200_MASK_*
+  float   eps, delta;
+  float   F[9];
+  RefCamera qcam;
+  float   P[12];           // target projection (host, getProjectionMatrix)
+};
+
+struct ssrlcv_b200_set_impl {
+  uint64_t n, n_pad;
+  uint8_t* desc;      // [n_pad][128]
+  uint8_t* ext;       // [n_pad][32]   fold digits
+  int32_t* norm;      // [n_pad]       |b|^2
+  int32_t* wcol;      // [n_pad]       W (same value the digits encode), 0 on padding rows
+  float2*  loc;       // [n_pad]
+  float2*  sigtheta;  // [n_pad]
+  int32_t  hmin, hmax;   // range of |b|^2 >> 1 over the set (host copy)
+  bool     fold_ok;      // W fits the digit range -> fused extra-K-block path
+  CUtensorMap map_a;     // desc, box 128 x kBM rows, SWIZZLE_128B
+  CUtensorMap map_b;     // desc, box 128 x kBN rows, SWIZZLE_128B
+  CUtensorMap map_ext;   // ext,  box  32 x kBN rows, SWIZZLE_32B
+};
+
+// arguments of the fused tcgen05 kernel
+struct SmaxArgs {
+  uint32_t nq, nt;               // real sizes
+  uint32_t nq_pad;
+  uint32_t n_qtiles;             // ceil(nq / kBM)
+  uint32_t n_ttiles;             // ceil(nt / kBN)
+  uint32_t n_splits;             // target range split count
+  uint32_t tiles_per_split;
+  uint64_t target_offset;        // global index of target 0 of this set (sharded mode)
+  const uint8_t* q_desc; const int32_t* q_norm; const float2* q_loc;
+  const uint8_t* t_desc; const int32_t* t_norm; const float2* t_loc; const int32_t* t_wcol;
+  uint64_t* keys;                // [n_splits][nq_pad]
+  uint32_t* flagged;             // list of (split * nq_pad + row) needing the exact kernel
+  uint32_t* n_flagged;
+};
+
+}  // namespace b200
+
+struct ssrlcv_b200_set : b200::ssrlcv_b200_set_impl {
+  ssrlcv_b200_ctx* ctx;
+};

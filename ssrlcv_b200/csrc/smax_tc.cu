@@ -1,0 +1,341 @@
+// smax_tc.cu -- the fused tensor-core matcher for sm_100a.
+//
+// Brute-force 128-D nearest neighbour as the dense contraction it is.  For query a and target b
+//     d2(a,b) = |a|^2 + |b|^2 - 2 a.b ,        |b|^2 = 2h + p  (p = parity)
+// so minimising d2 over b is maximising the integer score
+//     S(a,b) = a.b + W_b ,   W_b = hmax - h_b + 2          (d2 = |a|^2 - 2 (S - hmax - 2) + p)
+// S is produced ENTIRELY by the tensor core: four tcgen05.mma kind::i8 (u8 x u8 -> s32, K = 32 each)
+// contract the 128 descriptor bytes and a fifth contracts a constant vector [1,255,...,255] with 32
+// base-255 digits of W_b ("fold"), accumulating in TMEM.  The epilogue therefore does no arithmetic on
+// the accumulator except a running 3-input max: per 32-target window it keeps the window maximum and,
+// only when a window reaches the running best, records which window it was.  Nothing of the 128 x Nt
+// score matrix ever reaches shared or global memory.
+//
+// After a query tile has seen its whole target range the same warps resolve the recorded window
+// exactly: 32 lanes = the 32 targets of the window = the 32 lanes of the reference's block, exact
+// integer d2 by dp4a, winner by the reference's rule min (d2, f mod 32, f)
+// (ref: src/MatchFactory.cu:1476-1492).  Score ties ACROSS windows (equal d2 up to parity) are rare and
+// are flagged for the exact SIMT kernel (exact.cu) instead of being guessed.
+//
+// Pipeline per CTA (one CTA per SM, persistent over (query tile, target split) work units):
+//   warp 0  TMA producer : A tile (128 x 128 B, SWIZZLE_128B) per unit; per stage a B tile
+//                          (256 x 128 B, SWIZZLE_128B) + its digit tile (256 x 32 B, SWIZZLE_32B)
+//   warp 1  MMA issuer   : 5 x tcgen05.mma (M128 N256 K32) per stage into one of two 256-column
+//                          TMEM accumulators; tcgen05.commit releases the smem stage and publishes
+//                          the accumulator
+//   warp 2  TMEM allocator, warp 3 idle
+//   warps 4-7 epilogue   : tcgen05.ld 32x32b.x32, max3 tree, window bookkeeping, final exact resolve
+// Masked variants (epipolar constraints) evaluate the reference's float mask per (query, target) in the
+// epilogue on target locations staged through a small shared-memory ring.
+#include "geometry.cuh"
+#include "matcher.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int kStages = 4;
+constexpr int kColStages = 4;
+constexpr uint32_t kABytes = kBM * kDescBytes;       // 16384
+constexpr uint32_t kBBytes = kBN * kDescBytes;       // 32768
+constexpr uint32_t kBExtBytes = kBN * kExtBytes;     // 8192
+constexpr uint32_t kAExtBytes = kBM * kExtBytes;     // 4096
+constexpr uint32_t kColLocBytes = kBN * 8;           // float2 per target
+constexpr uint32_t kColWBytes = kBN * 4;             // int32 W per target
+constexpr uint32_t kTmemCols = 512;
+
+struct SmemLayout {
+  static constexpr uint32_t a = 0;                                       // 2 x 16 KB
+  static constexpr uint32_t b = a + 2 * kABytes;                         // kStages x 32 KB
+  static constexpr uint32_t bext = b + kStages * kBBytes;                // kStages x 8 KB
+  static constexpr uint32_t aext = bext + kStages * kBExtBytes;          // 4 KB
+  static constexpr uint32_t col_loc = aext + kAExtBytes;                 // kColStages x 2 KB
+  static constexpr uint32_t col_w = col_loc + kColStages * kColLocBytes; // kColStages x 1 KB
+  static constexpr uint32_t bars = col_w + kColStages * kColWBytes;
+  static constexpr uint32_t n_bars = 2 * kStages + 4 + 4 + 2 * kColStages;
+  static constexpr uint32_t tmem_ptr = bars + n_bars * 8;
+  static constexpr uint32_t total = tmem_ptr + 16;
+};
+constexpr uint32_t kSmemBytes = SmemLayout::total + 1024;   // + slack for manual 1024-byte alignment
+
+__device__ __forceinline__ int32_t max3(int32_t a, int32_t b, int32_t c) { return max(max(a, b), c); }
+
+__device__ __forceinline__ uint64_t warp_min_u64_tc(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const uint32_t lo = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v), o);
+    const uint32_t hi = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), o);
+    const uint64_t w = (static_cast<uint64_t>(hi) << 32) | lo;
+    v = w < v ? w : v;
+  }
+  return v;
+}
+
+// kMask: SSRLCV_B200_MASK_*.  kFold: W_b carried by the fifth MMA (true) or added in the epilogue (false).
+template <int kMask, bool kFold>
+__global__ void __launch_bounds__(256, 1)
+smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
+            const __grid_constant__ CUtensorMap map_text, const SmaxArgs args, const MaskParams mp) {
+  constexpr bool kCols = (kMask != SSRLCV_B200_MASK_NONE) || !kFold;   // epilogue needs per-target data
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SmemLayout::bars);
+  uint64_t* full = bars;                         // [kStages]   TMA -> MMA
+  uint64_t* empty = bars + kStages;              // [kStages]   MMA -> TMA
+  uint64_t* a_full = bars + 2 * kStages;         // [2]
+  uint64_t* a_empty = a_full + 2;                // [2]
+  uint64_t* t_full = a_empty + 2;                // [2]         MMA -> epilogue (accumulator ready)
+  uint64_t* t_empty = t_full + 2;                // [2]         epilogue -> MMA (accumulator drained)
+  uint64_t* c_full = t_empty + 2;                // [kColStages] TMA -> epilogue (target columns data)
+  uint64_t* c_empty = c_full + kColStages;       // [kColStages]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SmemLayout::tmem_ptr);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n_units = args.n_qtiles * args.n_splits;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_t); tma_prefetch_desc(&map_text);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+    for (int i = 0; i < kColStages; ++i) { mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 2) { tmem_alloc<kTmemCols>(tmem_ptr); tmem_relinquish(); }
+  if (warp == 3) {
+    // constant A-side operand of the fold MMA: every row = [1, 255 x 31], stored in the SWIZZLE_32B
+    // K-major layout (32-byte rows, 16-byte chunk index ^= bit 7 of the byte address).
+    for (int r = lane; r < kBM; r += 32) {
+      const uint32_t sw = (r >> 2) & 1;
+      uint4 c0 = make_uint4(0xFFFFFF01u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+      uint4 c1 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+      uint4* row = reinterpret_cast<uint4*>(smem + SmemLayout::aext + r * kExtBytes);
+      row[0 ^ sw] = c0;
+      row[1 ^ sw] = c1;
+    }
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0, aslot = 0, aphase = 0, cs = 0, cphase = 0;
+      for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const uint32_t qt = unit / args.n_splits, sp = unit % args.n_splits;
+        const uint32_t t0 = sp * args.tiles_per_split;
+        const uint32_t t1 = min(t0 + args.tiles_per_split, args.n_ttiles);
+        mbar_wait(&a_empty[aslot], aphase ^ 1);
+        mbar_arrive_expect_tx(&a_full[aslot], kABytes);
+        tma_load_2d(smem + SmemLayout::a + aslot * kABytes, &map_q, &a_full[aslot], 0, static_cast<int32_t>(qt * kBM));
+        for (uint32_t j = t0; j < t1; ++j) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], kBBytes + (kFold ? kBExtBytes : 0));
+          tma_load_2d(smem + SmemLayout::b + stage * kBBytes, &map_t, &full[stage], 0, static_cast<int32_t>(j * kBN));
+          if (kFold) tma_load_2d(smem + SmemLayout::bext + stage * kBExtBytes, &map_text, &full[stage], 0, static_cast<int32_t>(j * kBN));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (kCols) {
+            mbar_wait(&c_empty[cs], cphase ^ 1);
+            const uint32_t bytes = (kMask != SSRLCV_B200_MASK_NONE ? kColLocBytes : 0) + (!kFold ? kColWBytes : 0);
+            mbar_arrive_expect_tx(&c_full[cs], bytes);
+            if (kMask != SSRLCV_B200_MASK_NONE)
+              bulk_load_1d(smem + SmemLayout::col_loc + cs * kColLocBytes, args.t_loc + static_cast<uint64_t>(j) * kBN, kColLocBytes, &c_full[cs]);
+            if (!kFold)
+              bulk_load_1d(smem + SmemLayout::col_w + cs * kColWBytes, args.t_wcol + static_cast<uint64_t>(j) * kBN, kColWBytes, &c_full[cs]);
+            if (++cs == kColStages) { cs = 0; cphase ^= 1; }
+          }
+        }
+        if (++aslot == 2) { aslot = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_i8(kBM, kBN, 0, 0);
+      const uint64_t aext_desc = make_smem_desc(smem_u32(smem + SmemLayout::aext), 256, kSwizzle32B);
+      uint32_t stage = 0, phase = 0, aslot = 0, aphase = 0, acc = 0, accphase = 0;
+      for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const uint32_t sp = unit % args.n_splits;
+        const uint32_t t0 = sp * args.tiles_per_split;
+        const uint32_t t1 = min(t0 + args.tiles_per_split, args.n_ttiles);
+        mbar_wait(&a_full[aslot], aphase);
+        const uint64_t a_desc = make_smem_desc(smem_u32(smem + SmemLayout::a + aslot * kABytes), 1024, kSwizzle128B);
+        for (uint32_t j = t0; j < t1; ++j) {
+          mbar_wait(&t_empty[acc], accphase ^ 1);
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * kBN;
+          const uint64_t b_desc = make_smem_desc(smem_u32(smem + SmemLayout::b + stage * kBBytes), 1024, kSwizzle128B);
+#pragma unroll
+          for (uint32_t k = 0; k < 4; ++k)   // +32 bytes along K inside the 128-byte swizzle atom = +2 in the address field
+            mma_i8_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, k);
+          if (kFold) {
+            const uint64_t bext_desc = make_smem_desc(smem_u32(smem + SmemLayout::bext + stage * kBExtBytes), 256, kSwizzle32B);
+            mma_i8_ss(d_tmem, aext_desc, bext_desc, idesc, 1);
+          }
+          mma_commit(&empty[stage]);
+          mma_commit(&t_full[acc]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++acc == 2) { acc = 0; accphase ^= 1; }
+        }
+        mma_commit(&a_empty[aslot]);
+        if (++aslot == 2) { aslot = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================== epilogue ===============================
+    const uint32_t quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32)
+    const uint32_t lane_addr = (quarter * 32u) << 16;
+    uint32_t acc = 0, accphase = 0, cs = 0, cphase = 0;
+    for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      const uint32_t qt = unit / args.n_splits, sp = unit % args.n_splits;
+      const uint32_t t0 = sp * args.tiles_per_split;
+      const uint32_t t1 = min(t0 + args.tiles_per_split, args.n_ttiles);
+      const uint32_t row = qt * kBM + quarter * 32 + lane;       // this thread's query
+      QueryMask qm;
+      if (kMask != SSRLCV_B200_MASK_NONE) qm = make_query_mask<kMask>(mp, args.q_loc[min(row, args.nq_pad - 1)]);
+
+      int32_t best = 1;            // real scores are >= 2, padding / masked entries are 0
+      uint32_t bwin = 0;           // window (32 targets) index inside this target set
+      uint32_t tie = 0;
+      for (uint32_t j = t0; j < t1; ++j) {
+        mbar_wait(&t_full[acc], accphase);
+        tc_fence_after();
+        const float2* s_loc = reinterpret_cast<const float2*>(smem + SmemLayout::col_loc + cs * kColLocBytes);
+        const int32_t* s_w = reinterpret_cast<const int32_t*>(smem + SmemLayout::col_w + cs * kColWBytes);
+        if (kCols) mbar_wait(&c_full[cs], cphase);
+        const uint32_t taddr = tmem_base + acc * kBN + lane_addr;
+        const uint32_t n_win = min(static_cast<uint32_t>(kBN / kChunk), (args.nt - j * kBN + kChunk - 1) / kChunk);
+        uint32_t v[2][32];
+        tmem_ld_32x32(taddr, v[0]);
+#pragma unroll
+        for (uint32_t c = 0; c < kBN / kChunk; ++c) {
+          if (c < n_win) {                                        // warp-uniform
+            tmem_ld_wait();
+            if (c + 1 < n_win) tmem_ld_32x32(taddr + (c + 1) * kChunk, v[(c + 1) & 1]);
+            uint32_t(&x)[32] = v[c & 1];
+            if (!kFold) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) x[e] = static_cast<uint32_t>(static_cast<int32_t>(x[e]) + s_w[c * kChunk + e]);
+            }
+            if (kMask != SSRLCV_B200_MASK_NONE) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 2) {
+                const float4 l2 = *reinterpret_cast<const float4*>(&s_loc[c * kChunk + e]);
+                if (mask_skips<kMask>(qm, l2.x, l2.y, mp.eps)) x[e] = 0;
+                if (mask_skips<kMask>(qm, l2.z, l2.w, mp.eps)) x[e + 1] = 0;
+              }
+            }
+            int32_t m = max3(static_cast<int32_t>(x[0]), static_cast<int32_t>(x[1]), static_cast<int32_t>(x[2]));
+#pragma unroll
+            for (int e = 3; e < 31; e += 2) m = max3(m, static_cast<int32_t>(x[e]), static_cast<int32_t>(x[e + 1]));
+            m = max(m, static_cast<int32_t>(x[31]));
+            if (m >= best) {                                       // rare after the first windows
+              if (m > best) { best = m; bwin = j * (kBN / kChunk) + c; tie = 0; }
+              else tie = 1;
+            }
+          }
+        }
+        // accumulator drained -> hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&t_empty[acc]);
+          if (kCols) mbar_arrive(&c_empty[cs]);
+        }
+        if (++acc == 2) { acc = 0; accphase ^= 1; }
+        if (kCols) { if (++cs == kColStages) { cs = 0; cphase ^= 1; } }
+      }
+
+      // ---------------- exact resolve of the recorded window, one query per iteration ----------------
+      uint64_t mykey = kKeyNone;
+      const uint32_t row0 = qt * kBM + quarter * 32;
+      for (int r = 0; r < 32; ++r) {
+        const uint32_t qrow = row0 + r;
+        if (qrow >= args.nq) break;                                // warp-uniform
+        const int32_t S_r = __shfl_sync(0xffffffffu, best, r);
+        const uint32_t win_r = __shfl_sync(0xffffffffu, bwin, r);
+        const uint32_t tie_r = __shfl_sync(0xffffffffu, tie, r);
+        uint64_t res = kKeyNone;
+        if (S_r > 1) {
+          if (tie_r) {
+            res = kKeyNeedsExact;
+            if (lane == 0) {
+              const uint32_t slot = atomicAdd(args.n_flagged, 1u);
+              args.flagged[slot] = sp * args.nq_pad + qrow;
+            }
+          } else {
+            const uint64_t f = static_cast<uint64_t>(win_r) * kChunk + lane;
+            uint64_t key = kKeyNone;
+            bool ok = f < args.nt;
+            if (kMask != SSRLCV_B200_MASK_NONE) {
+              // re-evaluate the mask with the owning thread's per-query state
+              const float2 tl = ok ? args.t_loc[f] : make_float2(0.f, 0.f);
+              QueryMask qr;
+              qr.seg.lo_x = __shfl_sync(0xffffffffu, qm.seg.lo_x, r);   qr.seg.hi_x = __shfl_sync(0xffffffffu, qm.seg.hi_x, r);
+              qr.seg.left_x = __shfl_sync(0xffffffffu, qm.seg.left_x, r); qr.seg.left_y = __shfl_sync(0xffffffffu, qm.seg.left_y, r);
+              qr.seg.slope = __shfl_sync(0xffffffffu, qm.seg.slope, r);  qr.seg.top_lo = __shfl_sync(0xffffffffu, qm.seg.top_lo, r);
+              qr.seg.bot_hi = __shfl_sync(0xffffffffu, qm.seg.bot_hi, r); qr.seg.vertical = __shfl_sync(0xffffffffu, qm.seg.vertical, r);
+              qr.line.ex = __shfl_sync(0xffffffffu, qm.line.ex, r); qr.line.ey = __shfl_sync(0xffffffffu, qm.line.ey, r);
+              qr.line.ez = __shfl_sync(0xffffffffu, qm.line.ez, r);
+              if (ok && mask_skips<kMask>(qr, tl.x, tl.y, mp.eps)) ok = false;
+            }
+            if (ok) {
+              const uint4* qd = reinterpret_cast<const uint4*>(args.q_desc + static_cast<uint64_t>(qrow) * kDescBytes);
+              const uint4* td = reinterpret_cast<const uint4*>(args.t_desc + f * kDescBytes);
+              uint32_t dot = 0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint4 a4 = __ldg(qd + i), b4 = __ldg(td + i);
+                dot = __dp4a(a4.x, b4.x, dot); dot = __dp4a(a4.y, b4.y, dot);
+                dot = __dp4a(a4.z, b4.z, dot); dot = __dp4a(a4.w, b4.w, dot);
+              }
+              const uint32_t d2 = static_cast<uint32_t>(args.q_norm[qrow] + args.t_norm[f] - 2 * static_cast<int32_t>(dot));
+              key = make_key(d2, f + args.target_offset);
+            }
+            res = warp_min_u64_tc(key);
+          }
+        }
+        if (lane == r) mykey = res;
+      }
+      if (row < args.nq) args.keys[static_cast<uint64_t>(sp) * args.nq_pad + row] = mykey;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+template <int kMask, bool kFold>
+static cudaError_t launch_one(cudaStream_t st, int grid, const ssrlcv_b200_set_impl& q, const ssrlcv_b200_set_impl& t,
+                              const SmaxArgs& a, const MaskParams& mp) {
+  auto kern = smax_kernel<kMask, kFold>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<grid, 256, kSmemBytes, st>>>(q.map_a, t.map_b, t.map_ext, a, mp);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_smax(cudaStream_t st, int grid, const ssrlcv_b200_set_impl& q, const ssrlcv_b200_set_impl& t,
+                        const SmaxArgs& a, const MaskParams& mp) {
+  const bool fold = t.fold_ok;
+  switch (mp.kind) {
+    case SSRLCV_B200_MASK_NONE:
+      return fold ? launch_one<SSRLCV_B200_MASK_NONE, true>(st, grid, q, t, a, mp) : launch_one<SSRLCV_B200_MASK_NONE, false>(st, grid, q, t, a, mp);
+    case SSRLCV_B200_MASK_FUNDAMENTAL:
+      return fold ? launch_one<SSRLCV_B200_MASK_FUNDAMENTAL, true>(st, grid, q, t, a, mp) : launch_one<SSRLCV_B200_MASK_FUNDAMENTAL, false>(st, grid, q, t, a, mp);
+    default:
+      return fold ? launch_one<SSRLCV_B200_MASK_DOUBLE, true>(st, grid, q, t, a, mp) : launch_one<SSRLCV_B200_MASK_DOUBLE, false>(st, grid, q, t, a, mp);
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,328 @@
+"""Host-side mirror of ssrlcv::MatchFactory<SIFT_Descriptor> over the C ABI.
+
+Same method names, argument meaning, post-conditions and error behaviour as the reference class
+(ref: include/MatchFactory.cuh:131-311, src/MatchFactory.cu:14-1028):
+  * inputs are borrowed Unity arrays; their MemoryState is forced to gpu for the call and restored on exit
+    (ref: src/MatchFactory.cu:350-353, :390-391)
+  * outputs are new Unity arrays in state gpu, sized to the number of valid matches, ascending query index
+  * argument errors raise MatchFactoryError where the reference logs and exit(-1)s
+    (seed size mismatch :370-373, threshold == 0 :138-141)
+All arithmetic happens in libssrlcv_match_b200.so (hand-written sm_100a CUDA); this module only marshals.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from . import types as T
+from .unity import MemoryState, Unity, both, cpu, gpu
+
+FLT_MAX = float(np.finfo(np.float32).max)
+ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
+
+
+class MatchFactoryError(RuntimeError):
+    """Raised where the reference prints to logger.err and calls exit(-1)."""
+
+
+@dataclass
+class Image:
+    """The fields of ssrlcv::Image the matching path reads (ref: include/Image.cuh:79-85)."""
+    id: int = -1
+    camera: np.ndarray = field(default_factory=lambda: np.zeros((), T.CAMERA))
+
+    @property
+    def size(self):
+        return tuple(int(x) for x in self.camera["size"])
+
+
+@dataclass
+class MatchSet:
+    keyPoints: Unity
+    matches: Unity
+
+
+class Context:
+    """One per (process, device): owns the library context bound to torch's current stream."""
+    _instances: dict = {}
+
+    def __init__(self, device: int = 0):
+        import torch
+
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.B200Error(-2, "no CUDA device: the matching path has no CPU fallback")
+        torch.cuda.set_device(device)
+        self.device = device
+        self.handle = C.c_void_p()
+        stream = torch.cuda.current_stream(device).cuda_stream
+        rc = self.lib.ssrlcv_b200_create(C.byref(self.handle), device, C.c_void_p(stream))
+        if rc != 0:
+            raise _lib.B200Error(rc, "ssrlcv_b200_create failed (needs an sm_100 GPU)")
+
+    @classmethod
+    def get(cls, device: int = 0) -> "Context":
+        if device not in cls._instances:
+            cls._instances[device] = cls(device)
+        return cls._instances[device]
+
+    def check(self, rc: int) -> None:
+        _lib.check(self.handle, rc)
+
+    def launch_count(self) -> int:
+        return int(self.lib.ssrlcv_b200_launch_count(self.handle))
+
+
+class PackedSet:
+    def __init__(self, ctx: Context, handle: C.c_void_p, n: int):
+        self.ctx, self.handle, self.n = ctx, handle, n
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.ctx.lib.ssrlcv_b200_set_free(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def pack(ctx: Context, features: Unity) -> PackedSet:
+    """Repack (and cache on the Unity) the device copy of a Feature<SIFT_Descriptor> array."""
+    if features._packed is not None and features._packed.ctx is ctx:
+        return features._packed
+    h = C.c_void_p()
+    ctx.check(ctx.lib.ssrlcv_b200_pack(ctx.handle, C.c_void_p(features.device_ptr() if features.size() else 0),
+                                       features.size(), C.byref(h)))
+    features._packed = PackedSet(ctx, h, features.size())
+    return features._packed
+
+
+class MatchFactory:
+    def __init__(self, relativeThreshold: float = 1.0, absoluteThreshold: float = FLT_MAX, device: int = 0,
+                 engine: int = ENGINE_TCGEN05):
+        self.relativeThreshold = float(np.float32(relativeThreshold))
+        self.absoluteThreshold = float(np.float32(absoluteThreshold))
+        self.seedFeatures: Unity | None = None
+        self.device = device
+        self.engine = engine
+        self.ctx = Context.get(device)
+
+    # ------------------------------------------------------------------ helpers
+    def setSeedFeatures(self, seedFeatures: Unity) -> None:
+        self.seedFeatures = seedFeatures
+
+    def _torch(self):
+        import torch
+
+        return torch
+
+    def _params(self, out_kind, mask_kind, query: Image, target: Image, epsilon=0.0, delta=0.0, fundamental=None,
+                compact=1) -> _lib.MatchParams:
+        p = _lib.MatchParams()
+        p.out_kind, p.mask_kind = out_kind, mask_kind
+        p.absolute_threshold, p.relative_threshold = self.absoluteThreshold, self.relativeThreshold
+        p.query_image_id, p.target_image_id = query.id & 0xFFFFFFFF, target.id & 0xFFFFFFFF
+        p.epsilon, p.delta = float(np.float32(epsilon)), float(np.float32(delta))
+        if fundamental is not None:
+            p.fundamental = (C.c_float * 9)(*np.asarray(fundamental, np.float32).reshape(9))
+        p.query_camera = (C.c_uint8 * 80).from_buffer_copy(np.asarray(query.camera, T.CAMERA).tobytes())
+        p.target_camera = (C.c_uint8 * 80).from_buffer_copy(np.asarray(target.camera, T.CAMERA).tobytes())
+        p.compact, p.engine = compact, self.engine
+        return p
+
+    def _run(self, p: _lib.MatchParams, queryFeatures: Unity, targetFeatures: Unity, seedDistances: Unity | None) -> Unity:
+        torch = self._torch()
+        origin = (queryFeatures.getMemoryState(), targetFeatures.getMemoryState())
+        if origin[0] != gpu:
+            queryFeatures.setMemoryState(gpu)
+        if origin[1] != gpu:
+            targetFeatures.setMemoryState(gpu)
+        try:
+            nq = queryFeatures.size()
+            seed_ptr, n_seed = None, 0
+            seed_origin = None
+            if seedDistances is not None:
+                if seedDistances.size() != nq:
+                    raise MatchFactoryError("ERROR: seedDistances should have come from matching a seed image to queryFeatures")
+                seed_origin = seedDistances.getMemoryState()
+                if seed_origin != gpu:
+                    seedDistances.setMemoryState(gpu)
+                seed_ptr, n_seed = C.c_void_p(seedDistances.device_ptr()), nq
+            q, t = pack(self.ctx, queryFeatures), pack(self.ctx, targetFeatures)
+            dt = T.OUT_DTYPES[p.out_kind]
+            out = torch.empty(max(nq, 1) * dt.itemsize, dtype=torch.uint8, device=f"cuda:{self.device}")
+            n_out = C.c_uint64(0)
+            self.ctx.check(self.ctx.lib.ssrlcv_b200_match(self.ctx.handle, C.byref(p), q.handle, t.handle, seed_ptr, n_seed,
+                                                          C.c_void_p(out.data_ptr()), C.byref(n_out)))
+            if seedDistances is not None and seed_origin != gpu:
+                seedDistances.setMemoryState(seed_origin)
+            n = int(n_out.value)
+            if p.compact and n == 0 and nq > 0:
+                # reference quirk (src/MatchFactory.cu:40-45): validateMatches clears only its own copy of the
+                # smart pointer, so the caller keeps the uncompacted array of invalid entries
+                p2 = _lib.MatchParams.from_buffer_copy(bytes(p))
+                p2.compact = 0
+                self.ctx.check(self.ctx.lib.ssrlcv_b200_match(self.ctx.handle, C.byref(p2), q.handle, t.handle, seed_ptr, n_seed,
+                                                              C.c_void_p(out.data_ptr()), C.byref(n_out)))
+                n = int(n_out.value)
+            return Unity(out[: n * dt.itemsize].clone() if n != nq else out[: n * dt.itemsize], dt, gpu, self.device, n)
+        finally:
+            if origin[0] != gpu:
+                queryFeatures.setMemoryState(origin[0])
+            if origin[1] != gpu:
+                targetFeatures.setMemoryState(origin[1])
+
+    # ------------------------------------------------------------------ seed distances
+    def getSeedDistances(self, features: Unity) -> Unity:
+        """ref: src/MatchFactory.cu:315-346"""
+        torch = self._torch()
+        if self.seedFeatures is None:
+            raise MatchFactoryError("getSeedDistances called without seed features")
+        origin = features.getMemoryState()
+        if self.seedFeatures.getMemoryState() != gpu:
+            self.seedFeatures.setMemoryState(gpu)
+        if origin != gpu:
+            features.setMemoryState(gpu)
+        try:
+            q, s = pack(self.ctx, features), pack(self.ctx, self.seedFeatures)
+            out = torch.empty(max(features.size(), 1), dtype=torch.float32, device=f"cuda:{self.device}")
+            self.ctx.check(self.ctx.lib.ssrlcv_b200_seed_distances(self.ctx.handle, q.handle, s.handle,
+                                                                   C.c_void_p(out.data_ptr()), self.engine))
+            self.ctx.check(self.ctx.lib.ssrlcv_b200_synchronize(self.ctx.handle))
+            return Unity(out[: features.size()], np.dtype("<f4"), gpu, self.device, features.size())
+        finally:
+            if origin != gpu:
+                features.setMemoryState(origin)
+
+    # ------------------------------------------------------------------ Match
+    def generateMatches(self, query, queryFeatures, target, targetFeatures, seedDistances=None) -> Unity:
+        """ref: src/MatchFactory.cu:349-394"""
+        return self._run(self._params(T.OUT_MATCH, T.MASK_NONE, query, target), queryFeatures, targetFeatures, seedDistances)
+
+    def generateMatchesConstrained(self, query, queryFeatures, target, targetFeatures, epsilon, fundamental, seedDistances=None) -> Unity:
+        """ref: src/MatchFactory.cu:395-445"""
+        return self._run(self._params(T.OUT_MATCH, T.MASK_FUNDAMENTAL, query, target, epsilon, 0.0, fundamental),
+                         queryFeatures, targetFeatures, seedDistances)
+
+    def generateMatchesDoubleConstrained(self, query, queryFeatures, target, targetFeatures, epsilon, delta, seedDistances=None) -> Unity:
+        """ref: src/MatchFactory.cu:447-501"""
+        return self._run(self._params(T.OUT_MATCH, T.MASK_DOUBLE, query, target, epsilon, delta), queryFeatures, targetFeatures, seedDistances)
+
+    # ------------------------------------------------------------------ DMatch
+    def generateDistanceMatches(self, query, queryFeatures, target, targetFeatures, seedDistances=None) -> Unity:
+        """ref: src/MatchFactory.cu:504-547"""
+        return self._run(self._params(T.OUT_DMATCH, T.MASK_NONE, query, target), queryFeatures, targetFeatures, seedDistances)
+
+    def generateDistanceMatchesConstrained(self, query, queryFeatures, target, targetFeatures, epsilon, fundamental, seedDistances=None) -> Unity:
+        """ref: src/MatchFactory.cu:549-597"""
+        return self._run(self._params(T.OUT_DMATCH, T.MASK_FUNDAMENTAL, query, target, epsilon, 0.0, fundamental),
+                         queryFeatures, targetFeatures, seedDistances)
+
+    def generateDistanceMatchesDoubleConstrained(self, query, queryFeatures, target, targetFeatures, epsilon, delta, seedDistances=None) -> Unity:
+        """ref: src/MatchFactory.cu:600-651"""
+        return self._run(self._params(T.OUT_DMATCH, T.MASK_DOUBLE, query, target, epsilon, delta), queryFeatures, targetFeatures, seedDistances)
+
+    # ------------------------------------------------------------------ FeatureMatch
+    def generateFeatureMatches(self, query, queryFeatures, target, targetFeatures, seedDistances=None) -> Unity:
+        """ref: src/MatchFactory.cu:654-697 -- quirk kept: neither synchronises nor compacts, returns numQuery raw entries."""
+        return self._run(self._params(T.OUT_FEATUREMATCH, T.MASK_NONE, query, target, compact=0), queryFeatures, targetFeatures, seedDistances)
+
+    def generateFeatureMatchesConstrained(self, query, queryFeatures, target, targetFeatures, epsilon, fundamental, seedDistances=None) -> Unity:
+        """ref: src/MatchFactory.cu:699-750"""
+        return self._run(self._params(T.OUT_FEATUREMATCH, T.MASK_FUNDAMENTAL, query, target, epsilon, 0.0, fundamental),
+                         queryFeatures, targetFeatures, seedDistances)
+
+    # ------------------------------------------------------------------ uint2_pair
+    def generateMatchesIndexOnly(self, query, queryFeatures, target, targetFeatures, seedDistances=None) -> Unity:
+        """ref: src/MatchFactory.cu:755-800"""
+        return self._run(self._params(T.OUT_PAIR, T.MASK_NONE, query, target), queryFeatures, targetFeatures, seedDistances)
+
+    def generateMatchesConstrainedIndexOnly(self, query, queryFeatures, target, targetFeatures, epsilon, fundamental, seedDistances=None) -> Unity:
+        """ref: src/MatchFactory.cu:802-851"""
+        return self._run(self._params(T.OUT_PAIR, T.MASK_FUNDAMENTAL, query, target, epsilon, 0.0, fundamental),
+                         queryFeatures, targetFeatures, seedDistances)
+
+    def generateMatchesDoubleConstrainedIndexOnly(self, query, queryFeatures, target, targetFeatures, epsilon, delta, seedDistances=None) -> Unity:
+        """ref: src/MatchFactory.cu:853-905"""
+        return self._run(self._params(T.OUT_PAIR, T.MASK_DOUBLE, query, target, epsilon, delta), queryFeatures, targetFeatures, seedDistances)
+
+    # ------------------------------------------------------------------ post-processing
+    def _kind_of(self, matches: Unity) -> int:
+        for k, dt in T.OUT_DTYPES.items():
+            if dt == matches.dtype:
+                return k
+        raise MatchFactoryError("not a match array")
+
+    def _inplace(self, matches: Unity, call) -> None:
+        origin = matches.getMemoryState()
+        if origin != gpu:
+            matches.setMemoryState(gpu)
+        n_out = C.c_uint64(0)
+        self.ctx.check(call(C.c_void_p(matches.device_ptr() if matches.size() else 0), matches.size(), n_out))
+        n = int(n_out.value)
+        if n == 0:
+            # reference quirk: "matches.clear(); return;" on a by-value smart pointer leaves the caller's array untouched
+            if origin != gpu:
+                matches.setMemoryState(origin)
+            return
+        kept = matches.device[: n * matches.dtype.itemsize].clone()
+        matches.setData(kept, n, gpu)
+        if origin != gpu:
+            matches.setMemoryState(origin)
+
+    def validateMatches(self, matches: Unity) -> None:
+        """ref: src/MatchFactory.cu:31-135"""
+        kind = self._kind_of(matches)
+        self._inplace(matches, lambda p, n, out: self.ctx.lib.ssrlcv_b200_validate(self.ctx.handle, kind, p, n, C.byref(out)))
+
+    def refineMatches(self, matches: Unity, threshold: float) -> None:
+        """ref: src/MatchFactory.cu:137-160"""
+        if float(threshold) == 0.0:
+            raise MatchFactoryError("ERROR illegal value used for threshold: 0.0")
+        self._inplace(matches, lambda p, n, out: self.ctx.lib.ssrlcv_b200_refine(self.ctx.handle, p, n, float(np.float32(threshold)), C.byref(out)))
+
+    def sortMatches(self, matches: Unity) -> None:
+        """ref: src/MatchFactory.cu:191-222 (device branch; equal distances keep input order)"""
+        if matches.getFore() not in (cpu, gpu, both):
+            raise MatchFactoryError(f"ERROR cannot perform sortMatches with matches->getMemoryState() = {int(matches.getMemoryState())}")
+        state = matches.getMemoryState()
+        if matches.getFore() == cpu:
+            matches.transferMemoryTo(gpu) if state == both else matches.setMemoryState(gpu)
+        self.ctx.check(self.ctx.lib.ssrlcv_b200_sort(self.ctx.handle, C.c_void_p(matches.device_ptr() if matches.size() else 0), matches.size()))
+        matches.setFore(gpu)
+        if state == both:
+            matches.transferMemoryTo(cpu)
+        elif state == cpu:
+            matches.setMemoryState(cpu)
+
+    def getRawMatches(self, matches: Unity) -> Unity:
+        """ref: src/MatchFactory.cu:257-280"""
+        torch = self._torch()
+        origin = matches.getMemoryState()
+        if origin == cpu:
+            matches.setMemoryState(gpu)
+        n = matches.size()
+        out = torch.empty(max(n, 1) * T.MATCH.itemsize, dtype=torch.uint8, device=f"cuda:{self.device}")
+        self.ctx.check(self.ctx.lib.ssrlcv_b200_raw_matches(self.ctx.handle, C.c_void_p(matches.device_ptr() if n else 0), n,
+                                                            C.c_void_p(out.data_ptr())))
+        res = Unity(out[: n * T.MATCH.itemsize], T.MATCH, gpu, self.device, n)
+        if origin == cpu:
+            matches.setMemoryState(cpu)
+            res.setMemoryState(cpu)
+        return res
+
+    # ------------------------------------------------------------------ N-view
+    def generateMatchesExhaustive(self, images, features, epsilon, delta, ordered=True, estimatedOverlap=0.0,
+                                  geo_orbit: bool = True) -> MatchSet:
+        """ref: src/MatchFactory.cu:907-1028.  Pair loop on the GPU; the adjacency fusion follows in pair_fusion."""
+        from .pair_scheduler import exhaustive_pairs
+        from .fusion import fuse_pairs
+
+        pair_lists = exhaustive_pairs(self, images, features, epsilon, delta, ordered, estimatedOverlap, geo_orbit)
+        if sum(p.size() for p in pair_lists) == 0:
+            raise MatchFactoryError("There were no matches found in the set of images, likely due to unreasonable threshold")
+        mm, kp = fuse_pairs([f.to_numpy() for f in features], [p.to_numpy() for p in pair_lists])
+        return MatchSet(keyPoints=Unity(kp, T.KEYPOINT, cpu, self.device), matches=Unity(mm, T.MULTIMATCH, cpu, self.device))

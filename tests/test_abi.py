@@ -1,0 +1,118 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol the header declares,
+record layouts match the reference's, and the library refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from ssrlcv_b200 import _lib, checkpoint as ck, types as T
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "ssrlcv_b200.h")).read()
+    declared = set(re.findall(r"\b(ssrlcv_b200_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ssrlcv_b200_abi_version() == 1
+
+
+def test_params_struct_matches_header():
+    # 2 i32 + 2 f32 + 2 u32 + 2 f32 + 9 f32 + 80 + 80 + 2 i32
+    assert C.sizeof(_lib.MatchParams) == 8 * 4 + 36 + 160 + 8
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.ssrlcv_b200_create(C.byref(h), 0, None) == -2        # SSRLCV_B200_ENODEVICE
+    from ssrlcv_b200.match_factory import MatchFactory
+    with pytest.raises(Exception):
+        MatchFactory()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "ssrlcv_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no CPU fallback", ""), os.path.join(dirpath, f)
+
+
+def test_record_layouts():
+    assert T.FEATURE.itemsize == 152 and T.FEATURE.fields["values"][1] == 24
+    assert T.CAMERA.itemsize == 80 and T.CAMERA.fields["size"][1] == 72
+    assert (T.KEYPOINT.itemsize, T.MATCH.itemsize, T.DMATCH.itemsize, T.UINT2_PAIR.itemsize, T.MULTIMATCH.itemsize) == (16, 40, 48, 16, 8)
+    assert T.FEATUREMATCH.itemsize == 320 and T.FEATUREMATCH.fields["descriptors"][1] == 44
+    assert T.DMATCH.fields["distance"][1] == 40
+
+
+def test_uty_roundtrip_and_hash(tmp_path, everest):
+    # the hash is libstdc++'s typeid(T).hash_code(); checked against the value stored in the reference's own fixtures
+    assert ck.libstdcxx_hash_bytes(b"f") != 0
+    p = ck.write_uty(str(tmp_path), "keypoint", everest.g2_keypoints[:100], ck.STATE_CPU, id=7)
+    assert os.path.basename(p) == "7_N6ssrlcv8KeyPointE.uty"
+    back = ck.read_uty(p, "keypoint")
+    assert back.state == ck.STATE_CPU and T.fields_equal(back.data, everest.g2_keypoints[:100])
+    with pytest.raises(ValueError):
+        ck.read_uty(p, "feature")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/test/checkpoints"), reason="reference checkout not present")
+def test_hash_matches_reference_fixture_header():
+    d = "/root/reference/test/checkpoints/Pipeline2View/"
+    for kind in ("feature", "keypoint", "multimatch"):
+        name = ck.TYPE_NAMES[kind]
+        fn = [f for f in os.listdir(d) if f.endswith(name + ".uty")][0]
+        raw = open(d + fn, "rb").read(len(name) + 1 + 8)
+        stored = int.from_bytes(raw[len(name) + 1:], "little")
+        assert stored == ck.libstdcxx_hash_bytes(name.encode()), kind
+
+
+def test_cpimg_roundtrip(tmp_path, everest):
+    m = ck.ImageMeta(3, (1024, 1024), 1, everest.cameras[1])
+    ck.write_cpimg(str(tmp_path / "3.cpimg"), m)
+    b = ck.read_cpimg(str(tmp_path / "3.cpimg"))
+    assert b.id == 3 and b.size == (1024, 1024) and b.camera.tobytes() == everest.cameras[1].tobytes()
+
+
+def test_pair_order_and_assignment():
+    from ssrlcv_b200.pair_scheduler import assign_pairs, pair_order
+
+    assert pair_order(4) == [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
+    pairs = pair_order(16)
+    assert len(pairs) == 120
+    parts = assign_pairs(pairs, [32768] * 16, 8)
+    assert sorted(sum(parts, [])) == list(range(120)) and all(len(p) == 15 for p in parts)
+    parts = assign_pairs(pair_order(3), [10, 1000, 10], 2)
+    assert sorted(sum(parts, [])) == [0, 1, 2]
+
+
+def test_fusion_matches_oracle_on_synthetic():
+    from oracle import oracle as O
+    from ssrlcv_b200 import fusion
+    from tests import synth
+
+    feats = [synth.make_pair(300, 300, seed=s)[0] for s in range(4)]
+    rng = np.random.default_rng(0)
+    pairs = []
+    for q in range(3):
+        for t in range(q + 1, 4):
+            n = 120
+            qi = np.sort(rng.choice(300, n, replace=False))
+            p = np.zeros(n, T.UINT2_PAIR)
+            p["a"][:, 0], p["a"][:, 1], p["b"][:, 0], p["b"][:, 1] = q, qi, t, rng.integers(0, 300, n)
+            pairs.append(p)
+    mm, kp = fusion.fuse_pairs(feats, pairs)
+    mm2, kp2 = O.fuse_nview(feats, pairs)
+    assert T.fields_equal(mm, mm2) and T.fields_equal(kp, kp2)

@@ -1,0 +1,377 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same inputs,
+against the reference's committed golden fixtures, and -- when oracle/_ref was built -- against the
+reference's own CUDA kernels running on the same device.  Integer work is bit-exact; float fields are
+compared by bit pattern."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from ssrlcv_b200 import types as T
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+FLT_MAX = float(np.finfo(np.float32).max)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def api():
+    from oracle import oracle as O
+    from ssrlcv_b200.match_factory import Image, MatchFactory
+    from ssrlcv_b200.unity import Unity, both, cpu, gpu
+
+    class Api:
+        pass
+
+    a = Api()
+    a.O, a.Image, a.MatchFactory, a.Unity, a.cpu, a.gpu, a.both = O, Image, MatchFactory, Unity, cpu, gpu, both
+    return a
+
+
+def _unity(api, arr, state=None):
+    return api.Unity(arr, T.FEATURE, api.cpu if state is None else state)
+
+
+# ------------------------------------------------------------------------------------ unconstrained
+@pytest.mark.parametrize("nq,nt", [(1, 1), (5, 31), (128, 256), (129, 257), (1000, 4097), (4096, 4096)])
+@pytest.mark.parametrize("engine", [0, 1])
+def test_bruteforce_dmatch_matches_oracle(api, nq, nt, engine):
+    q, t = synth.make_pair(nq, nt, seed=nq + nt)
+    mf = api.MatchFactory(1.0, FLT_MAX, engine=engine)
+    got = mf.generateDistanceMatches(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t)).to_numpy()
+    want = api.O.generate_matches(api.O.make_params(out_kind=T.OUT_DMATCH), q, t)
+    assert T.fields_equal(got, want)
+
+
+@pytest.mark.parametrize("out_kind", [T.OUT_MATCH, T.OUT_DMATCH, T.OUT_PAIR])
+@pytest.mark.parametrize("seeded", [False, True])
+def test_output_kinds_and_ratio_rule(api, out_kind, seeded):
+    """rel vs rel^2 depends on the output type."""
+    q, t = synth.make_pair(3000, 3500, seed=11)
+    s = synth.make_seed(800)
+    mf = api.MatchFactory(0.75, 1.2e5)
+    mf.setSeedFeatures(_unity(api, s))
+    qu, tu = _unity(api, q), _unity(api, t)
+    sd = mf.getSeedDistances(qu) if seeded else None
+    sd_want = api.O.seed_distances(q, s) if seeded else None
+    if seeded:
+        assert np.array_equal(sd.to_numpy(), sd_want)
+    fn = {T.OUT_MATCH: mf.generateMatches, T.OUT_DMATCH: mf.generateDistanceMatches, T.OUT_PAIR: mf.generateMatchesIndexOnly}[out_kind]
+    got = fn(api.Image(4), qu, api.Image(9), tu, sd).to_numpy()
+    p = api.O.make_params(out_kind=out_kind, has_seed=seeded, abs_threshold=1.2e5, rel_threshold=0.75, query_id=4, target_id=9)
+    want = api.O.generate_matches(p, q, t, sd_want)
+    assert len(want) > 100 and T.fields_equal(got, want)
+
+
+def test_feature_match_keeps_all_entries(api):
+    """generateFeatureMatches neither compacts nor drops invalid entries (ref: src/MatchFactory.cu:674-696)."""
+    q, t = synth.make_pair(700, 900, seed=5)
+    mf = api.MatchFactory(1.0, 3.0e4)
+    got = mf.generateFeatureMatches(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t)).to_numpy()
+    assert len(got) == 700
+    bd, bi, ok = api.O.match_winners(api.O.make_params(out_kind=T.OUT_FEATUREMATCH, abs_threshold=3.0e4), q, t)
+    assert np.array_equal(got["invalid"] == 0, ok.astype(bool)) and 0 < ok.sum() < 700
+    v = np.flatnonzero(ok)
+    assert np.array_equal(got["distance"][v], bd[v])
+    assert np.array_equal(got["descriptors"]["values"][v, 0], q["values"][v])
+    assert np.array_equal(got["descriptors"]["values"][v, 1], t["values"][bi[v]])
+    assert np.array_equal(got["keyPoints"]["loc"][v, 1], t["loc"][bi[v]])
+    # and the constrained form does compact
+    F = np.array([[0, 0, 0.001], [0, 0, -1.0], [-0.001, 1.0, 2.0]], np.float32)
+    got = mf.generateFeatureMatchesConstrained(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t), 60.0, F).to_numpy()
+    want = api.O.generate_matches(api.O.make_params(out_kind=T.OUT_FEATUREMATCH, mask_kind=T.MASK_FUNDAMENTAL, abs_threshold=3.0e4,
+                                                    epsilon=60.0, fundamental=F), q, t)
+    assert T.fields_equal(got, want)
+
+
+# ------------------------------------------------------------------------------------ ties / edge cases
+@pytest.mark.parametrize("engine", [0, 1])
+def test_tie_break_lane_then_index(api, engine):
+    """ref: src/MatchFactory.cu:1476-1492 -- winner among equal distances is min (f mod 32, f)."""
+    rng = np.random.default_rng(2)
+    qv = synth.sift_descriptors(rng, 64)
+    tv = synth.sift_descriptors(rng, 2048)
+    for k in range(64):                       # duplicates in the same window, in different windows, in different tiles
+        near = qv[k].copy(); near[k % 128] ^= 1
+        for f in (37 + 64 * (k % 3), 66 + 64 * (k % 3), 300 + k, 1500 + (k * 7) % 500):
+            tv[f] = near
+    q, t = T.make_features(qv), T.make_features(tv)
+    mf = api.MatchFactory(1.0, FLT_MAX, engine=engine)
+    got = mf.generateMatchesIndexOnly(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t)).to_numpy()
+    want = api.O.generate_matches(api.O.make_params(out_kind=T.OUT_PAIR), q, t)
+    assert T.fields_equal(got, want)
+    assert (want["b"][:, 1] != np.array([min(f for f in range(2048) if (tv[f] == tv[w]).all()) for w in want["b"][:, 1]])).any()
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+def test_degenerate_inputs(api, engine):
+    """all-equal descriptors (every score ties), all-zero, all-255 (norm range beyond the fold), empty target set."""
+    mf = api.MatchFactory(1.0, FLT_MAX, engine=engine)
+    for qv, tv in [
+        (np.full((40, 128), 7, np.uint8), np.full((700, 128), 7, np.uint8)),
+        (np.zeros((40, 128), np.uint8), np.zeros((300, 128), np.uint8)),
+        (np.concatenate([np.zeros((20, 128), np.uint8), np.full((20, 128), 255, np.uint8)]),
+         np.concatenate([np.full((300, 128), 255, np.uint8), np.zeros((300, 128), np.uint8), np.full((100, 128), 128, np.uint8)])),
+    ]:
+        q, t = T.make_features(qv), T.make_features(tv)
+        got = mf.generateDistanceMatches(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t)).to_numpy()
+        want = api.O.generate_matches(api.O.make_params(out_kind=T.OUT_DMATCH), q, t)
+        assert T.fields_equal(got, want)
+    q = T.make_features(np.ones((10, 128), np.uint8))
+    empty = np.zeros(0, T.FEATURE)
+    got = mf.generateDistanceMatches(api.Image(0), _unity(api, q), api.Image(1), _unity(api, empty))
+    # reference quirk: zero valid matches -> caller keeps the uncompacted, all-invalid array
+    assert got.size() == 10 and np.all(got.to_numpy()["invalid"] == 1)
+    mf.setSeedFeatures(_unity(api, empty))
+    assert np.all(mf.getSeedDistances(_unity(api, q)).to_numpy() == np.float32(FLT_MAX))
+
+
+def test_absolute_threshold_is_strict(api):
+    q, t = synth.make_pair(500, 800, seed=21)
+    bd, _, _ = api.O.match_winners(api.O.make_params(), q, t)
+    thr = float(np.sort(bd)[250])             # some winner sits exactly at the threshold
+    mf = api.MatchFactory(1.0, thr)
+    got = mf.generateDistanceMatches(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t)).to_numpy()
+    want = api.O.generate_matches(api.O.make_params(out_kind=T.OUT_DMATCH, abs_threshold=thr), q, t)
+    assert T.fields_equal(got, want) and got["distance"].max() < thr
+
+
+def test_memory_states_restored(api):
+    q, t = synth.make_pair(300, 400, seed=1)
+    qu, tu = _unity(api, q, api.both), _unity(api, t, api.cpu)
+    mf = api.MatchFactory()
+    m = mf.generateMatches(api.Image(0), qu, api.Image(1), tu)
+    assert qu.getMemoryState() == api.both and tu.getMemoryState() == api.cpu and m.getMemoryState() == api.gpu
+    from ssrlcv_b200.match_factory import MatchFactoryError
+    with pytest.raises(MatchFactoryError):
+        mf.generateMatches(api.Image(0), qu, api.Image(1), tu, api.Unity(np.zeros(5, np.float32), np.dtype("<f4"), api.cpu))
+
+
+# ------------------------------------------------------------------------------------ masks
+@pytest.mark.parametrize("engine", [0, 1])
+def test_double_constrained_matches_oracle(api, everest, engine):
+    q, t = synth.make_pair(4000, 6000, seed=31)
+    s = synth.make_seed(1000)
+    mf = api.MatchFactory(0.8, 1.0e5, engine=engine)
+    mf.setSeedFeatures(_unity(api, s))
+    qu, tu = _unity(api, q), _unity(api, t)
+    qi, ti = api.Image(0, everest.cameras[0]), api.Image(1, everest.cameras[1])
+    sd = mf.getSeedDistances(qu)
+    sd_want = api.O.seed_distances(q, s)
+    for out_kind, fn in ((T.OUT_DMATCH, mf.generateDistanceMatchesDoubleConstrained), (T.OUT_MATCH, mf.generateMatchesDoubleConstrained),
+                         (T.OUT_PAIR, mf.generateMatchesDoubleConstrainedIndexOnly)):
+        got = fn(qi, qu, ti, tu, 25.0, 5.0, sd).to_numpy()
+        p = api.O.make_params(out_kind=out_kind, mask_kind=T.MASK_DOUBLE, has_seed=True, abs_threshold=1.0e5, rel_threshold=0.8,
+                              query_id=0, target_id=1, epsilon=25, delta=5, query_camera=everest.cameras[0], target_camera=everest.cameras[1])
+        want = api.O.generate_matches(p, q, t, sd_want)
+        assert len(want) > 20 and T.fields_equal(got, want)
+    got = mf.generateDistanceMatchesDoubleConstrained(qi, qu, ti, tu, 25.0, 5.0).to_numpy()      # non-seed variant
+    p = api.O.make_params(out_kind=T.OUT_DMATCH, mask_kind=T.MASK_DOUBLE, abs_threshold=1.0e5, query_id=0, target_id=1, epsilon=25, delta=5,
+                          query_camera=everest.cameras[0], target_camera=everest.cameras[1])
+    assert T.fields_equal(got, api.O.generate_matches(p, q, t))
+
+
+def test_epipolar_endpoints_bitwise(api, everest):
+    """the DoubleConstrained prologue (device float geometry) equals the oracle's restatement bit for bit."""
+    from ssrlcv_b200.match_factory import Context, pack
+    rng = np.random.default_rng(0)
+    q = T.make_features(np.zeros((5000, 128), np.uint8), rng.uniform(0, 1024, (5000, 2)).astype(np.float32))
+    mf = api.MatchFactory()
+    qu = _unity(api, q, api.gpu) if False else _unity(api, q)
+    qu.setMemoryState(api.gpu)
+    import torch
+    out = torch.empty(5000 * 4, dtype=torch.float32, device="cuda")
+    p = mf._params(T.OUT_DMATCH, T.MASK_DOUBLE, api.Image(0, everest.cameras[0]), api.Image(1, everest.cameras[1]), 25.0, 5.0)
+    ctx = mf.ctx
+    ctx.check(ctx.lib.ssrlcv_b200_epipolar_endpoints(ctx.handle, C.byref(p), pack(ctx, qu).handle, C.c_void_p(out.data_ptr())))
+    got = out.cpu().numpy().reshape(-1, 4)
+    P = api.O.projection_matrix(everest.cameras[1])
+    for i in range(0, 5000, 7):
+        p1, p2 = api.O.epipolar_endpoints(everest.cameras[0], P, q["loc"][i], 5.0)
+        assert np.array_equal(got[i].view(np.uint32), np.concatenate([p1, p2]).view(np.uint32)), i
+
+
+def test_device_trig_equals_oracle_port(api):
+    import torch
+    mf = api.MatchFactory()
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(-7, 7, 100000), rng.uniform(-2000, 2000, 20000)]).astype(np.float32)
+    xd = torch.from_numpy(x).cuda(); s = torch.empty_like(xd); c = torch.empty_like(xd)
+    mf.ctx.check(mf.ctx.lib.ssrlcv_b200_device_sincos(mf.ctx.handle, C.c_void_p(xd.data_ptr()), len(x), C.c_void_p(s.data_ptr()), C.c_void_p(c.data_ptr())))
+    lib = api.O.lib()
+    sw = np.array([lib.orc_cuda_sinf(float(v)) for v in x], np.float32)
+    cw = np.array([lib.orc_cuda_cosf(float(v)) for v in x], np.float32)
+    assert np.array_equal(s.cpu().numpy().view(np.uint32), sw.view(np.uint32))
+    assert np.array_equal(c.cpu().numpy().view(np.uint32), cw.view(np.uint32))
+
+
+def test_fundamental_constrained_matches_oracle(api):
+    q, t = synth.make_pair(2500, 3000, seed=41)
+    F = np.array([[1e-6, 2e-6, 0.0015], [-3e-6, 1e-7, -1.0], [-0.0013, 1.0, 4.0]], np.float32)
+    mf = api.MatchFactory(1.0, 2.0e5)
+    for out_kind, fn in ((T.OUT_MATCH, mf.generateMatchesConstrained), (T.OUT_DMATCH, mf.generateDistanceMatchesConstrained),
+                         (T.OUT_PAIR, mf.generateMatchesConstrainedIndexOnly)):
+        got = fn(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t), 30.0, F).to_numpy()
+        want = api.O.generate_matches(api.O.make_params(out_kind=out_kind, mask_kind=T.MASK_FUNDAMENTAL, abs_threshold=2.0e5,
+                                                        epsilon=30.0, fundamental=F), q, t)
+        assert len(want) > 20 and T.fields_equal(got, want)
+
+
+# ------------------------------------------------------------------------------------ golden fixtures of the reference
+def test_two_view_golden(api, everest):
+    """ref: test/Pipeline.cu:183-216 through doFeatureMatching (src/Pipeline.cu:173-241)."""
+    ev = everest
+    mf = api.MatchFactory(ev.rel_threshold, ev.abs_threshold)
+    mf.setSeedFeatures(_unity(api, ev.seed2))
+    qu, tu = _unity(api, ev.views2[0], api.both), _unity(api, ev.views2[1], api.both)
+    sd = mf.getSeedDistances(qu)
+    m = mf.generateDistanceMatchesDoubleConstrained(api.Image(ev.img_ids[0], ev.cameras[0]), qu, api.Image(ev.img_ids[1], ev.cameras[1]), tu,
+                                                    ev.epsilon, ev.delta, sd)
+    assert m.size() == 13534
+    kp = mf.getRawMatches(m).to_numpy()["keyPoints"].reshape(-1).copy()
+    assert T.fields_equal(kp, ev.g2_keypoints)
+
+
+def test_three_view_golden(api, everest):
+    """ref: test/Pipeline.cu:218-255 -- generateMatchesExhaustive with GEO_ORBIT=1."""
+    ev = everest
+    mf = api.MatchFactory(ev.rel_threshold, ev.abs_threshold)
+    mf.setSeedFeatures(_unity(api, ev.seed3))
+    images = [api.Image(ev.img_ids[i], ev.cameras[i]) for i in range(3)]
+    feats = [_unity(api, v, api.both) for v in ev.views3]
+    ms = mf.generateMatchesExhaustive(images, feats, ev.epsilon, ev.delta)
+    assert T.fields_equal(ms.matches.to_numpy(), ev.g3_multimatch)
+    assert T.fields_equal(ms.keyPoints.to_numpy(), ev.g3_keypoints)
+
+
+# ------------------------------------------------------------------------------------ post-processing
+def test_refine_sort_raw_validate(api):
+    q, t = synth.make_pair(5000, 5000, seed=51)
+    mf = api.MatchFactory(1.0, FLT_MAX)
+    m = mf.generateDistanceMatches(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t))
+    base = m.to_numpy().copy()
+    mf.sortMatches(m)
+    assert T.fields_equal(m.to_numpy(), api.O.sort(base))
+    thr = float(np.median(base["distance"]))
+    mf.refineMatches(m, thr)
+    assert T.fields_equal(m.to_numpy(), api.O.refine(api.O.sort(base), thr))
+    assert T.fields_equal(mf.getRawMatches(m).to_numpy(), api.O.raw_matches(m.to_numpy()))
+    from ssrlcv_b200.match_factory import MatchFactoryError
+    with pytest.raises(MatchFactoryError):
+        mf.refineMatches(m, 0.0)
+    dirty = base.copy(); dirty["invalid"][::3] = 1
+    u = api.Unity(dirty, T.DMATCH, api.cpu)
+    mf.validateMatches(u)
+    assert T.fields_equal(u.to_numpy(), dirty[dirty["invalid"] == 0])
+
+
+# ------------------------------------------------------------------------------------ sharded targets (multi-GPU data path on one device)
+def test_sharded_targets_merge_equals_single_call(api):
+    import torch
+    from ssrlcv_b200.match_factory import pack
+    q, t = synth.make_pair(3000, 8192 + 512, seed=61)
+    mf = api.MatchFactory(1.0, 1.0e5)
+    qu = _unity(api, q); qu.setMemoryState(api.gpu)
+    want = mf.generateDistanceMatches(api.Image(0), qu, api.Image(1), _unity(api, t)).to_numpy()
+    ctx = mf.ctx
+    bounds = [0, 2048, 4096, 6400, len(t)]
+    keys = torch.empty((4, len(q)), dtype=torch.int64, device="cuda")
+    p = mf._params(T.OUT_DMATCH, T.MASK_NONE, api.Image(0), api.Image(1))
+    shards = []
+    for r in range(4):
+        su = _unity(api, t[bounds[r]:bounds[r + 1]]); su.setMemoryState(api.gpu); shards.append(su)
+        ctx.check(ctx.lib.ssrlcv_b200_match_candidates(ctx.handle, C.byref(p), pack(ctx, qu).handle, pack(ctx, su).handle, bounds[r],
+                                                       C.c_void_p(keys[r].data_ptr())))
+    tloc = torch.from_numpy(np.ascontiguousarray(t["loc"])).cuda()
+    out = torch.empty(len(q) * 48, dtype=torch.uint8, device="cuda")
+    n = C.c_uint64(0)
+    ctx.check(ctx.lib.ssrlcv_b200_finalize_candidates(ctx.handle, C.byref(p), pack(ctx, qu).handle, C.c_void_p(keys.data_ptr()), 4,
+                                                      C.c_void_p(tloc.data_ptr()), None, C.c_void_p(out.data_ptr()), C.byref(n)))
+    got = out[: n.value * 48].cpu().numpy().view(T.DMATCH)
+    assert T.fields_equal(got, want)
+
+
+# ------------------------------------------------------------------------------------ the reference's own CUDA kernels
+def _ref_lib():
+    path = os.path.join(ROOT, "oracle", "_ref", "libssrlcv_ref.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    cwd = os.getcwd()
+    os.makedirs("/tmp/ssrlcv_ref_run", exist_ok=True)
+    os.chdir("/tmp/ssrlcv_ref_run")          # the reference's global logger writes ./out/ssrlcv.log
+    lib = C.CDLL(path)
+    os.chdir(cwd)
+    lib.ref_match.restype = C.c_long
+    return lib
+
+
+def _ref_match(lib, out_kind, mask_kind, abs_thr, rel, q, t, seed, eps=0.0, delta=0.0, F=None, qcam=None, tcam=None, qid=0, tid=1):
+    out = np.zeros(len(q), T.OUT_DTYPES[out_kind])
+    ms = C.c_double(0)
+    cwd = os.getcwd(); os.chdir("/tmp/ssrlcv_ref_run")
+    try:
+        n = lib.ref_match(out_kind, mask_kind, C.c_float(abs_thr), C.c_float(rel), qid, tid,
+                          q.ctypes.data_as(C.c_void_p), C.c_ulong(len(q)), t.ctypes.data_as(C.c_void_p), C.c_ulong(len(t)),
+                          None if seed is None else seed.ctypes.data_as(C.POINTER(C.c_float)), 2, C.c_float(eps), C.c_float(delta),
+                          None if F is None else np.ascontiguousarray(F, np.float32).ctypes.data_as(C.POINTER(C.c_float)),
+                          None if qcam is None else np.asarray(qcam).tobytes(), None if tcam is None else np.asarray(tcam).tobytes(),
+                          out.ctypes.data_as(C.c_void_p), C.byref(ms))
+    finally:
+        os.chdir(cwd)
+    assert n >= 0
+    return out[:n]
+
+
+def test_against_reference_cuda_unconstrained(api):
+    lib = _ref_lib()
+    q, t = synth.make_pair(3000, 5000, seed=71)
+    s = synth.make_seed(700)
+    sd = api.O.seed_distances(q, s)
+    mf = api.MatchFactory(0.8, 1.5e5)
+    for out_kind, fn in ((T.OUT_MATCH, mf.generateMatches), (T.OUT_DMATCH, mf.generateDistanceMatches), (T.OUT_PAIR, mf.generateMatchesIndexOnly)):
+        for seed in (None, sd):
+            ref = _ref_match(lib, out_kind, 0, 1.5e5, 0.8, q, t, seed)
+            su = None if seed is None else api.Unity(seed, np.dtype("<f4"), api.cpu)
+            got = fn(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t), su).to_numpy()
+            assert len(ref) > 50 and T.fields_equal(got, ref), (out_kind, seed is not None)
+
+
+def test_against_reference_cuda_masked(api, everest):
+    lib = _ref_lib()
+    q, t = synth.make_pair(3000, 5000, seed=81)
+    sd = api.O.seed_distances(q, synth.make_seed(700))
+    su = api.Unity(sd, np.dtype("<f4"), api.cpu)
+    mf = api.MatchFactory(0.8, 1.5e5)
+    qi, ti = api.Image(0, everest.cameras[0]), api.Image(1, everest.cameras[1])
+    for out_kind, fn in ((T.OUT_MATCH, mf.generateMatchesDoubleConstrained), (T.OUT_DMATCH, mf.generateDistanceMatchesDoubleConstrained),
+                         (T.OUT_PAIR, mf.generateMatchesDoubleConstrainedIndexOnly)):
+        ref = _ref_match(lib, out_kind, 2, 1.5e5, 0.8, q, t, sd, eps=25.0, delta=5.0, qcam=everest.cameras[0], tcam=everest.cameras[1])
+        got = fn(qi, _unity(api, q), ti, _unity(api, t), 25.0, 5.0, su).to_numpy()
+        assert len(ref) > 10 and T.fields_equal(got, ref), out_kind
+    F = np.array([[1e-6, 2e-6, 0.0015], [-3e-6, 1e-7, -1.0], [-0.0013, 1.0, 4.0]], np.float32)
+    for out_kind, fn in ((T.OUT_MATCH, mf.generateMatchesConstrained), (T.OUT_DMATCH, mf.generateDistanceMatchesConstrained),
+                         (T.OUT_PAIR, mf.generateMatchesConstrainedIndexOnly)):
+        ref = _ref_match(lib, out_kind, 1, 1.5e5, 0.8, q, t, sd, eps=30.0, F=F)
+        got = fn(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t), 30.0, F, su).to_numpy()
+        assert len(ref) > 10 and T.fields_equal(got, ref), out_kind
+
+
+def test_reference_cuda_reproduces_golden(api, everest):
+    """sanity of the rebuilt reference on B200: it reproduces its own 2-view fixture."""
+    lib = _ref_lib()
+    ev = everest
+    sd = np.zeros(len(ev.views2[0]), np.float32)
+    cwd = os.getcwd(); os.chdir("/tmp/ssrlcv_ref_run")
+    try:
+        lib.ref_seed_distances(ev.views2[0].ctypes.data_as(C.c_void_p), C.c_ulong(len(sd)), ev.seed2.ctypes.data_as(C.c_void_p),
+                               C.c_ulong(len(ev.seed2)), 2, sd.ctypes.data_as(C.POINTER(C.c_float)), None)
+    finally:
+        os.chdir(cwd)
+    assert np.array_equal(sd, api.O.seed_distances(ev.views2[0], ev.seed2))
+    ref = _ref_match(lib, T.OUT_DMATCH, 2, ev.abs_threshold, ev.rel_threshold, ev.views2[0], ev.views2[1], sd, eps=ev.epsilon, delta=ev.delta,
+                     qcam=ev.cameras[0], tcam=ev.cameras[1], qid=ev.img_ids[0], tid=ev.img_ids[1])
+    assert len(ref) == 13534
+    assert T.fields_equal(ref["keyPoints"].reshape(-1).copy(), ev.g2_keypoints)
