@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SIFT matching hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3|C2|C1]
+  (N > 1: launched by torchrun, one rank per GPU; each rank matches its own image pair of the same
+   shape -- pair-sharded N-view matching, no data-path collective -- so scaling is "weak")
+
+A "step" is one pass of the hot path over one synthetic 2-view batch:
+  C3 (default): generateDistanceMatches on 65 536 x 65 536 SIFT-shaped uint8[128] descriptors, unconstrained
+  C2          : getSeedDistances (8 192 seed) + generateDistanceMatchesDoubleConstrained on 16 384 x 16 384 (GEO_ORBIT=1)
+  C1          : getSeedDistances (1 024 seed) + generateMatches on 4 096 x 4 096
+`value`  = distance evaluations / s, whole job, with the Feature<SIFT_Descriptor> arrays already resident in HBM
+           (the step still repacks them: the reference API hands over 152-byte AoS records).
+`e2e`    = same metric through ssrlcv_b200_match_host: HOST buffers in, H2D + pack + match + D2H inside the timed region.
+`roofline` = the tensor-core matcher kernel alone (CUDA events on its stream): 256 int8 ops per distance evaluation.
+`cpu_baseline` = the CPU oracle (OpenMP port of the same arithmetic) on a bounded sample of the same workload.
+--impl reference times the reference's own CUDA MatchFactory kernels (oracle/_ref, rebuilt for sm_100a) on the same
+inputs through the reference's public API; if that library is absent, the CPU oracle port on a bounded sample.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "C1": dict(nq=4096, nt=4096, ns=1024, mask=0, desc="2-view 4096x4096 + 1024 seed, unconstrained generateMatches"),
+    "C2": dict(nq=16384, nt=16384, ns=8192, mask=2, desc="2-view 16384x16384 + 8192 seed, seed ratio test + DoubleConstrained (GEO_ORBIT=1)"),
+    "C3": dict(nq=65536, nt=65536, ns=0, mask=0, desc="2-view 65536x65536 unconstrained generateDistanceMatches (tensor-pipe roofline case)"),
+}
+ABS_THR, REL_THR = 200.0 * 200.0, 0.6          # the reference's MatchFactory(0.6f, 200*200), src/Pipeline.cu:175
+EPS, DELTA = 25.0, 5.0                         # test/Pipeline.cu:198
+
+
+def synth_inputs(w, rank):
+    from tests import synth
+    q, t = synth.make_pair(w["nq"], w["nt"], seed=0x55524C43 + 17 * rank)
+    s = synth.make_seed(w["ns"], seed=99 + rank) if w["ns"] else None
+    return q, t, s
+
+
+def cameras():
+    from tests.golden_data import load_everest
+    ev = load_everest()
+    return ev.cameras[0], ev.cameras[1]
+
+
+def evals_per_step(w):
+    return w["nq"] * w["nt"] + w["nq"] * w["ns"]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if x > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 1590.0, 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(w, q, t, s, seconds=15.0):
+    """CPU oracle on a bounded query sample of the same workload."""
+    from oracle import oracle as O
+    from ssrlcv_b200 import types as T
+    cam0, cam1 = cameras()
+    n = 256
+    def run(nq_s):
+        t0 = time.perf_counter()
+        sd = O.seed_distances(q[:nq_s], s) if s is not None else None
+        p = O.make_params(out_kind=T.OUT_DMATCH, mask_kind=w["mask"], has_seed=s is not None, abs_threshold=ABS_THR, rel_threshold=REL_THR,
+                          epsilon=EPS, delta=DELTA, query_camera=cam0, target_camera=cam1)
+        O.generate_matches(p, q[:nq_s], t, sd)
+        return time.perf_counter() - t0
+    dt = run(n)
+    n2 = int(min(len(q), max(n, n * seconds / max(dt, 1e-6))))
+    n2 = max(256, (n2 // 256) * 256)
+    dt = run(n2)
+    ev = n2 * (len(t) + (len(s) if s is not None else 0))
+    return {"value": ev / dt, "unit": "dist-evals/s", "cores": O.num_threads(), "kind": "port",
+            "sample": f"{n2} of {len(q)} queries against all {len(t)} targets" + (f" + {len(s)} seed" if s is not None else "") + f", {dt:.1f} s of CPU work"}
+
+
+def run_reference(args, w, rank, world):
+    """--impl reference: the reference's own CUDA kernels (oracle/_ref) through its public API."""
+    if rank != 0:
+        return None
+    from ssrlcv_b200 import types as T
+    q, t, s = synth_inputs(w, 0)
+    cam0, cam1 = cameras()
+    path = os.path.join(ROOT, "oracle", "_ref", "libssrlcv_ref.so")
+    line = {"impl": "reference", "metric": "sift_dist_evals_per_s", "unit": "dist-evals/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {w['desc']}", "nq": w["nq"], "nt": w["nt"], "ns": w["ns"]}}
+    import torch
+    if os.path.exists(path) and torch.cuda.is_available():
+        run_dir = "/tmp/ssrlcv_ref_run"; os.makedirs(run_dir, exist_ok=True); os.chdir(run_dir)
+        ref = C.CDLL(path); ref.ref_match.restype = C.c_long
+        out = np.zeros(len(q), T.DMATCH)
+        sd = np.zeros(len(q), np.float32)
+        times = []
+        for it in range(args.warmup + args.steps):
+            ms_seed, ms = C.c_double(0), C.c_double(0)
+            if s is not None:
+                ref.ref_seed_distances(q.ctypes.data_as(C.c_void_p), C.c_ulong(len(q)), s.ctypes.data_as(C.c_void_p), C.c_ulong(len(s)), 2,
+                                       sd.ctypes.data_as(C.POINTER(C.c_float)), C.byref(ms_seed))
+            n = ref.ref_match(1, w["mask"], C.c_float(ABS_THR), C.c_float(REL_THR), 0, 1, q.ctypes.data_as(C.c_void_p), C.c_ulong(len(q)),
+                              t.ctypes.data_as(C.c_void_p), C.c_ulong(len(t)), sd.ctypes.data_as(C.POINTER(C.c_float)) if s is not None else None, 2,
+                              C.c_float(EPS), C.c_float(DELTA), None, np.asarray(cam0).tobytes(), np.asarray(cam1).tobytes(),
+                              out.ctypes.data_as(C.c_void_p), C.byref(ms))
+            if it >= args.warmup:
+                times.append(ms.value + ms_seed.value)
+        os.chdir(ROOT)
+        ms_step = sum(times) / len(times)
+        v = evals_per_step(w) / (ms_step * 1e-3)
+        line.update({"value": v, "ms_per_step": ms_step, "matches_per_step": int(n),
+                     "cpu_baseline": {"value": v, "unit": "dist-evals/s", "cores": 0, "kind": "reference",
+                                      "sample": "full workload; the reference has no CPU path -- this is its own CUDA MatchFactory rebuilt for sm_100a, "
+                                                "run on the GPU with device-resident inputs (API wall time incl. its cudaMalloc/compaction)"},
+                     "e2e": {"value": v, "unit": "dist-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    else:
+        cb = cpu_baseline(w, q, t, s, seconds=20.0)
+        line.update({"value": cb["value"], "ms_per_step": None, "cpu_baseline": cb,
+                     "e2e": {"value": cb["value"], "unit": "dist-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    return line
+
+
+def run_ours(args, w, rank, world, local_rank):
+    import torch
+    from ssrlcv_b200 import _lib, types as T
+    from ssrlcv_b200.match_factory import Context
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    ctx = Context.get(local_rank)
+    lib, h = ctx.lib, ctx.handle
+    q, t, s = synth_inputs(w, rank)
+    cam0, cam1 = cameras()
+    dev = f"cuda:{local_rank}"
+    to_dev = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev)
+    qd, td = to_dev(q), to_dev(t)
+    sd_feat = to_dev(s) if s is not None else None
+    out = torch.empty(len(q) * 48, dtype=torch.uint8, device=dev)
+    seed_dist = torch.empty(len(q), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    p = _lib.MatchParams()
+    p.out_kind, p.mask_kind = T.OUT_DMATCH, w["mask"]
+    p.absolute_threshold, p.relative_threshold = ABS_THR, REL_THR
+    p.query_image_id, p.target_image_id, p.epsilon, p.delta = 0, 1, EPS, DELTA
+    p.query_camera = (C.c_uint8 * 80).from_buffer_copy(np.asarray(cam0).tobytes())
+    p.target_camera = (C.c_uint8 * 80).from_buffer_copy(np.asarray(cam1).tobytes())
+    p.compact, p.engine = 1, 0
+    n_out = C.c_uint64(0)
+
+    def step():
+        """pack both sets (+ seed), seed distances, match; inputs are device-resident AoS arrays."""
+        hq, ht, hs = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        ctx.check(lib.ssrlcv_b200_pack(h, C.c_void_p(qd.data_ptr()), len(q), C.byref(hq)))
+        ctx.check(lib.ssrlcv_b200_pack(h, C.c_void_p(td.data_ptr()), len(t), C.byref(ht)))
+        seed_ptr, n_seed = None, 0
+        if s is not None:
+            ctx.check(lib.ssrlcv_b200_pack(h, C.c_void_p(sd_feat.data_ptr()), len(s), C.byref(hs)))
+            ctx.check(lib.ssrlcv_b200_seed_distances(h, hq, hs, C.c_void_p(seed_dist.data_ptr()), 0))
+            seed_ptr, n_seed = C.c_void_p(seed_dist.data_ptr()), len(q)
+        ctx.check(lib.ssrlcv_b200_match(h, C.byref(p), hq, ht, seed_ptr, n_seed, C.c_void_p(out.data_ptr()), C.byref(n_out)))
+        for x in (hq, ht, hs):
+            if x:
+                lib.ssrlcv_b200_set_free(x)
+        return int(n_out.value)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing ----------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    lib.ssrlcv_b200_set_profiling(h, 1)
+    sampler = ClockSampler(local_rank)
+    launches0 = ctx.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    n_matches = 0
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)                       # evict L2 between timed iterations (not timed)
+        ev[i][0].record()
+        n_matches = step()
+        ev[i][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
+    k_ms, k_n = C.c_double(0), C.c_uint64(0)
+    lib.ssrlcv_b200_kernel_time(h, C.byref(k_ms), C.byref(k_n))
+    lib.ssrlcv_b200_set_profiling(h, 0)
+
+    # ---------------- end-to-end through the C ABI with host buffers ----------------
+    pin = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1)).pin_memory()
+    qh, th = pin(q), pin(t)
+    sh = pin(s) if s is not None else None
+    out_h = torch.empty(len(q) * 48, dtype=torch.uint8).pin_memory()
+
+    def step_e2e():
+        ctx.check(lib.ssrlcv_b200_match_host(h, C.byref(p), C.c_void_p(qh.data_ptr()), len(q), C.c_void_p(th.data_ptr()), len(t),
+                                             C.c_void_p(sh.data_ptr()) if sh is not None else None, len(s) if s is not None else 0,
+                                             C.c_void_p(out_h.data_ptr()), C.byref(n_out)))
+        return int(n_out.value)
+
+    for _ in range(2):
+        step_e2e()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        ev2[i][0].record()
+        n_e2e = step_e2e()
+        ev2[i][1].record()
+    barrier()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+
+    # ---------------- max over ranks ----------------
+    tt = torch.tensor([total_ms, e2e_ms, wall * 1e3], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, wall_ms = (float(x) for x in tt.cpu())
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return None
+
+    evals = evals_per_step(w)
+    value = world * evals * args.steps / (total_ms * 1e-3)
+    bf16_burst, bf16_sust, hbm, src = measured_peaks()
+    peak_tops = 2.0 * bf16_burst                     # dense int8 tensor rate = 2 x dense bf16
+    kern_ms = k_ms.value / max(k_n.value, 1)
+    # per launch of the matcher kernel: the main (query x target) contraction dominates; seed launches are averaged in
+    ops_per_launch = 256.0 * evals / max(k_n.value / args.steps, 1)
+    achieved = ops_per_launch / (kern_ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(args.workload)
+    line = {
+        "metric": "sift_dist_evals_per_s", "value": value, "unit": "dist-evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w['desc']}", "nq": w["nq"], "nt": w["nt"], "ns": w["ns"], "parallelism": f"pair-sharded x{world}",
+                   "l2": "256 MiB flush between timed iterations", "step": "pack(AoS->SoA) + [seed distances] + match + compaction, device-resident inputs"},
+        "matches_per_s": world * n_matches * args.steps / (total_ms * 1e-3), "queries_per_s": world * w["nq"] * args.steps / (total_ms * 1e-3),
+        "matches_per_step": n_matches, "wall_ms_per_step": wall_ms / args.steps,
+        "int8_tops": 256.0 * value / 1e12, "frac_of_int8_peak_step": 256.0 * value / 1e12 / (world * peak_tops),
+        "clocks": clocks,
+        "e2e": {"value": world * evals * args.steps / (e2e_ms * 1e-3), "unit": "dist-evals/s", "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": (len(q) + len(t) + (len(s) if s is not None else 0)) * 152, "d2h_bytes_per_step": n_e2e * 48 + 8,
+                "api": "ssrlcv_b200_match_host (pinned host buffers in, records out)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tops, "unit": "TFLOP/s", "frac": achieved / peak_tops, "traffic": traffic,
+                     "kernel": "smax_kernel (tcgen05.mma kind::i8 + fused argmax epilogue)", "kernel_ms": kern_ms, "launches_timed": int(k_n.value),
+                     "ops": "int8 dense: 256 ops per distance evaluation (128 u8 x u8 MACs); the fold's extra K block is not counted",
+                     "peak_source": f"2 x bf16_tflops burst, {src}; nominal dense int8 is 4500"},
+    }
+    try:
+        line["cpu_baseline"] = cpu_baseline(w, q, t, s)
+    except Exception as e:  # noqa: BLE001
+        line["cpu_baseline"] = {"value": None, "unit": "dist-evals/s", "cores": 0, "kind": "port", "sample": f"failed: {e!r}"}
+    if dist is not None:
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        line = run_reference(args, w, rank, world)
+    else:
+        line = run_ours(args, w, rank, world, local_rank)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -95,6 +95,11 @@ const char* ssrlcv_b200_last_error(const ssrlcv_b200_ctx* ctx);
 int  ssrlcv_b200_synchronize(ssrlcv_b200_ctx* ctx);
 /* number of kernels this library has launched on the context so far (bench bookkeeping) */
 uint64_t ssrlcv_b200_launch_count(const ssrlcv_b200_ctx* ctx);
+/* bench instrumentation: when enabled, CUDA events bracket every launch of the tensor-core matcher kernel on the
+ * context's stream; kernel_time() synchronises and returns the accumulated device time (ms) and launch count
+ * since the last call, then resets both. */
+int  ssrlcv_b200_set_profiling(ssrlcv_b200_ctx* ctx, int enabled);
+int  ssrlcv_b200_kernel_time(ssrlcv_b200_ctx* ctx, double* total_ms, uint64_t* n_launches);
 
 /* ---- feature sets -------------------------------------------------------------------------
  * replaces: Unity<Feature<SIFT_Descriptor>>::device as consumed by the matching kernels.  The

@@ -17,7 +17,7 @@ ERRORS = {-1: "EINVAL", -2: "ENODEVICE", -3: "ESEEDSIZE", -4: "ETHRESHOLD", -5: 
 # every symbol include/ssrlcv_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "ssrlcv_b200_abi_version", "ssrlcv_b200_create", "ssrlcv_b200_destroy", "ssrlcv_b200_last_error",
-    "ssrlcv_b200_synchronize", "ssrlcv_b200_launch_count", "ssrlcv_b200_pack", "ssrlcv_b200_pack_host",
+    "ssrlcv_b200_synchronize", "ssrlcv_b200_launch_count", "ssrlcv_b200_set_profiling", "ssrlcv_b200_kernel_time", "ssrlcv_b200_pack", "ssrlcv_b200_pack_host",
     "ssrlcv_b200_set_size", "ssrlcv_b200_set_free", "ssrlcv_b200_seed_distances", "ssrlcv_b200_match",
     "ssrlcv_b200_match_host", "ssrlcv_b200_match_candidates", "ssrlcv_b200_finalize_candidates",
     "ssrlcv_b200_set_loc", "ssrlcv_b200_validate", "ssrlcv_b200_refine", "ssrlcv_b200_sort",
@@ -68,6 +68,8 @@ def load() -> C.CDLL:
     lib.ssrlcv_b200_synchronize.argtypes = [vp]
     lib.ssrlcv_b200_launch_count.argtypes = [vp]
     lib.ssrlcv_b200_launch_count.restype = u64
+    lib.ssrlcv_b200_set_profiling.argtypes = [vp, i32]
+    lib.ssrlcv_b200_kernel_time.argtypes = [vp, C.POINTER(C.c_double), pu64]
     lib.ssrlcv_b200_pack.argtypes = [vp, vp, u64, C.POINTER(vp)]
     lib.ssrlcv_b200_pack_host.argtypes = [vp, vp, u64, C.POINTER(vp)]
     lib.ssrlcv_b200_set_size.argtypes = [vp]

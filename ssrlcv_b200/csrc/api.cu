@@ -9,6 +9,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "matcher.cuh"
@@ -72,6 +73,9 @@ struct ssrlcv_b200_ctx {
   Workspace keys, flagged, counts, scratch, hostpin;
   uint32_t* d_scalars = nullptr;   // [0] n_flagged, [1] total, [2..3] hmin/hmax staging
   uint32_t* h_scalars = nullptr;   // pinned mirror
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
 };
 
 static int fail(ssrlcv_b200_ctx* c, int code, const char* fmt, ...) {
@@ -139,6 +143,7 @@ void ssrlcv_b200_destroy(ssrlcv_b200_ctx* ctx) {
   if (ctx->hostpin.p) cudaFreeHost(ctx->hostpin.p);
   if (ctx->d_scalars) cudaFree(ctx->d_scalars);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+  for (auto& pe : ctx->prof_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -150,6 +155,26 @@ int ssrlcv_b200_synchronize(ssrlcv_b200_ctx* ctx) {
   return 0;
 }
 uint64_t ssrlcv_b200_launch_count(const ssrlcv_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ssrlcv_b200_set_profiling(ssrlcv_b200_ctx* ctx, int enabled) {
+  if (!ctx) return SSRLCV_B200_EINVAL;
+  ctx->profiling = enabled != 0;
+  return 0;
+}
+int ssrlcv_b200_kernel_time(ssrlcv_b200_ctx* ctx, double* total_ms, uint64_t* n_launches) {
+  if (!ctx || !total_ms || !n_launches) return SSRLCV_B200_EINVAL;
+  CU(cudaStreamSynchronize(ctx->stream));
+  double t = 0.0;
+  for (size_t i = 0; i < ctx->prof_used; ++i) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ctx->prof_events[i].first, ctx->prof_events[i].second));
+    t += ms;
+  }
+  *total_ms = t;
+  *n_launches = ctx->prof_used;
+  ctx->prof_used = 0;
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------- sets
 static int encode_map(ssrlcv_b200_ctx* ctx, CUtensorMap* m, void* base, uint64_t rows, uint32_t row_bytes, uint32_t box_rows,
@@ -337,8 +362,17 @@ static int run_engine(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* q, const ssrl
     ctx->launches += 1;
   } else {
     CU(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(uint32_t), ctx->stream));
+    if (ctx->profiling) {
+      if (ctx->prof_used == ctx->prof_events.size()) {
+        cudaEvent_t e0, e1;
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        ctx->prof_events.emplace_back(e0, e1);
+      }
+      CU(cudaEventRecord(ctx->prof_events[ctx->prof_used].first, ctx->stream));
+    }
     cudaError_t e = launch_smax(ctx->stream, grid, *q, *t, a, mp);
     if (e != cudaSuccess) return fail(ctx, static_cast<int>(e), "smax launch: %s", cudaGetErrorString(e));
+    if (ctx->profiling) { CU(cudaEventRecord(ctx->prof_events[ctx->prof_used].second, ctx->stream)); ctx->prof_used++; }
     launch_exact(ctx->stream, a, mp, 1, ctx->sm_count);
     ctx->launches += 2;
   }
