@@ -127,6 +127,13 @@ int ssrlcv_b200_create(ssrlcv_b200_ctx** out, int device, void* stream) {
     return SSRLCV_B200_ENODEVICE;
   }
   ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  {  // packed sets come from the stream-ordered pool; keep freed blocks cached instead of returning them to the OS
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   if (cudaMalloc(&ctx->d_scalars, 16 * sizeof(uint32_t)) != cudaSuccess || cudaMallocHost(&ctx->h_scalars, 16 * sizeof(uint32_t)) != cudaSuccess) {
     delete ctx;
     return SSRLCV_B200_ENOMEM;
@@ -203,8 +210,8 @@ int ssrlcv_b200_pack(ssrlcv_b200_ctx* ctx, const void* features_dev, uint64_t n,
   const size_t np = s->n_pad;
   const size_t bytes = np * (kDescBytes + kExtBytes + 4 + 4 + 8 + 8);
   uint8_t* base = nullptr;
-  cudaError_t e = cudaMalloc(&base, bytes);
-  if (e != cudaSuccess) { delete s; return fail(ctx, static_cast<int>(e), "pack: cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+  cudaError_t e = cudaMallocAsync(&base, bytes, ctx->stream);
+  if (e != cudaSuccess) { delete s; return fail(ctx, static_cast<int>(e), "pack: cudaMallocAsync(%zu): %s", bytes, cudaGetErrorString(e)); }
   s->desc = base;
   s->ext = s->desc + np * kDescBytes;
   s->norm = reinterpret_cast<int32_t*>(s->ext + np * kExtBytes);
@@ -220,7 +227,7 @@ int ssrlcv_b200_pack(ssrlcv_b200_ctx* ctx, const void* features_dev, uint64_t n,
   cudaMemcpyAsync(ctx->h_scalars + 2, hmm, 8, cudaMemcpyDeviceToHost, ctx->stream);
   e = cudaStreamSynchronize(ctx->stream);
   if (e == cudaSuccess) e = cudaGetLastError();
-  if (e != cudaSuccess) { cudaFree(base); delete s; return fail(ctx, static_cast<int>(e), "pack: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { cudaFreeAsync(base, ctx->stream); delete s; return fail(ctx, static_cast<int>(e), "pack: %s", cudaGetErrorString(e)); }
   s->hmin = static_cast<int32_t>(ctx->h_scalars[2]);
   s->hmax = static_cast<int32_t>(ctx->h_scalars[3]);
   s->fold_ok = (n == 0) || (static_cast<int64_t>(s->hmax) - s->hmin + 2 <= kFoldMaxW);
@@ -228,7 +235,7 @@ int ssrlcv_b200_pack(ssrlcv_b200_ctx* ctx, const void* features_dev, uint64_t n,
   int rc = encode_map(ctx, &s->map_a, s->desc, np, kDescBytes, kBM, CU_TENSOR_MAP_SWIZZLE_128B);
   if (!rc) rc = encode_map(ctx, &s->map_b, s->desc, np, kDescBytes, kBN, CU_TENSOR_MAP_SWIZZLE_128B);
   if (!rc) rc = encode_map(ctx, &s->map_ext, s->ext, np, kExtBytes, kBN, CU_TENSOR_MAP_SWIZZLE_32B);
-  if (rc) { cudaFree(base); delete s; return rc; }
+  if (rc) { cudaFreeAsync(base, ctx->stream); delete s; return rc; }
   *out = s;
   return 0;
 }
@@ -248,8 +255,7 @@ const float* ssrlcv_b200_set_loc(const ssrlcv_b200_set* s) { return s ? reinterp
 void ssrlcv_b200_set_free(ssrlcv_b200_set* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
-  cudaStreamSynchronize(s->ctx->stream);
-  cudaFree(s->desc);
+  cudaFreeAsync(s->desc, s->ctx->stream);   // stream-ordered: every kernel that reads the set was enqueued before this
   delete s;
 }
 
@@ -317,6 +323,7 @@ static void plan(const ssrlcv_b200_ctx* ctx, uint32_t nq, uint32_t nt, SmaxArgs&
   a.n_qtiles = (nq + kBM - 1) / kBM;
   a.n_ttiles = (nt + kBN - 1) / kBN;
   const uint32_t sms = static_cast<uint32_t>(ctx->sm_count);
+  if (a.n_ttiles == 0 || a.n_qtiles == 0) { a.tiles_per_split = 1; a.n_splits = 1; grid = 1; return; }
   uint32_t best_s = 1;
   double best_eff = 0.0;
   const uint32_t max_s = a.n_ttiles < 64 ? (a.n_ttiles ? a.n_ttiles : 1) : 64;

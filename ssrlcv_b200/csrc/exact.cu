@@ -3,8 +3,8 @@
 //   * tie resolution: queries whose maximum score occurred in more than one 32-target window of the
 //     tensor-core kernel (rare: needs equal squared distances up to parity) are re-evaluated here;
 //   * SSRLCV_B200_ENGINE_SIMT: the whole problem, to cross-check the tcgen05 path on the device.
-// One warp per (split, query): lane l owns targets l, l+32, ... exactly like one block of the reference's
-// matchFeatures* kernels (ref: src/MatchFactory.cu:1466-1492), so the key (d2, f%32, f) falls out naturally.
+// One CTA per (split, query): thread t owns targets t, t+256, ... so f % 32 is the thread's lane, as in the reference's
+// 32-thread blocks (ref: src/MatchFactory.cu:1466-1492); the winner is the minimum of the key (d2, f%32, f).
 #include "geometry.cuh"
 #include "matcher.cuh"
 
@@ -21,13 +21,13 @@ __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
   return v;
 }
 
+// One CTA (8 warps) per (split, query) item; lane/warp-strided over the target range, then a block-wide min.
 template <int kMask>
 __global__ void __launch_bounds__(256) exact_kernel(SmaxArgs a, MaskParams mp, int use_list) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  __shared__ uint64_t s_min[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t total = use_list ? *a.n_flagged : a.n_splits * a.nq;
-  for (uint32_t item = warp; item < total; item += n_warps) {
+  for (uint32_t item = blockIdx.x; item < total; item += gridDim.x) {
     uint32_t split, row;
     if (use_list) { const uint32_t e = a.flagged[item]; split = e / a.nq_pad; row = e % a.nq_pad; }
     else { split = item / a.nq; row = item % a.nq; }
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) exact_kernel(SmaxArgs a, MaskParams mp, i
     uint64_t f_end = f_begin + static_cast<uint64_t>(a.tiles_per_split) * kBN;
     if (f_end > a.nt) f_end = a.nt;
     uint64_t best = kKeyNone;
-    for (uint64_t f = f_begin + lane; f < f_end; f += 32) {
+    for (uint64_t f = f_begin + threadIdx.x; f < f_end; f += 256) {     // f % 32 == lane for every f of this thread
       if (kMask != SSRLCV_B200_MASK_NONE) {
         const float2 tl = a.t_loc[f];
         if (mask_skips<kMask>(qm, tl.x, tl.y, mp.eps)) continue;
@@ -60,7 +60,15 @@ __global__ void __launch_bounds__(256) exact_kernel(SmaxArgs a, MaskParams mp, i
       best = key < best ? key : best;
     }
     best = warp_min_u64(best);
-    if (lane == 0) a.keys[static_cast<uint64_t>(split) * a.nq_pad + row] = best;
+    if (lane == 0) s_min[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint64_t m = s_min[0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) m = s_min[w] < m ? s_min[w] : m;
+      a.keys[static_cast<uint64_t>(split) * a.nq_pad + row] = m;
+    }
+    __syncthreads();
   }
 }
 

@@ -23,8 +23,10 @@
 //   warp 1  MMA issuer   : 5 x tcgen05.mma (M128 N256 K32) per stage into one of two 256-column
 //                          TMEM accumulators; tcgen05.commit releases the smem stage and publishes
 //                          the accumulator
-//   warp 2  TMEM allocator, warp 3 idle
-//   warps 4-7 epilogue   : tcgen05.ld 32x32b.x32, max3 tree, window bookkeeping, final exact resolve
+//   warp 2  TMEM allocator, warp 3 writes the constant fold operand
+//   warps 4-11 epilogue  : two warps per TMEM lane quarter (one per half of the 256 columns) so every SM
+//                          sub-partition has two epilogue warps to hide latency: tcgen05.ld 32x32b.x32,
+//                          max3 tree, window bookkeeping, final exact resolve (16 queries per warp)
 // Masked variants (epipolar constraints) evaluate the reference's float mask per (query, target) in the
 // epilogue on target locations staged through a small shared-memory ring.
 #include "geometry.cuh"
@@ -42,6 +44,9 @@ constexpr uint32_t kAExtBytes = kBM * kExtBytes;     // 4096
 constexpr uint32_t kColLocBytes = kBN * 8;           // float2 per target
 constexpr uint32_t kColWBytes = kBN * 4;             // int32 W per target
 constexpr uint32_t kTmemCols = 512;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (4 + kEpiWarps) * 32;      // 384
+constexpr uint32_t kNoWin = 0xFFFFFFFFu;
 
 struct SmemLayout {
   static constexpr uint32_t a = 0;                                       // 2 x 16 KB
@@ -53,11 +58,40 @@ struct SmemLayout {
   static constexpr uint32_t bars = col_w + kColStages * kColWBytes;
   static constexpr uint32_t n_bars = 2 * kStages + 4 + 4 + 2 * kColStages;
   static constexpr uint32_t tmem_ptr = bars + n_bars * 8;
-  static constexpr uint32_t total = tmem_ptr + 16;
+  static constexpr uint32_t xch = tmem_ptr + 16;                         // 2 (unit parity) x 2 (half) x 128 rows x 16 B
+  static constexpr uint32_t total = xch + 2 * 2 * kBM * 16;
 };
 constexpr uint32_t kSmemBytes = SmemLayout::total + 1024;   // + slack for manual 1024-byte alignment
 
 __device__ __forceinline__ int32_t max3(int32_t a, int32_t b, int32_t c) { return max(max(a, b), c); }
+
+// maximum of 32 values as a depth-4 tree of 3-input max (VIMNMX3): 17 instructions, no long dependency chain
+__device__ __forceinline__ int32_t max32(const uint32_t (&x)[32]) {
+  int32_t t[11];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) t[i] = max3(static_cast<int32_t>(x[3 * i]), static_cast<int32_t>(x[3 * i + 1]), static_cast<int32_t>(x[3 * i + 2]));
+  t[10] = max(static_cast<int32_t>(x[30]), static_cast<int32_t>(x[31]));
+  const int32_t u0 = max3(t[0], t[1], t[2]), u1 = max3(t[3], t[4], t[5]), u2 = max3(t[6], t[7], t[8]), u3 = max(t[9], t[10]);
+  return max(max3(u0, u1, u2), u3);
+}
+
+// per-query running state of the window search: best score and up to two windows that reached it
+struct WinState { int32_t best; uint32_t w1, w2, ovf; };
+__device__ __forceinline__ void win_update(WinState& s, int32_t m, uint32_t win) {
+  if (m > s.best) { s.best = m; s.w1 = win; s.w2 = kNoWin; s.ovf = 0; }
+  else if (s.w2 == kNoWin) s.w2 = win;
+  else s.ovf = 1;
+}
+__device__ __forceinline__ WinState win_merge(const WinState& a, const WinState& b) {
+  if (a.best > b.best) return a;
+  if (b.best > a.best) return b;
+  WinState r = a;                       // equal scores: union of the windows, at most two survive
+  if (a.best <= 1) return r;
+  r.ovf = a.ovf | b.ovf;
+  if (a.w2 == kNoWin) r.w2 = b.w1; else r.ovf = 1;
+  if (b.w2 != kNoWin) r.ovf = 1;
+  return r;
+}
 
 __device__ __forceinline__ uint64_t warp_min_u64_tc(uint64_t v) {
 #pragma unroll
@@ -72,7 +106,7 @@ __device__ __forceinline__ uint64_t warp_min_u64_tc(uint64_t v) {
 
 // kMask: SSRLCV_B200_MASK_*.  kFold: W_b carried by the fifth MMA (true) or added in the epilogue (false).
 template <int kMask, bool kFold>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
             const __grid_constant__ CUtensorMap map_text, const SmaxArgs args, const MaskParams mp) {
   constexpr bool kCols = (kMask != SSRLCV_B200_MASK_NONE) || !kFold;   // epilogue needs per-target data
@@ -98,8 +132,8 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
-    for (int i = 0; i < kColStages; ++i) { mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kEpiWarps); }
+    for (int i = 0; i < kColStages; ++i) { mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], kEpiWarps); }
     fence_mbar_init();
   }
   if (warp == 2) { tmem_alloc<kTmemCols>(tmem_ptr); tmem_relinquish(); }
@@ -189,8 +223,12 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
   } else if (warp >= 4) {
     // =============================== epilogue ===============================
     const uint32_t quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32)
+    const uint32_t half = (warp - 4) >> 2;             // which 128 of the 256 accumulator columns
     const uint32_t lane_addr = (quarter * 32u) << 16;
-    uint32_t acc = 0, accphase = 0, cs = 0, cphase = 0;
+    constexpr uint32_t kWinPerTile = kBN / kChunk;     // 8
+    constexpr uint32_t kWinPerWarp = kWinPerTile / 2;  // 4
+    WinState* xch = reinterpret_cast<WinState*>(smem + SmemLayout::xch);
+    uint32_t acc = 0, accphase = 0, cs = 0, cphase = 0, uparity = 0;
     for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
       const uint32_t qt = unit / args.n_splits, sp = unit % args.n_splits;
       const uint32_t t0 = sp * args.tiles_per_split;
@@ -199,25 +237,26 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
       QueryMask qm;
       if (kMask != SSRLCV_B200_MASK_NONE) qm = make_query_mask<kMask>(mp, args.q_loc[min(row, args.nq_pad - 1)]);
 
-      int32_t best = 1;            // real scores are >= 2, padding / masked entries are 0
-      uint32_t bwin = 0;           // window (32 targets) index inside this target set
-      uint32_t tie = 0;
+      WinState st;
+      st.best = 1; st.w1 = 0; st.w2 = kNoWin; st.ovf = 0;        // real scores are >= 2, padding / masked entries are 0
       for (uint32_t j = t0; j < t1; ++j) {
         mbar_wait(&t_full[acc], accphase);
         tc_fence_after();
         const float2* s_loc = reinterpret_cast<const float2*>(smem + SmemLayout::col_loc + cs * kColLocBytes);
         const int32_t* s_w = reinterpret_cast<const int32_t*>(smem + SmemLayout::col_w + cs * kColWBytes);
         if (kCols) mbar_wait(&c_full[cs], cphase);
+        const uint32_t n_win = min(kWinPerTile, (args.nt - j * kBN + kChunk - 1) / kChunk);
+        const uint32_t c_begin = half * kWinPerWarp;
         const uint32_t taddr = tmem_base + acc * kBN + lane_addr;
-        const uint32_t n_win = min(static_cast<uint32_t>(kBN / kChunk), (args.nt - j * kBN + kChunk - 1) / kChunk);
         uint32_t v[2][32];
-        tmem_ld_32x32(taddr, v[0]);
+        if (c_begin < n_win) tmem_ld_32x32(taddr + c_begin * kChunk, v[0]);
 #pragma unroll
-        for (uint32_t c = 0; c < kBN / kChunk; ++c) {
+        for (uint32_t k = 0; k < kWinPerWarp; ++k) {
+          const uint32_t c = c_begin + k;
           if (c < n_win) {                                        // warp-uniform
             tmem_ld_wait();
-            if (c + 1 < n_win) tmem_ld_32x32(taddr + (c + 1) * kChunk, v[(c + 1) & 1]);
-            uint32_t(&x)[32] = v[c & 1];
+            if (k + 1 < kWinPerWarp && c + 1 < n_win) tmem_ld_32x32(taddr + (c + 1) * kChunk, v[(k + 1) & 1]);
+            uint32_t(&x)[32] = v[k & 1];
             if (!kFold) {
 #pragma unroll
               for (int e = 0; e < 32; ++e) x[e] = static_cast<uint32_t>(static_cast<int32_t>(x[e]) + s_w[c * kChunk + e]);
@@ -230,17 +269,11 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                 if (mask_skips<kMask>(qm, l2.z, l2.w, mp.eps)) x[e + 1] = 0;
               }
             }
-            int32_t m = max3(static_cast<int32_t>(x[0]), static_cast<int32_t>(x[1]), static_cast<int32_t>(x[2]));
-#pragma unroll
-            for (int e = 3; e < 31; e += 2) m = max3(m, static_cast<int32_t>(x[e]), static_cast<int32_t>(x[e + 1]));
-            m = max(m, static_cast<int32_t>(x[31]));
-            if (m >= best) {                                       // rare after the first windows
-              if (m > best) { best = m; bwin = j * (kBN / kChunk) + c; tie = 0; }
-              else tie = 1;
-            }
+            const int32_t m = max32(x);
+            if (m >= st.best) win_update(st, m, j * kWinPerTile + c);   // rare after the first windows
           }
         }
-        // accumulator drained -> hand it back to the MMA warp
+        // accumulator half drained -> hand it back to the MMA warp
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -251,58 +284,75 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         if (kCols) { if (++cs == kColStages) { cs = 0; cphase ^= 1; } }
       }
 
-      // ---------------- exact resolve of the recorded window, one query per iteration ----------------
+      // ---------------- merge the two column halves, then resolve the recorded windows exactly ----------------
+      xch[(uparity * 2 + half) * kBM + quarter * 32 + lane] = st;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
       uint64_t mykey = kKeyNone;
-      const uint32_t row0 = qt * kBM + quarter * 32;
-      for (int r = 0; r < 32; ++r) {
-        const uint32_t qrow = row0 + r;
+      const uint32_t r_begin = half * 16;
+      for (uint32_t i = 0; i < 16; ++i) {
+        const uint32_t r = r_begin + i;
+        const uint32_t qrow = qt * kBM + quarter * 32 + r;
         if (qrow >= args.nq) break;                                // warp-uniform
-        const int32_t S_r = __shfl_sync(0xffffffffu, best, r);
-        const uint32_t win_r = __shfl_sync(0xffffffffu, bwin, r);
-        const uint32_t tie_r = __shfl_sync(0xffffffffu, tie, r);
+        const WinState m = win_merge(xch[(uparity * 2 + 0) * kBM + quarter * 32 + r], xch[(uparity * 2 + 1) * kBM + quarter * 32 + r]);
         uint64_t res = kKeyNone;
-        if (S_r > 1) {
-          if (tie_r) {
+        if (m.best > 1) {
+          if (m.ovf) {
             res = kKeyNeedsExact;
             if (lane == 0) {
               const uint32_t slot = atomicAdd(args.n_flagged, 1u);
               args.flagged[slot] = sp * args.nq_pad + qrow;
             }
           } else {
-            const uint64_t f = static_cast<uint64_t>(win_r) * kChunk + lane;
-            uint64_t key = kKeyNone;
-            bool ok = f < args.nt;
+            QueryMask qr;
             if (kMask != SSRLCV_B200_MASK_NONE) {
-              // re-evaluate the mask with the owning thread's per-query state
-              const float2 tl = ok ? args.t_loc[f] : make_float2(0.f, 0.f);
-              QueryMask qr;
+              // the per-query mask state lives in the thread that owns row r (same lane in both warps of a quarter)
               qr.seg.lo_x = __shfl_sync(0xffffffffu, qm.seg.lo_x, r);   qr.seg.hi_x = __shfl_sync(0xffffffffu, qm.seg.hi_x, r);
               qr.seg.left_x = __shfl_sync(0xffffffffu, qm.seg.left_x, r); qr.seg.left_y = __shfl_sync(0xffffffffu, qm.seg.left_y, r);
               qr.seg.slope = __shfl_sync(0xffffffffu, qm.seg.slope, r);  qr.seg.top_lo = __shfl_sync(0xffffffffu, qm.seg.top_lo, r);
               qr.seg.bot_hi = __shfl_sync(0xffffffffu, qm.seg.bot_hi, r); qr.seg.vertical = __shfl_sync(0xffffffffu, qm.seg.vertical, r);
               qr.line.ex = __shfl_sync(0xffffffffu, qm.line.ex, r); qr.line.ey = __shfl_sync(0xffffffffu, qm.line.ey, r);
               qr.line.ez = __shfl_sync(0xffffffffu, qm.line.ez, r);
-              if (ok && mask_skips<kMask>(qr, tl.x, tl.y, mp.eps)) ok = false;
             }
-            if (ok) {
-              const uint4* qd = reinterpret_cast<const uint4*>(args.q_desc + static_cast<uint64_t>(qrow) * kDescBytes);
-              const uint4* td = reinterpret_cast<const uint4*>(args.t_desc + f * kDescBytes);
-              uint32_t dot = 0;
+            const uint4* qd = reinterpret_cast<const uint4*>(args.q_desc + static_cast<uint64_t>(qrow) * kDescBytes);
+            uint4 qv[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const uint4 a4 = __ldg(qd + i), b4 = __ldg(td + i);
-                dot = __dp4a(a4.x, b4.x, dot); dot = __dp4a(a4.y, b4.y, dot);
-                dot = __dp4a(a4.z, b4.z, dot); dot = __dp4a(a4.w, b4.w, dot);
+            for (int w = 0; w < 8; ++w) qv[w] = __ldg(qd + w);
+            const int32_t qn = args.q_norm[qrow];
+            uint64_t key = kKeyNone;
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+              const uint32_t win = which == 0 ? m.w1 : m.w2;
+              if (win == kNoWin) continue;                         // warp-uniform
+              const uint64_t f = static_cast<uint64_t>(win) * kChunk + lane;
+              bool ok = f < args.nt;
+              if (kMask != SSRLCV_B200_MASK_NONE) {
+                const float2 tl = ok ? args.t_loc[f] : make_float2(0.f, 0.f);
+                if (ok && mask_skips<kMask>(qr, tl.x, tl.y, mp.eps)) ok = false;
               }
-              const uint32_t d2 = static_cast<uint32_t>(args.q_norm[qrow] + args.t_norm[f] - 2 * static_cast<int32_t>(dot));
-              key = make_key(d2, f + args.target_offset);
+              if (ok) {
+                const uint4* td = reinterpret_cast<const uint4*>(args.t_desc + f * kDescBytes);
+                uint32_t dot = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {
+                  const uint4 b4 = __ldg(td + w);
+                  dot = __dp4a(qv[w].x, b4.x, dot); dot = __dp4a(qv[w].y, b4.y, dot);
+                  dot = __dp4a(qv[w].z, b4.z, dot); dot = __dp4a(qv[w].w, b4.w, dot);
+                }
+                const uint32_t d2 = static_cast<uint32_t>(qn + args.t_norm[f] - 2 * static_cast<int32_t>(dot));
+                const uint64_t k2 = make_key(d2, f + args.target_offset);
+                key = k2 < key ? k2 : key;
+              }
             }
             res = warp_min_u64_tc(key);
           }
         }
-        if (lane == r) mykey = res;
+        if (lane == i) mykey = res;
       }
-      if (row < args.nq) args.keys[static_cast<uint64_t>(sp) * args.nq_pad + row] = mykey;
+      if (lane < 16) {
+        const uint32_t orow = qt * kBM + quarter * 32 + r_begin + lane;
+        if (orow < args.nq) args.keys[static_cast<uint64_t>(sp) * args.nq_pad + orow] = mykey;
+      }
+      uparity ^= 1;
     }
   }
 
@@ -321,7 +371,7 @@ static cudaError_t launch_one(cudaStream_t st, int grid, const ssrlcv_b200_set_i
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<grid, 256, kSmemBytes, st>>>(q.map_a, t.map_b, t.map_ext, a, mp);
+  kern<<<grid, kThreads, kSmemBytes, st>>>(q.map_a, t.map_b, t.map_ext, a, mp);
   return cudaGetLastError();
 }
 
