@@ -36,7 +36,7 @@ ssrlcv_b200_ctx* b200_context() {
     // the reference runs everything on the legacy default stream and synchronises after each kernel
     int rc = ssrlcv_b200_create(&ctx, dev, (void*)cudaStreamLegacy);
     if (rc != 0) {
-      ssrlcv::logger.err.printf("ERROR: ssrlcv_b200_create failed with code %d (an sm_100 GPU is required)", rc);
+      logger.err.printf("ERROR: ssrlcv_b200_create failed with code %d (an sm_100 GPU is required)", rc);
       exit(-1);
     }
   }
@@ -45,7 +45,7 @@ ssrlcv_b200_ctx* b200_context() {
 
 void b200_check(int rc, const char* what) {
   if (rc == 0) return;
-  ssrlcv::logger.err.printf("ERROR: %s failed with code %d: %s", what, rc, ssrlcv_b200_last_error(b200_context()));
+  logger.err.printf("ERROR: %s failed with code %d: %s", what, rc, ssrlcv_b200_last_error(b200_context()));
   exit(-1);
 }
 

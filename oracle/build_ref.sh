@@ -34,6 +34,18 @@ if [ ! -f "$OUT/obj/Logger.o" ]; then
   g++ -std=c++14 -fPIC -w -I"$REF/include" -I/usr/local/cuda/include -DLOG_LEVEL=3 -c "$REF/src/Logger.cpp" -o "$OUT/obj/Logger.o" &
   pids+=($!)
 fi
+# the drop-in: our integration/MatchFactory_b200.cu compiled against the reference's headers, in place of src/MatchFactory.cu
+ROOT="$(cd "$HERE/.." && pwd)"
+if [ ! -f "$OUT/obj/MatchFactory_b200.o" ] || [ "$ROOT/integration/MatchFactory_b200.cu" -nt "$OUT/obj/MatchFactory_b200.o" ] || [ "$ROOT/include/ssrlcv_b200.h" -nt "$OUT/obj/MatchFactory_b200.o" ]; then
+  nvcc $NVFLAGS -I"$ROOT/include" -dc "$ROOT/integration/MatchFactory_b200.cu" -o "$OUT/obj/MatchFactory_b200.o" &
+  pids+=($!)
+fi
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
-nvcc $ARCH -shared -Xcompiler -fPIC "$OUT"/obj/*.o -lcusolver -lcublas -lcuda -o "$OUT/libssrlcv_ref.so"
+COMMON="$OUT/obj/Feature.o $OUT/obj/matrix_util.o $OUT/obj/cuda_vec_util.o $OUT/obj/cuda_util.o $OUT/obj/Image.o $OUT/obj/Logger.o $OUT/obj/ref_harness.o"
+nvcc $ARCH -shared -Xcompiler -fPIC "$OUT/obj/MatchFactory.o" $COMMON -lcusolver -lcublas -lcuda -o "$OUT/libssrlcv_ref.so"
 echo "built $OUT/libssrlcv_ref.so"
+if [ -f "$ROOT/ssrlcv_b200/libssrlcv_match_b200.so" ]; then
+  nvcc $ARCH -shared -Xcompiler -fPIC "$OUT/obj/MatchFactory_b200.o" $COMMON -L"$ROOT/ssrlcv_b200" -lssrlcv_match_b200 \
+       -Xlinker -rpath -Xlinker '$ORIGIN/../../ssrlcv_b200' -lcusolver -lcublas -lcuda -o "$OUT/libssrlcv_dropin.so"
+  echo "built $OUT/libssrlcv_dropin.so"
+fi

@@ -14,6 +14,7 @@
 #include <chrono>
 #include <cstring>
 #include <sys/stat.h>
+#include <vector>
 
 using namespace ssrlcv;
 typedef Feature<SIFT_Descriptor> Feat;
@@ -138,6 +139,51 @@ long ref_match(int out_kind, int mask_kind, float abs_thr, float rel_thr, int qi
   else if (out_kind == 1) n = (long)copy_out(m1, out_host, sizeof(DMatch));
   else n = (long)copy_out(m2, out_host, sizeof(uint2_pair));
   return n;
+}
+
+/* generateMatchesExhaustive (ref: src/MatchFactory.cu:907-1028) over n_views host feature arrays.
+ * Returns the number of MultiMatch entries (copied to out_mm, capacity cap_mm); *n_kp keypoints to out_kp. */
+long ref_exhaustive(int n_views, const void* const* feats, const unsigned long* n_feats, const void* const* cams80, const int* ids,
+                    const void* seed, unsigned long n_seed, float rel_thr, float abs_thr, float eps, float delta, int state,
+                    void* out_mm, unsigned long cap_mm, void* out_kp, unsigned long cap_kp, unsigned long* n_kp, double* ms) {
+  mkdir("out", 0755);
+  std::vector<ptr::value<Image>> images;
+  std::vector<FeatSet> features;
+  for (int v = 0; v < n_views; ++v) {
+    images.push_back(make_image(ids[v], cams80[v]));
+    features.push_back(make_set(feats[v], n_feats[v], state));
+  }
+  MatchFactory<SIFT_Descriptor> mf(rel_thr, abs_thr);
+  if (seed) mf.setSeedFeatures(make_set(seed, n_seed, 2));
+  cudaDeviceSynchronize();
+  auto t0 = std::chrono::steady_clock::now();
+  MatchSet set = mf.generateMatchesExhaustive(images, features, eps, delta);
+  cudaDeviceSynchronize();
+  if (ms) *ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (set.matches->size() > cap_mm || set.keyPoints->size() > cap_kp) return -3;
+  if (set.matches->getMemoryState() == gpu) set.matches->transferMemoryTo(cpu);
+  if (set.keyPoints->getMemoryState() == gpu) set.keyPoints->transferMemoryTo(cpu);
+  memcpy(out_mm, (void*)set.matches->host.get(), set.matches->size() * sizeof(MultiMatch));
+  memcpy(out_kp, (void*)set.keyPoints->host.get(), set.keyPoints->size() * sizeof(KeyPoint));
+  *n_kp = set.keyPoints->size();
+  return (long)set.matches->size();
+}
+
+/* refineMatches + sortMatches + getRawMatches through the class API on a host DMatch array (in place); returns kept count */
+long ref_refine_sort(void* dmatches, unsigned long n, float threshold, int do_sort, void* raw_out) {
+  mkdir("out", 0755);
+  ptr::value<Unity<DMatch>> m(nullptr, n, cpu);
+  memcpy((void*)m->host.get(), dmatches, n * sizeof(DMatch));
+  m->setMemoryState(gpu);
+  MatchFactory<SIFT_Descriptor> mf;
+  if (threshold != 0.0f) mf.refineMatches(m, threshold);
+  if (do_sort) mf.sortMatches(m);
+  ptr::value<Unity<Match>> raw = mf.getRawMatches(m);
+  m->transferMemoryTo(cpu);
+  raw->transferMemoryTo(cpu);
+  memcpy(dmatches, (void*)m->host.get(), m->size() * sizeof(DMatch));
+  if (raw_out) memcpy(raw_out, (void*)raw->host.get(), raw->size() * sizeof(Match));
+  return (long)m->size();
 }
 
 }  // extern "C"

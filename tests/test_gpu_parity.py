@@ -375,3 +375,84 @@ def test_reference_cuda_reproduces_golden(api, everest):
                      qcam=ev.cameras[0], tcam=ev.cameras[1], qid=ev.img_ids[0], tid=ev.img_ids[1])
     assert len(ref) == 13534
     assert T.fields_equal(ref["keyPoints"].reshape(-1).copy(), ev.g2_keypoints)
+
+
+# ------------------------------------------------------------------------------------ the drop-in MatchFactory.cu
+def _load_harness(name):
+    path = os.path.join(ROOT, "oracle", "_ref", name)
+    if not os.path.exists(path):
+        pytest.skip(f"oracle/_ref/{name} not built (needs /root/reference at build time)")
+    cwd = os.getcwd()
+    os.makedirs("/tmp/ssrlcv_ref_run", exist_ok=True)
+    os.chdir("/tmp/ssrlcv_ref_run")
+    lib = C.CDLL(path, mode=os.RTLD_LOCAL | os.RTLD_NOW | getattr(os, "RTLD_DEEPBIND", 0))
+    os.chdir(cwd)
+    lib.ref_match.restype = C.c_long
+    lib.ref_exhaustive.restype = C.c_long
+    lib.ref_refine_sort.restype = C.c_long
+    return lib
+
+
+def test_dropin_matchfactory_equals_reference(api, everest):
+    """integration/MatchFactory_b200.cu compiled against the reference's own headers and linked with the reference's other
+    translation units: the reference's public API, our kernels.  Same inputs through both libraries -> same records."""
+    ref, drop = _load_harness("libssrlcv_ref.so"), _load_harness("libssrlcv_dropin.so")
+    q, t = synth.make_pair(2500, 4000, seed=91)
+    sd = api.O.seed_distances(q, synth.make_seed(600))
+    F = np.array([[1e-6, 2e-6, 0.0015], [-3e-6, 1e-7, -1.0], [-0.0013, 1.0, 4.0]], np.float32)
+    for out_kind in (T.OUT_MATCH, T.OUT_DMATCH, T.OUT_PAIR):
+        for mask_kind, kw in ((0, {}), (1, dict(eps=30.0, F=F)), (2, dict(eps=25.0, delta=5.0, qcam=everest.cameras[0], tcam=everest.cameras[1]))):
+            for seed in (None, sd):
+                a = _ref_match(ref, out_kind, mask_kind, 1.5e5, 0.8, q, t, seed, **kw)
+                b = _ref_match(drop, out_kind, mask_kind, 1.5e5, 0.8, q, t, seed, **kw)
+                assert len(a) > 5 and T.fields_equal(a, b), (out_kind, mask_kind, seed is not None)
+
+
+def _exhaustive(lib, ev):
+    n = 3
+    feats = (C.c_void_p * n)(*[v.ctypes.data for v in ev.views3])
+    nf = (C.c_ulong * n)(*[len(v) for v in ev.views3])
+    cam_bytes = [np.asarray(c).tobytes() for c in ev.cameras]
+    cams = (C.c_char_p * n)(*cam_bytes)
+    ids = (C.c_int * n)(*ev.img_ids)
+    mm = np.zeros(40000, T.MULTIMATCH); kp = np.zeros(120000, T.KEYPOINT)
+    nkp = C.c_ulong(0); ms = C.c_double(0)
+    cwd = os.getcwd(); os.chdir("/tmp/ssrlcv_ref_run")
+    try:
+        nmm = lib.ref_exhaustive(n, feats, nf, C.cast(cams, C.POINTER(C.c_void_p)), ids, ev.seed3.ctypes.data_as(C.c_void_p), C.c_ulong(len(ev.seed3)),
+                                 C.c_float(ev.rel_threshold), C.c_float(ev.abs_threshold), C.c_float(ev.epsilon), C.c_float(ev.delta), 3,
+                                 mm.ctypes.data_as(C.c_void_p), C.c_ulong(len(mm)), kp.ctypes.data_as(C.c_void_p), C.c_ulong(len(kp)), C.byref(nkp), C.byref(ms))
+    finally:
+        os.chdir(cwd)
+    assert nmm >= 0
+    return mm[:nmm], kp[: nkp.value], ms.value
+
+
+def test_dropin_three_view_golden(api, everest):
+    """PipelineTest.FeatureMatching3View (ref: test/Pipeline.cu:218-255) through the drop-in's generateMatchesExhaustive."""
+    drop = _load_harness("libssrlcv_dropin.so")
+    mm, kp, _ = _exhaustive(drop, everest)
+    assert T.fields_equal(mm, everest.g3_multimatch) and T.fields_equal(kp, everest.g3_keypoints)
+
+
+def test_dropin_refine_sort_raw(api):
+    ref, drop = _load_harness("libssrlcv_ref.so"), _load_harness("libssrlcv_dropin.so")
+    q, t = synth.make_pair(3000, 3000, seed=93)
+    base = api.O.generate_matches(api.O.make_params(out_kind=T.OUT_DMATCH), q, t)
+    thr = float(np.median(base["distance"]))
+    outs = []
+    for lib in (ref, drop):
+        m = base.copy(); raw = np.zeros(len(m), T.MATCH)
+        cwd = os.getcwd(); os.chdir("/tmp/ssrlcv_ref_run")
+        try:
+            n = lib.ref_refine_sort(m.ctypes.data_as(C.c_void_p), C.c_ulong(len(m)), C.c_float(thr), 1, raw.ctypes.data_as(C.c_void_p))
+        finally:
+            os.chdir(cwd)
+        outs.append((m[:n], raw[:n]))
+    (ma, ra), (mb, rb) = outs
+    assert len(ma) == len(mb) and np.array_equal(ma["distance"], mb["distance"])          # same multiset, same order of distances
+    want = api.O.sort(api.O.refine(base, thr))
+    assert T.fields_equal(mb, want) and T.fields_equal(rb, api.O.raw_matches(want))
+    # the reference's thrust::sort is unstable: inside runs of equal distance only the set of records is defined
+    key = lambda r: (float(r["distance"]), r["keyPoints"]["loc"].tobytes())
+    assert sorted(map(key, ma)) == sorted(map(key, mb))
