@@ -247,31 +247,61 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         if (kCols) mbar_wait(&c_full[cs], cphase);
         const uint32_t n_win = min(kWinPerTile, (args.nt - j * kBN + kChunk - 1) / kChunk);
         const uint32_t c_begin = half * kWinPerWarp;
-        const uint32_t taddr = tmem_base + acc * kBN + lane_addr;
+        const uint32_t taddr = tmem_base + acc * kBN + lane_addr + c_begin * kChunk;
         uint32_t v[2][32];
-        if (c_begin < n_win) tmem_ld_32x32(taddr + c_begin * kChunk, v[0]);
+        int32_t wm[kWinPerWarp];                                   // per-window maxima of this warp's 4 windows
+        if (n_win == kWinPerTile) {
+          // full tile: straight-line, one load in flight while the previous window is reduced
+          tmem_ld_32x32(taddr, v[0]);
 #pragma unroll
-        for (uint32_t k = 0; k < kWinPerWarp; ++k) {
-          const uint32_t c = c_begin + k;
-          if (c < n_win) {                                        // warp-uniform
+          for (uint32_t k = 0; k < kWinPerWarp; ++k) {
             tmem_ld_wait();
-            if (k + 1 < kWinPerWarp && c + 1 < n_win) tmem_ld_32x32(taddr + (c + 1) * kChunk, v[(k + 1) & 1]);
+            if (k + 1 < kWinPerWarp) tmem_ld_32x32(taddr + (k + 1) * kChunk, v[(k + 1) & 1]);
             uint32_t(&x)[32] = v[k & 1];
             if (!kFold) {
 #pragma unroll
-              for (int e = 0; e < 32; ++e) x[e] = static_cast<uint32_t>(static_cast<int32_t>(x[e]) + s_w[c * kChunk + e]);
+              for (int e = 0; e < 32; ++e) x[e] = static_cast<uint32_t>(static_cast<int32_t>(x[e]) + s_w[(c_begin + k) * kChunk + e]);
             }
             if (kMask != SSRLCV_B200_MASK_NONE) {
 #pragma unroll
               for (int e = 0; e < 32; e += 2) {
-                const float4 l2 = *reinterpret_cast<const float4*>(&s_loc[c * kChunk + e]);
+                const float4 l2 = *reinterpret_cast<const float4*>(&s_loc[(c_begin + k) * kChunk + e]);
                 if (mask_skips<kMask>(qm, l2.x, l2.y, mp.eps)) x[e] = 0;
                 if (mask_skips<kMask>(qm, l2.z, l2.w, mp.eps)) x[e + 1] = 0;
               }
             }
-            const int32_t m = max32(x);
-            if (m >= st.best) win_update(st, m, j * kWinPerTile + c);   // rare after the first windows
+            wm[k] = max32(x);
           }
+        } else {
+          // last, partial tile of the target set: windows past the end are skipped (warp-uniform)
+#pragma unroll
+          for (uint32_t k = 0; k < kWinPerWarp; ++k) {
+            wm[k] = 0;
+            if (c_begin + k < n_win) {
+              tmem_ld_32x32(taddr + k * kChunk, v[0]);
+              tmem_ld_wait();
+              uint32_t(&x)[32] = v[0];
+              if (!kFold) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) x[e] = static_cast<uint32_t>(static_cast<int32_t>(x[e]) + s_w[(c_begin + k) * kChunk + e]);
+              }
+              if (kMask != SSRLCV_B200_MASK_NONE) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                  const float2 l = s_loc[(c_begin + k) * kChunk + e];
+                  if (mask_skips<kMask>(qm, l.x, l.y, mp.eps)) x[e] = 0;
+                }
+              }
+              wm[k] = max32(x);
+            }
+          }
+        }
+        // one rarely-taken branch per tile: only when some window reaches the running best is the bookkeeping touched
+        const int32_t mt = max(max(wm[0], wm[1]), max(wm[2], wm[3]));
+        if (mt >= st.best) {
+#pragma unroll
+          for (uint32_t k = 0; k < kWinPerWarp; ++k)
+            if (wm[k] >= st.best) win_update(st, wm[k], j * kWinPerTile + c_begin + k);
         }
         // accumulator half drained -> hand it back to the MMA warp
         tc_fence_before();
