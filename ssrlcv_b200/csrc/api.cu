@@ -362,6 +362,10 @@ static int run_engine(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* q, const ssrl
   a.keys = static_cast<uint64_t*>(ctx->keys.p);
   a.flagged = static_cast<uint32_t*>(ctx->flagged.p);
   a.n_flagged = ctx->d_scalars;
+  a.timing = nullptr;
+  if (const char* tp = getenv("SSRLCV_B200_TIMING")) {       // diagnostics: device buffer address (hex) for cycle counters
+    a.timing = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 16));
+  }
   if (a.nq == 0) return 0;
   if (a.nt == 0) { launch_fill_u64(ctx->stream, a.keys, n_keys, kKeyNone); ctx->launches += 1; return 0; }
   if (engine == SSRLCV_B200_ENGINE_SIMT) {

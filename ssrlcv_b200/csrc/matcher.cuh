@@ -103,6 +103,7 @@ struct SmaxArgs {
   uint64_t* keys;                // [n_splits][nq_pad]
   uint32_t* flagged;             // list of (split * nq_pad + row) needing the exact kernel
   uint32_t* n_flagged;
+  unsigned long long* timing;    // optional [gridDim.x][16] cycle counters (diagnostics), or nullptr
 };
 
 }  // namespace b200

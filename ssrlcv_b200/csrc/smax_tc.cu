@@ -159,6 +159,8 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     // =============================== TMA producer ===============================
     if (elect_one()) {
       uint32_t stage = 0, phase = 0, aslot = 0, aphase = 0, cs = 0, cphase = 0;
+      long long tp_wait = 0;
+      const bool timing = args.timing != nullptr;
       for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const uint32_t qt = unit / args.n_splits, sp = unit % args.n_splits;
         const uint32_t t0 = sp * args.tiles_per_split;
@@ -167,7 +169,10 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         mbar_arrive_expect_tx(&a_full[aslot], kABytes);
         tma_load_2d(smem + SmemLayout::a + aslot * kABytes, &map_q, &a_full[aslot], 0, static_cast<int32_t>(qt * kBM));
         for (uint32_t j = t0; j < t1; ++j) {
+          long long p0 = 0;
+          if (timing) p0 = clock64();
           mbar_wait(&empty[stage], phase ^ 1);
+          if (timing) tp_wait += clock64() - p0;
           mbar_arrive_expect_tx(&full[stage], kBBytes + (kFold ? kBExtBytes : 0));
           tma_load_2d(smem + SmemLayout::b + stage * kBBytes, &map_t, &full[stage], 0, static_cast<int32_t>(j * kBN));
           if (kFold) tma_load_2d(smem + SmemLayout::bext + stage * kBExtBytes, &map_text, &full[stage], 0, static_cast<int32_t>(j * kBN));
@@ -185,6 +190,7 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         }
         if (++aslot == 2) { aslot = 0; aphase ^= 1; }
       }
+      if (timing) args.timing[blockIdx.x * 16 + 3] = tp_wait;
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
@@ -192,6 +198,8 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
       constexpr uint32_t idesc = make_idesc_i8(kBM, kBN, 0, 0);
       const uint64_t aext_desc = make_smem_desc(smem_u32(smem + SmemLayout::aext), 256, kSwizzle32B);
       uint32_t stage = 0, phase = 0, aslot = 0, aphase = 0, acc = 0, accphase = 0;
+      long long tm_wait_acc = 0, tm_wait_full = 0, tm_total0 = clock64();
+      const bool timing = args.timing != nullptr;
       for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const uint32_t sp = unit % args.n_splits;
         const uint32_t t0 = sp * args.tiles_per_split;
@@ -199,8 +207,12 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         mbar_wait(&a_full[aslot], aphase);
         const uint64_t a_desc = make_smem_desc(smem_u32(smem + SmemLayout::a + aslot * kABytes), 1024, kSwizzle128B);
         for (uint32_t j = t0; j < t1; ++j) {
+          long long c0 = 0, c1 = 0, c2 = 0;
+          if (timing) c0 = clock64();
           mbar_wait(&t_empty[acc], accphase ^ 1);
+          if (timing) c1 = clock64();
           mbar_wait(&full[stage], phase);
+          if (timing) { c2 = clock64(); tm_wait_acc += c1 - c0; tm_wait_full += c2 - c1; }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kBN;
           const uint64_t b_desc = make_smem_desc(smem_u32(smem + SmemLayout::b + stage * kBBytes), 1024, kSwizzle128B);
@@ -219,6 +231,11 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         mma_commit(&a_empty[aslot]);
         if (++aslot == 2) { aslot = 0; aphase ^= 1; }
       }
+      if (timing) {
+        args.timing[blockIdx.x * 16 + 0] = tm_wait_acc;
+        args.timing[blockIdx.x * 16 + 1] = tm_wait_full;
+        args.timing[blockIdx.x * 16 + 2] = clock64() - tm_total0;
+      }
     }
   } else if (warp >= 4) {
     // =============================== epilogue ===============================
@@ -229,6 +246,8 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     constexpr uint32_t kWinPerWarp = kWinPerTile / 2;  // 4
     WinState* xch = reinterpret_cast<WinState*>(smem + SmemLayout::xch);
     uint32_t acc = 0, accphase = 0, cs = 0, cphase = 0, uparity = 0;
+    const bool timing = args.timing != nullptr;
+    long long te_wait = 0, te_work = 0, te_resolve = 0, te_total0 = clock64();
     for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
       const uint32_t qt = unit / args.n_splits, sp = unit % args.n_splits;
       const uint32_t t0 = sp * args.tiles_per_split;
@@ -240,7 +259,10 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
       WinState st;
       st.best = 1; st.w1 = 0; st.w2 = kNoWin; st.ovf = 0;        // real scores are >= 2, padding / masked entries are 0
       for (uint32_t j = t0; j < t1; ++j) {
+        long long e0 = 0, e1 = 0;
+        if (timing) e0 = clock64();
         mbar_wait(&t_full[acc], accphase);
+        if (timing) e1 = clock64();
         tc_fence_after();
         const float2* s_loc = reinterpret_cast<const float2*>(smem + SmemLayout::col_loc + cs * kColLocBytes);
         const int32_t* s_w = reinterpret_cast<const int32_t*>(smem + SmemLayout::col_w + cs * kColWBytes);
@@ -312,7 +334,10 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         }
         if (++acc == 2) { acc = 0; accphase ^= 1; }
         if (kCols) { if (++cs == kColStages) { cs = 0; cphase ^= 1; } }
+        if (timing) { const long long e2 = clock64(); te_wait += e1 - e0; te_work += e2 - e1; }
       }
+      long long r0 = 0;
+      if (timing) r0 = clock64();
 
       // ---------------- merge the two column halves, then resolve the recorded windows exactly ----------------
       xch[(uparity * 2 + half) * kBM + quarter * 32 + lane] = st;
@@ -383,6 +408,14 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         if (orow < args.nq) args.keys[static_cast<uint64_t>(sp) * args.nq_pad + orow] = mykey;
       }
       uparity ^= 1;
+      if (timing) te_resolve += clock64() - r0;
+    }
+    if (timing && lane == 0) {
+      const uint32_t e = warp - 4;
+      if (e == 0 || e == 5) {
+        const uint32_t o = blockIdx.x * 16 + (e == 0 ? 4 : 8);
+        args.timing[o + 0] = te_wait; args.timing[o + 1] = te_work; args.timing[o + 2] = te_resolve; args.timing[o + 3] = clock64() - te_total0;
+      }
     }
   }
 
