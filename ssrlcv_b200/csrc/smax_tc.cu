@@ -342,70 +342,70 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
       // ---------------- merge the two column halves, then resolve the recorded windows exactly ----------------
       xch[(uparity * 2 + half) * kBM + quarter * 32 + lane] = st;
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-      uint64_t mykey = kKeyNone;
-      const uint32_t r_begin = half * 16;
-      for (uint32_t i = 0; i < 16; ++i) {
-        const uint32_t r = r_begin + i;
+      // lane = (window slot, query): lanes 0-15 take the first recorded window of 16 queries, lanes 16-31 the second one
+      // (if any).  Each lane walks the 32 targets of its window with independent loads in flight, so the exact
+      // resolve costs one pass of memory latency per unit instead of one per query.
+      {
+        const uint32_t r_begin = half * 16;
+        const uint32_t rl = lane & 15, which = lane >> 4;
+        const uint32_t r = r_begin + rl;
         const uint32_t qrow = qt * kBM + quarter * 32 + r;
-        if (qrow >= args.nq) break;                                // warp-uniform
         const WinState m = win_merge(xch[(uparity * 2 + 0) * kBM + quarter * 32 + r], xch[(uparity * 2 + 1) * kBM + quarter * 32 + r]);
-        uint64_t res = kKeyNone;
-        if (m.best > 1) {
-          if (m.ovf) {
-            res = kKeyNeedsExact;
-            if (lane == 0) {
-              const uint32_t slot = atomicAdd(args.n_flagged, 1u);
-              args.flagged[slot] = sp * args.nq_pad + qrow;
-            }
-          } else {
-            QueryMask qr;
+        QueryMask qr;
+        if (kMask != SSRLCV_B200_MASK_NONE) {
+          // the per-query mask state lives in the thread that owns row r (same lane index in both warps of a quarter)
+          qr.seg.lo_x = __shfl_sync(0xffffffffu, qm.seg.lo_x, r);   qr.seg.hi_x = __shfl_sync(0xffffffffu, qm.seg.hi_x, r);
+          qr.seg.left_x = __shfl_sync(0xffffffffu, qm.seg.left_x, r); qr.seg.left_y = __shfl_sync(0xffffffffu, qm.seg.left_y, r);
+          qr.seg.slope = __shfl_sync(0xffffffffu, qm.seg.slope, r);  qr.seg.top_lo = __shfl_sync(0xffffffffu, qm.seg.top_lo, r);
+          qr.seg.bot_hi = __shfl_sync(0xffffffffu, qm.seg.bot_hi, r); qr.seg.vertical = __shfl_sync(0xffffffffu, qm.seg.vertical, r);
+          qr.line.ex = __shfl_sync(0xffffffffu, qm.line.ex, r); qr.line.ey = __shfl_sync(0xffffffffu, qm.line.ey, r);
+          qr.line.ez = __shfl_sync(0xffffffffu, qm.line.ez, r);
+        }
+        uint64_t key = kKeyNone;
+        const bool live = qrow < args.nq && m.best > 1;
+        const uint32_t win = which == 0 ? m.w1 : m.w2;
+        if (live && !m.ovf && win != kNoWin) {
+          const uint4* qd = reinterpret_cast<const uint4*>(args.q_desc + static_cast<uint64_t>(qrow) * kDescBytes);
+          uint4 qv[8];
+#pragma unroll
+          for (int w = 0; w < 8; ++w) qv[w] = __ldg(qd + w);
+          const int32_t qn = args.q_norm[qrow];
+          const uint64_t f0 = static_cast<uint64_t>(win) * kChunk;
+#pragma unroll 2
+          for (uint32_t i = 0; i < kChunk; ++i) {
+            const uint64_t f = f0 + i;
+            if (f >= args.nt) break;
             if (kMask != SSRLCV_B200_MASK_NONE) {
-              // the per-query mask state lives in the thread that owns row r (same lane in both warps of a quarter)
-              qr.seg.lo_x = __shfl_sync(0xffffffffu, qm.seg.lo_x, r);   qr.seg.hi_x = __shfl_sync(0xffffffffu, qm.seg.hi_x, r);
-              qr.seg.left_x = __shfl_sync(0xffffffffu, qm.seg.left_x, r); qr.seg.left_y = __shfl_sync(0xffffffffu, qm.seg.left_y, r);
-              qr.seg.slope = __shfl_sync(0xffffffffu, qm.seg.slope, r);  qr.seg.top_lo = __shfl_sync(0xffffffffu, qm.seg.top_lo, r);
-              qr.seg.bot_hi = __shfl_sync(0xffffffffu, qm.seg.bot_hi, r); qr.seg.vertical = __shfl_sync(0xffffffffu, qm.seg.vertical, r);
-              qr.line.ex = __shfl_sync(0xffffffffu, qm.line.ex, r); qr.line.ey = __shfl_sync(0xffffffffu, qm.line.ey, r);
-              qr.line.ez = __shfl_sync(0xffffffffu, qm.line.ez, r);
+              const float2 tl = args.t_loc[f];
+              if (mask_skips<kMask>(qr, tl.x, tl.y, mp.eps)) continue;
             }
-            const uint4* qd = reinterpret_cast<const uint4*>(args.q_desc + static_cast<uint64_t>(qrow) * kDescBytes);
-            uint4 qv[8];
+            const uint4* td = reinterpret_cast<const uint4*>(args.t_desc + f * kDescBytes);
+            uint32_t dot = 0;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) qv[w] = __ldg(qd + w);
-            const int32_t qn = args.q_norm[qrow];
-            uint64_t key = kKeyNone;
-#pragma unroll
-            for (int which = 0; which < 2; ++which) {
-              const uint32_t win = which == 0 ? m.w1 : m.w2;
-              if (win == kNoWin) continue;                         // warp-uniform
-              const uint64_t f = static_cast<uint64_t>(win) * kChunk + lane;
-              bool ok = f < args.nt;
-              if (kMask != SSRLCV_B200_MASK_NONE) {
-                const float2 tl = ok ? args.t_loc[f] : make_float2(0.f, 0.f);
-                if (ok && mask_skips<kMask>(qr, tl.x, tl.y, mp.eps)) ok = false;
-              }
-              if (ok) {
-                const uint4* td = reinterpret_cast<const uint4*>(args.t_desc + f * kDescBytes);
-                uint32_t dot = 0;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) {
-                  const uint4 b4 = __ldg(td + w);
-                  dot = __dp4a(qv[w].x, b4.x, dot); dot = __dp4a(qv[w].y, b4.y, dot);
-                  dot = __dp4a(qv[w].z, b4.z, dot); dot = __dp4a(qv[w].w, b4.w, dot);
-                }
-                const uint32_t d2 = static_cast<uint32_t>(qn + args.t_norm[f] - 2 * static_cast<int32_t>(dot));
-                const uint64_t k2 = make_key(d2, f + args.target_offset);
-                key = k2 < key ? k2 : key;
-              }
+            for (int w = 0; w < 8; ++w) {
+              const uint4 b4 = __ldg(td + w);
+              dot = __dp4a(qv[w].x, b4.x, dot); dot = __dp4a(qv[w].y, b4.y, dot);
+              dot = __dp4a(qv[w].z, b4.z, dot); dot = __dp4a(qv[w].w, b4.w, dot);
             }
-            res = warp_min_u64_tc(key);
+            const uint32_t d2 = static_cast<uint32_t>(qn + args.t_norm[f] - 2 * static_cast<int32_t>(dot));
+            const uint64_t k2 = make_key(d2, f + args.target_offset);
+            key = k2 < key ? k2 : key;
           }
         }
-        if (lane == i) mykey = res;
-      }
-      if (lane < 16) {
-        const uint32_t orow = qt * kBM + quarter * 32 + r_begin + lane;
-        if (orow < args.nq) args.keys[static_cast<uint64_t>(sp) * args.nq_pad + orow] = mykey;
+        {  // fold the second window's result into the first
+          const uint32_t lo = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(key), 16);
+          const uint32_t hi = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(key >> 32), 16);
+          const uint64_t other = (static_cast<uint64_t>(hi) << 32) | lo;
+          key = other < key ? other : key;
+        }
+        if (which == 0 && qrow < args.nq) {
+          if (live && m.ovf) {
+            key = kKeyNeedsExact;
+            const uint32_t slot = atomicAdd(args.n_flagged, 1u);
+            args.flagged[slot] = sp * args.nq_pad + qrow;
+          }
+          args.keys[static_cast<uint64_t>(sp) * args.nq_pad + qrow] = key;
+        }
       }
       uparity ^= 1;
       if (timing) te_resolve += clock64() - r0;
