@@ -56,7 +56,7 @@ struct SmemLayout {
   static constexpr uint32_t col_loc = aext + kAExtBytes;                 // kColStages x 2 KB
   static constexpr uint32_t col_w = col_loc + kColStages * kColLocBytes; // kColStages x 1 KB
   static constexpr uint32_t bars = col_w + kColStages * kColWBytes;
-  static constexpr uint32_t n_bars = 2 * kStages + 4 + 4 + 2 * kColStages;
+  static constexpr uint32_t n_bars = 2 * kStages + 4 + 4 + 2 * kColStages + 4;
   static constexpr uint32_t tmem_ptr = bars + n_bars * 8;
   static constexpr uint32_t xch = tmem_ptr + 16;                         // 2 (unit parity) x 2 (half) x 128 rows x 16 B
   static constexpr uint32_t total = xch + 2 * 2 * kBM * 16;
@@ -122,6 +122,8 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
   uint64_t* t_empty = t_full + 2;                // [2]         epilogue -> MMA (accumulator drained)
   uint64_t* c_full = t_empty + 2;                // [kColStages] TMA -> epilogue (target columns data)
   uint64_t* c_empty = c_full + kColStages;       // [kColStages]
+  uint64_t* x_full = c_empty + kColStages;       // [2] epilogue -> resolver warps (window states of a finished unit)
+  uint64_t* x_empty = x_full + 2;                // [2] resolver -> epilogue
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SmemLayout::tmem_ptr);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -134,6 +136,7 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kEpiWarps); }
     for (int i = 0; i < kColStages; ++i) { mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], kEpiWarps); mbar_init(&x_empty[i], 2); }
     fence_mbar_init();
   }
   if (warp == 2) { tmem_alloc<kTmemCols>(tmem_ptr); tmem_relinquish(); }
@@ -237,6 +240,132 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         args.timing[blockIdx.x * 16 + 2] = clock64() - tm_total0;
       }
     }
+  } else if (warp == 2 || warp == 3) {
+    // =============================== resolver ===============================
+    // Exact evaluation of the recorded windows, off the epilogue's critical path: while the tensor pipe and the
+    // epilogue warps already work on the next unit, these two warps (64 queries each) turn (best score, window)
+    // into the reference's winner: 32 lanes = the 32 targets of the window = the 32 lanes of the reference's block
+    // (ref: src/MatchFactory.cu:1476-1492); exact integer d2 by dp4a, key (d2, f mod 32, f), warp-wide minimum.
+    // Two queries are in flight per iteration to overlap their global-memory latency.
+    const WinState* xch = reinterpret_cast<const WinState*>(smem + SmemLayout::xch);
+    const uint32_t rw = warp - 2;
+    uint32_t uparity = 0, uiter = 0;
+    const bool timing = args.timing != nullptr;
+    long long tr_wait = 0, tr_work = 0;
+    for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      const uint32_t qt = unit / args.n_splits, sp = unit % args.n_splits;
+      long long w0 = 0, w1 = 0;
+      if (timing) w0 = clock64();
+      mbar_wait(&x_full[uparity], (uiter >> 1) & 1);
+      if (timing) w1 = clock64();
+      uint64_t myA = kKeyNone, myB = kKeyNone;
+      for (uint32_t pair = 0; pair < 32; ++pair) {
+        uint64_t res[2];
+        WinState ms[2];
+        uint32_t qrows[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const uint32_t r = rw * 64 + pair * 2 + k;
+          qrows[k] = qt * kBM + r;
+          ms[k] = win_merge(xch[(uparity * 2 + 0) * kBM + r], xch[(uparity * 2 + 1) * kBM + r]);
+        }
+        // ---- first window of both queries: loads first, then the arithmetic ----
+        uint4 tv[2][8], qv[2][8];
+        int32_t tn[2], qn[2];
+        uint64_t fs[2];
+        bool ok[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const uint32_t qsafe = min(qrows[k], args.nq_pad - 1);
+          const uint64_t f = static_cast<uint64_t>(ms[k].w1) * kChunk + lane;
+          ok[k] = f < args.nt;
+          fs[k] = ok[k] ? f : 0;
+          const uint4* td = reinterpret_cast<const uint4*>(args.t_desc + fs[k] * kDescBytes);
+          const uint4* qd = reinterpret_cast<const uint4*>(args.q_desc + static_cast<uint64_t>(qsafe) * kDescBytes);
+#pragma unroll
+          for (int w = 0; w < 8; ++w) { tv[k][w] = __ldg(td + w); qv[k][w] = __ldg(qd + w); }
+          tn[k] = args.t_norm[fs[k]];
+          qn[k] = args.q_norm[qsafe];
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (kMask != SSRLCV_B200_MASK_NONE) {
+            const QueryMask qm = make_query_mask<kMask>(mp, args.q_loc[min(qrows[k], args.nq_pad - 1)]);
+            const float2 tl = args.t_loc[fs[k]];
+            if (mask_skips<kMask>(qm, tl.x, tl.y, mp.eps)) ok[k] = false;
+          }
+          uint32_t dot = 0;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) {
+            dot = __dp4a(qv[k][w].x, tv[k][w].x, dot); dot = __dp4a(qv[k][w].y, tv[k][w].y, dot);
+            dot = __dp4a(qv[k][w].z, tv[k][w].z, dot); dot = __dp4a(qv[k][w].w, tv[k][w].w, dot);
+          }
+          const uint32_t d2 = static_cast<uint32_t>(qn[k] + tn[k] - 2 * static_cast<int32_t>(dot));
+          res[k] = ok[k] ? make_key(d2, fs[k] + args.target_offset) : kKeyNone;
+        }
+        // ---- rare: a second window reached the same score ----
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (ms[k].w2 != kNoWin && ms[k].best > 1) {               // warp-uniform
+            const uint64_t f = static_cast<uint64_t>(ms[k].w2) * kChunk + lane;
+            bool ok2 = f < args.nt;
+            if (ok2 && kMask != SSRLCV_B200_MASK_NONE) {
+              const QueryMask qm = make_query_mask<kMask>(mp, args.q_loc[min(qrows[k], args.nq_pad - 1)]);
+              const float2 tl = args.t_loc[f];
+              if (mask_skips<kMask>(qm, tl.x, tl.y, mp.eps)) ok2 = false;
+            }
+            if (ok2) {
+              const uint4* td = reinterpret_cast<const uint4*>(args.t_desc + f * kDescBytes);
+              uint32_t dot = 0;
+#pragma unroll
+              for (int w = 0; w < 8; ++w) {
+                const uint4 b4 = __ldg(td + w);
+                dot = __dp4a(qv[k][w].x, b4.x, dot); dot = __dp4a(qv[k][w].y, b4.y, dot);
+                dot = __dp4a(qv[k][w].z, b4.z, dot); dot = __dp4a(qv[k][w].w, b4.w, dot);
+              }
+              const uint32_t d2 = static_cast<uint32_t>(qn[k] + args.t_norm[f] - 2 * static_cast<int32_t>(dot));
+              const uint64_t k2 = make_key(d2, f + args.target_offset);
+              res[k] = k2 < res[k] ? k2 : res[k];
+            }
+          }
+        }
+        // ---- warp-wide minima of both queries, interleaved ----
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const uint32_t lo = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(res[k]), o);
+            const uint32_t hi = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(res[k] >> 32), o);
+            const uint64_t other = (static_cast<uint64_t>(hi) << 32) | lo;
+            res[k] = other < res[k] ? other : res[k];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (ms[k].best <= 1) res[k] = kKeyNone;
+          else if (ms[k].ovf) {
+            res[k] = kKeyNeedsExact;
+            if (lane == 0 && qrows[k] < args.nq) {
+              const uint32_t slot = atomicAdd(args.n_flagged, 1u);
+              args.flagged[slot] = sp * args.nq_pad + qrows[k];
+            }
+          }
+        }
+        if (lane == pair) { myA = res[0]; myB = res[1]; }
+      }
+      // rows [rw*64 + 2*lane, +2): one 16-byte store per lane (rows beyond nq land in the padding of the key array)
+      {
+        const uint32_t orow = qt * kBM + rw * 64 + 2 * lane;
+        uint64_t* dst = args.keys + static_cast<uint64_t>(sp) * args.nq_pad + orow;
+        *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2(myA, myB);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&x_empty[uparity]);
+      uparity ^= 1;
+      ++uiter;
+      if (timing) { const long long w2 = clock64(); tr_wait += w1 - w0; tr_work += w2 - w1; }
+    }
+    if (timing && lane == 0 && rw == 0) { args.timing[blockIdx.x * 16 + 12] = tr_wait; args.timing[blockIdx.x * 16 + 13] = tr_work; }
   } else if (warp >= 4) {
     // =============================== epilogue ===============================
     const uint32_t quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32)
@@ -245,7 +374,7 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     constexpr uint32_t kWinPerTile = kBN / kChunk;     // 8
     constexpr uint32_t kWinPerWarp = kWinPerTile / 2;  // 4
     WinState* xch = reinterpret_cast<WinState*>(smem + SmemLayout::xch);
-    uint32_t acc = 0, accphase = 0, cs = 0, cphase = 0, uparity = 0;
+    uint32_t acc = 0, accphase = 0, cs = 0, cphase = 0, uparity = 0, uiter = 0;
     const bool timing = args.timing != nullptr;
     long long te_wait = 0, te_work = 0, te_resolve = 0, te_total0 = clock64();
     for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -338,76 +467,13 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
       }
       long long r0 = 0;
       if (timing) r0 = clock64();
-
-      // ---------------- merge the two column halves, then resolve the recorded windows exactly ----------------
+      // ---------------- hand the window states of this unit to the resolver warps ----------------
+      mbar_wait(&x_empty[uparity], ((uiter >> 1) & 1) ^ 1);
       xch[(uparity * 2 + half) * kBM + quarter * 32 + lane] = st;
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-      // lane = (window slot, query): lanes 0-15 take the first recorded window of 16 queries, lanes 16-31 the second one
-      // (if any).  Each lane walks the 32 targets of its window with independent loads in flight, so the exact
-      // resolve costs one pass of memory latency per unit instead of one per query.
-      {
-        const uint32_t r_begin = half * 16;
-        const uint32_t rl = lane & 15, which = lane >> 4;
-        const uint32_t r = r_begin + rl;
-        const uint32_t qrow = qt * kBM + quarter * 32 + r;
-        const WinState m = win_merge(xch[(uparity * 2 + 0) * kBM + quarter * 32 + r], xch[(uparity * 2 + 1) * kBM + quarter * 32 + r]);
-        QueryMask qr;
-        if (kMask != SSRLCV_B200_MASK_NONE) {
-          // the per-query mask state lives in the thread that owns row r (same lane index in both warps of a quarter)
-          qr.seg.lo_x = __shfl_sync(0xffffffffu, qm.seg.lo_x, r);   qr.seg.hi_x = __shfl_sync(0xffffffffu, qm.seg.hi_x, r);
-          qr.seg.left_x = __shfl_sync(0xffffffffu, qm.seg.left_x, r); qr.seg.left_y = __shfl_sync(0xffffffffu, qm.seg.left_y, r);
-          qr.seg.slope = __shfl_sync(0xffffffffu, qm.seg.slope, r);  qr.seg.top_lo = __shfl_sync(0xffffffffu, qm.seg.top_lo, r);
-          qr.seg.bot_hi = __shfl_sync(0xffffffffu, qm.seg.bot_hi, r); qr.seg.vertical = __shfl_sync(0xffffffffu, qm.seg.vertical, r);
-          qr.line.ex = __shfl_sync(0xffffffffu, qm.line.ex, r); qr.line.ey = __shfl_sync(0xffffffffu, qm.line.ey, r);
-          qr.line.ez = __shfl_sync(0xffffffffu, qm.line.ez, r);
-        }
-        uint64_t key = kKeyNone;
-        const bool live = qrow < args.nq && m.best > 1;
-        const uint32_t win = which == 0 ? m.w1 : m.w2;
-        if (live && !m.ovf && win != kNoWin) {
-          const uint4* qd = reinterpret_cast<const uint4*>(args.q_desc + static_cast<uint64_t>(qrow) * kDescBytes);
-          uint4 qv[8];
-#pragma unroll
-          for (int w = 0; w < 8; ++w) qv[w] = __ldg(qd + w);
-          const int32_t qn = args.q_norm[qrow];
-          const uint64_t f0 = static_cast<uint64_t>(win) * kChunk;
-#pragma unroll 2
-          for (uint32_t i = 0; i < kChunk; ++i) {
-            const uint64_t f = f0 + i;
-            if (f >= args.nt) break;
-            if (kMask != SSRLCV_B200_MASK_NONE) {
-              const float2 tl = args.t_loc[f];
-              if (mask_skips<kMask>(qr, tl.x, tl.y, mp.eps)) continue;
-            }
-            const uint4* td = reinterpret_cast<const uint4*>(args.t_desc + f * kDescBytes);
-            uint32_t dot = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-              const uint4 b4 = __ldg(td + w);
-              dot = __dp4a(qv[w].x, b4.x, dot); dot = __dp4a(qv[w].y, b4.y, dot);
-              dot = __dp4a(qv[w].z, b4.z, dot); dot = __dp4a(qv[w].w, b4.w, dot);
-            }
-            const uint32_t d2 = static_cast<uint32_t>(qn + args.t_norm[f] - 2 * static_cast<int32_t>(dot));
-            const uint64_t k2 = make_key(d2, f + args.target_offset);
-            key = k2 < key ? k2 : key;
-          }
-        }
-        {  // fold the second window's result into the first
-          const uint32_t lo = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(key), 16);
-          const uint32_t hi = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(key >> 32), 16);
-          const uint64_t other = (static_cast<uint64_t>(hi) << 32) | lo;
-          key = other < key ? other : key;
-        }
-        if (which == 0 && qrow < args.nq) {
-          if (live && m.ovf) {
-            key = kKeyNeedsExact;
-            const uint32_t slot = atomicAdd(args.n_flagged, 1u);
-            args.flagged[slot] = sp * args.nq_pad + qrow;
-          }
-          args.keys[static_cast<uint64_t>(sp) * args.nq_pad + qrow] = key;
-        }
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&x_full[uparity]);
       uparity ^= 1;
+      ++uiter;
       if (timing) te_resolve += clock64() - r0;
     }
     if (timing && lane == 0) {

@@ -35,7 +35,7 @@ for it in range(3):
 torch.cuda.synchronize()
 x = tim.cpu().numpy().reshape(148, 16)
 names = ["mma:wait_t_empty", "mma:wait_full", "mma:total", "tma:wait_empty", "epi0:wait_t_full", "epi0:work", "epi0:resolve", "epi0:total",
-         "epi5:wait_t_full", "epi5:work", "epi5:resolve", "epi5:total"]
+         "epi5:wait_t_full", "epi5:work", "epi5:resolve", "epi5:total", "res0:wait", "res0:work"]
 for i, n in enumerate(names):
     col = x[:, i]
     print(f"{n:18s} mean {col.mean():12.0f}  min {col.min():12d}  max {col.max():12d}")
