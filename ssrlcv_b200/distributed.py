@@ -98,7 +98,8 @@ def match_target_sharded(candidates: Callable[[int, int, int], "object"], finali
     import torch
 
     b = shard_bounds(n_targets, world_size)
-    mine = candidates(b[rank], b[rank + 1], b[rank])
+    # an empty trailing shard starts at n_targets, which need not be lane-aligned: its offset is irrelevant, pass 0
+    mine = candidates(b[rank], b[rank + 1], b[rank] if b[rank + 1] > b[rank] else 0)
     if world_size > 1:
         allk = torch.empty((world_size, n_queries), dtype=mine.dtype, device=mine.device)
         dist.all_gather_into_tensor(allk, mine.contiguous()) if hasattr(dist, "all_gather_into_tensor") and mine.device.type == "cuda" else \
