@@ -318,41 +318,71 @@ static void fill_mask(const ssrlcv_b200_match_params* p, MaskParams& mp) {
   }
 }
 
-// choose the number of target splits so that (query tiles x splits) fills the SMs evenly
-static void plan(const ssrlcv_b200_ctx* ctx, uint32_t nq, uint32_t nt, SmaxArgs& a, int& grid) {
-  a.n_qtiles = (nq + kBM - 1) / kBM;
-  a.n_ttiles = (nt + kBN - 1) / kBN;
+// SIMT engine: fixed-length target splits so that (queries x splits) fills the device
+static void plan_simt(const ssrlcv_b200_ctx* ctx, SmaxArgs& a) {
   const uint32_t sms = static_cast<uint32_t>(ctx->sm_count);
-  if (a.n_ttiles == 0 || a.n_qtiles == 0) { a.tiles_per_split = 1; a.n_splits = 1; grid = 1; return; }
-  uint32_t best_s = 1;
-  double best_eff = 0.0;
-  const uint32_t max_s = a.n_ttiles < 64 ? (a.n_ttiles ? a.n_ttiles : 1) : 64;
-  for (uint32_t s = 1; s <= max_s; ++s) {
-    const uint32_t tps = (a.n_ttiles + s - 1) / s;
-    if (tps < 4 && s > 1) break;
-    const uint32_t real_s = (a.n_ttiles + tps - 1) / tps;
-    const uint64_t units = static_cast<uint64_t>(a.n_qtiles) * real_s;
-    const uint64_t waves = (units + sms - 1) / sms;
-    // per-unit fixed cost (A tile load, pipeline fill, resolve) ~ 3 tiles of work
-    const double eff = static_cast<double>(a.n_qtiles) * a.n_ttiles / (static_cast<double>(waves) * sms * (tps + 3.0));
-    if (eff > best_eff * 1.02) { best_eff = eff; best_s = s; }
-  }
-  a.tiles_per_split = (a.n_ttiles + best_s - 1) / best_s;
+  uint32_t s = 1;
+  while (static_cast<uint64_t>(a.nq) * s < 8ull * sms && s * 4 <= a.n_ttiles) s *= 2;
+  a.tiles_per_split = (a.n_ttiles + s - 1) / s;
   if (a.tiles_per_split == 0) a.tiles_per_split = 1;
   a.n_splits = a.n_ttiles ? (a.n_ttiles + a.tiles_per_split - 1) / a.tiles_per_split : 1;
-  const uint64_t units = static_cast<uint64_t>(a.n_qtiles) * a.n_splits;
-  grid = static_cast<int>(units < sms ? units : sms);
-  if (grid < 1) grid = 1;
+  a.n_ctas = 1;
+  a.total_tiles = static_cast<uint64_t>(a.n_qtiles) * a.n_ttiles;
+}
+
+// Tensor-core engine: cut the linearised (query tile, target tile) space into one contiguous, equally long range per
+// CTA (matcher.cuh).  Every SM gets the same number of tiles (+-1) whatever the shape; a query tile is shared by the
+// few CTAs whose ranges cross it, each writing its own key slot.
+static void plan_tc(const ssrlcv_b200_ctx* ctx, SmaxArgs& a, int& grid) {
+  const uint32_t sms = static_cast<uint32_t>(ctx->sm_count);
+  a.total_tiles = static_cast<uint64_t>(a.n_qtiles) * a.n_ttiles;
+  const uint64_t min_tiles = 4;                       // per-unit fixed cost (A tile, pipeline fill, resolve) ~ a few tiles
+  uint64_t g = a.total_tiles / min_tiles;
+  if (g < 1) g = 1;
+  if (g > sms) g = sms;
+  a.n_ctas = static_cast<uint32_t>(g);
+  a.tiles_per_split = a.n_ttiles;
+  uint32_t slots = 1;
+  if (a.total_tiles) {
+    const uint64_t per = a.total_tiles / a.n_ctas;    // shortest range
+    slots = static_cast<uint32_t>((a.n_ttiles + per - 1) / per) + 1;
+    if (slots > a.n_ctas) slots = a.n_ctas;
+    if (a.n_qtiles <= 8192) {                         // exact: the widest query tile
+      uint32_t widest = 1;
+      for (uint32_t qt = 0; qt < a.n_qtiles; ++qt) {
+        const uint64_t base = static_cast<uint64_t>(qt) * a.n_ttiles;
+        const uint32_t w = cta_of_tile(a.total_tiles, a.n_ctas, base + a.n_ttiles - 1) - cta_of_tile(a.total_tiles, a.n_ctas, base) + 1;
+        if (w > widest) widest = w;
+      }
+      slots = widest;
+    }
+  }
+  a.n_splits = slots;
+  grid = static_cast<int>(a.n_ctas);
+}
+
+// largest integer d2 with (float)d2 < abs_thr, i.e. that the reference's `d2 >= abs` test lets through
+// (ref: src/MatchFactory.cu:1472, :1494); INT32_MAX when the threshold cannot bind (d2 <= 128 * 255^2)
+static int32_t d2_cap_of(float abs_thr) {
+  if (!(abs_thr > 0.0f)) return -1;                   // also NaN: nothing passes
+  if (abs_thr > 8323200.0f) return 0x7fffffff;
+  const float c = ceilf(abs_thr);
+  return static_cast<int32_t>(c) - 1;
 }
 
 // runs the distance engine; leaves exact keys in ctx->keys ([n_splits][nq_pad])
 static int run_engine(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* q, const ssrlcv_b200_set* t, const MaskParams& mp, int engine,
-                      uint64_t target_offset, SmaxArgs& a) {
+                      uint64_t target_offset, float abs_thr, SmaxArgs& a) {
   memset(&a, 0, sizeof a);
   a.nq = static_cast<uint32_t>(q->n); a.nt = static_cast<uint32_t>(t->n); a.nq_pad = static_cast<uint32_t>(q->n_pad);
   a.target_offset = target_offset;
+  a.n_qtiles = (a.nq + kBM - 1) / kBM;
+  a.n_ttiles = (a.nt + kBN - 1) / kBN;
+  a.t_hmax = t->hmax;
+  a.d2_cap = d2_cap_of(abs_thr);
   int grid = 1;
-  plan(ctx, a.nq, a.nt, a, grid);
+  if (engine == SSRLCV_B200_ENGINE_SIMT || a.nq == 0 || a.nt == 0) plan_simt(ctx, a);
+  else plan_tc(ctx, a, grid);
   a.q_desc = q->desc; a.q_norm = q->norm; a.q_loc = q->loc;
   a.t_desc = t->desc; a.t_norm = t->norm; a.t_loc = t->loc; a.t_wcol = t->wcol;
   const size_t n_keys = static_cast<size_t>(a.n_splits) * a.nq_pad;
@@ -372,6 +402,8 @@ static int run_engine(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* q, const ssrl
     launch_exact(ctx->stream, a, mp, 0, ctx->sm_count);
     ctx->launches += 1;
   } else {
+    // key slots a query tile does not use stay "no candidate" (kKeyNone is all ones)
+    if (a.n_splits > 1) CU(cudaMemsetAsync(a.keys, 0xFF, n_keys * sizeof(uint64_t), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(uint32_t), ctx->stream));
     if (ctx->profiling) {
       if (ctx->prof_used == ctx->prof_events.size()) {
@@ -396,7 +428,7 @@ int ssrlcv_b200_seed_distances(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* quer
   CU(cudaSetDevice(ctx->device));
   MaskParams mp; memset(&mp, 0, sizeof mp);
   SmaxArgs a;
-  int rc = run_engine(ctx, query, seed, mp, engine, 0, a);
+  int rc = run_engine(ctx, query, seed, mp, engine, 0, FLT_MAX, a);
   if (rc) return rc;
   if (a.nq) { launch_seed_from_keys(ctx->stream, a.keys, a.nq, a.nq_pad, a.n_splits, out_dev); ctx->launches += 1; }
   CU(cudaGetLastError());
@@ -459,7 +491,7 @@ int ssrlcv_b200_match(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, c
     return fail(ctx, SSRLCV_B200_EINVAL, "the reference has no DoubleConstrained FeatureMatch kernel");
   MaskParams mp; fill_mask(p, mp);
   SmaxArgs a;
-  rc = run_engine(ctx, query, target, mp, p->engine, 0, a);
+  rc = run_engine(ctx, query, target, mp, p->engine, 0, p->absolute_threshold, a);
   if (rc) return rc;
   return finalize_common(ctx, p, query, a.keys, a.n_splits, target->loc, target, seed_dist_dev, out_dev, n_out);
 }
@@ -472,7 +504,7 @@ int ssrlcv_b200_match_candidates(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_p
   CU(cudaSetDevice(ctx->device));
   MaskParams mp; fill_mask(p, mp);
   SmaxArgs a;
-  rc = run_engine(ctx, query, shard, mp, p->engine, target_offset, a);
+  rc = run_engine(ctx, query, shard, mp, p->engine, target_offset, p->absolute_threshold, a);
   if (rc) return rc;
   if (a.nq) {
     // reduce the local splits to one key per query, reusing the seed kernel's min loop via finalize-free path

@@ -29,8 +29,23 @@ __global__ void __launch_bounds__(256) exact_kernel(SmaxArgs a, MaskParams mp, i
   const uint32_t total = use_list ? *a.n_flagged : a.n_splits * a.nq;
   for (uint32_t item = blockIdx.x; item < total; item += gridDim.x) {
     uint32_t split, row;
-    if (use_list) { const uint32_t e = a.flagged[item]; split = e / a.nq_pad; row = e % a.nq_pad; }
-    else { split = item / a.nq; row = item % a.nq; }
+    uint64_t f_begin, f_end;
+    if (use_list) {
+      // entry = key slot * nq_pad + row; the slot's target range is the tensor-core kernel's unit (matcher.cuh)
+      const uint32_t e = a.flagged[item];
+      split = e / a.nq_pad; row = e % a.nq_pad;
+      const uint32_t qt = row / kBM;
+      const uint32_t cta = cta_of_tile(a.total_tiles, a.n_ctas, static_cast<uint64_t>(qt) * a.n_ttiles) + split;
+      uint32_t j0, j1;
+      unit_range(a, cta, qt, j0, j1);
+      f_begin = static_cast<uint64_t>(j0) * kBN;
+      f_end = static_cast<uint64_t>(j1) * kBN;
+    } else {
+      split = item / a.nq; row = item % a.nq;
+      f_begin = static_cast<uint64_t>(split) * a.tiles_per_split * kBN;
+      f_end = f_begin + static_cast<uint64_t>(a.tiles_per_split) * kBN;
+    }
+    if (f_end > a.nt) f_end = a.nt;
     const uint4* qd = reinterpret_cast<const uint4*>(a.q_desc + static_cast<uint64_t>(row) * kDescBytes);
     uint4 q[8];
 #pragma unroll
@@ -38,9 +53,6 @@ __global__ void __launch_bounds__(256) exact_kernel(SmaxArgs a, MaskParams mp, i
     const int32_t qn = a.q_norm[row];
     QueryMask qm;
     if (kMask != SSRLCV_B200_MASK_NONE) qm = make_query_mask<kMask>(mp, a.q_loc[row]);
-    const uint64_t f_begin = static_cast<uint64_t>(split) * a.tiles_per_split * kBN;
-    uint64_t f_end = f_begin + static_cast<uint64_t>(a.tiles_per_split) * kBN;
-    if (f_end > a.nt) f_end = a.nt;
     uint64_t best = kKeyNone;
     for (uint64_t f = f_begin + threadIdx.x; f < f_end; f += 256) {     // f % 32 == lane for every f of this thread
       if (kMask != SSRLCV_B200_MASK_NONE) {

@@ -95,16 +95,39 @@ struct SmaxArgs {
   uint32_t nq_pad;
   uint32_t n_qtiles;             // ceil(nq / kBM)
   uint32_t n_ttiles;             // ceil(nt / kBN)
-  uint32_t n_splits;             // target range split count
-  uint32_t tiles_per_split;
+  uint32_t n_splits;             // key slots per query: keys is [n_splits][nq_pad]
+  uint32_t tiles_per_split;      // SIMT engine only: fixed-length target splits, slot = split
+  // tensor-core engine: the linearised tile space L = qtile * n_ttiles + ttile is cut into n_ctas equal contiguous
+  // ranges (one per CTA); a "unit" is the part of a CTA's range inside one query tile, and writes key slot
+  // (cta - first cta touching that query tile).  Balanced to one tile, whatever the shape.
+  uint32_t n_ctas;
+  uint64_t total_tiles;
+  int32_t  t_hmax;               // max over targets of |b|^2 >> 1 (the W offset)
+  int32_t  d2_cap;               // largest integer d2 that still passes the absolute threshold; INT32_MAX = no threshold
   uint64_t target_offset;        // global index of target 0 of this set (sharded mode)
   const uint8_t* q_desc; const int32_t* q_norm; const float2* q_loc;
   const uint8_t* t_desc; const int32_t* t_norm; const float2* t_loc; const int32_t* t_wcol;
   uint64_t* keys;                // [n_splits][nq_pad]
-  uint32_t* flagged;             // list of (split * nq_pad + row) needing the exact kernel
+  uint32_t* flagged;             // list of (slot * nq_pad + row) needing the exact kernel
   uint32_t* n_flagged;
   unsigned long long* timing;    // optional [gridDim.x][16] cycle counters (diagnostics), or nullptr
 };
+
+__host__ __device__ __forceinline__ uint64_t cta_tile_begin(uint64_t total, uint32_t n_ctas, uint32_t c) {
+  return (total * c) / n_ctas;
+}
+// the CTA whose range contains linear tile X
+__host__ __device__ __forceinline__ uint32_t cta_of_tile(uint64_t total, uint32_t n_ctas, uint64_t X) {
+  return static_cast<uint32_t>(((X + 1) * n_ctas - 1) / total);
+}
+// target tile range [j0, j1) of the unit (cta, qt); empty if the CTA does not touch that query tile
+__host__ __device__ __forceinline__ void unit_range(const SmaxArgs& a, uint32_t cta, uint32_t qt, uint32_t& j0, uint32_t& j1) {
+  const uint64_t lo = cta_tile_begin(a.total_tiles, a.n_ctas, cta), hi = cta_tile_begin(a.total_tiles, a.n_ctas, cta + 1);
+  const uint64_t base = static_cast<uint64_t>(qt) * a.n_ttiles;
+  const uint64_t b = lo > base ? lo : base, e = hi < base + a.n_ttiles ? hi : base + a.n_ttiles;
+  if (b >= e) { j0 = j1 = 0; return; }
+  j0 = static_cast<uint32_t>(b - base); j1 = static_cast<uint32_t>(e - base);
+}
 
 }  // namespace b200
 

@@ -139,6 +139,38 @@ def test_absolute_threshold_is_strict(api):
     assert T.fields_equal(got, want) and got["distance"].max() < thr
 
 
+@pytest.mark.parametrize("thr_kind", ["fraction", "below_all", "median", "median_plus_half", "tiny", "zero", "huge"])
+def test_threshold_floor_never_prunes_a_valid_winner(api, thr_kind):
+    """The tensor-core kernel starts every query at the lowest score that can still pass `d2 < abs` (smax_tc.cu); the
+    winners must stay those of the reference for thresholds on, between and outside the distances that occur
+    (ref: src/MatchFactory.cu:1472, :1494)."""
+    q, t = synth.make_pair(700, 2600, seed=77)
+    bd, _, _ = api.O.match_winners(api.O.make_params(), q, t)
+    s = np.sort(bd)
+    thr = {"fraction": float(s[300]) + 0.25, "below_all": float(s[0]), "median": float(s[350]), "median_plus_half": float(s[350]) + 0.5,
+           "tiny": 1.0e-3, "zero": 0.0, "huge": 8323200.0}[thr_kind]
+    mf = api.MatchFactory(1.0, thr)
+    for kind, fn in ((T.OUT_DMATCH, mf.generateDistanceMatches), (T.OUT_PAIR, mf.generateMatchesIndexOnly)):
+        out = fn(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t))
+        want = api.O.generate_matches(api.O.make_params(out_kind=kind, abs_threshold=thr), q, t)
+        if len(want):                           # (all invalid: the reference keeps the uncompacted array, checked elsewhere)
+            assert T.fields_equal(out.to_numpy(), want)
+    if thr_kind in ("median", "fraction"):
+        assert 0 < len(want) < len(q)
+
+
+@pytest.mark.parametrize("nq,nt", [(300, 20000), (130, 70000), (2000, 300), (640, 1024 + 7)])
+def test_query_tiles_shared_by_many_ctas(api, nq, nt):
+    """Shapes where the per-CTA tile ranges cut query tiles into many units (several key slots per query), with
+    duplicates and planted matches spread over the whole target range."""
+    q, t = synth.make_pair(nq, nt, seed=nq * 7 + nt, dup=0.01)
+    for thr in (FLT_MAX, 45000.0):
+        mf = api.MatchFactory(1.0, thr)
+        got = mf.generateDistanceMatches(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t)).to_numpy()
+        want = api.O.generate_matches(api.O.make_params(out_kind=T.OUT_DMATCH, abs_threshold=thr), q, t)
+        assert len(want) and T.fields_equal(got, want)
+
+
 def test_memory_states_restored(api):
     q, t = synth.make_pair(300, 400, seed=1)
     qu, tu = _unity(api, q, api.both), _unity(api, t, api.cpu)
