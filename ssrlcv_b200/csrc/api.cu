@@ -22,6 +22,7 @@ cudaError_t launch_smax(cudaStream_t, int, const ssrlcv_b200_set_impl&, const ss
 // exact.cu
 void launch_exact(cudaStream_t, const SmaxArgs&, const MaskParams&, int, int);
 void launch_endpoints(cudaStream_t, const MaskParams&, const float2*, uint64_t, float4*);
+void launch_query_masks(cudaStream_t, const MaskParams&, const float2*, uint64_t, float4*);
 void launch_sincos(cudaStream_t, const float*, uint64_t, float*, float*);
 // finalize.cu
 struct FinalizeArgs {
@@ -70,7 +71,7 @@ struct ssrlcv_b200_ctx {
   EncodeTiledFn encode = nullptr;
   std::string err;
   uint64_t launches = 0;
-  Workspace keys, flagged, counts, scratch, hostpin;
+  Workspace keys, flagged, counts, scratch, hostpin, qmask;
   uint32_t* d_scalars = nullptr;   // [0] n_flagged, [1] total, [2..3] hmin/hmax staging
   uint32_t* h_scalars = nullptr;   // pinned mirror
   bool profiling = false;
@@ -146,7 +147,7 @@ void ssrlcv_b200_destroy(ssrlcv_b200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (Workspace* w : {&ctx->keys, &ctx->flagged, &ctx->counts, &ctx->scratch}) if (w->p) cudaFree(w->p);
+  for (Workspace* w : {&ctx->keys, &ctx->flagged, &ctx->counts, &ctx->scratch, &ctx->qmask}) if (w->p) cudaFree(w->p);
   if (ctx->hostpin.p) cudaFreeHost(ctx->hostpin.p);
   if (ctx->d_scalars) cudaFree(ctx->d_scalars);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
@@ -381,6 +382,8 @@ static int run_engine(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* q, const ssrl
   a.t_hmax = t->hmax;
   a.d2_cap = d2_cap_of(abs_thr);
   int grid = 1;
+  if (static_cast<uint64_t>(a.n_qtiles) * a.n_ttiles >= (1ull << 32))
+    return fail(ctx, SSRLCV_B200_EINVAL, "%u x %u features is too large for one call: shard the target set (ssrlcv_b200_match_candidates)", a.nq, a.nt);
   if (engine == SSRLCV_B200_ENGINE_SIMT || a.nq == 0 || a.nt == 0) plan_simt(ctx, a);
   else plan_tc(ctx, a, grid);
   a.q_desc = q->desc; a.q_norm = q->norm; a.q_loc = q->loc;
@@ -397,6 +400,13 @@ static int run_engine(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* q, const ssrl
     a.timing = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 16));
   }
   if (a.nq == 0) return 0;
+  if (mp.kind != SSRLCV_B200_MASK_NONE && a.nt != 0) {      // per-query mask state, once per call (all padded rows: loc = 0 there)
+    rc = ws_reserve(ctx, ctx->qmask, static_cast<size_t>(a.nq_pad) * 2 * sizeof(float4));
+    if (rc) return rc;
+    launch_query_masks(ctx->stream, mp, q->loc, a.nq_pad, static_cast<float4*>(ctx->qmask.p));
+    a.q_mask = static_cast<const float4*>(ctx->qmask.p);
+    ctx->launches += 1;
+  }
   if (a.nt == 0) { launch_fill_u64(ctx->stream, a.keys, n_keys, kKeyNone); ctx->launches += 1; return 0; }
   if (engine == SSRLCV_B200_ENGINE_SIMT) {
     launch_exact(ctx->stream, a, mp, 0, ctx->sm_count);

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) exact_kernel(SmaxArgs a, MaskParams mp, i
     for (int i = 0; i < 8; ++i) q[i] = __ldg(qd + i);
     const int32_t qn = a.q_norm[row];
     QueryMask qm;
-    if (kMask != SSRLCV_B200_MASK_NONE) qm = make_query_mask<kMask>(mp, a.q_loc[row]);
+    if (kMask != SSRLCV_B200_MASK_NONE) qm = load_query_mask<kMask>(a.q_mask + 2 * static_cast<uint64_t>(row));
     uint64_t best = kKeyNone;
     for (uint64_t f = f_begin + threadIdx.x; f < f_end; f += 256) {     // f % 32 == lane for every f of this thread
       if (kMask != SSRLCV_B200_MASK_NONE) {
@@ -91,6 +91,20 @@ void launch_exact(cudaStream_t st, const SmaxArgs& a, const MaskParams& mp, int 
     case SSRLCV_B200_MASK_FUNDAMENTAL: exact_kernel<SSRLCV_B200_MASK_FUNDAMENTAL><<<blocks, 256, 0, st>>>(a, mp, use_list); break;
     default: exact_kernel<SSRLCV_B200_MASK_DOUBLE><<<blocks, 256, 0, st>>>(a, mp, use_list); break;
   }
+}
+
+// ---- per-query mask prologue ---------------------------------------------------------------------
+template <int kMask>
+__global__ void __launch_bounds__(128) query_mask_kernel(MaskParams mp, const float2* __restrict__ loc, uint64_t n, float4* __restrict__ out) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  store_query_mask<kMask>(out + 2 * i, make_query_mask<kMask>(mp, loc[i]));
+}
+void launch_query_masks(cudaStream_t st, const MaskParams& mp, const float2* loc, uint64_t n, float4* out) {
+  if (n == 0 || mp.kind == SSRLCV_B200_MASK_NONE) return;
+  const unsigned blocks = static_cast<unsigned>((n + 127) / 128);
+  if (mp.kind == SSRLCV_B200_MASK_DOUBLE) query_mask_kernel<SSRLCV_B200_MASK_DOUBLE><<<blocks, 128, 0, st>>>(mp, loc, n, out);
+  else query_mask_kernel<SSRLCV_B200_MASK_FUNDAMENTAL><<<blocks, 128, 0, st>>>(mp, loc, n, out);
 }
 
 // ---- small diagnostics kernels -----------------------------------------------------------------

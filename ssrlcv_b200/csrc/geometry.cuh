@@ -145,4 +145,31 @@ __device__ __forceinline__ bool mask_skips(const QueryMask& m, float tx, float t
   return false;
 }
 
+// The per-query mask state is computed once per call by a prologue kernel (the trigonometry of getEpipolarEndpoints is
+// ~10^3 instructions) and stored as two float4 per query; the matcher kernels only load it.
+template <int kMask>
+__device__ __forceinline__ void store_query_mask(float4* dst, const QueryMask& m) {
+  if (kMask == SSRLCV_B200_MASK_DOUBLE) {
+    dst[0] = make_float4(m.seg.lo_x, m.seg.hi_x, m.seg.left_x, m.seg.left_y);
+    dst[1] = make_float4(m.seg.slope, m.seg.top_lo, m.seg.bot_hi, __int_as_float(m.seg.vertical));
+  } else {
+    dst[0] = make_float4(m.line.ex, m.line.ey, m.line.ez, 0.f);
+    dst[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+template <int kMask>
+__device__ __forceinline__ QueryMask load_query_mask(const float4* src) {
+  QueryMask m;
+  if (kMask == SSRLCV_B200_MASK_DOUBLE) {
+    const float4 a = src[0], b = src[1];
+    m.seg.lo_x = a.x; m.seg.hi_x = a.y; m.seg.left_x = a.z; m.seg.left_y = a.w;
+    m.seg.slope = b.x; m.seg.top_lo = b.y; m.seg.bot_hi = b.z; m.seg.vertical = __float_as_int(b.w);
+  }
+  if (kMask == SSRLCV_B200_MASK_FUNDAMENTAL) {
+    const float4 a = src[0];
+    m.line.ex = a.x; m.line.ey = a.y; m.line.ez = a.z;
+  }
+  return m;
+}
+
 }  // namespace b200

@@ -106,6 +106,7 @@ struct SmaxArgs {
   int32_t  d2_cap;               // largest integer d2 that still passes the absolute threshold; INT32_MAX = no threshold
   uint64_t target_offset;        // global index of target 0 of this set (sharded mode)
   const uint8_t* q_desc; const int32_t* q_norm; const float2* q_loc;
+  const float4* q_mask;          // [nq_pad][2] per-query epipolar mask state (geometry.cuh), masked modes only
   const uint8_t* t_desc; const int32_t* t_norm; const float2* t_loc; const int32_t* t_wcol;
   uint64_t* keys;                // [n_splits][nq_pad]
   uint32_t* flagged;             // list of (slot * nq_pad + row) needing the exact kernel

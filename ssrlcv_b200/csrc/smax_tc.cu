@@ -113,23 +113,146 @@ __device__ __forceinline__ uint64_t warp_min_u64_tc(uint64_t v) {
   return v;
 }
 
+__device__ __forceinline__ uint32_t word_of(const uint4 (&v)[8], int w) {
+  const uint4 q = v[w >> 2];
+  return (w & 3) == 0 ? q.x : (w & 3) == 1 ? q.y : (w & 3) == 2 ? q.z : q.w;
+}
+
+// Exact resolution of recorded windows: turns (best score, window) into the reference's winner.  One warp, four queries
+// in flight: lane l owns target l of each query's window (32 lanes = the 32 targets of the window = the 32 lanes of the
+// reference's block, ref: src/MatchFactory.cu:1476-1492) and holds its 128 descriptor bytes in registers; the query
+// descriptor is spread one 32-bit word per lane and broadcast by shuffle.  Exact integer d2 by dp4a, key
+// (d2, f mod 32, f), warp-wide minimum.  Rows [r_begin, r_begin + r_count) of the query tile, r_count % 4 == 0.
+template <int kMask, int kFly>
+__device__ __forceinline__ void resolve_rows(const SmaxArgs& args, const MaskParams& mp, const WinState* xa, const WinState* xb,
+                                             uint32_t qt, uint32_t slot, uint32_t r_begin, uint32_t r_count, int lane) {
+  constexpr uint32_t kFull = 0xffffffffu;
+  for (uint32_t g = 0; g < r_count; g += kFly) {
+    WinState ms[kFly];
+    uint32_t qrow[kFly];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < kFly; ++k) {
+      const uint32_t r = r_begin + g + k;
+      ms[k] = win_merge(xa[r], xb[r]);
+      qrow[k] = min(qt * kBM + r, args.nq_pad - 1);
+      any |= ms[k].w1 != kNoWin;
+    }
+    uint64_t res[kFly];
+#pragma unroll
+    for (int k = 0; k < kFly; ++k) res[k] = kKeyNone;
+    if (any) {                                                   // warp-uniform: every lane read the same states
+      uint4 tv[kFly][8];
+      uint32_t qw[kFly];
+      int32_t tn[kFly], qn[kFly];
+      uint64_t fs[kFly];
+      bool ok[kFly];
+#pragma unroll
+      for (int k = 0; k < kFly; ++k) {                              // all loads first
+        const uint32_t w = ms[k].w1 == kNoWin ? 0u : ms[k].w1;
+        const uint64_t f = static_cast<uint64_t>(w) * kChunk + lane;
+        ok[k] = (f < args.nt) & (ms[k].w1 != kNoWin);
+        fs[k] = ok[k] ? f : 0;
+        const uint4* td = reinterpret_cast<const uint4*>(args.t_desc + fs[k] * kDescBytes);
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) tv[k][w8] = __ldg(td + w8);
+        qw[k] = __ldg(reinterpret_cast<const uint32_t*>(args.q_desc + static_cast<uint64_t>(qrow[k]) * kDescBytes) + lane);
+        tn[k] = __ldg(args.t_norm + fs[k]);
+        qn[k] = __ldg(args.q_norm + qrow[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < kFly; ++k) {
+        if (kMask != SSRLCV_B200_MASK_NONE) {
+          const QueryMask qm = load_query_mask<kMask>(args.q_mask + 2 * static_cast<uint64_t>(qrow[k]));
+          const float2 tl = args.t_loc[fs[k]];
+          if (mask_skips<kMask>(qm, tl.x, tl.y, mp.eps)) ok[k] = false;
+        }
+        uint32_t dot = 0;
+#pragma unroll
+        for (int w = 0; w < 32; ++w) dot = __dp4a(__shfl_sync(kFull, qw[k], w), word_of(tv[k], w), dot);
+        const uint32_t d2 = static_cast<uint32_t>(qn[k] + tn[k] - 2 * static_cast<int32_t>(dot));
+        res[k] = ok[k] ? make_key(d2, fs[k] + args.target_offset) : kKeyNone;
+      }
+      // ---- rare: a second window reached the same score ----
+#pragma unroll
+      for (int k = 0; k < kFly; ++k) {
+        if (ms[k].w1 != kNoWin && ms[k].w2 != kNoWin) {          // warp-uniform
+          const uint64_t f = static_cast<uint64_t>(ms[k].w2) * kChunk + lane;
+          bool ok2 = f < args.nt;
+          const uint64_t f2 = ok2 ? f : 0;
+          if (kMask != SSRLCV_B200_MASK_NONE) {
+            const QueryMask qm = load_query_mask<kMask>(args.q_mask + 2 * static_cast<uint64_t>(qrow[k]));
+            const float2 tl = args.t_loc[f2];
+            if (mask_skips<kMask>(qm, tl.x, tl.y, mp.eps)) ok2 = false;
+          }
+          const uint4* td = reinterpret_cast<const uint4*>(args.t_desc + f2 * kDescBytes);
+          uint32_t dot = 0;
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) {
+            const uint4 b4 = __ldg(td + w8);
+            dot = __dp4a(__shfl_sync(kFull, qw[k], 4 * w8 + 0), b4.x, dot);
+            dot = __dp4a(__shfl_sync(kFull, qw[k], 4 * w8 + 1), b4.y, dot);
+            dot = __dp4a(__shfl_sync(kFull, qw[k], 4 * w8 + 2), b4.z, dot);
+            dot = __dp4a(__shfl_sync(kFull, qw[k], 4 * w8 + 3), b4.w, dot);
+          }
+          const uint32_t d2 = static_cast<uint32_t>(qn[k] + __ldg(args.t_norm + f2) - 2 * static_cast<int32_t>(dot));
+          const uint64_t k2 = ok2 ? make_key(d2, f2 + args.target_offset) : kKeyNone;
+          res[k] = k2 < res[k] ? k2 : res[k];
+        }
+      }
+      // ---- warp-wide minima of the queries in flight, interleaved ----
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < kFly; ++k) {
+          const uint32_t lo = __shfl_xor_sync(kFull, static_cast<uint32_t>(res[k]), o);
+          const uint32_t hi = __shfl_xor_sync(kFull, static_cast<uint32_t>(res[k] >> 32), o);
+          const uint64_t other = (static_cast<uint64_t>(hi) << 32) | lo;
+          res[k] = other < res[k] ? other : res[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kFly; ++k) {
+        if (ms[k].w1 == kNoWin) res[k] = kKeyNone;
+        else if (ms[k].ovf) {                                    // three or more windows tied: exact SIMT kernel
+          res[k] = kKeyNeedsExact;
+          const uint32_t row = qt * kBM + r_begin + g + k;
+          if (lane == 0 && row < args.nq) {
+            const uint32_t at = atomicAdd(args.n_flagged, 1u);
+            args.flagged[at] = slot * args.nq_pad + row;
+          }
+        }
+      }
+    }
+    // rows beyond nq land in the padding of the key array
+    if (lane < kFly) {
+      uint64_t mine = res[0];
+#pragma unroll
+      for (int k = 1; k < kFly; ++k) mine = lane == k ? res[k] : mine;
+      args.keys[static_cast<uint64_t>(slot) * args.nq_pad + qt * kBM + r_begin + g + lane] = mine;
+    }
+  }
+}
+
 // Iterates the units of one CTA: the parts of its contiguous tile range that fall inside one query tile.
 struct UnitIter {
-  uint64_t L, L_end;
-  uint32_t n_tt, qt, j0, j1, slot;
+  uint32_t L, L_end;                           // linear tile indices (the host guarantees total_tiles < 2^32)
+  uint32_t qt, j0, j1, slot;
+  bool last;                                   // the CTA's final unit
   __device__ __forceinline__ UnitIter(const SmaxArgs& a, uint32_t cta) {
-    L = cta_tile_begin(a.total_tiles, a.n_ctas, cta);
-    L_end = cta_tile_begin(a.total_tiles, a.n_ctas, cta + 1);
-    n_tt = a.n_ttiles;
+    L = static_cast<uint32_t>(cta_tile_begin(a.total_tiles, a.n_ctas, cta));
+    L_end = static_cast<uint32_t>(cta_tile_begin(a.total_tiles, a.n_ctas, cta + 1));
   }
   __device__ __forceinline__ bool next(const SmaxArgs& a, uint32_t cta) {
     if (L >= L_end) return false;
-    qt = static_cast<uint32_t>(L / n_tt);
-    j0 = static_cast<uint32_t>(L - static_cast<uint64_t>(qt) * n_tt);
-    const uint64_t room = L_end - L;
-    j1 = (n_tt - j0 <= room) ? n_tt : j0 + static_cast<uint32_t>(room);
+    const uint32_t n_tt = a.n_ttiles;
+    qt = L / n_tt;
+    j0 = L - qt * n_tt;
+    const uint32_t room = L_end - L;
+    j1 = (n_tt - j0 <= room) ? n_tt : j0 + room;
     slot = cta - cta_of_tile(a.total_tiles, a.n_ctas, static_cast<uint64_t>(qt) * n_tt);
     L += j1 - j0;
+    last = L >= L_end;
     return true;
   }
 };
@@ -267,128 +390,21 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     }
   } else if (warp == 2 || warp == 3) {
     // =============================== resolver ===============================
-    // Exact evaluation of the recorded windows, off the epilogue's critical path: while the tensor pipe and the
-    // epilogue warps already work on the next unit, these two warps (64 queries each) turn (best score, window)
-    // into the reference's winner: 32 lanes = the 32 targets of the window = the 32 lanes of the reference's block
-    // (ref: src/MatchFactory.cu:1476-1492); exact integer d2 by dp4a, key (d2, f mod 32, f), warp-wide minimum.
-    // Two queries are in flight per iteration to overlap their global-memory latency.
+    // Exact evaluation of the recorded windows (resolve_rows), off the epilogue's critical path: while the tensor pipe
+    // and the epilogue warps already work on the next unit, these two warps (64 queries each) finish the previous one.
+    // The CTA's last unit has nothing to overlap with and is resolved by the eight epilogue warps themselves.
     const WinState* xch = reinterpret_cast<const WinState*>(smem + SmemLayout::xch);
     const uint32_t rw = warp - 2;
     uint32_t uparity = 0, uiter = 0;
     long long tr_wait = 0, tr_work = 0;
     UnitIter u(args, blockIdx.x);
     while (u.next(args, blockIdx.x)) {
-      const uint32_t qt = u.qt, sp = u.slot;
+      if (u.last) break;
       long long w0 = 0, w1 = 0;
       if (kTiming) w0 = clock64();
       mbar_wait(&x_full[uparity], (uiter >> 1) & 1);
       if (kTiming) w1 = clock64();
-      uint64_t myA = kKeyNone, myB = kKeyNone;
-      for (uint32_t pair = 0; pair < 32; ++pair) {
-        uint64_t res[2];
-        WinState ms[2];
-        uint32_t qrows[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const uint32_t r = rw * 64 + pair * 2 + k;
-          qrows[k] = qt * kBM + r;
-          ms[k] = win_merge(xch[(uparity * 2 + 0) * kBM + r], xch[(uparity * 2 + 1) * kBM + r]);
-        }
-        if (ms[0].w1 == kNoWin && ms[1].w1 == kNoWin) {            // warp-uniform: nothing passed the threshold bound
-          if (lane == pair) { myA = kKeyNone; myB = kKeyNone; }
-          continue;
-        }
-        // ---- first window of both queries: loads first, then the arithmetic ----
-        uint4 tv[2][8], qv[2][8];
-        int32_t tn[2], qn[2];
-        uint64_t fs[2];
-        bool ok[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const uint32_t qsafe = min(qrows[k], args.nq_pad - 1);
-          const uint32_t w = ms[k].w1 == kNoWin ? 0u : ms[k].w1;
-          const uint64_t f = static_cast<uint64_t>(w) * kChunk + lane;
-          ok[k] = (f < args.nt) & (ms[k].w1 != kNoWin);
-          fs[k] = ok[k] ? f : 0;
-          const uint4* td = reinterpret_cast<const uint4*>(args.t_desc + fs[k] * kDescBytes);
-          const uint4* qd = reinterpret_cast<const uint4*>(args.q_desc + static_cast<uint64_t>(qsafe) * kDescBytes);
-#pragma unroll
-          for (int w8 = 0; w8 < 8; ++w8) { tv[k][w8] = __ldg(td + w8); qv[k][w8] = __ldg(qd + w8); }
-          tn[k] = args.t_norm[fs[k]];
-          qn[k] = args.q_norm[qsafe];
-        }
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          if (kMask != SSRLCV_B200_MASK_NONE) {
-            const QueryMask qm = make_query_mask<kMask>(mp, args.q_loc[min(qrows[k], args.nq_pad - 1)]);
-            const float2 tl = args.t_loc[fs[k]];
-            if (mask_skips<kMask>(qm, tl.x, tl.y, mp.eps)) ok[k] = false;
-          }
-          uint32_t dot = 0;
-#pragma unroll
-          for (int w = 0; w < 8; ++w) {
-            dot = __dp4a(qv[k][w].x, tv[k][w].x, dot); dot = __dp4a(qv[k][w].y, tv[k][w].y, dot);
-            dot = __dp4a(qv[k][w].z, tv[k][w].z, dot); dot = __dp4a(qv[k][w].w, tv[k][w].w, dot);
-          }
-          const uint32_t d2 = static_cast<uint32_t>(qn[k] + tn[k] - 2 * static_cast<int32_t>(dot));
-          res[k] = ok[k] ? make_key(d2, fs[k] + args.target_offset) : kKeyNone;
-        }
-        // ---- rare: a second window reached the same score ----
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          if (ms[k].w1 != kNoWin && ms[k].w2 != kNoWin) {          // warp-uniform
-            const uint64_t f = static_cast<uint64_t>(ms[k].w2) * kChunk + lane;
-            bool ok2 = f < args.nt;
-            if (ok2 && kMask != SSRLCV_B200_MASK_NONE) {
-              const QueryMask qm = make_query_mask<kMask>(mp, args.q_loc[min(qrows[k], args.nq_pad - 1)]);
-              const float2 tl = args.t_loc[f];
-              if (mask_skips<kMask>(qm, tl.x, tl.y, mp.eps)) ok2 = false;
-            }
-            if (ok2) {
-              const uint4* td = reinterpret_cast<const uint4*>(args.t_desc + f * kDescBytes);
-              uint32_t dot = 0;
-#pragma unroll
-              for (int w = 0; w < 8; ++w) {
-                const uint4 b4 = __ldg(td + w);
-                dot = __dp4a(qv[k][w].x, b4.x, dot); dot = __dp4a(qv[k][w].y, b4.y, dot);
-                dot = __dp4a(qv[k][w].z, b4.z, dot); dot = __dp4a(qv[k][w].w, b4.w, dot);
-              }
-              const uint32_t d2 = static_cast<uint32_t>(qn[k] + args.t_norm[f] - 2 * static_cast<int32_t>(dot));
-              const uint64_t k2 = make_key(d2, f + args.target_offset);
-              res[k] = k2 < res[k] ? k2 : res[k];
-            }
-          }
-        }
-        // ---- warp-wide minima of both queries, interleaved ----
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const uint32_t lo = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(res[k]), o);
-            const uint32_t hi = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(res[k] >> 32), o);
-            const uint64_t other = (static_cast<uint64_t>(hi) << 32) | lo;
-            res[k] = other < res[k] ? other : res[k];
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          if (ms[k].w1 == kNoWin) res[k] = kKeyNone;
-          else if (ms[k].ovf) {
-            res[k] = kKeyNeedsExact;
-            if (lane == 0 && qrows[k] < args.nq) {
-              const uint32_t slot = atomicAdd(args.n_flagged, 1u);
-              args.flagged[slot] = sp * args.nq_pad + qrows[k];
-            }
-          }
-        }
-        if (lane == pair) { myA = res[0]; myB = res[1]; }
-      }
-      // rows [rw*64 + 2*lane, +2): one 16-byte store per lane (rows beyond nq land in the padding of the key array)
-      {
-        const uint32_t orow = qt * kBM + rw * 64 + 2 * lane;
-        uint64_t* dst = args.keys + static_cast<uint64_t>(sp) * args.nq_pad + orow;
-        *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2(myA, myB);
-      }
+      resolve_rows<kMask, 2>(args, mp, xch + (uparity * 2 + 0) * kBM, xch + (uparity * 2 + 1) * kBM, u.qt, u.slot, rw * 64, 64, lane);
       __syncwarp();
       if (lane == 0) mbar_arrive(&x_empty[uparity]);
       uparity ^= 1;
@@ -404,14 +420,14 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     constexpr uint32_t kWinPerTile = kBN / kChunk;     // 8
     constexpr uint32_t kWinPerWarp = kWinPerTile / 2;  // 4
     WinState* xch = reinterpret_cast<WinState*>(smem + SmemLayout::xch);
-    uint32_t acc = 0, accphase = 0, cs = 0, cphase = 0, uparity = 0, uiter = 0;
+    uint32_t it = 0, uiter = 0;                       // it: tiles consumed so far -> accumulator slot / column stage and their phases
     long long te_wait = 0, te_work = 0, te_resolve = 0, te_total0 = 0;
     if (kTiming) te_total0 = clock64();
     UnitIter u(args, blockIdx.x);
     while (u.next(args, blockIdx.x)) {
       const uint32_t row = u.qt * kBM + quarter * 32 + lane;       // this thread's query
       QueryMask qm;
-      if (kMask != SSRLCV_B200_MASK_NONE) qm = make_query_mask<kMask>(mp, args.q_loc[min(row, args.nq_pad - 1)]);
+      if (kMask != SSRLCV_B200_MASK_NONE) qm = load_query_mask<kMask>(args.q_mask + 2 * static_cast<uint64_t>(min(row, args.nq_pad - 1)));
 
       // Lowest score that can still pass the absolute threshold: d2 = |a|^2 - 2 (S - hmax - 2) + p <= d2_cap
       // <=> S >= hmax + 2 + ceil((|a|^2 - d2_cap) / 2)  (p = 0 is the permissive case).  Real scores are >= 2,
@@ -428,6 +444,8 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
       for (uint32_t j = u.j0; j < u.j1; ++j) {
         long long e0 = 0, e1 = 0;
         if (kTiming) e0 = clock64();
+        const uint32_t acc = it & 1, accphase = (it >> 1) & 1, cs = it % kColStages, cphase = (it / kColStages) & 1;
+        ++it;
         mbar_wait(&t_full[acc], accphase);
         if (kTiming) e1 = clock64();
         tc_fence_after();
@@ -444,7 +462,6 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[acc]);
-        if (++acc == 2) { acc = 0; accphase ^= 1; }
 
         if (kCols) mbar_wait(&c_full[cs], cphase);
         int32_t wm[kWinPerWarp];                                   // per-window maxima of this warp's 4 windows
@@ -455,21 +472,26 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
 #pragma unroll
             for (int e = 0; e < 32; ++e) x[e] = static_cast<uint32_t>(static_cast<int32_t>(x[e]) + s_w[(c_begin + k) * kChunk + e]);
           }
+          int32_t m = max32(x);
           if (kMask != SSRLCV_B200_MASK_NONE) {
+            // The unmasked window maximum bounds the masked one: the reference's float mask (ref: src/MatchFactory.cu:
+            // 2241-2254, :1613-1627) is evaluated only for windows that could still reach some lane's running best.
+            if (__any_sync(0xffffffffu, m >= st.best)) {
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-              const float4 l2 = *reinterpret_cast<const float4*>(&s_loc[(c_begin + k) * kChunk + e]);
-              if (mask_skips<kMask>(qm, l2.x, l2.y, mp.eps)) x[e] = 0;
-              if (mask_skips<kMask>(qm, l2.z, l2.w, mp.eps)) x[e + 1] = 0;
+              for (int e = 0; e < 32; e += 2) {
+                const float4 l2 = *reinterpret_cast<const float4*>(&s_loc[(c_begin + k) * kChunk + e]);
+                if (mask_skips<kMask>(qm, l2.x, l2.y, mp.eps)) x[e] = 0;
+                if (mask_skips<kMask>(qm, l2.z, l2.w, mp.eps)) x[e + 1] = 0;
+              }
+              m = max32(x);
             }
           }
           // rows past the end of the target set are zero padding with W = 0: score 0, below every floor
-          wm[k] = max32(x);
+          wm[k] = m;
         }
         if (kCols) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&c_empty[cs]);
-          if (++cs == kColStages) { cs = 0; cphase ^= 1; }
         }
         // Bookkeeping only when some lane's window reaches its running best (warp-uniform test, branch-free body).
         const int32_t mt = max(max(wm[0], wm[1]), max(wm[2], wm[3]));
@@ -482,11 +504,17 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
       long long r0 = 0;
       if (kTiming) r0 = clock64();
       // ---------------- hand the window states of this unit to the resolver warps ----------------
+      const uint32_t uparity = uiter & 1;
       mbar_wait(&x_empty[uparity], ((uiter >> 1) & 1) ^ 1);
       xch[(uparity * 2 + half) * kBM + quarter * 32 + lane] = st;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&x_full[uparity]);
-      uparity ^= 1;
+      if (!u.last) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&x_full[uparity]);
+      } else {
+        // last unit of this CTA: nothing left to overlap with, so all eight epilogue warps resolve it (16 rows each)
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        resolve_rows<kMask, 2>(args, mp, xch + (uparity * 2 + 0) * kBM, xch + (uparity * 2 + 1) * kBM, u.qt, u.slot, (warp - 4) * 16, 16, lane);
+      }
       ++uiter;
       if (kTiming) te_resolve += clock64() - r0;
     }
