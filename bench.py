@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the SIFT matching hot path (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3|C2|C1]
-  (N > 1: launched by torchrun, one rank per GPU; each rank matches its own image pair of the same
-   shape -- pair-sharded N-view matching, no data-path collective -- so scaling is "weak")
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3|C2|C1|C4|C5]
+  (N > 1: launched by torchrun, one rank per GPU.  C1-C3: each rank matches its own image pair of the same
+   shape -- pair-sharded N-view matching, no data-path collective -- so scaling is "weak".
+   C4: 16 views x 32 768 features, the 120 pairs dealt to the ranks (strong scaling, one result exchange at the end).
+   C5: one 1 M x 1 M pair, target set sharded over the ranks, candidates merged through an NCCL all-gather.)
 
 A "step" is one pass of the hot path over one synthetic 2-view batch:
   C3 (default): generateDistanceMatches on 65 536 x 65 536 SIFT-shaped uint8[128] descriptors, unconstrained
@@ -37,6 +39,10 @@ WORKLOADS = {
     "C2": dict(nq=16384, nt=16384, ns=8192, mask=2, desc="2-view 16384x16384 + 8192 seed, seed ratio test + DoubleConstrained (GEO_ORBIT=1)"),
     "C3": dict(nq=65536, nt=65536, ns=0, mask=0, desc="2-view 65536x65536 unconstrained generateDistanceMatches (tensor-pipe roofline case)"),
 }
+WORKLOADS["C4"] = dict(views=16, n=32768, nq=32768, nt=32768, ns=0, mask=0,
+                       desc="N-view all-pairs: 16 views x 32768 features, 120 pairs, generateMatchesIndexOnly, pair-sharded over the ranks")
+WORKLOADS["C5"] = dict(nq=1 << 20, nt=1 << 20, ns=0, mask=0,
+                       desc="one 1048576 x 1048576 pair, generateDistanceMatches, target set sharded over the ranks + NCCL all-gather merge")
 ABS_THR, REL_THR = 200.0 * 200.0, 0.6          # the reference's MatchFactory(0.6f, 200*200), src/Pipeline.cu:175
 EPS, DELTA = 25.0, 5.0                         # test/Pipeline.cu:198
 
@@ -55,7 +61,19 @@ def cameras():
 
 
 def evals_per_step(w):
+    if "views" in w:
+        return (w["views"] * (w["views"] - 1) // 2) * w["n"] * w["n"]
     return w["nq"] * w["nt"] + w["nq"] * w["ns"]
+
+
+def big_pair(nq, nt, seed):
+    """make_pair in 65 536-row chunks (bounded host memory); planted correspondences stay inside a chunk pair."""
+    from tests import synth
+    qs, ts = [], []
+    for c in range(max(nq, nt) // 65536):
+        q, t = synth.make_pair(65536, 65536, seed=seed + 1000 * c)
+        qs.append(q); ts.append(t)
+    return np.concatenate(qs)[:nq], np.concatenate(ts)[:nt]
 
 
 class ClockSampler:
@@ -66,7 +84,7 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -138,11 +156,26 @@ def run_reference(args, w, rank, world):
     if rank != 0:
         return None
     from ssrlcv_b200 import types as T
-    q, t, s = synth_inputs(w, 0)
+    scale, sample_note = 1.0, "full workload"
+    if "views" in w:            # C4: every pair has the same shape -> time one pair, 120 pairs extrapolated
+        from tests import synth
+        q, t = synth.make_pair(w["n"], w["n"], seed=0x55524C43)
+        s = None
+        scale = w["views"] * (w["views"] - 1) / 2
+        sample_note = f"one {w['n']} x {w['n']} pair of the {int(scale)}; ms_per_step extrapolated x{int(scale)}"
+    elif args.workload == "C5":  # C5: 16 384-query subsample against the full target set, linear in Nq
+        q, t = big_pair(w["nq"], w["nt"], 0x55524C43)
+        q, s = q[:16384], None
+        scale = w["nq"] / len(q)
+        sample_note = f"{len(q)} of {w['nq']} queries against all {w['nt']} targets; ms_per_step extrapolated x{int(scale)}"
+    else:
+        q, t, s = synth_inputs(w, 0)
     cam0, cam1 = cameras()
     path = os.path.join(ROOT, "oracle", "_ref", "libssrlcv_ref.so")
+    w = dict(w, mask=w.get("mask", 0))
     line = {"impl": "reference", "metric": "sift_dist_evals_per_s", "unit": "dist-evals/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong" if args.workload in ("C4", "C5") else "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['desc']}", "nq": w["nq"], "nt": w["nt"], "ns": w["ns"]}}
     import torch
     if os.path.exists(path) and torch.cuda.is_available():
@@ -164,10 +197,10 @@ def run_reference(args, w, rank, world):
                 times.append(ms.value + ms_seed.value)
         os.chdir(ROOT)
         ms_step = sum(times) / len(times)
-        v = evals_per_step(w) / (ms_step * 1e-3)
-        line.update({"value": v, "ms_per_step": ms_step, "matches_per_step": int(n),
+        v = (len(q) * (len(t) + (len(s) if s is not None else 0))) / (ms_step * 1e-3)
+        line.update({"value": v, "ms_per_step": ms_step * scale, "matches_per_step": int(n),
                      "cpu_baseline": {"value": v, "unit": "dist-evals/s", "cores": 0, "kind": "reference",
-                                      "sample": "full workload; the reference has no CPU path -- this is its own CUDA MatchFactory rebuilt for sm_100a, "
+                                      "sample": sample_note + "; the reference has no CPU path -- this is its own CUDA MatchFactory rebuilt for sm_100a, "
                                                 "run on the GPU with device-resident inputs (API wall time incl. its cudaMalloc/compaction)"},
                      "e2e": {"value": v, "unit": "dist-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     else:
@@ -318,9 +351,183 @@ def run_ours(args, w, rank, world, local_rank):
                      "peak_source": f"2 x bf16_tflops burst, {src}; nominal dense int8 is 4500"},
     }
     try:
-        line["cpu_baseline"] = cpu_baseline(w, q, t, s)
+        line["cpu_baseline"] = cpu_baseline(w, q, t, s) if not args.no_cpu_baseline else None
     except Exception as e:  # noqa: BLE001
         line["cpu_baseline"] = {"value": None, "unit": "dist-evals/s", "cores": 0, "kind": "port", "sample": f"failed: {e!r}"}
+    if dist is not None:
+        dist.destroy_process_group()
+    return line
+
+
+def run_sharded(args, w, rank, world, local_rank):
+    """C4 (pairs dealt to ranks) and C5 (target set sharded over ranks, NCCL all-gather of candidate keys)."""
+    import torch
+    from ssrlcv_b200 import _lib, types as T
+    from ssrlcv_b200.distributed import shard_bounds
+    from ssrlcv_b200.match_factory import Context
+    from ssrlcv_b200.pair_scheduler import assign_pairs, pair_order
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    ctx = Context.get(local_rank)
+    lib, h = ctx.lib, ctx.handle
+    dev = f"cuda:{local_rank}"
+    pin = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1)).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    p = _lib.MatchParams()
+    p.absolute_threshold, p.relative_threshold, p.compact, p.engine = ABS_THR, REL_THR, 1, 0
+    n_out = C.c_uint64(0)
+    evals = evals_per_step(w)
+    is_c4 = "views" in w
+
+    if is_c4:
+        from tests import synth
+        V, n = w["views"], w["n"]
+        views = []
+        for k in range(V // 2):
+            a, b = synth.make_pair(n, n, seed=0x55524C43 + k)
+            views += [a, b]
+        pairs = pair_order(V)
+        mine = assign_pairs(pairs, [n] * V, world)[rank]
+        need = sorted({v for k in mine for v in pairs[k]})
+        host = {v: pin(views[v]) for v in need}
+        devbuf = {v: host[v].to(dev) for v in need}
+        slots = -(-len(pairs) // world)
+        out = torch.zeros((slots, n, 4), dtype=torch.int32, device=dev)           # uint2_pair records, padded per pair
+        counts = torch.zeros(len(pairs), dtype=torch.int64, device=dev)
+        gathered = torch.empty((world, slots, n, 4), dtype=torch.int32, device=dev) if world > 1 else None
+        p.out_kind, p.mask_kind = T.OUT_PAIR, 0
+        h2d = sum(len(views[v]) * 152 for v in need)
+
+        def step(from_host=False):
+            if from_host:
+                for v in need:
+                    devbuf[v].copy_(host[v], non_blocking=True)
+            sets = {}
+            for v in need:                                                         # every view is repacked once per step, not per pair
+                hs = C.c_void_p()
+                ctx.check(lib.ssrlcv_b200_pack(h, C.c_void_p(devbuf[v].data_ptr()), n, C.byref(hs)))
+                sets[v] = hs
+            counts.zero_()
+            total = 0
+            for s_i, k in enumerate(mine):
+                qv, tv = pairs[k]
+                p.query_image_id, p.target_image_id = qv, tv
+                ctx.check(lib.ssrlcv_b200_match(h, C.byref(p), sets[qv], sets[tv], None, 0, C.c_void_p(out[s_i].data_ptr()), C.byref(n_out)))
+                counts[k] = int(n_out.value)
+                total += int(n_out.value)
+            for hs in sets.values():
+                lib.ssrlcv_b200_set_free(hs)
+            if dist is not None:                                                   # the one exchange of the path: pair lists to every rank
+                dist.all_reduce(counts)
+                dist.all_gather_into_tensor(gathered, out)
+            if from_host:
+                counts.cpu()
+            return total
+
+        d2h = lambda: len(pairs) * 8
+        par = f"pair-sharded x{world} ({len(mine)} of {len(pairs)} pairs on rank 0)"
+    else:
+        nq, nt = w["nq"], w["nt"]
+        q, t = big_pair(nq, nt, 0x55524C43)
+        b = shard_bounds(nt, world)
+        lo, hi = b[rank], b[rank + 1]
+        qh, th = pin(q), pin(t[lo:hi])
+        qd, td = qh.to(dev), th.to(dev)
+        tloc = torch.from_numpy(np.ascontiguousarray(t["loc"])).to(dev)            # locations of the whole target set (8 B each)
+        keys = torch.empty(nq, dtype=torch.int64, device=dev)
+        allk = torch.empty((world, nq), dtype=torch.int64, device=dev)
+        out = torch.empty(nq * 48, dtype=torch.uint8, device=dev)
+        out_h = torch.empty(nq * 48, dtype=torch.uint8).pin_memory()
+        p.out_kind, p.mask_kind, p.query_image_id, p.target_image_id = T.OUT_DMATCH, 0, 0, 1
+        h2d = (nq + hi - lo) * 152
+
+        def step(from_host=False):
+            if from_host:
+                qd.copy_(qh, non_blocking=True); td.copy_(th, non_blocking=True)
+            hq, ht = C.c_void_p(), C.c_void_p()
+            ctx.check(lib.ssrlcv_b200_pack(h, C.c_void_p(qd.data_ptr()), nq, C.byref(hq)))
+            ctx.check(lib.ssrlcv_b200_pack(h, C.c_void_p(td.data_ptr()), hi - lo, C.byref(ht)))
+            ctx.check(lib.ssrlcv_b200_match_candidates(h, C.byref(p), hq, ht, lo if hi > lo else 0, C.c_void_p(keys.data_ptr())))
+            if dist is not None:
+                dist.all_gather_into_tensor(allk, keys)                            # 8 B per query per rank over NVLink
+                src = allk
+            else:
+                src = keys
+            ctx.check(lib.ssrlcv_b200_finalize_candidates(h, C.byref(p), hq, C.c_void_p(src.data_ptr()), world, C.c_void_p(tloc.data_ptr()),
+                                                          None, C.c_void_p(out.data_ptr()), C.byref(n_out)))
+            lib.ssrlcv_b200_set_free(hq); lib.ssrlcv_b200_set_free(ht)
+            if from_host:
+                out_h[: n_out.value * 48].copy_(out[: n_out.value * 48]); torch.cuda.synchronize()
+            return int(n_out.value)
+
+        d2h = lambda: int(n_out.value) * 48 + 8
+        par = f"target-sharded x{world} (rank 0 owns targets [{lo}, {hi}))"
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        n = 0
+        for i in range(steps):
+            flush.fill_(i & 0xFF)
+            ev[i][0].record()
+            n = fn()
+            ev[i][1].record()
+        barrier()
+        return sum(a.elapsed_time(b) for a, b in ev), n
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    lib.ssrlcv_b200_set_profiling(h, 1)
+    sampler = ClockSampler(local_rank)
+    launches0 = ctx.launch_count()
+    total_ms, n_matches = timed(step, args.steps)
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    k_ms, k_n = C.c_double(0), C.c_uint64(0)
+    lib.ssrlcv_b200_kernel_time(h, C.byref(k_ms), C.byref(k_n))
+    lib.ssrlcv_b200_set_profiling(h, 0)
+    step(True)
+    e2e_ms, _ = timed(lambda: step(True), args.steps)
+    tt = torch.tensor([total_ms, e2e_ms, float(n_matches)], dtype=torch.float64, device=dev)
+    tm = tt.clone()
+    if dist is not None:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+    total_ms, e2e_ms = float(tm[0]), float(tm[1])
+    n_total = int(tt[2]) if is_c4 else n_matches
+    if rank != 0:
+        dist.destroy_process_group()
+        return None
+    bf16_burst, _, _, src = measured_peaks()
+    peak_tops = 2.0 * bf16_burst
+    value = evals * args.steps / (total_ms * 1e-3)
+    kern_ms = k_ms.value / max(k_n.value, 1)
+    my_evals = evals / world if not is_c4 else len(mine) * w["n"] * w["n"]
+    ops_per_launch = 256.0 * my_evals / max(k_n.value / args.steps, 1)
+    achieved = ops_per_launch / (kern_ms * 1e-3) / 1e12
+    line = {
+        "metric": "sift_dist_evals_per_s", "value": value, "unit": "dist-evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w['desc']}", "parallelism": par, "l2": "256 MiB flush between timed iterations",
+                   "step": "pack + match of this rank's share + result exchange + finalize, device-resident inputs"},
+        "matches_per_s": n_total * args.steps / (total_ms * 1e-3), "matches_per_step": n_total,
+        "int8_tops": 256.0 * value / 1e12, "frac_of_int8_peak_step": 256.0 * value / 1e12 / (world * peak_tops), "clocks": clocks,
+        "e2e": {"value": evals * args.steps / (e2e_ms * 1e-3), "unit": "dist-evals/s", "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h(), "api": "C ABI with pinned host inputs copied in every step, counts / records read back"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tops, "unit": "TFLOP/s", "frac": achieved / peak_tops, "traffic": None,
+                     "kernel": "smax_kernel (tcgen05.mma kind::i8 + fused argmax epilogue), rank 0", "kernel_ms": kern_ms, "launches_timed": int(k_n.value),
+                     "peak_source": f"2 x bf16_tflops burst, {src}; nominal dense int8 is 4500"},
+        "cpu_baseline": None,
+    }
     if dist is not None:
         dist.destroy_process_group()
     return line
@@ -333,6 +540,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -340,6 +548,8 @@ def main():
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         line = run_reference(args, w, rank, world)
+    elif args.workload in ("C4", "C5"):
+        line = run_sharded(args, w, rank, world, local_rank)
     else:
         line = run_ours(args, w, rank, world, local_rank)
     if line is not None:
