@@ -397,6 +397,7 @@ def run_sharded(args, w, rank, world, local_rank):
         slots = -(-len(pairs) // world)
         out = torch.zeros((slots, n, 4), dtype=torch.int32, device=dev)           # uint2_pair records, padded per pair
         counts = torch.zeros(len(pairs), dtype=torch.int64, device=dev)
+        counts_h = torch.zeros(len(pairs), dtype=torch.int64).pin_memory()
         gathered = torch.empty((world, slots, n, 4), dtype=torch.int32, device=dev) if world > 1 else None
         p.out_kind, p.mask_kind = T.OUT_PAIR, 0
         h2d = sum(len(views[v]) * 152 for v in need)
@@ -410,14 +411,23 @@ def run_sharded(args, w, rank, world, local_rank):
                 hs = C.c_void_p()
                 ctx.check(lib.ssrlcv_b200_pack(h, C.c_void_p(devbuf[v].data_ptr()), n, C.byref(hs)))
                 sets[v] = hs
-            counts.zero_()
-            total = 0
+            # the pair scheduler's device side: all of this rank's pairs in one batch, one synchronisation
+            m = len(mine)
+            P = (_lib.MatchParams * m)()
+            Q, Tt, O = (C.c_void_p * m)(), (C.c_void_p * m)(), (C.c_void_p * m)()
             for s_i, k in enumerate(mine):
                 qv, tv = pairs[k]
                 p.query_image_id, p.target_image_id = qv, tv
-                ctx.check(lib.ssrlcv_b200_match(h, C.byref(p), sets[qv], sets[tv], None, 0, C.c_void_p(out[s_i].data_ptr()), C.byref(n_out)))
-                counts[k] = int(n_out.value)
-                total += int(n_out.value)
+                C.memmove(C.byref(P, s_i * C.sizeof(_lib.MatchParams)), C.byref(p), C.sizeof(_lib.MatchParams))
+                Q[s_i], Tt[s_i], O[s_i] = sets[qv], sets[tv], out[s_i].data_ptr()
+            n_outs = (C.c_uint64 * m)()
+            ctx.check(lib.ssrlcv_b200_match_batch(h, m, P, Q, Tt, None, O, n_outs))
+            total = 0
+            counts_h.zero_()
+            for s_i, k in enumerate(mine):
+                counts_h[k] = int(n_outs[s_i])
+                total += int(n_outs[s_i])
+            counts.copy_(counts_h, non_blocking=True)
             for hs in sets.values():
                 lib.ssrlcv_b200_set_free(hs)
             if dist is not None:                                                   # the one exchange of the path: pair lists to every rank

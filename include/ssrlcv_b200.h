@@ -125,6 +125,14 @@ int  ssrlcv_b200_match(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* par
                        const ssrlcv_b200_set* query, const ssrlcv_b200_set* target,
                        const float* seed_dist_dev, uint64_t n_seed_dist, void* out_dev, uint64_t* n_out);
 
+/* replaces: the pair loop of generateMatchesExhaustive (src/MatchFactory.cu:907-936) -- the pair scheduler's device side.
+ * n_pairs independent ssrlcv_b200_match calls (params[i], queries[i], targets[i], seed_dist_dev[i] or NULL, out_dev[i]) are
+ * enqueued back to back and synchronised once; n_out[i] receives the record count of pair i.  seed_dist_dev may be NULL
+ * (no pair uses seed distances); seed arrays must hold size(queries[i]) floats. */
+int  ssrlcv_b200_match_batch(ssrlcv_b200_ctx* ctx, uint32_t n_pairs, const ssrlcv_b200_match_params* params,
+                             const ssrlcv_b200_set* const* queries, const ssrlcv_b200_set* const* targets,
+                             const float* const* seed_dist_dev, void* const* out_dev, uint64_t* n_out);
+
 /* Whole reference call sequence with HOST buffers (what MatchFactory does when the Unity arrays are in
  * state `cpu`): H2D of both feature sets (+ seed set if seed_host != NULL), pack, seed distances, match,
  * D2H of the result.  out_host: capacity n_query records. */

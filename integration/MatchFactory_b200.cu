@@ -367,22 +367,65 @@ ssrlcv::MatchSet ssrlcv::MatchFactory<T>::generateMatchesExhaustive(std::vector<
   std::vector<ssrlcv::ptr::value<ssrlcv::Unity<uint2_pair>>> matchIndices;
   unsigned long long totalMatches = 0;
   logger.info << "matching images";
+  // The pair scheduler: seed distances once per query view, then every pair of the reference's loop (same order,
+  // same skip rule, ref: src/MatchFactory.cu:925-936) is handed to the library in ONE batch and synchronised once.
+#if GEO_ORBIT == 1
+  const int mask = SSRLCV_B200_MASK_DOUBLE;
+#else
+  const int mask = SSRLCV_B200_MASK_NONE;
+#endif
+  std::vector<ssrlcv::ptr::value<ssrlcv::Unity<float>>> seedOfView(n, nullptr);
+  std::vector<ssrlcv_b200_match_params> params;
+  std::vector<const ssrlcv_b200_set*> qsets, tsets;
+  std::vector<const float*> seeds;
+  std::vector<void*> outs;
+  std::vector<std::pair<size_t, size_t>> pairOf;
   int i = 0;
   for (size_t q = 0; q + 1 < n; ++q) {
-    ssrlcv::ptr::value<ssrlcv::Unity<float>> seedDistances = nullptr;
-    if (this->seedFeatures != nullptr) seedDistances = this->getSeedDistances(features[q]);
+    if (this->seedFeatures != nullptr) seedOfView[q] = this->getSeedDistances(features[q]);
     for (size_t t = q + 1; t < n; ++t) {
       if (ordered && estimatedOverlap > 0.0f && ++i * (1 - estimatedOverlap) > 1.0f) continue;
-#if GEO_ORBIT == 1
-      const int mask = SSRLCV_B200_MASK_DOUBLE;
-#else
-      const int mask = SSRLCV_B200_MASK_NONE;
-#endif
-      matchIndices.push_back(b200_generate<uint2_pair, T>(relativeThreshold, absoluteThreshold, SSRLCV_B200_OUT_PAIR, mask, true, images[q],
-                                                          features[q], images[t], features[t], epsilon, delta, nullptr, seedDistances,
-                                                          packed[q], packed[t]));
-      totalMatches += matchIndices[i++]->size();
+      ++i;
+      ssrlcv_b200_match_params p;
+      memset(&p, 0, sizeof p);
+      p.out_kind = SSRLCV_B200_OUT_PAIR;
+      p.mask_kind = mask;
+      p.absolute_threshold = absoluteThreshold;
+      p.relative_threshold = relativeThreshold;
+      p.query_image_id = (unsigned int)images[q]->id;
+      p.target_image_id = (unsigned int)images[t]->id;
+      p.epsilon = epsilon;
+      p.delta = delta;
+      memcpy(p.query_camera, &images[q]->camera, 80);
+      memcpy(p.target_camera, &images[t]->camera, 80);
+      p.compact = 1;
+      p.engine = SSRLCV_B200_ENGINE_TCGEN05;
+      ptr::device<uint2_pair> dev(features[q]->size());
+      matchIndices.push_back(ptr::value<Unity<uint2_pair>>(dev, features[q]->size(), gpu));
+      params.push_back(p);
+      qsets.push_back(packed[q]->s);
+      tsets.push_back(packed[t]->s);
+      seeds.push_back(seedOfView[q] != nullptr ? seedOfView[q]->device.get() : nullptr);
+      outs.push_back(matchIndices.back()->device.get());
+      pairOf.push_back(std::make_pair(q, t));
     }
+  }
+  std::vector<uint64_t> counts(params.size(), 0);
+  b200_check(ssrlcv_b200_match_batch(b200_context(), (uint32_t)params.size(), params.data(), qsets.data(), tsets.data(), seeds.data(),
+                                     outs.data(), counts.data()),
+             "ssrlcv_b200_match_batch");
+  for (size_t k = 0; k < params.size(); ++k) {
+    if (counts[k] == 0) {
+      // reference quirk (validateMatches, src/MatchFactory.cu:118-123): the caller keeps the uncompacted all-invalid array
+      matchIndices[k] = b200_generate<uint2_pair, T>(relativeThreshold, absoluteThreshold, SSRLCV_B200_OUT_PAIR, mask, true, images[pairOf[k].first],
+                                                     features[pairOf[k].first], images[pairOf[k].second], features[pairOf[k].second], epsilon, delta,
+                                                     nullptr, seedOfView[pairOf[k].first], packed[pairOf[k].first], packed[pairOf[k].second]);
+    } else {
+      ptr::device<uint2_pair> validated(counts[k]);
+      CudaSafeCall(cudaMemcpy(validated.get(), matchIndices[k]->device.get(), counts[k] * sizeof(uint2_pair), cudaMemcpyDeviceToDevice));
+      matchIndices[k]->setData(validated, counts[k], gpu);
+    }
+    totalMatches += matchIndices[k]->size();
   }
   for (size_t v = 0; v < n; ++v) delete packed[v];
   if (totalMatches == 0) {

@@ -19,7 +19,7 @@ EXPORTS = [
     "ssrlcv_b200_abi_version", "ssrlcv_b200_create", "ssrlcv_b200_destroy", "ssrlcv_b200_last_error",
     "ssrlcv_b200_synchronize", "ssrlcv_b200_launch_count", "ssrlcv_b200_set_profiling", "ssrlcv_b200_kernel_time", "ssrlcv_b200_pack", "ssrlcv_b200_pack_host",
     "ssrlcv_b200_set_size", "ssrlcv_b200_set_free", "ssrlcv_b200_seed_distances", "ssrlcv_b200_match",
-    "ssrlcv_b200_match_host", "ssrlcv_b200_match_candidates", "ssrlcv_b200_finalize_candidates",
+    "ssrlcv_b200_match_host", "ssrlcv_b200_match_batch", "ssrlcv_b200_match_candidates", "ssrlcv_b200_finalize_candidates",
     "ssrlcv_b200_set_loc", "ssrlcv_b200_validate", "ssrlcv_b200_refine", "ssrlcv_b200_sort",
     "ssrlcv_b200_raw_matches", "ssrlcv_b200_epipolar_endpoints", "ssrlcv_b200_device_sincos",
 ]
@@ -80,6 +80,7 @@ def load() -> C.CDLL:
     lib.ssrlcv_b200_set_loc.restype = vp
     lib.ssrlcv_b200_seed_distances.argtypes = [vp, vp, vp, vp, i32]
     lib.ssrlcv_b200_match.argtypes = [vp, pp, vp, vp, vp, u64, vp, pu64]
+    lib.ssrlcv_b200_match_batch.argtypes = [vp, u32, pp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), pu64]
     lib.ssrlcv_b200_match_host.argtypes = [vp, pp, vp, u64, vp, u64, vp, u64, vp, pu64]
     lib.ssrlcv_b200_match_candidates.argtypes = [vp, pp, vp, vp, u64, vp]
     lib.ssrlcv_b200_finalize_candidates.argtypes = [vp, pp, vp, vp, u32, vp, vp, vp, pu64]

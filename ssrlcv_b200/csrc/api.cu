@@ -71,7 +71,7 @@ struct ssrlcv_b200_ctx {
   EncodeTiledFn encode = nullptr;
   std::string err;
   uint64_t launches = 0;
-  Workspace keys, flagged, counts, scratch, hostpin, qmask;
+  Workspace keys, flagged, counts, scratch, hostpin, qmask, totals;
   uint32_t* d_scalars = nullptr;   // [0] n_flagged, [1] total, [2..3] hmin/hmax staging
   uint32_t* h_scalars = nullptr;   // pinned mirror
   bool profiling = false;
@@ -147,7 +147,7 @@ void ssrlcv_b200_destroy(ssrlcv_b200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (Workspace* w : {&ctx->keys, &ctx->flagged, &ctx->counts, &ctx->scratch, &ctx->qmask}) if (w->p) cudaFree(w->p);
+  for (Workspace* w : {&ctx->keys, &ctx->flagged, &ctx->counts, &ctx->scratch, &ctx->qmask, &ctx->totals}) if (w->p) cudaFree(w->p);
   if (ctx->hostpin.p) cudaFreeHost(ctx->hostpin.p);
   if (ctx->d_scalars) cudaFree(ctx->d_scalars);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
@@ -371,25 +371,33 @@ static int32_t d2_cap_of(float abs_thr) {
   return static_cast<int32_t>(c) - 1;
 }
 
-// runs the distance engine; leaves exact keys in ctx->keys ([n_splits][nq_pad])
-static int run_engine(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* q, const ssrlcv_b200_set* t, const MaskParams& mp, int engine,
-                      uint64_t target_offset, float abs_thr, SmaxArgs& a) {
+// shape-only part of the plan: tile counts, CTA ranges, key slots
+static int make_plan(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* q, const ssrlcv_b200_set* t, int engine, SmaxArgs& a, int& grid) {
   memset(&a, 0, sizeof a);
   a.nq = static_cast<uint32_t>(q->n); a.nt = static_cast<uint32_t>(t->n); a.nq_pad = static_cast<uint32_t>(q->n_pad);
-  a.target_offset = target_offset;
   a.n_qtiles = (a.nq + kBM - 1) / kBM;
   a.n_ttiles = (a.nt + kBN - 1) / kBN;
-  a.t_hmax = t->hmax;
-  a.d2_cap = d2_cap_of(abs_thr);
-  int grid = 1;
+  grid = 1;
   if (static_cast<uint64_t>(a.n_qtiles) * a.n_ttiles >= (1ull << 32))
     return fail(ctx, SSRLCV_B200_EINVAL, "%u x %u features is too large for one call: shard the target set (ssrlcv_b200_match_candidates)", a.nq, a.nt);
   if (engine == SSRLCV_B200_ENGINE_SIMT || a.nq == 0 || a.nt == 0) plan_simt(ctx, a);
   else plan_tc(ctx, a, grid);
+  return 0;
+}
+
+// runs the distance engine; leaves exact keys in ctx->keys ([n_splits][nq_pad])
+static int run_engine(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* q, const ssrlcv_b200_set* t, const MaskParams& mp, int engine,
+                      uint64_t target_offset, float abs_thr, SmaxArgs& a) {
+  int grid = 1;
+  int rc = make_plan(ctx, q, t, engine, a, grid);
+  if (rc) return rc;
+  a.target_offset = target_offset;
+  a.t_hmax = t->hmax;
+  a.d2_cap = d2_cap_of(abs_thr);
   a.q_desc = q->desc; a.q_norm = q->norm; a.q_loc = q->loc;
   a.t_desc = t->desc; a.t_norm = t->norm; a.t_loc = t->loc; a.t_wcol = t->wcol;
   const size_t n_keys = static_cast<size_t>(a.n_splits) * a.nq_pad;
-  int rc = ws_reserve(ctx, ctx->keys, n_keys * sizeof(uint64_t));
+  rc = ws_reserve(ctx, ctx->keys, n_keys * sizeof(uint64_t));
   if (!rc) rc = ws_reserve(ctx, ctx->flagged, n_keys * sizeof(uint32_t));
   if (rc) return rc;
   a.keys = static_cast<uint64_t*>(ctx->keys.p);
@@ -455,9 +463,10 @@ static size_t out_elt(int kind) {
   return 0;
 }
 
-static int finalize_common(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const ssrlcv_b200_set* q, const uint64_t* keys,
-                           uint32_t n_splits, const float2* t_loc, const ssrlcv_b200_set* t, const float* seed, void* out_dev,
-                           uint64_t* n_out) {
+// enqueue thresholds / writers / compaction; the number of records written lands in *total_dev (device)
+static int finalize_enqueue(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const ssrlcv_b200_set* q, const uint64_t* keys,
+                            uint32_t n_splits, const float2* t_loc, const ssrlcv_b200_set* t, const float* seed, void* out_dev,
+                            uint32_t* total_dev) {
   FinalizeArgs f; memset(&f, 0, sizeof f);
   f.nq = static_cast<uint32_t>(q->n); f.nq_pad = static_cast<uint32_t>(q->n_pad); f.n_splits = n_splits;
   f.keys = keys; f.seed = seed;
@@ -473,10 +482,18 @@ static int finalize_common(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params*
   int rc = ws_reserve(ctx, ctx->counts, (blocks + 1) * sizeof(uint32_t));
   if (rc) return rc;
   f.block_counts = static_cast<uint32_t*>(ctx->counts.p);
-  f.total = ctx->d_scalars + 1;
+  f.total = total_dev;
   launch_finalize(ctx->stream, f);
   if (f.nq) ctx->launches += 2;
-  CU(cudaMemcpyAsync(ctx->h_scalars + 1, f.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+
+static int finalize_common(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const ssrlcv_b200_set* q, const uint64_t* keys,
+                           uint32_t n_splits, const float2* t_loc, const ssrlcv_b200_set* t, const float* seed, void* out_dev,
+                           uint64_t* n_out) {
+  int rc = finalize_enqueue(ctx, p, q, keys, n_splits, t_loc, t, seed, out_dev, ctx->d_scalars + 1);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->h_scalars + 1, ctx->d_scalars + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaGetLastError());
   if (n_out) *n_out = ctx->h_scalars[1];
@@ -504,6 +521,58 @@ int ssrlcv_b200_match(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, c
   rc = run_engine(ctx, query, target, mp, p->engine, 0, p->absolute_threshold, a);
   if (rc) return rc;
   return finalize_common(ctx, p, query, a.keys, a.n_splits, target->loc, target, seed_dist_dev, out_dev, n_out);
+}
+
+// The pair scheduler's device side: every pair of the batch is enqueued back to back on the context's stream (workspaces are
+// reused in stream order), the per-pair record counts are collected on the device and read back with ONE synchronisation.
+int ssrlcv_b200_match_batch(ssrlcv_b200_ctx* ctx, uint32_t n_pairs, const ssrlcv_b200_match_params* params,
+                            const ssrlcv_b200_set* const* queries, const ssrlcv_b200_set* const* targets,
+                            const float* const* seed_dist_dev, void* const* out_dev, uint64_t* n_out) {
+  if (!ctx || (n_pairs && (!params || !queries || !targets || !out_dev || !n_out))) return fail(ctx, SSRLCV_B200_EINVAL, "match_batch: bad arguments");
+  if (n_pairs == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  int rc = 0;
+  size_t max_keys = 0, max_rows = 0;
+  for (uint32_t i = 0; i < n_pairs; ++i) {
+    rc = check_params(ctx, &params[i]);
+    if (rc) return rc;
+    if (!queries[i] || !targets[i] || (queries[i]->n && !out_dev[i])) return fail(ctx, SSRLCV_B200_EINVAL, "match_batch: pair %u: bad arguments", i);
+    if (params[i].out_kind == SSRLCV_B200_OUT_FEATUREMATCH && params[i].mask_kind == SSRLCV_B200_MASK_DOUBLE)
+      return fail(ctx, SSRLCV_B200_EINVAL, "the reference has no DoubleConstrained FeatureMatch kernel");
+    SmaxArgs a; int grid;
+    rc = make_plan(ctx, queries[i], targets[i], params[i].engine, a, grid);
+    if (rc) return rc;
+    const size_t nk = static_cast<size_t>(a.n_splits) * a.nq_pad;
+    if (nk > max_keys) max_keys = nk;
+    if (queries[i]->n_pad > max_rows) max_rows = queries[i]->n_pad;
+  }
+  // grow every workspace once, up front: a reallocation in the middle of the batch would have to drain the stream
+  rc = ws_reserve(ctx, ctx->keys, max_keys * sizeof(uint64_t));
+  if (!rc) rc = ws_reserve(ctx, ctx->flagged, max_keys * sizeof(uint32_t));
+  if (!rc) rc = ws_reserve(ctx, ctx->qmask, max_rows * 2 * sizeof(float4));
+  if (!rc) rc = ws_reserve(ctx, ctx->counts, (max_rows / 256 + 2) * sizeof(uint32_t));
+  if (!rc) rc = ws_reserve(ctx, ctx->totals, static_cast<size_t>(n_pairs) * sizeof(uint32_t));
+  if (rc) return rc;
+  if (ctx->hostpin.cap < n_pairs * sizeof(uint32_t)) {
+    if (ctx->hostpin.p) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFreeHost(ctx->hostpin.p)); ctx->hostpin.p = nullptr; ctx->hostpin.cap = 0; }
+    CU(cudaMallocHost(&ctx->hostpin.p, n_pairs * sizeof(uint32_t) * 2));
+    ctx->hostpin.cap = n_pairs * sizeof(uint32_t) * 2;
+  }
+  uint32_t* totals = static_cast<uint32_t*>(ctx->totals.p);
+  for (uint32_t i = 0; i < n_pairs; ++i) {
+    const ssrlcv_b200_match_params* p = &params[i];
+    MaskParams mp; fill_mask(p, mp);
+    SmaxArgs a;
+    rc = run_engine(ctx, queries[i], targets[i], mp, p->engine, 0, p->absolute_threshold, a);
+    if (!rc) rc = finalize_enqueue(ctx, p, queries[i], a.keys, a.n_splits, targets[i]->loc, targets[i],
+                                   seed_dist_dev ? seed_dist_dev[i] : nullptr, out_dev[i], totals + i);
+    if (rc) return rc;
+  }
+  CU(cudaMemcpyAsync(ctx->hostpin.p, totals, n_pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaGetLastError());
+  for (uint32_t i = 0; i < n_pairs; ++i) n_out[i] = static_cast<const uint32_t*>(ctx->hostpin.p)[i];
+  return 0;
 }
 
 int ssrlcv_b200_match_candidates(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const ssrlcv_b200_set* query,

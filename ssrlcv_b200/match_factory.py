@@ -314,6 +314,54 @@ class MatchFactory:
             res.setMemoryState(cpu)
         return res
 
+    # ------------------------------------------------------------------ pair scheduler (device side)
+    def matchBatch(self, jobs) -> list:
+        """Run many independent generate* calls with one synchronisation (ssrlcv_b200_match_batch).
+        jobs: list of (params, queryFeatures, targetFeatures, seedDistances-or-None); returns one Unity per job, exactly what
+        the corresponding generate* call returns (ref: the pair loop of src/MatchFactory.cu:907-936)."""
+        torch = self._torch()
+        n = len(jobs)
+        if n == 0:
+            return []
+        touched = {}
+        for _, qf, tf, sd in jobs:
+            for u in (qf, tf, sd):
+                if u is not None and id(u) not in touched:
+                    touched[id(u)] = (u, u.getMemoryState())
+                    if u.getMemoryState() != gpu:
+                        u.setMemoryState(gpu)
+        try:
+            P = (_lib.MatchParams * n)()
+            Q, Tt, S, O = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_void_p * n)()
+            outs, keep = [], []
+            for i, (p, qf, tf, sd) in enumerate(jobs):
+                if sd is not None and sd.size() != qf.size():
+                    raise MatchFactoryError("ERROR: seedDistances should have come from matching a seed image to queryFeatures")
+                C.memmove(C.byref(P, i * C.sizeof(_lib.MatchParams)), C.byref(p), C.sizeof(_lib.MatchParams))
+                q, t = pack(self.ctx, qf), pack(self.ctx, tf)
+                keep += [q, t]
+                Q[i], Tt[i] = q.handle, t.handle
+                S[i] = sd.device_ptr() if sd is not None else None
+                dt = T.OUT_DTYPES[p.out_kind]
+                out = torch.empty(max(qf.size(), 1) * dt.itemsize, dtype=torch.uint8, device=f"cuda:{self.device}")
+                outs.append(out)
+                O[i] = out.data_ptr()
+            n_out = (C.c_uint64 * n)()
+            self.ctx.check(self.ctx.lib.ssrlcv_b200_match_batch(self.ctx.handle, n, P, Q, Tt, S, O, n_out))
+            res = []
+            for i, (p, qf, tf, sd) in enumerate(jobs):
+                k = int(n_out[i])
+                dt = T.OUT_DTYPES[p.out_kind]
+                if p.compact and k == 0 and qf.size() > 0:
+                    res.append(self._run(p, qf, tf, sd))          # rare reference quirk path (all-invalid array is kept), see _run
+                else:
+                    res.append(Unity(outs[i][: k * dt.itemsize], dt, gpu, self.device, k))
+            return res
+        finally:
+            for u, st in touched.values():
+                if st != gpu:
+                    u.setMemoryState(st)
+
     # ------------------------------------------------------------------ N-view
     def generateMatchesExhaustive(self, images, features, epsilon, delta, ordered=True, estimatedOverlap=0.0,
                                   geo_orbit: bool = True) -> MatchSet:

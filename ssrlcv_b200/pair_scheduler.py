@@ -48,19 +48,20 @@ def exhaustive_pairs(mf, images, features, epsilon, delta, ordered=True, estimat
                      only: Sequence[int] | None = None):
     """Run the pair loop on this process' GPU. `only`: indices into pair_order() to run (multi-GPU sharding)."""
     pairs = pair_order(len(images), ordered, estimatedOverlap)
-    todo = range(len(pairs)) if only is None else only
+    todo = list(range(len(pairs)) if only is None else only)
     seed_cache = {}
-    out = []
+    jobs = []
     for k in todo:
         q, t = pairs[k]
         seed = None
         if mf.seedFeatures is not None:
             if q not in seed_cache:
-                seed_cache[q] = mf.getSeedDistances(features[q])
+                seed_cache[q] = mf.getSeedDistances(features[q])      # once per query view, not once per pair
             seed = seed_cache[q]
         if geo_orbit:
-            m = mf.generateMatchesDoubleConstrainedIndexOnly(images[q], features[q], images[t], features[t], epsilon, delta, seed)
+            p = mf._params(T.OUT_PAIR, T.MASK_DOUBLE, images[q], images[t], epsilon, delta)
         else:
-            m = mf.generateMatchesIndexOnly(images[q], features[q], images[t], features[t], seed)
-        out.append(m)
-    return out
+            p = mf._params(T.OUT_PAIR, T.MASK_NONE, images[q], images[t])
+        jobs.append((p, features[q], features[t], seed))
+    # every pair is enqueued back to back on the device and synchronised once (ssrlcv_b200_match_batch)
+    return mf.matchBatch(jobs)

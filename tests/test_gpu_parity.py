@@ -300,6 +300,33 @@ def test_refine_sort_raw_validate(api):
     assert T.fields_equal(u.to_numpy(), dirty[dirty["invalid"] == 0])
 
 
+# ------------------------------------------------------------------------------------ pair scheduler: one batch, one synchronisation
+def test_match_batch_equals_individual_calls(api, everest):
+    """ssrlcv_b200_match_batch (the pair loop of generateMatchesExhaustive, ref: src/MatchFactory.cu:907-936) must return, pair by
+    pair, exactly what the single calls return: mixed sizes, masks, output kinds, seed distances, and one pair with no survivor."""
+    sets = [synth.make_pair(n, 16, seed=300 + i)[0] for i, n in enumerate((900, 2100, 513, 1280))]
+    us = [_unity(api, f) for f in sets]
+    imgs = [api.Image(i, everest.cameras[i % 2]) for i in range(4)]
+    mf = api.MatchFactory(0.8, 70000.0)
+    mf.setSeedFeatures(_unity(api, synth.make_seed(300)))
+    sd0 = mf.getSeedDistances(us[0])
+    jobs = [
+        (mf._params(T.OUT_PAIR, T.MASK_NONE, imgs[0], imgs[1]), us[0], us[1], None),
+        (mf._params(T.OUT_DMATCH, T.MASK_NONE, imgs[0], imgs[2]), us[0], us[2], sd0),
+        (mf._params(T.OUT_PAIR, T.MASK_DOUBLE, imgs[0], imgs[1], 2000.0, 5.0), us[0], us[1], sd0),
+        (mf._params(T.OUT_MATCH, T.MASK_NONE, imgs[1], imgs[3]), us[1], us[3], None),
+        (mf._params(T.OUT_PAIR, T.MASK_NONE, imgs[2], imgs[3]), us[2], us[3], None),
+    ]
+    strict = api.MatchFactory(0.8, 1.0)                      # nothing survives d2 < 1: the all-invalid array is kept
+    jobs.append((strict._params(T.OUT_PAIR, T.MASK_NONE, imgs[2], imgs[3]), us[2], us[3], None))
+    got = mf.matchBatch(jobs)
+    assert len(got) == len(jobs)
+    for (p, qf, tf, sd), g in zip(jobs, got):
+        want = mf._run(p, qf, tf, sd)
+        assert g.size() == want.size() and T.fields_equal(g.to_numpy(), want.to_numpy())
+    assert got[-1].size() == us[2].size() and got[0].size() > 0
+
+
 # ------------------------------------------------------------------------------------ sharded targets (multi-GPU data path on one device)
 def test_sharded_targets_merge_equals_single_call(api):
     import torch
