@@ -14,7 +14,14 @@ from bench import WORKLOADS, synth_inputs  # noqa: E402
 from ssrlcv_b200 import _lib, types as T  # noqa: E402
 from ssrlcv_b200.match_factory import Context  # noqa: E402
 
-w = WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "C3"]
+# usage: kerneltiming.py [C1|C2|C3]   or   kerneltiming.py NQ NT [ABS_THRESHOLD]   (unmasked, fold variant)
+abs_thr = 4e4
+if len(sys.argv) > 2:
+    w = dict(nq=int(sys.argv[1]), nt=int(sys.argv[2]), ns=0, mask=0)
+    if len(sys.argv) > 3:
+        abs_thr = float(sys.argv[3])
+else:
+    w = WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "C3"]
 ctx = Context.get(0)
 lib, h = ctx.lib, ctx.handle
 q, t, s = synth_inputs(w, 0)
@@ -23,16 +30,25 @@ td = torch.from_numpy(t.view(np.uint8).reshape(-1)).cuda()
 out = torch.empty(len(q) * 48, dtype=torch.uint8, device="cuda")
 tim = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
 p = _lib.MatchParams()
-p.out_kind, p.mask_kind, p.absolute_threshold, p.relative_threshold, p.compact = T.OUT_DMATCH, 0, 4e4, 0.6, 1
+p.out_kind, p.mask_kind, p.absolute_threshold, p.relative_threshold, p.compact = T.OUT_DMATCH, 0, abs_thr, 0.6, 1
 n_out = C.c_uint64(0)
 hq, ht = C.c_void_p(), C.c_void_p()
 lib.ssrlcv_b200_pack(h, C.c_void_p(qd.data_ptr()), len(q), C.byref(hq))
 lib.ssrlcv_b200_pack(h, C.c_void_p(td.data_ptr()), len(t), C.byref(ht))
-for it in range(3):
-    if it == 2:
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+lib.ssrlcv_b200_set_profiling(h, 1)
+for it in range(6):
+    if it == 5:
         os.environ["SSRLCV_B200_TIMING"] = hex(tim.data_ptr())
     lib.ssrlcv_b200_match(h, C.byref(p), hq, ht, None, 0, C.c_void_p(out.data_ptr()), C.byref(n_out))
+    if it == 4:
+        k_ms, k_n = C.c_double(0), C.c_uint64(0)
+        lib.ssrlcv_b200_kernel_time(h, C.byref(k_ms), C.byref(k_n))
+        print(f"production kernel (no counters): {1e3 * k_ms.value / k_n.value:.2f} us per launch over {k_n.value} launches; matches {n_out.value}")
 torch.cuda.synchronize()
+k_ms, k_n = C.c_double(0), C.c_uint64(0)
+lib.ssrlcv_b200_kernel_time(h, C.byref(k_ms), C.byref(k_n))
+print(f"instrumented kernel: {1e3 * k_ms.value / k_n.value:.2f} us")
 x = tim.cpu().numpy().reshape(148, 16)
 names = ["mma:wait_t_empty", "mma:wait_full", "mma:total", "tma:wait_empty", "epi0:wait_t_full", "epi0:work", "epi0:resolve", "epi0:total",
          "epi5:wait_t_full", "epi5:work", "epi5:resolve", "epi5:total", "res0:wait", "res0:work"]
