@@ -77,7 +77,31 @@ struct ssrlcv_b200_ctx {
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
+  // pack() does not synchronise: the (hmin, hmax) of a set lands in a pinned slot and is read when a match first
+  // needs it (set_resolve).  Slots and their events are recycled through this free list.
+  struct PackSlot { int32_t* mm; cudaEvent_t ready; };
+  std::vector<PackSlot> free_slots;
+  std::vector<int32_t*> slot_blocks;
 };
+
+static int slot_acquire(ssrlcv_b200_ctx* ctx, ssrlcv_b200_ctx::PackSlot& out) {
+  if (ctx->free_slots.empty()) {
+    constexpr int kPerBlock = 256;
+    int32_t* block = nullptr;
+    cudaError_t e = cudaMallocHost(&block, kPerBlock * 2 * sizeof(int32_t));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    ctx->slot_blocks.push_back(block);
+    for (int i = 0; i < kPerBlock; ++i) {
+      ssrlcv_b200_ctx::PackSlot s{block + 2 * i, nullptr};
+      e = cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      ctx->free_slots.push_back(s);
+    }
+  }
+  out = ctx->free_slots.back();
+  ctx->free_slots.pop_back();
+  return 0;
+}
 
 static int fail(ssrlcv_b200_ctx* c, int code, const char* fmt, ...) {
   if (c) {
@@ -139,6 +163,7 @@ int ssrlcv_b200_create(ssrlcv_b200_ctx** out, int device, void* stream) {
     delete ctx;
     return SSRLCV_B200_ENOMEM;
   }
+  ctx->h_scalars[2] = 0x7fffffff; ctx->h_scalars[3] = 0xffffffffu;   // constant: initial (hmin, hmax) = (INT_MAX, -1)
   *out = ctx;
   return 0;
 }
@@ -149,6 +174,8 @@ void ssrlcv_b200_destroy(ssrlcv_b200_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (Workspace* w : {&ctx->keys, &ctx->flagged, &ctx->counts, &ctx->scratch, &ctx->qmask, &ctx->totals}) if (w->p) cudaFree(w->p);
   if (ctx->hostpin.p) cudaFreeHost(ctx->hostpin.p);
+  for (auto& sl : ctx->free_slots) cudaEventDestroy(sl.ready);
+  for (int32_t* b : ctx->slot_blocks) cudaFreeHost(b);
   if (ctx->d_scalars) cudaFree(ctx->d_scalars);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
   for (auto& pe : ctx->prof_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
@@ -197,6 +224,8 @@ static int encode_map(ssrlcv_b200_ctx* ctx, CUtensorMap* m, void* base, uint64_t
   return 0;
 }
 
+// Enqueue-only: nothing here waits for the device.  The (hmin, hmax) range of the set's norms, which selects the kernel
+// variant and offsets the scores, is copied to a pinned slot and read by set_resolve() when a match first needs it.
 int ssrlcv_b200_pack(ssrlcv_b200_ctx* ctx, const void* features_dev, uint64_t n, ssrlcv_b200_set** out) {
   if (!ctx || !out || (n && !features_dev) || n > 0x7fffffffull) return fail(ctx, SSRLCV_B200_EINVAL, "pack: bad arguments");
   CU(cudaSetDevice(ctx->device));
@@ -207,48 +236,83 @@ int ssrlcv_b200_pack(ssrlcv_b200_ctx* ctx, const void* features_dev, uint64_t n,
   s->n = n;
   s->n_pad = ((n + kRowPad - 1) / kRowPad) * kRowPad;
   if (s->n_pad == 0) s->n_pad = kRowPad;
+  ssrlcv_b200_ctx::PackSlot slot;
+  int rc = slot_acquire(ctx, slot);
+  if (rc) { delete s; return fail(ctx, rc, "pack: pinned slot: %s", cudaGetErrorString(static_cast<cudaError_t>(rc))); }
+  s->h_mm = slot.mm; s->ready = slot.ready; s->resolved = false;
   // one allocation: desc | ext | norm | wcol | loc | sigtheta   (all segments 256-byte aligned since n_pad % 256 == 0)
   const size_t np = s->n_pad;
   const size_t bytes = np * (kDescBytes + kExtBytes + 4 + 4 + 8 + 8);
   uint8_t* base = nullptr;
   cudaError_t e = cudaMallocAsync(&base, bytes, ctx->stream);
-  if (e != cudaSuccess) { delete s; return fail(ctx, static_cast<int>(e), "pack: cudaMallocAsync(%zu): %s", bytes, cudaGetErrorString(e)); }
+  if (e != cudaSuccess) {
+    ctx->free_slots.push_back(slot); delete s;
+    return fail(ctx, static_cast<int>(e), "pack: cudaMallocAsync(%zu): %s", bytes, cudaGetErrorString(e));
+  }
   s->desc = base;
   s->ext = s->desc + np * kDescBytes;
   s->norm = reinterpret_cast<int32_t*>(s->ext + np * kExtBytes);
   s->wcol = s->norm + np;
   s->loc = reinterpret_cast<float2*>(s->wcol + np);
   s->sigtheta = s->loc + np;
-  cudaMemsetAsync(base, 0, bytes, ctx->stream);
-  int32_t* hmm = reinterpret_cast<int32_t*>(ctx->d_scalars + 2);
-  ctx->h_scalars[2] = 0x7fffffff; ctx->h_scalars[3] = 0xffffffffu;   // hmin = INT_MAX, hmax = -1
+  // only the padding rows need zeroing (the kernels write every real row); everything when the set is tiny
+  if (np - n >= n) {
+    cudaMemsetAsync(base, 0, bytes, ctx->stream);
+  } else {
+    const size_t pad = np - n;
+    if (pad) {
+      cudaMemsetAsync(s->desc + n * kDescBytes, 0, pad * kDescBytes, ctx->stream);
+      cudaMemsetAsync(s->ext + n * kExtBytes, 0, pad * kExtBytes, ctx->stream);
+      cudaMemsetAsync(s->norm + n, 0, pad * 4, ctx->stream);
+      cudaMemsetAsync(s->wcol + n, 0, pad * 4, ctx->stream);
+      cudaMemsetAsync(s->loc + n, 0, pad * 8, ctx->stream);
+      cudaMemsetAsync(s->sigtheta + n, 0, pad * 8, ctx->stream);
+    }
+  }
+  int32_t* hmm = reinterpret_cast<int32_t*>(ctx->d_scalars + 2);   // shared staging: every use is ordered by the stream
   cudaMemcpyAsync(hmm, ctx->h_scalars + 2, 8, cudaMemcpyHostToDevice, ctx->stream);
   launch_pack(ctx->stream, features_dev, n, *s, hmm, ctx->sm_count);
   if (n) ctx->launches += 2;
-  cudaMemcpyAsync(ctx->h_scalars + 2, hmm, 8, cudaMemcpyDeviceToHost, ctx->stream);
-  e = cudaStreamSynchronize(ctx->stream);
-  if (e == cudaSuccess) e = cudaGetLastError();
-  if (e != cudaSuccess) { cudaFreeAsync(base, ctx->stream); delete s; return fail(ctx, static_cast<int>(e), "pack: %s", cudaGetErrorString(e)); }
-  s->hmin = static_cast<int32_t>(ctx->h_scalars[2]);
-  s->hmax = static_cast<int32_t>(ctx->h_scalars[3]);
-  s->fold_ok = (n == 0) || (static_cast<int64_t>(s->hmax) - s->hmin + 2 <= kFoldMaxW);
-  if (getenv("SSRLCV_B200_NOFOLD")) s->fold_ok = false;   // test hook: force the epilogue-add variant
-  int rc = encode_map(ctx, &s->map_a, s->desc, np, kDescBytes, kBM, CU_TENSOR_MAP_SWIZZLE_128B);
+  cudaMemcpyAsync(s->h_mm, hmm, 8, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaEventRecord(s->ready, ctx->stream);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { ssrlcv_b200_set_free(s); return fail(ctx, static_cast<int>(e), "pack: %s", cudaGetErrorString(e)); }
+  rc = encode_map(ctx, &s->map_a, s->desc, np, kDescBytes, kBM, CU_TENSOR_MAP_SWIZZLE_128B);
   if (!rc) rc = encode_map(ctx, &s->map_b, s->desc, np, kDescBytes, kBN, CU_TENSOR_MAP_SWIZZLE_128B);
   if (!rc) rc = encode_map(ctx, &s->map_ext, s->ext, np, kExtBytes, kBN, CU_TENSOR_MAP_SWIZZLE_32B);
-  if (rc) { cudaFreeAsync(base, ctx->stream); delete s; return rc; }
+  if (rc) { ssrlcv_b200_set_free(s); return rc; }
   *out = s;
   return 0;
 }
 
-int ssrlcv_b200_pack_host(ssrlcv_b200_ctx* ctx, const void* features_host, uint64_t n, ssrlcv_b200_set** out) {
-  if (!ctx || !out || (n && !features_host)) return fail(ctx, SSRLCV_B200_EINVAL, "pack_host: bad arguments");
+// first use of a set's norm range on the host: wait for its pack (normally long finished)
+static int set_resolve(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* cs) {
+  ssrlcv_b200_set* s = const_cast<ssrlcv_b200_set*>(cs);
+  if (s->resolved) return 0;
+  CU(cudaEventSynchronize(s->ready));
+  s->hmin = s->h_mm[0];
+  s->hmax = s->h_mm[1];
+  s->fold_ok = (s->n == 0) || (static_cast<int64_t>(s->hmax) - s->hmin + 2 <= kFoldMaxW);
+  if (getenv("SSRLCV_B200_NOFOLD")) s->fold_ok = false;   // test hook: force the epilogue-add variant
+  s->resolved = true;
+  return 0;
+}
+
+static int pack_host_async(ssrlcv_b200_ctx* ctx, const void* features_host, uint64_t n, ssrlcv_b200_set** out) {
   CU(cudaSetDevice(ctx->device));
   const size_t bytes = static_cast<size_t>(n) * sizeof(RefFeature);
   int rc = ws_reserve(ctx, ctx->scratch, bytes ? bytes : 16);
   if (rc) return rc;
   if (bytes) CU(cudaMemcpyAsync(ctx->scratch.p, features_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  return ssrlcv_b200_pack(ctx, ctx->scratch.p, n, out);   // pack synchronises, so scratch can be reused afterwards
+  return ssrlcv_b200_pack(ctx, ctx->scratch.p, n, out);   // stream order keeps the scratch buffer safe to reuse
+}
+
+int ssrlcv_b200_pack_host(ssrlcv_b200_ctx* ctx, const void* features_host, uint64_t n, ssrlcv_b200_set** out) {
+  if (!ctx || !out || (n && !features_host)) return fail(ctx, SSRLCV_B200_EINVAL, "pack_host: bad arguments");
+  int rc = pack_host_async(ctx, features_host, n, out);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));                  // the caller's host buffer is free again on return
+  return 0;
 }
 
 uint64_t ssrlcv_b200_set_size(const ssrlcv_b200_set* s) { return s ? s->n : 0; }
@@ -256,7 +320,11 @@ const float* ssrlcv_b200_set_loc(const ssrlcv_b200_set* s) { return s ? reinterp
 void ssrlcv_b200_set_free(ssrlcv_b200_set* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
-  cudaFreeAsync(s->desc, s->ctx->stream);   // stream-ordered: every kernel that reads the set was enqueued before this
+  if (s->desc) cudaFreeAsync(s->desc, s->ctx->stream);   // stream-ordered: every kernel that reads the set was enqueued before this
+  if (s->ready) {
+    // the slot's D2H was enqueued before this point; a later pack that reuses it is ordered after it on the same stream
+    s->ctx->free_slots.push_back(ssrlcv_b200_ctx::PackSlot{s->h_mm, s->ready});
+  }
   delete s;
 }
 
@@ -390,6 +458,7 @@ static int run_engine(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* q, const ssrl
                       uint64_t target_offset, float abs_thr, SmaxArgs& a) {
   int grid = 1;
   int rc = make_plan(ctx, q, t, engine, a, grid);
+  if (!rc) rc = set_resolve(ctx, t);
   if (rc) return rc;
   a.target_offset = target_offset;
   a.t_hmax = t->hmax;
@@ -623,9 +692,10 @@ int ssrlcv_b200_match_host(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params*
   float* seed_dev = nullptr;
   void* out_dev = nullptr;
   const size_t elt = out_elt(p->out_kind);
-  rc = ssrlcv_b200_pack_host(ctx, query_host, n_query, &q);
-  if (!rc) rc = ssrlcv_b200_pack_host(ctx, target_host, n_target, &t);
-  if (!rc && seed_host) rc = ssrlcv_b200_pack_host(ctx, seed_host, n_seed, &s);
+  if ((n_query && !query_host) || (n_target && !target_host) || (seed_host == nullptr && n_seed)) return fail(ctx, SSRLCV_B200_EINVAL, "match_host: bad arguments");
+  rc = pack_host_async(ctx, query_host, n_query, &q);
+  if (!rc) rc = pack_host_async(ctx, target_host, n_target, &t);
+  if (!rc && seed_host) rc = pack_host_async(ctx, seed_host, n_seed, &s);
   if (!rc) {
     // scratch layout after the packs: [out records | seed distances]
     const size_t out_bytes = ((n_query * elt + 255) / 256) * 256;

@@ -134,4 +134,9 @@ __host__ __device__ __forceinline__ void unit_range(const SmaxArgs& a, uint32_t 
 
 struct ssrlcv_b200_set : b200::ssrlcv_b200_set_impl {
   ssrlcv_b200_ctx* ctx;
+  // pack() is enqueue-only: (hmin, hmax) arrive in this pinned slot once `ready` has fired; hmin / hmax / fold_ok of the
+  // impl are valid on the host only after set_resolve() (api.cu)
+  int32_t* h_mm;
+  cudaEvent_t ready;
+  bool resolved;
 };

@@ -58,7 +58,9 @@ class Context:
         torch.cuda.set_device(device)
         self.device = device
         self.handle = C.c_void_p()
-        stream = torch.cuda.current_stream(device).cuda_stream
+        # torch's default stream is the legacy default stream (handle 0): name it explicitly (cudaStreamLegacy = 1) so the
+        # library's work is ordered with the caller's torch ops instead of running on a private non-blocking stream
+        stream = torch.cuda.current_stream(device).cuda_stream or 1
         rc = self.lib.ssrlcv_b200_create(C.byref(self.handle), device, C.c_void_p(stream))
         if rc != 0:
             raise _lib.B200Error(rc, "ssrlcv_b200_create failed (needs an sm_100 GPU)")
