@@ -16,34 +16,21 @@
 
 namespace b200 {
 // pack.cu
-void launch_pack(cudaStream_t, const void*, uint64_t, ssrlcv_b200_set_impl&, int32_t*, int);
+void launch_pack(cudaStream_t, const void*, uint64_t n, uint64_t n_rows, uint64_t row0, ssrlcv_b200_set_impl&, int32_t* meta_dev, int sm_count);
 // smax_tc.cu
-cudaError_t launch_smax(cudaStream_t, int, const ssrlcv_b200_set_impl&, const ssrlcv_b200_set_impl&, const SmaxArgs&, const MaskParams&);
+cudaError_t launch_smax(cudaStream_t, const SmaxBatch&, int mask_kind, bool fold);
 // exact.cu
-void launch_exact(cudaStream_t, const SmaxArgs&, const MaskParams&, int, int);
+void launch_exact(cudaStream_t, const SmaxArgs&, int mask_kind, int sm_count);
+void launch_exact_list(cudaStream_t, const SmaxJob*, uint32_t, int mask_kind, int sm_count);
 void launch_endpoints(cudaStream_t, const MaskParams&, const float2*, uint64_t, float4*);
 void launch_query_masks(cudaStream_t, const MaskParams&, const float2*, uint64_t, float4*);
 void launch_sincos(cudaStream_t, const float*, uint64_t, float*, float*);
 // finalize.cu
-struct FinalizeArgs {
-  uint32_t nq, nq_pad, n_splits;
-  const uint64_t* keys;
-  const float* seed;
-  float abs_thr, ratio;
-  int32_t out_kind, compact;
-  uint32_t qid, tid;
-  const float2* q_loc; const float2* t_loc;
-  const float2* q_sigtheta; const float2* t_sigtheta;
-  const uint8_t* q_desc; const uint8_t* t_desc;
-  void* out;
-  uint32_t* block_counts;
-  uint32_t* total;
-};
 struct CompactArgs {
   const uint8_t* in; uint8_t* out; uint32_t n; uint32_t elt; int32_t pred; float threshold;
   uint32_t* block_counts; uint32_t* total;
 };
-void launch_finalize(cudaStream_t, FinalizeArgs);
+void launch_finalize(cudaStream_t, const FinalizeArgs*, uint32_t, uint32_t);
 void launch_seed_from_keys(cudaStream_t, const uint64_t*, uint32_t, uint32_t, uint32_t, float*);
 void launch_fill_u64(cudaStream_t, uint64_t*, uint64_t, uint64_t);
 void launch_min_keys(cudaStream_t, const uint64_t*, uint32_t, uint32_t, uint32_t, uint64_t*);
@@ -71,8 +58,12 @@ struct ssrlcv_b200_ctx {
   EncodeTiledFn encode = nullptr;
   std::string err;
   uint64_t launches = 0;
-  Workspace keys, flagged, counts, scratch, hostpin, qmask, totals;
-  uint32_t* d_scalars = nullptr;   // [0] n_flagged, [1] total, [2..3] hmin/hmax staging
+  Workspace keys, flagged, counts, scratch, hostpin, qmask, totals, nflag;
+  uint32_t* d_scalars = nullptr;   // [1] total of a single match, [2..3] hmin/hmax staging
+  // job descriptors (SmaxJob / FinalizeArgs arrays) travel host -> device through a small ring of pinned buffers
+  struct Staged { void* h = nullptr; void* d = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; bool pending = false; };
+  Staged staged[8];
+  unsigned staged_next = 0;
   uint32_t* h_scalars = nullptr;   // pinned mirror
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -88,11 +79,11 @@ static int slot_acquire(ssrlcv_b200_ctx* ctx, ssrlcv_b200_ctx::PackSlot& out) {
   if (ctx->free_slots.empty()) {
     constexpr int kPerBlock = 256;
     int32_t* block = nullptr;
-    cudaError_t e = cudaMallocHost(&block, kPerBlock * 2 * sizeof(int32_t));
+    cudaError_t e = cudaMallocHost(&block, kPerBlock * 4 * sizeof(int32_t));
     if (e != cudaSuccess) return static_cast<int>(e);
     ctx->slot_blocks.push_back(block);
     for (int i = 0; i < kPerBlock; ++i) {
-      ssrlcv_b200_ctx::PackSlot s{block + 2 * i, nullptr};
+      ssrlcv_b200_ctx::PackSlot s{block + 4 * i, nullptr};
       e = cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming);
       if (e != cudaSuccess) return static_cast<int>(e);
       ctx->free_slots.push_back(s);
@@ -163,7 +154,6 @@ int ssrlcv_b200_create(ssrlcv_b200_ctx** out, int device, void* stream) {
     delete ctx;
     return SSRLCV_B200_ENOMEM;
   }
-  ctx->h_scalars[2] = 0x7fffffff; ctx->h_scalars[3] = 0xffffffffu;   // constant: initial (hmin, hmax) = (INT_MAX, -1)
   *out = ctx;
   return 0;
 }
@@ -172,7 +162,12 @@ void ssrlcv_b200_destroy(ssrlcv_b200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (Workspace* w : {&ctx->keys, &ctx->flagged, &ctx->counts, &ctx->scratch, &ctx->qmask, &ctx->totals}) if (w->p) cudaFree(w->p);
+  for (Workspace* w : {&ctx->keys, &ctx->flagged, &ctx->counts, &ctx->scratch, &ctx->qmask, &ctx->totals, &ctx->nflag}) if (w->p) cudaFree(w->p);
+  for (auto& st : ctx->staged) {
+    if (st.h) cudaFreeHost(st.h);
+    if (st.d) cudaFree(st.d);
+    if (st.done) cudaEventDestroy(st.done);
+  }
   if (ctx->hostpin.p) cudaFreeHost(ctx->hostpin.p);
   for (auto& sl : ctx->free_slots) cudaEventDestroy(sl.ready);
   for (int32_t* b : ctx->slot_blocks) cudaFreeHost(b);
@@ -240,9 +235,10 @@ int ssrlcv_b200_pack(ssrlcv_b200_ctx* ctx, const void* features_dev, uint64_t n,
   int rc = slot_acquire(ctx, slot);
   if (rc) { delete s; return fail(ctx, rc, "pack: pinned slot: %s", cudaGetErrorString(static_cast<cudaError_t>(rc))); }
   s->h_mm = slot.mm; s->ready = slot.ready; s->resolved = false;
-  // one allocation: desc | ext | norm | wcol | loc | sigtheta   (all segments 256-byte aligned since n_pad % 256 == 0)
+  // one allocation: desc | ext | norm | wcol | loc | sigtheta | meta   (all segments 256-byte aligned since n_pad % 256 == 0);
+  // the pack kernels write every row including the zero padding, so nothing is memset except the 16 bytes of meta
   const size_t np = s->n_pad;
-  const size_t bytes = np * (kDescBytes + kExtBytes + 4 + 4 + 8 + 8);
+  const size_t bytes = np * (kDescBytes + kExtBytes + 4 + 4 + 8 + 8) + 256;
   uint8_t* base = nullptr;
   cudaError_t e = cudaMallocAsync(&base, bytes, ctx->stream);
   if (e != cudaSuccess) {
@@ -255,25 +251,11 @@ int ssrlcv_b200_pack(ssrlcv_b200_ctx* ctx, const void* features_dev, uint64_t n,
   s->wcol = s->norm + np;
   s->loc = reinterpret_cast<float2*>(s->wcol + np);
   s->sigtheta = s->loc + np;
-  // only the padding rows need zeroing (the kernels write every real row); everything when the set is tiny
-  if (np - n >= n) {
-    cudaMemsetAsync(base, 0, bytes, ctx->stream);
-  } else {
-    const size_t pad = np - n;
-    if (pad) {
-      cudaMemsetAsync(s->desc + n * kDescBytes, 0, pad * kDescBytes, ctx->stream);
-      cudaMemsetAsync(s->ext + n * kExtBytes, 0, pad * kExtBytes, ctx->stream);
-      cudaMemsetAsync(s->norm + n, 0, pad * 4, ctx->stream);
-      cudaMemsetAsync(s->wcol + n, 0, pad * 4, ctx->stream);
-      cudaMemsetAsync(s->loc + n, 0, pad * 8, ctx->stream);
-      cudaMemsetAsync(s->sigtheta + n, 0, pad * 8, ctx->stream);
-    }
-  }
-  int32_t* hmm = reinterpret_cast<int32_t*>(ctx->d_scalars + 2);   // shared staging: every use is ordered by the stream
-  cudaMemcpyAsync(hmm, ctx->h_scalars + 2, 8, cudaMemcpyHostToDevice, ctx->stream);
-  launch_pack(ctx->stream, features_dev, n, *s, hmm, ctx->sm_count);
-  if (n) ctx->launches += 2;
-  cudaMemcpyAsync(s->h_mm, hmm, 8, cudaMemcpyDeviceToHost, ctx->stream);
+  s->meta = reinterpret_cast<int32_t*>(s->sigtheta + np);
+  cudaMemsetAsync(s->meta, 0x80, 16, ctx->stream);          // running maxima start at 0x80808080 (pack.cu)
+  launch_pack(ctx->stream, features_dev, n, np, 0, *s, s->meta, ctx->sm_count);
+  ctx->launches += 2;
+  cudaMemcpyAsync(s->h_mm, s->meta, 16, cudaMemcpyDeviceToHost, ctx->stream);
   cudaEventRecord(s->ready, ctx->stream);
   e = cudaGetLastError();
   if (e != cudaSuccess) { ssrlcv_b200_set_free(s); return fail(ctx, static_cast<int>(e), "pack: %s", cudaGetErrorString(e)); }
@@ -290,9 +272,9 @@ static int set_resolve(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* cs) {
   ssrlcv_b200_set* s = const_cast<ssrlcv_b200_set*>(cs);
   if (s->resolved) return 0;
   CU(cudaEventSynchronize(s->ready));
-  s->hmin = s->h_mm[0];
-  s->hmax = s->h_mm[1];
-  s->fold_ok = (s->n == 0) || (static_cast<int64_t>(s->hmax) - s->hmin + 2 <= kFoldMaxW);
+  if (s->h_mm[1] < 0) { s->hmin = 0x7fffffff; s->hmax = -1; }   // empty set
+  else { s->hmin = -s->h_mm[0]; s->hmax = s->h_mm[1]; }
+  s->fold_ok = s->h_mm[2] != 0;
   if (getenv("SSRLCV_B200_NOFOLD")) s->fold_ok = false;   // test hook: force the epilogue-add variant
   s->resolved = true;
   return 0;
@@ -387,6 +369,30 @@ static void fill_mask(const ssrlcv_b200_match_params* p, MaskParams& mp) {
   }
 }
 
+// ---- job staging ------------------------------------------------------------------------------------------------
+// Returns a pinned buffer of `bytes` (fill it, then stage_upload) whose device mirror the kernels of this call read.
+static int stage_acquire(ssrlcv_b200_ctx* ctx, size_t bytes, ssrlcv_b200_ctx::Staged** out) {
+  ssrlcv_b200_ctx::Staged& st = ctx->staged[ctx->staged_next++ % 8];
+  if (st.pending) { CU(cudaEventSynchronize(st.done)); st.pending = false; }   // its previous upload has long finished
+  if (!st.done) CU(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+  if (bytes > st.cap) {
+    if (st.h) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFreeHost(st.h)); CU(cudaFree(st.d)); st.h = st.d = nullptr; st.cap = 0; }
+    const size_t cap = bytes + bytes / 2 + 4096;
+    CU(cudaMallocHost(&st.h, cap));
+    CU(cudaMalloc(&st.d, cap));
+    st.cap = cap;
+  }
+  *out = &st;
+  return 0;
+}
+static int stage_upload(ssrlcv_b200_ctx* ctx, ssrlcv_b200_ctx::Staged* st, size_t bytes) {
+  CU(cudaMemcpyAsync(st->d, st->h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaEventRecord(st->done, ctx->stream));
+  st->pending = true;
+  return 0;
+}
+
+// ---- planning ---------------------------------------------------------------------------------------------------
 // SIMT engine: fixed-length target splits so that (queries x splits) fills the device
 static void plan_simt(const ssrlcv_b200_ctx* ctx, SmaxArgs& a) {
   const uint32_t sms = static_cast<uint32_t>(ctx->sm_count);
@@ -397,37 +403,34 @@ static void plan_simt(const ssrlcv_b200_ctx* ctx, SmaxArgs& a) {
   a.n_splits = a.n_ttiles ? (a.n_ttiles + a.tiles_per_split - 1) / a.tiles_per_split : 1;
   a.n_ctas = 1;
   a.total_tiles = static_cast<uint64_t>(a.n_qtiles) * a.n_ttiles;
+  a.tile_begin = 0; a.tile_end = a.total_tiles;
 }
 
-// Tensor-core engine: cut the linearised (query tile, target tile) space into one contiguous, equally long range per
-// CTA (matcher.cuh).  Every SM gets the same number of tiles (+-1) whatever the shape; a query tile is shared by the
-// few CTAs whose ranges cross it, each writing its own key slot.
-static void plan_tc(const ssrlcv_b200_ctx* ctx, SmaxArgs& a, int& grid) {
-  const uint32_t sms = static_cast<uint32_t>(ctx->sm_count);
-  a.total_tiles = static_cast<uint64_t>(a.n_qtiles) * a.n_ttiles;
-  const uint64_t min_tiles = 4;                       // per-unit fixed cost (A tile, pipeline fill, resolve) ~ a few tiles
-  uint64_t g = a.total_tiles / min_tiles;
+// Tensor-core engine: the tile spaces (query tile x target tile) of all jobs of a launch are laid end to end and cut into
+// one contiguous, equally long range per CTA (matcher.cuh).  Every SM gets the same number of tiles (+-1) whatever the
+// shapes; a query tile is shared by the few CTAs whose ranges cross it, each writing its own key slot.
+static uint32_t launch_ctas(const ssrlcv_b200_ctx* ctx, uint64_t total_tiles) {
+  const uint64_t min_tiles = 4;                         // per-unit fixed cost (A tile, pipeline fill, resolve) ~ a few tiles
+  uint64_t g = total_tiles / min_tiles;
   if (g < 1) g = 1;
-  if (g > sms) g = sms;
-  a.n_ctas = static_cast<uint32_t>(g);
-  a.tiles_per_split = a.n_ttiles;
-  uint32_t slots = 1;
-  if (a.total_tiles) {
-    const uint64_t per = a.total_tiles / a.n_ctas;    // shortest range
-    slots = static_cast<uint32_t>((a.n_ttiles + per - 1) / per) + 1;
-    if (slots > a.n_ctas) slots = a.n_ctas;
-    if (a.n_qtiles <= 8192) {                         // exact: the widest query tile
-      uint32_t widest = 1;
-      for (uint32_t qt = 0; qt < a.n_qtiles; ++qt) {
-        const uint64_t base = static_cast<uint64_t>(qt) * a.n_ttiles;
-        const uint32_t w = cta_of_tile(a.total_tiles, a.n_ctas, base + a.n_ttiles - 1) - cta_of_tile(a.total_tiles, a.n_ctas, base) + 1;
-        if (w > widest) widest = w;
-      }
-      slots = widest;
+  if (g > static_cast<uint64_t>(ctx->sm_count)) g = static_cast<uint64_t>(ctx->sm_count);
+  return static_cast<uint32_t>(g);
+}
+// key slots of a job = the widest crossing of one of its query tiles (total_tiles, n_ctas, tile_begin already set)
+static uint32_t job_slots(const SmaxArgs& a) {
+  const uint64_t per = a.total_tiles / a.n_ctas;        // shortest range
+  uint32_t slots = static_cast<uint32_t>((a.n_ttiles + per - 1) / per) + 1;
+  if (slots > a.n_ctas) slots = a.n_ctas;
+  if (a.n_qtiles <= 8192) {                             // exact
+    uint32_t widest = 1;
+    for (uint32_t qt = 0; qt < a.n_qtiles; ++qt) {
+      const uint64_t base = a.tile_begin + static_cast<uint64_t>(qt) * a.n_ttiles;
+      const uint32_t w = cta_of_tile(a.total_tiles, a.n_ctas, base + a.n_ttiles - 1) - cta_of_tile(a.total_tiles, a.n_ctas, base) + 1;
+      if (w > widest) widest = w;
     }
+    slots = widest;
   }
-  a.n_splits = slots;
-  grid = static_cast<int>(a.n_ctas);
+  return slots;
 }
 
 // largest integer d2 with (float)d2 < abs_thr, i.e. that the reference's `d2 >= abs` test lets through
@@ -439,72 +442,156 @@ static int32_t d2_cap_of(float abs_thr) {
   return static_cast<int32_t>(c) - 1;
 }
 
-// shape-only part of the plan: tile counts, CTA ranges, key slots
-static int make_plan(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* q, const ssrlcv_b200_set* t, int engine, SmaxArgs& a, int& grid) {
-  memset(&a, 0, sizeof a);
-  a.nq = static_cast<uint32_t>(q->n); a.nt = static_cast<uint32_t>(t->n); a.nq_pad = static_cast<uint32_t>(q->n_pad);
-  a.n_qtiles = (a.nq + kBM - 1) / kBM;
-  a.n_ttiles = (a.nt + kBN - 1) / kBN;
-  grid = 1;
-  if (static_cast<uint64_t>(a.n_qtiles) * a.n_ttiles >= (1ull << 32))
-    return fail(ctx, SSRLCV_B200_EINVAL, "%u x %u features is too large for one call: shard the target set (ssrlcv_b200_match_candidates)", a.nq, a.nt);
-  if (engine == SSRLCV_B200_ENGINE_SIMT || a.nq == 0 || a.nt == 0) plan_simt(ctx, a);
-  else plan_tc(ctx, a, grid);
-  return 0;
-}
+// One pair of a batch: inputs, and (after engine_enqueue) where its keys are.
+struct PairWork {
+  const ssrlcv_b200_set* q = nullptr;
+  const ssrlcv_b200_set* t = nullptr;
+  MaskParams mp;
+  int engine = 0;
+  uint64_t target_offset = 0;
+  float abs_thr = 0.f;
+  SmaxArgs a;                     // out: a.keys, a.n_splits, a.nq_pad describe the pair's candidate keys
+};
 
-// runs the distance engine; leaves exact keys in ctx->keys ([n_splits][nq_pad])
-static int run_engine(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* q, const ssrlcv_b200_set* t, const MaskParams& mp, int engine,
-                      uint64_t target_offset, float abs_thr, SmaxArgs& a) {
-  int grid = 1;
-  int rc = make_plan(ctx, q, t, engine, a, grid);
-  if (!rc) rc = set_resolve(ctx, t);
-  if (rc) return rc;
-  a.target_offset = target_offset;
-  a.t_hmax = t->hmax;
-  a.d2_cap = d2_cap_of(abs_thr);
-  a.q_desc = q->desc; a.q_norm = q->norm; a.q_loc = q->loc;
-  a.t_desc = t->desc; a.t_norm = t->norm; a.t_loc = t->loc; a.t_wcol = t->wcol;
-  const size_t n_keys = static_cast<size_t>(a.n_splits) * a.nq_pad;
-  rc = ws_reserve(ctx, ctx->keys, n_keys * sizeof(uint64_t));
-  if (!rc) rc = ws_reserve(ctx, ctx->flagged, n_keys * sizeof(uint32_t));
-  if (rc) return rc;
-  a.keys = static_cast<uint64_t*>(ctx->keys.p);
-  a.flagged = static_cast<uint32_t*>(ctx->flagged.p);
-  a.n_flagged = ctx->d_scalars;
-  a.timing = nullptr;
-  if (const char* tp = getenv("SSRLCV_B200_TIMING")) {       // diagnostics: device buffer address (hex) for cycle counters
-    a.timing = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 16));
-  }
-  if (a.nq == 0) return 0;
-  if (mp.kind != SSRLCV_B200_MASK_NONE && a.nt != 0) {      // per-query mask state, once per call (all padded rows: loc = 0 there)
-    rc = ws_reserve(ctx, ctx->qmask, static_cast<size_t>(a.nq_pad) * 2 * sizeof(float4));
-    if (rc) return rc;
-    launch_query_masks(ctx->stream, mp, q->loc, a.nq_pad, static_cast<float4*>(ctx->qmask.p));
-    a.q_mask = static_cast<const float4*>(ctx->qmask.p);
-    ctx->launches += 1;
-  }
-  if (a.nt == 0) { launch_fill_u64(ctx->stream, a.keys, n_keys, kKeyNone); ctx->launches += 1; return 0; }
-  if (engine == SSRLCV_B200_ENGINE_SIMT) {
-    launch_exact(ctx->stream, a, mp, 0, ctx->sm_count);
-    ctx->launches += 1;
-  } else {
-    // key slots a query tile does not use stay "no candidate" (kKeyNone is all ones)
-    if (a.n_splits > 1) CU(cudaMemsetAsync(a.keys, 0xFF, n_keys * sizeof(uint64_t), ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(uint32_t), ctx->stream));
-    if (ctx->profiling) {
-      if (ctx->prof_used == ctx->prof_events.size()) {
-        cudaEvent_t e0, e1;
-        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-        ctx->prof_events.emplace_back(e0, e1);
+// Runs the distance engine over n pairs: exact candidate keys land in w[i].a.keys ([n_splits][nq_pad]).  All tensor-core
+// pairs with the same (mask kind, fold variant) share ONE persistent launch; nothing here waits for the device.
+// optimistic != NULL: a target set whose pack has not reported back yet is not waited for; the fold variant is launched
+// (the kernel skips the job if the set turns out not to fit the fold digits) and *optimistic tells the caller to check
+// those sets once the stream has been synchronised.  optimistic == NULL: wait for the sets' packs first.
+static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* optimistic) {
+  struct Group { std::vector<uint32_t> idx; uint64_t total = 0; };
+  Group groups[6];
+  size_t keys_total = 0, qmask_total = 0;
+  if (optimistic) *optimistic = false;
+  for (uint32_t i = 0; i < n; ++i) {
+    PairWork& p = w[i];
+    SmaxArgs& a = p.a;
+    memset(&a, 0, sizeof a);
+    a.nq = static_cast<uint32_t>(p.q->n); a.nt = static_cast<uint32_t>(p.t->n); a.nq_pad = static_cast<uint32_t>(p.q->n_pad);
+    a.n_qtiles = (a.nq + kBM - 1) / kBM;
+    a.n_ttiles = (a.nt + kBN - 1) / kBN;
+    const uint64_t tiles = static_cast<uint64_t>(a.n_qtiles) * a.n_ttiles;
+    if (tiles >= (1ull << 32))
+      return fail(ctx, SSRLCV_B200_EINVAL, "%u x %u features is too large for one call: shard the target set (ssrlcv_b200_match_candidates)", a.nq, a.nt);
+    a.target_offset = p.target_offset;
+    a.eps = p.mp.eps;
+    a.t_meta = p.t->meta;
+    a.d2_cap = d2_cap_of(p.abs_thr);
+    a.q_desc = p.q->desc; a.q_norm = p.q->norm; a.q_loc = p.q->loc;
+    a.t_desc = p.t->desc; a.t_norm = p.t->norm; a.t_loc = p.t->loc; a.t_wcol = p.t->wcol;
+    if (p.engine == SSRLCV_B200_ENGINE_SIMT || tiles == 0) {
+      plan_simt(ctx, a);
+    } else {
+      bool fold = true;
+      if (p.t->resolved || !optimistic) {
+        int rc = set_resolve(ctx, p.t);
+        if (rc) return rc;
+        fold = p.t->fold_ok;
+      } else {
+        *optimistic = true;
       }
-      CU(cudaEventRecord(ctx->prof_events[ctx->prof_used].first, ctx->stream));
+      Group& g = groups[p.mp.kind * 2 + (fold ? 1 : 0)];
+      a.tile_begin = g.total;
+      g.total += tiles;
+      a.tile_end = g.total;
+      g.idx.push_back(i);
     }
-    cudaError_t e = launch_smax(ctx->stream, grid, *q, *t, a, mp);
-    if (e != cudaSuccess) return fail(ctx, static_cast<int>(e), "smax launch: %s", cudaGetErrorString(e));
-    if (ctx->profiling) { CU(cudaEventRecord(ctx->prof_events[ctx->prof_used].second, ctx->stream)); ctx->prof_used++; }
-    launch_exact(ctx->stream, a, mp, 1, ctx->sm_count);
-    ctx->launches += 2;
+  }
+  uint32_t n_tc = 0;
+  for (Group& g : groups) {
+    if (g.idx.empty()) continue;
+    const uint32_t n_ctas = launch_ctas(ctx, g.total);
+    for (uint32_t i : g.idx) {
+      SmaxArgs& a = w[i].a;
+      a.total_tiles = g.total; a.n_ctas = n_ctas; a.tiles_per_split = a.n_ttiles;
+      a.n_splits = job_slots(a);
+    }
+    n_tc += static_cast<uint32_t>(g.idx.size());
+  }
+  // ---- workspaces: one region per pair in each
+  std::vector<size_t> keys_off(n), qmask_off(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    keys_off[i] = keys_total;
+    keys_total += static_cast<size_t>(w[i].a.n_splits) * w[i].a.nq_pad;
+    qmask_off[i] = qmask_total;
+    if (w[i].mp.kind != SSRLCV_B200_MASK_NONE && w[i].a.nq && w[i].a.nt) qmask_total += static_cast<size_t>(w[i].a.nq_pad) * 2;
+  }
+  int rc = ws_reserve(ctx, ctx->keys, keys_total * sizeof(uint64_t));
+  if (!rc) rc = ws_reserve(ctx, ctx->flagged, keys_total * sizeof(uint32_t));
+  if (!rc && qmask_total) rc = ws_reserve(ctx, ctx->qmask, qmask_total * sizeof(float4));
+  if (rc) return rc;
+  for (uint32_t i = 0; i < n; ++i) {
+    SmaxArgs& a = w[i].a;
+    a.keys = static_cast<uint64_t*>(ctx->keys.p) + keys_off[i];
+    a.flagged = static_cast<uint32_t*>(ctx->flagged.p) + keys_off[i];
+  }
+  // every key slot starts as "no candidate" (kKeyNone is all ones): slots a query tile does not use, empty target sets
+  if (keys_total) CU(cudaMemsetAsync(ctx->keys.p, 0xFF, keys_total * sizeof(uint64_t), ctx->stream));
+  // ---- per-query mask state, once per masked pair (all padded rows: loc = 0 there)
+  for (uint32_t i = 0; i < n; ++i) {
+    PairWork& p = w[i];
+    if (p.mp.kind == SSRLCV_B200_MASK_NONE || p.a.nq == 0 || p.a.nt == 0) continue;
+    float4* qm = static_cast<float4*>(ctx->qmask.p) + qmask_off[i];
+    launch_query_masks(ctx->stream, p.mp, p.q->loc, p.a.nq_pad, qm);
+    p.a.q_mask = qm;
+    ctx->launches += 1;
+  }
+  // ---- tensor-core launches: one per (mask kind, fold variant) group
+  if (n_tc) {
+    // staged blob: [SmaxJob x n_tc][tie-list counters, u32 x n_tc, zero]
+    ssrlcv_b200_ctx::Staged* st = nullptr;
+    const size_t blob = static_cast<size_t>(n_tc) * (sizeof(SmaxJob) + sizeof(uint32_t));
+    rc = stage_acquire(ctx, blob, &st);
+    if (rc) return rc;
+    SmaxJob* hj = static_cast<SmaxJob*>(st->h);
+    uint32_t* h_nflag = reinterpret_cast<uint32_t*>(hj + n_tc);
+    uint32_t* d_nflag = reinterpret_cast<uint32_t*>(static_cast<SmaxJob*>(st->d) + n_tc);
+    uint32_t at = 0;
+    for (Group& g : groups)
+      for (uint32_t i : g.idx) {
+        h_nflag[at] = 0;
+        w[i].a.n_flagged = d_nflag + at;
+        SmaxJob& j = hj[at++];
+        j.map_q = w[i].q->map_a; j.map_t = w[i].t->map_b; j.map_text = w[i].t->map_ext;
+        j.a = w[i].a;
+      }
+    rc = stage_upload(ctx, st, blob);
+    if (rc) return rc;
+    unsigned long long* timing = nullptr;
+    if (const char* tp = getenv("SSRLCV_B200_TIMING"))     // diagnostics: device buffer address (hex) for cycle counters
+      timing = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 16));
+    at = 0;
+    for (int gi = 0; gi < 6; ++gi) {
+      Group& g = groups[gi];
+      if (g.idx.empty()) continue;
+      SmaxBatch b;
+      b.jobs = static_cast<const SmaxJob*>(st->d) + at;
+      b.n_jobs = static_cast<uint32_t>(g.idx.size());
+      b.n_ctas = w[g.idx[0]].a.n_ctas;
+      b.total_tiles = g.total;
+      b.timing = timing;
+      if (ctx->profiling) {
+        if (ctx->prof_used == ctx->prof_events.size()) {
+          cudaEvent_t e0, e1;
+          CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+          ctx->prof_events.emplace_back(e0, e1);
+        }
+        CU(cudaEventRecord(ctx->prof_events[ctx->prof_used].first, ctx->stream));
+      }
+      cudaError_t e = launch_smax(ctx->stream, b, gi / 2, (gi & 1) != 0);
+      if (e != cudaSuccess) return fail(ctx, static_cast<int>(e), "smax launch: %s", cudaGetErrorString(e));
+      if (ctx->profiling) { CU(cudaEventRecord(ctx->prof_events[ctx->prof_used].second, ctx->stream)); ctx->prof_used++; }
+      launch_exact_list(ctx->stream, b.jobs, b.n_jobs, gi / 2, ctx->sm_count);
+      ctx->launches += 2;
+      at += b.n_jobs;
+    }
+  }
+  // ---- SIMT engine pairs (cross-check engine), one launch each
+  for (uint32_t i = 0; i < n; ++i) {
+    PairWork& p = w[i];
+    if (p.engine != SSRLCV_B200_ENGINE_SIMT || p.a.nq == 0 || p.a.nt == 0) continue;
+    launch_exact(ctx->stream, p.a, p.mp.kind, ctx->sm_count);
+    ctx->launches += 1;
   }
   CU(cudaGetLastError());
   return 0;
@@ -513,11 +600,12 @@ static int run_engine(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* q, const ssrl
 int ssrlcv_b200_seed_distances(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* query, const ssrlcv_b200_set* seed, float* out_dev, int engine) {
   if (!ctx || !query || !seed || (query->n && !out_dev)) return fail(ctx, SSRLCV_B200_EINVAL, "seed_distances: bad arguments");
   CU(cudaSetDevice(ctx->device));
-  MaskParams mp; memset(&mp, 0, sizeof mp);
-  SmaxArgs a;
-  int rc = run_engine(ctx, query, seed, mp, engine, 0, FLT_MAX, a);
+  PairWork w;
+  memset(&w.mp, 0, sizeof w.mp);
+  w.q = query; w.t = seed; w.engine = engine; w.abs_thr = FLT_MAX;
+  int rc = engine_enqueue(ctx, &w, 1, nullptr);
   if (rc) return rc;
-  if (a.nq) { launch_seed_from_keys(ctx->stream, a.keys, a.nq, a.nq_pad, a.n_splits, out_dev); ctx->launches += 1; }
+  if (w.a.nq) { launch_seed_from_keys(ctx->stream, w.a.keys, w.a.nq, w.a.nq_pad, w.a.n_splits, out_dev); ctx->launches += 1; }
   CU(cudaGetLastError());
   return 0;
 }
@@ -532,68 +620,82 @@ static size_t out_elt(int kind) {
   return 0;
 }
 
-// enqueue thresholds / writers / compaction; the number of records written lands in *total_dev (device)
-static int finalize_enqueue(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const ssrlcv_b200_set* q, const uint64_t* keys,
-                            uint32_t n_splits, const float2* t_loc, const ssrlcv_b200_set* t, const float* seed, void* out_dev,
-                            uint32_t* total_dev) {
-  FinalizeArgs f; memset(&f, 0, sizeof f);
-  f.nq = static_cast<uint32_t>(q->n); f.nq_pad = static_cast<uint32_t>(q->n_pad); f.n_splits = n_splits;
-  f.keys = keys; f.seed = seed;
-  f.abs_thr = p->absolute_threshold;
-  f.ratio = ratio_threshold(p->out_kind, p->mask_kind, p->relative_threshold);
-  f.out_kind = p->out_kind; f.compact = p->compact;
-  f.qid = p->query_image_id; f.tid = p->target_image_id;
-  f.q_loc = q->loc; f.t_loc = t_loc;
-  f.q_sigtheta = q->sigtheta; f.t_sigtheta = t ? t->sigtheta : nullptr;
-  f.q_desc = q->desc; f.t_desc = t ? t->desc : nullptr;
-  f.out = out_dev;
-  const uint32_t blocks = (f.nq + 255) / 256;
-  int rc = ws_reserve(ctx, ctx->counts, (blocks + 1) * sizeof(uint32_t));
-  if (rc) return rc;
-  f.block_counts = static_cast<uint32_t*>(ctx->counts.p);
-  f.total = total_dev;
-  launch_finalize(ctx->stream, f);
-  if (f.nq) ctx->launches += 2;
-  return 0;
-}
+// One pair's thresholds / writers / compaction request.
+struct FinalizeWork {
+  const ssrlcv_b200_match_params* p;
+  const ssrlcv_b200_set* q;
+  const uint64_t* keys; uint32_t n_splits; uint32_t key_stride;   // keys: [n_splits][key_stride]
+  const float2* t_loc; const ssrlcv_b200_set* t;                  // t may be NULL (sharded targets: locations only)
+  const float* seed;
+  void* out_dev;
+};
 
-static int finalize_common(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const ssrlcv_b200_set* q, const uint64_t* keys,
-                           uint32_t n_splits, const float2* t_loc, const ssrlcv_b200_set* t, const float* seed, void* out_dev,
-                           uint64_t* n_out) {
-  int rc = finalize_enqueue(ctx, p, q, keys, n_splits, t_loc, t, seed, out_dev, ctx->d_scalars + 1);
+// enqueue thresholds / writers / compaction of n pairs in two launches; the number of records of pair i lands in
+// (*totals_dev)[i] (device memory of the staged blob, valid until the ring slot comes round again)
+static int finalize_enqueue(ssrlcv_b200_ctx* ctx, const FinalizeWork* fw, uint32_t n, const uint32_t** totals_dev) {
+  if (n == 0) return 0;
+  size_t blocks_total = 0;
+  uint32_t max_nq = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t nq = static_cast<uint32_t>(fw[i].q->n);
+    blocks_total += (nq + 255) / 256;
+    if (nq > max_nq) max_nq = nq;
+  }
+  int rc = ws_reserve(ctx, ctx->counts, (blocks_total + 1) * sizeof(uint32_t));
   if (rc) return rc;
-  CU(cudaMemcpyAsync(ctx->h_scalars + 1, ctx->d_scalars + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  ssrlcv_b200_ctx::Staged* st = nullptr;
+  // staged blob: [FinalizeArgs x n][record counts, u32 x n, zero: pairs without queries write nothing]
+  const size_t blob = static_cast<size_t>(n) * (sizeof(FinalizeArgs) + sizeof(uint32_t));
+  rc = stage_acquire(ctx, blob, &st);
+  if (rc) return rc;
+  FinalizeArgs* hf = static_cast<FinalizeArgs*>(st->h);
+  uint32_t* h_totals = reinterpret_cast<uint32_t*>(hf + n);
+  uint32_t* d_totals = reinterpret_cast<uint32_t*>(static_cast<FinalizeArgs*>(st->d) + n);
+  *totals_dev = d_totals;
+  size_t blocks_at = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const FinalizeWork& x = fw[i];
+    FinalizeArgs& f = hf[i];
+    memset(&f, 0, sizeof f);
+    f.nq = static_cast<uint32_t>(x.q->n); f.nq_pad = x.key_stride; f.n_splits = x.n_splits;
+    f.keys = x.keys; f.seed = x.seed;
+    f.abs_thr = x.p->absolute_threshold;
+    f.ratio = ratio_threshold(x.p->out_kind, x.p->mask_kind, x.p->relative_threshold);
+    f.out_kind = x.p->out_kind; f.compact = x.p->compact;
+    f.qid = x.p->query_image_id; f.tid = x.p->target_image_id;
+    f.q_loc = x.q->loc; f.t_loc = x.t_loc;
+    f.q_sigtheta = x.q->sigtheta; f.t_sigtheta = x.t ? x.t->sigtheta : nullptr;
+    f.q_desc = x.q->desc; f.t_desc = x.t ? x.t->desc : nullptr;
+    f.out = x.out_dev;
+    f.block_counts = static_cast<uint32_t*>(ctx->counts.p) + blocks_at;
+    f.total = d_totals + i;
+    h_totals[i] = 0;
+    blocks_at += (f.nq + 255) / 256;
+  }
+  rc = stage_upload(ctx, st, blob);
+  if (rc) return rc;
+  if (max_nq) {
+    for (uint32_t at = 0; at < n; at += 32768) {           // gridDim.y limit
+      const uint32_t m = n - at < 32768 ? n - at : 32768;
+      launch_finalize(ctx->stream, static_cast<const FinalizeArgs*>(st->d) + at, m, max_nq);
+      ctx->launches += 2;
+    }
+  }
   CU(cudaGetLastError());
-  if (n_out) *n_out = ctx->h_scalars[1];
   return 0;
 }
 
 static int check_params(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p) {
   if (!p) return fail(ctx, SSRLCV_B200_EINVAL, "match: params is NULL");
   if (p->out_kind < 0 || p->out_kind > 3 || p->mask_kind < 0 || p->mask_kind > 2) return fail(ctx, SSRLCV_B200_EINVAL, "match: unknown out_kind/mask_kind");
+  if (p->out_kind == SSRLCV_B200_OUT_FEATUREMATCH && p->mask_kind == SSRLCV_B200_MASK_DOUBLE)
+    return fail(ctx, SSRLCV_B200_EINVAL, "the reference has no DoubleConstrained FeatureMatch kernel");
   return 0;
 }
 
-int ssrlcv_b200_match(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const ssrlcv_b200_set* query, const ssrlcv_b200_set* target,
-                      const float* seed_dist_dev, uint64_t n_seed_dist, void* out_dev, uint64_t* n_out) {
-  if (!ctx || !query || !target || !n_out || (query->n && !out_dev)) return fail(ctx, SSRLCV_B200_EINVAL, "match: bad arguments");
-  int rc = check_params(ctx, p);
-  if (rc) return rc;
-  if (seed_dist_dev && n_seed_dist != query->n)
-    return fail(ctx, SSRLCV_B200_ESEEDSIZE, "seedDistances should have come from matching a seed image to queryFeatures");
-  CU(cudaSetDevice(ctx->device));
-  if (p->out_kind == SSRLCV_B200_OUT_FEATUREMATCH && p->mask_kind == SSRLCV_B200_MASK_DOUBLE)
-    return fail(ctx, SSRLCV_B200_EINVAL, "the reference has no DoubleConstrained FeatureMatch kernel");
-  MaskParams mp; fill_mask(p, mp);
-  SmaxArgs a;
-  rc = run_engine(ctx, query, target, mp, p->engine, 0, p->absolute_threshold, a);
-  if (rc) return rc;
-  return finalize_common(ctx, p, query, a.keys, a.n_splits, target->loc, target, seed_dist_dev, out_dev, n_out);
-}
-
-// The pair scheduler's device side: every pair of the batch is enqueued back to back on the context's stream (workspaces are
-// reused in stream order), the per-pair record counts are collected on the device and read back with ONE synchronisation.
+// The pair scheduler's device side (replaces the pair loop of generateMatchesExhaustive, ref: src/MatchFactory.cu:907-936):
+// all pairs of the batch go through ONE persistent tensor-core launch (per mask kind / fold variant), one tie-fallback
+// launch and two finalize launches; the per-pair record counts are read back with ONE synchronisation.
 int ssrlcv_b200_match_batch(ssrlcv_b200_ctx* ctx, uint32_t n_pairs, const ssrlcv_b200_match_params* params,
                             const ssrlcv_b200_set* const* queries, const ssrlcv_b200_set* const* targets,
                             const float* const* seed_dist_dev, void* const* out_dev, uint64_t* n_out) {
@@ -601,47 +703,57 @@ int ssrlcv_b200_match_batch(ssrlcv_b200_ctx* ctx, uint32_t n_pairs, const ssrlcv
   if (n_pairs == 0) return 0;
   CU(cudaSetDevice(ctx->device));
   int rc = 0;
-  size_t max_keys = 0, max_rows = 0;
   for (uint32_t i = 0; i < n_pairs; ++i) {
     rc = check_params(ctx, &params[i]);
     if (rc) return rc;
     if (!queries[i] || !targets[i] || (queries[i]->n && !out_dev[i])) return fail(ctx, SSRLCV_B200_EINVAL, "match_batch: pair %u: bad arguments", i);
-    if (params[i].out_kind == SSRLCV_B200_OUT_FEATUREMATCH && params[i].mask_kind == SSRLCV_B200_MASK_DOUBLE)
-      return fail(ctx, SSRLCV_B200_EINVAL, "the reference has no DoubleConstrained FeatureMatch kernel");
-    SmaxArgs a; int grid;
-    rc = make_plan(ctx, queries[i], targets[i], params[i].engine, a, grid);
-    if (rc) return rc;
-    const size_t nk = static_cast<size_t>(a.n_splits) * a.nq_pad;
-    if (nk > max_keys) max_keys = nk;
-    if (queries[i]->n_pad > max_rows) max_rows = queries[i]->n_pad;
   }
-  // grow every workspace once, up front: a reallocation in the middle of the batch would have to drain the stream
-  rc = ws_reserve(ctx, ctx->keys, max_keys * sizeof(uint64_t));
-  if (!rc) rc = ws_reserve(ctx, ctx->flagged, max_keys * sizeof(uint32_t));
-  if (!rc) rc = ws_reserve(ctx, ctx->qmask, max_rows * 2 * sizeof(float4));
-  if (!rc) rc = ws_reserve(ctx, ctx->counts, (max_rows / 256 + 2) * sizeof(uint32_t));
-  if (!rc) rc = ws_reserve(ctx, ctx->totals, static_cast<size_t>(n_pairs) * sizeof(uint32_t));
-  if (rc) return rc;
   if (ctx->hostpin.cap < n_pairs * sizeof(uint32_t)) {
     if (ctx->hostpin.p) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFreeHost(ctx->hostpin.p)); ctx->hostpin.p = nullptr; ctx->hostpin.cap = 0; }
     CU(cudaMallocHost(&ctx->hostpin.p, n_pairs * sizeof(uint32_t) * 2));
     ctx->hostpin.cap = n_pairs * sizeof(uint32_t) * 2;
   }
-  uint32_t* totals = static_cast<uint32_t*>(ctx->totals.p);
-  for (uint32_t i = 0; i < n_pairs; ++i) {
-    const ssrlcv_b200_match_params* p = &params[i];
-    MaskParams mp; fill_mask(p, mp);
-    SmaxArgs a;
-    rc = run_engine(ctx, queries[i], targets[i], mp, p->engine, 0, p->absolute_threshold, a);
-    if (!rc) rc = finalize_enqueue(ctx, p, queries[i], a.keys, a.n_splits, targets[i]->loc, targets[i],
-                                   seed_dist_dev ? seed_dist_dev[i] : nullptr, out_dev[i], totals + i);
+  std::vector<PairWork> w(n_pairs);
+  std::vector<FinalizeWork> fw(n_pairs);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    for (uint32_t i = 0; i < n_pairs; ++i) {
+      fill_mask(&params[i], w[i].mp);
+      w[i].q = queries[i]; w[i].t = targets[i]; w[i].engine = params[i].engine; w[i].abs_thr = params[i].absolute_threshold;
+    }
+    bool optimistic = false;
+    rc = engine_enqueue(ctx, w.data(), n_pairs, &optimistic);
     if (rc) return rc;
+    for (uint32_t i = 0; i < n_pairs; ++i)
+      fw[i] = FinalizeWork{&params[i], queries[i], w[i].a.keys, w[i].a.n_splits, w[i].a.nq_pad, targets[i]->loc, targets[i],
+                           seed_dist_dev ? seed_dist_dev[i] : nullptr, out_dev[i]};
+    const uint32_t* totals = nullptr;
+    rc = finalize_enqueue(ctx, fw.data(), n_pairs, &totals);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->hostpin.p, totals, n_pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    if (!optimistic) break;
+    // every pack has reported by now: were all the fold variants launched above the right ones?
+    bool redo = false;
+    for (uint32_t i = 0; i < n_pairs; ++i) {
+      rc = set_resolve(ctx, targets[i]);
+      if (rc) return rc;
+      if (params[i].engine != SSRLCV_B200_ENGINE_SIMT && queries[i]->n && targets[i]->n && !targets[i]->fold_ok) redo = true;
+    }
+    if (!redo) break;                                    // otherwise: once more, every set resolved, right variants
   }
-  CU(cudaMemcpyAsync(ctx->hostpin.p, totals, n_pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaGetLastError());
   for (uint32_t i = 0; i < n_pairs; ++i) n_out[i] = static_cast<const uint32_t*>(ctx->hostpin.p)[i];
   return 0;
+}
+
+int ssrlcv_b200_match(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const ssrlcv_b200_set* query, const ssrlcv_b200_set* target,
+                      const float* seed_dist_dev, uint64_t n_seed_dist, void* out_dev, uint64_t* n_out) {
+  if (!ctx || !query || !target || !n_out || (query->n && !out_dev)) return fail(ctx, SSRLCV_B200_EINVAL, "match: bad arguments");
+  if (seed_dist_dev && n_seed_dist != query->n)
+    return fail(ctx, SSRLCV_B200_ESEEDSIZE, "seedDistances should have come from matching a seed image to queryFeatures");
+  const float* seeds[1] = {seed_dist_dev};
+  void* outs[1] = {out_dev};
+  return ssrlcv_b200_match_batch(ctx, 1, p, &query, &target, seed_dist_dev ? seeds : nullptr, outs, n_out);
 }
 
 int ssrlcv_b200_match_candidates(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const ssrlcv_b200_set* query,
@@ -650,18 +762,14 @@ int ssrlcv_b200_match_candidates(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_p
   int rc = check_params(ctx, p);
   if (rc) return rc;
   CU(cudaSetDevice(ctx->device));
-  MaskParams mp; fill_mask(p, mp);
-  SmaxArgs a;
-  rc = run_engine(ctx, query, shard, mp, p->engine, target_offset, p->absolute_threshold, a);
+  PairWork w;
+  fill_mask(p, w.mp);
+  w.q = query; w.t = shard; w.engine = p->engine; w.target_offset = target_offset; w.abs_thr = p->absolute_threshold;
+  rc = engine_enqueue(ctx, &w, 1, nullptr);
   if (rc) return rc;
-  if (a.nq) {
-    // reduce the local splits to one key per query, reusing the seed kernel's min loop via finalize-free path
-    if (a.n_splits == 1) {
-      CU(cudaMemcpyAsync(keys_dev, a.keys, static_cast<size_t>(a.nq) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    } else {
-      launch_min_keys(ctx->stream, a.keys, a.nq, a.nq_pad, a.n_splits, keys_dev);
-      ctx->launches += 1;
-    }
+  if (w.a.nq) {                                            // reduce the local key slots to one key per query
+    launch_min_keys(ctx->stream, w.a.keys, w.a.nq, w.a.nq_pad, w.a.n_splits, keys_dev);
+    ctx->launches += 1;
   }
   CU(cudaGetLastError());
   return 0;
@@ -676,10 +784,17 @@ int ssrlcv_b200_finalize_candidates(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_matc
   if (p->out_kind == SSRLCV_B200_OUT_FEATUREMATCH) return fail(ctx, SSRLCV_B200_EINVAL, "FeatureMatch output is not available for sharded targets");
   if (p->out_kind != SSRLCV_B200_OUT_PAIR && !target_loc_dev) return fail(ctx, SSRLCV_B200_EINVAL, "target locations required");
   CU(cudaSetDevice(ctx->device));
-  // keys_dev is [n_shards][nq] (dense): finalize reads with stride nq_pad, so pass nq as the stride
-  ssrlcv_b200_set qview = *query;
-  qview.n_pad = query->n;
-  return finalize_common(ctx, p, &qview, keys_dev, n_shards, reinterpret_cast<const float2*>(target_loc_dev), nullptr, seed_dist_dev, out_dev, n_out);
+  // keys_dev is [n_shards][nq] (dense)
+  FinalizeWork fw{p, query, keys_dev, n_shards, static_cast<uint32_t>(query->n), reinterpret_cast<const float2*>(target_loc_dev), nullptr,
+                  seed_dist_dev, out_dev};
+  const uint32_t* total = nullptr;
+  rc = finalize_enqueue(ctx, &fw, 1, &total);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->h_scalars + 1, total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaGetLastError());
+  *n_out = ctx->h_scalars[1];
+  return 0;
 }
 
 int ssrlcv_b200_match_host(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const void* query_host, uint64_t n_query,

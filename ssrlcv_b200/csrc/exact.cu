@@ -23,9 +23,9 @@ __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
 
 // One CTA (8 warps) per (split, query) item; lane/warp-strided over the target range, then a block-wide min.
 template <int kMask>
-__global__ void __launch_bounds__(256) exact_kernel(SmaxArgs a, MaskParams mp, int use_list) {
-  __shared__ uint64_t s_min[8];
+__device__ __forceinline__ void exact_items(const SmaxArgs& a, int use_list, uint64_t* s_min) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float eps = a.eps;
   const uint32_t total = use_list ? *a.n_flagged : a.n_splits * a.nq;
   for (uint32_t item = blockIdx.x; item < total; item += gridDim.x) {
     uint32_t split, row;
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) exact_kernel(SmaxArgs a, MaskParams mp, i
       const uint32_t e = a.flagged[item];
       split = e / a.nq_pad; row = e % a.nq_pad;
       const uint32_t qt = row / kBM;
-      const uint32_t cta = cta_of_tile(a.total_tiles, a.n_ctas, static_cast<uint64_t>(qt) * a.n_ttiles) + split;
+      const uint32_t cta = cta_of_tile(a.total_tiles, a.n_ctas, a.tile_begin + static_cast<uint64_t>(qt) * a.n_ttiles) + split;
       uint32_t j0, j1;
       unit_range(a, cta, qt, j0, j1);
       f_begin = static_cast<uint64_t>(j0) * kBN;
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) exact_kernel(SmaxArgs a, MaskParams mp, i
     for (uint64_t f = f_begin + threadIdx.x; f < f_end; f += 256) {     // f % 32 == lane for every f of this thread
       if (kMask != SSRLCV_B200_MASK_NONE) {
         const float2 tl = a.t_loc[f];
-        if (mask_skips<kMask>(qm, tl.x, tl.y, mp.eps)) continue;
+        if (mask_skips<kMask>(qm, tl.x, tl.y, eps)) continue;
       }
       const uint4* td = reinterpret_cast<const uint4*>(a.t_desc + f * kDescBytes);
       uint32_t dot = 0;
@@ -84,12 +84,37 @@ __global__ void __launch_bounds__(256) exact_kernel(SmaxArgs a, MaskParams mp, i
   }
 }
 
-void launch_exact(cudaStream_t st, const SmaxArgs& a, const MaskParams& mp, int use_list, int sm_count) {
+// SSRLCV_B200_ENGINE_SIMT: the whole problem of one pair
+template <int kMask>
+__global__ void __launch_bounds__(256) exact_kernel(SmaxArgs a) {
+  __shared__ uint64_t s_min[8];
+  exact_items<kMask>(a, 0, s_min);
+}
+// tie fallback of the tensor-core engine: the flagged (slot, query) entries of every job of a launch
+template <int kMask>
+__global__ void __launch_bounds__(256) exact_list_kernel(const SmaxJob* __restrict__ jobs, uint32_t n_jobs) {
+  __shared__ uint64_t s_min[8];
+  for (uint32_t j = 0; j < n_jobs; ++j) {
+    if (*jobs[j].a.n_flagged == 0) continue;          // the common case: nothing to do for this job
+    const SmaxArgs a = jobs[j].a;
+    exact_items<kMask>(a, 1, s_min);
+  }
+}
+
+void launch_exact(cudaStream_t st, const SmaxArgs& a, int mask_kind, int sm_count) {
   const int blocks = sm_count * 8;
-  switch (mp.kind) {
-    case SSRLCV_B200_MASK_NONE: exact_kernel<SSRLCV_B200_MASK_NONE><<<blocks, 256, 0, st>>>(a, mp, use_list); break;
-    case SSRLCV_B200_MASK_FUNDAMENTAL: exact_kernel<SSRLCV_B200_MASK_FUNDAMENTAL><<<blocks, 256, 0, st>>>(a, mp, use_list); break;
-    default: exact_kernel<SSRLCV_B200_MASK_DOUBLE><<<blocks, 256, 0, st>>>(a, mp, use_list); break;
+  switch (mask_kind) {
+    case SSRLCV_B200_MASK_NONE: exact_kernel<SSRLCV_B200_MASK_NONE><<<blocks, 256, 0, st>>>(a); break;
+    case SSRLCV_B200_MASK_FUNDAMENTAL: exact_kernel<SSRLCV_B200_MASK_FUNDAMENTAL><<<blocks, 256, 0, st>>>(a); break;
+    default: exact_kernel<SSRLCV_B200_MASK_DOUBLE><<<blocks, 256, 0, st>>>(a); break;
+  }
+}
+void launch_exact_list(cudaStream_t st, const SmaxJob* jobs_dev, uint32_t n_jobs, int mask_kind, int sm_count) {
+  const int blocks = sm_count * 4;
+  switch (mask_kind) {
+    case SSRLCV_B200_MASK_NONE: exact_list_kernel<SSRLCV_B200_MASK_NONE><<<blocks, 256, 0, st>>>(jobs_dev, n_jobs); break;
+    case SSRLCV_B200_MASK_FUNDAMENTAL: exact_list_kernel<SSRLCV_B200_MASK_FUNDAMENTAL><<<blocks, 256, 0, st>>>(jobs_dev, n_jobs); break;
+    default: exact_list_kernel<SSRLCV_B200_MASK_DOUBLE><<<blocks, 256, 0, st>>>(jobs_dev, n_jobs); break;
   }
 }
 

@@ -11,21 +11,6 @@
 
 namespace b200 {
 
-struct FinalizeArgs {
-  uint32_t nq, nq_pad, n_splits;
-  const uint64_t* keys;
-  const float* seed;          // nullable
-  float abs_thr, ratio;
-  int32_t out_kind, compact;
-  uint32_t qid, tid;
-  const float2* q_loc; const float2* t_loc;            // t_loc indexed by global f
-  const float2* q_sigtheta; const float2* t_sigtheta;  // FeatureMatch only
-  const uint8_t* q_desc; const uint8_t* t_desc;
-  void* out;
-  uint32_t* block_counts;     // [gridDim.x]
-  uint32_t* total;            // [1]
-};
-
 struct Decision { bool valid; float cur; uint32_t f; bool has; };
 
 __device__ __forceinline__ Decision decide(const FinalizeArgs& a, uint32_t i) {
@@ -51,7 +36,10 @@ __device__ __forceinline__ Decision decide(const FinalizeArgs& a, uint32_t i) {
   return d;
 }
 
-__global__ void __launch_bounds__(256) finalize_count_kernel(FinalizeArgs a) {
+// Both kernels: grid = (blocks of 256 queries, jobs); `jobs` is device memory, one FinalizeArgs per pair of the batch.
+__global__ void __launch_bounds__(256) finalize_count_kernel(const FinalizeArgs* __restrict__ jobs) {
+  const FinalizeArgs a = jobs[blockIdx.y];
+  if (blockIdx.x * blockDim.x >= a.nq) return;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool v = false;
   if (i < a.nq) v = a.compact ? decide(a, i).valid : true;
@@ -64,9 +52,11 @@ __device__ __forceinline__ void store_keypoints(RefKeyPoint* kp, uint32_t qid, u
   kp[1].parentId = static_cast<int32_t>(tid); kp[1].pad_ = 0; kp[1].loc = tl;
 }
 
-__global__ void __launch_bounds__(256) finalize_write_kernel(FinalizeArgs a) {
+__global__ void __launch_bounds__(256) finalize_write_kernel(const FinalizeArgs* __restrict__ jobs) {
   __shared__ uint32_t s_warp[8];
   __shared__ uint32_t s_base;
+  const FinalizeArgs a = jobs[blockIdx.y];
+  if (blockIdx.x * blockDim.x >= a.nq) return;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // exclusive prefix of the preceding blocks' counts
@@ -94,7 +84,7 @@ __global__ void __launch_bounds__(256) finalize_write_kernel(FinalizeArgs a) {
   uint32_t off = base;
   for (int w = 0; w < warp; ++w) off += s_warp[w];
   off += __popc(bal & ((1u << lane) - 1u));
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+  if (blockIdx.x == (a.nq + 255) / 256 - 1 && threadIdx.x == 0) {
     uint32_t t = base;
     for (int w = 0; w < 8; ++w) t += s_warp[w];
     *a.total = t;
@@ -149,11 +139,13 @@ __global__ void __launch_bounds__(256) finalize_write_kernel(FinalizeArgs a) {
   }
 }
 
-void launch_finalize(cudaStream_t st, FinalizeArgs a) {
-  if (a.nq == 0) { cudaMemsetAsync(a.total, 0, sizeof(uint32_t), st); return; }
-  const unsigned blocks = (a.nq + 255) / 256;
-  finalize_count_kernel<<<blocks, 256, 0, st>>>(a);
-  finalize_write_kernel<<<blocks, 256, 0, st>>>(a);
+// jobs_dev: n_jobs FinalizeArgs in device memory; max_nq: the largest nq among them (> 0).  Jobs with nq == 0 must have
+// had their total zeroed by the caller (no block of theirs runs).
+void launch_finalize(cudaStream_t st, const FinalizeArgs* jobs_dev, uint32_t n_jobs, uint32_t max_nq) {
+  if (n_jobs == 0 || max_nq == 0) return;
+  const dim3 grid((max_nq + 255) / 256, n_jobs);
+  finalize_count_kernel<<<grid, 256, 0, st>>>(jobs_dev);
+  finalize_write_kernel<<<grid, 256, 0, st>>>(jobs_dev);
 }
 
 // keys -> float seed distances (min over splits; FLT_MAX when there is no seed feature)

@@ -82,7 +82,8 @@ struct ssrlcv_b200_set_impl {
   int32_t* wcol;      // [n_pad]       W (same value the digits encode), 0 on padding rows
   float2*  loc;       // [n_pad]
   float2*  sigtheta;  // [n_pad]
-  int32_t  hmin, hmax;   // range of |b|^2 >> 1 over the set (host copy)
+  int32_t* meta;      // [4] device scalars written by the pack kernels: -hmin, hmax, fold_ok (pack.cu)
+  int32_t  hmin, hmax;   // range of |b|^2 >> 1 over the set (host copy, valid after set_resolve)
   bool     fold_ok;      // W fits the digit range -> fused extra-K-block path
   CUtensorMap map_a;     // desc, box 128 x kBM rows, SWIZZLE_128B
   CUtensorMap map_b;     // desc, box 128 x kBN rows, SWIZZLE_128B
@@ -102,7 +103,11 @@ struct SmaxArgs {
   // (cta - first cta touching that query tile).  Balanced to one tile, whatever the shape.
   uint32_t n_ctas;
   uint64_t total_tiles;
-  int32_t  t_hmax;               // max over targets of |b|^2 >> 1 (the W offset)
+  // a launch may cover several independent pairs (SmaxJob): the tile spaces of the jobs are laid end to end, this job's
+  // tiles are [tile_begin, tile_end) of the launch's linear space; total_tiles / n_ctas describe the whole launch
+  uint64_t tile_begin, tile_end;
+  float    eps;                  // epipolar mask tolerance (masked modes)
+  const int32_t* t_meta;         // device scalars of the target set (pack.cu): [1] = hmax, the W offset; [2] = fold digits valid
   int32_t  d2_cap;               // largest integer d2 that still passes the absolute threshold; INT32_MAX = no threshold
   uint64_t target_offset;        // global index of target 0 of this set (sharded mode)
   const uint8_t* q_desc; const int32_t* q_norm; const float2* q_loc;
@@ -111,7 +116,37 @@ struct SmaxArgs {
   uint64_t* keys;                // [n_splits][nq_pad]
   uint32_t* flagged;             // list of (slot * nq_pad + row) needing the exact kernel
   uint32_t* n_flagged;
+};
+
+// One (query set, target set) pair of a launch; an array of these lives in device memory.
+struct alignas(128) SmaxJob {
+  CUtensorMap map_q;             // query descriptors,  box 128 B x kBM rows
+  CUtensorMap map_t;             // target descriptors, box 128 B x kBN rows
+  CUtensorMap map_text;          // target fold digits, box  32 B x kBN rows
+  SmaxArgs a;
+};
+struct SmaxBatch {
+  const SmaxJob* jobs;
+  uint32_t n_jobs;
+  uint32_t n_ctas;
+  uint64_t total_tiles;
   unsigned long long* timing;    // optional [gridDim.x][16] cycle counters (diagnostics), or nullptr
+};
+
+// thresholds / writers / compaction of one pair (finalize.cu); an array of these lives in device memory
+struct FinalizeArgs {
+  uint32_t nq, nq_pad, n_splits;
+  const uint64_t* keys;       // [n_splits][nq_pad]
+  const float* seed;          // nullable
+  float abs_thr, ratio;
+  int32_t out_kind, compact;
+  uint32_t qid, tid;
+  const float2* q_loc; const float2* t_loc;            // t_loc indexed by global f
+  const float2* q_sigtheta; const float2* t_sigtheta;  // FeatureMatch only
+  const uint8_t* q_desc; const uint8_t* t_desc;
+  void* out;
+  uint32_t* block_counts;     // [ceil(nq / 256)]
+  uint32_t* total;            // [1]
 };
 
 __host__ __device__ __forceinline__ uint64_t cta_tile_begin(uint64_t total, uint32_t n_ctas, uint32_t c) {
@@ -124,7 +159,7 @@ __host__ __device__ __forceinline__ uint32_t cta_of_tile(uint64_t total, uint32_
 // target tile range [j0, j1) of the unit (cta, qt); empty if the CTA does not touch that query tile
 __host__ __device__ __forceinline__ void unit_range(const SmaxArgs& a, uint32_t cta, uint32_t qt, uint32_t& j0, uint32_t& j1) {
   const uint64_t lo = cta_tile_begin(a.total_tiles, a.n_ctas, cta), hi = cta_tile_begin(a.total_tiles, a.n_ctas, cta + 1);
-  const uint64_t base = static_cast<uint64_t>(qt) * a.n_ttiles;
+  const uint64_t base = a.tile_begin + static_cast<uint64_t>(qt) * a.n_ttiles;
   const uint64_t b = lo > base ? lo : base, e = hi < base + a.n_ttiles ? hi : base + a.n_ttiles;
   if (b >= e) { j0 = j1 = 0; return; }
   j0 = static_cast<uint32_t>(b - base); j1 = static_cast<uint32_t>(e - base);

@@ -9,16 +9,22 @@
 
 namespace b200 {
 
+// Per-set device scalars ("meta", 4 x int32 at the end of the set's allocation), all written on the device so that no host
+// round trip sits between pack and the first match:
+//   meta[0] = max(-h)  (= -hmin)   meta[1] = max(h) (= hmax)   with h = |b|^2 >> 1;  both start at 0x80808080 (one memset)
+//   meta[2] = 1 if every W fits the fold digits (fold_digits_kernel)
+//
 // Two features per warp-iteration: 16 lanes x 8 bytes cover one descriptor (record base is only 8-byte aligned).
-__global__ void __launch_bounds__(256) pack_kernel(const RefFeature* __restrict__ in, uint64_t n,
+// Rows [n, n_rows) are the zero padding of the set and are written here too (no memset of the allocation).
+__global__ void __launch_bounds__(256) pack_kernel(const RefFeature* __restrict__ in, uint64_t n, uint64_t n_rows,
                                                    uint8_t* __restrict__ desc, int32_t* __restrict__ norm,
                                                    float2* __restrict__ loc, float2* __restrict__ sigtheta,
-                                                   int32_t* __restrict__ hminmax) {
+                                                   int32_t* __restrict__ meta) {
   const int lane = threadIdx.x & 31, half = lane >> 4, sub = lane & 15;
   const uint64_t warp_global = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t n_warps = (gridDim.x * (uint64_t)blockDim.x) >> 5;
-  int32_t hmin = 0x7fffffff, hmax = -1;
-  for (uint64_t base = warp_global * 2; base < n; base += n_warps * 2) {
+  int32_t nhmin = static_cast<int32_t>(0x80808080), hmax = static_cast<int32_t>(0x80808080);
+  for (uint64_t base = warp_global * 2; base < n_rows; base += n_warps * 2) {
     const uint64_t i = base + half;
     uint32_t s = 0;
     if (i < n) {
@@ -27,68 +33,84 @@ __global__ void __launch_bounds__(256) pack_kernel(const RefFeature* __restrict_
       *reinterpret_cast<uint2*>(desc + i * kDescBytes + sub * 8) = w;
       s = __dp4a(w.x, w.x, 0u);
       s = __dp4a(w.y, w.y, s);
+    } else if (i < n_rows) {
+      *reinterpret_cast<uint2*>(desc + i * kDescBytes + sub * 8) = make_uint2(0u, 0u);
     }
 #pragma unroll
     for (int o = 8; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (i < n && sub == 0) {
-      norm[i] = static_cast<int32_t>(s);
-      loc[i] = in[i].loc;
-      sigtheta[i] = make_float2(in[i].sigma, in[i].theta);
-      const int32_t h = static_cast<int32_t>(s >> 1);
-      hmin = min(hmin, h);
-      hmax = max(hmax, h);
+    if (sub == 0) {
+      if (i < n) {
+        norm[i] = static_cast<int32_t>(s);
+        loc[i] = in[i].loc;
+        sigtheta[i] = make_float2(in[i].sigma, in[i].theta);
+        const int32_t h = static_cast<int32_t>(s >> 1);
+        nhmin = max(nhmin, -h);
+        hmax = max(hmax, h);
+      } else if (i < n_rows) {
+        norm[i] = 0;
+        loc[i] = make_float2(0.f, 0.f);
+        sigtheta[i] = make_float2(0.f, 0.f);
+      }
     }
   }
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) {
-    hmin = min(hmin, __shfl_xor_sync(0xffffffffu, hmin, o));
+    nhmin = max(nhmin, __shfl_xor_sync(0xffffffffu, nhmin, o));
     hmax = max(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
   }
   if (lane == 0 && hmax >= 0) {
-    atomicMin(&hminmax[0], hmin);
-    atomicMax(&hminmax[1], hmax);
+    atomicMax(&meta[0], nhmin);
+    atomicMax(&meta[1], hmax);
   }
 }
 
-// W = hmax - h + 2 as  digits[0] + 255 * sum(digits[1..31]),  every digit <= 255.
-__global__ void __launch_bounds__(256) fold_digits_kernel(const int32_t* __restrict__ norm, uint64_t n,
-                                                          const int32_t* __restrict__ hminmax,
+// W = hmax - h + 2 as  digits[0] + 255 * sum(digits[1..31]),  every digit <= 255; zero on the padding rows [n, n_rows).
+__global__ void __launch_bounds__(256) fold_digits_kernel(const int32_t* __restrict__ norm, uint64_t n, uint64_t n_rows,
+                                                          int32_t* __restrict__ meta,
                                                           uint8_t* __restrict__ ext, int32_t* __restrict__ wcol) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int32_t hmax = hminmax[1];
-  const int32_t W = hmax - (norm[i] >> 1) + 2;
-  wcol[i] = W;
+  const int32_t hmax = meta[1];
+  if (i == 0) meta[2] = (static_cast<int64_t>(hmax) + meta[0] + 2 <= kFoldMaxW) ? 1 : 0;   // hmax - hmin + 2
+  if (i >= n_rows) return;
   uint32_t words[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (W <= kFoldMaxW) {
-    const uint32_t r = static_cast<uint32_t>(W) % 255u;
-    uint32_t s = static_cast<uint32_t>(W) / 255u;          // <= 31 * 255
-    uint8_t d[32];
-    d[0] = static_cast<uint8_t>(r);
+  int32_t W = 0;
+  if (i < n) {
+    W = hmax - (norm[i] >> 1) + 2;
+    if (W <= kFoldMaxW) {
+      const uint32_t r = static_cast<uint32_t>(W) % 255u;
+      uint32_t s = static_cast<uint32_t>(W) / 255u;          // <= 31 * 255
+      uint8_t d[32];
+      d[0] = static_cast<uint8_t>(r);
 #pragma unroll
-    for (int k = 1; k < 32; ++k) {
-      const uint32_t take = s < 255u ? s : 255u;
-      d[k] = static_cast<uint8_t>(take);
-      s -= take;
+      for (int k = 1; k < 32; ++k) {
+        const uint32_t take = s < 255u ? s : 255u;
+        d[k] = static_cast<uint8_t>(take);
+        s -= take;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        words[k] = d[4 * k] | (d[4 * k + 1] << 8) | (d[4 * k + 2] << 16) | (static_cast<uint32_t>(d[4 * k + 3]) << 24);
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-      words[k] = d[4 * k] | (d[4 * k + 1] << 8) | (d[4 * k + 2] << 16) | (static_cast<uint32_t>(d[4 * k + 3]) << 24);
   }
+  wcol[i] = W;
   uint4* o = reinterpret_cast<uint4*>(ext + i * kExtBytes);
   o[0] = make_uint4(words[0], words[1], words[2], words[3]);
   o[1] = make_uint4(words[4], words[5], words[6], words[7]);
 }
 
-void launch_pack(cudaStream_t st, const void* feat_dev, uint64_t n, ssrlcv_b200_set_impl& s, int32_t* hminmax_dev, int sm_count) {
-  if (n == 0) return;
-  const uint64_t warps_needed = (n + 1) / 2;
+// Packs rows [0, n) of `feat_dev` into rows [row0, row0 + n) of the set's arrays and zero-fills up to row0 + n_rows;
+// meta_dev: the 4 x int32 device scalars of this range (already memset to 0x80).
+void launch_pack(cudaStream_t st, const void* feat_dev, uint64_t n, uint64_t n_rows, uint64_t row0, ssrlcv_b200_set_impl& s,
+                 int32_t* meta_dev, int sm_count) {
+  if (n_rows == 0) return;
+  const uint64_t warps_needed = (n_rows + 1) / 2;
   uint64_t blocks = (warps_needed + 7) / 8;
   const uint64_t cap = static_cast<uint64_t>(sm_count) * 8;
   if (blocks > cap) blocks = cap;
-  pack_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const RefFeature*>(feat_dev), n, s.desc, s.norm, s.loc,
-                                                             s.sigtheta, hminmax_dev);
-  fold_digits_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(s.norm, n, hminmax_dev, s.ext, s.wcol);
+  pack_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const RefFeature*>(feat_dev), n, n_rows, s.desc + row0 * kDescBytes,
+                                                             s.norm + row0, s.loc + row0, s.sigtheta + row0, meta_dev);
+  fold_digits_kernel<<<static_cast<unsigned>((n_rows + 255) / 256), 256, 0, st>>>(s.norm + row0, n, n_rows, meta_dev, s.ext + row0 * kExtBytes,
+                                                                                  s.wcol + row0);
 }
 
 }  // namespace b200

@@ -57,6 +57,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
+// A tensor map that lives in GLOBAL memory (written by a host copy before the launch) must be acquired through the
+// tensormap proxy by the CTA that uses it; maps passed as __grid_constant__ parameters do not need this.
+__device__ __forceinline__ void tma_acquire_desc(const CUtensorMap* m) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
 // 2-D tiled load: coordinates are (inner, outer) in elements.
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1) {
   asm volatile(

@@ -124,9 +124,17 @@ __device__ __forceinline__ uint32_t word_of(const uint4 (&v)[8], int w) {
 // descriptor is spread one 32-bit word per lane and broadcast by shuffle.  Exact integer d2 by dp4a, key
 // (d2, f mod 32, f), warp-wide minimum.  Rows [r_begin, r_begin + r_count) of the query tile, r_count % 4 == 0.
 template <int kMask, int kFly>
-__device__ __forceinline__ void resolve_rows(const SmaxArgs& args, const MaskParams& mp, const WinState* xa, const WinState* xb,
+__device__ __forceinline__ void resolve_rows(const SmaxArgs& job, const WinState* xa, const WinState* xb,
                                              uint32_t qt, uint32_t slot, uint32_t r_begin, uint32_t r_count, int lane) {
   constexpr uint32_t kFull = 0xffffffffu;
+  // `job` lives in device memory: take the fields once (the stores below could alias it as far as the compiler knows)
+  struct {
+    uint32_t nq, nt, nq_pad; float eps; uint64_t target_offset;
+    const uint8_t* q_desc; const int32_t* q_norm; const float4* q_mask;
+    const uint8_t* t_desc; const int32_t* t_norm; const float2* t_loc;
+    uint64_t* keys; uint32_t* flagged; uint32_t* n_flagged;
+  } args = {job.nq, job.nt, job.nq_pad, job.eps, job.target_offset, job.q_desc, job.q_norm, job.q_mask,
+            job.t_desc, job.t_norm, job.t_loc, job.keys, job.flagged, job.n_flagged};
   for (uint32_t g = 0; g < r_count; g += kFly) {
     WinState ms[kFly];
     uint32_t qrow[kFly];
@@ -165,7 +173,7 @@ __device__ __forceinline__ void resolve_rows(const SmaxArgs& args, const MaskPar
         if (kMask != SSRLCV_B200_MASK_NONE) {
           const QueryMask qm = load_query_mask<kMask>(args.q_mask + 2 * static_cast<uint64_t>(qrow[k]));
           const float2 tl = args.t_loc[fs[k]];
-          if (mask_skips<kMask>(qm, tl.x, tl.y, mp.eps)) ok[k] = false;
+          if (mask_skips<kMask>(qm, tl.x, tl.y, args.eps)) ok[k] = false;
         }
         uint32_t dot = 0;
 #pragma unroll
@@ -183,7 +191,7 @@ __device__ __forceinline__ void resolve_rows(const SmaxArgs& args, const MaskPar
           if (kMask != SSRLCV_B200_MASK_NONE) {
             const QueryMask qm = load_query_mask<kMask>(args.q_mask + 2 * static_cast<uint64_t>(qrow[k]));
             const float2 tl = args.t_loc[f2];
-            if (mask_skips<kMask>(qm, tl.x, tl.y, mp.eps)) ok2 = false;
+            if (mask_skips<kMask>(qm, tl.x, tl.y, args.eps)) ok2 = false;
           }
           const uint4* td = reinterpret_cast<const uint4*>(args.t_desc + f2 * kDescBytes);
           uint32_t dot = 0;
@@ -234,23 +242,44 @@ __device__ __forceinline__ void resolve_rows(const SmaxArgs& args, const MaskPar
   }
 }
 
-// Iterates the units of one CTA: the parts of its contiguous tile range that fall inside one query tile.
+// Iterates the units of one CTA: the parts of its contiguous range of the launch's linear tile space that fall inside
+// one query tile of one job.  The jobs' tile spaces are laid end to end (SmaxArgs::tile_begin / tile_end).
 struct UnitIter {
-  uint32_t L, L_end;                           // linear tile indices (the host guarantees total_tiles < 2^32)
+  uint64_t L, L_end;                           // linear tile indices of the launch
+  const SmaxJob* J;                            // job of the current unit
+  uint32_t job;
   uint32_t qt, j0, j1, slot;
   bool last;                                   // the CTA's final unit
-  __device__ __forceinline__ UnitIter(const SmaxArgs& a, uint32_t cta) {
-    L = static_cast<uint32_t>(cta_tile_begin(a.total_tiles, a.n_ctas, cta));
-    L_end = static_cast<uint32_t>(cta_tile_begin(a.total_tiles, a.n_ctas, cta + 1));
+  __device__ __forceinline__ UnitIter(const SmaxBatch& b, uint32_t cta) {
+    L = cta_tile_begin(b.total_tiles, b.n_ctas, cta);
+    L_end = cta_tile_begin(b.total_tiles, b.n_ctas, cta + 1);
+    uint32_t lo = 0, hi = b.n_jobs - 1;        // the job whose range contains L (every job of a launch has tiles)
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (L >= b.jobs[mid].a.tile_end) lo = mid + 1; else hi = mid;
+    }
+    job = lo;
+    J = b.jobs + job;
   }
-  __device__ __forceinline__ bool next(const SmaxArgs& a, uint32_t cta) {
-    if (L >= L_end) return false;
-    const uint32_t n_tt = a.n_ttiles;
-    qt = L / n_tt;
-    j0 = L - qt * n_tt;
-    const uint32_t room = L_end - L;
-    j1 = (n_tt - j0 <= room) ? n_tt : j0 + room;
-    slot = cta - cta_of_tile(a.total_tiles, a.n_ctas, static_cast<uint64_t>(qt) * n_tt);
+  // check_fold: the launch is the fold variant; a job whose target set turned out not to fit the fold digits (the host
+  // launched optimistically, before the set's pack had reported back) is skipped by every role alike and redone by the
+  // host with the other variant.
+  __device__ __forceinline__ bool next(const SmaxBatch& b, uint32_t cta, bool check_fold) {
+    for (;;) {
+      if (L >= L_end) return false;
+      while (L >= b.jobs[job].a.tile_end) ++job;
+      J = b.jobs + job;
+      if (!check_fold || J->a.t_meta[2] != 0) break;
+      L = J->a.tile_end;
+    }
+    const uint32_t n_tt = J->a.n_ttiles;
+    const uint64_t begin = J->a.tile_begin;
+    const uint32_t rel = static_cast<uint32_t>(L - begin);         // a job has fewer than 2^32 tiles
+    qt = rel / n_tt;
+    j0 = rel - qt * n_tt;
+    const uint64_t room = L_end - L;
+    j1 = (n_tt - j0 <= room) ? n_tt : j0 + static_cast<uint32_t>(room);
+    slot = cta - cta_of_tile(b.total_tiles, b.n_ctas, begin + static_cast<uint64_t>(qt) * n_tt);
     L += j1 - j0;
     last = L >= L_end;
     return true;
@@ -261,8 +290,7 @@ struct UnitIter {
 // kTiming: per-role cycle counters (diagnostics build of the same kernel; never used by the product path).
 template <int kMask, bool kFold, bool kTiming>
 __global__ void __launch_bounds__(kThreads, 1)
-smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
-            const __grid_constant__ CUtensorMap map_text, const SmaxArgs args, const MaskParams mp) {
+smax_kernel(const SmaxBatch batch) {
   constexpr bool kCols = (kMask != SSRLCV_B200_MASK_NONE) || !kFold;   // epilogue needs per-target data
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -282,9 +310,6 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_t); tma_prefetch_desc(&map_text);
-  }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kEpiWarps); }
@@ -316,34 +341,45 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     if (elect_one()) {
       uint32_t stage = 0, phase = 0, aslot = 0, aphase = 0, cs = 0, cphase = 0;
       long long tp_wait = 0;
-      UnitIter u(args, blockIdx.x);
-      while (u.next(args, blockIdx.x)) {
+      uint32_t acquired = 0xFFFFFFFFu;
+      UnitIter u(batch, blockIdx.x);
+      while (u.next(batch, blockIdx.x, kFold)) {
+        const CUtensorMap* map_q = &u.J->map_q;
+        const CUtensorMap* map_t = &u.J->map_t;
+        const CUtensorMap* map_text = &u.J->map_text;
+        if (u.job != acquired) {                                   // first use of this job's tensor maps by this CTA
+          tma_acquire_desc(map_q); tma_acquire_desc(map_t);
+          if (kFold) tma_acquire_desc(map_text);
+          acquired = u.job;
+        }
+        const float2* t_loc = u.J->a.t_loc;
+        const int32_t* t_wcol = u.J->a.t_wcol;
         mbar_wait(&a_empty[aslot], aphase ^ 1);
         mbar_arrive_expect_tx(&a_full[aslot], kABytes);
-        tma_load_2d(smem + SmemLayout::a + aslot * kABytes, &map_q, &a_full[aslot], 0, static_cast<int32_t>(u.qt * kBM));
+        tma_load_2d(smem + SmemLayout::a + aslot * kABytes, map_q, &a_full[aslot], 0, static_cast<int32_t>(u.qt * kBM));
         for (uint32_t j = u.j0; j < u.j1; ++j) {
           long long p0 = 0;
           if (kTiming) p0 = clock64();
           mbar_wait(&empty[stage], phase ^ 1);
           if (kTiming) tp_wait += clock64() - p0;
           mbar_arrive_expect_tx(&full[stage], kBBytes + (kFold ? kBExtBytes : 0));
-          tma_load_2d(smem + SmemLayout::b + stage * kBBytes, &map_t, &full[stage], 0, static_cast<int32_t>(j * kBN));
-          if (kFold) tma_load_2d(smem + SmemLayout::bext + stage * kBExtBytes, &map_text, &full[stage], 0, static_cast<int32_t>(j * kBN));
+          tma_load_2d(smem + SmemLayout::b + stage * kBBytes, map_t, &full[stage], 0, static_cast<int32_t>(j * kBN));
+          if (kFold) tma_load_2d(smem + SmemLayout::bext + stage * kBExtBytes, map_text, &full[stage], 0, static_cast<int32_t>(j * kBN));
           if (++stage == kStages) { stage = 0; phase ^= 1; }
           if (kCols) {
             mbar_wait(&c_empty[cs], cphase ^ 1);
             const uint32_t bytes = (kMask != SSRLCV_B200_MASK_NONE ? kColLocBytes : 0) + (!kFold ? kColWBytes : 0);
             mbar_arrive_expect_tx(&c_full[cs], bytes);
             if (kMask != SSRLCV_B200_MASK_NONE)
-              bulk_load_1d(smem + SmemLayout::col_loc + cs * kColLocBytes, args.t_loc + static_cast<uint64_t>(j) * kBN, kColLocBytes, &c_full[cs]);
+              bulk_load_1d(smem + SmemLayout::col_loc + cs * kColLocBytes, t_loc + static_cast<uint64_t>(j) * kBN, kColLocBytes, &c_full[cs]);
             if (!kFold)
-              bulk_load_1d(smem + SmemLayout::col_w + cs * kColWBytes, args.t_wcol + static_cast<uint64_t>(j) * kBN, kColWBytes, &c_full[cs]);
+              bulk_load_1d(smem + SmemLayout::col_w + cs * kColWBytes, t_wcol + static_cast<uint64_t>(j) * kBN, kColWBytes, &c_full[cs]);
             if (++cs == kColStages) { cs = 0; cphase ^= 1; }
           }
         }
         if (++aslot == 2) { aslot = 0; aphase ^= 1; }
       }
-      if (kTiming) args.timing[blockIdx.x * 16 + 3] = tp_wait;
+      if (kTiming) batch.timing[blockIdx.x * 16 + 3] = tp_wait;
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
@@ -353,8 +389,8 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
       uint32_t stage = 0, phase = 0, aslot = 0, aphase = 0, acc = 0, accphase = 0;
       long long tm_wait_acc = 0, tm_wait_full = 0, tm_total0 = 0;
       if (kTiming) tm_total0 = clock64();
-      UnitIter u(args, blockIdx.x);
-      while (u.next(args, blockIdx.x)) {
+      UnitIter u(batch, blockIdx.x);
+      while (u.next(batch, blockIdx.x, kFold)) {
         mbar_wait(&a_full[aslot], aphase);
         const uint64_t a_desc = make_smem_desc(smem_u32(smem + SmemLayout::a + aslot * kABytes), 1024, kSwizzle128B);
         for (uint32_t j = u.j0; j < u.j1; ++j) {
@@ -383,9 +419,9 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         if (++aslot == 2) { aslot = 0; aphase ^= 1; }
       }
       if (kTiming) {
-        args.timing[blockIdx.x * 16 + 0] = tm_wait_acc;
-        args.timing[blockIdx.x * 16 + 1] = tm_wait_full;
-        args.timing[blockIdx.x * 16 + 2] = clock64() - tm_total0;
+        batch.timing[blockIdx.x * 16 + 0] = tm_wait_acc;
+        batch.timing[blockIdx.x * 16 + 1] = tm_wait_full;
+        batch.timing[blockIdx.x * 16 + 2] = clock64() - tm_total0;
       }
     }
   } else if (warp == 2 || warp == 3) {
@@ -397,21 +433,21 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     const uint32_t rw = warp - 2;
     uint32_t uparity = 0, uiter = 0;
     long long tr_wait = 0, tr_work = 0;
-    UnitIter u(args, blockIdx.x);
-    while (u.next(args, blockIdx.x)) {
+    UnitIter u(batch, blockIdx.x);
+    while (u.next(batch, blockIdx.x, kFold)) {
       if (u.last) break;
       long long w0 = 0, w1 = 0;
       if (kTiming) w0 = clock64();
       mbar_wait(&x_full[uparity], (uiter >> 1) & 1);
       if (kTiming) w1 = clock64();
-      resolve_rows<kMask, 2>(args, mp, xch + (uparity * 2 + 0) * kBM, xch + (uparity * 2 + 1) * kBM, u.qt, u.slot, rw * 64, 64, lane);
+      resolve_rows<kMask, 2>(u.J->a, xch + (uparity * 2 + 0) * kBM, xch + (uparity * 2 + 1) * kBM, u.qt, u.slot, rw * 64, 64, lane);
       __syncwarp();
       if (lane == 0) mbar_arrive(&x_empty[uparity]);
       uparity ^= 1;
       ++uiter;
       if (kTiming) { const long long w2 = clock64(); tr_wait += w1 - w0; tr_work += w2 - w1; }
     }
-    if (kTiming && lane == 0 && rw == 0) { args.timing[blockIdx.x * 16 + 12] = tr_wait; args.timing[blockIdx.x * 16 + 13] = tr_work; }
+    if (kTiming && lane == 0 && rw == 0) { batch.timing[blockIdx.x * 16 + 12] = tr_wait; batch.timing[blockIdx.x * 16 + 13] = tr_work; }
   } else if (warp >= 4) {
     // =============================== epilogue ===============================
     const uint32_t quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32)
@@ -423,11 +459,14 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     uint32_t it = 0, uiter = 0;                       // it: tiles consumed so far -> accumulator slot / column stage and their phases
     long long te_wait = 0, te_work = 0, te_resolve = 0, te_total0 = 0;
     if (kTiming) te_total0 = clock64();
-    UnitIter u(args, blockIdx.x);
-    while (u.next(args, blockIdx.x)) {
+    UnitIter u(batch, blockIdx.x);
+    while (u.next(batch, blockIdx.x, kFold)) {
+      const SmaxArgs& args = u.J->a;                               // device memory: read what the unit needs up front
       const uint32_t row = u.qt * kBM + quarter * 32 + lane;       // this thread's query
+      const uint32_t row_c = min(row, args.nq_pad - 1);
+      const float eps = args.eps;
       QueryMask qm;
-      if (kMask != SSRLCV_B200_MASK_NONE) qm = load_query_mask<kMask>(args.q_mask + 2 * static_cast<uint64_t>(min(row, args.nq_pad - 1)));
+      if (kMask != SSRLCV_B200_MASK_NONE) qm = load_query_mask<kMask>(args.q_mask + 2 * static_cast<uint64_t>(row_c));
 
       // Lowest score that can still pass the absolute threshold: d2 = |a|^2 - 2 (S - hmax - 2) + p <= d2_cap
       // <=> S >= hmax + 2 + ceil((|a|^2 - d2_cap) / 2)  (p = 0 is the permissive case).  Real scores are >= 2,
@@ -435,9 +474,10 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
       WinState st;
       {
         int32_t floor_s = 2;
-        if (args.d2_cap != 0x7fffffff) {
-          const int32_t qn = args.q_norm[min(row, args.nq_pad - 1)];
-          floor_s = max(2, args.t_hmax + 2 + ((qn - args.d2_cap + 1) >> 1));
+        const int32_t d2_cap = args.d2_cap;
+        if (d2_cap != 0x7fffffff) {
+          const int32_t qn = args.q_norm[row_c];
+          floor_s = max(2, args.t_meta[1] + 2 + ((qn - d2_cap + 1) >> 1));
         }
         st.best = floor_s - 1; st.w1 = kNoWin; st.w2 = kNoWin; st.ovf = 0;
       }
@@ -480,8 +520,8 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
 #pragma unroll
               for (int e = 0; e < 32; e += 2) {
                 const float4 l2 = *reinterpret_cast<const float4*>(&s_loc[(c_begin + k) * kChunk + e]);
-                if (mask_skips<kMask>(qm, l2.x, l2.y, mp.eps)) x[e] = 0;
-                if (mask_skips<kMask>(qm, l2.z, l2.w, mp.eps)) x[e + 1] = 0;
+                if (mask_skips<kMask>(qm, l2.x, l2.y, eps)) x[e] = 0;
+                if (mask_skips<kMask>(qm, l2.z, l2.w, eps)) x[e + 1] = 0;
               }
               m = max32(x);
             }
@@ -513,7 +553,7 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
       } else {
         // last unit of this CTA: nothing left to overlap with, so all eight epilogue warps resolve it (16 rows each)
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-        resolve_rows<kMask, 2>(args, mp, xch + (uparity * 2 + 0) * kBM, xch + (uparity * 2 + 1) * kBM, u.qt, u.slot, (warp - 4) * 16, 16, lane);
+        resolve_rows<kMask, 2>(args, xch + (uparity * 2 + 0) * kBM, xch + (uparity * 2 + 1) * kBM, u.qt, u.slot, (warp - 4) * 16, 16, lane);
       }
       ++uiter;
       if (kTiming) te_resolve += clock64() - r0;
@@ -522,7 +562,7 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
       const uint32_t e = warp - 4;
       if (e == 0 || e == 5) {
         const uint32_t o = blockIdx.x * 16 + (e == 0 ? 4 : 8);
-        args.timing[o + 0] = te_wait; args.timing[o + 1] = te_work; args.timing[o + 2] = te_resolve; args.timing[o + 3] = clock64() - te_total0;
+        batch.timing[o + 0] = te_wait; batch.timing[o + 1] = te_work; batch.timing[o + 2] = te_resolve; batch.timing[o + 3] = clock64() - te_total0;
       }
     }
   }
@@ -533,8 +573,7 @@ smax_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
 }
 
 template <int kMask, bool kFold, bool kTiming>
-static cudaError_t launch_one(cudaStream_t st, int grid, const ssrlcv_b200_set_impl& q, const ssrlcv_b200_set_impl& t,
-                              const SmaxArgs& a, const MaskParams& mp) {
+static cudaError_t launch_one(cudaStream_t st, const SmaxBatch& b) {
   auto kern = smax_kernel<kMask, kFold, kTiming>;
   static bool configured = false;
   if (!configured) {
@@ -542,26 +581,24 @@ static cudaError_t launch_one(cudaStream_t st, int grid, const ssrlcv_b200_set_i
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<grid, kThreads, kSmemBytes, st>>>(q.map_a, t.map_b, t.map_ext, a, mp);
+  kern<<<b.n_ctas, kThreads, kSmemBytes, st>>>(b);
   return cudaGetLastError();
 }
 
 template <int kMask>
-static cudaError_t launch_mask(cudaStream_t st, int grid, const ssrlcv_b200_set_impl& q, const ssrlcv_b200_set_impl& t,
-                               const SmaxArgs& a, const MaskParams& mp) {
-  const bool fold = t.fold_ok;
-  if (a.timing) {   // diagnostics build (tools/kerneltiming.py); unconstrained fold variant only
-    if (kMask == SSRLCV_B200_MASK_NONE && fold) return launch_one<SSRLCV_B200_MASK_NONE, true, true>(st, grid, q, t, a, mp);
+static cudaError_t launch_mask(cudaStream_t st, const SmaxBatch& b, bool fold) {
+  if (b.timing) {   // diagnostics build (tools/kerneltiming.py); unconstrained fold variant only
+    if (kMask == SSRLCV_B200_MASK_NONE && fold) return launch_one<SSRLCV_B200_MASK_NONE, true, true>(st, b);
   }
-  return fold ? launch_one<kMask, true, false>(st, grid, q, t, a, mp) : launch_one<kMask, false, false>(st, grid, q, t, a, mp);
+  return fold ? launch_one<kMask, true, false>(st, b) : launch_one<kMask, false, false>(st, b);
 }
 
-cudaError_t launch_smax(cudaStream_t st, int grid, const ssrlcv_b200_set_impl& q, const ssrlcv_b200_set_impl& t,
-                        const SmaxArgs& a, const MaskParams& mp) {
-  switch (mp.kind) {
-    case SSRLCV_B200_MASK_NONE: return launch_mask<SSRLCV_B200_MASK_NONE>(st, grid, q, t, a, mp);
-    case SSRLCV_B200_MASK_FUNDAMENTAL: return launch_mask<SSRLCV_B200_MASK_FUNDAMENTAL>(st, grid, q, t, a, mp);
-    default: return launch_mask<SSRLCV_B200_MASK_DOUBLE>(st, grid, q, t, a, mp);
+// one launch over all jobs of `b` (same mask kind, same fold variant); b.jobs is device memory
+cudaError_t launch_smax(cudaStream_t st, const SmaxBatch& b, int mask_kind, bool fold) {
+  switch (mask_kind) {
+    case SSRLCV_B200_MASK_NONE: return launch_mask<SSRLCV_B200_MASK_NONE>(st, b, fold);
+    case SSRLCV_B200_MASK_FUNDAMENTAL: return launch_mask<SSRLCV_B200_MASK_FUNDAMENTAL>(st, b, fold);
+    default: return launch_mask<SSRLCV_B200_MASK_DOUBLE>(st, b, fold);
   }
 }
 

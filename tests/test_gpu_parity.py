@@ -327,6 +327,44 @@ def test_match_batch_equals_individual_calls(api, everest):
     assert got[-1].size() == us[2].size() and got[0].size() > 0
 
 
+def test_match_batch_one_launch_many_shapes_matches_oracle(api):
+    """One persistent launch over pairs of very different shapes (CTA ranges cross job boundaries, query tiles shared by
+    several CTAs, a one-tile job, a job with an empty target set in the middle) against the CPU oracle, pair by pair."""
+    shapes = [(3000, 20000), (130, 70000), (1, 1), (4096, 4096), (700, 300), (50, 0), (5000, 9000), (129, 257)]
+    mf = api.MatchFactory(1.0, 60000.0)
+    jobs, feats = [], []
+    for i, (nq, nt) in enumerate(shapes):
+        q, t = synth.make_pair(nq, max(nt, 1), seed=900 + i)
+        t = t[:nt]
+        feats.append((q, t))
+        jobs.append((mf._params(T.OUT_DMATCH, T.MASK_NONE, api.Image(2 * i), api.Image(2 * i + 1)), _unity(api, q), _unity(api, t), None))
+    got = mf.matchBatch(jobs)
+    for (q, t), g, (p, _, _, _) in zip(feats, got, jobs):
+        want = api.O.generate_matches(api.O.make_params(out_kind=T.OUT_DMATCH, abs_threshold=60000.0, query_id=p.query_image_id,
+                                                        target_id=p.target_image_id), q, t)
+        if len(want) == 0:      # reference quirk: nothing valid -> the uncompacted all-invalid array is kept
+            assert g.size() == len(q) and np.all(g.to_numpy()["invalid"] == 1)
+        else:
+            assert T.fields_equal(g.to_numpy(), want)
+
+
+def test_full_size_c3_matches_oracle_and_simt_engine(api):
+    """BASELINE config C3 at full size (65 536 x 65 536, the bench workload): tensor-core engine == CPU oracle == SIMT engine,
+    field by field; plus the size-independent property that matching a set against itself returns every query at distance 0
+    with the reference's lane-rule winner among its duplicates."""
+    q, t = synth.make_pair(65536, 65536, seed=0x55524C43)
+    mf = api.MatchFactory(0.6, 200.0 * 200.0)
+    qu, tu = _unity(api, q), _unity(api, t)
+    got = mf.generateDistanceMatches(api.Image(0), qu, api.Image(1), tu).to_numpy()
+    want = api.O.generate_matches(api.O.make_params(out_kind=T.OUT_DMATCH, abs_threshold=200.0 * 200.0, rel_threshold=0.6), q, t)
+    assert len(got) == len(want) and T.fields_equal(got, want)
+    simt = api.MatchFactory(0.6, 200.0 * 200.0, engine=1).generateDistanceMatches(api.Image(0), qu, api.Image(1), tu).to_numpy()
+    assert T.fields_equal(simt, want)
+    me = mf.generateDistanceMatches(api.Image(0), tu, api.Image(0), tu).to_numpy()
+    assert len(me) == len(t) and np.all(me["distance"] == 0.0)
+    assert np.array_equal(me["keyPoints"]["loc"][:, 0], t["loc"])
+
+
 # ------------------------------------------------------------------------------------ sharded targets (multi-GPU data path on one device)
 def test_sharded_targets_merge_equals_single_call(api):
     import torch
