@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libssrlcv_match_b200.so")
+# SSRLCV_B200_LIB: another build of the same library (A/B timing of kernel changes); never a different implementation
+LIB_PATH = os.environ.get("SSRLCV_B200_LIB") or os.path.join(HERE, "libssrlcv_match_b200.so")
 
 ERRORS = {-1: "EINVAL", -2: "ENODEVICE", -3: "ESEEDSIZE", -4: "ETHRESHOLD", -5: "ENOMEM"}
 

@@ -18,7 +18,7 @@ namespace b200 {
 // pack.cu
 void launch_pack(cudaStream_t, const void*, uint64_t n, uint64_t n_rows, uint64_t row0, ssrlcv_b200_set_impl&, int32_t* meta_dev, int sm_count);
 // smax_tc.cu
-cudaError_t launch_smax(cudaStream_t, const SmaxBatch&, int mask_kind, bool fold);
+cudaError_t launch_smax(cudaStream_t, const SmaxBatch&, int mask_kind, bool fold, bool colmask);
 // exact.cu
 void launch_exact(cudaStream_t, const SmaxArgs&, int mask_kind, int sm_count);
 void launch_exact_list(cudaStream_t, const SmaxJob*, uint32_t, int mask_kind, int sm_count);
@@ -450,6 +450,7 @@ struct PairWork {
   int engine = 0;
   uint64_t target_offset = 0;
   float abs_thr = 0.f;
+  bool optimistic_fold = false;   // out: the fold variant was launched before the target set's pack had reported back
   SmaxArgs a;                     // out: a.keys, a.n_splits, a.nq_pad describe the pair's candidate keys
 };
 
@@ -460,13 +461,14 @@ struct PairWork {
 // those sets once the stream has been synchronised.  optimistic == NULL: wait for the sets' packs first.
 static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* optimistic) {
   struct Group { std::vector<uint32_t> idx; uint64_t total = 0; };
-  Group groups[6];
+  Group groups[12];                                       // [mask kind][fold][column-mask regime]
   size_t keys_total = 0, qmask_total = 0;
   if (optimistic) *optimistic = false;
   for (uint32_t i = 0; i < n; ++i) {
     PairWork& p = w[i];
     SmaxArgs& a = p.a;
     memset(&a, 0, sizeof a);
+    p.optimistic_fold = false;
     a.nq = static_cast<uint32_t>(p.q->n); a.nt = static_cast<uint32_t>(p.t->n); a.nq_pad = static_cast<uint32_t>(p.q->n_pad);
     a.n_qtiles = (a.nq + kBM - 1) / kBM;
     a.n_ttiles = (a.nt + kBN - 1) / kBN;
@@ -489,8 +491,11 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
         fold = p.t->fold_ok;
       } else {
         *optimistic = true;
+        p.optimistic_fold = true;
       }
-      Group& g = groups[p.mp.kind * 2 + (fold ? 1 : 0)];
+      // bookkeeping regime (smax_tc.cu): exact column masks for thresholded searches and short target sets
+      const bool colmask = a.d2_cap != 0x7fffffff || a.n_ttiles < 64;
+      Group& g = groups[p.mp.kind * 4 + (fold ? 2 : 0) + (colmask ? 1 : 0)];
       a.tile_begin = g.total;
       g.total += tiles;
       a.tile_end = g.total;
@@ -561,7 +566,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     if (const char* tp = getenv("SSRLCV_B200_TIMING"))     // diagnostics: device buffer address (hex) for cycle counters
       timing = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 16));
     at = 0;
-    for (int gi = 0; gi < 6; ++gi) {
+    for (int gi = 0; gi < 12; ++gi) {
       Group& g = groups[gi];
       if (g.idx.empty()) continue;
       SmaxBatch b;
@@ -578,10 +583,10 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
         }
         CU(cudaEventRecord(ctx->prof_events[ctx->prof_used].first, ctx->stream));
       }
-      cudaError_t e = launch_smax(ctx->stream, b, gi / 2, (gi & 1) != 0);
+      cudaError_t e = launch_smax(ctx->stream, b, gi / 4, (gi & 2) != 0, (gi & 1) != 0);
       if (e != cudaSuccess) return fail(ctx, static_cast<int>(e), "smax launch: %s", cudaGetErrorString(e));
       if (ctx->profiling) { CU(cudaEventRecord(ctx->prof_events[ctx->prof_used].second, ctx->stream)); ctx->prof_used++; }
-      launch_exact_list(ctx->stream, b.jobs, b.n_jobs, gi / 2, ctx->sm_count);
+      launch_exact_list(ctx->stream, b.jobs, b.n_jobs, gi / 4, ctx->sm_count);
       ctx->launches += 2;
       at += b.n_jobs;
     }
@@ -738,7 +743,7 @@ int ssrlcv_b200_match_batch(ssrlcv_b200_ctx* ctx, uint32_t n_pairs, const ssrlcv
     for (uint32_t i = 0; i < n_pairs; ++i) {
       rc = set_resolve(ctx, targets[i]);
       if (rc) return rc;
-      if (params[i].engine != SSRLCV_B200_ENGINE_SIMT && queries[i]->n && targets[i]->n && !targets[i]->fold_ok) redo = true;
+      if (w[i].optimistic_fold && queries[i]->n && targets[i]->n && !targets[i]->fold_ok) redo = true;
     }
     if (!redo) break;                                    // otherwise: once more, every set resolved, right variants
   }

@@ -8,14 +8,16 @@
 // contract the 128 descriptor bytes and a fifth contracts a constant vector [1,255,...,255] with 32
 // base-255 digits of W_b ("fold"), accumulating in TMEM.  The epilogue therefore does no arithmetic on
 // the accumulator except a running 3-input max: per 32-target window it keeps the window maximum and,
-// only when a window reaches the running best, records which window it was.  Nothing of the 128 x Nt
-// score matrix ever reaches shared or global memory.
+// only when a window reaches the query's running best, records the window and WHICH of its 32 columns
+// attained the maximum (a 32-bit mask).  Nothing of the 128 x Nt score matrix ever reaches shared or
+// global memory.
 //
-// After a query tile has seen its whole target range the same warps resolve the recorded window
-// exactly: 32 lanes = the 32 targets of the window = the 32 lanes of the reference's block, exact
-// integer d2 by dp4a, winner by the reference's rule min (d2, f mod 32, f)
-// (ref: src/MatchFactory.cu:1476-1492).  Score ties ACROSS windows (equal d2 up to parity) are rare and
-// are flagged for the exact SIMT kernel (exact.cu) instead of being guessed.
+// S is an exact integer, so the recorded columns ARE the exact answer: for a column f with score S
+//     d2 = |a|^2 - 2 S + 2 hmax + 4 + (|b_f|^2 & 1)
+// and the reference's winner (ref: src/MatchFactory.cu:1476-1492, min of (d2, f mod 32, f)) is the
+// minimum of that key over the recorded columns -- equal scores differ in d2 only by the parity bit.
+// No descriptor is read a second time.  Three or more windows tying at the best score (rare) do not
+// fit the per-query state and are flagged for the exact SIMT kernel (exact.cu) instead of being guessed.
 //
 // Pipeline per CTA (one CTA per SM, persistent over (query tile, target split) work units):
 //   warp 0  TMA producer : A tile (128 x 128 B, SWIZZLE_128B) per unit; per stage a B tile
@@ -26,7 +28,9 @@
 //   warp 2  TMEM allocator, warp 3 writes the constant fold operand
 //   warps 4-11 epilogue  : two warps per TMEM lane quarter (one per half of the 256 columns) so every SM
 //                          sub-partition has two epilogue warps to hide latency: tcgen05.ld 32x32b.x32,
-//                          max3 tree, window bookkeeping, final exact resolve (16 queries per warp)
+//                          max3 tree, window bookkeeping
+//   warps 2-3 also turn the recorded (score, window, column mask) states of a finished unit into keys while
+//   the pipe works on the next unit (one lane per query: a norm parity load and a 64-bit key each)
 // Masked variants (epipolar constraints) evaluate the reference's float mask per (query, target) in the
 // epilogue on target locations staged through a small shared-memory ring.
 #include "geometry.cuh"
@@ -58,8 +62,8 @@ struct SmemLayout {
   static constexpr uint32_t bars = col_w + kColStages * kColWBytes;
   static constexpr uint32_t n_bars = 2 * kStages + 4 + 4 + 2 * kColStages + 4;
   static constexpr uint32_t tmem_ptr = bars + n_bars * 8;
-  static constexpr uint32_t xch = tmem_ptr + 16;                         // 2 (unit parity) x 2 (half) x 128 rows x 16 B
-  static constexpr uint32_t total = xch + 2 * 2 * kBM * 16;
+  static constexpr uint32_t xch = tmem_ptr + 16;                         // 2 (unit parity) x 2 (half) x 128 rows x 24 B
+  static constexpr uint32_t total = xch + 2 * 2 * kBM * 24;
 };
 constexpr uint32_t kSmemBytes = SmemLayout::total + 1024;   // + slack for manual 1024-byte alignment
 
@@ -75,19 +79,21 @@ __device__ __forceinline__ int32_t max32(const uint32_t (&x)[32]) {
   return max(max3(u0, u1, u2), u3);
 }
 
-// per-query running state of the window search: best score and up to two windows that reached it.
+// per-query running state of the window search: best score and up to two (window, column mask) records that reached it.
 // `best` starts at (lowest score that can still pass the absolute threshold) - 1, so with a finite threshold
 // (the reference's MatchFactory(0.6, 200*200), src/Pipeline.cu:175) almost no tile ever touches the bookkeeping;
 // w1 == kNoWin means "no acceptable window yet".
-struct WinState { int32_t best; uint32_t w1, w2, ovf; };
-// branch-free update with one window maximum
-__device__ __forceinline__ void win_update(WinState& s, int32_t m, uint32_t win) {
+struct WinState { int32_t best; uint32_t w1, m1, w2, m2, ovf; };
+// branch-free update with one window maximum and the columns of the window that attained it
+__device__ __forceinline__ void win_update(WinState& s, int32_t m, uint32_t win, uint32_t mask) {
   const bool gt = m > s.best;
   const bool eq = (m == s.best) & (s.w1 != kNoWin);
   const bool second = eq & (s.w2 == kNoWin);
   s.ovf = gt ? 0u : ((eq & !second) ? 1u : s.ovf);
   s.w2 = gt ? kNoWin : (second ? win : s.w2);
+  s.m2 = second ? mask : s.m2;
   s.w1 = gt ? win : s.w1;
+  s.m1 = gt ? mask : s.m1;
   s.best = max(s.best, m);
 }
 __device__ __forceinline__ WinState win_merge(const WinState& a, const WinState& b) {
@@ -101,16 +107,60 @@ __device__ __forceinline__ WinState win_merge(const WinState& a, const WinState&
   if (b.w2 != kNoWin) r.ovf = 1;
   return r;
 }
-
-__device__ __forceinline__ uint64_t warp_min_u64_tc(uint64_t v) {
+// Which columns of a window attained its maximum is recorded (kColMask) only where that is cheap: thresholded searches
+// (almost no window reaches the floor) and short target sets (where re-reading 4 KB of descriptors per query and unit
+// would cost more than the unit's tensor work).  A long unthresholded search updates some lane's running best in ~14 %
+// of its windows; there only the window is recorded and the one or two surviving windows are re-evaluated afterwards.
+// bit e set <=> x[e] == m
+__device__ __forceinline__ uint32_t eq_mask32(const uint32_t (&x)[32], int32_t m) {
+  uint32_t mask = 0;
 #pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    const uint32_t lo = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v), o);
-    const uint32_t hi = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), o);
-    const uint64_t w = (static_cast<uint64_t>(hi) << 32) | lo;
-    v = w < v ? w : v;
+  for (int e = 0; e < 32; ++e) mask |= (static_cast<int32_t>(x[e]) == m) ? (1u << e) : 0u;
+  return mask;
+}
+
+// Turns the recorded states of query row r of tile qt (xa: the warp that saw columns [0,128) of every tile, xb: [128,256))
+// into the reference's winner key.  Every recorded column holds exactly the score `top`, so its distance follows from
+// the score and the parity of the target's norm; the minimum key over the recorded columns is the winner.
+__device__ __forceinline__ void resolve_row(const SmaxArgs& job, const WinState& a, const WinState& b, uint32_t qt, uint32_t slot, uint32_t r) {
+  const uint32_t row = qt * kBM + r;                    // < nq_pad: rows beyond nq land in the padding of the key array
+  const bool va = a.w1 != kNoWin, vb = b.w1 != kNoWin;
+  uint64_t key = kKeyNone;
+  if (va | vb) {
+    const int32_t top = va ? (vb ? max(a.best, b.best) : a.best) : b.best;
+    const int32_t base = __ldg(job.q_norm + row) - 2 * top + 2 * __ldg(job.t_meta + 1) + 4;
+    const int32_t* t_norm = job.t_norm;
+    const uint64_t off = job.target_offset;
+    bool ovf = false;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const WinState& s = h ? b : a;
+      if (s.w1 == kNoWin || s.best != top) continue;
+      ovf |= s.ovf != 0;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint32_t w = i ? s.w2 : s.w1;
+        uint32_t m = i ? s.m2 : s.m1;
+        if (w == kNoWin) continue;
+        while (m) {
+          const uint32_t e = __ffs(m) - 1;
+          m &= m - 1;
+          const uint64_t f = static_cast<uint64_t>(w) * kChunk + e;
+          const uint32_t d2 = static_cast<uint32_t>(base + (__ldg(t_norm + f) & 1));
+          const uint64_t k = make_key(d2, f + off);
+          key = k < key ? k : key;
+        }
+      }
+    }
+    if (ovf) {                                          // three or more windows tied: exact SIMT kernel
+      key = kKeyNeedsExact;
+      if (row < job.nq) {
+        const uint32_t at = atomicAdd(job.n_flagged, 1u);
+        job.flagged[at] = slot * job.nq_pad + row;
+      }
+    }
   }
-  return v;
+  job.keys[static_cast<uint64_t>(slot) * job.nq_pad + row] = key;
 }
 
 __device__ __forceinline__ uint32_t word_of(const uint4 (&v)[8], int w) {
@@ -118,13 +168,13 @@ __device__ __forceinline__ uint32_t word_of(const uint4 (&v)[8], int w) {
   return (w & 3) == 0 ? q.x : (w & 3) == 1 ? q.y : (w & 3) == 2 ? q.z : q.w;
 }
 
-// Exact resolution of recorded windows: turns (best score, window) into the reference's winner.  One warp, four queries
-// in flight: lane l owns target l of each query's window (32 lanes = the 32 targets of the window = the 32 lanes of the
+// Window regime (no column masks were recorded, see smax_kernel): exact re-evaluation of the recorded windows.  One warp,
+// kFly queries in flight: lane l owns target l of each query's window (32 lanes = the 32 targets of the window = the 32 lanes of the
 // reference's block, ref: src/MatchFactory.cu:1476-1492) and holds its 128 descriptor bytes in registers; the query
 // descriptor is spread one 32-bit word per lane and broadcast by shuffle.  Exact integer d2 by dp4a, key
 // (d2, f mod 32, f), warp-wide minimum.  Rows [r_begin, r_begin + r_count) of the query tile, r_count % 4 == 0.
 template <int kMask, int kFly>
-__device__ __forceinline__ void resolve_rows(const SmaxArgs& job, const WinState* xa, const WinState* xb,
+__device__ __forceinline__ void resolve_rows_windows(const SmaxArgs& job, const WinState* xa, const WinState* xb,
                                              uint32_t qt, uint32_t slot, uint32_t r_begin, uint32_t r_count, int lane) {
   constexpr uint32_t kFull = 0xffffffffu;
   // `job` lives in device memory: take the fields once (the stores below could alias it as far as the compiler knows)
@@ -286,9 +336,16 @@ struct UnitIter {
   }
 };
 
-// kMask: SSRLCV_B200_MASK_*.  kFold: W_b carried by the fifth MMA (true) or added in the epilogue (false).
+// kMask: SSRLCV_B200_MASK_*.
+// kFold: W_b carried by the fifth MMA (true: +25 % tensor-pipe time, no epilogue work) or added to every accumulator
+//        element in the epilogue (false: any W, ALU-bound; sets whose norm range does not fit the fold digits).
+//        (A third way -- the epilogue warps storing W_b into the accumulator with tcgen05.st so that four accumulating MMAs
+//        suffice -- was built and measured: the tensor pipe is undisturbed, but the epilogue warps' serial ld -> st -> max
+//        chain takes 1 200 cycles per tile; 0.76 ms against 0.37 ms at 65 536 x 65 536.  profiles/r1c_init_variant.txt)
+// kColMask: record WHICH columns of a window attained its maximum (true) or only the window (false), see above
+//        unit_records_columns(); chosen per job by the host (job_records_columns).
 // kTiming: per-role cycle counters (diagnostics build of the same kernel; never used by the product path).
-template <int kMask, bool kFold, bool kTiming>
+template <int kMask, bool kFold, bool kColMask, bool kTiming>
 __global__ void __launch_bounds__(kThreads, 1)
 smax_kernel(const SmaxBatch batch) {
   constexpr bool kCols = (kMask != SSRLCV_B200_MASK_NONE) || !kFold;   // epilogue needs per-target data
@@ -440,7 +497,15 @@ smax_kernel(const SmaxBatch batch) {
       if (kTiming) w0 = clock64();
       mbar_wait(&x_full[uparity], (uiter >> 1) & 1);
       if (kTiming) w1 = clock64();
-      resolve_rows<kMask, 2>(u.J->a, xch + (uparity * 2 + 0) * kBM, xch + (uparity * 2 + 1) * kBM, u.qt, u.slot, rw * 64, 64, lane);
+      if (kColMask) {
+#pragma unroll
+        for (uint32_t g = 0; g < 2; ++g) {
+          const uint32_t r = rw * 64 + g * 32 + lane;
+          resolve_row(u.J->a, xch[(uparity * 2 + 0) * kBM + r], xch[(uparity * 2 + 1) * kBM + r], u.qt, u.slot, r);
+        }
+      } else {
+        resolve_rows_windows<kMask, 2>(u.J->a, xch + (uparity * 2 + 0) * kBM, xch + (uparity * 2 + 1) * kBM, u.qt, u.slot, rw * 64, 64, lane);
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&x_empty[uparity]);
       uparity ^= 1;
@@ -479,7 +544,7 @@ smax_kernel(const SmaxBatch batch) {
           const int32_t qn = args.q_norm[row_c];
           floor_s = max(2, args.t_meta[1] + 2 + ((qn - d2_cap + 1) >> 1));
         }
-        st.best = floor_s - 1; st.w1 = kNoWin; st.w2 = kNoWin; st.ovf = 0;
+        st.best = floor_s - 1; st.w1 = kNoWin; st.w2 = kNoWin; st.m1 = 0; st.m2 = 0; st.ovf = 0;
       }
       for (uint32_t j = u.j0; j < u.j1; ++j) {
         long long e0 = 0, e1 = 0;
@@ -536,8 +601,16 @@ smax_kernel(const SmaxBatch batch) {
         // Bookkeeping only when some lane's window reaches its running best (warp-uniform test, branch-free body).
         const int32_t mt = max(max(wm[0], wm[1]), max(wm[2], wm[3]));
         if (__any_sync(0xffffffffu, mt >= st.best)) {
+          if (kColMask) {
 #pragma unroll
-          for (uint32_t k = 0; k < kWinPerWarp; ++k) win_update(st, wm[k], j * kWinPerTile + c_begin + k);
+            for (uint32_t k = 0; k < kWinPerWarp; ++k) {
+              if (__any_sync(0xffffffffu, wm[k] >= st.best))     // which columns attained it: only for windows that matter
+                win_update(st, wm[k], j * kWinPerTile + c_begin + k, eq_mask32(v[k], wm[k]));
+            }
+          } else {
+#pragma unroll
+            for (uint32_t k = 0; k < kWinPerWarp; ++k) win_update(st, wm[k], j * kWinPerTile + c_begin + k, 0u);
+          }
         }
         if (kTiming) { const long long e2 = clock64(); te_wait += e1 - e0; te_work += e2 - e1; }
       }
@@ -551,9 +624,14 @@ smax_kernel(const SmaxBatch batch) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&x_full[uparity]);
       } else {
-        // last unit of this CTA: nothing left to overlap with, so all eight epilogue warps resolve it (16 rows each)
+        // last unit of this CTA: nothing left to overlap with, the epilogue warps turn it into keys themselves
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-        resolve_rows<kMask, 2>(args, xch + (uparity * 2 + 0) * kBM, xch + (uparity * 2 + 1) * kBM, u.qt, u.slot, (warp - 4) * 16, 16, lane);
+        if (!kColMask) {
+          resolve_rows_windows<kMask, 2>(args, xch + (uparity * 2 + 0) * kBM, xch + (uparity * 2 + 1) * kBM, u.qt, u.slot, (warp - 4) * 16, 16, lane);
+        } else if (half == 0) {
+          const uint32_t r = quarter * 32 + lane;
+          resolve_row(args, xch[(uparity * 2 + 0) * kBM + r], xch[(uparity * 2 + 1) * kBM + r], u.qt, u.slot, r);
+        }
       }
       ++uiter;
       if (kTiming) te_resolve += clock64() - r0;
@@ -572,9 +650,9 @@ smax_kernel(const SmaxBatch batch) {
   if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
-template <int kMask, bool kFold, bool kTiming>
+template <int kMask, bool kFold, bool kColMask, bool kTiming>
 static cudaError_t launch_one(cudaStream_t st, const SmaxBatch& b) {
-  auto kern = smax_kernel<kMask, kFold, kTiming>;
+  auto kern = smax_kernel<kMask, kFold, kColMask, kTiming>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes));
@@ -586,19 +664,21 @@ static cudaError_t launch_one(cudaStream_t st, const SmaxBatch& b) {
 }
 
 template <int kMask>
-static cudaError_t launch_mask(cudaStream_t st, const SmaxBatch& b, bool fold) {
-  if (b.timing) {   // diagnostics build (tools/kerneltiming.py); unconstrained fold variant only
-    if (kMask == SSRLCV_B200_MASK_NONE && fold) return launch_one<SSRLCV_B200_MASK_NONE, true, true>(st, b);
+static cudaError_t launch_mask(cudaStream_t st, const SmaxBatch& b, bool fold, bool colmask) {
+  if (b.timing) {   // diagnostics build (tools/kerneltiming.py); unconstrained fold variants only
+    if (kMask == SSRLCV_B200_MASK_NONE && fold)
+      return colmask ? launch_one<SSRLCV_B200_MASK_NONE, true, true, true>(st, b) : launch_one<SSRLCV_B200_MASK_NONE, true, false, true>(st, b);
   }
-  return fold ? launch_one<kMask, true, false>(st, b) : launch_one<kMask, false, false>(st, b);
+  if (fold) return colmask ? launch_one<kMask, true, true, false>(st, b) : launch_one<kMask, true, false, false>(st, b);
+  return colmask ? launch_one<kMask, false, true, false>(st, b) : launch_one<kMask, false, false, false>(st, b);
 }
 
-// one launch over all jobs of `b` (same mask kind, same fold variant); b.jobs is device memory
-cudaError_t launch_smax(cudaStream_t st, const SmaxBatch& b, int mask_kind, bool fold) {
+// one launch over all jobs of `b` (same mask kind, fold variant and bookkeeping regime); b.jobs is device memory
+cudaError_t launch_smax(cudaStream_t st, const SmaxBatch& b, int mask_kind, bool fold, bool colmask) {
   switch (mask_kind) {
-    case SSRLCV_B200_MASK_NONE: return launch_mask<SSRLCV_B200_MASK_NONE>(st, b, fold);
-    case SSRLCV_B200_MASK_FUNDAMENTAL: return launch_mask<SSRLCV_B200_MASK_FUNDAMENTAL>(st, b, fold);
-    default: return launch_mask<SSRLCV_B200_MASK_DOUBLE>(st, b, fold);
+    case SSRLCV_B200_MASK_NONE: return launch_mask<SSRLCV_B200_MASK_NONE>(st, b, fold, colmask);
+    case SSRLCV_B200_MASK_FUNDAMENTAL: return launch_mask<SSRLCV_B200_MASK_FUNDAMENTAL>(st, b, fold, colmask);
+    default: return launch_mask<SSRLCV_B200_MASK_DOUBLE>(st, b, fold, colmask);
   }
 }
 

@@ -106,6 +106,31 @@ def test_tie_break_lane_then_index(api, engine):
     assert (want["b"][:, 1] != np.array([min(f for f in range(2048) if (tv[f] == tv[w]).all()) for w in want["b"][:, 1]])).any()
 
 
+@pytest.mark.parametrize("thr", [FLT_MAX, 30000.0])
+def test_tie_break_both_bookkeeping_regimes(api, thr):
+    """The tensor-core kernel records the exact columns that attained a window maximum for thresholded searches and short
+    target sets, and only the window (re-evaluated afterwards) for long unthresholded ones (smax_tc.cu, kColMask).  20 480
+    targets put FLT_MAX into the second regime; ties within a window, across windows, across tiles and across the CTAs'
+    units, two and three ways (three tied windows go to the exact kernel)."""
+    rng = np.random.default_rng(5)
+    qv = synth.sift_descriptors(rng, 160)
+    tv = synth.sift_descriptors(rng, 20480)
+    for k in range(160):
+        near = qv[k].copy(); near[(3 * k) % 128] ^= 1
+        spots = [(40 + 97 * k) % 20480, (41 + 97 * k + 32 * (k % 5)) % 20480, (9000 + 131 * k) % 20480]
+        if k % 4 == 0:
+            spots.append((17000 + 61 * k) % 20480)
+        for f in spots[: 2 + k % 3]:
+            tv[f] = near
+    q, t = T.make_features(qv), T.make_features(tv)
+    mf = api.MatchFactory(1.0, thr)
+    got = mf.generateMatchesIndexOnly(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t)).to_numpy()
+    want = api.O.generate_matches(api.O.make_params(out_kind=T.OUT_PAIR, abs_threshold=thr), q, t)
+    assert len(want) >= 100 and T.fields_equal(got, want)
+    simt = api.MatchFactory(1.0, thr, engine=1).generateMatchesIndexOnly(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t)).to_numpy()
+    assert T.fields_equal(simt, want)
+
+
 @pytest.mark.parametrize("engine", [0, 1])
 def test_degenerate_inputs(api, engine):
     """all-equal descriptors (every score ties), all-zero, all-255 (norm range beyond the fold), empty target set."""
