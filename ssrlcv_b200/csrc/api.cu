@@ -59,7 +59,7 @@ struct ssrlcv_b200_ctx {
   std::string err;
   uint64_t launches = 0;
   Workspace keys, flagged, counts, scratch, hostpin, qmask, totals, nflag;
-  uint32_t* d_scalars = nullptr;   // [1] total of a single match, [2..3] hmin/hmax staging
+  uint32_t* d_scalars = nullptr;   // [1] total of a single match
   // job descriptors (SmaxJob / FinalizeArgs arrays) travel host -> device through a small ring of pinned buffers
   struct Staged { void* h = nullptr; void* d = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; bool pending = false; };
   Staged staged[8];
@@ -68,7 +68,7 @@ struct ssrlcv_b200_ctx {
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
-  // pack() does not synchronise: the (hmin, hmax) of a set lands in a pinned slot and is read when a match first
+  // pack() does not synchronise: the meta scalars of a set land in a pinned slot and are read when a match first
   // needs it (set_resolve).  Slots and their events are recycled through this free list.
   struct PackSlot { int32_t* mm; cudaEvent_t ready; };
   std::vector<PackSlot> free_slots;
@@ -219,8 +219,8 @@ static int encode_map(ssrlcv_b200_ctx* ctx, CUtensorMap* m, void* base, uint64_t
   return 0;
 }
 
-// Enqueue-only: nothing here waits for the device.  The (hmin, hmax) range of the set's norms, which selects the kernel
-// variant and offsets the scores, is copied to a pinned slot and read by set_resolve() when a match first needs it.
+// Enqueue-only: nothing here waits for the device.  Whether every norm of the set fits the fold digits, which selects the
+// kernel variant, is copied to a pinned slot and read by set_resolve() when a match first needs it.
 int ssrlcv_b200_pack(ssrlcv_b200_ctx* ctx, const void* features_dev, uint64_t n, ssrlcv_b200_set** out) {
   if (!ctx || !out || (n && !features_dev) || n > 0x7fffffffull) return fail(ctx, SSRLCV_B200_EINVAL, "pack: bad arguments");
   CU(cudaSetDevice(ctx->device));
@@ -252,9 +252,9 @@ int ssrlcv_b200_pack(ssrlcv_b200_ctx* ctx, const void* features_dev, uint64_t n,
   s->loc = reinterpret_cast<float2*>(s->wcol + np);
   s->sigtheta = s->loc + np;
   s->meta = reinterpret_cast<int32_t*>(s->sigtheta + np);
-  cudaMemsetAsync(s->meta, 0x80, 16, ctx->stream);          // running maxima start at 0x80808080 (pack.cu)
+  cudaMemsetAsync(s->meta, 0, 16, ctx->stream);
   launch_pack(ctx->stream, features_dev, n, np, 0, *s, s->meta, ctx->sm_count);
-  ctx->launches += 2;
+  ctx->launches += 1;
   cudaMemcpyAsync(s->h_mm, s->meta, 16, cudaMemcpyDeviceToHost, ctx->stream);
   cudaEventRecord(s->ready, ctx->stream);
   e = cudaGetLastError();
@@ -272,9 +272,7 @@ static int set_resolve(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* cs) {
   ssrlcv_b200_set* s = const_cast<ssrlcv_b200_set*>(cs);
   if (s->resolved) return 0;
   CU(cudaEventSynchronize(s->ready));
-  if (s->h_mm[1] < 0) { s->hmin = 0x7fffffff; s->hmax = -1; }   // empty set
-  else { s->hmin = -s->h_mm[0]; s->hmax = s->h_mm[1]; }
-  s->fold_ok = s->h_mm[2] != 0;
+  s->fold_ok = s->h_mm[0] == 0;
   if (getenv("SSRLCV_B200_NOFOLD")) s->fold_ok = false;   // test hook: force the epilogue-add variant
   s->resolved = true;
   return 0;

@@ -54,9 +54,14 @@ constexpr int kRowPad = 256;      // packed sets are padded to a multiple of thi
 constexpr int kChunk = 32;        // candidate window (targets) resolved exactly per query
 
 // Fold constants: the extra K block multiplies the constant vector c = [1, 255 x 31] (u8) with
-// per-target digits so that c . digits = W = hmax - (|b|^2 >> 1) + 2  (>= 2 for every real target,
-// 0 for padding rows).  Representable range of W: [0, 255 + 255*31*255].
+// per-target digits so that c . digits = W = kFoldC - (|b|^2 >> 1)  (>= 2 for every real target,
+// 0 for padding rows).  Representable range of W: [0, 255 + 255*31*255], so the fold serves every set whose
+// largest |b|^2 is at most 2 * (kFoldC - 2) + 1 = 4 032 057 (SIFT descriptors: ~65 000; uniform random bytes: ~2.8 M).
+// Sets beyond that take the epilogue-add variant, whose W = kNoFoldC - (|b|^2 >> 1) >= 2 for ANY uint8[128] row.
+// Constant offsets (rather than the set's own maximum norm) make a row's W a function of that row alone.
 constexpr int32_t kFoldMaxW = 255 + 255 * 31 * 255;   // 2 016 030
+constexpr int32_t kFoldC = kFoldMaxW;
+constexpr int32_t kNoFoldC = 128 * 255 * 255 / 2 + 2;  // 4 161 602
 
 // 64-bit candidate key: d2 << 37 | (f & 31) << 32 | f   (min == the reference's winner rule)
 constexpr uint64_t kKeyNone = ~0ull;                 // no candidate
@@ -79,12 +84,11 @@ struct ssrlcv_b200_set_impl {
   uint8_t* desc;      // [n_pad][128]
   uint8_t* ext;       // [n_pad][32]   fold digits
   int32_t* norm;      // [n_pad]       |b|^2
-  int32_t* wcol;      // [n_pad]       W (same value the digits encode), 0 on padding rows
+  int32_t* wcol;      // [n_pad]       kNoFoldC - (|b|^2 >> 1) (epilogue-add variant), 0 on padding rows
   float2*  loc;       // [n_pad]
   float2*  sigtheta;  // [n_pad]
-  int32_t* meta;      // [4] device scalars written by the pack kernels: -hmin, hmax, fold_ok (pack.cu)
-  int32_t  hmin, hmax;   // range of |b|^2 >> 1 over the set (host copy, valid after set_resolve)
-  bool     fold_ok;      // W fits the digit range -> fused extra-K-block path
+  int32_t* meta;      // [4] device scalars written by the pack kernel: [0] != 0 <=> some W does not fit the fold digits
+  bool     fold_ok;      // every W fits the digit range -> fused extra-K-block path (host copy, valid after set_resolve)
   CUtensorMap map_a;     // desc, box 128 x kBM rows, SWIZZLE_128B
   CUtensorMap map_b;     // desc, box 128 x kBN rows, SWIZZLE_128B
   CUtensorMap map_ext;   // ext,  box  32 x kBN rows, SWIZZLE_32B
@@ -107,7 +111,7 @@ struct SmaxArgs {
   // tiles are [tile_begin, tile_end) of the launch's linear space; total_tiles / n_ctas describe the whole launch
   uint64_t tile_begin, tile_end;
   float    eps;                  // epipolar mask tolerance (masked modes)
-  const int32_t* t_meta;         // device scalars of the target set (pack.cu): [1] = hmax, the W offset; [2] = fold digits valid
+  const int32_t* t_meta;         // device scalars of the target set (pack.cu): [0] == 0 <=> fold digits valid
   int32_t  d2_cap;               // largest integer d2 that still passes the absolute threshold; INT32_MAX = no threshold
   uint64_t target_offset;        // global index of target 0 of this set (sharded mode)
   const uint8_t* q_desc; const int32_t* q_norm; const float2* q_loc;
@@ -169,8 +173,8 @@ __host__ __device__ __forceinline__ void unit_range(const SmaxArgs& a, uint32_t 
 
 struct ssrlcv_b200_set : b200::ssrlcv_b200_set_impl {
   ssrlcv_b200_ctx* ctx;
-  // pack() is enqueue-only: (hmin, hmax) arrive in this pinned slot once `ready` has fired; hmin / hmax / fold_ok of the
-  // impl are valid on the host only after set_resolve() (api.cu)
+  // pack() is enqueue-only: the set's meta scalars arrive in this pinned slot once `ready` has fired; fold_ok of the
+  // impl is valid on the host only after set_resolve() (api.cu)
   int32_t* h_mm;
   cudaEvent_t ready;
   bool resolved;

@@ -1,29 +1,30 @@
 // pack.cu -- repack Feature<SIFT_Descriptor>[n] (152-byte AoS, descriptor at byte 24, ref:
 // include/Feature.cuh:30-38,68-94) into the layout the tensor pipeline wants:
 //   desc  uint8[n_pad][128]   one 128-byte row per feature (TMA box rows, SWIZZLE_128B)
-//   ext   uint8[n_pad][32]    base-255 digits of W = hmax - (|b|^2 >> 1) + 2 (extra K block, SWIZZLE_32B)
-//   norm  int32[n_pad]        |b|^2            wcol int32[n_pad]   W
+//   ext   uint8[n_pad][32]    base-255 digits of W = kFoldC - (|b|^2 >> 1) (extra K block, SWIZZLE_32B)
+//   norm  int32[n_pad]        |b|^2            wcol int32[n_pad]   kNoFoldC - (|b|^2 >> 1)
 //   loc   float2[n_pad]       sigtheta float2[n_pad]
 // HBM-bound byte shuffling: 152 B read, 188 B written per feature.
 #include "matcher.cuh"
 
 namespace b200 {
 
-// Per-set device scalars ("meta", 4 x int32 at the end of the set's allocation), all written on the device so that no host
-// round trip sits between pack and the first match:
-//   meta[0] = max(-h)  (= -hmin)   meta[1] = max(h) (= hmax)   with h = |b|^2 >> 1;  both start at 0x80808080 (one memset)
-//   meta[2] = 1 if every W fits the fold digits (fold_digits_kernel)
+// Per-set device scalars ("meta", 4 x int32 at the end of the set's allocation, zeroed by one memset before the pack):
+//   meta[0] != 0  <=>  some target's W does not fit the fold digits (the matcher then runs its epilogue-add variant)
+// W is measured against a CONSTANT offset (kFoldC / kNoFoldC, matcher.cuh), not against the set's own maximum norm, so
+// the digits of a row depend on that row alone: one kernel, no grid-wide dependency, no host round trip.
 //
-// Two features per warp-iteration: 16 lanes x 8 bytes cover one descriptor (record base is only 8-byte aligned).
+// Two features per warp-iteration: 16 lanes x 8 bytes cover one descriptor (record base is only 8-byte aligned); the lane
+// that ends up with the norm also writes the row's scalars and its 32 fold digits.
 // Rows [n, n_rows) are the zero padding of the set and are written here too (no memset of the allocation).
 __global__ void __launch_bounds__(256) pack_kernel(const RefFeature* __restrict__ in, uint64_t n, uint64_t n_rows,
-                                                   uint8_t* __restrict__ desc, int32_t* __restrict__ norm,
-                                                   float2* __restrict__ loc, float2* __restrict__ sigtheta,
+                                                   uint8_t* __restrict__ desc, uint8_t* __restrict__ ext, int32_t* __restrict__ norm,
+                                                   int32_t* __restrict__ wcol, float2* __restrict__ loc, float2* __restrict__ sigtheta,
                                                    int32_t* __restrict__ meta) {
   const int lane = threadIdx.x & 31, half = lane >> 4, sub = lane & 15;
   const uint64_t warp_global = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t n_warps = (gridDim.x * (uint64_t)blockDim.x) >> 5;
-  int32_t nhmin = static_cast<int32_t>(0x80808080), hmax = static_cast<int32_t>(0x80808080);
+  bool bad = false;
   for (uint64_t base = warp_global * 2; base < n_rows; base += n_warps * 2) {
     const uint64_t i = base + half;
     uint32_t s = 0;
@@ -38,68 +39,46 @@ __global__ void __launch_bounds__(256) pack_kernel(const RefFeature* __restrict_
     }
 #pragma unroll
     for (int o = 8; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (sub == 0) {
+    if (sub == 0 && i < n_rows) {
+      // W = kFoldC - h as  digits[0] + 255 * sum(digits[1..31]),  every digit <= 255; zero on padding rows and on rows
+      // whose W does not fit (the whole set then takes the epilogue-add variant, which reads wcol = kNoFoldC - h)
+      uint32_t words[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      int32_t wn = 0;
       if (i < n) {
+        const int32_t h = static_cast<int32_t>(s >> 1);
         norm[i] = static_cast<int32_t>(s);
         loc[i] = in[i].loc;
         sigtheta[i] = make_float2(in[i].sigma, in[i].theta);
-        const int32_t h = static_cast<int32_t>(s >> 1);
-        nhmin = max(nhmin, -h);
-        hmax = max(hmax, h);
-      } else if (i < n_rows) {
+        wn = kNoFoldC - h;
+        const int32_t W = kFoldC - h;
+        if (W >= 2) {
+          uint32_t rest = static_cast<uint32_t>(W) / 255u;        // <= 31 * 255, spread greedily over digits 1..31
+          words[0] = static_cast<uint32_t>(W) % 255u;
+#pragma unroll
+          for (int k = 1; k < 32; ++k) {
+            const uint32_t take = rest < 255u ? rest : 255u;
+            words[k >> 2] |= take << (8 * (k & 3));
+            rest -= take;
+          }
+        } else {
+          bad = true;
+        }
+      } else {
         norm[i] = 0;
         loc[i] = make_float2(0.f, 0.f);
         sigtheta[i] = make_float2(0.f, 0.f);
       }
+      wcol[i] = wn;
+      uint4* o = reinterpret_cast<uint4*>(ext + i * kExtBytes);
+      o[0] = make_uint4(words[0], words[1], words[2], words[3]);
+      o[1] = make_uint4(words[4], words[5], words[6], words[7]);
     }
   }
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    nhmin = max(nhmin, __shfl_xor_sync(0xffffffffu, nhmin, o));
-    hmax = max(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
-  }
-  if (lane == 0 && hmax >= 0) {
-    atomicMax(&meta[0], nhmin);
-    atomicMax(&meta[1], hmax);
-  }
-}
-
-// W = hmax - h + 2 as  digits[0] + 255 * sum(digits[1..31]),  every digit <= 255; zero on the padding rows [n, n_rows).
-__global__ void __launch_bounds__(256) fold_digits_kernel(const int32_t* __restrict__ norm, uint64_t n, uint64_t n_rows,
-                                                          int32_t* __restrict__ meta,
-                                                          uint8_t* __restrict__ ext, int32_t* __restrict__ wcol) {
-  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  const int32_t hmax = meta[1];
-  if (i == 0) meta[2] = (static_cast<int64_t>(hmax) + meta[0] + 2 <= kFoldMaxW) ? 1 : 0;   // hmax - hmin + 2
-  if (i >= n_rows) return;
-  uint32_t words[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  int32_t W = 0;
-  if (i < n) {
-    W = hmax - (norm[i] >> 1) + 2;
-    if (W <= kFoldMaxW) {
-      const uint32_t r = static_cast<uint32_t>(W) % 255u;
-      uint32_t s = static_cast<uint32_t>(W) / 255u;          // <= 31 * 255
-      uint8_t d[32];
-      d[0] = static_cast<uint8_t>(r);
-#pragma unroll
-      for (int k = 1; k < 32; ++k) {
-        const uint32_t take = s < 255u ? s : 255u;
-        d[k] = static_cast<uint8_t>(take);
-        s -= take;
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        words[k] = d[4 * k] | (d[4 * k + 1] << 8) | (d[4 * k + 2] << 16) | (static_cast<uint32_t>(d[4 * k + 3]) << 24);
-    }
-  }
-  wcol[i] = W;
-  uint4* o = reinterpret_cast<uint4*>(ext + i * kExtBytes);
-  o[0] = make_uint4(words[0], words[1], words[2], words[3]);
-  o[1] = make_uint4(words[4], words[5], words[6], words[7]);
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&meta[0], 1);
 }
 
 // Packs rows [0, n) of `feat_dev` into rows [row0, row0 + n) of the set's arrays and zero-fills up to row0 + n_rows;
-// meta_dev: the 4 x int32 device scalars of this range (already memset to 0x80).
+// meta_dev: the 4 x int32 device scalars of this range (already zeroed).
 void launch_pack(cudaStream_t st, const void* feat_dev, uint64_t n, uint64_t n_rows, uint64_t row0, ssrlcv_b200_set_impl& s,
                  int32_t* meta_dev, int sm_count) {
   if (n_rows == 0) return;
@@ -108,9 +87,8 @@ void launch_pack(cudaStream_t st, const void* feat_dev, uint64_t n, uint64_t n_r
   const uint64_t cap = static_cast<uint64_t>(sm_count) * 8;
   if (blocks > cap) blocks = cap;
   pack_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const RefFeature*>(feat_dev), n, n_rows, s.desc + row0 * kDescBytes,
-                                                             s.norm + row0, s.loc + row0, s.sigtheta + row0, meta_dev);
-  fold_digits_kernel<<<static_cast<unsigned>((n_rows + 255) / 256), 256, 0, st>>>(s.norm + row0, n, n_rows, meta_dev, s.ext + row0 * kExtBytes,
-                                                                                  s.wcol + row0);
+                                                             s.ext + row0 * kExtBytes, s.norm + row0, s.wcol + row0, s.loc + row0,
+                                                             s.sigtheta + row0, meta_dev);
 }
 
 }  // namespace b200

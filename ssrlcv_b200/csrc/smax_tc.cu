@@ -3,7 +3,7 @@
 // Brute-force 128-D nearest neighbour as the dense contraction it is.  For query a and target b
 //     d2(a,b) = |a|^2 + |b|^2 - 2 a.b ,        |b|^2 = 2h + p  (p = parity)
 // so minimising d2 over b is maximising the integer score
-//     S(a,b) = a.b + W_b ,   W_b = hmax - h_b + 2          (d2 = |a|^2 - 2 (S - hmax - 2) + p)
+//     S(a,b) = a.b + W_b ,   W_b = C - h_b  (C constant)    (d2 = |a|^2 - 2 (S - C) + p)
 // S is produced ENTIRELY by the tensor core: four tcgen05.mma kind::i8 (u8 x u8 -> s32, K = 32 each)
 // contract the 128 descriptor bytes and a fifth contracts a constant vector [1,255,...,255] with 32
 // base-255 digits of W_b ("fold"), accumulating in TMEM.  The epilogue therefore does no arithmetic on
@@ -13,7 +13,7 @@
 // global memory.
 //
 // S is an exact integer, so the recorded columns ARE the exact answer: for a column f with score S
-//     d2 = |a|^2 - 2 S + 2 hmax + 4 + (|b_f|^2 & 1)
+//     d2 = |a|^2 - 2 S + 2 C + (|b_f|^2 & 1)
 // and the reference's winner (ref: src/MatchFactory.cu:1476-1492, min of (d2, f mod 32, f)) is the
 // minimum of that key over the recorded columns -- equal scores differ in d2 only by the parity bit.
 // No descriptor is read a second time.  Three or more windows tying at the best score (rare) do not
@@ -122,13 +122,14 @@ __device__ __forceinline__ uint32_t eq_mask32(const uint32_t (&x)[32], int32_t m
 // Turns the recorded states of query row r of tile qt (xa: the warp that saw columns [0,128) of every tile, xb: [128,256))
 // into the reference's winner key.  Every recorded column holds exactly the score `top`, so its distance follows from
 // the score and the parity of the target's norm; the minimum key over the recorded columns is the winner.
-__device__ __forceinline__ void resolve_row(const SmaxArgs& job, const WinState& a, const WinState& b, uint32_t qt, uint32_t slot, uint32_t r) {
+__device__ __forceinline__ void resolve_row(const SmaxArgs& job, const WinState& a, const WinState& b, uint32_t qt, uint32_t slot, uint32_t r,
+                                            int32_t w_offset) {
   const uint32_t row = qt * kBM + r;                    // < nq_pad: rows beyond nq land in the padding of the key array
   const bool va = a.w1 != kNoWin, vb = b.w1 != kNoWin;
   uint64_t key = kKeyNone;
   if (va | vb) {
     const int32_t top = va ? (vb ? max(a.best, b.best) : a.best) : b.best;
-    const int32_t base = __ldg(job.q_norm + row) - 2 * top + 2 * __ldg(job.t_meta + 1) + 4;
+    const int32_t base = __ldg(job.q_norm + row) - 2 * top + 2 * w_offset;
     const int32_t* t_norm = job.t_norm;
     const uint64_t off = job.target_offset;
     bool ovf = false;
@@ -319,7 +320,7 @@ struct UnitIter {
       if (L >= L_end) return false;
       while (L >= b.jobs[job].a.tile_end) ++job;
       J = b.jobs + job;
-      if (!check_fold || J->a.t_meta[2] != 0) break;
+      if (!check_fold || J->a.t_meta[0] == 0) break;
       L = J->a.tile_end;
     }
     const uint32_t n_tt = J->a.n_ttiles;
@@ -349,6 +350,7 @@ template <int kMask, bool kFold, bool kColMask, bool kTiming>
 __global__ void __launch_bounds__(kThreads, 1)
 smax_kernel(const SmaxBatch batch) {
   constexpr bool kCols = (kMask != SSRLCV_B200_MASK_NONE) || !kFold;   // epilogue needs per-target data
+  constexpr int32_t kWOffset = kFold ? kFoldC : kNoFoldC;               // the C of W_b = C - h_b
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
 
@@ -501,7 +503,7 @@ smax_kernel(const SmaxBatch batch) {
 #pragma unroll
         for (uint32_t g = 0; g < 2; ++g) {
           const uint32_t r = rw * 64 + g * 32 + lane;
-          resolve_row(u.J->a, xch[(uparity * 2 + 0) * kBM + r], xch[(uparity * 2 + 1) * kBM + r], u.qt, u.slot, r);
+          resolve_row(u.J->a, xch[(uparity * 2 + 0) * kBM + r], xch[(uparity * 2 + 1) * kBM + r], u.qt, u.slot, r, kWOffset);
         }
       } else {
         resolve_rows_windows<kMask, 2>(u.J->a, xch + (uparity * 2 + 0) * kBM, xch + (uparity * 2 + 1) * kBM, u.qt, u.slot, rw * 64, 64, lane);
@@ -533,8 +535,8 @@ smax_kernel(const SmaxBatch batch) {
       QueryMask qm;
       if (kMask != SSRLCV_B200_MASK_NONE) qm = load_query_mask<kMask>(args.q_mask + 2 * static_cast<uint64_t>(row_c));
 
-      // Lowest score that can still pass the absolute threshold: d2 = |a|^2 - 2 (S - hmax - 2) + p <= d2_cap
-      // <=> S >= hmax + 2 + ceil((|a|^2 - d2_cap) / 2)  (p = 0 is the permissive case).  Real scores are >= 2,
+      // Lowest score that can still pass the absolute threshold: d2 = |a|^2 - 2 (S - C) + p <= d2_cap
+      // <=> S >= C + ceil((|a|^2 - d2_cap) / 2)  (p = 0 is the permissive case).  Real scores are >= 2,
       // padding / masked entries are 0, so the floor never drops below 2.
       WinState st;
       {
@@ -542,7 +544,7 @@ smax_kernel(const SmaxBatch batch) {
         const int32_t d2_cap = args.d2_cap;
         if (d2_cap != 0x7fffffff) {
           const int32_t qn = args.q_norm[row_c];
-          floor_s = max(2, args.t_meta[1] + 2 + ((qn - d2_cap + 1) >> 1));
+          floor_s = max(2, kWOffset + ((qn - d2_cap + 1) >> 1));
         }
         st.best = floor_s - 1; st.w1 = kNoWin; st.w2 = kNoWin; st.m1 = 0; st.m2 = 0; st.ovf = 0;
       }
@@ -630,7 +632,7 @@ smax_kernel(const SmaxBatch batch) {
           resolve_rows_windows<kMask, 2>(args, xch + (uparity * 2 + 0) * kBM, xch + (uparity * 2 + 1) * kBM, u.qt, u.slot, (warp - 4) * 16, 16, lane);
         } else if (half == 0) {
           const uint32_t r = quarter * 32 + lane;
-          resolve_row(args, xch[(uparity * 2 + 0) * kBM + r], xch[(uparity * 2 + 1) * kBM + r], u.qt, u.slot, r);
+          resolve_row(args, xch[(uparity * 2 + 0) * kBM + r], xch[(uparity * 2 + 1) * kBM + r], u.qt, u.slot, r, kWOffset);
         }
       }
       ++uiter;
@@ -665,9 +667,10 @@ static cudaError_t launch_one(cudaStream_t st, const SmaxBatch& b) {
 
 template <int kMask>
 static cudaError_t launch_mask(cudaStream_t st, const SmaxBatch& b, bool fold, bool colmask) {
-  if (b.timing) {   // diagnostics build (tools/kerneltiming.py); unconstrained fold variants only
-    if (kMask == SSRLCV_B200_MASK_NONE && fold)
-      return colmask ? launch_one<SSRLCV_B200_MASK_NONE, true, true, true>(st, b) : launch_one<SSRLCV_B200_MASK_NONE, true, false, true>(st, b);
+  if (b.timing) {   // diagnostics build (tools/kerneltiming.py); fold variants of the unconstrained and DoubleConstrained kernels
+    if (kMask != SSRLCV_B200_MASK_FUNDAMENTAL && fold)
+      return colmask ? launch_one<kMask == SSRLCV_B200_MASK_FUNDAMENTAL ? 0 : kMask, true, true, true>(st, b)
+                     : launch_one<kMask == SSRLCV_B200_MASK_FUNDAMENTAL ? 0 : kMask, true, false, true>(st, b);
   }
   if (fold) return colmask ? launch_one<kMask, true, true, false>(st, b) : launch_one<kMask, true, false, false>(st, b);
   return colmask ? launch_one<kMask, false, true, false>(st, b) : launch_one<kMask, false, false, false>(st, b);

@@ -131,6 +131,29 @@ def test_tie_break_both_bookkeeping_regimes(api, thr):
     assert T.fields_equal(simt, want)
 
 
+@pytest.mark.parametrize("kind", ["bright", "mixed", "uniform"])
+@pytest.mark.parametrize("thr", [FLT_MAX, 3.0e5])
+def test_large_norm_sets_take_the_epilogue_add_variant(api, kind, thr):
+    """Targets whose |b|^2 exceeds what the fold digits can carry (> 4 032 057, pack.cu / matcher.cuh kFoldC) are matched by
+    the kFold = false variant (W added in the epilogue); uniform random bytes (|b|^2 ~ 2.8 M) still fold.  Both are exact."""
+    rng = np.random.default_rng(21)
+    nq, nt = 700, 5000
+    if kind == "bright":
+        qv = rng.integers(180, 256, (nq, 128), dtype=np.uint8); tv = rng.integers(180, 256, (nt, 128), dtype=np.uint8)
+    elif kind == "mixed":        # SIFT-like rows next to saturated ones, all-zero and all-255 rows included
+        qv = synth.sift_descriptors(rng, nq); tv = synth.sift_descriptors(rng, nt)
+        tv[::3] = rng.integers(200, 256, (len(tv[::3]), 128), dtype=np.uint8)
+        tv[7] = 255; tv[8] = 0; qv[5] = 255; qv[6] = 0
+    else:
+        qv = rng.integers(0, 256, (nq, 128), dtype=np.uint8); tv = rng.integers(0, 256, (nt, 128), dtype=np.uint8)
+    tv[rng.choice(nt, 300, replace=False)] = np.clip(qv[:300].astype(int) + rng.integers(-3, 4, (300, 128)), 0, 255)
+    q, t = T.make_features(qv), T.make_features(tv)
+    mf = api.MatchFactory(1.0, thr)
+    got = mf.generateDistanceMatches(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t)).to_numpy()
+    want = api.O.generate_matches(api.O.make_params(out_kind=T.OUT_DMATCH, abs_threshold=thr), q, t)
+    assert len(want) >= 300 and T.fields_equal(got, want)
+
+
 @pytest.mark.parametrize("engine", [0, 1])
 def test_degenerate_inputs(api, engine):
     """all-equal descriptors (every score ties), all-zero, all-255 (norm range beyond the fold), empty target set."""

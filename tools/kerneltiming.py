@@ -14,14 +14,19 @@ from bench import WORKLOADS, synth_inputs  # noqa: E402
 from ssrlcv_b200 import _lib, types as T  # noqa: E402
 from ssrlcv_b200.match_factory import Context  # noqa: E402
 
-# usage: kerneltiming.py [C1|C2|C3]   or   kerneltiming.py NQ NT [ABS_THRESHOLD]   (unmasked, fold variant)
-abs_thr = 4e4
+# usage: kerneltiming.py [C1|C2|C3]   or   kerneltiming.py NQ NT [ABS_THRESHOLD [MASK_KIND [EPSILON]]]   (fold variant)
+abs_thr, eps = 4e4, 25.0
 if len(sys.argv) > 2:
     w = dict(nq=int(sys.argv[1]), nt=int(sys.argv[2]), ns=0, mask=0)
     if len(sys.argv) > 3:
         abs_thr = float(sys.argv[3])
+    if len(sys.argv) > 4:
+        w["mask"] = int(sys.argv[4])
+    if len(sys.argv) > 5:
+        eps = float(sys.argv[5])
 else:
     w = WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "C3"]
+print("workload", w, "abs", abs_thr, "eps", eps)
 ctx = Context.get(0)
 lib, h = ctx.lib, ctx.handle
 q, t, s = synth_inputs(w, 0)
@@ -30,7 +35,13 @@ td = torch.from_numpy(t.view(np.uint8).reshape(-1)).cuda()
 out = torch.empty(len(q) * 48, dtype=torch.uint8, device="cuda")
 tim = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
 p = _lib.MatchParams()
-p.out_kind, p.mask_kind, p.absolute_threshold, p.relative_threshold, p.compact = T.OUT_DMATCH, 0, abs_thr, 0.6, 1
+p.out_kind, p.mask_kind, p.absolute_threshold, p.relative_threshold, p.compact = T.OUT_DMATCH, w["mask"], abs_thr, 0.6, 1
+if w["mask"]:
+    from bench import cameras
+    cam0, cam1 = cameras()
+    p.epsilon, p.delta = eps, 5.0
+    p.query_camera = (C.c_uint8 * 80).from_buffer_copy(np.asarray(cam0).tobytes())
+    p.target_camera = (C.c_uint8 * 80).from_buffer_copy(np.asarray(cam1).tobytes())
 n_out = C.c_uint64(0)
 hq, ht = C.c_void_p(), C.c_void_p()
 lib.ssrlcv_b200_pack(h, C.c_void_p(qd.data_ptr()), len(q), C.byref(hq))
