@@ -3,6 +3,7 @@
 // kernels; there is no CPU fallback: without an sm_100 device every entry point fails.
 #include <cfloat>
 #include <cmath>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -73,6 +74,11 @@ struct ssrlcv_b200_ctx {
   struct PackSlot { int32_t* mm; cudaEvent_t ready; };
   std::vector<PackSlot> free_slots;
   std::vector<int32_t*> slot_blocks;
+  // match_host with large sets: uploads run on their own stream, chunk by chunk, while the matcher already works on the
+  // chunks that have arrived (match_host_streamed)
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> copy_events;
+  Workspace upload;
 };
 
 static int slot_acquire(ssrlcv_b200_ctx* ctx, ssrlcv_b200_ctx::PackSlot& out) {
@@ -169,6 +175,9 @@ void ssrlcv_b200_destroy(ssrlcv_b200_ctx* ctx) {
     if (st.done) cudaEventDestroy(st.done);
   }
   if (ctx->hostpin.p) cudaFreeHost(ctx->hostpin.p);
+  if (ctx->upload.p) cudaFree(ctx->upload.p);
+  for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& sl : ctx->free_slots) cudaEventDestroy(sl.ready);
   for (int32_t* b : ctx->slot_blocks) cudaFreeHost(b);
   if (ctx->d_scalars) cudaFree(ctx->d_scalars);
@@ -219,11 +228,8 @@ static int encode_map(ssrlcv_b200_ctx* ctx, CUtensorMap* m, void* base, uint64_t
   return 0;
 }
 
-// Enqueue-only: nothing here waits for the device.  Whether every norm of the set fits the fold digits, which selects the
-// kernel variant, is copied to a pinned slot and read by set_resolve() when a match first needs it.
-int ssrlcv_b200_pack(ssrlcv_b200_ctx* ctx, const void* features_dev, uint64_t n, ssrlcv_b200_set** out) {
-  if (!ctx || !out || (n && !features_dev) || n > 0x7fffffffull) return fail(ctx, SSRLCV_B200_EINVAL, "pack: bad arguments");
-  CU(cudaSetDevice(ctx->device));
+// Allocates a set of n rows (one allocation, tensor maps, pinned slot for the meta scalars, meta zeroed); nothing is packed yet.
+static int set_alloc(ssrlcv_b200_ctx* ctx, uint64_t n, ssrlcv_b200_set** out) {
   ssrlcv_b200_set* s = new (std::nothrow) ssrlcv_b200_set();
   if (!s) return SSRLCV_B200_ENOMEM;
   memset(static_cast<ssrlcv_b200_set_impl*>(s), 0, sizeof(ssrlcv_b200_set_impl));
@@ -253,15 +259,33 @@ int ssrlcv_b200_pack(ssrlcv_b200_ctx* ctx, const void* features_dev, uint64_t n,
   s->sigtheta = s->loc + np;
   s->meta = reinterpret_cast<int32_t*>(s->sigtheta + np);
   cudaMemsetAsync(s->meta, 0, 16, ctx->stream);
-  launch_pack(ctx->stream, features_dev, n, np, 0, *s, s->meta, ctx->sm_count);
-  ctx->launches += 1;
-  cudaMemcpyAsync(s->h_mm, s->meta, 16, cudaMemcpyDeviceToHost, ctx->stream);
-  cudaEventRecord(s->ready, ctx->stream);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) { ssrlcv_b200_set_free(s); return fail(ctx, static_cast<int>(e), "pack: %s", cudaGetErrorString(e)); }
   rc = encode_map(ctx, &s->map_a, s->desc, np, kDescBytes, kBM, CU_TENSOR_MAP_SWIZZLE_128B);
   if (!rc) rc = encode_map(ctx, &s->map_b, s->desc, np, kDescBytes, kBN, CU_TENSOR_MAP_SWIZZLE_128B);
   if (!rc) rc = encode_map(ctx, &s->map_ext, s->ext, np, kExtBytes, kBN, CU_TENSOR_MAP_SWIZZLE_32B);
+  if (rc) { ssrlcv_b200_set_free(s); return rc; }
+  *out = s;
+  return 0;
+}
+// After the last pack launch of a set: its meta scalars travel to the pinned slot (read by set_resolve).
+static int set_finish(ssrlcv_b200_ctx* ctx, ssrlcv_b200_set* s) {
+  cudaMemcpyAsync(s->h_mm, s->meta, 16, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaEventRecord(s->ready, ctx->stream);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ctx, static_cast<int>(e), "pack: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// Enqueue-only: nothing here waits for the device.  Whether every norm of the set fits the fold digits, which selects the
+// kernel variant, is copied to a pinned slot and read by set_resolve() when a match first needs it.
+int ssrlcv_b200_pack(ssrlcv_b200_ctx* ctx, const void* features_dev, uint64_t n, ssrlcv_b200_set** out) {
+  if (!ctx || !out || (n && !features_dev) || n > 0x7fffffffull) return fail(ctx, SSRLCV_B200_EINVAL, "pack: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  ssrlcv_b200_set* s = nullptr;
+  int rc = set_alloc(ctx, n, &s);
+  if (rc) return rc;
+  launch_pack(ctx->stream, features_dev, n, s->n_pad, 0, *s, s->meta, ctx->sm_count);
+  ctx->launches += 1;
+  rc = set_finish(ctx, s);
   if (rc) { ssrlcv_b200_set_free(s); return rc; }
   *out = s;
   return 0;
@@ -800,6 +824,195 @@ int ssrlcv_b200_finalize_candidates(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_matc
   return 0;
 }
 
+// A window of rows [row0, row0 + rows_pad) of a packed set, usable wherever a set is (its own tensor maps; rows_real of
+// them are features, the rest the parent's zero padding).  row0 and rows_pad are multiples of kRowPad.  Borrowed memory:
+// never passed to ssrlcv_b200_set_free.
+static int make_view(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* parent, uint64_t row0, uint64_t rows_real, uint64_t rows_pad,
+                     ssrlcv_b200_set* v) {
+  *v = *parent;
+  v->n = rows_real; v->n_pad = rows_pad;
+  v->desc += row0 * kDescBytes; v->ext += row0 * kExtBytes;
+  v->norm += row0; v->wcol += row0; v->loc += row0; v->sigtheta += row0;
+  v->resolved = false;                                   // the parent's packs may still be in flight: optimistic fold launch
+  int rc = encode_map(ctx, &v->map_a, v->desc, rows_pad, kDescBytes, kBM, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (!rc) rc = encode_map(ctx, &v->map_b, v->desc, rows_pad, kDescBytes, kBN, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (!rc) rc = encode_map(ctx, &v->map_ext, v->ext, rows_pad, kExtBytes, kBN, CU_TENSOR_MAP_SWIZZLE_32B);
+  return rc;
+}
+
+// How match_host cuts a set of n rows for the streamed upload: equal chunks (a multiple of kRowPad rows) of at least
+// kMinChunkRows, at most kMaxChunks.  Every chunk costs a pack + matcher + tie-list + key-reduction launch (~25 us of
+// device time, ~30 us of host time), so few, large chunks win: measured at 65 536 x 65 536 (tools/e2e_chunks.sh,
+// profiles/r1f_e2e_chunks.txt): one piece 0.94 ms, 2 + 2 chunks 0.80 ms, 4 + 4 chunks 0.94 ms, 8 + 8 chunks 1.10 ms.
+// SSRLCV_B200_HOST_CHUNK_ROWS="<rows>" or "<query rows>,<target rows>" overrides (0 = never cut; tests use tiny chunks).
+static uint64_t host_chunk_rows(uint64_t n, int which) {
+  constexpr uint64_t kMinChunkRows = 16384, kMaxChunks = 2;
+  uint64_t rows;
+  if (const char* e = getenv("SSRLCV_B200_HOST_CHUNK_ROWS")) {      // "<rows>" or "<query rows>,<target rows>"
+    const char* comma = strchr(e, ',');
+    rows = strtoull(which == 1 && comma ? comma + 1 : e, nullptr, 10);
+    if (rows == 0) return n ? ((n + kRowPad - 1) / kRowPad) * kRowPad : kRowPad;   // 0: never cut
+  } else {
+    uint64_t c = n / kMinChunkRows;
+    if (c < 1) c = 1;
+    if (c > kMaxChunks) c = kMaxChunks;
+    rows = (n + c - 1) / c;
+  }
+  rows = ((rows + kRowPad - 1) / kRowPad) * kRowPad;
+  return rows ? rows : kRowPad;
+}
+
+// match_host for sets large enough that the PCIe transfer matters: both sets are uploaded chunk by chunk on a copy
+// stream (query and target chunks interleaved) and every chunk is packed and matched against everything that has already
+// arrived while the next one is still on the bus:
+//   target chunk j arrives: (queries so far) x (chunk j)            -> key slot j of those queries
+//   query chunk i arrives : (chunk i) x (targets so far, one view)  -> key slot n_tchunks of those queries
+// Each (query, target) combination is evaluated exactly once; the minimum over a query's slots is the reference's winner
+// (keys carry the global target index, chunk boundaries are multiples of 32 so f mod 32 is unchanged), then one finalize.
+static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const void* query_host, uint64_t nq,
+                               const void* target_host, uint64_t nt, const void* seed_host, uint64_t ns, void* out_host,
+                               uint64_t* n_out, uint64_t q_rows, uint64_t t_rows) {
+  CU(cudaSetDevice(ctx->device));
+  const auto host_t0 = std::chrono::steady_clock::now();
+  if (!ctx->copy_stream) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  const uint64_t n_qc = (nq + q_rows - 1) / q_rows, n_tc = (nt + t_rows - 1) / t_rows;
+  while (ctx->copy_events.size() < n_qc + n_tc + 2) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->copy_events.push_back(e);
+  }
+  const size_t rec = sizeof(RefFeature), elt = out_elt(p->out_kind);
+  int rc = ws_reserve(ctx, ctx->upload, (nq + nt + ns) * rec + 16);
+  if (rc) return rc;
+  uint8_t* up_q = static_cast<uint8_t*>(ctx->upload.p);
+  uint8_t* up_t = up_q + nq * rec;
+  uint8_t* up_s = up_t + nt * rec;
+  // scratch: [out records | seed distances | chunk keys (n_tc + 1) x nq]
+  const size_t out_bytes = ((nq * elt + 255) / 256) * 256, seed_bytes = ((nq * sizeof(float) + 255) / 256) * 256;
+  const size_t n_slots = n_tc + 1;
+  rc = ws_reserve(ctx, ctx->scratch, out_bytes + seed_bytes + n_slots * nq * sizeof(uint64_t) + 256);
+  if (rc) return rc;
+  void* out_dev = ctx->scratch.p;
+  float* seed_dev = reinterpret_cast<float*>(static_cast<uint8_t*>(ctx->scratch.p) + out_bytes);
+  uint64_t* ckeys = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(ctx->scratch.p) + out_bytes + seed_bytes);
+
+  // ---- the copy stream starts after everything already enqueued on the main stream (earlier readers of the upload buffer)
+  cudaEvent_t ev_fence = ctx->copy_events[n_qc + n_tc + 1], ev_seed = ctx->copy_events[n_qc + n_tc];
+  CU(cudaEventRecord(ev_fence, ctx->stream));
+  CU(cudaStreamWaitEvent(ctx->copy_stream, ev_fence, 0));
+  // upload order: seed set, then query / target chunks interleaved in proportion (query chunk first)
+  struct Up { bool is_q; uint64_t idx; };
+  std::vector<Up> order;
+  {
+    uint64_t qi = 0, ti = 0;
+    while (qi < n_qc || ti < n_tc) {
+      const bool take_q = ti >= n_tc || (qi < n_qc && qi * n_tc <= ti * n_qc);
+      if (take_q) order.push_back(Up{true, qi++}); else order.push_back(Up{false, ti++});
+    }
+  }
+  if (seed_host && ns) CU(cudaMemcpyAsync(up_s, seed_host, ns * rec, cudaMemcpyHostToDevice, ctx->copy_stream));
+  if (seed_host) CU(cudaEventRecord(ev_seed, ctx->copy_stream));
+  for (size_t k = 0; k < order.size(); ++k) {
+    const Up& u = order[k];
+    const uint64_t rows = u.is_q ? q_rows : t_rows, n = u.is_q ? nq : nt, r0 = u.idx * rows;
+    const uint64_t cnt = n - r0 < rows ? n - r0 : rows;
+    const uint8_t* src = static_cast<const uint8_t*>(u.is_q ? query_host : target_host) + r0 * rec;
+    CU(cudaMemcpyAsync((u.is_q ? up_q : up_t) + r0 * rec, src, cnt * rec, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaEventRecord(ctx->copy_events[k], ctx->copy_stream));
+  }
+
+  // ---- main stream: pack and match as the chunks arrive
+  ssrlcv_b200_set *q = nullptr, *t = nullptr, *s = nullptr;
+  auto cleanup = [&](int code) { ssrlcv_b200_set_free(q); ssrlcv_b200_set_free(t); ssrlcv_b200_set_free(s); return code; };
+  rc = set_alloc(ctx, nq, &q);
+  if (!rc) rc = set_alloc(ctx, nt, &t);
+  if (rc) return cleanup(rc);
+  if (seed_host) {
+    CU(cudaStreamWaitEvent(ctx->stream, ev_seed, 0));
+    rc = ssrlcv_b200_pack(ctx, up_s, ns, &s);
+    if (rc) return cleanup(rc);
+  }
+  launch_fill_u64(ctx->stream, ckeys, n_slots * nq, kKeyNone);
+  ctx->launches += 1;
+  PairWork w;
+  fill_mask(p, w.mp);
+  w.engine = p->engine; w.abs_thr = p->absolute_threshold;
+  uint64_t q_arrived = 0, t_arrived = 0;                      // rows
+  bool any_optimistic = false;
+  for (size_t k = 0; k < order.size(); ++k) {
+    const Up& u = order[k];
+    ssrlcv_b200_set* set = u.is_q ? q : t;
+    const uint64_t rows = u.is_q ? q_rows : t_rows, r0 = u.idx * rows;
+    const bool last = r0 + rows >= set->n;
+    const uint64_t cnt = last ? set->n - r0 : rows, pad = last ? set->n_pad - r0 : rows;
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->copy_events[k], 0));
+    launch_pack(ctx->stream, (u.is_q ? up_q : up_t) + r0 * rec, cnt, pad, r0, *set, set->meta, ctx->sm_count);
+    ctx->launches += 1;
+    ssrlcv_b200_set qv, tv;
+    uint64_t q0 = 0, slot = 0;
+    bool run = false;
+    if (u.is_q) {
+      if (last) { rc = set_finish(ctx, q); if (rc) return cleanup(rc); }
+      if (t_arrived) {                                         // (chunk i) x (targets so far)
+        rc = make_view(ctx, q, r0, cnt, pad, &qv);
+        if (!rc) rc = make_view(ctx, t, 0, t_arrived, t_arrived == t->n ? t->n_pad : t_arrived, &tv);
+        if (rc) return cleanup(rc);
+        w.target_offset = 0; q0 = r0; slot = n_tc; run = cnt != 0;
+      }
+      q_arrived = r0 + cnt;
+    } else {
+      if (last) { rc = set_finish(ctx, t); if (rc) return cleanup(rc); }
+      if (q_arrived) {                                         // (queries so far) x (chunk j)
+        const uint64_t q_pad = q_arrived == q->n ? q->n_pad : q_arrived;
+        rc = make_view(ctx, q, 0, q_arrived, q_pad, &qv);
+        if (!rc) rc = make_view(ctx, t, r0, cnt, pad, &tv);
+        if (rc) return cleanup(rc);
+        w.target_offset = r0; q0 = 0; slot = u.idx; run = cnt != 0;
+      }
+      t_arrived = r0 + cnt;                                    // a multiple of t_rows until the last chunk
+    }
+    if (run) {
+      w.q = &qv; w.t = &tv;
+      bool optimistic = false;
+      rc = engine_enqueue(ctx, &w, 1, &optimistic);
+      if (rc) return cleanup(rc);
+      any_optimistic |= optimistic;
+      launch_min_keys(ctx->stream, w.a.keys, w.a.nq, w.a.nq_pad, w.a.n_splits, ckeys + slot * nq + q0);
+      ctx->launches += 1;
+    }
+    if (u.is_q && last && s) {                                 // every query is on the device: seed distances
+      rc = ssrlcv_b200_seed_distances(ctx, q, s, seed_dev, p->engine);
+      if (rc) return cleanup(rc);
+    }
+  }
+  FinalizeWork fw{p, q, ckeys, static_cast<uint32_t>(n_slots), static_cast<uint32_t>(nq), t->loc, t, s ? seed_dev : nullptr, out_dev};
+  const uint32_t* total = nullptr;
+  rc = finalize_enqueue(ctx, &fw, 1, &total);
+  if (rc) return cleanup(rc);
+  CU(cudaMemcpyAsync(ctx->h_scalars + 2, total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  const auto host_t1 = std::chrono::steady_clock::now();
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (getenv("SSRLCV_B200_DEBUG_HOST"))
+    fprintf(stderr, "match_host_streamed: %zu uploads, host enqueue %.1f us, wait %.1f us\n", order.size(),
+            std::chrono::duration<double, std::micro>(host_t1 - host_t0).count(),
+            std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t1).count());
+  *n_out = ctx->h_scalars[2];
+  rc = set_resolve(ctx, t);
+  if (rc) return cleanup(rc);
+  if (any_optimistic && !t->fold_ok) {
+    // some target norm does not fit the fold digits: the optimistic launches skipped their jobs.  Both sets are packed
+    // by now; redo the pair in one piece with the epilogue-add variant.
+    rc = ssrlcv_b200_match(ctx, p, q, t, s ? seed_dev : nullptr, s ? nq : 0, out_dev, n_out);
+    if (rc) return cleanup(rc);
+  }
+  if (*n_out) {
+    cudaError_t e = cudaMemcpyAsync(out_host, out_dev, *n_out * elt, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return cleanup(fail(ctx, static_cast<int>(e), "match_host: D2H: %s", cudaGetErrorString(e)));
+  }
+  return cleanup(0);
+}
+
 int ssrlcv_b200_match_host(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const void* query_host, uint64_t n_query,
                            const void* target_host, uint64_t n_target, const void* seed_host, uint64_t n_seed, void* out_host,
                            uint64_t* n_out) {
@@ -811,6 +1024,12 @@ int ssrlcv_b200_match_host(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params*
   void* out_dev = nullptr;
   const size_t elt = out_elt(p->out_kind);
   if ((n_query && !query_host) || (n_target && !target_host) || (seed_host == nullptr && n_seed)) return fail(ctx, SSRLCV_B200_EINVAL, "match_host: bad arguments");
+  if (n_query > 0x7fffffffull || n_target > 0x7fffffffull || n_seed > 0x7fffffffull) return fail(ctx, SSRLCV_B200_EINVAL, "match_host: too many features");
+  {
+    const uint64_t q_rows = host_chunk_rows(n_query, 0), t_rows = host_chunk_rows(n_target, 1);
+    if (n_query && n_target && p->engine != SSRLCV_B200_ENGINE_SIMT && (q_rows < n_query || t_rows < n_target))
+      return match_host_streamed(ctx, p, query_host, n_query, target_host, n_target, seed_host, n_seed, out_host, n_out, q_rows, t_rows);
+  }
   rc = pack_host_async(ctx, query_host, n_query, &q);
   if (!rc) rc = pack_host_async(ctx, target_host, n_target, &t);
   if (!rc && seed_host) rc = pack_host_async(ctx, seed_host, n_seed, &s);

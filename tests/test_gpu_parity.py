@@ -230,6 +230,84 @@ def test_memory_states_restored(api):
         mf.generateMatches(api.Image(0), qu, api.Image(1), tu, api.Unity(np.zeros(5, np.float32), np.dtype("<f4"), api.cpu))
 
 
+# ------------------------------------------------------------------------------------ host-buffer entry point
+def _match_host(api, mf, p, q, t, s, elt_dtype):
+    """ssrlcv_b200_match_host on plain (pageable) numpy buffers -> record array"""
+    lib, h = mf.ctx.lib, mf.ctx.handle
+    out = np.zeros(max(len(q), 1), elt_dtype)
+    n_out = C.c_uint64(0)
+    ptr = lambda a: C.c_void_p(a.ctypes.data) if a is not None and len(a) else (C.c_void_p(a.ctypes.data) if a is not None else None)
+    mf.ctx.check(lib.ssrlcv_b200_match_host(h, C.byref(p), ptr(q), len(q), ptr(t), len(t), ptr(s), len(s) if s is not None else 0,
+                                            C.c_void_p(out.ctypes.data), C.byref(n_out)))
+    return out[: n_out.value]
+
+
+@pytest.mark.parametrize("chunk_rows", ["0", "256", "512", "1280", None])
+@pytest.mark.parametrize("nq,nt", [(3000, 3500), (700, 2049), (2049, 300), (1024, 1024)])
+def test_match_host_streamed_upload_equals_oracle(api, monkeypatch, chunk_rows, nq, nt):
+    """match_host uploads large sets chunk by chunk and matches every chunk against what has already arrived (api.cu
+    match_host_streamed); the chunk length is forced down here so that small cases take that path: every cut of the query
+    and target sets gives the oracle's records.  "0" = never cut (the one-piece path), None = the library's own rule."""
+    if chunk_rows is None:
+        monkeypatch.delenv("SSRLCV_B200_HOST_CHUNK_ROWS", raising=False)
+    else:
+        monkeypatch.setenv("SSRLCV_B200_HOST_CHUNK_ROWS", chunk_rows)
+    q, t = synth.make_pair(nq, nt, seed=nq * 7 + nt)
+    s = synth.make_seed(600)
+    mf = api.MatchFactory(0.8, 1.1e5)
+    sd_want = api.O.seed_distances(q, s)
+    for out_kind, dt in ((T.OUT_DMATCH, T.DMATCH), (T.OUT_PAIR, T.UINT2_PAIR), (T.OUT_MATCH, T.MATCH)):
+        for seeded in (False, True):
+            p = mf._params(out_kind, T.MASK_NONE, api.Image(3), api.Image(8))
+            got = _match_host(api, mf, p, q, t, s if seeded else None, dt)
+            po = api.O.make_params(out_kind=out_kind, has_seed=seeded, abs_threshold=1.1e5, rel_threshold=0.8, query_id=3, target_id=8)
+            want = api.O.generate_matches(po, q, t, sd_want if seeded else None)
+            assert len(want) > 50 and T.fields_equal(got, want), (out_kind, seeded)
+
+
+def test_match_host_streamed_masked_and_unthresholded(api, everest, monkeypatch):
+    monkeypatch.setenv("SSRLCV_B200_HOST_CHUNK_ROWS", "768")
+    q, t = synth.make_pair(4000, 6000, seed=31)
+    s = synth.make_seed(1000)
+    sd_want = api.O.seed_distances(q, s)
+    mf = api.MatchFactory(0.8, 1.0e5)
+    p = mf._params(T.OUT_DMATCH, T.MASK_DOUBLE, api.Image(0, everest.cameras[0]), api.Image(1, everest.cameras[1]), epsilon=25.0, delta=5.0)
+    got = _match_host(api, mf, p, q, t, s, T.DMATCH)
+    po = api.O.make_params(out_kind=T.OUT_DMATCH, mask_kind=T.MASK_DOUBLE, has_seed=True, abs_threshold=1.0e5, rel_threshold=0.8,
+                           query_id=0, target_id=1, epsilon=25, delta=5, query_camera=everest.cameras[0], target_camera=everest.cameras[1])
+    want = api.O.generate_matches(po, q, t, sd_want)
+    assert len(want) > 20 and T.fields_equal(got, want)
+    # no absolute threshold: the window regime of the matcher (long target sets) and the column regime (short chunks)
+    mf2 = api.MatchFactory(1.0, FLT_MAX)
+    p2 = mf2._params(T.OUT_DMATCH, T.MASK_NONE, api.Image(0), api.Image(1))
+    got2 = _match_host(api, mf2, p2, q, t, None, T.DMATCH)
+    assert T.fields_equal(got2, api.O.generate_matches(api.O.make_params(out_kind=T.OUT_DMATCH), q, t))
+    # FeatureMatch records need the target descriptors of the whole set at finalize time
+    p3 = mf._params(T.OUT_FEATUREMATCH, T.MASK_NONE, api.Image(0), api.Image(1), compact=0)
+    got3 = _match_host(api, mf, p3, q, t, None, T.FEATUREMATCH)
+    bd, bi, ok = api.O.match_winners(api.O.make_params(out_kind=T.OUT_FEATUREMATCH, abs_threshold=1.0e5), q, t)
+    v = np.flatnonzero(ok)
+    assert len(got3) == len(q) and np.array_equal(got3["invalid"] == 0, ok.astype(bool)) and len(v) > 100
+    assert np.array_equal(got3["distance"][v], bd[v]) and np.array_equal(got3["descriptors"]["values"][v, 1], t["values"][bi[v]])
+    assert np.array_equal(got3["keyPoints"]["loc"][v, 1], t["loc"][bi[v]])
+
+
+def test_match_host_streamed_large_norms_fall_back(api, monkeypatch):
+    """a target chunk whose norms do not fit the fold digits: the optimistic chunk launches are discarded and the pair is
+    redone in one piece by the epilogue-add variant."""
+    monkeypatch.setenv("SSRLCV_B200_HOST_CHUNK_ROWS", "1024")
+    rng = np.random.default_rng(5)
+    nq, nt = 1500, 5000
+    qv = synth.sift_descriptors(rng, nq); tv = synth.sift_descriptors(rng, nt)
+    tv[3000:3400] = rng.integers(200, 256, (400, 128), dtype=np.uint8)          # only the third chunk is "bright"
+    tv[rng.choice(nt, 300, replace=False)] = np.clip(qv[:300].astype(int) + rng.integers(-3, 4, (300, 128)), 0, 255)
+    q, t = T.make_features(qv), T.make_features(tv)
+    mf = api.MatchFactory(1.0, 3.0e5)
+    got = _match_host(api, mf, mf._params(T.OUT_DMATCH, T.MASK_NONE, api.Image(0), api.Image(1)), q, t, None, T.DMATCH)
+    want = api.O.generate_matches(api.O.make_params(out_kind=T.OUT_DMATCH, abs_threshold=3.0e5), q, t)
+    assert len(want) >= 250 and T.fields_equal(got, want)
+
+
 # ------------------------------------------------------------------------------------ masks
 @pytest.mark.parametrize("engine", [0, 1])
 def test_double_constrained_matches_oracle(api, everest, engine):
