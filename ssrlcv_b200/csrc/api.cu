@@ -241,10 +241,11 @@ static int set_alloc(ssrlcv_b200_ctx* ctx, uint64_t n, ssrlcv_b200_set** out) {
   int rc = slot_acquire(ctx, slot);
   if (rc) { delete s; return fail(ctx, rc, "pack: pinned slot: %s", cudaGetErrorString(static_cast<cudaError_t>(rc))); }
   s->h_mm = slot.mm; s->ready = slot.ready; s->resolved = false;
-  // one allocation: desc | ext | norm | wcol | loc | sigtheta | meta   (all segments 256-byte aligned since n_pad % 256 == 0);
-  // the pack kernels write every row including the zero padding, so nothing is memset except the 16 bytes of meta
+  // one allocation: desc | ext | norm | wcol | loc | sigtheta | wmax | meta   (all segments 32-byte aligned since n_pad % 256 == 0);
+  // the pack kernels write every row including the zero padding, so nothing is memset except wmax (4 bytes per 32 rows,
+  // accumulated with atomicMax) and the 16 bytes of meta
   const size_t np = s->n_pad;
-  const size_t bytes = np * (kDescBytes + kExtBytes + 4 + 4 + 8 + 8) + 256;
+  const size_t bytes = np * (kDescBytes + kExtBytes + 4 + 4 + 8 + 8) + (np / kChunk) * 4 + 256;
   uint8_t* base = nullptr;
   cudaError_t e = cudaMallocAsync(&base, bytes, ctx->stream);
   if (e != cudaSuccess) {
@@ -257,8 +258,9 @@ static int set_alloc(ssrlcv_b200_ctx* ctx, uint64_t n, ssrlcv_b200_set** out) {
   s->wcol = s->norm + np;
   s->loc = reinterpret_cast<float2*>(s->wcol + np);
   s->sigtheta = s->loc + np;
-  s->meta = reinterpret_cast<int32_t*>(s->sigtheta + np);
-  cudaMemsetAsync(s->meta, 0, 16, ctx->stream);
+  s->wmax = reinterpret_cast<int32_t*>(s->sigtheta + np);
+  s->meta = s->wmax + np / kChunk;
+  cudaMemsetAsync(s->wmax, 0, (np / kChunk) * 4 + 16, ctx->stream);
   rc = encode_map(ctx, &s->map_a, s->desc, np, kDescBytes, kBM, CU_TENSOR_MAP_SWIZZLE_128B);
   if (!rc) rc = encode_map(ctx, &s->map_b, s->desc, np, kDescBytes, kBN, CU_TENSOR_MAP_SWIZZLE_128B);
   if (!rc) rc = encode_map(ctx, &s->map_ext, s->ext, np, kExtBytes, kBN, CU_TENSOR_MAP_SWIZZLE_32B);
@@ -297,7 +299,6 @@ static int set_resolve(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* cs) {
   if (s->resolved) return 0;
   CU(cudaEventSynchronize(s->ready));
   s->fold_ok = s->h_mm[0] == 0;
-  if (getenv("SSRLCV_B200_NOFOLD")) s->fold_ok = false;   // test hook: force the epilogue-add variant
   s->resolved = true;
   return 0;
 }
@@ -502,18 +503,27 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     a.t_meta = p.t->meta;
     a.d2_cap = d2_cap_of(p.abs_thr);
     a.q_desc = p.q->desc; a.q_norm = p.q->norm; a.q_loc = p.q->loc;
-    a.t_desc = p.t->desc; a.t_norm = p.t->norm; a.t_loc = p.t->loc; a.t_wcol = p.t->wcol;
+    a.t_desc = p.t->desc; a.t_norm = p.t->norm; a.t_loc = p.t->loc; a.t_wcol = p.t->wcol; a.t_wmax = p.t->wmax;
     if (p.engine == SSRLCV_B200_ENGINE_SIMT || tiles == 0) {
       plan_simt(ctx, a);
     } else {
+      // Variant (smax_tc.cu): the fold kernel (five MMAs per tile, the accumulator IS the score) whenever the target set's
+      // norms fit the fold digits; otherwise the no-fold kernel (four MMAs, W added in the epilogue to the few windows whose
+      // bound reaches a running best), which serves any norm range.  Measured at 65 536 x 65 536 (profiles/r1f_fold_ab.txt):
+      // fold 0.371 ms, no-fold 0.431 ms -- with four MMAs the tile period drops below the epilogue's own time per tile and
+      // every rare bookkeeping event of any of the 8 epilogue warps stalls the two-accumulator hand-off; the fifth MMA is the
+      // slack that hides them.  SSRLCV_B200_FOLD=0|1 forces a variant (tests, A/B timing).
       bool fold = true;
-      if (p.t->resolved || !optimistic) {
-        int rc = set_resolve(ctx, p.t);
-        if (rc) return rc;
-        fold = p.t->fold_ok;
-      } else {
-        *optimistic = true;
-        p.optimistic_fold = true;
+      if (const char* f = getenv("SSRLCV_B200_FOLD")) fold = f[0] != '0';
+      if (fold) {
+        if (p.t->resolved || !optimistic) {
+          int rc = set_resolve(ctx, p.t);
+          if (rc) return rc;
+          fold = p.t->fold_ok;
+        } else {
+          *optimistic = true;
+          p.optimistic_fold = true;
+        }
       }
       // bookkeeping regime (smax_tc.cu): exact column masks for thresholded searches and short target sets
       const bool colmask = a.d2_cap != 0x7fffffff || a.n_ttiles < 64;
@@ -832,7 +842,7 @@ static int make_view(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* parent, uint64
   *v = *parent;
   v->n = rows_real; v->n_pad = rows_pad;
   v->desc += row0 * kDescBytes; v->ext += row0 * kExtBytes;
-  v->norm += row0; v->wcol += row0; v->loc += row0; v->sigtheta += row0;
+  v->norm += row0; v->wcol += row0; v->loc += row0; v->sigtheta += row0; v->wmax += row0 / kChunk;
   v->resolved = false;                                   // the parent's packs may still be in flight: optimistic fold launch
   int rc = encode_map(ctx, &v->map_a, v->desc, rows_pad, kDescBytes, kBM, CU_TENSOR_MAP_SWIZZLE_128B);
   if (!rc) rc = encode_map(ctx, &v->map_b, v->desc, rows_pad, kDescBytes, kBN, CU_TENSOR_MAP_SWIZZLE_128B);

@@ -87,6 +87,7 @@ struct ssrlcv_b200_set_impl {
   int32_t* wcol;      // [n_pad]       kNoFoldC - (|b|^2 >> 1) (epilogue-add variant), 0 on padding rows
   float2*  loc;       // [n_pad]
   float2*  sigtheta;  // [n_pad]
+  int32_t* wmax;      // [n_pad / 32]  largest wcol of each 32-row window, 0 for windows of padding only
   int32_t* meta;      // [4] device scalars written by the pack kernel: [0] != 0 <=> some W does not fit the fold digits
   bool     fold_ok;      // every W fits the digit range -> fused extra-K-block path (host copy, valid after set_resolve)
   CUtensorMap map_a;     // desc, box 128 x kBM rows, SWIZZLE_128B
@@ -117,6 +118,7 @@ struct SmaxArgs {
   const uint8_t* q_desc; const int32_t* q_norm; const float2* q_loc;
   const float4* q_mask;          // [nq_pad][2] per-query epipolar mask state (geometry.cuh), masked modes only
   const uint8_t* t_desc; const int32_t* t_norm; const float2* t_loc; const int32_t* t_wcol;
+  const int32_t* t_wmax;         // [n_ttiles * 8] per-window maximum of t_wcol (no-fold variant)
   uint64_t* keys;                // [n_splits][nq_pad]
   uint32_t* flagged;             // list of (slot * nq_pad + row) needing the exact kernel
   uint32_t* n_flagged;

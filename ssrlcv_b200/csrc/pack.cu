@@ -3,6 +3,8 @@
 //   desc  uint8[n_pad][128]   one 128-byte row per feature (TMA box rows, SWIZZLE_128B)
 //   ext   uint8[n_pad][32]    base-255 digits of W = kFoldC - (|b|^2 >> 1) (extra K block, SWIZZLE_32B)
 //   norm  int32[n_pad]        |b|^2            wcol int32[n_pad]   kNoFoldC - (|b|^2 >> 1)
+//   wmax  int32[n_pad / 32]   largest wcol of each 32-row window (0 for windows of padding only): the bound the matcher's
+//                             no-fold variant tests before it adds W to a window's accumulators
 //   loc   float2[n_pad]       sigtheta float2[n_pad]
 // HBM-bound byte shuffling: 152 B read, 188 B written per feature.
 #include "matcher.cuh"
@@ -19,8 +21,8 @@ namespace b200 {
 // Rows [n, n_rows) are the zero padding of the set and are written here too (no memset of the allocation).
 __global__ void __launch_bounds__(256) pack_kernel(const RefFeature* __restrict__ in, uint64_t n, uint64_t n_rows,
                                                    uint8_t* __restrict__ desc, uint8_t* __restrict__ ext, int32_t* __restrict__ norm,
-                                                   int32_t* __restrict__ wcol, float2* __restrict__ loc, float2* __restrict__ sigtheta,
-                                                   int32_t* __restrict__ meta) {
+                                                   int32_t* __restrict__ wcol, int32_t* __restrict__ wmax, float2* __restrict__ loc,
+                                                   float2* __restrict__ sigtheta, int32_t* __restrict__ meta) {
   const int lane = threadIdx.x & 31, half = lane >> 4, sub = lane & 15;
   const uint64_t warp_global = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t n_warps = (gridDim.x * (uint64_t)blockDim.x) >> 5;
@@ -50,6 +52,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const RefFeature* __restrict_
         loc[i] = in[i].loc;
         sigtheta[i] = make_float2(in[i].sigma, in[i].theta);
         wn = kNoFoldC - h;
+        atomicMax(&wmax[i >> 5], wn);                              // wmax is zeroed with the meta scalars; wn >= 2
         const int32_t W = kFoldC - h;
         if (W >= 2) {
           uint32_t rest = static_cast<uint32_t>(W) / 255u;        // <= 31 * 255, spread greedily over digits 1..31
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const RefFeature* __restrict_
 }
 
 // Packs rows [0, n) of `feat_dev` into rows [row0, row0 + n) of the set's arrays and zero-fills up to row0 + n_rows;
-// meta_dev: the 4 x int32 device scalars of this range (already zeroed).
+// meta_dev: the 4 x int32 device scalars of this range (already zeroed, like the windows' wmax).  row0 % 32 == 0.
 void launch_pack(cudaStream_t st, const void* feat_dev, uint64_t n, uint64_t n_rows, uint64_t row0, ssrlcv_b200_set_impl& s,
                  int32_t* meta_dev, int sm_count) {
   if (n_rows == 0) return;
@@ -87,8 +90,8 @@ void launch_pack(cudaStream_t st, const void* feat_dev, uint64_t n, uint64_t n_r
   const uint64_t cap = static_cast<uint64_t>(sm_count) * 8;
   if (blocks > cap) blocks = cap;
   pack_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const RefFeature*>(feat_dev), n, n_rows, s.desc + row0 * kDescBytes,
-                                                             s.ext + row0 * kExtBytes, s.norm + row0, s.wcol + row0, s.loc + row0,
-                                                             s.sigtheta + row0, meta_dev);
+                                                             s.ext + row0 * kExtBytes, s.norm + row0, s.wcol + row0, s.wmax + row0 / kChunk,
+                                                             s.loc + row0, s.sigtheta + row0, meta_dev);
 }
 
 }  // namespace b200

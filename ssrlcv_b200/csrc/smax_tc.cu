@@ -40,13 +40,14 @@
 namespace b200 {
 
 constexpr int kStages = 4;
-constexpr int kColStages = 4;
+constexpr int kColStages = 8;   // deeper than the B ring: the producer must never wait for the epilogue before it can fetch B tiles
 constexpr uint32_t kABytes = kBM * kDescBytes;       // 16384
 constexpr uint32_t kBBytes = kBN * kDescBytes;       // 32768
 constexpr uint32_t kBExtBytes = kBN * kExtBytes;     // 8192
 constexpr uint32_t kAExtBytes = kBM * kExtBytes;     // 4096
 constexpr uint32_t kColLocBytes = kBN * 8;           // float2 per target
 constexpr uint32_t kColWBytes = kBN * 4;             // int32 W per target
+constexpr uint32_t kColWmaxBytes = (kBN / kChunk) * 4;  // int32 largest W per 32-target window
 constexpr uint32_t kTmemCols = 512;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (4 + kEpiWarps) * 32;      // 384
@@ -57,9 +58,11 @@ struct SmemLayout {
   static constexpr uint32_t b = a + 2 * kABytes;                         // kStages x 32 KB
   static constexpr uint32_t bext = b + kStages * kBBytes;                // kStages x 8 KB
   static constexpr uint32_t aext = bext + kStages * kBExtBytes;          // 4 KB
-  static constexpr uint32_t col_loc = aext + kAExtBytes;                 // kColStages x 2 KB
-  static constexpr uint32_t col_w = col_loc + kColStages * kColLocBytes; // kColStages x 1 KB
-  static constexpr uint32_t bars = col_w + kColStages * kColWBytes;
+  static constexpr uint32_t col_loc = aext + kAExtBytes;                 // kColStages x 2 KB   (masked variants)
+  // the no-fold variants have no digit tiles: their per-target W ring and window-bound ring live in the bext region
+  static constexpr uint32_t col_w = bext;                                // kColStages x 1 KB   (no-fold variants)
+  static constexpr uint32_t col_wmax = col_w + kColStages * kColWBytes;  // kColStages x 32 B   (8 window bounds per tile)
+  static constexpr uint32_t bars = col_loc + kColStages * kColLocBytes;
   static constexpr uint32_t n_bars = 2 * kStages + 4 + 4 + 2 * kColStages + 4;
   static constexpr uint32_t tmem_ptr = bars + n_bars * 8;
   static constexpr uint32_t xch = tmem_ptr + 16;                         // 2 (unit parity) x 2 (half) x 128 rows x 24 B
@@ -338,8 +341,10 @@ struct UnitIter {
 };
 
 // kMask: SSRLCV_B200_MASK_*.
-// kFold: W_b carried by the fifth MMA (true: +25 % tensor-pipe time, no epilogue work) or added to every accumulator
-//        element in the epilogue (false: any W, ALU-bound; sets whose norm range does not fit the fold digits).
+// kFold: W_b carried by the fifth MMA (true: +25 % tensor-pipe time, the accumulator IS the score) or left out of the
+//        contraction (false: four MMAs per tile, no digit tile; the epilogue takes the window maximum of a.b, adds the
+//        window's largest W -- a bound on every score of the window, pack.cu wmax -- and only when that bound reaches some
+//        lane's running best adds W to the 32 values and takes the exact maximum.  Any W, no fold-digit limit.)
 //        (A third way -- the epilogue warps storing W_b into the accumulator with tcgen05.st so that four accumulating MMAs
 //        suffice -- was built and measured: the tensor pipe is undisturbed, but the epilogue warps' serial ld -> st -> max
 //        chain takes 1 200 cycles per tile; 0.76 ms against 0.37 ms at 65 536 x 65 536.  profiles/r1c_init_variant.txt)
@@ -349,7 +354,7 @@ struct UnitIter {
 template <int kMask, bool kFold, bool kColMask, bool kTiming>
 __global__ void __launch_bounds__(kThreads, 1)
 smax_kernel(const SmaxBatch batch) {
-  constexpr bool kCols = (kMask != SSRLCV_B200_MASK_NONE) || !kFold;   // epilogue needs per-target data
+  constexpr bool kCols = (kMask != SSRLCV_B200_MASK_NONE) || !kFold;   // epilogue needs per-target data (locations / W)
   constexpr int32_t kWOffset = kFold ? kFoldC : kNoFoldC;               // the C of W_b = C - h_b
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -413,6 +418,7 @@ smax_kernel(const SmaxBatch batch) {
         }
         const float2* t_loc = u.J->a.t_loc;
         const int32_t* t_wcol = u.J->a.t_wcol;
+        const int32_t* t_wmax = u.J->a.t_wmax;
         mbar_wait(&a_empty[aslot], aphase ^ 1);
         mbar_arrive_expect_tx(&a_full[aslot], kABytes);
         tma_load_2d(smem + SmemLayout::a + aslot * kABytes, map_q, &a_full[aslot], 0, static_cast<int32_t>(u.qt * kBM));
@@ -427,12 +433,14 @@ smax_kernel(const SmaxBatch batch) {
           if (++stage == kStages) { stage = 0; phase ^= 1; }
           if (kCols) {
             mbar_wait(&c_empty[cs], cphase ^ 1);
-            const uint32_t bytes = (kMask != SSRLCV_B200_MASK_NONE ? kColLocBytes : 0) + (!kFold ? kColWBytes : 0);
+            const uint32_t bytes = (kMask != SSRLCV_B200_MASK_NONE ? kColLocBytes : 0) + (!kFold ? kColWBytes + kColWmaxBytes : 0);
             mbar_arrive_expect_tx(&c_full[cs], bytes);
             if (kMask != SSRLCV_B200_MASK_NONE)
               bulk_load_1d(smem + SmemLayout::col_loc + cs * kColLocBytes, t_loc + static_cast<uint64_t>(j) * kBN, kColLocBytes, &c_full[cs]);
-            if (!kFold)
+            if (!kFold) {   // W of the tile's 256 targets and the largest W of each of its 8 windows (pack.cu wcol / wmax)
               bulk_load_1d(smem + SmemLayout::col_w + cs * kColWBytes, t_wcol + static_cast<uint64_t>(j) * kBN, kColWBytes, &c_full[cs]);
+              bulk_load_1d(smem + SmemLayout::col_wmax + cs * kColWmaxBytes, t_wmax + static_cast<uint64_t>(j) * (kBN / kChunk), kColWmaxBytes, &c_full[cs]);
+            }
             if (++cs == kColStages) { cs = 0; cphase ^= 1; }
           }
         }
@@ -524,7 +532,7 @@ smax_kernel(const SmaxBatch batch) {
     constexpr uint32_t kWinPerWarp = kWinPerTile / 2;  // 4
     WinState* xch = reinterpret_cast<WinState*>(smem + SmemLayout::xch);
     uint32_t it = 0, uiter = 0;                       // it: tiles consumed so far -> accumulator slot / column stage and their phases
-    long long te_wait = 0, te_work = 0, te_resolve = 0, te_total0 = 0;
+    long long te_wait = 0, te_work = 0, te_resolve = 0, te_total0 = 0, te_live = 0, te_cwait = 0;
     if (kTiming) te_total0 = clock64();
     UnitIter u(batch, blockIdx.x);
     while (u.next(batch, blockIdx.x, kFold)) {
@@ -553,6 +561,16 @@ smax_kernel(const SmaxBatch batch) {
         if (kTiming) e0 = clock64();
         const uint32_t acc = it & 1, accphase = (it >> 1) & 1, cs = it % kColStages, cphase = (it / kColStages) & 1;
         ++it;
+        // the tile's column data (staged several tiles ahead) first: nothing then stands between the accumulator and the max trees
+        long long cw0 = 0;
+        if (kTiming) cw0 = clock64();
+        if (kCols) mbar_wait(&c_full[cs], cphase);
+        if (kTiming) te_cwait += clock64() - cw0;
+        int32_t wbound[kWinPerWarp] = {0, 0, 0, 0};                // no-fold: largest W of each of this warp's windows
+        if (!kFold) {
+          const int4 wb = ld_shared_v4(smem_u32(smem + SmemLayout::col_wmax + cs * kColWmaxBytes + half * (kWinPerWarp * 4)));
+          wbound[0] = wb.x; wbound[1] = wb.y; wbound[2] = wb.z; wbound[3] = wb.w;
+        }
         mbar_wait(&t_full[acc], accphase);
         if (kTiming) e1 = clock64();
         tc_fence_after();
@@ -563,46 +581,54 @@ smax_kernel(const SmaxBatch batch) {
         // Copy this warp's 32 x 128 slice of the accumulator into registers and hand the TMEM buffer straight back to
         // the MMA warp: the tensor pipe never waits for the reduction below, only for these four loads.
         uint32_t v[kWinPerWarp][32];
-#pragma unroll
-        for (uint32_t k = 0; k < kWinPerWarp; ++k) tmem_ld_32x32(taddr + k * kChunk, v[k]);
+        tmem_ld_32x128(taddr, v);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[acc]);
 
-        if (kCols) mbar_wait(&c_full[cs], cphase);
-        int32_t wm[kWinPerWarp];                                   // per-window maxima of this warp's 4 windows
+        // Window maxima of this warp's 4 windows, straight from the accumulator: one branch-free block (the four max trees
+        // interleave).  Fold, unmasked: these ARE the windows' best scores.  Otherwise they are upper bounds of them:
+        //   no-fold: the accumulator holds a.b only; max(a.b) + (largest W of the window) bounds every score of the window
+        //   masked : the unmasked maximum bounds the masked one
+        int32_t wm[kWinPerWarp];
 #pragma unroll
-        for (uint32_t k = 0; k < kWinPerWarp; ++k) {
-          uint32_t(&x)[32] = v[k];
-          if (!kFold) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) x[e] = static_cast<uint32_t>(static_cast<int32_t>(x[e]) + s_w[(c_begin + k) * kChunk + e]);
-          }
-          int32_t m = max32(x);
-          if (kMask != SSRLCV_B200_MASK_NONE) {
-            // The unmasked window maximum bounds the masked one: the reference's float mask (ref: src/MatchFactory.cu:
-            // 2241-2254, :1613-1627) is evaluated only for windows that could still reach some lane's running best.
-            if (__any_sync(0xffffffffu, m >= st.best)) {
-#pragma unroll
-              for (int e = 0; e < 32; e += 2) {
-                const float4 l2 = *reinterpret_cast<const float4*>(&s_loc[(c_begin + k) * kChunk + e]);
-                if (mask_skips<kMask>(qm, l2.x, l2.y, eps)) x[e] = 0;
-                if (mask_skips<kMask>(qm, l2.z, l2.w, eps)) x[e + 1] = 0;
-              }
-              m = max32(x);
-            }
-          }
-          // rows past the end of the target set are zero padding with W = 0: score 0, below every floor
-          wm[k] = m;
-        }
-        if (kCols) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&c_empty[cs]);
-        }
-        // Bookkeeping only when some lane's window reaches its running best (warp-uniform test, branch-free body).
+        for (uint32_t k = 0; k < kWinPerWarp; ++k) wm[k] = max32(v[k]) + wbound[k];
+        // One warp-uniform test per tile: does any window reach some lane's running best?  (Thresholded search: next to never.)
         const int32_t mt = max(max(wm[0], wm[1]), max(wm[2], wm[3]));
         if (__any_sync(0xffffffffu, mt >= st.best)) {
+          if (kMask != SSRLCV_B200_MASK_NONE || !kFold) {
+            // turn the bounds of the windows that matter into exact maxima; the others stay bounds below every lane's best
+#pragma unroll
+            for (uint32_t k = 0; k < kWinPerWarp; ++k) {
+              if (!__any_sync(0xffffffffu, wm[k] >= st.best)) continue;
+              uint32_t(&x)[32] = v[k];
+              if (kTiming) ++te_live;
+              if (!kFold) {                                        // exact scores, as the fold variant gets them from the tensor pipe
+                const uint32_t wp = smem_u32(s_w + (c_begin + k) * kChunk);
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) {
+                  const int4 w4 = ld_shared_v4(wp + 4 * e);
+                  x[e] += static_cast<uint32_t>(w4.x); x[e + 1] += static_cast<uint32_t>(w4.y);
+                  x[e + 2] += static_cast<uint32_t>(w4.z); x[e + 3] += static_cast<uint32_t>(w4.w);
+                }
+                wm[k] = max32(x);
+                if (kMask != SSRLCV_B200_MASK_NONE && !__any_sync(0xffffffffu, wm[k] >= st.best)) continue;
+              }
+              if (kMask != SSRLCV_B200_MASK_NONE) {
+                // the reference's float mask (ref: src/MatchFactory.cu:2241-2254, :1613-1627); masked entries score 0, below
+                // every floor (as do the rows past the end of the target set: zero padding with W = 0)
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                  const float4 l2 = *reinterpret_cast<const float4*>(&s_loc[(c_begin + k) * kChunk + e]);
+                  if (mask_skips<kMask>(qm, l2.x, l2.y, eps)) x[e] = 0;
+                  if (mask_skips<kMask>(qm, l2.z, l2.w, eps)) x[e + 1] = 0;
+                }
+                wm[k] = max32(x);
+              }
+            }
+          }
+          // bookkeeping (branch-free body)
           if (kColMask) {
 #pragma unroll
             for (uint32_t k = 0; k < kWinPerWarp; ++k) {
@@ -613,6 +639,10 @@ smax_kernel(const SmaxBatch batch) {
 #pragma unroll
             for (uint32_t k = 0; k < kWinPerWarp; ++k) win_update(st, wm[k], j * kWinPerTile + c_begin + k, 0u);
           }
+        }
+        if (kCols) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&c_empty[cs]);
         }
         if (kTiming) { const long long e2 = clock64(); te_wait += e1 - e0; te_work += e2 - e1; }
       }
@@ -643,6 +673,8 @@ smax_kernel(const SmaxBatch batch) {
       if (e == 0 || e == 5) {
         const uint32_t o = blockIdx.x * 16 + (e == 0 ? 4 : 8);
         batch.timing[o + 0] = te_wait; batch.timing[o + 1] = te_work; batch.timing[o + 2] = te_resolve; batch.timing[o + 3] = clock64() - te_total0;
+        if (e == 0) { batch.timing[blockIdx.x * 16 + 14] = te_live; batch.timing[blockIdx.x * 16 + 15] = te_cwait; }
+        if (e == 0 && false) batch.timing[blockIdx.x * 16 + 14] = te_live;     // no-fold: windows whose bound reached a running best
       }
     }
   }
@@ -671,6 +703,8 @@ static cudaError_t launch_mask(cudaStream_t st, const SmaxBatch& b, bool fold, b
     if (kMask != SSRLCV_B200_MASK_FUNDAMENTAL && fold)
       return colmask ? launch_one<kMask == SSRLCV_B200_MASK_FUNDAMENTAL ? 0 : kMask, true, true, true>(st, b)
                      : launch_one<kMask == SSRLCV_B200_MASK_FUNDAMENTAL ? 0 : kMask, true, false, true>(st, b);
+    if (kMask == SSRLCV_B200_MASK_NONE && !fold)
+      return colmask ? launch_one<SSRLCV_B200_MASK_NONE, false, true, true>(st, b) : launch_one<SSRLCV_B200_MASK_NONE, false, false, true>(st, b);
   }
   if (fold) return colmask ? launch_one<kMask, true, true, false>(st, b) : launch_one<kMask, true, false, false>(st, b);
   return colmask ? launch_one<kMask, false, true, false>(st, b) : launch_one<kMask, false, false, false>(st, b);

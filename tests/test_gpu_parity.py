@@ -230,6 +230,31 @@ def test_memory_states_restored(api):
         mf.generateMatches(api.Image(0), qu, api.Image(1), tu, api.Unity(np.zeros(5, np.float32), np.dtype("<f4"), api.cpu))
 
 
+@pytest.mark.parametrize("fold", ["0", "1"])
+@pytest.mark.parametrize("thr", [FLT_MAX, 9.0e4])
+def test_forced_matcher_variants(api, everest, monkeypatch, fold, thr):
+    """SSRLCV_B200_FOLD forces the tensor-core kernel variant: five MMAs per tile with W folded into the contraction ("1"), or
+    four MMAs with the window-bound test and W added in the epilogue ("0", otherwise only taken by sets whose norms do not
+    fit the fold digits).  Both are exact, thresholded (column regime) and not (window regime), masked and unmasked."""
+    monkeypatch.setenv("SSRLCV_B200_FOLD", fold)
+    q, t = synth.make_pair(3000, 9000, seed=77)
+    s = synth.make_seed(700)
+    mf = api.MatchFactory(0.8, thr)
+    mf.setSeedFeatures(_unity(api, s))
+    qu, tu = _unity(api, q), _unity(api, t)
+    sd = mf.getSeedDistances(qu)
+    sd_want = api.O.seed_distances(q, s)
+    assert np.array_equal(sd.to_numpy(), sd_want)
+    got = mf.generateDistanceMatches(api.Image(0), qu, api.Image(1), tu, sd).to_numpy()
+    want = api.O.generate_matches(api.O.make_params(out_kind=T.OUT_DMATCH, has_seed=True, abs_threshold=thr, rel_threshold=0.8), q, t, sd_want)
+    assert len(want) > 100 and T.fields_equal(got, want)
+    qi, ti = api.Image(0, everest.cameras[0]), api.Image(1, everest.cameras[1])
+    got = mf.generateDistanceMatchesDoubleConstrained(qi, qu, ti, tu, 25.0, 5.0).to_numpy()
+    p = api.O.make_params(out_kind=T.OUT_DMATCH, mask_kind=T.MASK_DOUBLE, abs_threshold=thr, query_id=0, target_id=1, epsilon=25, delta=5,
+                          query_camera=everest.cameras[0], target_camera=everest.cameras[1])
+    assert T.fields_equal(got, api.O.generate_matches(p, q, t))
+
+
 # ------------------------------------------------------------------------------------ host-buffer entry point
 def _match_host(api, mf, p, q, t, s, elt_dtype):
     """ssrlcv_b200_match_host on plain (pageable) numpy buffers -> record array"""

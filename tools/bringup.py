@@ -70,7 +70,7 @@ def rung(name):
         for nq, nt in ((1, 1), (7, 33), (128, 256), (300, 1000)):
             ok &= run_engine_case(1, nq, nt, "simt")
     elif name == "tc_nofold":
-        os.environ["SSRLCV_B200_NOFOLD"] = "1"
+        os.environ["SSRLCV_B200_FOLD"] = "0"
         for nq, nt in ((128, 256), (1, 1), (300, 1000), (1000, 5000)):
             ok &= run_engine_case(0, nq, nt, "tc_nofold")
     elif name == "tc_fold":
@@ -79,7 +79,7 @@ def rung(name):
         ok &= run_engine_case(0, 500, 3000, "tc_fold_uniform_bytes", sift_like=False)
     elif name == "tc_big":
         ok &= run_engine_case(0, 16384, 16384, "tc_fold", seed=3)
-        os.environ["SSRLCV_B200_NOFOLD"] = "1"
+        os.environ["SSRLCV_B200_FOLD"] = "0"
         ok &= run_engine_case(0, 8192, 20000, "tc_nofold", seed=4)
     elif name == "masked":
         from oracle import oracle as O
