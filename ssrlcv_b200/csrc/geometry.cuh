@@ -145,6 +145,23 @@ __device__ __forceinline__ bool mask_skips(const QueryMask& m, float tx, float t
   return false;
 }
 
+// the mask state of lane `src`, on every lane of the warp
+template <int kMask>
+__device__ __forceinline__ QueryMask shfl_query_mask(const QueryMask& m, int src) {
+  QueryMask r;
+  if (kMask == SSRLCV_B200_MASK_DOUBLE) {
+    r.seg.lo_x = __shfl_sync(0xffffffffu, m.seg.lo_x, src); r.seg.hi_x = __shfl_sync(0xffffffffu, m.seg.hi_x, src);
+    r.seg.left_x = __shfl_sync(0xffffffffu, m.seg.left_x, src); r.seg.left_y = __shfl_sync(0xffffffffu, m.seg.left_y, src);
+    r.seg.slope = __shfl_sync(0xffffffffu, m.seg.slope, src); r.seg.top_lo = __shfl_sync(0xffffffffu, m.seg.top_lo, src);
+    r.seg.bot_hi = __shfl_sync(0xffffffffu, m.seg.bot_hi, src); r.seg.vertical = __shfl_sync(0xffffffffu, m.seg.vertical, src);
+  }
+  if (kMask == SSRLCV_B200_MASK_FUNDAMENTAL) {
+    r.line.ex = __shfl_sync(0xffffffffu, m.line.ex, src); r.line.ey = __shfl_sync(0xffffffffu, m.line.ey, src);
+    r.line.ez = __shfl_sync(0xffffffffu, m.line.ez, src);
+  }
+  return r;
+}
+
 // The per-query mask state is computed once per call by a prologue kernel (the trigonometry of getEpipolarEndpoints is
 // ~10^3 instructions) and stored as two float4 per query; the matcher kernels only load it.
 template <int kMask>

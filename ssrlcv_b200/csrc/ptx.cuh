@@ -116,6 +116,12 @@ __device__ __forceinline__ int4 ld_shared_v4(uint32_t addr) {
   return v;
 }
 
+__device__ __forceinline__ float2 ld_shared_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+
 // 32 lanes x 32 columns of 32-bit: thread i of the warp gets columns [c, c+32) of TMEM lane (lane_base + i).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

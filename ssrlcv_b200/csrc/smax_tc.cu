@@ -616,14 +616,22 @@ smax_kernel(const SmaxBatch batch) {
                 if (kMask != SSRLCV_B200_MASK_NONE && !__any_sync(0xffffffffu, wm[k] >= st.best)) continue;
               }
               if (kMask != SSRLCV_B200_MASK_NONE) {
-                // the reference's float mask (ref: src/MatchFactory.cu:2241-2254, :1613-1627); masked entries score 0, below
-                // every floor (as do the rows past the end of the target set: zero padding with W = 0)
-#pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                  const float4 l2 = *reinterpret_cast<const float4*>(&s_loc[(c_begin + k) * kChunk + e]);
-                  if (mask_skips<kMask>(qm, l2.x, l2.y, eps)) x[e] = 0;
-                  if (mask_skips<kMask>(qm, l2.z, l2.w, eps)) x[e + 1] = 0;
+                // The reference's float mask (ref: src/MatchFactory.cu:2241-2254, :1613-1627) for the queries (lanes) this window
+                // matters to -- usually one.  The warp evaluates it together: the live query's mask state is broadcast, lane l
+                // tests target l of the window, the ballot comes back to the query's lane as a column mask.  Masked entries
+                // score 0, below every floor (as do the rows past the end of the target set: zero padding with W = 0).
+                uint32_t todo = __ballot_sync(0xffffffffu, wm[k] >= st.best);
+                uint32_t skip = 0;
+                const float2 tl = ld_shared_f2(smem_u32(s_loc + (c_begin + k) * kChunk + lane));
+                while (todo) {
+                  const int src = __ffs(todo) - 1;
+                  todo &= todo - 1;
+                  const QueryMask qs = shfl_query_mask<kMask>(qm, src);
+                  const uint32_t b = __ballot_sync(0xffffffffu, mask_skips<kMask>(qs, tl.x, tl.y, eps));
+                  skip = lane == src ? b : skip;
                 }
+#pragma unroll
+                for (int e = 0; e < 32; ++e) x[e] = (skip >> e) & 1u ? 0u : x[e];
                 wm[k] = max32(x);
               }
             }
