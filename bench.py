@@ -76,6 +76,29 @@ def big_pair(nq, nt, seed):
     return np.concatenate(qs)[:nq], np.concatenate(ts)[:nt]
 
 
+def bind_to_gpu_numa(index):
+    """Run this process on the CPUs local to GPU `index` (NVML's ideal CPU affinity) so that the pinned host buffers of the
+    e2e leg are allocated, and their copies issued, on the NUMA node the GPU hangs off; a pinned buffer on the far socket
+    costs up to 3x in H2D time (profiles/r1f_e2eprof_c3.txt).  Returns the previous mask (restore before the CPU baseline,
+    which wants every core), or None when NVML is not available."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(index).uuid))
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        prev = os.sched_getaffinity(0)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(prev) + 64) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1} & prev
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return prev
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -225,6 +248,7 @@ def run_ours(args, w, rank, world, local_rank):
     from ssrlcv_b200 import _lib, types as T
     from ssrlcv_b200.match_factory import Context
     torch.cuda.set_device(local_rank)
+    prev_affinity = bind_to_gpu_numa(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -354,13 +378,16 @@ def run_ours(args, w, rank, world, local_rank):
         "clocks": clocks,
         "e2e": {"value": world * evals * args.steps / (e2e_ms * 1e-3), "unit": "dist-evals/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": (len(q) + len(t) + (len(s) if s is not None else 0)) * 152, "d2h_bytes_per_step": n_e2e * 48 + 8,
-                "api": "ssrlcv_b200_match_host (pinned host buffers in, records out)"},
+                "api": "ssrlcv_b200_match_host (pinned host buffers in, records out)",
+                "host": "process bound to the GPU-local CPUs (NVML affinity) while the pinned buffers are allocated and used" if prev_affinity else "no NUMA binding"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tops, "unit": "TFLOP/s", "frac": achieved / peak_tops, "traffic": traffic,
                      "kernel": "smax_kernel (tcgen05.mma kind::i8 + fused argmax epilogue)", "kernel_ms": kern_ms, "launches_timed": int(k_n.value),
                      "ops": "int8 dense: 256 ops per distance evaluation (128 u8 x u8 MACs); the fold's extra K block is not counted",
                      "peak_source": f"2 x bf16_tflops burst, {src}; nominal dense int8 is 4500"},
     }
+    if prev_affinity:
+        os.sched_setaffinity(0, prev_affinity)       # the CPU baseline uses every core the box gives us
     try:
         line["cpu_baseline"] = cpu_baseline(w, q, t, s) if not args.no_cpu_baseline else None
     except Exception as e:  # noqa: BLE001
@@ -378,6 +405,7 @@ def run_sharded(args, w, rank, world, local_rank):
     from ssrlcv_b200.match_factory import Context
     from ssrlcv_b200.pair_scheduler import assign_pairs, pair_order
     torch.cuda.set_device(local_rank)
+    bind_to_gpu_numa(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist

@@ -168,6 +168,12 @@ int  ssrlcv_b200_refine(ssrlcv_b200_ctx* ctx, void* dmatches_dev, uint64_t n, fl
 int  ssrlcv_b200_sort(ssrlcv_b200_ctx* ctx, void* dmatches_dev, uint64_t n);
 /* replaces: getRawMatches + convertMatchToRaw (src/MatchFactory.cu:257-280, :2921-2926). */
 int  ssrlcv_b200_raw_matches(ssrlcv_b200_ctx* ctx, const void* dmatches_dev, uint64_t n, void* matches_dev);
+/* replaces: the 2-view tail of doFeatureMatching (src/Pipeline.cu:198-222): D2H of the DMatch array, host scan for the
+ * largest distance, getRawMatches, D2H, host loop writing the MatchSet.  One device pass: keypoints_dev receives
+ * KeyPoint[2n] (16 B each: match i -> entries 2i, 2i+1), multimatches_dev MultiMatch[n] = {numKeyPoints 2, index 2i}
+ * (8 B each), *max_distance the largest DMatch.distance (0 if n == 0; may be NULL). */
+int  ssrlcv_b200_match_set_2view(ssrlcv_b200_ctx* ctx, const void* dmatches_dev, uint64_t n, void* keypoints_dev,
+                                 void* multimatches_dev, float* max_distance);
 
 /* ---- diagnostics used by the parity tests ----------------------------------------------------
  * per-query epipolar segment end points (p1.x,p1.y,p2.x,p2.y) as the DoubleConstrained prologue

@@ -22,7 +22,7 @@ EXPORTS = [
     "ssrlcv_b200_set_size", "ssrlcv_b200_set_free", "ssrlcv_b200_seed_distances", "ssrlcv_b200_match",
     "ssrlcv_b200_match_host", "ssrlcv_b200_match_batch", "ssrlcv_b200_match_candidates", "ssrlcv_b200_finalize_candidates",
     "ssrlcv_b200_set_loc", "ssrlcv_b200_validate", "ssrlcv_b200_refine", "ssrlcv_b200_sort",
-    "ssrlcv_b200_raw_matches", "ssrlcv_b200_epipolar_endpoints", "ssrlcv_b200_device_sincos",
+    "ssrlcv_b200_raw_matches", "ssrlcv_b200_match_set_2view", "ssrlcv_b200_epipolar_endpoints", "ssrlcv_b200_device_sincos",
 ]
 
 
@@ -89,6 +89,7 @@ def load() -> C.CDLL:
     lib.ssrlcv_b200_refine.argtypes = [vp, vp, u64, f32, pu64]
     lib.ssrlcv_b200_sort.argtypes = [vp, vp, u64]
     lib.ssrlcv_b200_raw_matches.argtypes = [vp, vp, u64, vp]
+    lib.ssrlcv_b200_match_set_2view.argtypes = [vp, vp, u64, vp, vp, C.POINTER(C.c_float)]
     lib.ssrlcv_b200_epipolar_endpoints.argtypes = [vp, pp, vp, vp]
     lib.ssrlcv_b200_device_sincos.argtypes = [vp, vp, u64, vp, vp]
     for name in EXPORTS:

@@ -37,6 +37,7 @@ void launch_fill_u64(cudaStream_t, uint64_t*, uint64_t, uint64_t);
 void launch_min_keys(cudaStream_t, const uint64_t*, uint32_t, uint32_t, uint32_t, uint64_t*);
 void launch_compact(cudaStream_t, CompactArgs);
 void launch_raw_matches(cudaStream_t, const void*, uint32_t, void*);
+void launch_match_set_2view(cudaStream_t, const void*, uint32_t, void*, void*, uint32_t*);
 uint64_t launch_sort(cudaStream_t, void*, uint32_t, uint64_t*, void*);
 }  // namespace b200
 
@@ -526,7 +527,8 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
         }
       }
       // bookkeeping regime (smax_tc.cu): exact column masks for thresholded searches and short target sets
-      const bool colmask = a.d2_cap != 0x7fffffff || a.n_ttiles < 64;
+      bool colmask = a.d2_cap != 0x7fffffff || a.n_ttiles < 64;
+      if (const char* c = getenv("SSRLCV_B200_COLMASK")) colmask = c[0] != '0';   // A/B timing, tests
       Group& g = groups[p.mp.kind * 4 + (fold ? 2 : 0) + (colmask ? 1 : 0)];
       a.tile_begin = g.total;
       g.total += tiles;
@@ -1119,6 +1121,21 @@ int ssrlcv_b200_raw_matches(ssrlcv_b200_ctx* ctx, const void* dmatches_dev, uint
   if (n) ctx->launches += 1;
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaGetLastError());
+  return 0;
+}
+
+int ssrlcv_b200_match_set_2view(ssrlcv_b200_ctx* ctx, const void* dmatches_dev, uint64_t n, void* keypoints_dev, void* multimatches_dev,
+                                float* max_distance) {
+  if (!ctx || (n && (!dmatches_dev || !keypoints_dev || !multimatches_dev)) || n > 0x3fffffffull)
+    return fail(ctx, SSRLCV_B200_EINVAL, "match_set_2view: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemsetAsync(ctx->d_scalars + 3, 0, sizeof(uint32_t), ctx->stream));
+  launch_match_set_2view(ctx->stream, dmatches_dev, static_cast<uint32_t>(n), keypoints_dev, multimatches_dev, ctx->d_scalars + 3);
+  if (n) ctx->launches += 1;
+  CU(cudaMemcpyAsync(ctx->h_scalars + 3, ctx->d_scalars + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaGetLastError());
+  if (max_distance) memcpy(max_distance, ctx->h_scalars + 3, sizeof(float));
   return 0;
 }
 

@@ -250,6 +250,33 @@ void launch_raw_matches(cudaStream_t st, const void* in, uint32_t n, void* out) 
   if (n) raw_matches_kernel<<<(n + 255) / 256, 256, 0, st>>>(static_cast<const RefDMatch*>(in), n, static_cast<RefMatch*>(out));
 }
 
+// ---------------------------------------------------------------- 2-view MatchSet (tail of doFeatureMatching)
+// ref: src/Pipeline.cu:198-222 -- D2H of the DMatch array, host scan for the largest distance, getRawMatches, D2H of the
+// Match array and a host loop writing KeyPoint[2n] / MultiMatch[n] = {2, 2i}.  One pass on the device instead: the MatchSet
+// arrays are written straight from the DMatch records and the largest distance is reduced on the way (distances are >= 0,
+// so their bit patterns order like the floats; the reference's scan starts at 0.0f and uses `<`, NaN never wins).
+struct RefMultiMatch { uint32_t numKeyPoints; int32_t index; };
+__global__ void match_set_2view_kernel(const RefDMatch* in, uint32_t n, RefKeyPoint* kp, RefMultiMatch* mm, uint32_t* max_bits) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t bits = 0;
+  if (i < n) {
+    const uint64_t* s = reinterpret_cast<const uint64_t*>(in + i);
+    uint64_t* d = reinterpret_cast<uint64_t*>(kp + 2 * static_cast<uint64_t>(i));
+    d[0] = s[1]; d[1] = s[2]; d[2] = s[3]; d[3] = s[4];            // keyPoints[0], keyPoints[1] (16 B each, at byte 8 of the record)
+    mm[i].numKeyPoints = 2u;
+    mm[i].index = static_cast<int32_t>(2 * i);
+    const float dist = in[i].distance;
+    if (dist > 0.0f) bits = __float_as_uint(dist);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
+  if ((threadIdx.x & 31) == 0 && bits) atomicMax(max_bits, bits);
+}
+void launch_match_set_2view(cudaStream_t st, const void* in, uint32_t n, void* kp, void* mm, uint32_t* max_bits) {
+  if (n) match_set_2view_kernel<<<(n + 255) / 256, 256, 0, st>>>(static_cast<const RefDMatch*>(in), n, static_cast<RefKeyPoint*>(kp),
+                                                                  static_cast<RefMultiMatch*>(mm), max_bits);
+}
+
 // ---------------------------------------------------------------- sortMatches: bitonic sort of (orderable distance bits, index)
 __device__ __forceinline__ uint32_t orderable(float f) {
   const uint32_t u = __float_as_uint(f);

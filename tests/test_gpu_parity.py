@@ -704,3 +704,30 @@ def test_dropin_refine_sort_raw(api):
     # the reference's thrust::sort is unstable: inside runs of equal distance only the set of records is defined
     key = lambda r: (float(r["distance"]), r["keyPoints"]["loc"].tobytes())
     assert sorted(map(key, ma)) == sorted(map(key, mb))
+
+
+def test_do_feature_matching_two_view_golden(api, everest):
+    """ref: src/Pipeline.cu:173-241 through the mirror in ssrlcv_b200/pipeline.py: the 2-view tail (D2H, max-distance scan,
+    getRawMatches, host loop) is one device pass (ssrlcv_b200_match_set_2view); output = the reference's golden MatchSet
+    (test/checkpoints/Pipeline2View, test/Pipeline.cu:183-216)."""
+    from ssrlcv_b200.pipeline import FeatureMatchingInput, doFeatureMatching
+    ev = everest
+    inp = FeatureMatchingInput(images=[api.Image(ev.img_ids[0], ev.cameras[0]), api.Image(ev.img_ids[1], ev.cameras[1])],
+                               allFeatures=[_unity(api, ev.views2[0]), _unity(api, ev.views2[1])], seedFeatures=_unity(api, ev.seed2),
+                               epsilon=ev.epsilon, delta=ev.delta)
+    out = doFeatureMatching(inp)
+    kp, mm = out.matchSet.keyPoints.to_numpy(), out.matchSet.matches.to_numpy()
+    assert len(mm) == 13534 and len(kp) == 27068
+    assert T.fields_equal(kp, ev.g2_keypoints) and T.fields_equal(mm, ev.g2_multimatch)
+    # the largest distance the reference logs: against the oracle's DMatch list
+    sd = api.O.seed_distances(ev.views2[0], ev.seed2)
+    p = api.O.make_params(out_kind=T.OUT_DMATCH, mask_kind=T.MASK_DOUBLE, has_seed=True, abs_threshold=ev.abs_threshold, rel_threshold=ev.rel_threshold,
+                          query_id=ev.img_ids[0], target_id=ev.img_ids[1], epsilon=ev.epsilon, delta=ev.delta,
+                          query_camera=ev.cameras[0], target_camera=ev.cameras[1])
+    want = api.O.generate_matches(p, ev.views2[0], ev.views2[1], sd)
+    assert out.maxDistance == float(want["distance"].max())
+    # empty list
+    from ssrlcv_b200.pipeline import match_set_2view
+    mf = api.MatchFactory(0.6, 4e4)
+    ms, mx = match_set_2view(mf, api.Unity(np.zeros(0, T.DMATCH), T.DMATCH, api.cpu))
+    assert ms.matches.size() == 0 and ms.keyPoints.size() == 0 and mx == 0.0

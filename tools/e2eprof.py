@@ -12,11 +12,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from bench import ABS_THR, REL_THR, WORKLOADS, synth_inputs  # noqa: E402
+from bench import ABS_THR, REL_THR, WORKLOADS, bind_to_gpu_numa, synth_inputs  # noqa: E402
 from ssrlcv_b200 import _lib, types as T  # noqa: E402
 from ssrlcv_b200.match_factory import Context  # noqa: E402
 
 w = WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "C3"]
+if os.environ.get("E2EPROF_NO_BIND") is None:
+    print("affinity before", len(os.sched_getaffinity(0)), "cpus; bound:", bind_to_gpu_numa(0) is not None, "->", len(os.sched_getaffinity(0)), "cpus")
 ctx = Context.get(0)
 lib, h = ctx.lib, ctx.handle
 q, t, s = synth_inputs(w, 0)
@@ -42,6 +44,9 @@ def med(fn, n=12):
 
 # plain copies
 d = torch.empty_like(qh, device="cuda")
+d2 = torch.empty_like(th, device="cuda")
+us2 = med(lambda: d2.copy_(th, non_blocking=True))
+print(f"H2D pinned (target buffer) {th.numel() / 1e6:.1f} MB: {us2:.1f} us = {th.numel() / us2 / 1e3:.1f} GB/s")
 us = med(lambda: d.copy_(qh, non_blocking=True))
 print(f"H2D pinned {qh.numel() / 1e6:.1f} MB: {us:.1f} us = {qh.numel() / us / 1e3:.1f} GB/s")
 us = med(lambda: out_h.copy_(out_d, non_blocking=True))
