@@ -589,6 +589,17 @@ def run_sharded(args, w, rank, world, local_rank):
                      "peak_source": f"2 x bf16_tflops burst, {src}; nominal dense int8 is 4500"},
         "cpu_baseline": None,
     }
+    if world == 1 and not args.no_cpu_baseline:
+        # the CPU oracle on a bounded sample of the same workload: C4 = a query sample of ONE of its 120 equal pairs,
+        # C5 = a query sample against the whole target set (dist-evals/s does not depend on which pair / which queries)
+        try:
+            cq, ct = (views[0], views[1]) if is_c4 else (q, t)
+            cb = cpu_baseline(dict(w, mask=0), cq, ct, None)
+            if is_c4:
+                cb["sample"] += f" (one pair of the {len(pairs)})"
+            line["cpu_baseline"] = cb
+        except Exception as e:  # the oracle library is test infrastructure; its absence must not hide the GPU numbers
+            line["cpu_baseline"] = {"unavailable": str(e)}
     if dist is not None:
         dist.destroy_process_group()
     return line
