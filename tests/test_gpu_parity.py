@@ -731,3 +731,87 @@ def test_do_feature_matching_two_view_golden(api, everest):
     mf = api.MatchFactory(0.6, 4e4)
     ms, mx = match_set_2view(mf, api.Unity(np.zeros(0, T.DMATCH), T.DMATCH, api.cpu))
     assert ms.matches.size() == 0 and ms.keyPoints.size() == 0 and mx == 0.0
+
+
+# ------------------------------------------------------------------------------------ size-independent properties at full size
+def test_c5_size_self_match_and_sharded_merge(api):
+    """BASELINE C5 size (1 048 576 x 1 048 576), where the CPU oracle would take minutes: a set matched against ITSELF has a known
+    answer -- every query finds distance 0 at the member of its group of identical descriptors with the smallest key
+    (f mod 32, f) (the reference's lane rule, src/MatchFactory.cu:1476-1492) -- and the answer must not depend on how the
+    target set is sharded (4 shards merged through the candidate keys == one call)."""
+    import torch
+    from ssrlcv_b200.match_factory import pack
+    n = 1 << 20
+    rng = np.random.default_rng(2026)
+    base = synth.sift_descriptors(rng, 1 << 16)
+    v = base[rng.integers(0, len(base), n)].copy()                                  # many exact duplicates, all over the index range
+    v[:, :4] = (v[:, :4].astype(np.int32) + rng.integers(0, 4, (n, 4))).astype(np.uint8)   # ... thinned out to groups of a few
+    f = T.make_features(v, rng.uniform(0, 4096, (n, 2)).astype(np.float32))
+    # expected winner per query: smallest (f % 32, f) within its group of identical descriptors
+    _, inv = np.unique(v.view(np.dtype((np.void, 128))).reshape(-1), return_inverse=True)
+    idx = np.arange(n, dtype=np.int64)
+    key = ((idx & 31) << 32) | idx
+    best = np.full(inv.max() + 1, np.iinfo(np.int64).max)
+    np.minimum.at(best, inv, key)
+    want_t = (best[inv] & 0xFFFFFFFF).astype(np.uint32)
+    assert (want_t != idx).sum() > 1000                                              # the tie rule is really exercised
+    mf = api.MatchFactory(1.0, FLT_MAX)
+    u = _unity(api, f); u.setMemoryState(api.gpu)
+    got = mf.generateMatchesIndexOnly(api.Image(0), u, api.Image(1), u).to_numpy()
+    assert len(got) == n
+    assert np.array_equal(got["a"][:, 1], idx.astype(np.uint32)) and np.array_equal(got["b"][:, 1], want_t)
+    dm = mf.generateDistanceMatches(api.Image(0), u, api.Image(1), u).to_numpy()
+    assert len(dm) == n and not dm["distance"].any()
+    # sharded: 4 target shards (boundaries multiples of 32), merged candidate keys
+    ctx = mf.ctx
+    p = mf._params(T.OUT_PAIR, T.MASK_NONE, api.Image(0), api.Image(1))
+    bounds = [0, 262144 + 256, 524288, 786432 - 512, n]
+    keys = torch.empty((4, n), dtype=torch.int64, device="cuda")
+    hq = pack(ctx, u)
+    for r in range(4):
+        su = _unity(api, f[bounds[r]:bounds[r + 1]]); su.setMemoryState(api.gpu)
+        ctx.check(ctx.lib.ssrlcv_b200_match_candidates(ctx.handle, C.byref(p), hq.handle, pack(ctx, su).handle, bounds[r], C.c_void_p(keys[r].data_ptr())))
+    out = torch.empty(n * 16, dtype=torch.uint8, device="cuda")
+    cnt = C.c_uint64(0)
+    ctx.check(ctx.lib.ssrlcv_b200_finalize_candidates(ctx.handle, C.byref(p), hq.handle, C.c_void_p(keys.data_ptr()), 4, None, None,
+                                                      C.c_void_p(out.data_ptr()), C.byref(cnt)))
+    merged = out[: cnt.value * 16].cpu().numpy().view(T.UINT2_PAIR)
+    assert T.fields_equal(merged, got)
+
+
+def test_random_sweep_against_oracle(api, everest):
+    """seeded sweep over shapes (ragged, tiny, one-sided), thresholds, seeds, mask and output kinds: every case equals the oracle"""
+    rng = np.random.default_rng(7)
+    F = np.array([[0, 0, 0.001], [0, 0, -1.0], [-0.001, 1.0, 2.0]], np.float32)
+    qi, ti = api.Image(2, everest.cameras[0]), api.Image(5, everest.cameras[1])
+    n_empty = 0
+    for case in range(36):
+        nq = int(rng.choice([1, 31, 127, 128, 129, 257, 700, 1500, 4097]))
+        nt = int(rng.choice([1, 32, 255, 256, 257, 1000, 2047, 5000, 12000]))
+        thr = float(rng.choice([FLT_MAX, 2.0e5, 6.0e4, 3.0e4]))
+        rel = float(rng.choice([1.0, 0.9, 0.7]))
+        out_kind = int(rng.choice([T.OUT_MATCH, T.OUT_DMATCH, T.OUT_PAIR]))
+        mask_kind = int(rng.choice([T.MASK_NONE, T.MASK_NONE, T.MASK_FUNDAMENTAL, T.MASK_DOUBLE]))
+        seeded = bool(rng.integers(0, 2))
+        q, t = synth.make_pair(nq, nt, seed=1000 + case, uniform_bytes=bool(case % 7 == 3))
+        s = synth.make_seed(int(rng.choice([1, 200, 900])), seed=case)
+        mf = api.MatchFactory(rel, thr)
+        mf.setSeedFeatures(_unity(api, s))
+        qu, tu = _unity(api, q), _unity(api, t)
+        sd = mf.getSeedDistances(qu) if seeded else None
+        sd_want = api.O.seed_distances(q, s) if seeded else None
+        p = mf._params(out_kind, mask_kind, qi, ti, epsilon=30.0, delta=5.0, fundamental=F)
+        got = mf._run(p, qu, tu, sd).to_numpy()
+        po = api.O.make_params(out_kind=out_kind, mask_kind=mask_kind, has_seed=seeded, abs_threshold=thr, rel_threshold=rel, query_id=2, target_id=5,
+                               epsilon=30.0, delta=5.0, fundamental=F, query_camera=everest.cameras[0], target_camera=everest.cameras[1])
+        want = api.O.generate_matches(po, q, t, sd_want)
+        if len(want) == 0:      # reference quirk (src/MatchFactory.cu:40-45): nothing valid -> the caller keeps the uncompacted array
+            assert len(got) == nq, (case, nq, nt)
+            if out_kind == T.OUT_PAIR:
+                assert np.array_equal(got["a"], got["b"])            # uint2_pair marks "invalid" as a self pair
+            else:
+                assert np.all(got["invalid"] == 1)
+            n_empty += 1
+        else:
+            assert T.fields_equal(got, want), (case, nq, nt, thr, rel, out_kind, mask_kind, seeded)
+    assert n_empty < 18
