@@ -71,8 +71,18 @@ ssrlcv::ptr::value<ssrlcv::Unity<Out>> b200_generate(
   if (origin[1] != gpu) targetFeatures->setMemoryState(gpu);
 
   const unsigned long numPossibleMatches = queryFeatures->size();
-  ptr::device<Out> matches_device(numPossibleMatches);
-  ptr::value<Unity<Out>> matches = ptr::value<Unity<Out>>(matches_device, numPossibleMatches, gpu);
+  // The reference allocates numPossibleMatches records, compacts into a second allocation and frees the first
+  // (src/MatchFactory.cu:31-60, :355-357): two cudaMalloc and a cudaFree of megabyte blocks cost milliseconds, more than the
+  // whole match.  Here the records land in a grow-only scratch buffer first and the Unity the caller gets is allocated once,
+  // at its final size.
+  static void* scratch = nullptr;
+  static size_t scratch_bytes = 0;
+  if (scratch_bytes < numPossibleMatches * sizeof(Out)) {
+    if (scratch) CudaSafeCall(cudaFree(scratch));
+    scratch_bytes = numPossibleMatches * sizeof(Out) + (numPossibleMatches * sizeof(Out)) / 2 + 256;
+    CudaSafeCall(cudaMalloc(&scratch, scratch_bytes));
+  }
+  ptr::value<Unity<Out>> matches = nullptr;
 
   ssrlcv_b200_match_params p;
   memset(&p, 0, sizeof p);
@@ -109,8 +119,7 @@ ssrlcv::ptr::value<ssrlcv::Unity<Out>> b200_generate(
     const ssrlcv_b200_set* qs = queryPacked ? queryPacked->s : own_q->s;
     const ssrlcv_b200_set* ts = targetPacked ? targetPacked->s : own_t->s;
     uint64_t n_out = 0;
-    b200_check(ssrlcv_b200_match(b200_context(), &p, qs, ts, seed_dev, seed_dev ? numPossibleMatches : 0, matches->device.get(), &n_out),
-               "ssrlcv_b200_match");
+    b200_check(ssrlcv_b200_match(b200_context(), &p, qs, ts, seed_dev, seed_dev ? numPossibleMatches : 0, scratch, &n_out), "ssrlcv_b200_match");
     if (compact) {
       // validateMatches (ref: src/MatchFactory.cu:31-135), already fused into the call above
       if (n_out == 0) {
@@ -118,15 +127,14 @@ ssrlcv::ptr::value<ssrlcv::Unity<Out>> b200_generate(
         // reference quirk: validateMatches clears only its own copy of the smart pointer, so the caller keeps
         // the uncompacted array -> materialise it
         p.compact = 0;
-        b200_check(ssrlcv_b200_match(b200_context(), &p, qs, ts, seed_dev, seed_dev ? numPossibleMatches : 0, matches->device.get(), &n_out),
-                   "ssrlcv_b200_match");
+        b200_check(ssrlcv_b200_match(b200_context(), &p, qs, ts, seed_dev, seed_dev ? numPossibleMatches : 0, scratch, &n_out), "ssrlcv_b200_match");
       } else {
-        logger.info.printf("%d valid matches found out of %lu original matches", (int)n_out, matches->size());
-        ptr::device<Out> validatedMatches_device(n_out);
-        CudaSafeCall(cudaMemcpy(validatedMatches_device.get(), matches->device.get(), n_out * sizeof(Out), cudaMemcpyDeviceToDevice));
-        matches->setData(validatedMatches_device, n_out, gpu);
+        logger.info.printf("%d valid matches found out of %lu original matches", (int)n_out, numPossibleMatches);
       }
     }
+    ptr::device<Out> matches_device(n_out);
+    if (n_out) CudaSafeCall(cudaMemcpy(matches_device.get(), scratch, n_out * sizeof(Out), cudaMemcpyDeviceToDevice));
+    matches = ptr::value<Unity<Out>>(matches_device, n_out, gpu);
     delete own_q;
     delete own_t;
   }

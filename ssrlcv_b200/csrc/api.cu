@@ -474,6 +474,8 @@ struct PairWork {
   int engine = 0;
   uint64_t target_offset = 0;
   float abs_thr = 0.f;
+  const float* seed = nullptr;    // seed distances of the query set (device) when the ratio test will drop what exceeds it
+  float seed_ratio = 0.f;
   bool optimistic_fold = false;   // out: the fold variant was launched before the target set's pack had reported back
   SmaxArgs a;                     // out: a.keys, a.n_splits, a.nq_pad describe the pair's candidate keys
 };
@@ -503,6 +505,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     a.eps = p.mp.eps;
     a.t_meta = p.t->meta;
     a.d2_cap = d2_cap_of(p.abs_thr);
+    a.q_seed = p.seed; a.seed_ratio = p.seed_ratio;
     a.q_desc = p.q->desc; a.q_norm = p.q->norm; a.q_loc = p.q->loc;
     a.t_desc = p.t->desc; a.t_norm = p.t->norm; a.t_loc = p.t->loc; a.t_wcol = p.t->wcol; a.t_wmax = p.t->wmax;
     if (p.engine == SSRLCV_B200_ENGINE_SIMT || tiles == 0) {
@@ -527,7 +530,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
         }
       }
       // bookkeeping regime (smax_tc.cu): exact column masks for thresholded searches and short target sets
-      bool colmask = a.d2_cap != 0x7fffffff || a.n_ttiles < 64;
+      bool colmask = a.d2_cap != 0x7fffffff || a.q_seed != nullptr || a.n_ttiles < 64;
       if (const char* c = getenv("SSRLCV_B200_COLMASK")) colmask = c[0] != '0';   // A/B timing, tests
       Group& g = groups[p.mp.kind * 4 + (fold ? 2 : 0) + (colmask ? 1 : 0)];
       a.tile_begin = g.total;
@@ -758,6 +761,10 @@ int ssrlcv_b200_match_batch(ssrlcv_b200_ctx* ctx, uint32_t n_pairs, const ssrlcv
     for (uint32_t i = 0; i < n_pairs; ++i) {
       fill_mask(&params[i], w[i].mp);
       w[i].q = queries[i]; w[i].t = targets[i]; w[i].engine = params[i].engine; w[i].abs_thr = params[i].absolute_threshold;
+      // invalid entries are compacted away: candidates the seed-ratio test would reject need not be tracked (matcher.cuh)
+      const float* sd = seed_dist_dev ? seed_dist_dev[i] : nullptr;
+      w[i].seed = (sd && params[i].compact) ? sd : nullptr;
+      w[i].seed_ratio = ratio_threshold(params[i].out_kind, params[i].mask_kind, params[i].relative_threshold);
     }
     bool optimistic = false;
     rc = engine_enqueue(ctx, w.data(), n_pairs, &optimistic);
@@ -916,9 +923,11 @@ static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_par
   struct Up { bool is_q; uint64_t idx; };
   std::vector<Up> order;
   {
+    // With a seed set every query chunk goes first: the seed distances (needed to bound the candidates, matcher.cuh
+    // q_seed) exist once the last query has arrived, before the first (queries x target chunk) job is enqueued.
     uint64_t qi = 0, ti = 0;
     while (qi < n_qc || ti < n_tc) {
-      const bool take_q = ti >= n_tc || (qi < n_qc && qi * n_tc <= ti * n_qc);
+      const bool take_q = ti >= n_tc || (qi < n_qc && (seed_host != nullptr || qi * n_tc <= ti * n_qc));
       if (take_q) order.push_back(Up{true, qi++}); else order.push_back(Up{false, ti++});
     }
   }
@@ -970,6 +979,7 @@ static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_par
         if (!rc) rc = make_view(ctx, t, 0, t_arrived, t_arrived == t->n ? t->n_pad : t_arrived, &tv);
         if (rc) return cleanup(rc);
         w.target_offset = 0; q0 = r0; slot = n_tc; run = cnt != 0;
+        w.seed = nullptr;                                        // (a query chunk's seed distances do not exist yet)
       }
       q_arrived = r0 + cnt;
     } else {
@@ -980,6 +990,9 @@ static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_par
         if (!rc) rc = make_view(ctx, t, r0, cnt, pad, &tv);
         if (rc) return cleanup(rc);
         w.target_offset = r0; q0 = 0; slot = u.idx; run = cnt != 0;
+        // the whole query set has arrived and its seed distances are enqueued (see the upload order above)
+        w.seed = (s && p->compact && q_arrived == q->n) ? seed_dev : nullptr;
+        w.seed_ratio = ratio_threshold(p->out_kind, p->mask_kind, p->relative_threshold);
       }
       t_arrived = r0 + cnt;                                    // a multiple of t_rows until the last chunk
     }

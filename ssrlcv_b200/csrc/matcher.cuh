@@ -114,6 +114,12 @@ struct SmaxArgs {
   float    eps;                  // epipolar mask tolerance (masked modes)
   const int32_t* t_meta;         // device scalars of the target set (pack.cu): [0] == 0 <=> fold digits valid
   int32_t  d2_cap;               // largest integer d2 that still passes the absolute threshold; INT32_MAX = no threshold
+  // Seeded searches whose invalid entries are compacted away: the seed-ratio test (ref: src/MatchFactory.cu:1691-1697) applies to
+  // the WINNER, so a query whose best d2 exceeds ratio * seed[q] is dropped whatever else it found -- candidates beyond that
+  // bound need no bookkeeping.  On real SIFT data this, not the absolute threshold, is what makes windows rare
+  // (everest fixture: 84 % of the (query, window) pairs reach d2 < 200^2, 0.04 % reach 0.36 * seed[q]).
+  const float* q_seed;           // [nq] seed distances (exact integers as float, FLT_MAX = none) or nullptr
+  float    seed_ratio;           // rel or rel^2 as the output kind prescribes (api.cu ratio_threshold)
   uint64_t target_offset;        // global index of target 0 of this set (sharded mode)
   const uint8_t* q_desc; const int32_t* q_norm; const float2* q_loc;
   const float4* q_mask;          // [nq_pad][2] per-query epipolar mask state (geometry.cuh), masked modes only

@@ -549,7 +549,13 @@ smax_kernel(const SmaxBatch batch) {
       WinState st;
       {
         int32_t floor_s = 2;
-        const int32_t d2_cap = args.d2_cap;
+        int32_t d2_cap = args.d2_cap;
+        if (args.q_seed != nullptr && row < args.nq) {
+          // largest d2 whose ratio test (float)d2 / seed <= ratio can still pass, generously rounded up (finalize applies the
+          // reference's exact float test; this only has to keep every candidate that could pass it)
+          const float c = __fmul_rn(__fmul_rn(args.seed_ratio, args.q_seed[row]), 1.00001f);
+          if (c < 8.4e6f) d2_cap = min(d2_cap, static_cast<int32_t>(c) + 1);
+        }
         if (d2_cap != 0x7fffffff) {
           const int32_t qn = args.q_norm[row_c];
           floor_s = max(2, kWOffset + ((qn - d2_cap + 1) >> 1));
@@ -621,17 +627,28 @@ smax_kernel(const SmaxBatch batch) {
                 // tests target l of the window, the ballot comes back to the query's lane as a column mask.  Masked entries
                 // score 0, below every floor (as do the rows past the end of the target set: zero padding with W = 0).
                 uint32_t todo = __ballot_sync(0xffffffffu, wm[k] >= st.best);
-                uint32_t skip = 0;
-                const float2 tl = ld_shared_f2(smem_u32(s_loc + (c_begin + k) * kChunk + lane));
-                while (todo) {
-                  const int src = __ffs(todo) - 1;
-                  todo &= todo - 1;
-                  const QueryMask qs = shfl_query_mask<kMask>(qm, src);
-                  const uint32_t b = __ballot_sync(0xffffffffu, mask_skips<kMask>(qs, tl.x, tl.y, eps));
-                  skip = lane == src ? b : skip;
-                }
+                if (__popc(todo) <= 10) {
+                  uint32_t skip = 0;
+                  const float2 tl = ld_shared_f2(smem_u32(s_loc + (c_begin + k) * kChunk + lane));
+                  while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const QueryMask qs = shfl_query_mask<kMask>(qm, src);
+                    const uint32_t b = __ballot_sync(0xffffffffu, mask_skips<kMask>(qs, tl.x, tl.y, eps));
+                    skip = lane == src ? b : skip;
+                  }
 #pragma unroll
-                for (int e = 0; e < 32; ++e) x[e] = (skip >> e) & 1u ? 0u : x[e];
+                  for (int e = 0; e < 32; ++e) x[e] = (skip >> e) & 1u ? 0u : x[e];
+                } else {
+                  // many live queries (loose thresholds on real data): every lane tests the 32 targets of its own row
+                  const uint32_t lp = smem_u32(s_loc + (c_begin + k) * kChunk);
+#pragma unroll
+                  for (int e = 0; e < 32; e += 2) {
+                    const int4 l2 = ld_shared_v4(lp + 8 * e);
+                    if (mask_skips<kMask>(qm, __int_as_float(l2.x), __int_as_float(l2.y), eps)) x[e] = 0;
+                    if (mask_skips<kMask>(qm, __int_as_float(l2.z), __int_as_float(l2.w), eps)) x[e + 1] = 0;
+                  }
+                }
                 wm[k] = max32(x);
               }
             }
