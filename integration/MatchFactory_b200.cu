@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <chrono>
 #include <map>
 #include <set>
 
@@ -49,6 +50,14 @@ void b200_check(int rc, const char* what) {
   exit(-1);
 }
 
+// Read-only inputs: a Unity in state `both` whose device side is current needs no transition (the reference drops the host copy
+// and re-downloads it afterwards, src/MatchFactory.cu:350-353 / :390-391 -- two transfers of the whole array per call).
+template <typename U>
+inline bool b200_device_current(const U& u) {
+  const ssrlcv::MemoryState st = u->getMemoryState();
+  return st == ssrlcv::gpu || (st == ssrlcv::both && u->getFore() != ssrlcv::cpu);
+}
+
 struct PackedSet {   // RAII over ssrlcv_b200_set
   ssrlcv_b200_set* s = nullptr;
   PackedSet(void* features_dev, unsigned long n) { b200_check(ssrlcv_b200_pack(b200_context(), features_dev, n, &s), "ssrlcv_b200_pack"); }
@@ -67,8 +76,8 @@ ssrlcv::ptr::value<ssrlcv::Unity<Out>> b200_generate(
   using namespace ssrlcv;
   static_assert(sizeof(Feature<T>) == 152, "only Feature<SIFT_Descriptor> is supported");
   MemoryState origin[2] = {queryFeatures->getMemoryState(), targetFeatures->getMemoryState()};
-  if (origin[0] != gpu) queryFeatures->setMemoryState(gpu);
-  if (origin[1] != gpu) targetFeatures->setMemoryState(gpu);
+  if (!b200_device_current(queryFeatures)) queryFeatures->setMemoryState(gpu);
+  if (!b200_device_current(targetFeatures)) targetFeatures->setMemoryState(gpu);
 
   const unsigned long numPossibleMatches = queryFeatures->size();
   // The reference allocates numPossibleMatches records, compacts into a second allocation and frees the first
@@ -110,7 +119,7 @@ ssrlcv::ptr::value<ssrlcv::Unity<Out>> b200_generate(
       exit(-1);
     }
     seedOrigin = seedDistances->getMemoryState();
-    if (seedOrigin != gpu) seedDistances->setMemoryState(gpu);
+    if (!b200_device_current(seedDistances)) seedDistances->setMemoryState(gpu);
     seed_dev = seedDistances->device.get();
   }
   {
@@ -138,11 +147,11 @@ ssrlcv::ptr::value<ssrlcv::Unity<Out>> b200_generate(
     delete own_q;
     delete own_t;
   }
-  if (seedDistances != nullptr && seedOrigin != gpu) seedDistances->setMemoryState(seedOrigin);
+  if (seedDistances != nullptr && seedDistances->getMemoryState() != seedOrigin) seedDistances->setMemoryState(seedOrigin);
   logger.info.printf("done in %f seconds.", ((float)clock() - timer) / CLOCKS_PER_SEC);
 
-  if (origin[0] != gpu) queryFeatures->setMemoryState(origin[0]);
-  if (origin[1] != gpu) targetFeatures->setMemoryState(origin[1]);
+  if (queryFeatures->getMemoryState() != origin[0]) queryFeatures->setMemoryState(origin[0]);
+  if (targetFeatures->getMemoryState() != origin[1]) targetFeatures->setMemoryState(origin[1]);
   return matches;
 }
 
@@ -287,8 +296,8 @@ ssrlcv::ptr::value<ssrlcv::Unity<ssrlcv::Match>> ssrlcv::MatchFactory<T>::getRaw
 template <typename T>
 ssrlcv::ptr::value<ssrlcv::Unity<float>> ssrlcv::MatchFactory<T>::getSeedDistances(ssrlcv::ptr::value<Unity<Feature<T>>> features) {
   MemoryState origin = features->getMemoryState();
-  if (this->seedFeatures->getMemoryState() != gpu) this->seedFeatures->setMemoryState(gpu);
-  if (origin != gpu) features->setMemoryState(gpu);
+  if (!b200_device_current(this->seedFeatures)) this->seedFeatures->setMemoryState(gpu);
+  if (!b200_device_current(features)) features->setMemoryState(gpu);
   unsigned int numPossibleMatches = features->size();
   ssrlcv::ptr::value<ssrlcv::Unity<float>> matchDistances = ssrlcv::ptr::value<ssrlcv::Unity<float>>(nullptr, numPossibleMatches, gpu);
   clock_t timer = clock();
@@ -300,7 +309,7 @@ ssrlcv::ptr::value<ssrlcv::Unity<float>> ssrlcv::MatchFactory<T>::getSeedDistanc
     b200_check(ssrlcv_b200_synchronize(b200_context()), "ssrlcv_b200_synchronize");
   }
   logger.info.printf("seed match distances computed in %f seconds.", ((float)clock() - timer) / CLOCKS_PER_SEC);
-  if (origin != gpu) features->setMemoryState(origin);
+  if (features->getMemoryState() != origin) features->setMemoryState(origin);
   return matchDistances;
 }
 
@@ -365,18 +374,28 @@ ssrlcv::MatchSet ssrlcv::MatchFactory<T>::generateMatchesExhaustive(std::vector<
   matchSet.matches = nullptr;
   if (estimatedOverlap == 0) logger.warn << "WARNING: estimated overlap fraction of 0.0f requires unordered match interpolation";
   const size_t n = images.size();
+  const bool debugPhases = getenv("SSRLCV_B200_DEBUG_HOST") != nullptr;
+  auto phase0 = std::chrono::steady_clock::now();
+  auto phase = [&](const char* what) {
+    if (!debugPhases) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "generateMatchesExhaustive: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - phase0).count());
+    phase0 = now;
+  };
   std::vector<MemoryState> origin(n);
   std::vector<PackedSet*> packed(n, nullptr);
   for (size_t v = 0; v < n; ++v) {
     origin[v] = features[v]->getMemoryState();
-    if (origin[v] != gpu) features[v]->setMemoryState(gpu);
+    if (!b200_device_current(features[v])) features[v]->setMemoryState(gpu);
     packed[v] = new PackedSet(features[v]->device.get(), features[v]->size());
   }
-  std::vector<ssrlcv::ptr::value<ssrlcv::Unity<uint2_pair>>> matchIndices;
   unsigned long long totalMatches = 0;
+  phase("states + pack");
   logger.info << "matching images";
   // The pair scheduler: seed distances once per query view, then every pair of the reference's loop (same order,
   // same skip rule, ref: src/MatchFactory.cu:925-936) is handed to the library in ONE batch and synchronised once.
+  // The index pairs land in one grow-only device buffer (the reference cudaMallocs, compacts into a second allocation and
+  // frees per pair, :909-936 via :853-905) and only the valid ones travel to the host.
 #if GEO_ORBIT == 1
   const int mask = SSRLCV_B200_MASK_DOUBLE;
 #else
@@ -386,11 +405,24 @@ ssrlcv::MatchSet ssrlcv::MatchFactory<T>::generateMatchesExhaustive(std::vector<
   std::vector<ssrlcv_b200_match_params> params;
   std::vector<const ssrlcv_b200_set*> qsets, tsets;
   std::vector<const float*> seeds;
-  std::vector<void*> outs;
+  std::vector<size_t> outOffset;
   std::vector<std::pair<size_t, size_t>> pairOf;
+  size_t outRecords = 0;
   int i = 0;
+  PackedSet* seedPacked = nullptr;
+  if (this->seedFeatures != nullptr) {
+    if (!b200_device_current(this->seedFeatures)) this->seedFeatures->setMemoryState(gpu);
+    seedPacked = new PackedSet(this->seedFeatures->device.get(), this->seedFeatures->size());
+  }
   for (size_t q = 0; q + 1 < n; ++q) {
-    if (this->seedFeatures != nullptr) seedOfView[q] = this->getSeedDistances(features[q]);
+    if (seedPacked != nullptr) {
+      // getSeedDistances (ref: :915-917) on the sets that are packed already; stream-ordered before the batch below
+      clock_t timer = clock();
+      seedOfView[q] = ssrlcv::ptr::value<ssrlcv::Unity<float>>(nullptr, features[q]->size(), gpu);
+      b200_check(ssrlcv_b200_seed_distances(b200_context(), packed[q]->s, seedPacked->s, seedOfView[q]->device.get(), SSRLCV_B200_ENGINE_TCGEN05),
+                 "ssrlcv_b200_seed_distances");
+      logger.info.printf("seed match distances computed in %f seconds.", ((float)clock() - timer) / CLOCKS_PER_SEC);
+    }
     for (size_t t = q + 1; t < n; ++t) {
       if (ordered && estimatedOverlap > 0.0f && ++i * (1 - estimatedOverlap) > 1.0f) continue;
       ++i;
@@ -408,94 +440,138 @@ ssrlcv::MatchSet ssrlcv::MatchFactory<T>::generateMatchesExhaustive(std::vector<
       memcpy(p.target_camera, &images[t]->camera, 80);
       p.compact = 1;
       p.engine = SSRLCV_B200_ENGINE_TCGEN05;
-      ptr::device<uint2_pair> dev(features[q]->size());
-      matchIndices.push_back(ptr::value<Unity<uint2_pair>>(dev, features[q]->size(), gpu));
       params.push_back(p);
       qsets.push_back(packed[q]->s);
       tsets.push_back(packed[t]->s);
       seeds.push_back(seedOfView[q] != nullptr ? seedOfView[q]->device.get() : nullptr);
-      outs.push_back(matchIndices.back()->device.get());
+      outOffset.push_back(outRecords);
+      outRecords += features[q]->size();
       pairOf.push_back(std::make_pair(q, t));
     }
   }
+  static uint2_pair* pairScratch = nullptr;
+  static size_t pairScratchRecords = 0;
+  if (pairScratchRecords < outRecords) {
+    if (pairScratch) CudaSafeCall(cudaFree(pairScratch));
+    pairScratchRecords = outRecords + outRecords / 2 + 64;
+    CudaSafeCall(cudaMalloc(&pairScratch, pairScratchRecords * sizeof(uint2_pair)));
+  }
+  std::vector<void*> outs(params.size());
+  for (size_t k = 0; k < params.size(); ++k) outs[k] = pairScratch + outOffset[k];
   std::vector<uint64_t> counts(params.size(), 0);
   b200_check(ssrlcv_b200_match_batch(b200_context(), (uint32_t)params.size(), params.data(), qsets.data(), tsets.data(), seeds.data(),
                                      outs.data(), counts.data()),
              "ssrlcv_b200_match_batch");
+  phase("seed distances + batch");
+  std::vector<std::vector<uint2_pair>> matchIndices(params.size());
   for (size_t k = 0; k < params.size(); ++k) {
     if (counts[k] == 0) {
       // reference quirk (validateMatches, src/MatchFactory.cu:118-123): the caller keeps the uncompacted all-invalid array
-      matchIndices[k] = b200_generate<uint2_pair, T>(relativeThreshold, absoluteThreshold, SSRLCV_B200_OUT_PAIR, mask, true, images[pairOf[k].first],
-                                                     features[pairOf[k].first], images[pairOf[k].second], features[pairOf[k].second], epsilon, delta,
-                                                     nullptr, seedOfView[pairOf[k].first], packed[pairOf[k].first], packed[pairOf[k].second]);
+      ptr::value<Unity<uint2_pair>> all = b200_generate<uint2_pair, T>(relativeThreshold, absoluteThreshold, SSRLCV_B200_OUT_PAIR, mask, true,
+                                                                      images[pairOf[k].first], features[pairOf[k].first], images[pairOf[k].second],
+                                                                      features[pairOf[k].second], epsilon, delta, nullptr, seedOfView[pairOf[k].first],
+                                                                      packed[pairOf[k].first], packed[pairOf[k].second]);
+      all->setMemoryState(cpu);
+      matchIndices[k].assign(all->host.get(), all->host.get() + all->size());
     } else {
-      ptr::device<uint2_pair> validated(counts[k]);
-      CudaSafeCall(cudaMemcpy(validated.get(), matchIndices[k]->device.get(), counts[k] * sizeof(uint2_pair), cudaMemcpyDeviceToDevice));
-      matchIndices[k]->setData(validated, counts[k], gpu);
+      matchIndices[k].resize(counts[k]);
+      CudaSafeCall(cudaMemcpy(matchIndices[k].data(), outs[k], counts[k] * sizeof(uint2_pair), cudaMemcpyDeviceToHost));
     }
-    totalMatches += matchIndices[k]->size();
+    totalMatches += matchIndices[k].size();
   }
-  for (size_t v = 0; v < n; ++v) delete packed[v];
   if (totalMatches == 0) {
     logger.err << "There were no matches found in the set of images, likely due to unreasonable threshold";
     logger.err << "exiting...";
     exit(0);
   }
+  phase("records to host");
+  // Key-point locations: 8 bytes per feature from the packed sets instead of the whole 152-byte records the reference moves to
+  // the host (:966-967); the Unity arrays were forced to state gpu above, so none of them has a host copy right now.
+  std::vector<std::vector<float2>> locOf(n);
+  for (size_t v = 0; v < n; ++v) {
+    locOf[v].resize(features[v]->size());
+    if (!locOf[v].empty())
+      CudaSafeCall(cudaMemcpy(locOf[v].data(), ssrlcv_b200_set_loc(packed[v]->s), locOf[v].size() * sizeof(float2), cudaMemcpyDeviceToHost));
+  }
+  for (size_t v = 0; v < n; ++v) delete packed[v];
+  delete seedPacked;
+
+  // Match interpolation (ref: src/MatchFactory.cu:943-1020), same visiting order and the same side effects, on flat arrays:
+  // a feature of view v has at most one partner per later view, so its adjacency list is a fixed-stride slot of (n - 1 - v)
+  // nodes, filled in ascending partner view (the pair order) -- already sorted the way std::set_intersection needs it.
+  phase("locations to host");
   logger.info << "building adjacency list";
   typedef std::pair<unsigned int, unsigned int> Node;   // (view, feature); std::pair orders like uint2's operator<
-  std::vector<std::map<unsigned int, std::vector<Node>>> adjacency(n ? n - 1 : 0);
-  for (auto& m : matchIndices) {
-    if (m->getMemoryState() != cpu) m->setMemoryState(cpu);
-    const uint2_pair* h = m->host.get();
-    for (unsigned long p = 0; p < m->size(); ++p) adjacency[h[p].a.x][h[p].a.y].push_back(Node(h[p].b.x, h[p].b.y));
-  }
-  logger.info << "deriving matches from adjacency";
-  std::vector<std::vector<Node>> multiMatch_vec;
+  std::vector<std::vector<Node>> adjNodes(n ? n - 1 : 0);
+  std::vector<std::vector<unsigned short>> adjCount(n ? n - 1 : 0);
+  std::vector<size_t> stride(n ? n - 1 : 0);
   for (size_t v = 0; v + 1 < n; ++v) {
-    if (features[v]->getMemoryState() != cpu && features[v]->getMemoryState() != both) features[v]->setMemoryState(both);
-    for (unsigned long f = 0; v + 2 < n && f < features[v]->size(); ++f) {
-      auto it = adjacency[v].find((unsigned int)f);
-      if (it == adjacency[v].end() || it->second.empty()) continue;
-      std::vector<Node>* adj = &it->second;
-      bool badMatch = false;
-      std::vector<Node>* prev_adj = adj;
-      while (true) {
-        if (prev_adj->begin()->first == n - 1) break;
-        std::vector<Node>* next_adj = &adjacency[prev_adj->begin()->first][prev_adj->begin()->second];
-        if (next_adj->empty()) break;
-        std::vector<Node> intersection;
-        std::set_intersection(prev_adj->begin(), prev_adj->end(), next_adj->begin(), next_adj->end(), std::back_inserter(intersection));
-        if (intersection.size() != next_adj->size()) { badMatch = true; break; }
-        else if (next_adj->size() == 1) break;
-        else prev_adj = next_adj;
+    stride[v] = n - 1 - v;
+    adjNodes[v].resize(features[v]->size() * stride[v]);
+    adjCount[v].assign(features[v]->size(), 0);
+  }
+  for (auto& m : matchIndices)
+    for (const uint2_pair& pr : m) {
+      const size_t v = pr.a.x, f = pr.a.y;
+      if (v + 1 >= n || f >= adjCount[v].size() || adjCount[v][f] >= stride[v]) {
+        logger.err << "ERROR: image ids must be 0..n-1 in view order for match interpolation";
+        exit(-1);
       }
-      if (badMatch) { adj->clear(); continue; }
-      std::vector<Node> match;
-      match.push_back(Node((unsigned int)v, (unsigned int)f));
-      match.insert(match.end(), adj->begin(), adj->end());
-      multiMatch_vec.push_back(match);
-      for (auto m = adj->begin(); m != adj->end() - 1; ++m) {
-        if (m->first == n - 1) break;
-        adjacency[m->first][m->second].clear();
+      adjNodes[v][f * stride[v] + adjCount[v][f]++] = Node(pr.b.x, pr.b.y);
+    }
+  logger.info << "deriving matches from adjacency";
+  std::vector<Node> flatMatches;            // all multi-matches back to back
+  std::vector<MultiMatch> mm_vec;
+  for (size_t v = 0; v + 2 < n; ++v) {
+    const unsigned long nf = features[v]->size();
+    for (unsigned long f = 0; f < nf; ++f) {
+      const unsigned short cnt = adjCount[v][f];
+      if (!cnt) continue;
+      const Node* adj = &adjNodes[v][f * stride[v]];
+      bool badMatch = false;
+      const Node* prev = adj;
+      unsigned short prevCnt = cnt;
+      while (true) {
+        if (prev[0].first == n - 1) break;
+        const size_t nv = prev[0].first, nfeat = prev[0].second;
+        const unsigned short nextCnt = adjCount[nv][nfeat];
+        if (!nextCnt) break;
+        const Node* next = &adjNodes[nv][nfeat * stride[nv]];
+        unsigned short a = 0, b = 0, common = 0;      // |prev ∩ next| by merge (both ascending)
+        while (a < prevCnt && b < nextCnt) {
+          if (prev[a] < next[b]) ++a;
+          else if (next[b] < prev[a]) ++b;
+          else { ++common; ++a; ++b; }
+        }
+        if (common != nextCnt) { badMatch = true; break; }
+        else if (nextCnt == 1) break;
+        prev = next; prevCnt = nextCnt;
+      }
+      if (badMatch) { adjCount[v][f] = 0; continue; }
+      mm_vec.push_back({(unsigned int)(cnt + 1), (int)flatMatches.size()});
+      flatMatches.push_back(Node((unsigned int)v, (unsigned int)f));
+      flatMatches.insert(flatMatches.end(), adj, adj + cnt);
+      for (unsigned short m = 0; m + 1 < cnt; ++m) {
+        if (adj[m].first == n - 1) break;
+        adjCount[adj[m].first][adj[m].second] = 0;
       }
     }
   }
-  logger.info.printf("total matches found in set = %d", (int)multiMatch_vec.size());
-  for (size_t v = 0; v < n; ++v)
-    if (features[v]->getMemoryState() == gpu) features[v]->setMemoryState(both);
-  matchSet.matches = ssrlcv::ptr::value<ssrlcv::Unity<MultiMatch>>(nullptr, multiMatch_vec.size(), cpu);
-  std::vector<KeyPoint> kp_vec;
-  int index = 0;
-  MultiMatch* mhost = matchSet.matches->host.get();
-  size_t mi = 0;
-  for (auto& m : multiMatch_vec) {
-    mhost[mi++] = {(unsigned int)m.size(), index};
-    index += (int)m.size();
-    for (auto& kp : m) kp_vec.push_back({(int)kp.first, features[kp.first]->host.get()[kp.second].loc});
+  phase("match interpolation");
+  logger.info.printf("total matches found in set = %d", (int)mm_vec.size());
+  matchSet.matches = ssrlcv::ptr::value<ssrlcv::Unity<MultiMatch>>(nullptr, mm_vec.size(), cpu);
+  if (!mm_vec.empty()) memcpy((void*)matchSet.matches->host.get(), mm_vec.data(), mm_vec.size() * sizeof(MultiMatch));
+  std::vector<KeyPoint> kp_vec(flatMatches.size());
+  for (size_t k = 0; k < flatMatches.size(); ++k) {
+    const Node& nd = flatMatches[k];
+    const float2 loc = locOf[nd.first][nd.second];
+    kp_vec[k] = {(int)nd.first, loc};
   }
   matchSet.keyPoints = ssrlcv::ptr::value<ssrlcv::Unity<KeyPoint>>(nullptr, kp_vec.size(), gpu);
   CudaSafeCall(cudaMemcpy(matchSet.keyPoints->device.get(), &kp_vec[0], kp_vec.size() * sizeof(KeyPoint), cudaMemcpyHostToDevice));
+  phase("MatchSet");
   for (size_t v = 0; v < n; ++v)
     if (features[v]->getMemoryState() != origin[v]) features[v]->setMemoryState(origin[v]);
+  phase("restore states");
   return matchSet;
 }

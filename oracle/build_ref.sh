@@ -37,7 +37,8 @@ fi
 # the drop-in: our integration/MatchFactory_b200.cu compiled against the reference's headers, in place of src/MatchFactory.cu
 ROOT="$(cd "$HERE/.." && pwd)"
 if [ ! -f "$OUT/obj/MatchFactory_b200.o" ] || [ "$ROOT/integration/MatchFactory_b200.cu" -nt "$OUT/obj/MatchFactory_b200.o" ] || [ "$ROOT/include/ssrlcv_b200.h" -nt "$OUT/obj/MatchFactory_b200.o" ]; then
-  nvcc $NVFLAGS -I"$ROOT/include" -dc "$ROOT/integration/MatchFactory_b200.cu" -o "$OUT/obj/MatchFactory_b200.o" &
+  # (the reference's Makefile compiles host code without -O, :21-27; the drop-in's own translation unit asks for -O2, as INTEGRATION.md says)
+  nvcc $NVFLAGS -Xcompiler -O2 -I"$ROOT/include" -dc "$ROOT/integration/MatchFactory_b200.cu" -o "$OUT/obj/MatchFactory_b200.o" &
   pids+=($!)
 fi
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
