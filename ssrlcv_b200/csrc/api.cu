@@ -894,15 +894,28 @@ static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_par
   CU(cudaSetDevice(ctx->device));
   const auto host_t0 = std::chrono::steady_clock::now();
   if (!ctx->copy_stream) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  // Every exit after this point goes through cleanup(): on failure both streams are drained first, because copies from the
+  // CALLER's host buffers may still be in flight and the caller is free to release them once we return.
+  ssrlcv_b200_set *q = nullptr, *t = nullptr, *s = nullptr;
+  auto cleanup = [&](int code) {
+    if (code != 0) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); }
+    ssrlcv_b200_set_free(q); ssrlcv_b200_set_free(t); ssrlcv_b200_set_free(s);
+    return code;
+  };
+#define CUS(call)                                                                                                   \
+  do {                                                                                                              \
+    cudaError_t e_ = (call);                                                                                        \
+    if (e_ != cudaSuccess) return cleanup(fail(ctx, static_cast<int>(e_), "%s: %s", #call, cudaGetErrorString(e_))); \
+  } while (0)
   const uint64_t n_qc = (nq + q_rows - 1) / q_rows, n_tc = (nt + t_rows - 1) / t_rows;
   while (ctx->copy_events.size() < n_qc + n_tc + 2) {
     cudaEvent_t e;
-    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUS(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ctx->copy_events.push_back(e);
   }
   const size_t rec = sizeof(RefFeature), elt = out_elt(p->out_kind);
   int rc = ws_reserve(ctx, ctx->upload, (nq + nt + ns) * rec + 16);
-  if (rc) return rc;
+  if (rc) return cleanup(rc);
   uint8_t* up_q = static_cast<uint8_t*>(ctx->upload.p);
   uint8_t* up_t = up_q + nq * rec;
   uint8_t* up_s = up_t + nt * rec;
@@ -910,15 +923,15 @@ static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_par
   const size_t out_bytes = ((nq * elt + 255) / 256) * 256, seed_bytes = ((nq * sizeof(float) + 255) / 256) * 256;
   const size_t n_slots = n_tc + 1;
   rc = ws_reserve(ctx, ctx->scratch, out_bytes + seed_bytes + n_slots * nq * sizeof(uint64_t) + 256);
-  if (rc) return rc;
+  if (rc) return cleanup(rc);
   void* out_dev = ctx->scratch.p;
   float* seed_dev = reinterpret_cast<float*>(static_cast<uint8_t*>(ctx->scratch.p) + out_bytes);
   uint64_t* ckeys = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(ctx->scratch.p) + out_bytes + seed_bytes);
 
   // ---- the copy stream starts after everything already enqueued on the main stream (earlier readers of the upload buffer)
   cudaEvent_t ev_fence = ctx->copy_events[n_qc + n_tc + 1], ev_seed = ctx->copy_events[n_qc + n_tc];
-  CU(cudaEventRecord(ev_fence, ctx->stream));
-  CU(cudaStreamWaitEvent(ctx->copy_stream, ev_fence, 0));
+  CUS(cudaEventRecord(ev_fence, ctx->stream));
+  CUS(cudaStreamWaitEvent(ctx->copy_stream, ev_fence, 0));
   // upload order: seed set, then query / target chunks interleaved in proportion (query chunk first)
   struct Up { bool is_q; uint64_t idx; };
   std::vector<Up> order;
@@ -931,25 +944,23 @@ static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_par
       if (take_q) order.push_back(Up{true, qi++}); else order.push_back(Up{false, ti++});
     }
   }
-  if (seed_host && ns) CU(cudaMemcpyAsync(up_s, seed_host, ns * rec, cudaMemcpyHostToDevice, ctx->copy_stream));
-  if (seed_host) CU(cudaEventRecord(ev_seed, ctx->copy_stream));
+  if (seed_host && ns) CUS(cudaMemcpyAsync(up_s, seed_host, ns * rec, cudaMemcpyHostToDevice, ctx->copy_stream));
+  if (seed_host) CUS(cudaEventRecord(ev_seed, ctx->copy_stream));
   for (size_t k = 0; k < order.size(); ++k) {
     const Up& u = order[k];
     const uint64_t rows = u.is_q ? q_rows : t_rows, n = u.is_q ? nq : nt, r0 = u.idx * rows;
     const uint64_t cnt = n - r0 < rows ? n - r0 : rows;
     const uint8_t* src = static_cast<const uint8_t*>(u.is_q ? query_host : target_host) + r0 * rec;
-    CU(cudaMemcpyAsync((u.is_q ? up_q : up_t) + r0 * rec, src, cnt * rec, cudaMemcpyHostToDevice, ctx->copy_stream));
-    CU(cudaEventRecord(ctx->copy_events[k], ctx->copy_stream));
+    CUS(cudaMemcpyAsync((u.is_q ? up_q : up_t) + r0 * rec, src, cnt * rec, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUS(cudaEventRecord(ctx->copy_events[k], ctx->copy_stream));
   }
 
   // ---- main stream: pack and match as the chunks arrive
-  ssrlcv_b200_set *q = nullptr, *t = nullptr, *s = nullptr;
-  auto cleanup = [&](int code) { ssrlcv_b200_set_free(q); ssrlcv_b200_set_free(t); ssrlcv_b200_set_free(s); return code; };
   rc = set_alloc(ctx, nq, &q);
   if (!rc) rc = set_alloc(ctx, nt, &t);
   if (rc) return cleanup(rc);
   if (seed_host) {
-    CU(cudaStreamWaitEvent(ctx->stream, ev_seed, 0));
+    CUS(cudaStreamWaitEvent(ctx->stream, ev_seed, 0));
     rc = ssrlcv_b200_pack(ctx, up_s, ns, &s);
     if (rc) return cleanup(rc);
   }
@@ -966,7 +977,7 @@ static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_par
     const uint64_t rows = u.is_q ? q_rows : t_rows, r0 = u.idx * rows;
     const bool last = r0 + rows >= set->n;
     const uint64_t cnt = last ? set->n - r0 : rows, pad = last ? set->n_pad - r0 : rows;
-    CU(cudaStreamWaitEvent(ctx->stream, ctx->copy_events[k], 0));
+    CUS(cudaStreamWaitEvent(ctx->stream, ctx->copy_events[k], 0));
     launch_pack(ctx->stream, (u.is_q ? up_q : up_t) + r0 * rec, cnt, pad, r0, *set, set->meta, ctx->sm_count);
     ctx->launches += 1;
     ssrlcv_b200_set qv, tv;
@@ -1014,9 +1025,9 @@ static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_par
   const uint32_t* total = nullptr;
   rc = finalize_enqueue(ctx, &fw, 1, &total);
   if (rc) return cleanup(rc);
-  CU(cudaMemcpyAsync(ctx->h_scalars + 2, total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CUS(cudaMemcpyAsync(ctx->h_scalars + 2, total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   const auto host_t1 = std::chrono::steady_clock::now();
-  CU(cudaStreamSynchronize(ctx->stream));
+  CUS(cudaStreamSynchronize(ctx->stream));
   if (getenv("SSRLCV_B200_DEBUG_HOST"))
     fprintf(stderr, "match_host_streamed: %zu uploads, host enqueue %.1f us, wait %.1f us\n", order.size(),
             std::chrono::duration<double, std::micro>(host_t1 - host_t0).count(),
@@ -1037,6 +1048,7 @@ static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_par
   }
   return cleanup(0);
 }
+#undef CUS
 
 int ssrlcv_b200_match_host(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const void* query_host, uint64_t n_query,
                            const void* target_host, uint64_t n_target, const void* seed_host, uint64_t n_seed, void* out_host,
@@ -1074,6 +1086,7 @@ int ssrlcv_b200_match_host(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params*
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) rc = fail(ctx, static_cast<int>(e), "match_host: D2H: %s", cudaGetErrorString(e));
   }
+  if (rc) cudaStreamSynchronize(ctx->stream);              // copies from the caller's host buffers may still be in flight
   ssrlcv_b200_set_free(q); ssrlcv_b200_set_free(t); ssrlcv_b200_set_free(s);
   return rc;
 }
