@@ -142,3 +142,29 @@ def test_shard_bounds_are_lane_aligned():
         assert all(b[i] <= b[i + 1] for i in range(w))
         # every non-empty shard starts on a lane boundary (f % 32 must be shard-invariant)
         assert all(b[i] % 32 == 0 for i in range(w) if b[i + 1] > b[i])
+
+
+def test_assign_pairs_is_balanced_and_keeps_views_local():
+    """pair_scheduler.assign_pairs: every pair exactly once, loads balanced by cost, and a rank touches few views
+    (a rank uploads and packs every view it touches: 16 equal views over 8 ranks must not need all 16 per rank)."""
+    from ssrlcv_b200.pair_scheduler import assign_pairs, pair_order
+    pairs = pair_order(16)
+    for world in (1, 2, 3, 4, 8):
+        a = assign_pairs(pairs, [32768] * 16, world)
+        assert sorted(k for r in a for k in r) == list(range(len(pairs)))
+        sizes = [len(r) for r in a]
+        assert max(sizes) - min(sizes) <= 1
+        assert a == assign_pairs(pairs, [32768] * 16, world)            # deterministic
+    views8 = [len({v for k in r for v in pairs[k]}) for r in assign_pairs(pairs, [32768] * 16, 8)]
+    assert max(views8) <= 10, views8
+    # unequal sizes: longest-processing-time balance within a few percent
+    rng = np.random.default_rng(3)
+    sizes = [int(x) for x in rng.integers(2000, 60000, 11)]
+    pairs = pair_order(11)
+    a = assign_pairs(pairs, sizes, 4)
+    load = [sum(sizes[pairs[k][0]] * sizes[pairs[k][1]] for k in r) for r in a]
+    assert max(load) / min(load) < 1.10, load
+    # the reference's skip rule for ordered image sets survives the assignment (pairs are indices into pair_order)
+    skipped = pair_order(6, ordered=True, estimatedOverlap=0.5)
+    a = assign_pairs(skipped, [1000] * 6, 2)
+    assert sorted(k for r in a for k in r) == list(range(len(skipped)))
