@@ -18,6 +18,9 @@
 namespace b200 {
 // pack.cu
 void launch_pack(cudaStream_t, const void*, uint64_t n, uint64_t n_rows, uint64_t row0, ssrlcv_b200_set_impl&, int32_t* meta_dev, int sm_count);
+size_t sort_x_temp_bytes(uint32_t n);
+cudaError_t launch_sort_gather(cudaStream_t, const ssrlcv_b200_set_impl& src, ssrlcv_b200_set_impl& dst, uint32_t* keys_in, uint32_t* keys_out,
+                               uint32_t* vals_in, uint32_t* vals_out, void* temp, size_t temp_bytes);
 // smax_tc.cu
 cudaError_t launch_smax(cudaStream_t, const SmaxBatch&, int mask_kind, bool fold, bool colmask);
 // exact.cu
@@ -60,7 +63,7 @@ struct ssrlcv_b200_ctx {
   EncodeTiledFn encode = nullptr;
   std::string err;
   uint64_t launches = 0;
-  Workspace keys, flagged, counts, scratch, hostpin, qmask, totals, nflag;
+  Workspace keys, flagged, counts, scratch, hostpin, qmask, totals, nflag, sortws;
   uint32_t* d_scalars = nullptr;   // [1] total of a single match
   // job descriptors (SmaxJob / FinalizeArgs arrays) travel host -> device through a small ring of pinned buffers
   struct Staged { void* h = nullptr; void* d = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; bool pending = false; };
@@ -169,7 +172,7 @@ void ssrlcv_b200_destroy(ssrlcv_b200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (Workspace* w : {&ctx->keys, &ctx->flagged, &ctx->counts, &ctx->scratch, &ctx->qmask, &ctx->totals, &ctx->nflag}) if (w->p) cudaFree(w->p);
+  for (Workspace* w : {&ctx->keys, &ctx->flagged, &ctx->counts, &ctx->scratch, &ctx->qmask, &ctx->totals, &ctx->nflag, &ctx->sortws}) if (w->p) cudaFree(w->p);
   for (auto& st : ctx->staged) {
     if (st.h) cudaFreeHost(st.h);
     if (st.d) cudaFree(st.d);
@@ -230,7 +233,7 @@ static int encode_map(ssrlcv_b200_ctx* ctx, CUtensorMap* m, void* base, uint64_t
 }
 
 // Allocates a set of n rows (one allocation, tensor maps, pinned slot for the meta scalars, meta zeroed); nothing is packed yet.
-static int set_alloc(ssrlcv_b200_ctx* ctx, uint64_t n, ssrlcv_b200_set** out) {
+static int set_alloc(ssrlcv_b200_ctx* ctx, uint64_t n, ssrlcv_b200_set** out, bool with_orig = false) {
   ssrlcv_b200_set* s = new (std::nothrow) ssrlcv_b200_set();
   if (!s) return SSRLCV_B200_ENOMEM;
   memset(static_cast<ssrlcv_b200_set_impl*>(s), 0, sizeof(ssrlcv_b200_set_impl));
@@ -241,12 +244,12 @@ static int set_alloc(ssrlcv_b200_ctx* ctx, uint64_t n, ssrlcv_b200_set** out) {
   ssrlcv_b200_ctx::PackSlot slot;
   int rc = slot_acquire(ctx, slot);
   if (rc) { delete s; return fail(ctx, rc, "pack: pinned slot: %s", cudaGetErrorString(static_cast<cudaError_t>(rc))); }
-  s->h_mm = slot.mm; s->ready = slot.ready; s->resolved = false;
+  s->h_mm = slot.mm; s->ready = slot.ready; s->resolved = false; s->is_view = false; s->sorted = nullptr;
   // one allocation: desc | ext | norm | wcol | loc | sigtheta | wmax | meta   (all segments 32-byte aligned since n_pad % 256 == 0);
   // the pack kernels write every row including the zero padding, so nothing is memset except wmax (4 bytes per 32 rows,
   // accumulated with atomicMax) and the 16 bytes of meta
   const size_t np = s->n_pad;
-  const size_t bytes = np * (kDescBytes + kExtBytes + 4 + 4 + 8 + 8) + (np / kChunk) * 4 + 256;
+  const size_t bytes = np * (kDescBytes + kExtBytes + 4 + 4 + 8 + 8 + (with_orig ? 4 : 0)) + (np / kChunk) * 4 + 256;
   uint8_t* base = nullptr;
   cudaError_t e = cudaMallocAsync(&base, bytes, ctx->stream);
   if (e != cudaSuccess) {
@@ -261,6 +264,7 @@ static int set_alloc(ssrlcv_b200_ctx* ctx, uint64_t n, ssrlcv_b200_set** out) {
   s->sigtheta = s->loc + np;
   s->wmax = reinterpret_cast<int32_t*>(s->sigtheta + np);
   s->meta = s->wmax + np / kChunk;
+  s->orig = with_orig ? reinterpret_cast<uint32_t*>(s->meta + 64) : nullptr;   // meta: 16 B used, 256 B reserved
   cudaMemsetAsync(s->wmax, 0, (np / kChunk) * 4 + 16, ctx->stream);
   rc = encode_map(ctx, &s->map_a, s->desc, np, kDescBytes, kBM, CU_TENSOR_MAP_SWIZZLE_128B);
   if (!rc) rc = encode_map(ctx, &s->map_b, s->desc, np, kDescBytes, kBN, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -326,6 +330,7 @@ const float* ssrlcv_b200_set_loc(const ssrlcv_b200_set* s) { return s ? reinterp
 void ssrlcv_b200_set_free(ssrlcv_b200_set* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
+  if (s->sorted) { ssrlcv_b200_set_free(s->sorted); s->sorted = nullptr; }
   if (s->desc) cudaFreeAsync(s->desc, s->ctx->stream);   // stream-ordered: every kernel that reads the set was enqueued before this
   if (s->ready) {
     // the slot's D2H was enqueued before this point; a later pack that reuses it is ordered after it on the same stream
@@ -466,6 +471,32 @@ static int32_t d2_cap_of(float abs_thr) {
   return static_cast<int32_t>(c) - 1;
 }
 
+// The x-sorted copy of a packed set (cached on the set, built on first use; enqueue-only).  Rows are ordered by loc.x, padding
+// and NaN locations last; `orig` maps a row back to the caller's index.  Used as the target side of DoubleConstrained
+// searches that have no seed distances to bound their candidates (matcher.cuh t_orig).
+static int sorted_of(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* ct, const ssrlcv_b200_set** out) {
+  ssrlcv_b200_set* t = const_cast<ssrlcv_b200_set*>(ct);
+  if (t->sorted) { *out = t->sorted; return 0; }
+  ssrlcv_b200_set* s2 = nullptr;
+  int rc = set_alloc(ctx, t->n, &s2, true);
+  if (rc) return rc;
+  const size_t n4 = ((static_cast<size_t>(t->n) * 4 + 255) / 256) * 256;
+  const size_t temp = sort_x_temp_bytes(static_cast<uint32_t>(t->n));
+  rc = ws_reserve(ctx, ctx->sortws, 4 * n4 + temp + 256);
+  if (rc) { ssrlcv_b200_set_free(s2); return rc; }
+  uint8_t* w = static_cast<uint8_t*>(ctx->sortws.p);
+  cudaError_t e = launch_sort_gather(ctx->stream, *t, *s2, reinterpret_cast<uint32_t*>(w), reinterpret_cast<uint32_t*>(w + n4),
+                                     reinterpret_cast<uint32_t*>(w + 2 * n4), reinterpret_cast<uint32_t*>(w + 3 * n4), w + 4 * n4, temp);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s2->meta, t->meta, 16, cudaMemcpyDeviceToDevice, ctx->stream);   // same rows, same fold verdict
+  if (e != cudaSuccess) { ssrlcv_b200_set_free(s2); return fail(ctx, static_cast<int>(e), "sorted copy: %s", cudaGetErrorString(e)); }
+  ctx->launches += 3;
+  rc = set_finish(ctx, s2);
+  if (rc) { ssrlcv_b200_set_free(s2); return rc; }
+  t->sorted = s2;
+  *out = s2;
+  return 0;
+}
+
 // One pair of a batch: inputs, and (after engine_enqueue) where its keys are.
 struct PairWork {
   const ssrlcv_b200_set* q = nullptr;
@@ -477,6 +508,7 @@ struct PairWork {
   const float* seed = nullptr;    // seed distances of the query set (device) when the ratio test will drop what exceeds it
   float seed_ratio = 0.f;
   bool optimistic_fold = false;   // out: the fold variant was launched before the target set's pack had reported back
+  const ssrlcv_b200_set* tt = nullptr;   // out: the set the kernel reads its targets from (t, or t's x-sorted copy)
   SmaxArgs a;                     // out: a.keys, a.n_splits, a.nq_pad describe the pair's candidate keys
 };
 
@@ -503,11 +535,22 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       return fail(ctx, SSRLCV_B200_EINVAL, "%u x %u features is too large for one call: shard the target set (ssrlcv_b200_match_candidates)", a.nq, a.nt);
     a.target_offset = p.target_offset;
     a.eps = p.mp.eps;
-    a.t_meta = p.t->meta;
     a.d2_cap = d2_cap_of(p.abs_thr);
     a.q_seed = p.seed; a.seed_ratio = p.seed_ratio;
+    p.tt = p.t;
+    if (p.engine != SSRLCV_B200_ENGINE_SIMT && tiles != 0 && p.mp.kind == SSRLCV_B200_MASK_DOUBLE && p.seed == nullptr && !p.t->is_view) {
+      // worth its three launches (~40 us, once per target set) only for pairs whose matcher runs much longer than that
+      bool use_sorted = a.nt >= 16384 && static_cast<uint64_t>(a.nq) * a.nt >= (1ull << 28);
+      if (const char* so = getenv("SSRLCV_B200_SORTED")) use_sorted = so[0] != '0';     // "0" never / "1" always (A/B timing, tests)
+      if (use_sorted) {
+        int rc = sorted_of(ctx, p.t, &p.tt);
+        if (rc) return rc;
+      }
+    }
+    a.t_meta = p.tt->meta;
+    a.t_orig = p.tt->orig;
     a.q_desc = p.q->desc; a.q_norm = p.q->norm; a.q_loc = p.q->loc;
-    a.t_desc = p.t->desc; a.t_norm = p.t->norm; a.t_loc = p.t->loc; a.t_wcol = p.t->wcol; a.t_wmax = p.t->wmax;
+    a.t_desc = p.tt->desc; a.t_norm = p.tt->norm; a.t_loc = p.tt->loc; a.t_wcol = p.tt->wcol; a.t_wmax = p.tt->wmax;
     if (p.engine == SSRLCV_B200_ENGINE_SIMT || tiles == 0) {
       plan_simt(ctx, a);
     } else {
@@ -594,7 +637,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
         h_nflag[at] = 0;
         w[i].a.n_flagged = d_nflag + at;
         SmaxJob& j = hj[at++];
-        j.map_q = w[i].q->map_a; j.map_t = w[i].t->map_b; j.map_text = w[i].t->map_ext;
+        j.map_q = w[i].q->map_a; j.map_t = w[i].tt->map_b; j.map_text = w[i].tt->map_ext;
         j.a = w[i].a;
       }
     rc = stage_upload(ctx, st, blob);
@@ -853,6 +896,7 @@ static int make_view(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* parent, uint64
   v->desc += row0 * kDescBytes; v->ext += row0 * kExtBytes;
   v->norm += row0; v->wcol += row0; v->loc += row0; v->sigtheta += row0; v->wmax += row0 / kChunk;
   v->resolved = false;                                   // the parent's packs may still be in flight: optimistic fold launch
+  v->is_view = true; v->sorted = nullptr;
   int rc = encode_map(ctx, &v->map_a, v->desc, rows_pad, kDescBytes, kBM, CU_TENSOR_MAP_SWIZZLE_128B);
   if (!rc) rc = encode_map(ctx, &v->map_b, v->desc, rows_pad, kDescBytes, kBN, CU_TENSOR_MAP_SWIZZLE_128B);
   if (!rc) rc = encode_map(ctx, &v->map_ext, v->ext, rows_pad, kExtBytes, kBN, CU_TENSOR_MAP_SWIZZLE_32B);

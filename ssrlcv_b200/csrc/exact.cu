@@ -68,7 +68,7 @@ __device__ __forceinline__ void exact_items(const SmaxArgs& a, int use_list, uin
         dot = __dp4a(q[i].z, t.z, dot); dot = __dp4a(q[i].w, t.w, dot);
       }
       const uint32_t d2 = static_cast<uint32_t>(qn + a.t_norm[f] - 2 * static_cast<int32_t>(dot));
-      const uint64_t key = make_key(d2, f + a.target_offset);
+      const uint64_t key = make_key(d2, (a.t_orig ? static_cast<uint64_t>(a.t_orig[f]) : f) + a.target_offset);   // x-sorted rows: the caller's index
       best = key < best ? key : best;
     }
     best = warp_min_u64(best);

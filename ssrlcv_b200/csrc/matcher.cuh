@@ -88,6 +88,7 @@ struct ssrlcv_b200_set_impl {
   float2*  loc;       // [n_pad]
   float2*  sigtheta;  // [n_pad]
   int32_t* wmax;      // [n_pad / 32]  largest wcol of each 32-row window, 0 for windows of padding only
+  uint32_t* orig;     // [n_pad]       x-sorted copies of a set only (api.cu sorted_of): row -> index in the original set
   int32_t* meta;      // [4] device scalars written by the pack kernel: [0] != 0 <=> some W does not fit the fold digits
   bool     fold_ok;      // every W fits the digit range -> fused extra-K-block path (host copy, valid after set_resolve)
   CUtensorMap map_a;     // desc, box 128 x kBM rows, SWIZZLE_128B
@@ -125,6 +126,10 @@ struct SmaxArgs {
   const float4* q_mask;          // [nq_pad][2] per-query epipolar mask state (geometry.cuh), masked modes only
   const uint8_t* t_desc; const int32_t* t_norm; const float2* t_loc; const int32_t* t_wcol;
   const int32_t* t_wmax;         // [n_ttiles * 8] per-window maximum of t_wcol (no-fold variant)
+  // Targets sorted by x (DoubleConstrained searches without seed distances, api.cu sorted_of): row r of the target arrays is
+  // feature t_orig[r] of the caller's set; keys carry the caller's index, so the winner rule is unchanged.  The rows of a
+  // 32-target window then span a narrow x range and a query whose epipolar segment lies outside it skips the window.
+  const uint32_t* t_orig;        // nullptr: rows are in the caller's order
   uint64_t* keys;                // [n_splits][nq_pad]
   uint32_t* flagged;             // list of (slot * nq_pad + row) needing the exact kernel
   uint32_t* n_flagged;
@@ -186,4 +191,6 @@ struct ssrlcv_b200_set : b200::ssrlcv_b200_set_impl {
   int32_t* h_mm;
   cudaEvent_t ready;
   bool resolved;
+  bool is_view;                  // rows of another set (match_host_streamed): borrowed memory
+  ssrlcv_b200_set* sorted;       // cached x-sorted copy (owned), or nullptr
 };

@@ -7,6 +7,8 @@
 //                             no-fold variant tests before it adds W to a window's accumulators
 //   loc   float2[n_pad]       sigtheta float2[n_pad]
 // HBM-bound byte shuffling: 152 B read, 188 B written per feature.
+#include <cub/cub.cuh>
+
 #include "matcher.cuh"
 
 namespace b200 {
@@ -92,6 +94,75 @@ void launch_pack(cudaStream_t st, const void* feat_dev, uint64_t n, uint64_t n_r
   pack_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const RefFeature*>(feat_dev), n, n_rows, s.desc + row0 * kDescBytes,
                                                              s.ext + row0 * kExtBytes, s.norm + row0, s.wcol + row0, s.wmax + row0 / kChunk,
                                                              s.loc + row0, s.sigtheta + row0, meta_dev);
+}
+
+// ---------------------------------------------------------------- x-sorted copy of a packed set (masked searches, api.cu sorted_of)
+// key = loc.x as an order-preserving integer; every NaN sorts last (a NaN coordinate passes the reference's mask,
+// src/MatchFactory.cu:2241-2254, so the window that holds it must never be culled: it ends in a NaN, see smax_tc.cu)
+__global__ void sort_keys_x_kernel(const float2* __restrict__ loc, uint32_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = loc[i].x;
+  const uint32_t u = __float_as_uint(x);
+  keys[i] = (x != x) ? 0xFFFFFFFFu : ((u & 0x80000000u) ? ~u : (u | 0x80000000u));
+  vals[i] = i;
+}
+// one warp per output row: row r of the sorted set = row perm[r] of the source; rows [n, n_rows) are padding (zero descriptor
+// and digits, W = 0, location NaN so that the last windows are never culled)
+__global__ void __launch_bounds__(256) gather_sorted_kernel(const uint32_t* __restrict__ perm, uint32_t n, uint32_t n_rows,
+                                                            const uint8_t* __restrict__ s_desc, const uint8_t* __restrict__ s_ext,
+                                                            const int32_t* __restrict__ s_norm, const int32_t* __restrict__ s_wcol,
+                                                            const float2* __restrict__ s_loc, const float2* __restrict__ s_sigtheta,
+                                                            uint8_t* __restrict__ desc, uint8_t* __restrict__ ext, int32_t* __restrict__ norm,
+                                                            int32_t* __restrict__ wcol, int32_t* __restrict__ wmax, float2* __restrict__ loc,
+                                                            float2* __restrict__ sigtheta, uint32_t* __restrict__ orig) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_rows) return;
+  uint32_t* d = reinterpret_cast<uint32_t*>(desc + static_cast<uint64_t>(r) * kDescBytes);
+  uint32_t* e = reinterpret_cast<uint32_t*>(ext + static_cast<uint64_t>(r) * kExtBytes);
+  if (r < n) {
+    const uint32_t src = perm[r];
+    d[lane] = reinterpret_cast<const uint32_t*>(s_desc + static_cast<uint64_t>(src) * kDescBytes)[lane];
+    if (lane < 8) e[lane] = reinterpret_cast<const uint32_t*>(s_ext + static_cast<uint64_t>(src) * kExtBytes)[lane];
+    if (lane == 0) {
+      norm[r] = s_norm[src];
+      const int32_t w = s_wcol[src];
+      wcol[r] = w;
+      atomicMax(&wmax[r >> 5], w);
+      loc[r] = s_loc[src];
+      sigtheta[r] = s_sigtheta[src];
+      orig[r] = src;
+    }
+  } else {
+    d[lane] = 0u;
+    if (lane < 8) e[lane] = 0u;
+    if (lane == 0) {
+      norm[r] = 0; wcol[r] = 0;
+      loc[r] = make_float2(__uint_as_float(0x7fc00000u), 0.f);
+      sigtheta[r] = make_float2(0.f, 0.f);
+      orig[r] = 0u;
+    }
+  }
+}
+size_t sort_x_temp_bytes(uint32_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, static_cast<const uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
+                                  static_cast<const uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), static_cast<int>(n));
+  return bytes;
+}
+// scratch: [keys_in | keys_out | vals_in | vals_out] (4 x n u32, each 256-byte aligned by the caller) followed by cub's temp storage
+cudaError_t launch_sort_gather(cudaStream_t st, const ssrlcv_b200_set_impl& src, ssrlcv_b200_set_impl& dst, uint32_t* keys_in,
+                               uint32_t* keys_out, uint32_t* vals_in, uint32_t* vals_out, void* temp, size_t temp_bytes) {
+  const uint32_t n = static_cast<uint32_t>(src.n), n_rows = static_cast<uint32_t>(dst.n_pad);
+  if (n) {
+    sort_keys_x_kernel<<<(n + 255) / 256, 256, 0, st>>>(src.loc, n, keys_in, vals_in);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, static_cast<int>(n), 0, 32, st);
+    if (e != cudaSuccess) return e;
+  }
+  gather_sorted_kernel<<<(n_rows + 7) / 8, 256, 0, st>>>(vals_out, n, n_rows, src.desc, src.ext, src.norm, src.wcol, src.loc, src.sigtheta,
+                                                         dst.desc, dst.ext, dst.norm, dst.wcol, dst.wmax, dst.loc, dst.sigtheta, dst.orig);
+  return cudaGetLastError();
 }
 
 }  // namespace b200

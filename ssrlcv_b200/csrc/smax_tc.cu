@@ -134,6 +134,7 @@ __device__ __forceinline__ void resolve_row(const SmaxArgs& job, const WinState&
     const int32_t top = va ? (vb ? max(a.best, b.best) : a.best) : b.best;
     const int32_t base = __ldg(job.q_norm + row) - 2 * top + 2 * w_offset;
     const int32_t* t_norm = job.t_norm;
+    const uint32_t* t_orig = job.t_orig;
     const uint64_t off = job.target_offset;
     bool ovf = false;
 #pragma unroll
@@ -151,7 +152,7 @@ __device__ __forceinline__ void resolve_row(const SmaxArgs& job, const WinState&
           m &= m - 1;
           const uint64_t f = static_cast<uint64_t>(w) * kChunk + e;
           const uint32_t d2 = static_cast<uint32_t>(base + (__ldg(t_norm + f) & 1));
-          const uint64_t k = make_key(d2, f + off);
+          const uint64_t k = make_key(d2, (t_orig ? static_cast<uint64_t>(__ldg(t_orig + f)) : f) + off);
           key = k < key ? k : key;
         }
       }
@@ -185,10 +186,10 @@ __device__ __forceinline__ void resolve_rows_windows(const SmaxArgs& job, const 
   struct {
     uint32_t nq, nt, nq_pad; float eps; uint64_t target_offset;
     const uint8_t* q_desc; const int32_t* q_norm; const float4* q_mask;
-    const uint8_t* t_desc; const int32_t* t_norm; const float2* t_loc;
+    const uint8_t* t_desc; const int32_t* t_norm; const float2* t_loc; const uint32_t* t_orig;
     uint64_t* keys; uint32_t* flagged; uint32_t* n_flagged;
   } args = {job.nq, job.nt, job.nq_pad, job.eps, job.target_offset, job.q_desc, job.q_norm, job.q_mask,
-            job.t_desc, job.t_norm, job.t_loc, job.keys, job.flagged, job.n_flagged};
+            job.t_desc, job.t_norm, job.t_loc, job.t_orig, job.keys, job.flagged, job.n_flagged};
   for (uint32_t g = 0; g < r_count; g += kFly) {
     WinState ms[kFly];
     uint32_t qrow[kFly];
@@ -233,7 +234,7 @@ __device__ __forceinline__ void resolve_rows_windows(const SmaxArgs& job, const 
 #pragma unroll
         for (int w = 0; w < 32; ++w) dot = __dp4a(__shfl_sync(kFull, qw[k], w), word_of(tv[k], w), dot);
         const uint32_t d2 = static_cast<uint32_t>(qn[k] + tn[k] - 2 * static_cast<int32_t>(dot));
-        res[k] = ok[k] ? make_key(d2, fs[k] + args.target_offset) : kKeyNone;
+        res[k] = ok[k] ? make_key(d2, (args.t_orig ? static_cast<uint64_t>(__ldg(args.t_orig + fs[k])) : fs[k]) + args.target_offset) : kKeyNone;
       }
       // ---- rare: a second window reached the same score ----
 #pragma unroll
@@ -258,7 +259,7 @@ __device__ __forceinline__ void resolve_rows_windows(const SmaxArgs& job, const 
             dot = __dp4a(__shfl_sync(kFull, qw[k], 4 * w8 + 3), b4.w, dot);
           }
           const uint32_t d2 = static_cast<uint32_t>(qn[k] + __ldg(args.t_norm + f2) - 2 * static_cast<int32_t>(dot));
-          const uint64_t k2 = ok2 ? make_key(d2, f2 + args.target_offset) : kKeyNone;
+          const uint64_t k2 = ok2 ? make_key(d2, (args.t_orig ? static_cast<uint64_t>(__ldg(args.t_orig + f2)) : f2) + args.target_offset) : kKeyNone;
           res[k] = k2 < res[k] ? k2 : res[k];
         }
       }
@@ -540,6 +541,7 @@ smax_kernel(const SmaxBatch batch) {
       const uint32_t row = u.qt * kBM + quarter * 32 + lane;       // this thread's query
       const uint32_t row_c = min(row, args.nq_pad - 1);
       const float eps = args.eps;
+      const bool sorted = args.t_orig != nullptr;
       QueryMask qm;
       if (kMask != SSRLCV_B200_MASK_NONE) qm = load_query_mask<kMask>(args.q_mask + 2 * static_cast<uint64_t>(row_c));
 
@@ -600,6 +602,21 @@ smax_kernel(const SmaxBatch batch) {
         int32_t wm[kWinPerWarp];
 #pragma unroll
         for (uint32_t k = 0; k < kWinPerWarp; ++k) wm[k] = max32(v[k]) + wbound[k];
+        uint32_t culled = 0;                                       // bit k: this lane's query cannot match anything in window k
+        if (kMask == SSRLCV_B200_MASK_DOUBLE && sorted) {
+          // x-sorted targets: a window's rows span [first.x, last.x]; the mask rejects every target left of lo_x or right of hi_x
+          // (first test of the reference's mask, src/MatchFactory.cu:2241-2243), so a query whose segment lies outside that span
+          // skips the window without looking at it.  A window that ends in a NaN (NaN coordinates pass the mask; they and the
+          // padding sort last) is never skipped on its left edge.
+#pragma unroll
+          for (uint32_t k = 0; k < kWinPerWarp; ++k) {
+            const float x_first = ld_shared_f2(smem_u32(s_loc + (c_begin + k) * kChunk)).x;
+            const float x_last = ld_shared_f2(smem_u32(s_loc + (c_begin + k) * kChunk + kChunk - 1)).x;
+            const bool outside = (x_last < qm.seg.lo_x) | ((x_first > qm.seg.hi_x) & (x_last == x_last));
+            wm[k] = outside ? 0 : wm[k];
+            culled |= outside ? (1u << k) : 0u;
+          }
+        }
         // One warp-uniform test per tile: does any window reach some lane's running best?  (Thresholded search: next to never.)
         const int32_t mt = max(max(wm[0], wm[1]), max(wm[2], wm[3]));
         if (__any_sync(0xffffffffu, mt >= st.best)) {
@@ -618,7 +635,7 @@ smax_kernel(const SmaxBatch batch) {
                   x[e] += static_cast<uint32_t>(w4.x); x[e + 1] += static_cast<uint32_t>(w4.y);
                   x[e + 2] += static_cast<uint32_t>(w4.z); x[e + 3] += static_cast<uint32_t>(w4.w);
                 }
-                wm[k] = max32(x);
+                wm[k] = ((culled >> k) & 1u) ? 0 : max32(x);
                 if (kMask != SSRLCV_B200_MASK_NONE && !__any_sync(0xffffffffu, wm[k] >= st.best)) continue;
               }
               if (kMask != SSRLCV_B200_MASK_NONE) {
@@ -627,6 +644,7 @@ smax_kernel(const SmaxBatch batch) {
                 // tests target l of the window, the ballot comes back to the query's lane as a column mask.  Masked entries
                 // score 0, below every floor (as do the rows past the end of the target set: zero padding with W = 0).
                 uint32_t todo = __ballot_sync(0xffffffffu, wm[k] >= st.best);
+                const bool mine = (todo >> lane) & 1u;             // this lane's query is one of the live ones
                 if (__popc(todo) <= 10) {
                   uint32_t skip = 0;
                   const float2 tl = ld_shared_f2(smem_u32(s_loc + (c_begin + k) * kChunk + lane));
@@ -649,7 +667,8 @@ smax_kernel(const SmaxBatch batch) {
                     if (mask_skips<kMask>(qm, __int_as_float(l2.z), __int_as_float(l2.w), eps)) x[e + 1] = 0;
                   }
                 }
-                wm[k] = max32(x);
+                // a lane that was not live keeps its bound (below its best; its row may not have been masked)
+                wm[k] = mine ? max32(x) : min(wm[k], st.best - 1);
               }
             }
           }

@@ -815,3 +815,31 @@ def test_random_sweep_against_oracle(api, everest):
         else:
             assert T.fields_equal(got, want), (case, nq, nt, thr, rel, out_kind, mask_kind, seeded)
     assert n_empty < 18
+
+
+@pytest.mark.parametrize("thr", [FLT_MAX, 1.2e5])
+def test_double_constrained_without_seeds_takes_the_x_sorted_targets(api, everest, monkeypatch, thr):
+    """DoubleConstrained searches without seed distances run on an x-sorted copy of the target set (api.cu sorted_of) so that whole
+    32-target windows fall outside a query's epipolar segment: NaN / negative / repeated x coordinates, a ragged last window,
+    both bookkeeping regimes -- same records as the oracle and as the unsorted path."""
+    q, t = synth.make_pair(2500, 8192 + 77, seed=123)
+    rng = np.random.default_rng(9)
+    t["loc"][rng.choice(len(t), 40, replace=False), 0] = np.nan          # NaN coordinates pass the reference's mask
+    t["loc"][rng.choice(len(t), 40, replace=False), 0] = -5.0
+    t["loc"][rng.choice(len(t), 300, replace=False), 0] = 512.0           # many equal keys
+    t["loc"][rng.choice(len(t), 10, replace=False), 1] = np.nan
+    qi, ti = api.Image(0, everest.cameras[0]), api.Image(1, everest.cameras[1])
+    p = api.O.make_params(out_kind=T.OUT_DMATCH, mask_kind=T.MASK_DOUBLE, abs_threshold=thr, query_id=0, target_id=1, epsilon=40, delta=5,
+                          query_camera=everest.cameras[0], target_camera=everest.cameras[1])
+    want = api.O.generate_matches(p, q, t)
+    assert len(want) > 50
+    got = {}
+    for so in ("1", "0"):
+        monkeypatch.setenv("SSRLCV_B200_SORTED", so)
+        mf = api.MatchFactory(1.0, thr)
+        got[so] = mf.generateDistanceMatchesDoubleConstrained(qi, _unity(api, q), ti, _unity(api, t), 40.0, 5.0).to_numpy()
+        assert T.fields_equal(got[so], want), so
+    monkeypatch.delenv("SSRLCV_B200_SORTED")
+    pr = api.MatchFactory(1.0, thr).generateMatchesDoubleConstrainedIndexOnly(qi, _unity(api, q), ti, _unity(api, t), 40.0, 5.0).to_numpy()
+    p.out_kind = T.OUT_PAIR
+    assert T.fields_equal(pr, api.O.generate_matches(p, q, t))
