@@ -1108,7 +1108,9 @@ int ssrlcv_b200_match_host(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params*
   if (n_query > 0x7fffffffull || n_target > 0x7fffffffull || n_seed > 0x7fffffffull) return fail(ctx, SSRLCV_B200_EINVAL, "match_host: too many features");
   {
     const uint64_t q_rows = host_chunk_rows(n_query, 0), t_rows = host_chunk_rows(n_target, 1);
-    if (n_query && n_target && p->engine != SSRLCV_B200_ENGINE_SIMT && (q_rows < n_query || t_rows < n_target))
+    // also for smaller seeded calls: the target set travels on the copy stream while the seed pass (queries x seed set) runs
+    const bool overlap_seed_pass = seed_host != nullptr && n_seed != 0 && n_target >= 8192 && getenv("SSRLCV_B200_HOST_CHUNK_ROWS") == nullptr;
+    if (n_query && n_target && p->engine != SSRLCV_B200_ENGINE_SIMT && (q_rows < n_query || t_rows < n_target || overlap_seed_pass))
       return match_host_streamed(ctx, p, query_host, n_query, target_host, n_target, seed_host, n_seed, out_host, n_out, q_rows, t_rows);
   }
   rc = pack_host_async(ctx, query_host, n_query, &q);
