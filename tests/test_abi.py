@@ -116,3 +116,28 @@ def test_fusion_matches_oracle_on_synthetic():
     mm, kp = fusion.fuse_pairs(feats, pairs)
     mm2, kp2 = O.fuse_nview(feats, pairs)
     assert T.fields_equal(mm, mm2) and T.fields_equal(kp, kp2)
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """the boundary is a C ABI: include/ssrlcv_b200.h compiles as C99 (pedantic) and as C++11, and a C program links against
+    the library and calls it (no CUDA or torch types in any signature)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "ssrlcv_b200.h"\n'
+                   "int main(void) {\n"
+                   "  ssrlcv_b200_match_params p; ssrlcv_b200_ctx* ctx = 0; (void)p;\n"
+                   "  if (ssrlcv_b200_abi_version() != 1) return 1;\n"
+                   "  if (ssrlcv_b200_create(0, 0, 0) == 0) return 2;          /* NULL out pointer: rejected */\n"
+                   "  ssrlcv_b200_destroy(ctx);                                 /* NULL: no-op */\n"
+                   "  return 0;\n}\n")
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.join(ROOT, "ssrlcv_b200")
+    _lib.load()                                                       # builds the library if it is stale
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", inc, "-c", str(src), "-o", str(tmp_path / "abi.o")])
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-I", inc, "-x", "c++", "-c", str(src), "-o", str(tmp_path / "abi_cxx.o")])
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", str(tmp_path / "abi.o"), "-L", libdir, "-lssrlcv_match_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)])
+    assert subprocess.call([str(exe)]) == 0
