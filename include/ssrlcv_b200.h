@@ -147,6 +147,12 @@ int  ssrlcv_b200_match_host(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params
 int  ssrlcv_b200_match_candidates(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* params,
                                   const ssrlcv_b200_set* query, const ssrlcv_b200_set* target_shard,
                                   uint64_t target_offset, uint64_t* keys_dev);
+/* Same, for searches that will be finalized with seed distances (ssrlcv_b200_finalize_candidates, params->compact != 0): the
+ * seed-ratio test (src/MatchFactory.cu:1691-1697) applies to the merged winner, so a shard only has to track candidates with
+ * d2 <= ratio * seed[q].  seed_dist_dev: float[size(query)] on the device, may be NULL (then identical to the call above). */
+int  ssrlcv_b200_match_candidates_seeded(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* params,
+                                         const ssrlcv_b200_set* query, const ssrlcv_b200_set* target_shard,
+                                         uint64_t target_offset, const float* seed_dist_dev, uint64_t* keys_dev);
 /* Merge n_shards candidate arrays (keys_dev: [n_shards][size(query)], e.g. the output of an all-gather),
  * then thresholds / ratio test / writers / compaction exactly as ssrlcv_b200_match.
  * target_loc_dev: float2[n_target_total] locations of the whole target set (index = global f);

@@ -847,6 +847,12 @@ int ssrlcv_b200_match(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, c
 
 int ssrlcv_b200_match_candidates(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const ssrlcv_b200_set* query,
                                  const ssrlcv_b200_set* shard, uint64_t target_offset, uint64_t* keys_dev) {
+  return ssrlcv_b200_match_candidates_seeded(ctx, p, query, shard, target_offset, nullptr, keys_dev);
+}
+
+int ssrlcv_b200_match_candidates_seeded(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const ssrlcv_b200_set* query,
+                                        const ssrlcv_b200_set* shard, uint64_t target_offset, const float* seed_dist_dev,
+                                        uint64_t* keys_dev) {
   if (!ctx || !query || !shard || (query->n && !keys_dev) || (target_offset & 31)) return fail(ctx, SSRLCV_B200_EINVAL, "match_candidates: bad arguments");
   int rc = check_params(ctx, p);
   if (rc) return rc;
@@ -854,6 +860,9 @@ int ssrlcv_b200_match_candidates(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_p
   PairWork w;
   fill_mask(p, w.mp);
   w.q = query; w.t = shard; w.engine = p->engine; w.target_offset = target_offset; w.abs_thr = p->absolute_threshold;
+  // the merged winner is dropped when it fails the seed-ratio test, so no shard needs candidates beyond that bound (matcher.cuh)
+  w.seed = (seed_dist_dev && p->compact) ? seed_dist_dev : nullptr;
+  w.seed_ratio = ratio_threshold(p->out_kind, p->mask_kind, p->relative_threshold);
   rc = engine_enqueue(ctx, &w, 1, nullptr);
   if (rc) return rc;
   if (w.a.nq) {                                            // reduce the local key slots to one key per query

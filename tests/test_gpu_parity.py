@@ -542,6 +542,40 @@ def test_sharded_targets_merge_equals_single_call(api):
     assert T.fields_equal(got, want)
 
 
+def test_sharded_targets_with_seed_distances(api, everest):
+    """target shards + seed distances (masked and not): each shard tracks only candidates that can pass the seed-ratio test
+    (ssrlcv_b200_match_candidates_seeded); the merged result equals the single call and the oracle."""
+    import torch
+    from ssrlcv_b200.match_factory import pack
+    q, t = synth.make_pair(3000, 8192 + 512, seed=62)
+    s = synth.make_seed(900)
+    sd_want = api.O.seed_distances(q, s)
+    mf = api.MatchFactory(0.8, 1.0e5)
+    mf.setSeedFeatures(_unity(api, s))
+    qu = _unity(api, q); qu.setMemoryState(api.gpu)
+    sd = mf.getSeedDistances(qu); sd.setMemoryState(api.gpu)
+    ctx = mf.ctx
+    bounds = [0, 2048, 4096, 6400, len(t)]
+    tloc = torch.from_numpy(np.ascontiguousarray(t["loc"])).cuda()
+    qi, ti = api.Image(0, everest.cameras[0]), api.Image(1, everest.cameras[1])
+    for mask_kind, kw in ((T.MASK_NONE, {}), (T.MASK_DOUBLE, dict(epsilon=25.0, delta=5.0))):
+        p = mf._params(T.OUT_DMATCH, mask_kind, qi, ti, **kw)
+        keys = torch.empty((4, len(q)), dtype=torch.int64, device="cuda")
+        for r in range(4):
+            su = _unity(api, t[bounds[r]:bounds[r + 1]]); su.setMemoryState(api.gpu)
+            ctx.check(ctx.lib.ssrlcv_b200_match_candidates_seeded(ctx.handle, C.byref(p), pack(ctx, qu).handle, pack(ctx, su).handle, bounds[r],
+                                                                  C.c_void_p(sd.device_ptr()), C.c_void_p(keys[r].data_ptr())))
+        out = torch.empty(len(q) * 48, dtype=torch.uint8, device="cuda")
+        n = C.c_uint64(0)
+        ctx.check(ctx.lib.ssrlcv_b200_finalize_candidates(ctx.handle, C.byref(p), pack(ctx, qu).handle, C.c_void_p(keys.data_ptr()), 4,
+                                                          C.c_void_p(tloc.data_ptr()), C.c_void_p(sd.device_ptr()), C.c_void_p(out.data_ptr()), C.byref(n)))
+        got = out[: n.value * 48].cpu().numpy().view(T.DMATCH)
+        po = api.O.make_params(out_kind=T.OUT_DMATCH, mask_kind=mask_kind, has_seed=True, abs_threshold=1.0e5, rel_threshold=0.8, query_id=0, target_id=1,
+                               epsilon=25, delta=5, query_camera=everest.cameras[0], target_camera=everest.cameras[1])
+        want = api.O.generate_matches(po, q, t, sd_want)
+        assert len(want) > 10 and T.fields_equal(got, want), mask_kind
+
+
 # ------------------------------------------------------------------------------------ the reference's own CUDA kernels
 def _ref_lib():
     path = os.path.join(ROOT, "oracle", "_ref", "libssrlcv_ref.so")
