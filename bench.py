@@ -213,6 +213,11 @@ def run_reference(args, w, rank, world):
     import torch
     if os.path.exists(path) and torch.cuda.is_available():
         run_dir = "/tmp/ssrlcv_ref_run"; os.makedirs(run_dir, exist_ok=True); os.chdir(run_dir)
+        # the reference's global logger announces its log file on stdout when the library is loaded and may print later: this
+        # process' stdout carries exactly one JSON line, so the C-level stdout goes to stderr while the reference runs
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         ref = C.CDLL(path); ref.ref_match.restype = C.c_long
         out = np.zeros(len(q), T.DMATCH)
         sd = np.zeros(len(q), np.float32)
@@ -229,6 +234,9 @@ def run_reference(args, w, rank, world):
             if it >= args.warmup:
                 times.append(ms.value + ms_seed.value)
         os.chdir(ROOT)
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
         ms_step = sum(times) / len(times)
         v = (len(q) * (len(t) + (len(s) if s is not None else 0))) / (ms_step * 1e-3)
         line.update({"value": v, "ms_per_step": ms_step * scale, "matches_per_step": int(n),
