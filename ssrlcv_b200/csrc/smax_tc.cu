@@ -717,8 +717,8 @@ smax_kernel(const SmaxBatch batch) {
       if (e == 0 || e == 5) {
         const uint32_t o = blockIdx.x * 16 + (e == 0 ? 4 : 8);
         batch.timing[o + 0] = te_wait; batch.timing[o + 1] = te_work; batch.timing[o + 2] = te_resolve; batch.timing[o + 3] = clock64() - te_total0;
+        // windows refined in the rare path (no-fold bounds / masks) and the time spent waiting for the column ring
         if (e == 0) { batch.timing[blockIdx.x * 16 + 14] = te_live; batch.timing[blockIdx.x * 16 + 15] = te_cwait; }
-        if (e == 0 && false) batch.timing[blockIdx.x * 16 + 14] = te_live;     // no-fold: windows whose bound reached a running best
       }
     }
   }
