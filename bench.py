@@ -60,6 +60,12 @@ def cameras():
     return ev.cameras[0], ev.cameras[1]
 
 
+def config_of(name, w):
+    """the `config` object both arms print (identical keys and values: the driver compares them)"""
+    return {"workload": f"{name}: {w['desc']}", "nq": w["nq"], "nt": w["nt"], "ns": w["ns"],
+            "l2": "256 MiB flush between timed iterations", "inputs": "Feature<SIFT_Descriptor> AoS arrays resident in HBM"}
+
+
 def evals_per_step(w):
     if "views" in w:
         return (w["views"] * (w["views"] - 1) // 2) * w["n"] * w["n"]
@@ -209,7 +215,7 @@ def run_reference(args, w, rank, world):
     line = {"impl": "reference", "metric": "sift_dist_evals_per_s", "unit": "dist-evals/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "strong" if args.workload in ("C4", "C5") else "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w['desc']}", "nq": w["nq"], "nt": w["nt"], "ns": w["ns"]}}
+            "config": config_of(args.workload, w)}
     import torch
     if os.path.exists(path) and torch.cuda.is_available():
         run_dir = "/tmp/ssrlcv_ref_run"; os.makedirs(run_dir, exist_ok=True); os.chdir(run_dir)
@@ -251,27 +257,88 @@ def run_reference(args, w, rank, world):
     return line
 
 
-def run_ours(args, w, rank, world, local_rank):
-    import torch
+class Env:
+    """one per process: device, library context, (for N > 1) the NCCL process group"""
+
+    def __init__(self, rank, world, local_rank):
+        import torch
+        from ssrlcv_b200.match_factory import Context
+        self.torch, self.rank, self.world, self.local_rank = torch, rank, world, local_rank
+        torch.cuda.set_device(local_rank)
+        self.prev_affinity = bind_to_gpu_numa(local_rank)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+            self.dist = dist
+        self.ctx = Context.get(local_rank)
+        # A/B timing of kernel variants: SSRLCV_BENCH_TUNE="fold=0,colmask=1,chunk_q=16384,chunk_t=16384" (tools/ab_fold.sh, e2e_chunks.sh)
+        from ssrlcv_b200 import _lib
+        knob_ids = {"fold": _lib.TUNE_FOLD, "colmask": _lib.TUNE_COLUMN_MASKS, "sorted": _lib.TUNE_SORTED_TARGETS,
+                    "chunk_q": _lib.TUNE_HOST_CHUNK_QUERY_ROWS, "chunk_t": _lib.TUNE_HOST_CHUNK_TARGET_ROWS}
+        for kv in filter(None, os.environ.get("SSRLCV_BENCH_TUNE", "").split(",")):
+            k, v = kv.split("=")
+            self.ctx.tune(knob_ids[k.strip()], int(v))
+        self.dev = f"cuda:{local_rank}"
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)       # > 126 MB L2
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        """CUDA events around every step on the library's stream, an L2 flush (not timed) in front of each"""
+        torch = self.torch
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        self.barrier()
+        wall0 = time.perf_counter()
+        n = 0
+        for i in range(steps):
+            self.flush.fill_(i & 0xFF)
+            ev[i][0].record()
+            n = fn()
+            ev[i][1].record()
+        self.barrier()
+        wall = time.perf_counter() - wall0
+        return sum(a.elapsed_time(b) for a, b in ev), n, wall
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def roofline_of(world, evals_per_launch_set, kern_ms, k_n, steps, kernel_note=""):
+    bf16_burst, bf16_sust, hbm, src = measured_peaks()
+    peak_tops = 2.0 * bf16_burst                     # dense int8 tensor rate = 2 x dense bf16
+    ops_per_launch = 256.0 * evals_per_launch_set / max(k_n / steps, 1)
+    achieved = ops_per_launch / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
+    mma_meas = None
+    mp = os.path.join(ROOT, "profiles", "int8_mma_peak.json")       # tools/microbench.cu on this pool (MMA-only issue rate)
+    if os.path.exists(mp):
+        mma_meas = json.load(open(mp)).get("int8_tops")
+    r = {"bound": "tensor", "achieved": achieved, "peak": peak_tops, "unit": "TFLOP/s", "frac": achieved / peak_tops,
+         "frac_vs_nominal": achieved / 4500.0, "frac_vs_int8_mma_measured": (achieved / mma_meas) if mma_meas else None,
+         "int8_mma_measured": mma_meas,
+         "kernel": "smax_kernel (tcgen05.mma kind::i8 + fused argmax epilogue)" + kernel_note, "kernel_ms": kern_ms, "launches_timed": int(k_n),
+         "ops": "int8 dense: 256 ops per distance evaluation (128 u8 x u8 MACs); the fold's extra K block is not counted",
+         "peak_source": f"2 x bf16_tflops burst, {src}; nominal dense int8 is 4500; int8_mma_measured = MMA-only microbenchmark (tools/microbench.cu)"}
+    return r, peak_tops
+
+
+def run_ours(args, w, env):
+    torch = env.torch
     from ssrlcv_b200 import _lib, types as T
-    from ssrlcv_b200.match_factory import Context
-    torch.cuda.set_device(local_rank)
-    prev_affinity = bind_to_gpu_numa(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    ctx = Context.get(local_rank)
+    rank, world, dev = env.rank, env.world, env.dev
+    ctx = env.ctx
     lib, h = ctx.lib, ctx.handle
     q, t, s = synth_inputs(w, rank)
     cam0, cam1 = cameras()
-    dev = f"cuda:{local_rank}"
     to_dev = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev)
     qd, td = to_dev(q), to_dev(t)
     sd_feat = to_dev(s) if s is not None else None
     out = torch.empty(len(q) * 48, dtype=torch.uint8, device=dev)
     seed_dist = torch.empty(len(q), dtype=torch.float32, device=dev)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
     p = _lib.MatchParams()
     p.out_kind, p.mask_kind = T.OUT_DMATCH, w["mask"]
@@ -279,55 +346,40 @@ def run_ours(args, w, rank, world, local_rank):
     p.query_image_id, p.target_image_id, p.epsilon, p.delta = 0, 1, EPS, DELTA
     p.query_camera = (C.c_uint8 * 80).from_buffer_copy(np.asarray(cam0).tobytes())
     p.target_camera = (C.c_uint8 * 80).from_buffer_copy(np.asarray(cam1).tobytes())
-    p.compact, p.engine = 1, 0
+    p.compact, p.reserved = 1, 0
     n_out = C.c_uint64(0)
+    n_sets = 3 if s is not None else 2
+    ptrs = (C.c_void_p * n_sets)(qd.data_ptr(), td.data_ptr(), *([sd_feat.data_ptr()] if s is not None else []))
+    sizes = (C.c_uint64 * n_sets)(len(q), len(t), *([len(s)] if s is not None else []))
+    sets = (C.c_void_p * n_sets)()
 
     def step():
-        """pack both sets (+ seed), seed distances, match; inputs are device-resident AoS arrays."""
-        hq, ht, hs = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        ctx.check(lib.ssrlcv_b200_pack(h, C.c_void_p(qd.data_ptr()), len(q), C.byref(hq)))
-        ctx.check(lib.ssrlcv_b200_pack(h, C.c_void_p(td.data_ptr()), len(t), C.byref(ht)))
+        """pack every set (one launch), seed distances, match; inputs are device-resident AoS arrays."""
+        ctx.check(lib.ssrlcv_b200_pack_batch(h, n_sets, ptrs, sizes, sets))
         seed_ptr, n_seed = None, 0
         if s is not None:
-            ctx.check(lib.ssrlcv_b200_pack(h, C.c_void_p(sd_feat.data_ptr()), len(s), C.byref(hs)))
-            ctx.check(lib.ssrlcv_b200_seed_distances(h, hq, hs, C.c_void_p(seed_dist.data_ptr()), 0))
+            ctx.check(lib.ssrlcv_b200_seed_distances(h, sets[0], sets[2], C.c_void_p(seed_dist.data_ptr())))
             seed_ptr, n_seed = C.c_void_p(seed_dist.data_ptr()), len(q)
-        ctx.check(lib.ssrlcv_b200_match(h, C.byref(p), hq, ht, seed_ptr, n_seed, C.c_void_p(out.data_ptr()), C.byref(n_out)))
-        for x in (hq, ht, hs):
-            if x:
-                lib.ssrlcv_b200_set_free(x)
+        ctx.check(lib.ssrlcv_b200_match(h, C.byref(p), sets[0], sets[1], seed_ptr, n_seed, C.c_void_p(out.data_ptr()), C.byref(n_out)))
+        for x in sets:
+            lib.ssrlcv_b200_set_free(x)
         return int(n_out.value)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     # ---------------- device-resident timing ----------------
     for _ in range(max(args.warmup, 3)):
         step()
     lib.ssrlcv_b200_set_profiling(h, 1)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(env.local_rank) if rank == 0 else None      # one sampler per job, not per rank
     launches0 = ctx.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    wall0 = time.perf_counter()
-    n_matches = 0
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)                       # evict L2 between timed iterations (not timed)
-        ev[i][0].record()
-        n_matches = step()
-        ev[i][1].record()
-    barrier()
-    wall = time.perf_counter() - wall0
+    total_ms, n_matches, wall = env.timed(step, args.steps)
     launches = ctx.launch_count() - launches0
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = sum(step_ms)
     k_ms, k_n = C.c_double(0), C.c_uint64(0)
     lib.ssrlcv_b200_kernel_time(h, C.byref(k_ms), C.byref(k_n))
     lib.ssrlcv_b200_set_profiling(h, 0)
-    sampler.ensure(step, torch.cuda.synchronize)    # short timed regions: same steps, untimed, until nvidia-smi has answered
-    clocks = sampler.stop()
+    clocks = None
+    if sampler is not None:
+        sampler.ensure(step, torch.cuda.synchronize)    # short timed regions: same steps, untimed, until nvidia-smi has answered
+        clocks = sampler.stop()
 
     # ---------------- end-to-end through the C ABI with host buffers ----------------
     pin = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1)).pin_memory()
@@ -343,91 +395,70 @@ def run_ours(args, w, rank, world, local_rank):
 
     for _ in range(2):
         step_e2e()
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)
-        ev2[i][0].record()
-        n_e2e = step_e2e()
-        ev2[i][1].record()
-    barrier()
-    e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+    e2e_ms, n_e2e, _ = env.timed(step_e2e, args.steps)
 
     # ---------------- max over ranks ----------------
     tt = torch.tensor([total_ms, e2e_ms, wall * 1e3], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if env.dist is not None:
+        env.dist.all_reduce(tt, op=env.dist.ReduceOp.MAX)
     total_ms, e2e_ms, wall_ms = (float(x) for x in tt.cpu())
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
         return None
 
     evals = evals_per_step(w)
     value = world * evals * args.steps / (total_ms * 1e-3)
-    bf16_burst, bf16_sust, hbm, src = measured_peaks()
-    peak_tops = 2.0 * bf16_burst                     # dense int8 tensor rate = 2 x dense bf16
     kern_ms = k_ms.value / max(k_n.value, 1)
     # per launch of the matcher kernel: the main (query x target) contraction dominates; seed launches are averaged in
-    ops_per_launch = 256.0 * evals / max(k_n.value / args.steps, 1)
-    achieved = ops_per_launch / (kern_ms * 1e-3) / 1e12
-    traffic = None
+    roof, peak_tops = roofline_of(world, evals, kern_ms, k_n.value, args.steps)
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.workload)
+    roof["traffic"] = json.load(open(tp)).get(args.workload) if os.path.exists(tp) else None
     line = {
         "metric": "sift_dist_evals_per_s", "value": value, "unit": "dist-evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {w['desc']}", "nq": w["nq"], "nt": w["nt"], "ns": w["ns"], "parallelism": f"pair-sharded x{world}",
-                   "l2": "256 MiB flush between timed iterations", "step": "pack(AoS->SoA) + [seed distances] + match + compaction, device-resident inputs"},
+        "config": config_of(args.workload, w),
+        "parallelism": f"pair-sharded x{world}: every rank matches its own image pair of this shape, no data-path collective",
+        "step": "pack(AoS->SoA, one launch) + [seed distances] + match + compaction, device-resident inputs",
         "matches_per_s": world * n_matches * args.steps / (total_ms * 1e-3), "queries_per_s": world * w["nq"] * args.steps / (total_ms * 1e-3),
         "matches_per_step": n_matches, "wall_ms_per_step": wall_ms / args.steps,
         "int8_tops": 256.0 * value / 1e12, "frac_of_int8_peak_step": 256.0 * value / 1e12 / (world * peak_tops),
+        "frac_of_nominal_int8_step": 256.0 * value / 1e12 / (world * 4500.0),
         "clocks": clocks,
         "e2e": {"value": world * evals * args.steps / (e2e_ms * 1e-3), "unit": "dist-evals/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": (len(q) + len(t) + (len(s) if s is not None else 0)) * 152, "d2h_bytes_per_step": n_e2e * 48 + 8,
                 "api": "ssrlcv_b200_match_host (pinned host buffers in, records out)",
-                "host": "process bound to the GPU-local CPUs (NVML affinity) while the pinned buffers are allocated and used" if prev_affinity else "no NUMA binding"},
+                "host": "process bound to the GPU-local CPUs (NVML affinity) while the pinned buffers are allocated and used" if env.prev_affinity else "no NUMA binding"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tops, "unit": "TFLOP/s", "frac": achieved / peak_tops, "traffic": traffic,
-                     "kernel": "smax_kernel (tcgen05.mma kind::i8 + fused argmax epilogue)", "kernel_ms": kern_ms, "launches_timed": int(k_n.value),
-                     "ops": "int8 dense: 256 ops per distance evaluation (128 u8 x u8 MACs); the fold's extra K block is not counted",
-                     "peak_source": f"2 x bf16_tflops burst, {src}; nominal dense int8 is 4500"},
+        "roofline": roof,
     }
-    if prev_affinity:
-        os.sched_setaffinity(0, prev_affinity)       # the CPU baseline uses every core the box gives us
-    try:
-        line["cpu_baseline"] = cpu_baseline(w, q, t, s) if not args.no_cpu_baseline else None
-    except Exception as e:  # noqa: BLE001
-        line["cpu_baseline"] = {"value": None, "unit": "dist-evals/s", "cores": 0, "kind": "port", "sample": f"failed: {e!r}"}
-    if dist is not None:
-        dist.destroy_process_group()
+    line["cpu_baseline"] = None
+    if world == 1 and not args.no_cpu_baseline:
+        if env.prev_affinity:
+            os.sched_setaffinity(0, env.prev_affinity)       # the CPU baseline uses every core the box gives us
+        try:
+            line["cpu_baseline"] = cpu_baseline(w, q, t, s)
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": "dist-evals/s", "cores": 0, "kind": "port", "sample": f"failed: {e!r}"}
     return line
 
 
-def run_sharded(args, w, rank, world, local_rank):
-    """C4 (pairs dealt to ranks) and C5 (target set sharded over ranks, NCCL all-gather of candidate keys)."""
-    import torch
+def run_sharded(args, name, w, env, with_clocks=True, with_e2e=True):
+    """C4 (pairs dealt to ranks) and C5 (target set sharded over ranks, NCCL all-gather of candidate keys).  After the timed
+    regions rank 0 recomputes the whole job alone on its GPU and compares the sharded records with it byte for byte
+    (`parity`, outside the timed regions)."""
+    torch = env.torch
     from ssrlcv_b200 import _lib, types as T
-    from ssrlcv_b200.distributed import shard_bounds
-    from ssrlcv_b200.match_factory import Context
+    from ssrlcv_b200.distributed import exchange_pair_lists, shard_bounds
     from ssrlcv_b200.pair_scheduler import assign_pairs, pair_order
-    torch.cuda.set_device(local_rank)
-    bind_to_gpu_numa(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    ctx = Context.get(local_rank)
+    rank, world, dev, dist = env.rank, env.world, env.dev, env.dist
+    ctx = env.ctx
     lib, h = ctx.lib, ctx.handle
-    dev = f"cuda:{local_rank}"
     pin = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1)).pin_memory()
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     p = _lib.MatchParams()
-    p.absolute_threshold, p.relative_threshold, p.compact, p.engine = ABS_THR, REL_THR, 1, 0
+    p.absolute_threshold, p.relative_threshold, p.compact, p.reserved = ABS_THR, REL_THR, 1, 0
     n_out = C.c_uint64(0)
     evals = evals_per_step(w)
     is_c4 = "views" in w
+    state = {"exchange_bytes": 0}
 
     if is_c4:
         from tests import synth
@@ -437,16 +468,13 @@ def run_sharded(args, w, rank, world, local_rank):
             a, b = synth.make_pair(n, n, seed=0x55524C43 + k)
             views += [a, b]
         pairs = pair_order(V)
-        mine = assign_pairs(pairs, [n] * V, world)[rank]
+        assign = assign_pairs(pairs, [n] * V, world)
+        mine = assign[rank]
         need = sorted({v for k in mine for v in pairs[k]})
         host = {v: pin(views[v]) for v in need}
         devbuf = {v: host[v].to(dev) for v in need}
-        slots = -(-len(pairs) // world)
-        out = torch.zeros((slots, n, 4), dtype=torch.int32, device=dev)           # uint2_pair records, padded per pair
-        counts = torch.zeros(len(pairs), dtype=torch.int64, device=dev)
-        counts_h = torch.zeros(len(pairs), dtype=torch.int64).pin_memory()
-        gathered = torch.empty((world * slots * n, 4), dtype=torch.int32, device=dev) if world > 1 else None
-        state = {}
+        slots = max(len(a) for a in assign)
+        out = torch.zeros((max(slots, 1), n, 4), dtype=torch.int32, device=dev)      # uint2_pair records, one slot per owned pair
         p.out_kind, p.mask_kind = T.OUT_PAIR, 0
         h2d = sum(len(views[v]) * 152 for v in need)
         # per-pair parameters and output slots do not change from step to step; only the packed-set handles do
@@ -454,44 +482,54 @@ def run_sharded(args, w, rank, world, local_rank):
         P = (_lib.MatchParams * max(m, 1))()
         Q, Tt, O = (C.c_void_p * max(m, 1))(), (C.c_void_p * max(m, 1))(), (C.c_void_p * max(m, 1))()
         n_outs = (C.c_uint64 * max(m, 1))()
-        n_outs_np, counts_np, mine_idx = np.ctypeslib.as_array(n_outs), counts_h.numpy(), np.asarray(mine, np.int64)
+        n_outs_np = np.ctypeslib.as_array(n_outs)
         for s_i, k in enumerate(mine):
             p.query_image_id, p.target_image_id = pairs[k]
             C.memmove(C.byref(P, s_i * C.sizeof(_lib.MatchParams)), C.byref(p), C.sizeof(_lib.MatchParams))
             O[s_i] = out[s_i].data_ptr()
+        nv = len(need)
+        vptr = (C.c_void_p * nv)(*[devbuf[v].data_ptr() for v in need])
+        vsize = (C.c_uint64 * nv)(*([n] * nv))
+        vsets = (C.c_void_p * nv)()
+        vpos = {v: i for i, v in enumerate(need)}
+        xch = exchange_pair_lists(len(pairs), assign, n, rank, world, dist, dev)
 
         def step(from_host=False):
             if from_host:
                 for v in need:
                     devbuf[v].copy_(host[v], non_blocking=True)
-            sets = {}
-            for v in need:                                                         # every view is repacked once per step, not per pair
-                hs = C.c_void_p()
-                ctx.check(lib.ssrlcv_b200_pack(h, C.c_void_p(devbuf[v].data_ptr()), n, C.byref(hs)))
-                sets[v] = hs
+            ctx.check(lib.ssrlcv_b200_pack_batch(h, nv, vptr, vsize, vsets))      # every view this rank touches: ONE pack launch per step
             # the pair scheduler's device side: all of this rank's pairs in one batch, one synchronisation
             for s_i, k in enumerate(mine):
-                Q[s_i], Tt[s_i] = sets[pairs[k][0]], sets[pairs[k][1]]
+                Q[s_i], Tt[s_i] = vsets[vpos[pairs[k][0]]], vsets[vpos[pairs[k][1]]]
             ctx.check(lib.ssrlcv_b200_match_batch(h, m, P, Q, Tt, None, O, n_outs))
-            counts_np[:] = 0
-            counts_np[mine_idx] = n_outs_np[:m]
-            total = int(n_outs_np[:m].sum())
-            counts.copy_(counts_h, non_blocking=True)
-            for hs in sets.values():
+            for hs in vsets:
                 lib.ssrlcv_b200_set_free(hs)
-            if dist is not None:                                                   # the one exchange of the path: pair lists to every rank
-                dist.all_reduce(counts)                                            # every pair is owned by exactly one rank
-                cap = max(int(counts.max().item()), 1)                             # longest list: the lists travel padded to it, not to n
-                send = out[:, :cap].contiguous()
-                recv = gathered[: world * slots * cap].view(world, slots, cap, 4)
-                dist.all_gather_into_tensor(recv, send)
-                state["exchange_bytes"] = recv.numel() * 4
-            elif from_host:
-                counts.cpu()
-            return total
+            # the one exchange of the path: every rank ends up with every pair list, in the reference's pair order
+            state["lists"] = xch.run(out, n_outs_np[:m])
+            state["exchange_bytes"] = xch.last_bytes
+            return int(n_outs_np[:m].sum())
 
         d2h = lambda: len(pairs) * 8
         par = f"pair-sharded x{world} ({len(mine)} of {len(pairs)} pairs on rank 0)"
+
+        def parity():
+            """rank 0: all 120 pairs alone, pair by pair == what the exchange delivered"""
+            allv = {v: torch.from_numpy(views[v].view(np.uint8).reshape(-1)).to(dev) for v in range(V)}
+            ok, total = True, 0
+            got_counts, got_buf = state["lists"]
+            solo = torch.zeros((n, 4), dtype=torch.int32, device=dev)
+            hq, ht = C.c_void_p(), C.c_void_p()
+            for k, (a, b) in enumerate(pairs):
+                ctx.check(lib.ssrlcv_b200_pack(h, C.c_void_p(allv[a].data_ptr()), n, C.byref(hq)))
+                ctx.check(lib.ssrlcv_b200_pack(h, C.c_void_p(allv[b].data_ptr()), n, C.byref(ht)))
+                p.query_image_id, p.target_image_id = a, b
+                ctx.check(lib.ssrlcv_b200_match(h, C.byref(p), hq, ht, None, 0, C.c_void_p(solo.data_ptr()), C.byref(n_out)))
+                lib.ssrlcv_b200_set_free(hq); lib.ssrlcv_b200_set_free(ht)
+                c = int(n_out.value)
+                total += c
+                ok = ok and c == int(got_counts[k]) and bool(torch.equal(solo[:c], got_buf[k][:c]))
+            return ok, total
     else:
         nq, nt = w["nq"], w["nt"]
         q, t = big_pair(nq, nt, 0x55524C43)
@@ -506,22 +544,24 @@ def run_sharded(args, w, rank, world, local_rank):
         out_h = torch.empty(nq * 48, dtype=torch.uint8).pin_memory()
         p.out_kind, p.mask_kind, p.query_image_id, p.target_image_id = T.OUT_DMATCH, 0, 0, 1
         h2d = (nq + hi - lo) * 152
+        ptrs = (C.c_void_p * 2)(qd.data_ptr(), td.data_ptr())
+        sizes = (C.c_uint64 * 2)(nq, hi - lo)
+        sets = (C.c_void_p * 2)()
 
         def step(from_host=False):
             if from_host:
                 qd.copy_(qh, non_blocking=True); td.copy_(th, non_blocking=True)
-            hq, ht = C.c_void_p(), C.c_void_p()
-            ctx.check(lib.ssrlcv_b200_pack(h, C.c_void_p(qd.data_ptr()), nq, C.byref(hq)))
-            ctx.check(lib.ssrlcv_b200_pack(h, C.c_void_p(td.data_ptr()), hi - lo, C.byref(ht)))
-            ctx.check(lib.ssrlcv_b200_match_candidates(h, C.byref(p), hq, ht, lo if hi > lo else 0, C.c_void_p(keys.data_ptr())))
+            ctx.check(lib.ssrlcv_b200_pack_batch(h, 2, ptrs, sizes, sets))
+            ctx.check(lib.ssrlcv_b200_match_candidates(h, C.byref(p), sets[0], sets[1], lo if hi > lo else 0, C.c_void_p(keys.data_ptr())))
             if dist is not None:
                 dist.all_gather_into_tensor(allk, keys)                            # 8 B per query per rank over NVLink
                 src = allk
+                state["exchange_bytes"] = allk.numel() * 8
             else:
                 src = keys
-            ctx.check(lib.ssrlcv_b200_finalize_candidates(h, C.byref(p), hq, C.c_void_p(src.data_ptr()), world, C.c_void_p(tloc.data_ptr()),
+            ctx.check(lib.ssrlcv_b200_finalize_candidates(h, C.byref(p), sets[0], C.c_void_p(src.data_ptr()), world, C.c_void_p(tloc.data_ptr()),
                                                           None, C.c_void_p(out.data_ptr()), C.byref(n_out)))
-            lib.ssrlcv_b200_set_free(hq); lib.ssrlcv_b200_set_free(ht)
+            lib.ssrlcv_b200_set_free(sets[0]); lib.ssrlcv_b200_set_free(sets[1])
             if from_host:
                 out_h[: n_out.value * 48].copy_(out[: n_out.value * 48]); torch.cuda.synchronize()
             return int(n_out.value)
@@ -529,78 +569,94 @@ def run_sharded(args, w, rank, world, local_rank):
         d2h = lambda: int(n_out.value) * 48 + 8
         par = f"target-sharded x{world} (rank 0 owns targets [{lo}, {hi}))"
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        barrier()
-        n = 0
-        for i in range(steps):
-            flush.fill_(i & 0xFF)
-            ev[i][0].record()
-            n = fn()
-            ev[i][1].record()
-        barrier()
-        return sum(a.elapsed_time(b) for a, b in ev), n
+        def parity():
+            """rank 0: the whole 1 M x 1 M pair alone on its GPU == the merged result of the shards"""
+            n_sh = step()
+            got = out[: n_sh * 48].clone()
+            tfull = torch.from_numpy(t.view(np.uint8).reshape(-1)).to(dev)
+            hq, ht = C.c_void_p(), C.c_void_p()
+            ctx.check(lib.ssrlcv_b200_pack(h, C.c_void_p(qd.data_ptr()), nq, C.byref(hq)))
+            ctx.check(lib.ssrlcv_b200_pack(h, C.c_void_p(tfull.data_ptr()), nt, C.byref(ht)))
+            solo = torch.empty(nq * 48, dtype=torch.uint8, device=dev)
+            ctx.check(lib.ssrlcv_b200_match(h, C.byref(p), hq, ht, None, 0, C.c_void_p(solo.data_ptr()), C.byref(n_out)))
+            lib.ssrlcv_b200_set_free(hq); lib.ssrlcv_b200_set_free(ht)
+            c = int(n_out.value)
+            return c == n_sh and bool(torch.equal(solo[: c * 48], got)), c
 
     for _ in range(max(args.warmup, 3)):
         step()
     lib.ssrlcv_b200_set_profiling(h, 1)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(env.local_rank) if (with_clocks and rank == 0) else None
     launches0 = ctx.launch_count()
-    total_ms, n_matches = timed(step, args.steps)
+    total_ms, n_matches, _ = env.timed(step, args.steps)
     launches = ctx.launch_count() - launches0
     k_ms, k_n = C.c_double(0), C.c_uint64(0)
     lib.ssrlcv_b200_kernel_time(h, C.byref(k_ms), C.byref(k_n))
     lib.ssrlcv_b200_set_profiling(h, 0)
-    step(True)
-    e2e_ms, _ = timed(lambda: step(True), args.steps)
-    tt = torch.tensor([total_ms, e2e_ms, float(n_matches)], dtype=torch.float64, device=dev)
+    e2e_ms = 0.0
+    if with_e2e:
+        step(True)
+        e2e_ms, _, _ = env.timed(lambda: step(True), args.steps)
+    tt = torch.tensor([total_ms, e2e_ms, float(n_matches), k_ms.value / max(k_n.value, 1)], dtype=torch.float64, device=dev)
     tm = tt.clone()
     if dist is not None:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         dist.all_reduce(tt, op=dist.ReduceOp.SUM)
-    total_ms, e2e_ms = float(tm[0]), float(tm[1])
+    total_ms, e2e_ms, kern_ms_max = float(tm[0]), float(tm[1]), float(tm[3])
     n_total = int(tt[2]) if is_c4 else n_matches
-    # short timed regions: the same steps, untimed, until nvidia-smi has had time to answer.  The steps contain collectives,
-    # so every rank runs the same number of them (derived from the all-reduced time).
-    if total_ms < 400.0:
-        for _ in range(min(400, int(400.0 * args.steps / max(total_ms, 1e-3)) + 1)):
+    clocks = None
+    if with_clocks:
+        # short timed regions: the same steps, untimed, until nvidia-smi has had time to answer.  The steps contain collectives,
+        # so every rank runs the same number of them (derived from the all-reduced time).
+        if total_ms < 400.0:
+            for _ in range(min(400, int(400.0 * args.steps / max(total_ms, 1e-3)) + 1)):
+                step()
+            torch.cuda.synchronize()
+        if sampler is not None:
+            clocks = sampler.stop()
+    # ---- parity against the single-GPU result (rank 0 computes it; the others wait at the barrier)
+    par_ok, par_n = None, None
+    if is_c4:
+        step()
+    if rank == 0:
+        par_ok, par_n = parity() if is_c4 else (None, None)
+    if not is_c4:                      # C5's check runs one more sharded step: every rank takes part in its all-gather
+        if rank == 0:
+            par_ok, par_n = parity()
+        else:
             step()
-        torch.cuda.synchronize()
-    clocks = sampler.stop()
+    env.barrier()
     if rank != 0:
-        dist.destroy_process_group()
         return None
-    bf16_burst, _, _, src = measured_peaks()
-    peak_tops = 2.0 * bf16_burst
     value = evals * args.steps / (total_ms * 1e-3)
     kern_ms = k_ms.value / max(k_n.value, 1)
     my_evals = evals / world if not is_c4 else len(mine) * w["n"] * w["n"]
-    ops_per_launch = 256.0 * my_evals / max(k_n.value / args.steps, 1)
-    achieved = ops_per_launch / (kern_ms * 1e-3) / 1e12
+    roof, peak_tops = roofline_of(world, my_evals, kern_ms, k_n.value, args.steps, ", rank 0")
+    roof["traffic"] = None
+    roof["kernel_ms_max_over_ranks"] = kern_ms_max
     line = {
         "metric": "sift_dist_evals_per_s", "value": value, "unit": "dist-evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {w['desc']}", "parallelism": par, "l2": "256 MiB flush between timed iterations",
-                   "step": "pack + match of this rank's share + result exchange + finalize, device-resident inputs"},
+        "config": config_of(name, w), "parallelism": par,
+        "step": "pack + match of this rank's share + result exchange + finalize, device-resident inputs",
         "matches_per_s": n_total * args.steps / (total_ms * 1e-3), "matches_per_step": n_total,
-        "int8_tops": 256.0 * value / 1e12, "frac_of_int8_peak_step": 256.0 * value / 1e12 / (world * peak_tops), "clocks": clocks,
-        "e2e": {"value": evals * args.steps / (e2e_ms * 1e-3), "unit": "dist-evals/s", "ms_per_step": e2e_ms / args.steps,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h(), "api": "C ABI with pinned host inputs copied in every step, counts / records read back"},
+        "int8_tops": 256.0 * value / 1e12, "frac_of_int8_peak_step": 256.0 * value / 1e12 / (world * peak_tops),
+        "frac_of_nominal_int8_step": 256.0 * value / 1e12 / (world * 4500.0), "clocks": clocks,
+        "exchange_bytes_per_step": int(state["exchange_bytes"]),
+        "parity": par_ok, "parity_note": f"sharded records == the single-GPU result recomputed on rank 0 ({par_n} records), byte for byte",
+        "e2e": ({"value": evals * args.steps / (e2e_ms * 1e-3), "unit": "dist-evals/s", "ms_per_step": e2e_ms / args.steps,
+                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h(), "api": "C ABI with pinned host inputs copied in every step, counts / records read back"}
+                if with_e2e else None),
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tops, "unit": "TFLOP/s", "frac": achieved / peak_tops, "traffic": None,
-                     "kernel": "smax_kernel (tcgen05.mma kind::i8 + fused argmax epilogue), rank 0", "kernel_ms": kern_ms, "launches_timed": int(k_n.value),
-                     "peak_source": f"2 x bf16_tflops burst, {src}; nominal dense int8 is 4500"},
+        "roofline": roof,
         "cpu_baseline": None,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and with_e2e:
         # the CPU oracle on a bounded sample of the same workload: C4 = a query sample of ONE of its 120 equal pairs,
         # C5 = a query sample against the whole target set (dist-evals/s does not depend on which pair / which queries)
         try:
+            if env.prev_affinity:
+                os.sched_setaffinity(0, env.prev_affinity)
             cq, ct = (views[0], views[1]) if is_c4 else (q, t)
             cb = cpu_baseline(dict(w, mask=0), cq, ct, None)
             if is_c4:
@@ -608,8 +664,6 @@ def run_sharded(args, w, rank, world, local_rank):
             line["cpu_baseline"] = cb
         except Exception as e:  # the oracle library is test infrastructure; its absence must not hide the GPU numbers
             line["cpu_baseline"] = {"unavailable": str(e)}
-    if dist is not None:
-        dist.destroy_process_group()
     return line
 
 
@@ -621,6 +675,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the C4 / C5 sub-records of the default line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -628,10 +683,30 @@ def main():
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         line = run_reference(args, w, rank, world)
-    elif args.workload in ("C4", "C5"):
-        line = run_sharded(args, w, rank, world, local_rank)
     else:
-        line = run_ours(args, w, rank, world, local_rank)
+        env = Env(rank, world, local_rank)
+        if args.workload in ("C4", "C5"):
+            line = run_sharded(args, args.workload, w, env)
+        else:
+            line = run_ours(args, w, env)
+            if world > 1 and args.workload == "C3" and not args.no_sharded:
+                # The multi-GPU configurations of BASELINE.json, measured by the same launch: C4 (120 pairs dealt to the ranks)
+                # and C5 (one 1 M x 1 M pair, target set sharded, NCCL all-gather of the candidate keys), strong scaling,
+                # each with its record-equality check against the single-GPU result.
+                sub = {}
+                sub_args = argparse.Namespace(**vars(args))
+                sub_args.steps = min(args.steps, 10)
+                for name in ("C4", "C5"):
+                    env.torch.cuda.empty_cache()
+                    try:
+                        r = run_sharded(sub_args, name, WORKLOADS[name], env, with_clocks=False, with_e2e=False)
+                    except Exception as e:  # noqa: BLE001 -- the headline line must survive a failure of a sub-record
+                        r = {"error": repr(e)}
+                    if rank == 0:
+                        sub[name] = r
+                if line is not None:
+                    line["sharded"] = sub
+        env.close()
     if line is not None:
         print(json.dumps(line), flush=True)
 

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SSRLCV_B200_ABI_VERSION 1
+#define SSRLCV_B200_ABI_VERSION 2
 
 enum {
   SSRLCV_B200_EINVAL = -1,      /* bad argument (NULL, size mismatch, unknown kind) */
@@ -58,7 +58,21 @@ enum {
   SSRLCV_B200_MASK_FUNDAMENTAL = 1, /* matchFeaturesConstrained       (F matrix, src/MatchFactory.cu:1598-1657) */
   SSRLCV_B200_MASK_DOUBLE = 2       /* matchFeaturesDoubleConstrained (GEO_ORBIT=1, src/MatchFactory.cu:1507-1597) */
 };
-/* distance engine; TCGEN05 is the product path, SIMT exists to cross-check it on device */
+/* Tuning / diagnostics knobs of a context (ssrlcv_b200_tune).  Value -1 (the default) lets the library decide; the product
+ * path never needs them.  They exist for A/B timing and so that the parity tests can force every kernel variant and the
+ * second, independent device implementation (CROSSCHECK_SIMT) the tensor-core path is checked against on the device. */
+enum {
+  SSRLCV_B200_TUNE_FOLD = 0,                  /* 0 / 1: matcher variant without / with the fold K block (smax_tc.cu)            */
+  SSRLCV_B200_TUNE_COLUMN_MASKS = 1,          /* 0 / 1: bookkeeping regime of the matcher's epilogue                            */
+  SSRLCV_B200_TUNE_SORTED_TARGETS = 2,        /* 0 / 1: x-sorted target copy for unseeded DoubleConstrained searches           */
+  SSRLCV_B200_TUNE_HOST_CHUNK_QUERY_ROWS = 3, /* match_host: rows per upload chunk of the query set (0 = never cut)            */
+  SSRLCV_B200_TUNE_HOST_CHUNK_TARGET_ROWS = 4,/* match_host: rows per upload chunk of the target set (0 = never cut)           */
+  SSRLCV_B200_TUNE_CROSSCHECK_SIMT = 5,       /* 1: evaluate distances with the SIMT cross-check kernel instead of tcgen05     */
+  SSRLCV_B200_TUNE_TIMING_BUFFER = 6,         /* device address of u64[148][16] cycle counters: runs the instrumented build of the
+                                                 matcher kernel (tools/kerneltiming.py); 0 / -1 = off                           */
+  SSRLCV_B200_TUNE_COUNT_ = 7
+};
+/* internal engine ids (kept for the library's own use) */
 enum { SSRLCV_B200_ENGINE_TCGEN05 = 0, SSRLCV_B200_ENGINE_SIMT = 1 };
 
 typedef struct ssrlcv_b200_ctx ssrlcv_b200_ctx;   /* device, stream, workspaces */
@@ -83,7 +97,7 @@ typedef struct {
   int32_t  compact;             /* 1: stable-compact valid entries (validateMatches, src/MatchFactory.cu:31-135);
                                    0: keep all numQuery entries, invalid ones flagged (generateFeatureMatches
                                    quirk, src/MatchFactory.cu:674-696) */
-  int32_t  engine;              /* SSRLCV_B200_ENGINE_* */
+  int32_t  reserved;            /* must be 0 */
 } ssrlcv_b200_match_params;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -98,6 +112,7 @@ uint64_t ssrlcv_b200_launch_count(const ssrlcv_b200_ctx* ctx);
 /* bench instrumentation: when enabled, CUDA events bracket every launch of the tensor-core matcher kernel on the
  * context's stream; kernel_time() synchronises and returns the accumulated device time (ms) and launch count
  * since the last call, then resets both. */
+int  ssrlcv_b200_tune(ssrlcv_b200_ctx* ctx, int knob, int64_t value);
 int  ssrlcv_b200_set_profiling(ssrlcv_b200_ctx* ctx, int enabled);
 int  ssrlcv_b200_kernel_time(ssrlcv_b200_ctx* ctx, double* total_ms, uint64_t* n_launches);
 
@@ -106,15 +121,21 @@ int  ssrlcv_b200_kernel_time(ssrlcv_b200_ctx* ctx, double* total_ms, uint64_t* n
  * 152-byte AoS records cannot be read by TMA (stride 152 = 8 mod 16); pack() repacks them once
  * into dense uint8[n][128] rows (+ norms, locations, sigma/theta). */
 int  ssrlcv_b200_pack(ssrlcv_b200_ctx* ctx, const void* features_dev, uint64_t n, ssrlcv_b200_set** out);
+/* n_sets feature arrays in ONE launch (the views of an N-view job, or the query / target / seed sets of a 2-view call).
+ * Enqueue-only, like pack(). */
+int  ssrlcv_b200_pack_batch(ssrlcv_b200_ctx* ctx, uint32_t n_sets, const void* const* features_dev, const uint64_t* n,
+                            ssrlcv_b200_set** out);
 int  ssrlcv_b200_pack_host(ssrlcv_b200_ctx* ctx, const void* features_host, uint64_t n, ssrlcv_b200_set** out);
 uint64_t ssrlcv_b200_set_size(const ssrlcv_b200_set* s);
 void ssrlcv_b200_set_free(ssrlcv_b200_set* s);
 
 /* ---- matching -----------------------------------------------------------------------------
  * replaces: MatchFactory<T>::getSeedDistances (src/MatchFactory.cu:315-346) + getSeedMatchDistances
- * (:1433-1460).  out_dev: float[size(query)]; FLT_MAX when the seed set is empty. */
+ * (:1433-1460).  out_dev: float[size(query)]; FLT_MAX when the seed set is empty.  Enqueue-only: the distances are
+ * complete for later calls on the same context (stream order); call ssrlcv_b200_synchronize before reading them on
+ * the host.  Both sets must stay alive until then (releasing one settles the pass first). */
 int  ssrlcv_b200_seed_distances(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* query, const ssrlcv_b200_set* seed,
-                                float* out_dev, int engine);
+                                float* out_dev);
 
 /* replaces: generateMatches / generateDistanceMatches / generateMatchesIndexOnly / generateFeatureMatches
  * and their Constrained / DoubleConstrained forms (src/MatchFactory.cu:349-905) including the

@@ -24,6 +24,7 @@
 #include <chrono>
 #include <map>
 #include <set>
+#include <vector>
 
 #include "ssrlcv_b200.h"
 
@@ -61,10 +62,20 @@ inline bool b200_device_current(const U& u) {
 struct PackedSet {   // RAII over ssrlcv_b200_set
   ssrlcv_b200_set* s = nullptr;
   PackedSet(void* features_dev, unsigned long n) { b200_check(ssrlcv_b200_pack(b200_context(), features_dev, n, &s), "ssrlcv_b200_pack"); }
+  explicit PackedSet(ssrlcv_b200_set* adopted) : s(adopted) {}
   ~PackedSet() { ssrlcv_b200_set_free(s); }
   PackedSet(const PackedSet&) = delete;
   PackedSet& operator=(const PackedSet&) = delete;
 };
+// Packs several device arrays with ONE launch (ssrlcv_b200_pack_batch).  Packed sets are never cached across calls: a
+// (device pointer, size) key cannot tell a buffer from a later allocation at the same address, and validating the contents
+// costs as much as repacking them (one HBM pass); within a call every array is packed exactly once.
+inline void b200_pack_all(const std::vector<const void*>& dev, const std::vector<uint64_t>& n, std::vector<PackedSet*>& out) {
+  std::vector<ssrlcv_b200_set*> sets(dev.size(), nullptr);
+  b200_check(ssrlcv_b200_pack_batch(b200_context(), (uint32_t)dev.size(), dev.data(), n.data(), sets.data()), "ssrlcv_b200_pack_batch");
+  out.resize(dev.size());
+  for (size_t i = 0; i < dev.size(); ++i) out[i] = new PackedSet(sets[i]);
+}
 
 template <typename Out, typename T>
 ssrlcv::ptr::value<ssrlcv::Unity<Out>> b200_generate(
@@ -108,7 +119,6 @@ ssrlcv::ptr::value<ssrlcv::Unity<Out>> b200_generate(
   memcpy(p.query_camera, &query->camera, 80);
   memcpy(p.target_camera, &target->camera, 80);
   p.compact = compact ? 1 : 0;
-  p.engine = SSRLCV_B200_ENGINE_TCGEN05;
 
   clock_t timer = clock();
   MemoryState seedOrigin = gpu;
@@ -123,8 +133,16 @@ ssrlcv::ptr::value<ssrlcv::Unity<Out>> b200_generate(
     seed_dev = seedDistances->device.get();
   }
   {
-    PackedSet* own_q = queryPacked ? nullptr : new PackedSet(queryFeatures->device.get(), queryFeatures->size());
-    PackedSet* own_t = targetPacked ? nullptr : new PackedSet(targetFeatures->device.get(), targetFeatures->size());
+    PackedSet* own_q = nullptr;
+    PackedSet* own_t = nullptr;
+    if (!queryPacked && !targetPacked) {                   // the usual 2-view call: both sets in one pack launch
+      std::vector<PackedSet*> both;
+      b200_pack_all({queryFeatures->device.get(), targetFeatures->device.get()}, {queryFeatures->size(), targetFeatures->size()}, both);
+      own_q = both[0]; own_t = both[1];
+    } else {
+      if (!queryPacked) own_q = new PackedSet(queryFeatures->device.get(), queryFeatures->size());
+      if (!targetPacked) own_t = new PackedSet(targetFeatures->device.get(), targetFeatures->size());
+    }
     const ssrlcv_b200_set* qs = queryPacked ? queryPacked->s : own_q->s;
     const ssrlcv_b200_set* ts = targetPacked ? targetPacked->s : own_t->s;
     uint64_t n_out = 0;
@@ -302,11 +320,12 @@ ssrlcv::ptr::value<ssrlcv::Unity<float>> ssrlcv::MatchFactory<T>::getSeedDistanc
   ssrlcv::ptr::value<ssrlcv::Unity<float>> matchDistances = ssrlcv::ptr::value<ssrlcv::Unity<float>>(nullptr, numPossibleMatches, gpu);
   clock_t timer = clock();
   {
-    PackedSet q(features->device.get(), features->size());
-    PackedSet s(this->seedFeatures->device.get(), this->seedFeatures->size());
-    b200_check(ssrlcv_b200_seed_distances(b200_context(), q.s, s.s, matchDistances->device.get(), SSRLCV_B200_ENGINE_TCGEN05),
-               "ssrlcv_b200_seed_distances");
+    std::vector<PackedSet*> qs;
+    b200_pack_all({features->device.get(), this->seedFeatures->device.get()}, {features->size(), this->seedFeatures->size()}, qs);
+    b200_check(ssrlcv_b200_seed_distances(b200_context(), qs[0]->s, qs[1]->s, matchDistances->device.get()), "ssrlcv_b200_seed_distances");
     b200_check(ssrlcv_b200_synchronize(b200_context()), "ssrlcv_b200_synchronize");
+    delete qs[0];
+    delete qs[1];
   }
   logger.info.printf("seed match distances computed in %f seconds.", ((float)clock() - timer) / CLOCKS_PER_SEC);
   if (features->getMemoryState() != origin) features->setMemoryState(origin);
@@ -374,20 +393,36 @@ ssrlcv::MatchSet ssrlcv::MatchFactory<T>::generateMatchesExhaustive(std::vector<
   matchSet.matches = nullptr;
   if (estimatedOverlap == 0) logger.warn << "WARNING: estimated overlap fraction of 0.0f requires unordered match interpolation";
   const size_t n = images.size();
-  const bool debugPhases = getenv("SSRLCV_B200_DEBUG_HOST") != nullptr;
+#ifdef SSRLCV_B200_DEBUG_PHASES
   auto phase0 = std::chrono::steady_clock::now();
   auto phase = [&](const char* what) {
-    if (!debugPhases) return;
     auto now = std::chrono::steady_clock::now();
     fprintf(stderr, "generateMatchesExhaustive: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - phase0).count());
     phase0 = now;
   };
+#else
+  auto phase = [](const char*) {};
+#endif
   std::vector<MemoryState> origin(n);
-  std::vector<PackedSet*> packed(n, nullptr);
-  for (size_t v = 0; v < n; ++v) {
-    origin[v] = features[v]->getMemoryState();
-    if (!b200_device_current(features[v])) features[v]->setMemoryState(gpu);
-    packed[v] = new PackedSet(features[v]->device.get(), features[v]->size());
+  std::vector<PackedSet*> packed;
+  PackedSet* seedPacked = nullptr;
+  {
+    // every view (and the seed image's features) is packed once, all of them in ONE launch
+    std::vector<const void*> dev;
+    std::vector<uint64_t> cnt;
+    for (size_t v = 0; v < n; ++v) {
+      origin[v] = features[v]->getMemoryState();
+      if (!b200_device_current(features[v])) features[v]->setMemoryState(gpu);
+      dev.push_back(features[v]->device.get());
+      cnt.push_back(features[v]->size());
+    }
+    if (this->seedFeatures != nullptr) {
+      if (!b200_device_current(this->seedFeatures)) this->seedFeatures->setMemoryState(gpu);
+      dev.push_back(this->seedFeatures->device.get());
+      cnt.push_back(this->seedFeatures->size());
+    }
+    b200_pack_all(dev, cnt, packed);
+    if (this->seedFeatures != nullptr) { seedPacked = packed.back(); packed.pop_back(); }
   }
   unsigned long long totalMatches = 0;
   phase("states + pack");
@@ -409,18 +444,12 @@ ssrlcv::MatchSet ssrlcv::MatchFactory<T>::generateMatchesExhaustive(std::vector<
   std::vector<std::pair<size_t, size_t>> pairOf;
   size_t outRecords = 0;
   int i = 0;
-  PackedSet* seedPacked = nullptr;
-  if (this->seedFeatures != nullptr) {
-    if (!b200_device_current(this->seedFeatures)) this->seedFeatures->setMemoryState(gpu);
-    seedPacked = new PackedSet(this->seedFeatures->device.get(), this->seedFeatures->size());
-  }
   for (size_t q = 0; q + 1 < n; ++q) {
     if (seedPacked != nullptr) {
       // getSeedDistances (ref: :915-917) on the sets that are packed already; stream-ordered before the batch below
       clock_t timer = clock();
       seedOfView[q] = ssrlcv::ptr::value<ssrlcv::Unity<float>>(nullptr, features[q]->size(), gpu);
-      b200_check(ssrlcv_b200_seed_distances(b200_context(), packed[q]->s, seedPacked->s, seedOfView[q]->device.get(), SSRLCV_B200_ENGINE_TCGEN05),
-                 "ssrlcv_b200_seed_distances");
+      b200_check(ssrlcv_b200_seed_distances(b200_context(), packed[q]->s, seedPacked->s, seedOfView[q]->device.get()), "ssrlcv_b200_seed_distances");
       logger.info.printf("seed match distances computed in %f seconds.", ((float)clock() - timer) / CLOCKS_PER_SEC);
     }
     for (size_t t = q + 1; t < n; ++t) {
@@ -439,7 +468,6 @@ ssrlcv::MatchSet ssrlcv::MatchFactory<T>::generateMatchesExhaustive(std::vector<
       memcpy(p.query_camera, &images[q]->camera, 80);
       memcpy(p.target_camera, &images[t]->camera, 80);
       p.compact = 1;
-      p.engine = SSRLCV_B200_ENGINE_TCGEN05;
       params.push_back(p);
       qsets.push_back(packed[q]->s);
       tsets.push_back(packed[t]->s);

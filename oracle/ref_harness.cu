@@ -93,7 +93,9 @@ int ref_seed_distances(const void* q, unsigned long nq, const void* seed, unsign
   return 0;
 }
 
-/* out_kind: 0 Match, 1 DMatch, 2 uint2_pair.  mask_kind: 0 none, 1 fundamental, 2 double constrained.
+/* out_kind: 0 Match, 1 DMatch, 2 uint2_pair, 3 FeatureMatch (mask_kind 0 or 1 only: the reference has no DoubleConstrained
+ * FeatureMatch kernel; the unconstrained form returns all nq entries uncompacted, ref: src/MatchFactory.cu:654-697).
+ * mask_kind: 0 none, 1 fundamental, 2 double constrained.
  * seed_dist may be NULL.  Returns the number of entries the reference returned (after its own
  * validateMatches), copied to out_host.  ms = wall time of the API call (inputs already in `state`). */
 long ref_match(int out_kind, int mask_kind, float abs_thr, float rel_thr, int qid, int tid,
@@ -118,6 +120,8 @@ long ref_match(int out_kind, int mask_kind, float abs_thr, float rel_thr, int qi
   ptr::value<Unity<Match>> m0 = nullptr;
   ptr::value<Unity<DMatch>> m1 = nullptr;
   ptr::value<Unity<uint2_pair>> m2 = nullptr;
+  Unity<FeatureMatch<SIFT_Descriptor>>* m3 = nullptr;     // raw pointer API (ref: include/MatchFactory.cuh:288,293)
+  if (out_kind == 3 && mask_kind == 2) return -2;
   if (out_kind == 0) {
     if (mask_kind == 0) m0 = mf.generateMatches(qi, qs, ti, ts, sd);
     else if (mask_kind == 1) m0 = mf.generateMatchesConstrained(qi, qs, ti, ts, eps, F, sd);
@@ -130,6 +134,9 @@ long ref_match(int out_kind, int mask_kind, float abs_thr, float rel_thr, int qi
     if (mask_kind == 0) m2 = mf.generateMatchesIndexOnly(qi, qs, ti, ts, sd);
     else if (mask_kind == 1) m2 = mf.generateMatchesConstrainedIndexOnly(qi, qs, ti, ts, eps, F, sd);
     else m2 = mf.generateMatchesDoubleConstrainedIndexOnly(qi, qs, ti, ts, eps, delta, sd);
+  } else if (out_kind == 3) {
+    if (mask_kind == 0) m3 = mf.generateFeatureMatches(qi, qs, ti, ts, sd);
+    else m3 = mf.generateFeatureMatchesConstrained(qi, qs, ti, ts, eps, F, sd);
   } else {
     return -2;
   }
@@ -137,15 +144,17 @@ long ref_match(int out_kind, int mask_kind, float abs_thr, float rel_thr, int qi
   if (ms) *ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   if (out_kind == 0) n = (long)copy_out(m0, out_host, sizeof(Match));
   else if (out_kind == 1) n = (long)copy_out(m1, out_host, sizeof(DMatch));
-  else n = (long)copy_out(m2, out_host, sizeof(uint2_pair));
+  else if (out_kind == 2) n = (long)copy_out(m2, out_host, sizeof(uint2_pair));
+  else { n = (long)copy_out(m3, out_host, sizeof(FeatureMatch<SIFT_Descriptor>)); delete m3; }
   return n;
 }
 
 /* generateMatchesExhaustive (ref: src/MatchFactory.cu:907-1028) over n_views host feature arrays.
  * Returns the number of MultiMatch entries (copied to out_mm, capacity cap_mm); *n_kp keypoints to out_kp. */
-long ref_exhaustive(int n_views, const void* const* feats, const unsigned long* n_feats, const void* const* cams80, const int* ids,
-                    const void* seed, unsigned long n_seed, float rel_thr, float abs_thr, float eps, float delta, int state,
-                    void* out_mm, unsigned long cap_mm, void* out_kp, unsigned long cap_kp, unsigned long* n_kp, double* ms) {
+long ref_exhaustive2(int n_views, const void* const* feats, const unsigned long* n_feats, const void* const* cams80, const int* ids,
+                     const void* seed, unsigned long n_seed, float rel_thr, float abs_thr, float eps, float delta, int state,
+                     int ordered, float estimated_overlap,
+                     void* out_mm, unsigned long cap_mm, void* out_kp, unsigned long cap_kp, unsigned long* n_kp, double* ms) {
   mkdir("out", 0755);
   std::vector<ptr::value<Image>> images;
   std::vector<FeatSet> features;
@@ -157,7 +166,7 @@ long ref_exhaustive(int n_views, const void* const* feats, const unsigned long* 
   if (seed) mf.setSeedFeatures(make_set(seed, n_seed, 2));
   cudaDeviceSynchronize();
   auto t0 = std::chrono::steady_clock::now();
-  MatchSet set = mf.generateMatchesExhaustive(images, features, eps, delta);
+  MatchSet set = mf.generateMatchesExhaustive(images, features, eps, delta, ordered != 0, estimated_overlap);
   cudaDeviceSynchronize();
   if (ms) *ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   if (set.matches->size() > cap_mm || set.keyPoints->size() > cap_kp) return -3;
@@ -167,6 +176,50 @@ long ref_exhaustive(int n_views, const void* const* feats, const unsigned long* 
   memcpy(out_kp, (void*)set.keyPoints->host.get(), set.keyPoints->size() * sizeof(KeyPoint));
   *n_kp = set.keyPoints->size();
   return (long)set.matches->size();
+}
+
+long ref_exhaustive(int n_views, const void* const* feats, const unsigned long* n_feats, const void* const* cams80, const int* ids,
+                    const void* seed, unsigned long n_seed, float rel_thr, float abs_thr, float eps, float delta, int state,
+                    void* out_mm, unsigned long cap_mm, void* out_kp, unsigned long cap_kp, unsigned long* n_kp, double* ms) {
+  return ref_exhaustive2(n_views, feats, n_feats, cams80, ids, seed, n_seed, rel_thr, abs_thr, eps, delta, state, 1, 0.0f,
+                         out_mm, cap_mm, out_kp, cap_kp, n_kp, ms);
+}
+
+/* validateMatches (ref: src/MatchFactory.cu:31-135) through the class API on a host record array of out_kind 0..3 (in place);
+ * returns the size of the caller's array afterwards (unchanged when nothing was valid -- the reference's quirk, except for the raw
+ * FeatureMatch pointer, which the reference deletes: not driven with an all-invalid array). */
+long ref_validate(int out_kind, void* records, unsigned long n) {
+  mkdir("out", 0755);
+  MatchFactory<SIFT_Descriptor> mf;
+  if (out_kind == 0) {
+    ptr::value<Unity<Match>> m(nullptr, n, cpu);
+    memcpy((void*)m->host.get(), records, n * sizeof(Match));
+    m->setMemoryState(gpu); mf.validateMatches(m); m->transferMemoryTo(cpu);
+    memcpy(records, (void*)m->host.get(), m->size() * sizeof(Match));
+    return (long)m->size();
+  } else if (out_kind == 1) {
+    ptr::value<Unity<DMatch>> m(nullptr, n, cpu);
+    memcpy((void*)m->host.get(), records, n * sizeof(DMatch));
+    m->setMemoryState(gpu); mf.validateMatches(m); m->transferMemoryTo(cpu);
+    memcpy(records, (void*)m->host.get(), m->size() * sizeof(DMatch));
+    return (long)m->size();
+  } else if (out_kind == 2) {
+    ptr::value<Unity<uint2_pair>> m(nullptr, n, cpu);
+    memcpy((void*)m->host.get(), records, n * sizeof(uint2_pair));
+    m->setMemoryState(gpu); mf.validateMatches(m); m->transferMemoryTo(cpu);
+    memcpy(records, (void*)m->host.get(), m->size() * sizeof(uint2_pair));
+    return (long)m->size();
+  } else if (out_kind == 3) {
+    typedef FeatureMatch<SIFT_Descriptor> FM;
+    Unity<FM>* m = new Unity<FM>(nullptr, n, cpu);
+    memcpy((void*)m->host.get(), records, n * sizeof(FM));
+    m->setMemoryState(gpu); mf.validateMatches(m); m->transferMemoryTo(cpu);
+    memcpy(records, (void*)m->host.get(), m->size() * sizeof(FM));
+    long k = (long)m->size();
+    delete m;
+    return k;
+  }
+  return -2;
 }
 
 /* refineMatches + sortMatches + getRawMatches through the class API on a host DMatch array (in place); returns kept count */

@@ -18,7 +18,8 @@ ERRORS = {-1: "EINVAL", -2: "ENODEVICE", -3: "ESEEDSIZE", -4: "ETHRESHOLD", -5: 
 # every symbol include/ssrlcv_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "ssrlcv_b200_abi_version", "ssrlcv_b200_create", "ssrlcv_b200_destroy", "ssrlcv_b200_last_error",
-    "ssrlcv_b200_synchronize", "ssrlcv_b200_launch_count", "ssrlcv_b200_set_profiling", "ssrlcv_b200_kernel_time", "ssrlcv_b200_pack", "ssrlcv_b200_pack_host",
+    "ssrlcv_b200_synchronize", "ssrlcv_b200_launch_count", "ssrlcv_b200_tune", "ssrlcv_b200_set_profiling", "ssrlcv_b200_kernel_time",
+    "ssrlcv_b200_pack", "ssrlcv_b200_pack_batch", "ssrlcv_b200_pack_host",
     "ssrlcv_b200_set_size", "ssrlcv_b200_set_free", "ssrlcv_b200_seed_distances", "ssrlcv_b200_match",
     "ssrlcv_b200_match_host", "ssrlcv_b200_match_batch", "ssrlcv_b200_match_candidates", "ssrlcv_b200_match_candidates_seeded", "ssrlcv_b200_finalize_candidates",
     "ssrlcv_b200_set_loc", "ssrlcv_b200_validate", "ssrlcv_b200_refine", "ssrlcv_b200_sort",
@@ -34,8 +35,12 @@ class MatchParams(C.Structure):
         ("epsilon", C.c_float), ("delta", C.c_float),
         ("fundamental", C.c_float * 9),
         ("query_camera", C.c_uint8 * 80), ("target_camera", C.c_uint8 * 80),
-        ("compact", C.c_int32), ("engine", C.c_int32),
+        ("compact", C.c_int32), ("reserved", C.c_int32),
     ]
+
+
+# ssrlcv_b200_tune knobs (include/ssrlcv_b200.h)
+TUNE_FOLD, TUNE_COLUMN_MASKS, TUNE_SORTED_TARGETS, TUNE_HOST_CHUNK_QUERY_ROWS, TUNE_HOST_CHUNK_TARGET_ROWS, TUNE_CROSSCHECK_SIMT, TUNE_TIMING_BUFFER = range(7)
 
 
 class B200Error(RuntimeError):
@@ -69,9 +74,11 @@ def load() -> C.CDLL:
     lib.ssrlcv_b200_synchronize.argtypes = [vp]
     lib.ssrlcv_b200_launch_count.argtypes = [vp]
     lib.ssrlcv_b200_launch_count.restype = u64
+    lib.ssrlcv_b200_tune.argtypes = [vp, i32, C.c_int64]
     lib.ssrlcv_b200_set_profiling.argtypes = [vp, i32]
     lib.ssrlcv_b200_kernel_time.argtypes = [vp, C.POINTER(C.c_double), pu64]
     lib.ssrlcv_b200_pack.argtypes = [vp, vp, u64, C.POINTER(vp)]
+    lib.ssrlcv_b200_pack_batch.argtypes = [vp, u32, C.POINTER(vp), pu64, C.POINTER(vp)]
     lib.ssrlcv_b200_pack_host.argtypes = [vp, vp, u64, C.POINTER(vp)]
     lib.ssrlcv_b200_set_size.argtypes = [vp]
     lib.ssrlcv_b200_set_size.restype = u64
@@ -79,7 +86,7 @@ def load() -> C.CDLL:
     lib.ssrlcv_b200_set_free.restype = None
     lib.ssrlcv_b200_set_loc.argtypes = [vp]
     lib.ssrlcv_b200_set_loc.restype = vp
-    lib.ssrlcv_b200_seed_distances.argtypes = [vp, vp, vp, vp, i32]
+    lib.ssrlcv_b200_seed_distances.argtypes = [vp, vp, vp, vp]
     lib.ssrlcv_b200_match.argtypes = [vp, pp, vp, vp, vp, u64, vp, pu64]
     lib.ssrlcv_b200_match_batch.argtypes = [vp, u32, pp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), pu64]
     lib.ssrlcv_b200_match_host.argtypes = [vp, pp, vp, u64, vp, u64, vp, u64, vp, pu64]

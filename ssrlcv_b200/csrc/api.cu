@@ -3,11 +3,11 @@
 // kernels; there is no CPU fallback: without an sm_100 device every entry point fails.
 #include <cfloat>
 #include <cmath>
-#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <new>
 #include <string>
 #include <utility>
@@ -17,7 +17,7 @@
 
 namespace b200 {
 // pack.cu
-void launch_pack(cudaStream_t, const void*, uint64_t n, uint64_t n_rows, uint64_t row0, ssrlcv_b200_set_impl&, int32_t* meta_dev, int sm_count);
+void launch_pack(cudaStream_t, const PackJob* jobs, uint32_t n_jobs, int sm_count, uint64_t* launches);
 size_t sort_x_temp_bytes(uint32_t n);
 cudaError_t launch_sort_gather(cudaStream_t, const ssrlcv_b200_set_impl& src, ssrlcv_b200_set_impl& dst, uint32_t* keys_in, uint32_t* keys_out,
                                uint32_t* vals_in, uint32_t* vals_out, void* temp, size_t temp_bytes);
@@ -25,7 +25,7 @@ cudaError_t launch_sort_gather(cudaStream_t, const ssrlcv_b200_set_impl& src, ss
 cudaError_t launch_smax(cudaStream_t, const SmaxBatch&, int mask_kind, bool fold, bool colmask);
 // exact.cu
 void launch_exact(cudaStream_t, const SmaxArgs&, int mask_kind, int sm_count);
-void launch_exact_list(cudaStream_t, const SmaxJob*, uint32_t, int mask_kind, int sm_count);
+void launch_exact_list(cudaStream_t, const SmaxBatch&, uint32_t* done, int mask_kind, int sm_count);
 void launch_endpoints(cudaStream_t, const MaskParams&, const float2*, uint64_t, float4*);
 void launch_query_masks(cudaStream_t, const MaskParams&, const float2*, uint64_t, float4*);
 void launch_sincos(cudaStream_t, const float*, uint64_t, float*, float*);
@@ -34,14 +34,15 @@ struct CompactArgs {
   const uint8_t* in; uint8_t* out; uint32_t n; uint32_t elt; int32_t pred; float threshold;
   uint32_t* block_counts; uint32_t* total;
 };
-void launch_finalize(cudaStream_t, const FinalizeArgs*, uint32_t, uint32_t);
+void launch_finalize(cudaStream_t, const FinalizeBatch&, uint32_t, uint32_t);
 void launch_seed_from_keys(cudaStream_t, const uint64_t*, uint32_t, uint32_t, uint32_t, float*);
 void launch_fill_u64(cudaStream_t, uint64_t*, uint64_t, uint64_t);
 void launch_min_keys(cudaStream_t, const uint64_t*, uint32_t, uint32_t, uint32_t, uint64_t*);
 void launch_compact(cudaStream_t, CompactArgs);
 void launch_raw_matches(cudaStream_t, const void*, uint32_t, void*);
 void launch_match_set_2view(cudaStream_t, const void*, uint32_t, void*, void*, uint32_t*);
-uint64_t launch_sort(cudaStream_t, void*, uint32_t, uint64_t*, void*);
+size_t sort_temp_bytes(uint32_t n);
+cudaError_t launch_sort(cudaStream_t, void*, uint32_t, uint64_t*, uint64_t*, void*, size_t, void*, uint64_t*);
 }  // namespace b200
 
 using namespace b200;
@@ -63,8 +64,12 @@ struct ssrlcv_b200_ctx {
   EncodeTiledFn encode = nullptr;
   std::string err;
   uint64_t launches = 0;
-  Workspace keys, flagged, counts, scratch, hostpin, qmask, totals, nflag, sortws;
-  uint32_t* d_scalars = nullptr;   // [1] total of a single match
+  Workspace keys, flagged, counts, scratch, hostpin, qmask, sortws;
+  // zero-initialised once, left zero by the kernels that use them: tie counters ([0] = the tie kernel's `done` ticket),
+  // finalize tickets, finalize block states (stamped with `epoch`, so stale entries read as "not yet")
+  Workspace nflag, tickets, fstate;
+  uint32_t epoch = 0;
+  uint32_t* d_scalars = nullptr;   // small device scalars
   // job descriptors (SmaxJob / FinalizeArgs arrays) travel host -> device through a small ring of pinned buffers
   struct Staged { void* h = nullptr; void* d = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; bool pending = false; };
   Staged staged[8];
@@ -73,11 +78,20 @@ struct ssrlcv_b200_ctx {
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
-  // pack() does not synchronise: the meta scalars of a set land in a pinned slot and are read when a match first
-  // needs it (set_resolve).  Slots and their events are recycled through this free list.
-  struct PackSlot { int32_t* mm; cudaEvent_t ready; };
-  std::vector<PackSlot> free_slots;
+  // pack() does not synchronise and enqueues nothing but its kernel: a set's meta scalars live in a slot of a pool that is
+  // zero between uses (4 x int32 on the device + a pinned, device-mapped host mirror the pack kernel writes its rare "does
+  // not fit the fold digits" verdict to) and are read when a match first needs them (set_resolve).  Slots are recycled
+  // oldest first, so a slot that comes round again has long been quiescent.
+  struct PackSlot { int32_t* mm; cudaEvent_t ready; int32_t* d_meta; };
+  std::deque<PackSlot> free_slots;
   std::vector<int32_t*> slot_blocks;
+  std::vector<int32_t*> slot_dev_blocks;
+  // tuning / diagnostics knobs (ssrlcv_b200_tune); -1 = the library decides
+  int64_t knob[SSRLCV_B200_TUNE_COUNT_];
+  // seed passes launched with the fold variant before the seed set's pack had reported back (seed_distances does not
+  // wait): checked at the context's next synchronisation point, redone with the other variant if the guess was wrong
+  struct PendingSeed { const ssrlcv_b200_set* q; const ssrlcv_b200_set* seed; float* out; };
+  std::vector<PendingSeed> pending;
   // match_host with large sets: uploads run on their own stream, chunk by chunk, while the matcher already works on the
   // chunks that have arrived (match_host_streamed)
   cudaStream_t copy_stream = nullptr;
@@ -89,18 +103,31 @@ static int slot_acquire(ssrlcv_b200_ctx* ctx, ssrlcv_b200_ctx::PackSlot& out) {
   if (ctx->free_slots.empty()) {
     constexpr int kPerBlock = 256;
     int32_t* block = nullptr;
-    cudaError_t e = cudaMallocHost(&block, kPerBlock * 4 * sizeof(int32_t));
+    int32_t* dblock = nullptr;
+    cudaError_t e = cudaHostAlloc(&block, kPerBlock * 4 * sizeof(int32_t), cudaHostAllocMapped | cudaHostAllocPortable);
     if (e != cudaSuccess) return static_cast<int>(e);
+    memset(block, 0, kPerBlock * 4 * sizeof(int32_t));
     ctx->slot_blocks.push_back(block);
+    e = cudaMalloc(&dblock, kPerBlock * 4 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemset(dblock, 0, kPerBlock * 4 * sizeof(int32_t));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    ctx->slot_dev_blocks.push_back(dblock);
     for (int i = 0; i < kPerBlock; ++i) {
-      ssrlcv_b200_ctx::PackSlot s{block + 4 * i, nullptr};
+      ssrlcv_b200_ctx::PackSlot s{block + 4 * i, nullptr, dblock + 4 * i};
       e = cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming);
       if (e != cudaSuccess) return static_cast<int>(e);
       ctx->free_slots.push_back(s);
     }
   }
-  out = ctx->free_slots.back();
-  ctx->free_slots.pop_back();
+  out = ctx->free_slots.front();
+  ctx->free_slots.pop_front();
+  // the slot's previous user: normally finished long ago (oldest-first recycling); its verdict decides whether the device
+  // word has to be cleared (only sets that did not fit the fold digits ever dirty it)
+  if (cudaEventQuery(out.ready) == cudaErrorNotReady) cudaEventSynchronize(out.ready);
+  if (out.mm[0] != 0) {
+    cudaMemsetAsync(out.d_meta, 0, 4 * sizeof(int32_t), ctx->stream);
+    out.mm[0] = 0;
+  }
   return 0;
 }
 
@@ -127,6 +154,17 @@ static int ws_reserve(ssrlcv_b200_ctx* ctx, Workspace& w, size_t bytes) {
   return 0;
 }
 
+// same, and the buffer is zero whenever it is (re)allocated (workspaces whose users leave them zero)
+static int ws_reserve_zero(ssrlcv_b200_ctx* ctx, Workspace& w, size_t bytes) {
+  if (bytes <= w.cap) return 0;
+  int rc = ws_reserve(ctx, w, bytes * 2);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(w.p, 0, w.cap, ctx->stream));
+  return 0;
+}
+
+static int verify_pending(ssrlcv_b200_ctx* ctx, bool* redone);
+
 extern "C" {
 
 int ssrlcv_b200_abi_version(void) { return SSRLCV_B200_ABI_VERSION; }
@@ -143,6 +181,7 @@ int ssrlcv_b200_create(ssrlcv_b200_ctx** out, int device, void* stream) {
   if (!ctx) return SSRLCV_B200_ENOMEM;
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  for (int64_t& k : ctx->knob) k = -1;
   cudaSetDevice(device);
   if (stream) ctx->stream = static_cast<cudaStream_t>(stream);
   else { cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking); ctx->own_stream = true; }
@@ -160,7 +199,7 @@ int ssrlcv_b200_create(ssrlcv_b200_ctx** out, int device, void* stream) {
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
   }
-  if (cudaMalloc(&ctx->d_scalars, 16 * sizeof(uint32_t)) != cudaSuccess || cudaMallocHost(&ctx->h_scalars, 16 * sizeof(uint32_t)) != cudaSuccess) {
+  if (cudaMalloc(&ctx->d_scalars, 16 * sizeof(uint32_t)) != cudaSuccess || cudaHostAlloc(&ctx->h_scalars, 16 * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
     delete ctx;
     return SSRLCV_B200_ENOMEM;
   }
@@ -172,7 +211,7 @@ void ssrlcv_b200_destroy(ssrlcv_b200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (Workspace* w : {&ctx->keys, &ctx->flagged, &ctx->counts, &ctx->scratch, &ctx->qmask, &ctx->totals, &ctx->nflag, &ctx->sortws}) if (w->p) cudaFree(w->p);
+  for (Workspace* w : {&ctx->keys, &ctx->flagged, &ctx->counts, &ctx->scratch, &ctx->qmask, &ctx->nflag, &ctx->tickets, &ctx->fstate, &ctx->sortws}) if (w->p) cudaFree(w->p);
   for (auto& st : ctx->staged) {
     if (st.h) cudaFreeHost(st.h);
     if (st.d) cudaFree(st.d);
@@ -184,6 +223,7 @@ void ssrlcv_b200_destroy(ssrlcv_b200_ctx* ctx) {
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& sl : ctx->free_slots) cudaEventDestroy(sl.ready);
   for (int32_t* b : ctx->slot_blocks) cudaFreeHost(b);
+  for (int32_t* b : ctx->slot_dev_blocks) cudaFree(b);
   if (ctx->d_scalars) cudaFree(ctx->d_scalars);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
   for (auto& pe : ctx->prof_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
@@ -194,7 +234,17 @@ void ssrlcv_b200_destroy(ssrlcv_b200_ctx* ctx) {
 const char* ssrlcv_b200_last_error(const ssrlcv_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 int ssrlcv_b200_synchronize(ssrlcv_b200_ctx* ctx) {
   if (!ctx) return SSRLCV_B200_EINVAL;
+  CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->stream));
+  bool redone = false;
+  int rc = verify_pending(ctx, &redone);
+  if (rc) return rc;
+  if (redone) CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int ssrlcv_b200_tune(ssrlcv_b200_ctx* ctx, int knob, int64_t value) {
+  if (!ctx || knob < 0 || knob >= SSRLCV_B200_TUNE_COUNT_) return fail(ctx, SSRLCV_B200_EINVAL, "tune: unknown knob");
+  ctx->knob[knob] = value;
   return 0;
 }
 uint64_t ssrlcv_b200_launch_count(const ssrlcv_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -232,7 +282,8 @@ static int encode_map(ssrlcv_b200_ctx* ctx, CUtensorMap* m, void* base, uint64_t
   return 0;
 }
 
-// Allocates a set of n rows (one allocation, tensor maps, pinned slot for the meta scalars, meta zeroed); nothing is packed yet.
+// Allocates a set of n rows (one allocation, tensor maps, a slot of the meta pool); nothing is packed yet and nothing is
+// enqueued: the pack kernel writes every row including the zero padding and every window bound.
 static int set_alloc(ssrlcv_b200_ctx* ctx, uint64_t n, ssrlcv_b200_set** out, bool with_orig = false) {
   ssrlcv_b200_set* s = new (std::nothrow) ssrlcv_b200_set();
   if (!s) return SSRLCV_B200_ENOMEM;
@@ -243,13 +294,13 @@ static int set_alloc(ssrlcv_b200_ctx* ctx, uint64_t n, ssrlcv_b200_set** out, bo
   if (s->n_pad == 0) s->n_pad = kRowPad;
   ssrlcv_b200_ctx::PackSlot slot;
   int rc = slot_acquire(ctx, slot);
-  if (rc) { delete s; return fail(ctx, rc, "pack: pinned slot: %s", cudaGetErrorString(static_cast<cudaError_t>(rc))); }
-  s->h_mm = slot.mm; s->ready = slot.ready; s->resolved = false; s->is_view = false; s->sorted = nullptr;
-  // one allocation: desc | ext | norm | wcol | loc | sigtheta | wmax | meta   (all segments 32-byte aligned since n_pad % 256 == 0);
-  // the pack kernels write every row including the zero padding, so nothing is memset except wmax (4 bytes per 32 rows,
-  // accumulated with atomicMax) and the 16 bytes of meta
+  if (rc) { delete s; return fail(ctx, rc, "pack: meta slot: %s", cudaGetErrorString(static_cast<cudaError_t>(rc))); }
+  s->h_mm = slot.mm; s->ready = slot.ready; s->meta = slot.d_meta;
+  s->resolved = false; s->is_view = false; s->sorted = nullptr;
+  // one allocation: desc | ext | norm | wcol | loc | sigtheta | wmax | [orig]   (all segments 32-byte aligned since n_pad % 256 == 0)
   const size_t np = s->n_pad;
-  const size_t bytes = np * (kDescBytes + kExtBytes + 4 + 4 + 8 + 8 + (with_orig ? 4 : 0)) + (np / kChunk) * 4 + 256;
+  const size_t wmax_bytes = ((np / kChunk) * 4 + 255) / 256 * 256;
+  const size_t bytes = np * (kDescBytes + kExtBytes + 4 + 4 + 8 + 8 + (with_orig ? 4 : 0)) + wmax_bytes + 256;
   uint8_t* base = nullptr;
   cudaError_t e = cudaMallocAsync(&base, bytes, ctx->stream);
   if (e != cudaSuccess) {
@@ -263,9 +314,7 @@ static int set_alloc(ssrlcv_b200_ctx* ctx, uint64_t n, ssrlcv_b200_set** out, bo
   s->loc = reinterpret_cast<float2*>(s->wcol + np);
   s->sigtheta = s->loc + np;
   s->wmax = reinterpret_cast<int32_t*>(s->sigtheta + np);
-  s->meta = s->wmax + np / kChunk;
-  s->orig = with_orig ? reinterpret_cast<uint32_t*>(s->meta + 64) : nullptr;   // meta: 16 B used, 256 B reserved
-  cudaMemsetAsync(s->wmax, 0, (np / kChunk) * 4 + 16, ctx->stream);
+  s->orig = with_orig ? reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s->wmax) + wmax_bytes) : nullptr;
   rc = encode_map(ctx, &s->map_a, s->desc, np, kDescBytes, kBM, CU_TENSOR_MAP_SWIZZLE_128B);
   if (!rc) rc = encode_map(ctx, &s->map_b, s->desc, np, kDescBytes, kBN, CU_TENSOR_MAP_SWIZZLE_128B);
   if (!rc) rc = encode_map(ctx, &s->map_ext, s->ext, np, kExtBytes, kBN, CU_TENSOR_MAP_SWIZZLE_32B);
@@ -273,29 +322,57 @@ static int set_alloc(ssrlcv_b200_ctx* ctx, uint64_t n, ssrlcv_b200_set** out, bo
   *out = s;
   return 0;
 }
-// After the last pack launch of a set: its meta scalars travel to the pinned slot (read by set_resolve).
+// After the last pack launch of a set: the event set_resolve waits for before it reads the verdict from the pinned word.
 static int set_finish(ssrlcv_b200_ctx* ctx, ssrlcv_b200_set* s) {
-  cudaMemcpyAsync(s->h_mm, s->meta, 16, cudaMemcpyDeviceToHost, ctx->stream);
   cudaEventRecord(s->ready, ctx->stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ctx, static_cast<int>(e), "pack: %s", cudaGetErrorString(e));
   return 0;
 }
+// rows [row0, row0 + n_rows) of `s` <- n records at feat_dev (+ zero padding); row0 % 32 == 0, n_rows % 32 == 0
+static PackJob pack_job(const ssrlcv_b200_set* s, const void* feat_dev, uint64_t n, uint64_t n_rows, uint64_t row0) {
+  PackJob j;
+  j.in = static_cast<const RefFeature*>(feat_dev);
+  j.n = n; j.n_rows = n_rows;
+  j.desc = s->desc + row0 * kDescBytes; j.ext = s->ext + row0 * kExtBytes;
+  j.norm = s->norm + row0; j.wcol = s->wcol + row0; j.wmax = s->wmax + row0 / kChunk;
+  j.loc = s->loc + row0; j.sigtheta = s->sigtheta + row0;
+  j.meta = s->meta; j.h_meta = s->h_mm;
+  j.win_begin = 0;
+  return j;
+}
 
-// Enqueue-only: nothing here waits for the device.  Whether every norm of the set fits the fold digits, which selects the
-// kernel variant, is copied to a pinned slot and read by set_resolve() when a match first needs it.
-int ssrlcv_b200_pack(ssrlcv_b200_ctx* ctx, const void* features_dev, uint64_t n, ssrlcv_b200_set** out) {
-  if (!ctx || !out || (n && !features_dev) || n > 0x7fffffffull) return fail(ctx, SSRLCV_B200_EINVAL, "pack: bad arguments");
+// Enqueue-only: nothing here waits for the device, and the pack kernel is the only node that enters the stream.  Whether
+// every norm of a set fits the fold digits, which selects the kernel variant, is read by set_resolve() from the set's pinned
+// word when a match first needs it.  All sets of the call share ONE launch (N-view jobs: one launch for all views).
+int ssrlcv_b200_pack_batch(ssrlcv_b200_ctx* ctx, uint32_t n_sets, const void* const* features_dev, const uint64_t* n,
+                           ssrlcv_b200_set** out) {
+  if (!ctx || (n_sets && (!features_dev || !n || !out))) return fail(ctx, SSRLCV_B200_EINVAL, "pack_batch: bad arguments");
+  for (uint32_t i = 0; i < n_sets; ++i) {
+    out[i] = nullptr;
+    if ((n[i] && !features_dev[i]) || n[i] > 0x7fffffffull) return fail(ctx, SSRLCV_B200_EINVAL, "pack_batch: set %u: bad arguments", i);
+  }
   CU(cudaSetDevice(ctx->device));
-  ssrlcv_b200_set* s = nullptr;
-  int rc = set_alloc(ctx, n, &s);
-  if (rc) return rc;
-  launch_pack(ctx->stream, features_dev, n, s->n_pad, 0, *s, s->meta, ctx->sm_count);
-  ctx->launches += 1;
-  rc = set_finish(ctx, s);
-  if (rc) { ssrlcv_b200_set_free(s); return rc; }
-  *out = s;
+  std::vector<PackJob> jobs(n_sets);
+  int rc = 0;
+  for (uint32_t i = 0; i < n_sets && !rc; ++i) {
+    rc = set_alloc(ctx, n[i], &out[i]);
+    if (!rc) jobs[i] = pack_job(out[i], features_dev[i], n[i], out[i]->n_pad, 0);
+  }
+  if (!rc) {
+    launch_pack(ctx->stream, jobs.data(), n_sets, ctx->sm_count, &ctx->launches);
+    for (uint32_t i = 0; i < n_sets && !rc; ++i) rc = set_finish(ctx, out[i]);
+  }
+  if (rc) {
+    for (uint32_t i = 0; i < n_sets; ++i) { ssrlcv_b200_set_free(out[i]); out[i] = nullptr; }
+    return rc;
+  }
   return 0;
+}
+
+int ssrlcv_b200_pack(ssrlcv_b200_ctx* ctx, const void* features_dev, uint64_t n, ssrlcv_b200_set** out) {
+  if (!ctx || !out) return fail(ctx, SSRLCV_B200_EINVAL, "pack: bad arguments");
+  return ssrlcv_b200_pack_batch(ctx, 1, &features_dev, &n, out);
 }
 
 // first use of a set's norm range on the host: wait for its pack (normally long finished)
@@ -306,6 +383,16 @@ static int set_resolve(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* cs) {
   s->fold_ok = s->h_mm[0] == 0;
   s->resolved = true;
   return 0;
+}
+
+// the same without waiting: true if the verdict is known now
+static bool set_try_resolve(const ssrlcv_b200_set* cs) {
+  ssrlcv_b200_set* s = const_cast<ssrlcv_b200_set*>(cs);
+  if (s->resolved) return true;
+  if (cudaEventQuery(s->ready) != cudaSuccess) { cudaGetLastError(); return false; }
+  s->fold_ok = s->h_mm[0] == 0;
+  s->resolved = true;
+  return true;
 }
 
 static int pack_host_async(ssrlcv_b200_ctx* ctx, const void* features_host, uint64_t n, ssrlcv_b200_set** out) {
@@ -329,13 +416,18 @@ uint64_t ssrlcv_b200_set_size(const ssrlcv_b200_set* s) { return s ? s->n : 0; }
 const float* ssrlcv_b200_set_loc(const ssrlcv_b200_set* s) { return s ? reinterpret_cast<const float*>(s->loc) : nullptr; }
 void ssrlcv_b200_set_free(ssrlcv_b200_set* s) {
   if (!s) return;
-  cudaSetDevice(s->ctx->device);
-  if (s->sorted) { ssrlcv_b200_set_free(s->sorted); s->sorted = nullptr; }
-  if (s->desc) cudaFreeAsync(s->desc, s->ctx->stream);   // stream-ordered: every kernel that reads the set was enqueued before this
-  if (s->ready) {
-    // the slot's D2H was enqueued before this point; a later pack that reuses it is ordered after it on the same stream
-    s->ctx->free_slots.push_back(ssrlcv_b200_ctx::PackSlot{s->h_mm, s->ready});
+  ssrlcv_b200_ctx* ctx = s->ctx;
+  cudaSetDevice(ctx->device);
+  if (!s->is_view && !ctx->pending.empty()) {
+    // a seed pass that still awaits its verdict reads this set: settle it while the set is alive
+    bool touched = false;
+    for (const auto& p : ctx->pending) touched |= p.q == s || p.seed == s;
+    if (touched) { bool redone = false; verify_pending(ctx, &redone); }
   }
+  if (s->is_view) return;                              // borrowed rows of another set (match_host_streamed): nothing to release
+  if (s->sorted) { ssrlcv_b200_set_free(s->sorted); s->sorted = nullptr; }
+  if (s->desc) cudaFreeAsync(s->desc, ctx->stream);   // stream-ordered: every kernel that reads the set was enqueued before this
+  if (s->ready) ctx->free_slots.push_back(ssrlcv_b200_ctx::PackSlot{s->h_mm, s->ready, s->meta});
   delete s;
 }
 
@@ -477,32 +569,44 @@ static int32_t d2_cap_of(float abs_thr) {
 static int sorted_of(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* ct, const ssrlcv_b200_set** out) {
   ssrlcv_b200_set* t = const_cast<ssrlcv_b200_set*>(ct);
   if (t->sorted) { *out = t->sorted; return 0; }
+  int rc = set_resolve(ctx, t);                            // same rows, same fold verdict: the copy starts out resolved
+  if (rc) return rc;
   ssrlcv_b200_set* s2 = nullptr;
-  int rc = set_alloc(ctx, t->n, &s2, true);
+  rc = set_alloc(ctx, t->n, &s2, true);
   if (rc) return rc;
   const size_t n4 = ((static_cast<size_t>(t->n) * 4 + 255) / 256) * 256;
   const size_t temp = sort_x_temp_bytes(static_cast<uint32_t>(t->n));
   rc = ws_reserve(ctx, ctx->sortws, 4 * n4 + temp + 256);
   if (rc) { ssrlcv_b200_set_free(s2); return rc; }
   uint8_t* w = static_cast<uint8_t*>(ctx->sortws.p);
-  cudaError_t e = launch_sort_gather(ctx->stream, *t, *s2, reinterpret_cast<uint32_t*>(w), reinterpret_cast<uint32_t*>(w + n4),
-                                     reinterpret_cast<uint32_t*>(w + 2 * n4), reinterpret_cast<uint32_t*>(w + 3 * n4), w + 4 * n4, temp);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(s2->meta, t->meta, 16, cudaMemcpyDeviceToDevice, ctx->stream);   // same rows, same fold verdict
+  cudaError_t e = cudaMemsetAsync(s2->wmax, 0, (s2->n_pad / kChunk) * 4, ctx->stream);   // the gather accumulates the window bounds with atomicMax
+  if (e == cudaSuccess)
+    e = launch_sort_gather(ctx->stream, *t, *s2, reinterpret_cast<uint32_t*>(w), reinterpret_cast<uint32_t*>(w + n4),
+                           reinterpret_cast<uint32_t*>(w + 2 * n4), reinterpret_cast<uint32_t*>(w + 3 * n4), w + 4 * n4, temp);
+  if (e == cudaSuccess && !t->fold_ok) {
+    e = cudaMemsetAsync(s2->meta, 1, sizeof(int32_t), ctx->stream);
+    s2->h_mm[0] = 1;
+  }
   if (e != cudaSuccess) { ssrlcv_b200_set_free(s2); return fail(ctx, static_cast<int>(e), "sorted copy: %s", cudaGetErrorString(e)); }
   ctx->launches += 3;
   rc = set_finish(ctx, s2);
   if (rc) { ssrlcv_b200_set_free(s2); return rc; }
+  s2->fold_ok = t->fold_ok; s2->resolved = true;
   t->sorted = s2;
   *out = s2;
   return 0;
 }
 
 // One pair of a batch: inputs, and (after engine_enqueue) where its keys are.
+static inline int engine_of(const ssrlcv_b200_ctx* ctx) {
+  return ctx->knob[SSRLCV_B200_TUNE_CROSSCHECK_SIMT] == 1 ? SSRLCV_B200_ENGINE_SIMT : SSRLCV_B200_ENGINE_TCGEN05;
+}
+
 struct PairWork {
   const ssrlcv_b200_set* q = nullptr;
   const ssrlcv_b200_set* t = nullptr;
   MaskParams mp;
-  int engine = 0;
+  int engine = 0;                 // filled by engine_enqueue (the context's cross-check knob)
   uint64_t target_offset = 0;
   float abs_thr = 0.f;
   const float* seed = nullptr;    // seed distances of the query set (device) when the ratio test will drop what exceeds it
@@ -527,6 +631,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     SmaxArgs& a = p.a;
     memset(&a, 0, sizeof a);
     p.optimistic_fold = false;
+    p.engine = engine_of(ctx);
     a.nq = static_cast<uint32_t>(p.q->n); a.nt = static_cast<uint32_t>(p.t->n); a.nq_pad = static_cast<uint32_t>(p.q->n_pad);
     a.n_qtiles = (a.nq + kBM - 1) / kBM;
     a.n_ttiles = (a.nt + kBN - 1) / kBN;
@@ -541,7 +646,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     if (p.engine != SSRLCV_B200_ENGINE_SIMT && tiles != 0 && p.mp.kind == SSRLCV_B200_MASK_DOUBLE && p.seed == nullptr && !p.t->is_view) {
       // worth its three launches (~40 us, once per target set) only for pairs whose matcher runs much longer than that
       bool use_sorted = a.nt >= 16384 && static_cast<uint64_t>(a.nq) * a.nt >= (1ull << 28);
-      if (const char* so = getenv("SSRLCV_B200_SORTED")) use_sorted = so[0] != '0';     // "0" never / "1" always (A/B timing, tests)
+      if (ctx->knob[SSRLCV_B200_TUNE_SORTED_TARGETS] >= 0) use_sorted = ctx->knob[SSRLCV_B200_TUNE_SORTED_TARGETS] != 0;
       if (use_sorted) {
         int rc = sorted_of(ctx, p.t, &p.tt);
         if (rc) return rc;
@@ -559,11 +664,10 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       // bound reaches a running best), which serves any norm range.  Measured at 65 536 x 65 536 (profiles/r1f_fold_ab.txt):
       // fold 0.371 ms, no-fold 0.431 ms -- with four MMAs the tile period drops below the epilogue's own time per tile and
       // every rare bookkeeping event of any of the 8 epilogue warps stalls the two-accumulator hand-off; the fifth MMA is the
-      // slack that hides them.  SSRLCV_B200_FOLD=0|1 forces a variant (tests, A/B timing).
-      bool fold = true;
-      if (const char* f = getenv("SSRLCV_B200_FOLD")) fold = f[0] != '0';
+      // slack that hides them.  ssrlcv_b200_tune(SSRLCV_B200_TUNE_FOLD) forces a variant (tests, A/B timing).
+      bool fold = ctx->knob[SSRLCV_B200_TUNE_FOLD] != 0;
       if (fold) {
-        if (p.t->resolved || !optimistic) {
+        if (set_try_resolve(p.t) || !optimistic) {
           int rc = set_resolve(ctx, p.t);
           if (rc) return rc;
           fold = p.t->fold_ok;
@@ -574,7 +678,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       }
       // bookkeeping regime (smax_tc.cu): exact column masks for thresholded searches and short target sets
       bool colmask = a.d2_cap != 0x7fffffff || a.q_seed != nullptr || a.n_ttiles < 64;
-      if (const char* c = getenv("SSRLCV_B200_COLMASK")) colmask = c[0] != '0';   // A/B timing, tests
+      if (ctx->knob[SSRLCV_B200_TUNE_COLUMN_MASKS] >= 0) colmask = ctx->knob[SSRLCV_B200_TUNE_COLUMN_MASKS] != 0;   // A/B timing, tests
       Group& g = groups[p.mp.kind * 4 + (fold ? 2 : 0) + (colmask ? 1 : 0)];
       a.tile_begin = g.total;
       g.total += tiles;
@@ -604,14 +708,18 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
   int rc = ws_reserve(ctx, ctx->keys, keys_total * sizeof(uint64_t));
   if (!rc) rc = ws_reserve(ctx, ctx->flagged, keys_total * sizeof(uint32_t));
   if (!rc && qmask_total) rc = ws_reserve(ctx, ctx->qmask, qmask_total * sizeof(float4));
+  if (!rc && n_tc) rc = ws_reserve_zero(ctx, ctx->nflag, (static_cast<size_t>(n_tc) + 1) * sizeof(uint32_t));
   if (rc) return rc;
   for (uint32_t i = 0; i < n; ++i) {
     SmaxArgs& a = w[i].a;
     a.keys = static_cast<uint64_t*>(ctx->keys.p) + keys_off[i];
     a.flagged = static_cast<uint32_t*>(ctx->flagged.p) + keys_off[i];
+    // The tensor-core kernel writes every key slot of every query tile itself (units that end a tile also mark the slots
+    // no unit owns); only pairs it never sees -- empty target sets, whose single slot must read "no candidate" -- are preset.
+    const bool tc = w[i].engine != SSRLCV_B200_ENGINE_SIMT && a.n_qtiles != 0 && a.n_ttiles != 0;
+    if (!tc && a.nt == 0 && a.nq_pad)
+      CU(cudaMemsetAsync(a.keys, 0xFF, static_cast<size_t>(a.n_splits) * a.nq_pad * sizeof(uint64_t), ctx->stream));
   }
-  // every key slot starts as "no candidate" (kKeyNone is all ones): slots a query tile does not use, empty target sets
-  if (keys_total) CU(cudaMemsetAsync(ctx->keys.p, 0xFF, keys_total * sizeof(uint64_t), ctx->stream));
   // ---- per-query mask state, once per masked pair (all padded rows: loc = 0 there)
   for (uint32_t i = 0; i < n; ++i) {
     PairWork& p = w[i];
@@ -621,40 +729,44 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     p.a.q_mask = qm;
     ctx->launches += 1;
   }
-  // ---- tensor-core launches: one per (mask kind, fold variant) group
+  // ---- tensor-core launches: one per (mask kind, fold variant, bookkeeping regime) group
   if (n_tc) {
-    // staged blob: [SmaxJob x n_tc][tie-list counters, u32 x n_tc, zero]
+    // The job table of a single pair rides in the kernel's parameter block; several pairs are staged through a pinned ring
+    // (one small copy for the whole batch).  Tie counters: persistent zero words, [0] is the tie kernel's `done` ticket.
+    uint32_t* d_nflag = static_cast<uint32_t*>(ctx->nflag.p);
     ssrlcv_b200_ctx::Staged* st = nullptr;
-    const size_t blob = static_cast<size_t>(n_tc) * (sizeof(SmaxJob) + sizeof(uint32_t));
-    rc = stage_acquire(ctx, blob, &st);
-    if (rc) return rc;
-    SmaxJob* hj = static_cast<SmaxJob*>(st->h);
-    uint32_t* h_nflag = reinterpret_cast<uint32_t*>(hj + n_tc);
-    uint32_t* d_nflag = reinterpret_cast<uint32_t*>(static_cast<SmaxJob*>(st->d) + n_tc);
+    SmaxJob* hj = nullptr;
+    SmaxJob single;
+    if (n_tc > 1) {
+      rc = stage_acquire(ctx, static_cast<size_t>(n_tc) * sizeof(SmaxJob), &st);
+      if (rc) return rc;
+      hj = static_cast<SmaxJob*>(st->h);
+    }
     uint32_t at = 0;
     for (Group& g : groups)
       for (uint32_t i : g.idx) {
-        h_nflag[at] = 0;
-        w[i].a.n_flagged = d_nflag + at;
-        SmaxJob& j = hj[at++];
+        w[i].a.n_flagged = d_nflag + 1 + at;
+        SmaxJob& j = n_tc > 1 ? hj[at] : single;
+        ++at;
         j.map_q = w[i].q->map_a; j.map_t = w[i].tt->map_b; j.map_text = w[i].tt->map_ext;
         j.a = w[i].a;
       }
-    rc = stage_upload(ctx, st, blob);
-    if (rc) return rc;
-    unsigned long long* timing = nullptr;
-    if (const char* tp = getenv("SSRLCV_B200_TIMING"))     // diagnostics: device buffer address (hex) for cycle counters
-      timing = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 16));
+    if (n_tc > 1) {
+      rc = stage_upload(ctx, st, static_cast<size_t>(n_tc) * sizeof(SmaxJob));
+      if (rc) return rc;
+    }
     at = 0;
     for (int gi = 0; gi < 12; ++gi) {
       Group& g = groups[gi];
       if (g.idx.empty()) continue;
       SmaxBatch b;
-      b.jobs = static_cast<const SmaxJob*>(st->d) + at;
+      memset(&b, 0, sizeof b);
+      if (n_tc > 1) b.jobs = static_cast<const SmaxJob*>(st->d) + at;
+      else { b.jobs = nullptr; b.inline_job = single; }
       b.n_jobs = static_cast<uint32_t>(g.idx.size());
       b.n_ctas = w[g.idx[0]].a.n_ctas;
       b.total_tiles = g.total;
-      b.timing = timing;
+      b.timing = ctx->knob[SSRLCV_B200_TUNE_TIMING_BUFFER] > 0 ? reinterpret_cast<unsigned long long*>(ctx->knob[SSRLCV_B200_TUNE_TIMING_BUFFER]) : nullptr;
       if (ctx->profiling) {
         if (ctx->prof_used == ctx->prof_events.size()) {
           cudaEvent_t e0, e1;
@@ -666,7 +778,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       cudaError_t e = launch_smax(ctx->stream, b, gi / 4, (gi & 2) != 0, (gi & 1) != 0);
       if (e != cudaSuccess) return fail(ctx, static_cast<int>(e), "smax launch: %s", cudaGetErrorString(e));
       if (ctx->profiling) { CU(cudaEventRecord(ctx->prof_events[ctx->prof_used].second, ctx->stream)); ctx->prof_used++; }
-      launch_exact_list(ctx->stream, b.jobs, b.n_jobs, gi / 4, ctx->sm_count);
+      launch_exact_list(ctx->stream, b, d_nflag, gi / 4, ctx->sm_count);
       ctx->launches += 2;
       at += b.n_jobs;
     }
@@ -682,18 +794,53 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
   return 0;
 }
 
-int ssrlcv_b200_seed_distances(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* query, const ssrlcv_b200_set* seed, float* out_dev, int engine) {
-  if (!ctx || !query || !seed || (query->n && !out_dev)) return fail(ctx, SSRLCV_B200_EINVAL, "seed_distances: bad arguments");
-  CU(cudaSetDevice(ctx->device));
+// enqueue one seed pass; `optimistic`: do not wait for the seed set's pack (see engine_enqueue)
+static int seed_pass_enqueue(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* query, const ssrlcv_b200_set* seed, float* out_dev, bool* optimistic) {
   PairWork w;
   memset(&w.mp, 0, sizeof w.mp);
-  w.q = query; w.t = seed; w.engine = engine; w.abs_thr = FLT_MAX;
-  int rc = engine_enqueue(ctx, &w, 1, nullptr);
+  w.q = query; w.t = seed; w.abs_thr = FLT_MAX;
+  int rc = engine_enqueue(ctx, &w, 1, optimistic);
   if (rc) return rc;
   if (w.a.nq) { launch_seed_from_keys(ctx->stream, w.a.keys, w.a.nq, w.a.nq_pad, w.a.n_splits, out_dev); ctx->launches += 1; }
   CU(cudaGetLastError());
   return 0;
 }
+
+// Enqueue-only.  If the seed set's pack has not reported back yet the fold variant is launched on the (almost always right)
+// guess that its norms fit the fold digits, and the pass is remembered: the next synchronisation point of the context
+// (ssrlcv_b200_match*, ssrlcv_b200_synchronize, or the release of either set) checks the verdict and redoes the pass with
+// the other variant if the guess was wrong -- ssrlcv_b200_match* then also redo the matches that consumed the distances.
+int ssrlcv_b200_seed_distances(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* query, const ssrlcv_b200_set* seed, float* out_dev) {
+  if (!ctx || !query || !seed || (query->n && !out_dev)) return fail(ctx, SSRLCV_B200_EINVAL, "seed_distances: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  bool optimistic = false;
+  int rc = seed_pass_enqueue(ctx, query, seed, out_dev, &optimistic);
+  if (rc) return rc;
+  if (optimistic) ctx->pending.push_back(ssrlcv_b200_ctx::PendingSeed{query, seed, out_dev});
+  return 0;
+}
+
+}  // extern "C"
+
+// Called right after a synchronisation of the context's stream: every pack has reported, so every optimistic seed pass can
+// be checked.  *redone = true: some pass was enqueued again (the caller synchronises again; whoever consumed the
+// distances in between must be redone as well).
+static int verify_pending(ssrlcv_b200_ctx* ctx, bool* redone) {
+  if (ctx->pending.empty()) return 0;
+  std::vector<ssrlcv_b200_ctx::PendingSeed> todo;
+  todo.swap(ctx->pending);
+  for (const auto& p : todo) {
+    int rc = set_resolve(ctx, p.seed);
+    if (rc) return rc;
+    if (p.seed->fold_ok || p.q->n == 0 || p.seed->n == 0) continue;
+    rc = seed_pass_enqueue(ctx, p.q, p.seed, p.out, nullptr);
+    if (rc) return rc;
+    *redone = true;
+  }
+  return 0;
+}
+
+extern "C" {
 
 static size_t out_elt(int kind) {
   switch (kind) {
@@ -715,9 +862,9 @@ struct FinalizeWork {
   void* out_dev;
 };
 
-// enqueue thresholds / writers / compaction of n pairs in two launches; the number of records of pair i lands in
-// (*totals_dev)[i] (device memory of the staged blob, valid until the ring slot comes round again)
-static int finalize_enqueue(ssrlcv_b200_ctx* ctx, const FinalizeWork* fw, uint32_t n, const uint32_t** totals_dev) {
+// enqueue thresholds / writers / compaction of n pairs in ONE launch; the number of records of pair i lands in totals_host[i]
+// (pinned, device-mapped host memory, written by the kernel itself: valid after the stream has been synchronised)
+static int finalize_enqueue(ssrlcv_b200_ctx* ctx, const FinalizeWork* fw, uint32_t n, uint32_t* totals_host) {
   if (n == 0) return 0;
   size_t blocks_total = 0;
   uint32_t max_nq = 0;
@@ -725,18 +872,23 @@ static int finalize_enqueue(ssrlcv_b200_ctx* ctx, const FinalizeWork* fw, uint32
     const uint32_t nq = static_cast<uint32_t>(fw[i].q->n);
     blocks_total += (nq + 255) / 256;
     if (nq > max_nq) max_nq = nq;
+    totals_host[i] = 0;                                    // pairs without queries launch no block
   }
-  int rc = ws_reserve(ctx, ctx->counts, (blocks_total + 1) * sizeof(uint32_t));
+  int rc = ws_reserve_zero(ctx, ctx->fstate, (blocks_total + 1) * sizeof(uint64_t));
+  if (!rc) rc = ws_reserve_zero(ctx, ctx->tickets, static_cast<size_t>(n) * sizeof(uint32_t));
   if (rc) return rc;
+  if (++ctx->epoch == 0) ctx->epoch = 1;
+  // the job table of a single pair rides in the kernel's parameter block; several pairs are staged (one small copy)
   ssrlcv_b200_ctx::Staged* st = nullptr;
-  // staged blob: [FinalizeArgs x n][record counts, u32 x n, zero: pairs without queries write nothing]
-  const size_t blob = static_cast<size_t>(n) * (sizeof(FinalizeArgs) + sizeof(uint32_t));
-  rc = stage_acquire(ctx, blob, &st);
-  if (rc) return rc;
-  FinalizeArgs* hf = static_cast<FinalizeArgs*>(st->h);
-  uint32_t* h_totals = reinterpret_cast<uint32_t*>(hf + n);
-  uint32_t* d_totals = reinterpret_cast<uint32_t*>(static_cast<FinalizeArgs*>(st->d) + n);
-  *totals_dev = d_totals;
+  FinalizeBatch fb;
+  memset(&fb, 0, sizeof fb);
+  FinalizeArgs* hf = &fb.inline_job;
+  if (n > 1) {
+    rc = stage_acquire(ctx, static_cast<size_t>(n) * sizeof(FinalizeArgs), &st);
+    if (rc) return rc;
+    hf = static_cast<FinalizeArgs*>(st->h);
+    fb.jobs = static_cast<const FinalizeArgs*>(st->d);
+  }
   size_t blocks_at = 0;
   for (uint32_t i = 0; i < n; ++i) {
     const FinalizeWork& x = fw[i];
@@ -752,18 +904,24 @@ static int finalize_enqueue(ssrlcv_b200_ctx* ctx, const FinalizeWork* fw, uint32
     f.q_sigtheta = x.q->sigtheta; f.t_sigtheta = x.t ? x.t->sigtheta : nullptr;
     f.q_desc = x.q->desc; f.t_desc = x.t ? x.t->desc : nullptr;
     f.out = x.out_dev;
-    f.block_counts = static_cast<uint32_t*>(ctx->counts.p) + blocks_at;
-    f.total = d_totals + i;
-    h_totals[i] = 0;
+    f.state = static_cast<uint64_t*>(ctx->fstate.p) + blocks_at;
+    f.ticket = static_cast<uint32_t*>(ctx->tickets.p) + i;
+    f.epoch = ctx->epoch;
+    f.total = nullptr;
+    f.total_host = totals_host + i;
     blocks_at += (f.nq + 255) / 256;
   }
-  rc = stage_upload(ctx, st, blob);
-  if (rc) return rc;
+  if (n > 1) {
+    rc = stage_upload(ctx, st, static_cast<size_t>(n) * sizeof(FinalizeArgs));
+    if (rc) return rc;
+  }
   if (max_nq) {
     for (uint32_t at = 0; at < n; at += 32768) {           // gridDim.y limit
       const uint32_t m = n - at < 32768 ? n - at : 32768;
-      launch_finalize(ctx->stream, static_cast<const FinalizeArgs*>(st->d) + at, m, max_nq);
-      ctx->launches += 2;
+      FinalizeBatch part = fb;
+      if (n > 1) part.jobs = fb.jobs + at;
+      launch_finalize(ctx->stream, part, m, max_nq);
+      ctx->launches += 1;
     }
   }
   CU(cudaGetLastError());
@@ -795,15 +953,16 @@ int ssrlcv_b200_match_batch(ssrlcv_b200_ctx* ctx, uint32_t n_pairs, const ssrlcv
   }
   if (ctx->hostpin.cap < n_pairs * sizeof(uint32_t)) {
     if (ctx->hostpin.p) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFreeHost(ctx->hostpin.p)); ctx->hostpin.p = nullptr; ctx->hostpin.cap = 0; }
-    CU(cudaMallocHost(&ctx->hostpin.p, n_pairs * sizeof(uint32_t) * 2));
+    CU(cudaHostAlloc(&ctx->hostpin.p, n_pairs * sizeof(uint32_t) * 2, cudaHostAllocMapped | cudaHostAllocPortable));
     ctx->hostpin.cap = n_pairs * sizeof(uint32_t) * 2;
   }
+  uint32_t* totals = static_cast<uint32_t*>(ctx->hostpin.p);
   std::vector<PairWork> w(n_pairs);
   std::vector<FinalizeWork> fw(n_pairs);
-  for (int attempt = 0; attempt < 2; ++attempt) {
+  for (int attempt = 0; attempt < 3; ++attempt) {
     for (uint32_t i = 0; i < n_pairs; ++i) {
       fill_mask(&params[i], w[i].mp);
-      w[i].q = queries[i]; w[i].t = targets[i]; w[i].engine = params[i].engine; w[i].abs_thr = params[i].absolute_threshold;
+      w[i].q = queries[i]; w[i].t = targets[i]; w[i].abs_thr = params[i].absolute_threshold;
       // invalid entries are compacted away: candidates the seed-ratio test would reject need not be tracked (matcher.cuh)
       const float* sd = seed_dist_dev ? seed_dist_dev[i] : nullptr;
       w[i].seed = (sd && params[i].compact) ? sd : nullptr;
@@ -815,23 +974,24 @@ int ssrlcv_b200_match_batch(ssrlcv_b200_ctx* ctx, uint32_t n_pairs, const ssrlcv
     for (uint32_t i = 0; i < n_pairs; ++i)
       fw[i] = FinalizeWork{&params[i], queries[i], w[i].a.keys, w[i].a.n_splits, w[i].a.nq_pad, targets[i]->loc, targets[i],
                            seed_dist_dev ? seed_dist_dev[i] : nullptr, out_dev[i]};
-    const uint32_t* totals = nullptr;
-    rc = finalize_enqueue(ctx, fw.data(), n_pairs, &totals);
+    rc = finalize_enqueue(ctx, fw.data(), n_pairs, totals);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(ctx->hostpin.p, totals, n_pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));               // the record counts were written to pinned memory by the kernel
     CU(cudaGetLastError());
-    if (!optimistic) break;
-    // every pack has reported by now: were all the fold variants launched above the right ones?
+    // every pack has reported by now: seed passes launched on a guess (they may have fed this batch), then this batch's own
     bool redo = false;
-    for (uint32_t i = 0; i < n_pairs; ++i) {
-      rc = set_resolve(ctx, targets[i]);
-      if (rc) return rc;
-      if (w[i].optimistic_fold && queries[i]->n && targets[i]->n && !targets[i]->fold_ok) redo = true;
+    rc = verify_pending(ctx, &redo);
+    if (rc) return rc;
+    if (optimistic) {
+      for (uint32_t i = 0; i < n_pairs; ++i) {
+        rc = set_resolve(ctx, targets[i]);
+        if (rc) return rc;
+        if (w[i].optimistic_fold && queries[i]->n && targets[i]->n && !targets[i]->fold_ok) redo = true;
+      }
     }
     if (!redo) break;                                    // otherwise: once more, every set resolved, right variants
   }
-  for (uint32_t i = 0; i < n_pairs; ++i) n_out[i] = static_cast<const uint32_t*>(ctx->hostpin.p)[i];
+  for (uint32_t i = 0; i < n_pairs; ++i) n_out[i] = totals[i];
   return 0;
 }
 
@@ -859,7 +1019,7 @@ int ssrlcv_b200_match_candidates_seeded(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_
   CU(cudaSetDevice(ctx->device));
   PairWork w;
   fill_mask(p, w.mp);
-  w.q = query; w.t = shard; w.engine = p->engine; w.target_offset = target_offset; w.abs_thr = p->absolute_threshold;
+  w.q = query; w.t = shard; w.target_offset = target_offset; w.abs_thr = p->absolute_threshold;
   // the merged winner is dropped when it fails the seed-ratio test, so no shard needs candidates beyond that bound (matcher.cuh)
   w.seed = (seed_dist_dev && p->compact) ? seed_dist_dev : nullptr;
   w.seed_ratio = ratio_threshold(p->out_kind, p->mask_kind, p->relative_threshold);
@@ -885,10 +1045,8 @@ int ssrlcv_b200_finalize_candidates(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_matc
   // keys_dev is [n_shards][nq] (dense)
   FinalizeWork fw{p, query, keys_dev, n_shards, static_cast<uint32_t>(query->n), reinterpret_cast<const float2*>(target_loc_dev), nullptr,
                   seed_dist_dev, out_dev};
-  const uint32_t* total = nullptr;
-  rc = finalize_enqueue(ctx, &fw, 1, &total);
+  rc = finalize_enqueue(ctx, &fw, 1, ctx->h_scalars + 1);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(ctx->h_scalars + 1, total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaGetLastError());
   *n_out = ctx->h_scalars[1];
@@ -916,13 +1074,13 @@ static int make_view(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* parent, uint64
 // kMinChunkRows, at most kMaxChunks.  Every chunk costs a pack + matcher + tie-list + key-reduction launch (~25 us of
 // device time, ~30 us of host time), so few, large chunks win: measured at 65 536 x 65 536 (tools/e2e_chunks.sh,
 // profiles/r1f_e2e_chunks.txt): one piece 0.94 ms, 2 + 2 chunks 0.80 ms, 4 + 4 chunks 0.94 ms, 8 + 8 chunks 1.10 ms.
-// SSRLCV_B200_HOST_CHUNK_ROWS="<rows>" or "<query rows>,<target rows>" overrides (0 = never cut; tests use tiny chunks).
-static uint64_t host_chunk_rows(uint64_t n, int which) {
+// ssrlcv_b200_tune(SSRLCV_B200_TUNE_HOST_CHUNK_{QUERY,TARGET}_ROWS) overrides (0 = never cut; tests use tiny chunks).
+static uint64_t host_chunk_rows(const ssrlcv_b200_ctx* ctx, uint64_t n, int which) {
   constexpr uint64_t kMinChunkRows = 16384, kMaxChunks = 2;
   uint64_t rows;
-  if (const char* e = getenv("SSRLCV_B200_HOST_CHUNK_ROWS")) {      // "<rows>" or "<query rows>,<target rows>"
-    const char* comma = strchr(e, ',');
-    rows = strtoull(which == 1 && comma ? comma + 1 : e, nullptr, 10);
+  const int64_t knob = ctx->knob[which == 1 ? SSRLCV_B200_TUNE_HOST_CHUNK_TARGET_ROWS : SSRLCV_B200_TUNE_HOST_CHUNK_QUERY_ROWS];
+  if (knob >= 0) {
+    rows = static_cast<uint64_t>(knob);
     if (rows == 0) return n ? ((n + kRowPad - 1) / kRowPad) * kRowPad : kRowPad;   // 0: never cut
   } else {
     uint64_t c = n / kMinChunkRows;
@@ -945,7 +1103,6 @@ static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_par
                                const void* target_host, uint64_t nt, const void* seed_host, uint64_t ns, void* out_host,
                                uint64_t* n_out, uint64_t q_rows, uint64_t t_rows) {
   CU(cudaSetDevice(ctx->device));
-  const auto host_t0 = std::chrono::steady_clock::now();
   if (!ctx->copy_stream) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   // Every exit after this point goes through cleanup(): on failure both streams are drained first, because copies from the
   // CALLER's host buffers may still be in flight and the caller is free to release them once we return.
@@ -1021,7 +1178,7 @@ static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_par
   ctx->launches += 1;
   PairWork w;
   fill_mask(p, w.mp);
-  w.engine = p->engine; w.abs_thr = p->absolute_threshold;
+  w.abs_thr = p->absolute_threshold;
   uint64_t q_arrived = 0, t_arrived = 0;                      // rows
   bool any_optimistic = false;
   for (size_t k = 0; k < order.size(); ++k) {
@@ -1031,8 +1188,8 @@ static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_par
     const bool last = r0 + rows >= set->n;
     const uint64_t cnt = last ? set->n - r0 : rows, pad = last ? set->n_pad - r0 : rows;
     CUS(cudaStreamWaitEvent(ctx->stream, ctx->copy_events[k], 0));
-    launch_pack(ctx->stream, (u.is_q ? up_q : up_t) + r0 * rec, cnt, pad, r0, *set, set->meta, ctx->sm_count);
-    ctx->launches += 1;
+    const PackJob pj = pack_job(set, (u.is_q ? up_q : up_t) + r0 * rec, cnt, pad, r0);
+    launch_pack(ctx->stream, &pj, 1, ctx->sm_count, &ctx->launches);
     ssrlcv_b200_set qv, tv;
     uint64_t q0 = 0, slot = 0;
     bool run = false;
@@ -1070,27 +1227,22 @@ static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_par
       ctx->launches += 1;
     }
     if (u.is_q && last && s) {                                 // every query is on the device: seed distances
-      rc = ssrlcv_b200_seed_distances(ctx, q, s, seed_dev, p->engine);
+      rc = ssrlcv_b200_seed_distances(ctx, q, s, seed_dev);
       if (rc) return cleanup(rc);
     }
   }
   FinalizeWork fw{p, q, ckeys, static_cast<uint32_t>(n_slots), static_cast<uint32_t>(nq), t->loc, t, s ? seed_dev : nullptr, out_dev};
-  const uint32_t* total = nullptr;
-  rc = finalize_enqueue(ctx, &fw, 1, &total);
+  rc = finalize_enqueue(ctx, &fw, 1, ctx->h_scalars + 2);
   if (rc) return cleanup(rc);
-  CUS(cudaMemcpyAsync(ctx->h_scalars + 2, total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  const auto host_t1 = std::chrono::steady_clock::now();
   CUS(cudaStreamSynchronize(ctx->stream));
-  if (getenv("SSRLCV_B200_DEBUG_HOST"))
-    fprintf(stderr, "match_host_streamed: %zu uploads, host enqueue %.1f us, wait %.1f us\n", order.size(),
-            std::chrono::duration<double, std::micro>(host_t1 - host_t0).count(),
-            std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t1).count());
   *n_out = ctx->h_scalars[2];
-  rc = set_resolve(ctx, t);
+  bool seeds_redone = false;
+  rc = verify_pending(ctx, &seeds_redone);
+  if (!rc) rc = set_resolve(ctx, t);
   if (rc) return cleanup(rc);
-  if (any_optimistic && !t->fold_ok) {
-    // some target norm does not fit the fold digits: the optimistic launches skipped their jobs.  Both sets are packed
-    // by now; redo the pair in one piece with the epilogue-add variant.
+  if (seeds_redone || (any_optimistic && !t->fold_ok)) {
+    // some norm does not fit the fold digits: the optimistic launches skipped their jobs (or ran on seed distances that
+    // have only now been computed).  Both sets are packed by now; redo the pair in one piece.
     rc = ssrlcv_b200_match(ctx, p, q, t, s ? seed_dev : nullptr, s ? nq : 0, out_dev, n_out);
     if (rc) return cleanup(rc);
   }
@@ -1116,10 +1268,11 @@ int ssrlcv_b200_match_host(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params*
   if ((n_query && !query_host) || (n_target && !target_host) || (seed_host == nullptr && n_seed)) return fail(ctx, SSRLCV_B200_EINVAL, "match_host: bad arguments");
   if (n_query > 0x7fffffffull || n_target > 0x7fffffffull || n_seed > 0x7fffffffull) return fail(ctx, SSRLCV_B200_EINVAL, "match_host: too many features");
   {
-    const uint64_t q_rows = host_chunk_rows(n_query, 0), t_rows = host_chunk_rows(n_target, 1);
+    const uint64_t q_rows = host_chunk_rows(ctx, n_query, 0), t_rows = host_chunk_rows(ctx, n_target, 1);
     // also for smaller seeded calls: the target set travels on the copy stream while the seed pass (queries x seed set) runs
-    const bool overlap_seed_pass = seed_host != nullptr && n_seed != 0 && n_target >= 8192 && getenv("SSRLCV_B200_HOST_CHUNK_ROWS") == nullptr;
-    if (n_query && n_target && p->engine != SSRLCV_B200_ENGINE_SIMT && (q_rows < n_query || t_rows < n_target || overlap_seed_pass))
+    const bool overlap_seed_pass = seed_host != nullptr && n_seed != 0 && n_target >= 8192 &&
+                                   ctx->knob[SSRLCV_B200_TUNE_HOST_CHUNK_QUERY_ROWS] < 0 && ctx->knob[SSRLCV_B200_TUNE_HOST_CHUNK_TARGET_ROWS] < 0;
+    if (n_query && n_target && engine_of(ctx) != SSRLCV_B200_ENGINE_SIMT && (q_rows < n_query || t_rows < n_target || overlap_seed_pass))
       return match_host_streamed(ctx, p, query_host, n_query, target_host, n_target, seed_host, n_seed, out_host, n_out, q_rows, t_rows);
   }
   rc = pack_host_async(ctx, query_host, n_query, &q);
@@ -1134,7 +1287,7 @@ int ssrlcv_b200_match_host(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params*
       seed_dev = reinterpret_cast<float*>(static_cast<uint8_t*>(ctx->scratch.p) + out_bytes);
     }
   }
-  if (!rc && s) rc = ssrlcv_b200_seed_distances(ctx, q, s, seed_dev, p->engine);
+  if (!rc && s) rc = ssrlcv_b200_seed_distances(ctx, q, s, seed_dev);
   if (!rc) rc = ssrlcv_b200_match(ctx, p, q, t, s ? seed_dev : nullptr, s ? n_query : 0, out_dev, n_out);
   if (!rc && *n_out) {
     cudaError_t e = cudaMemcpyAsync(out_host, out_dev, *n_out * elt, cudaMemcpyDeviceToHost, ctx->stream);
@@ -1184,12 +1337,15 @@ int ssrlcv_b200_sort(ssrlcv_b200_ctx* ctx, void* dmatches_dev, uint64_t n) {
   if (!ctx || (n && !dmatches_dev) || n > 0x7fffffffull) return fail(ctx, SSRLCV_B200_EINVAL, "sort: bad arguments");
   CU(cudaSetDevice(ctx->device));
   if (n < 2) return 0;
-  uint64_t p2 = 1;
-  while (p2 < n) p2 <<= 1;
-  int rc = ws_reserve(ctx, ctx->keys, p2 * sizeof(uint64_t));
+  const size_t kb = ((n * sizeof(uint64_t) + 255) / 256) * 256;
+  const size_t temp = sort_temp_bytes(static_cast<uint32_t>(n));
+  int rc = ws_reserve(ctx, ctx->sortws, 2 * kb + temp + 256);
   if (!rc) rc = ws_reserve(ctx, ctx->scratch, n * sizeof(RefDMatch));
   if (rc) return rc;
-  ctx->launches += launch_sort(ctx->stream, dmatches_dev, static_cast<uint32_t>(n), static_cast<uint64_t*>(ctx->keys.p), ctx->scratch.p);
+  uint8_t* w = static_cast<uint8_t*>(ctx->sortws.p);
+  cudaError_t e = launch_sort(ctx->stream, dmatches_dev, static_cast<uint32_t>(n), reinterpret_cast<uint64_t*>(w), reinterpret_cast<uint64_t*>(w + kb),
+                              w + 2 * kb, temp, ctx->scratch.p, &ctx->launches);
+  if (e != cudaSuccess) return fail(ctx, static_cast<int>(e), "sort: %s", cudaGetErrorString(e));
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaGetLastError());
   return 0;

@@ -5,7 +5,10 @@
 //   * writers for Match / DMatch / uint2_pair / FeatureMatch
 //   * stable compaction by query index == thrust::remove_if in validateMatches (ref: :31-135)
 //   * refineMatches / sortMatches / getRawMatches equivalents (ref: :137-160, :191-222, :257-280)
+// HBM/latency-bound record shuffling: 8 B x slots read and <= 48 B written per query.
 #include <cfloat>
+
+#include <cub/cub.cuh>
 
 #include "matcher.cuh"
 
@@ -21,7 +24,7 @@ __device__ __forceinline__ Decision decide(const FinalizeArgs& a, uint32_t i) {
   }
   Decision d;
   d.has = false; d.f = 0; d.cur = a.abs_thr;
-  if (key != kKeyNone) {
+  if (key < kKeyNeedsExact) {                                                  // neither "no candidate" nor an unresolved tie marker
     const float dist = static_cast<float>(static_cast<uint32_t>(key >> 37));   // exact: d2 < 2^24
     if (a.abs_thr > dist) { d.has = true; d.cur = dist; d.f = static_cast<uint32_t>(key); }
   }
@@ -36,60 +39,75 @@ __device__ __forceinline__ Decision decide(const FinalizeArgs& a, uint32_t i) {
   return d;
 }
 
-// Both kernels: grid = (blocks of 256 queries, jobs); `jobs` is device memory, one FinalizeArgs per pair of the batch.
-__global__ void __launch_bounds__(256) finalize_count_kernel(const FinalizeArgs* __restrict__ jobs) {
-  const FinalizeArgs a = jobs[blockIdx.y];
-  if (blockIdx.x * blockDim.x >= a.nq) return;
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool v = false;
-  if (i < a.nq) v = a.compact ? decide(a, i).valid : true;
-  const int c = __syncthreads_count(v);
-  if (threadIdx.x == 0) a.block_counts[blockIdx.x] = static_cast<uint32_t>(c);
-}
-
 __device__ __forceinline__ void store_keypoints(RefKeyPoint* kp, uint32_t qid, uint32_t tid, float2 ql, float2 tl) {
   kp[0].parentId = static_cast<int32_t>(qid); kp[0].pad_ = 0; kp[0].loc = ql;
   kp[1].parentId = static_cast<int32_t>(tid); kp[1].pad_ = 0; kp[1].loc = tl;
 }
 
-__global__ void __launch_bounds__(256) finalize_write_kernel(const FinalizeArgs* __restrict__ jobs) {
+__device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Thresholds, writers and the stable compaction in ONE pass.  grid = (blocks of 256 queries, jobs).  A block draws a ticket
+// (its position in scheduling order, so every block it will wait for is already running), decides its 256 queries,
+// publishes its count stamped with this call's epoch and sums the counts of the tickets before it -- they are published
+// without waiting for anything, so the wait is bounded by one block's decide().  Output order = ascending query index,
+// exactly thrust::remove_if's (ref: src/MatchFactory.cu:31-135).
+__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeBatch fb) {
   __shared__ uint32_t s_warp[8];
-  __shared__ uint32_t s_base;
-  const FinalizeArgs a = jobs[blockIdx.y];
-  if (blockIdx.x * blockDim.x >= a.nq) return;
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ uint32_t s_pre[8];
+  __shared__ uint32_t s_ticket;
+  const FinalizeArgs a = fb.jobs ? fb.jobs[blockIdx.y] : fb.inline_job;
+  const uint32_t nq = a.nq, n_blocks = (nq + 255) / 256;
+  if (blockIdx.x >= n_blocks) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // exclusive prefix of the preceding blocks' counts
-  uint32_t part = 0;
-  for (uint32_t b = threadIdx.x; b < blockIdx.x; b += blockDim.x) part += a.block_counts[b];
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-  if (lane == 0) s_warp[warp] = part;
-  __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t t = 0;
-    for (int w = 0; w < 8; ++w) t += s_warp[w];
-    s_base = t;
+    const uint32_t t = atomicAdd(a.ticket, 1u);
+    if (t == n_blocks - 1) *a.ticket = 0;             // the last ticket of this job: ready for the next call
+    s_ticket = t;
   }
   __syncthreads();
-  const uint32_t base = s_base;
-  __syncthreads();
+  const uint32_t vb = s_ticket;
+  const uint32_t i = vb * 256 + threadIdx.x;
 
   Decision d; d.valid = false; d.has = false; d.cur = 0.f; d.f = 0;
-  if (i < a.nq) d = decide(a, i);
-  const bool emit = (i < a.nq) && (a.compact ? d.valid : true);
+  if (i < nq) d = decide(a, i);
+  const bool emit = (i < nq) && (a.compact ? d.valid : true);
   const uint32_t bal = __ballot_sync(0xffffffffu, emit);
   if (lane == 0) s_warp[warp] = __popc(bal);
   __syncthreads();
+  uint32_t mine = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) mine += s_warp[w];
+  const uint64_t stamp = static_cast<uint64_t>(a.epoch) << 32;
+  if (threadIdx.x == 0) st_release_u64(a.state + vb, stamp | mine);
+  // exclusive prefix over the tickets before this one
+  uint32_t part = 0;
+  for (uint32_t b = threadIdx.x; b < vb; b += 256) {
+    uint64_t v;
+    do { v = ld_acquire_u64(a.state + b); } while ((v >> 32) != a.epoch);
+    part += static_cast<uint32_t>(v);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) s_pre[warp] = part;
+  __syncthreads();
+  uint32_t base = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) base += s_pre[w];
+  if (vb == n_blocks - 1 && threadIdx.x == 0) {
+    if (a.total) *a.total = base + mine;
+    if (a.total_host) *reinterpret_cast<volatile uint32_t*>(a.total_host) = base + mine;
+  }
+  if (!emit) return;
   uint32_t off = base;
   for (int w = 0; w < warp; ++w) off += s_warp[w];
   off += __popc(bal & ((1u << lane) - 1u));
-  if (blockIdx.x == (a.nq + 255) / 256 - 1 && threadIdx.x == 0) {
-    uint32_t t = base;
-    for (int w = 0; w < 8; ++w) t += s_warp[w];
-    *a.total = t;
-  }
-  if (!emit) return;
 
   const float2 zero2 = make_float2(0.f, 0.f);
   const float2 ql = d.valid ? a.q_loc[i] : zero2;
@@ -139,13 +157,12 @@ __global__ void __launch_bounds__(256) finalize_write_kernel(const FinalizeArgs*
   }
 }
 
-// jobs_dev: n_jobs FinalizeArgs in device memory; max_nq: the largest nq among them (> 0).  Jobs with nq == 0 must have
-// had their total zeroed by the caller (no block of theirs runs).
-void launch_finalize(cudaStream_t st, const FinalizeArgs* jobs_dev, uint32_t n_jobs, uint32_t max_nq) {
+// fb.jobs: n_jobs FinalizeArgs in device memory, or nullptr with the single job inline; max_nq: the largest nq among them
+// (> 0).  Jobs with nq == 0 must have had their totals zeroed by the caller (no block of theirs runs).
+void launch_finalize(cudaStream_t st, const FinalizeBatch& fb, uint32_t n_jobs, uint32_t max_nq) {
   if (n_jobs == 0 || max_nq == 0) return;
   const dim3 grid((max_nq + 255) / 256, n_jobs);
-  finalize_count_kernel<<<grid, 256, 0, st>>>(jobs_dev);
-  finalize_write_kernel<<<grid, 256, 0, st>>>(jobs_dev);
+  finalize_kernel<<<grid, 256, 0, st>>>(fb);
 }
 
 // keys -> float seed distances (min over splits; FLT_MAX when there is no seed feature)
@@ -157,7 +174,7 @@ __global__ void seed_from_keys_kernel(const uint64_t* keys, uint32_t nq, uint32_
     const uint64_t k = keys[static_cast<uint64_t>(s) * nq_pad + i];
     key = k < key ? k : key;
   }
-  out[i] = key == kKeyNone ? FLT_MAX : static_cast<float>(static_cast<uint32_t>(key >> 37));
+  out[i] = key >= kKeyNeedsExact ? FLT_MAX : static_cast<float>(static_cast<uint32_t>(key >> 37));
 }
 void launch_seed_from_keys(cudaStream_t st, const uint64_t* keys, uint32_t nq, uint32_t nq_pad, uint32_t n_splits, float* out) {
   if (nq) seed_from_keys_kernel<<<(nq + 255) / 256, 256, 0, st>>>(keys, nq, nq_pad, n_splits, out);
@@ -277,25 +294,14 @@ void launch_match_set_2view(cudaStream_t st, const void* in, uint32_t n, void* k
                                                                   static_cast<RefMultiMatch*>(mm), max_bits);
 }
 
-// ---------------------------------------------------------------- sortMatches: bitonic sort of (orderable distance bits, index)
+// ---------------------------------------------------------------- sortMatches: radix sort of (orderable distance bits, index)
 __device__ __forceinline__ uint32_t orderable(float f) {
   const uint32_t u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
-__global__ void sort_keys_kernel(const RefDMatch* m, uint32_t n, uint32_t n_pow2, uint64_t* keys) {
+__global__ void sort_keys_kernel(const RefDMatch* m, uint32_t n, uint64_t* keys) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pow2) return;
-  keys[i] = i < n ? ((static_cast<uint64_t>(orderable(m[i].distance)) << 32) | i) : ~0ull;
-}
-__global__ void bitonic_step_kernel(uint64_t* keys, uint32_t n_pow2, uint32_t j, uint32_t k) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pow2) return;
-  const uint32_t l = i ^ j;
-  if (l > i) {
-    const uint64_t a = keys[i], b = keys[l];
-    const bool up = (i & k) == 0;
-    if ((a > b) == up) { keys[i] = b; keys[l] = a; }
-  }
+  if (i < n) keys[i] = (static_cast<uint64_t>(orderable(m[i].distance)) << 32) | i;
 }
 __global__ void sort_gather_kernel(const RefDMatch* in, const uint64_t* keys, uint32_t n, RefDMatch* out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -305,20 +311,23 @@ __global__ void sort_gather_kernel(const RefDMatch* in, const uint64_t* keys, ui
 #pragma unroll
   for (int w = 0; w < 6; ++w) d[w] = s[w];
 }
-// tmp_keys: n_pow2 u64 ; tmp_records: n DMatch
-uint64_t launch_sort(cudaStream_t st, void* dmatches, uint32_t n, uint64_t* tmp_keys, void* tmp_records) {
-  if (n < 2) return 0;
-  uint32_t p2 = 1;
-  while (p2 < n) p2 <<= 1;
-  const unsigned blocks = (p2 + 255) / 256;
-  uint64_t launches = 0;
-  sort_keys_kernel<<<blocks, 256, 0, st>>>(static_cast<const RefDMatch*>(dmatches), n, p2, tmp_keys); ++launches;
-  for (uint32_t k = 2; k <= p2; k <<= 1)
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) { bitonic_step_kernel<<<blocks, 256, 0, st>>>(tmp_keys, p2, j, k); ++launches; }
-  sort_gather_kernel<<<(n + 255) / 256, 256, 0, st>>>(static_cast<const RefDMatch*>(dmatches), tmp_keys, n,
-                                                      static_cast<RefDMatch*>(tmp_records)); ++launches;
-  cudaMemcpyAsync(dmatches, tmp_records, static_cast<size_t>(n) * sizeof(RefDMatch), cudaMemcpyDeviceToDevice, st);
-  return launches;
+size_t sort_temp_bytes(uint32_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, bytes, static_cast<const uint64_t*>(nullptr), static_cast<uint64_t*>(nullptr), static_cast<int>(n));
+  return bytes;
+}
+// keys_in / keys_out: n u64 each; tmp_records: n DMatch.  The key's low word is the record's position, so equal distances
+// keep their input order: deterministic, and one valid outcome of the reference's unstable thrust::sort (ref: :191-222).
+cudaError_t launch_sort(cudaStream_t st, void* dmatches, uint32_t n, uint64_t* keys_in, uint64_t* keys_out, void* temp, size_t temp_bytes,
+                        void* tmp_records, uint64_t* launches) {
+  if (n < 2) return cudaSuccess;
+  const unsigned blocks = (n + 255) / 256;
+  sort_keys_kernel<<<blocks, 256, 0, st>>>(static_cast<const RefDMatch*>(dmatches), n, keys_in);
+  cudaError_t e = cub::DeviceRadixSort::SortKeys(temp, temp_bytes, keys_in, keys_out, static_cast<int>(n), 0, 64, st);
+  if (e != cudaSuccess) return e;
+  sort_gather_kernel<<<blocks, 256, 0, st>>>(static_cast<const RefDMatch*>(dmatches), keys_out, n, static_cast<RefDMatch*>(tmp_records));
+  if (launches) *launches += 3;
+  return cudaMemcpyAsync(dmatches, tmp_records, static_cast<size_t>(n) * sizeof(RefDMatch), cudaMemcpyDeviceToDevice, st);
 }
 
 }  // namespace b200

@@ -142,12 +142,30 @@ struct alignas(128) SmaxJob {
   CUtensorMap map_text;          // target fold digits, box  32 B x kBN rows
   SmaxArgs a;
 };
+// The launch's job table: device memory (many pairs, staged by the host) or, for a single pair, carried in the kernel's
+// parameter block itself (no staging copy in front of the launch; tensor maps are read straight from the parameter space).
 struct SmaxBatch {
-  const SmaxJob* jobs;
+  const SmaxJob* jobs;           // nullptr: the single job is `inline_job`
   uint32_t n_jobs;
   uint32_t n_ctas;
   uint64_t total_tiles;
-  unsigned long long* timing;    // optional [gridDim.x][16] cycle counters (diagnostics), or nullptr
+  unsigned long long* timing;    // optional [gridDim.x][16] cycle counters (diagnostics build), or nullptr
+  SmaxJob inline_job;
+};
+
+// pack.cu: one set (or one row range of a set) of a pack launch
+struct PackJob {
+  const RefFeature* in;          // n records
+  uint64_t n, n_rows;            // rows [0, n) are features, [n, n_rows) zero padding; n_rows % 32 == 0
+  uint8_t* desc; uint8_t* ext; int32_t* norm; int32_t* wcol; int32_t* wmax; float2* loc; float2* sigtheta;   // at the range's first row
+  int32_t* meta;                 // device scalars of the set (zero unless some W does not fit the fold digits)
+  int32_t* h_meta;               // the same verdict in pinned, device-mapped host memory
+  uint32_t win_begin;            // first 32-row window of this job in the launch's linear window space
+};
+constexpr int kPackInline = 8;
+struct PackBatch {
+  PackJob jobs[kPackInline];
+  uint32_t n_jobs, total_windows;
 };
 
 // thresholds / writers / compaction of one pair (finalize.cu); an array of these lives in device memory
@@ -162,8 +180,16 @@ struct FinalizeArgs {
   const float2* q_sigtheta; const float2* t_sigtheta;  // FeatureMatch only
   const uint8_t* q_desc; const uint8_t* t_desc;
   void* out;
-  uint32_t* block_counts;     // [ceil(nq / 256)]
-  uint32_t* total;            // [1]
+  // single-pass stable compaction: block b (in ticket order) publishes (epoch << 32 | count) in state[b] and sums its predecessors
+  uint64_t* state;            // [ceil(nq / 256)], zero-initialised once; entries of other epochs are "not yet"
+  uint32_t* ticket;           // [1] zero before the launch, reset by the block that draws the last ticket
+  uint32_t epoch;             // this call's stamp (never 0)
+  uint32_t* total;            // [1] device
+  uint32_t* total_host;       // [1] pinned, device-mapped host word (or nullptr)
+};
+struct FinalizeBatch {
+  const FinalizeArgs* jobs;   // device memory, or nullptr: the single job is `inline_job`
+  FinalizeArgs inline_job;
 };
 
 __host__ __device__ __forceinline__ uint64_t cta_tile_begin(uint64_t total, uint32_t n_ctas, uint32_t c) {

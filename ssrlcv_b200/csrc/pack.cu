@@ -4,96 +4,128 @@
 //   ext   uint8[n_pad][32]    base-255 digits of W = kFoldC - (|b|^2 >> 1) (extra K block, SWIZZLE_32B)
 //   norm  int32[n_pad]        |b|^2            wcol int32[n_pad]   kNoFoldC - (|b|^2 >> 1)
 //   wmax  int32[n_pad / 32]   largest wcol of each 32-row window (0 for windows of padding only): the bound the matcher's
-//                             no-fold variant tests before it adds W to a window's accumulators
+//                             no-fold variant tests before it adds W to a window's scores
 //   loc   float2[n_pad]       sigtheta float2[n_pad]
-// HBM-bound byte shuffling: 152 B read, 188 B written per feature.
+// HBM-bound byte shuffling: 152 B read, 188 B written per feature (+ 4 B per 32 features).
 #include <cub/cub.cuh>
 
 #include "matcher.cuh"
 
 namespace b200 {
 
-// Per-set device scalars ("meta", 4 x int32 at the end of the set's allocation, zeroed by one memset before the pack):
+// Per-set device scalars ("meta", 4 x int32 from the context's zero-initialised slot pool, api.cu):
 //   meta[0] != 0  <=>  some target's W does not fit the fold digits (the matcher then runs its epilogue-add variant)
 // W is measured against a CONSTANT offset (kFoldC / kNoFoldC, matcher.cuh), not against the set's own maximum norm, so
-// the digits of a row depend on that row alone: one kernel, no grid-wide dependency, no host round trip.
+// the digits of a row depend on that row alone: one kernel, no grid-wide dependency, no host round trip.  The (rare) bad
+// verdict is also stored straight into the set's pinned, device-mapped host word, so no copy node follows the kernel.
 //
-// Two features per warp-iteration: 16 lanes x 8 bytes cover one descriptor (record base is only 8-byte aligned); the lane
-// that ends up with the norm also writes the row's scalars and its 32 fold digits.
-// Rows [n, n_rows) are the zero padding of the set and are written here too (no memset of the allocation).
-__global__ void __launch_bounds__(256) pack_kernel(const RefFeature* __restrict__ in, uint64_t n, uint64_t n_rows,
-                                                   uint8_t* __restrict__ desc, uint8_t* __restrict__ ext, int32_t* __restrict__ norm,
-                                                   int32_t* __restrict__ wcol, int32_t* __restrict__ wmax, float2* __restrict__ loc,
-                                                   float2* __restrict__ sigtheta, int32_t* __restrict__ meta) {
+// One launch packs up to kPackInline sets (the job table travels as a kernel parameter: no staging copy).  The unit of work
+// is a 32-row window -- the matcher's candidate window -- handled by ONE warp in 16 steps of two rows (16 lanes x 8 bytes
+// cover one descriptor; the record base is only 8-byte aligned), so the window's largest W is a register maximum: no atomics
+// and nothing to zero beforehand.  Rows [n, n_rows) are the zero padding of the set and are written here too.
+__global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackBatch b) {
   const int lane = threadIdx.x & 31, half = lane >> 4, sub = lane & 15;
-  const uint64_t warp_global = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
-  const uint64_t n_warps = (gridDim.x * (uint64_t)blockDim.x) >> 5;
-  bool bad = false;
-  for (uint64_t base = warp_global * 2; base < n_rows; base += n_warps * 2) {
-    const uint64_t i = base + half;
-    uint32_t s = 0;
-    if (i < n) {
-      const uint8_t* rec = reinterpret_cast<const uint8_t*>(in + i);
-      const uint2 w = *reinterpret_cast<const uint2*>(rec + 24 + sub * 8);
-      *reinterpret_cast<uint2*>(desc + i * kDescBytes + sub * 8) = w;
-      s = __dp4a(w.x, w.x, 0u);
-      s = __dp4a(w.y, w.y, s);
-    } else if (i < n_rows) {
-      *reinterpret_cast<uint2*>(desc + i * kDescBytes + sub * 8) = make_uint2(0u, 0u);
-    }
+  const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t w = warp_global; w < b.total_windows; w += n_warps) {
+    uint32_t j = 0;
+    while (j + 1 < b.n_jobs && w >= b.jobs[j + 1].win_begin) ++j;
+    const RefFeature* __restrict__ in = b.jobs[j].in;
+    const uint64_t n = b.jobs[j].n;
+    const uint32_t win = w - b.jobs[j].win_begin;
+    uint8_t* __restrict__ desc = b.jobs[j].desc;
+    uint8_t* __restrict__ ext = b.jobs[j].ext;
+    int32_t* __restrict__ norm = b.jobs[j].norm;
+    int32_t* __restrict__ wcol = b.jobs[j].wcol;
+    float2* __restrict__ loc = b.jobs[j].loc;
+    float2* __restrict__ sigtheta = b.jobs[j].sigtheta;
+    const uint64_t row0 = static_cast<uint64_t>(win) * kChunk;
+    int32_t wtop = 0;
+    bool bad = false;
+#pragma unroll 1
+    for (int it0 = 0; it0 < 16; it0 += 4) {
+      uint2 v[4];
 #pragma unroll
-    for (int o = 8; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (sub == 0 && i < n_rows) {
-      // W = kFoldC - h as  digits[0] + 255 * sum(digits[1..31]),  every digit <= 255; zero on padding rows and on rows
-      // whose W does not fit (the whole set then takes the epilogue-add variant, which reads wcol = kNoFoldC - h)
-      uint32_t words[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      int32_t wn = 0;
-      if (i < n) {
-        const int32_t h = static_cast<int32_t>(s >> 1);
-        norm[i] = static_cast<int32_t>(s);
-        loc[i] = in[i].loc;
-        sigtheta[i] = make_float2(in[i].sigma, in[i].theta);
-        wn = kNoFoldC - h;
-        atomicMax(&wmax[i >> 5], wn);                              // wmax is zeroed with the meta scalars; wn >= 2
-        const int32_t W = kFoldC - h;
-        if (W >= 2) {
-          uint32_t rest = static_cast<uint32_t>(W) / 255u;        // <= 31 * 255, spread greedily over digits 1..31
-          words[0] = static_cast<uint32_t>(W) % 255u;
-#pragma unroll
-          for (int k = 1; k < 32; ++k) {
-            const uint32_t take = rest < 255u ? rest : 255u;
-            words[k >> 2] |= take << (8 * (k & 3));
-            rest -= take;
-          }
-        } else {
-          bad = true;
-        }
-      } else {
-        norm[i] = 0;
-        loc[i] = make_float2(0.f, 0.f);
-        sigtheta[i] = make_float2(0.f, 0.f);
+      for (int k = 0; k < 4; ++k) {                                   // four descriptor loads in flight per lane
+        const uint64_t i = row0 + (it0 + k) * 2 + half;
+        v[k] = make_uint2(0u, 0u);
+        if (i < n) v[k] = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(in + i) + 24 + sub * 8);
       }
-      wcol[i] = wn;
-      uint4* o = reinterpret_cast<uint4*>(ext + i * kExtBytes);
-      o[0] = make_uint4(words[0], words[1], words[2], words[3]);
-      o[1] = make_uint4(words[4], words[5], words[6], words[7]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t i = row0 + (it0 + k) * 2 + half;               // < n_rows: windows are whole
+        *reinterpret_cast<uint2*>(desc + i * kDescBytes + sub * 8) = v[k];
+        uint32_t s = __dp4a(v[k].x, v[k].x, 0u);
+        s = __dp4a(v[k].y, v[k].y, s);
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (sub == 0) {
+          // W = kFoldC - h as  digits[0] + 255 * sum(digits[1..31]),  every digit <= 255; zero on padding rows and on rows
+          // whose W does not fit (the whole set then takes the epilogue-add variant, which reads wcol = kNoFoldC - h)
+          uint32_t words[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          int32_t wn = 0;
+          if (i < n) {
+            const int32_t h = static_cast<int32_t>(s >> 1);
+            norm[i] = static_cast<int32_t>(s);
+            loc[i] = in[i].loc;
+            sigtheta[i] = make_float2(in[i].sigma, in[i].theta);
+            wn = kNoFoldC - h;                                         // >= 2
+            const int32_t W = kFoldC - h;
+            if (W >= 2) {
+              uint32_t rest = static_cast<uint32_t>(W) / 255u;        // <= 31 * 255, spread greedily over digits 1..31
+              words[0] = static_cast<uint32_t>(W) % 255u;
+#pragma unroll
+              for (int q = 1; q < 32; ++q) {
+                const uint32_t take = rest < 255u ? rest : 255u;
+                words[q >> 2] |= take << (8 * (q & 3));
+                rest -= take;
+              }
+            } else {
+              bad = true;
+            }
+          } else {
+            norm[i] = 0;
+            loc[i] = make_float2(0.f, 0.f);
+            sigtheta[i] = make_float2(0.f, 0.f);
+          }
+          wtop = max(wtop, wn);
+          wcol[i] = wn;
+          uint4* o = reinterpret_cast<uint4*>(ext + i * kExtBytes);
+          o[0] = make_uint4(words[0], words[1], words[2], words[3]);
+          o[1] = make_uint4(words[4], words[5], words[6], words[7]);
+        }
+      }
+    }
+    wtop = max(wtop, __shfl_xor_sync(0xffffffffu, wtop, 16));          // lanes 0 and 16 hold the two halves' maxima
+    if (lane == 0) b.jobs[j].wmax[win] = wtop;                         // 0 for windows of padding only
+    if (__any_sync(0xffffffffu, bad) && lane == 0) {
+      atomicOr(b.jobs[j].meta, 1);
+      *reinterpret_cast<volatile int32_t*>(b.jobs[j].h_meta) = 1;      // pinned host word, read after the set's `ready` event
     }
   }
-  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&meta[0], 1);
 }
 
-// Packs rows [0, n) of `feat_dev` into rows [row0, row0 + n) of the set's arrays and zero-fills up to row0 + n_rows;
-// meta_dev: the 4 x int32 device scalars of this range (already zeroed, like the windows' wmax).  row0 % 32 == 0.
-void launch_pack(cudaStream_t st, const void* feat_dev, uint64_t n, uint64_t n_rows, uint64_t row0, ssrlcv_b200_set_impl& s,
-                 int32_t* meta_dev, int sm_count) {
-  if (n_rows == 0) return;
-  const uint64_t warps_needed = (n_rows + 1) / 2;
-  uint64_t blocks = (warps_needed + 7) / 8;
-  const uint64_t cap = static_cast<uint64_t>(sm_count) * 8;
-  if (blocks > cap) blocks = cap;
-  pack_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const RefFeature*>(feat_dev), n, n_rows, s.desc + row0 * kDescBytes,
-                                                             s.ext + row0 * kExtBytes, s.norm + row0, s.wcol + row0, s.wmax + row0 / kChunk,
-                                                             s.loc + row0, s.sigtheta + row0, meta_dev);
+// jobs: host array; each launch takes up to kPackInline of them.  Every job's n_rows is a multiple of 32.
+void launch_pack(cudaStream_t st, const PackJob* jobs, uint32_t n_jobs, int sm_count, uint64_t* launches) {
+  for (uint32_t at = 0; at < n_jobs;) {
+    PackBatch b;
+    b.n_jobs = 0; b.total_windows = 0;
+    while (at < n_jobs && b.n_jobs < static_cast<uint32_t>(kPackInline)) {
+      const uint64_t windows = jobs[at].n_rows / kChunk;
+      if (windows == 0) { ++at; continue; }
+      if (static_cast<uint64_t>(b.total_windows) + windows > 0xFFFFFFFFull) break;
+      b.jobs[b.n_jobs] = jobs[at];
+      b.jobs[b.n_jobs].win_begin = b.total_windows;
+      b.total_windows += static_cast<uint32_t>(windows);
+      ++b.n_jobs; ++at;
+    }
+    if (b.n_jobs == 0) continue;
+    uint64_t blocks = (static_cast<uint64_t>(b.total_windows) + 7) / 8;
+    const uint64_t cap = static_cast<uint64_t>(sm_count) * 8;
+    if (blocks > cap) blocks = cap;
+    pack_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(b);
+    if (launches) *launches += 1;
+  }
 }
 
 // ---------------------------------------------------------------- x-sorted copy of a packed set (masked searches, api.cu sorted_of)

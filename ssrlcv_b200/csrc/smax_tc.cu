@@ -168,6 +168,17 @@ __device__ __forceinline__ void resolve_row(const SmaxArgs& job, const WinState&
   job.keys[static_cast<uint64_t>(slot) * job.nq_pad + row] = key;
 }
 
+// Key slots [slot + 1, fill_end) of a query tile whose last unit this is have no unit of their own (the tile is crossed by
+// fewer CTAs than the widest one): mark them "no candidate" for rows [r_begin, r_begin + r_count).
+__device__ __forceinline__ void fill_unused_slots(const SmaxArgs& job, uint32_t qt, uint32_t slot, uint32_t fill_end, uint32_t r_begin,
+                                                  uint32_t r_count, int lane) {
+  if (slot + 1 >= fill_end) return;
+  uint64_t* keys = job.keys;
+  const uint64_t stride = job.nq_pad;
+  for (uint32_t s = slot + 1; s < fill_end; ++s)
+    for (uint32_t r = lane; r < r_count; r += 32) keys[s * stride + qt * kBM + r_begin + r] = kKeyNone;
+}
+
 __device__ __forceinline__ uint32_t word_of(const uint4 (&v)[8], int w) {
   const uint4 q = v[w >> 2];
   return (w & 3) == 0 ? q.x : (w & 3) == 1 ? q.y : (w & 3) == 2 ? q.z : q.w;
@@ -304,17 +315,21 @@ struct UnitIter {
   const SmaxJob* J;                            // job of the current unit
   uint32_t job;
   uint32_t qt, j0, j1, slot;
+  uint32_t fill_end;                           // key slots [slot + 1, fill_end) of this query tile have no unit: the unit that ends the
+                                               // tile's target range marks them "no candidate" (nothing is memset beforehand)
   bool last;                                   // the CTA's final unit
+  const SmaxJob* jobs;                         // device memory, or the launch's parameter block (single pair)
   __device__ __forceinline__ UnitIter(const SmaxBatch& b, uint32_t cta) {
+    jobs = b.jobs ? b.jobs : &b.inline_job;
     L = cta_tile_begin(b.total_tiles, b.n_ctas, cta);
     L_end = cta_tile_begin(b.total_tiles, b.n_ctas, cta + 1);
     uint32_t lo = 0, hi = b.n_jobs - 1;        // the job whose range contains L (every job of a launch has tiles)
     while (lo < hi) {
       const uint32_t mid = (lo + hi) >> 1;
-      if (L >= b.jobs[mid].a.tile_end) lo = mid + 1; else hi = mid;
+      if (L >= jobs[mid].a.tile_end) lo = mid + 1; else hi = mid;
     }
     job = lo;
-    J = b.jobs + job;
+    J = jobs + job;
   }
   // check_fold: the launch is the fold variant; a job whose target set turned out not to fit the fold digits (the host
   // launched optimistically, before the set's pack had reported back) is skipped by every role alike and redone by the
@@ -322,8 +337,8 @@ struct UnitIter {
   __device__ __forceinline__ bool next(const SmaxBatch& b, uint32_t cta, bool check_fold) {
     for (;;) {
       if (L >= L_end) return false;
-      while (L >= b.jobs[job].a.tile_end) ++job;
-      J = b.jobs + job;
+      while (L >= jobs[job].a.tile_end) ++job;
+      J = jobs + job;
       if (!check_fold || J->a.t_meta[0] == 0) break;
       L = J->a.tile_end;
     }
@@ -335,6 +350,7 @@ struct UnitIter {
     const uint64_t room = L_end - L;
     j1 = (n_tt - j0 <= room) ? n_tt : j0 + static_cast<uint32_t>(room);
     slot = cta - cta_of_tile(b.total_tiles, b.n_ctas, begin + static_cast<uint64_t>(qt) * n_tt);
+    fill_end = j1 == n_tt ? J->a.n_splits : slot + 1;
     L += j1 - j0;
     last = L >= L_end;
     return true;
@@ -354,7 +370,7 @@ struct UnitIter {
 // kTiming: per-role cycle counters (diagnostics build of the same kernel; never used by the product path).
 template <int kMask, bool kFold, bool kColMask, bool kTiming>
 __global__ void __launch_bounds__(kThreads, 1)
-smax_kernel(const SmaxBatch batch) {
+smax_kernel(const __grid_constant__ SmaxBatch batch) {
   constexpr bool kCols = (kMask != SSRLCV_B200_MASK_NONE) || !kFold;   // epilogue needs per-target data (locations / W)
   constexpr int32_t kWOffset = kFold ? kFoldC : kNoFoldC;               // the C of W_b = C - h_b
   extern __shared__ uint8_t smem_raw[];
@@ -412,7 +428,7 @@ smax_kernel(const SmaxBatch batch) {
         const CUtensorMap* map_q = &u.J->map_q;
         const CUtensorMap* map_t = &u.J->map_t;
         const CUtensorMap* map_text = &u.J->map_text;
-        if (u.job != acquired) {                                   // first use of this job's tensor maps by this CTA
+        if (u.job != acquired && batch.jobs != nullptr) {          // first use of this job's tensor maps (global memory) by this CTA
           tma_acquire_desc(map_q); tma_acquire_desc(map_t);
           if (kFold) tma_acquire_desc(map_text);
           acquired = u.job;
@@ -517,6 +533,7 @@ smax_kernel(const SmaxBatch batch) {
       } else {
         resolve_rows_windows<kMask, 2>(u.J->a, xch + (uparity * 2 + 0) * kBM, xch + (uparity * 2 + 1) * kBM, u.qt, u.slot, rw * 64, 64, lane);
       }
+      fill_unused_slots(u.J->a, u.qt, u.slot, u.fill_end, rw * 64, 64, lane);
       __syncwarp();
       if (lane == 0) mbar_arrive(&x_empty[uparity]);
       uparity ^= 1;
@@ -708,6 +725,7 @@ smax_kernel(const SmaxBatch batch) {
           const uint32_t r = quarter * 32 + lane;
           resolve_row(args, xch[(uparity * 2 + 0) * kBM + r], xch[(uparity * 2 + 1) * kBM + r], u.qt, u.slot, r, kWOffset);
         }
+        fill_unused_slots(args, u.qt, u.slot, u.fill_end, (warp - 4) * 16, 16, lane);
       }
       ++uiter;
       if (kTiming) te_resolve += clock64() - r0;

@@ -33,52 +33,110 @@ def shard_bounds(n_targets: int, world_size: int, align: int = 256) -> List[int]
     return b
 
 
-def gather_pair_lists(local: dict, n_pairs: int, rank: int, world_size: int, dist, device="cpu") -> List[np.ndarray]:
-    """local: {pair_index: UINT2_PAIR array} computed by this rank.  Returns all pair lists in pair order on every rank."""
+class PairListExchange:
+    """The one exchange of pair-sharded N-view matching: every rank ends up with every pair's uint2_pair list, addressable
+    in the reference's pair order (ref: src/MatchFactory.cu:925-936, :1025).
+
+    Everything stays on the device (NCCL over NVLink; gloo on CPU for the tests): the ranks' record counts travel first
+    (one small all-gather, the only host synchronisation of the exchange), then the lists, padded to the LONGEST list rather
+    than to the number of queries.  Buffers are allocated once per job shape."""
+
+    def __init__(self, n_pairs: int, assign: Sequence[Sequence[int]], capacity: int, rank: int, world_size: int, dist, device="cpu"):
+        import torch
+
+        self.torch, self.dist, self.rank, self.world, self.device = torch, dist, rank, world_size, device
+        self.n_pairs, self.capacity = n_pairs, capacity
+        self.slots = max(1, max((len(a) for a in assign), default=1))
+        self.where = [(-1, -1)] * n_pairs                       # pair -> (rank, slot)
+        for r, a in enumerate(assign):
+            for s_i, k in enumerate(a):
+                self.where[k] = (r, s_i)
+        pinned = str(device).startswith("cuda")
+        self.counts_h = torch.zeros(self.slots, dtype=torch.int64, pin_memory=pinned)
+        self.counts_d = torch.zeros(self.slots, dtype=torch.int64, device=device)
+        self.all_counts_d = torch.zeros((world_size, self.slots), dtype=torch.int64, device=device)
+        self.all_counts_h = torch.zeros((world_size, self.slots), dtype=torch.int64, pin_memory=pinned)
+        self.gathered = torch.empty(world_size * self.slots * max(capacity, 1) * 4, dtype=torch.int32, device=device) if world_size > 1 else None
+        self.last_bytes = 0
+
+    def run(self, out, counts):
+        """out: int32[slots, capacity, 4] records of this rank's pairs (slot order = its assignment order);
+        counts: record count per owned pair (host).  Returns (counts per pair [n_pairs] on the host, lists) where lists[k]
+        is a device tensor int32[count_k.., 4] view of pair k's records."""
+        torch = self.torch
+        m = len(counts)
+        self.counts_h.zero_()
+        if m:
+            self.counts_h[:m] = torch.as_tensor(np.asarray(counts, dtype=np.int64))
+        if self.world == 1:
+            allc = self.counts_h.reshape(1, -1)
+            view = out.reshape(1, self.slots, -1, 4) if out.numel() else out
+            cap = out.shape[1] if out.dim() == 3 else 0
+            self.last_bytes = 0
+        else:
+            self.counts_d.copy_(self.counts_h, non_blocking=True)
+            self.dist.all_gather_into_tensor(self.all_counts_d.reshape(-1), self.counts_d)
+            self.all_counts_h.copy_(self.all_counts_d, non_blocking=True)
+            if str(self.device).startswith("cuda"):
+                torch.cuda.current_stream().synchronize()
+            allc = self.all_counts_h
+            cap = max(int(allc.max()), 1)                        # longest list of the job: the lists travel padded to it
+            send = out[:, :cap].contiguous()
+            recv = self.gathered[: self.world * self.slots * cap * 4]
+            self.dist.all_gather_into_tensor(recv, send.reshape(-1))
+            view = recv.view(self.world, self.slots, cap, 4)
+            self.last_bytes = recv.numel() * 4 + self.all_counts_d.numel() * 8
+        per_pair = np.zeros(self.n_pairs, np.int64)
+        lists = [None] * self.n_pairs
+        ac = allc.numpy()
+        for k, (r, s_i) in enumerate(self.where):
+            if r < 0:
+                continue
+            per_pair[k] = ac[r, s_i]
+            lists[k] = view[r, s_i, : per_pair[k]]
+        return per_pair, lists
+
+
+def exchange_pair_lists(n_pairs, assign, capacity, rank, world_size, dist, device="cpu") -> PairListExchange:
+    return PairListExchange(n_pairs, assign, capacity, rank, world_size, dist, device)
+
+
+def gather_pair_lists(local: dict, n_pairs: int, rank: int, world_size: int, dist, device="cpu", assign=None) -> List[np.ndarray]:
+    """local: {pair_index: UINT2_PAIR array} computed by this rank.  Returns all pair lists in pair order on every rank
+    (host arrays; the exchange itself runs on `device` through PairListExchange)."""
     import torch
 
-    counts = torch.zeros(n_pairs, dtype=torch.int64, device=device)
-    for k, arr in local.items():
-        counts[k] = len(arr)
+    if assign is None:                                          # who owns what: one small all-gather of the owners' index lists
+        mine = sorted(local)
+        if world_size > 1:
+            idx = torch.full((n_pairs,), -1, dtype=torch.int64, device=device)
+            idx[: len(mine)] = torch.as_tensor(mine, dtype=torch.int64)
+            alli = torch.empty((world_size, n_pairs), dtype=torch.int64, device=device)
+            parts = [alli[r] for r in range(world_size)]
+            dist.all_gather(parts, idx)
+            assign = [[int(k) for k in alli[r].cpu().tolist() if k >= 0] for r in range(world_size)]
+        else:
+            assign = [mine]
+    mine = list(assign[rank])
+    cap = max([len(local[k]) for k in mine], default=0)
     if world_size > 1:
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)        # every pair is owned by exactly one rank
-    counts_h = counts.cpu().numpy()
-    cap = int(counts_h.max()) if n_pairs else 0
-    mine = sorted(local)
-    per_rank = [0] * world_size
-    if world_size > 1:
-        n_mine = torch.tensor([len(mine)], dtype=torch.int64, device=device)
-        all_n = [torch.zeros_like(n_mine) for _ in range(world_size)]
-        dist.all_gather(all_n, n_mine)
-        per_rank = [int(x.item()) for x in all_n]
-    else:
-        per_rank = [len(mine)]
-    slots = max(per_rank) if per_rank else 0
-    # payload per rank: [slots] pair indices + [slots, cap, 4] uint32 records
-    idx = torch.full((max(slots, 1),), -1, dtype=torch.int64, device=device)
-    buf = torch.zeros((max(slots, 1), max(cap, 1), 4), dtype=torch.int32, device=device)
-    for s, k in enumerate(mine):
-        idx[s] = k
+        capt = torch.tensor([cap], dtype=torch.int64, device=device)
+        dist.all_reduce(capt, op=dist.ReduceOp.MAX)
+        cap = int(capt.item())
+    xch = PairListExchange(n_pairs, assign, max(cap, 1), rank, world_size, dist, device)
+    out = torch.zeros((xch.slots, max(cap, 1), 4), dtype=torch.int32, device=device)
+    for s_i, k in enumerate(mine):
         arr = np.ascontiguousarray(local[k], T.UINT2_PAIR)
         if len(arr):
-            buf[s, : len(arr)] = torch.from_numpy(arr.view(np.int32).reshape(-1, 4)).to(device)
-    if world_size > 1:
-        all_idx = [torch.empty_like(idx) for _ in range(world_size)]
-        all_buf = [torch.empty_like(buf) for _ in range(world_size)]
-        dist.all_gather(all_idx, idx)
-        dist.all_gather(all_buf, buf)
-    else:
-        all_idx, all_buf = [idx], [buf]
-    out: List[np.ndarray] = [np.zeros(0, T.UINT2_PAIR) for _ in range(n_pairs)]
-    for r in range(world_size):
-        ih = all_idx[r].cpu().numpy()
-        bh = all_buf[r].cpu().numpy()
-        for s, k in enumerate(ih):
-            if k < 0:
-                continue
-            n = int(counts_h[k])
-            out[int(k)] = np.ascontiguousarray(bh[s, :n]).view(np.uint32).reshape(-1).view(T.UINT2_PAIR).copy()
-    return out
+            out[s_i, : len(arr)] = torch.from_numpy(arr.view(np.int32).reshape(-1, 4)).to(device)
+    per_pair, lists = xch.run(out, [len(local[k]) for k in mine])
+    res: List[np.ndarray] = []
+    for k in range(n_pairs):
+        if lists[k] is None or per_pair[k] == 0:
+            res.append(np.zeros(0, T.UINT2_PAIR))
+        else:
+            res.append(np.ascontiguousarray(lists[k].cpu().numpy()).view(np.uint32).reshape(-1).view(T.UINT2_PAIR).copy())
+    return res
 
 
 def exhaustive_pairs_sharded(match_pair: Callable[[int, int], np.ndarray], sizes: Sequence[int], rank: int, world_size: int, dist,
@@ -86,8 +144,9 @@ def exhaustive_pairs_sharded(match_pair: Callable[[int, int], np.ndarray], sizes
     """Pair-sharded all-pairs matching.  match_pair(q, t) -> UINT2_PAIR array for views (q, t), run on this rank's GPU."""
     pairs = pair_order(len(sizes), ordered, estimatedOverlap)
     mine = assign_pairs(pairs, sizes, world_size)[rank]
+    assign = assign_pairs(pairs, sizes, world_size)
     local = {k: match_pair(*pairs[k]) for k in mine}
-    return gather_pair_lists(local, len(pairs), rank, world_size, dist, device)
+    return gather_pair_lists(local, len(pairs), rank, world_size, dist, device, assign=assign)
 
 
 def match_target_sharded(candidates: Callable[[int, int, int], "object"], finalize: Callable[["object", int], np.ndarray],

@@ -77,6 +77,10 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.ssrlcv_b200_launch_count(self.handle))
 
+    def tune(self, knob: int, value: int) -> None:
+        """ssrlcv_b200_tune: -1 = the library decides (tests / A-B timing only, see include/ssrlcv_b200.h)."""
+        self.check(self.lib.ssrlcv_b200_tune(self.handle, knob, int(value)))
+
 
 class PackedSet:
     def __init__(self, ctx: Context, handle: C.c_void_p, n: int):
@@ -91,15 +95,41 @@ class PackedSet:
             pass
 
 
+def _pack_key(features: Unity):
+    d = features.device
+    return (d.data_ptr(), d._version, features.size()) if d is not None else (0, 0, features.size())
+
+
 def pack(ctx: Context, features: Unity) -> PackedSet:
-    """Repack (and cache on the Unity) the device copy of a Feature<SIFT_Descriptor> array."""
-    if features._packed is not None and features._packed.ctx is ctx:
+    """Repack (and cache on the Unity) the device copy of a Feature<SIFT_Descriptor> array.  The cache is keyed on the
+    device buffer's address, torch version counter and length, so an in-place edit of the buffer repacks."""
+    key = _pack_key(features)
+    if features._packed is not None and features._packed.ctx is ctx and getattr(features._packed, "key", None) == key:
         return features._packed
     h = C.c_void_p()
     ctx.check(ctx.lib.ssrlcv_b200_pack(ctx.handle, C.c_void_p(features.device_ptr() if features.size() else 0),
                                        features.size(), C.byref(h)))
     features._packed = PackedSet(ctx, h, features.size())
+    features._packed.key = key
     return features._packed
+
+
+def pack_many(ctx: Context, sets) -> list:
+    """pack() for several Unity arrays with ONE launch for all that are not cached yet (ssrlcv_b200_pack_batch)."""
+    todo = []
+    for u in sets:
+        if not any(u is v for v in todo) and not (u._packed is not None and u._packed.ctx is ctx and getattr(u._packed, "key", None) == _pack_key(u)):
+            todo.append(u)
+    if len(todo) > 1:
+        n = len(todo)
+        ptrs = (C.c_void_p * n)(*[u.device_ptr() if u.size() else 0 for u in todo])
+        sizes = (C.c_uint64 * n)(*[u.size() for u in todo])
+        outs = (C.c_void_p * n)()
+        ctx.check(ctx.lib.ssrlcv_b200_pack_batch(ctx.handle, n, ptrs, sizes, outs))
+        for u, h in zip(todo, outs):
+            u._packed = PackedSet(ctx, C.c_void_p(h), u.size())
+            u._packed.key = _pack_key(u)
+    return [pack(ctx, u) for u in sets]
 
 
 class MatchFactory:
@@ -132,8 +162,12 @@ class MatchFactory:
             p.fundamental = (C.c_float * 9)(*np.asarray(fundamental, np.float32).reshape(9))
         p.query_camera = (C.c_uint8 * 80).from_buffer_copy(np.asarray(query.camera, T.CAMERA).tobytes())
         p.target_camera = (C.c_uint8 * 80).from_buffer_copy(np.asarray(target.camera, T.CAMERA).tobytes())
-        p.compact, p.engine = compact, self.engine
+        p.compact, p.reserved = compact, 0
         return p
+
+    def _select_engine(self) -> None:
+        # engine 1 = the SIMT cross-check kernel (tests only): a knob of the context, not a parameter of the call
+        self.ctx.tune(_lib.TUNE_CROSSCHECK_SIMT, 1 if self.engine == ENGINE_SIMT else -1)
 
     def _run(self, p: _lib.MatchParams, queryFeatures: Unity, targetFeatures: Unity, seedDistances: Unity | None) -> Unity:
         torch = self._torch()
@@ -153,7 +187,8 @@ class MatchFactory:
                 if seed_origin != gpu:
                     seedDistances.setMemoryState(gpu)
                 seed_ptr, n_seed = C.c_void_p(seedDistances.device_ptr()), nq
-            q, t = pack(self.ctx, queryFeatures), pack(self.ctx, targetFeatures)
+            q, t = pack_many(self.ctx, [queryFeatures, targetFeatures])
+            self._select_engine()
             dt = T.OUT_DTYPES[p.out_kind]
             out = torch.empty(max(nq, 1) * dt.itemsize, dtype=torch.uint8, device=f"cuda:{self.device}")
             n_out = C.c_uint64(0)
@@ -189,10 +224,11 @@ class MatchFactory:
         if origin != gpu:
             features.setMemoryState(gpu)
         try:
-            q, s = pack(self.ctx, features), pack(self.ctx, self.seedFeatures)
+            q, s = pack_many(self.ctx, [features, self.seedFeatures])
+            self._select_engine()
             out = torch.empty(max(features.size(), 1), dtype=torch.float32, device=f"cuda:{self.device}")
             self.ctx.check(self.ctx.lib.ssrlcv_b200_seed_distances(self.ctx.handle, q.handle, s.handle,
-                                                                   C.c_void_p(out.data_ptr()), self.engine))
+                                                                   C.c_void_p(out.data_ptr())))
             self.ctx.check(self.ctx.lib.ssrlcv_b200_synchronize(self.ctx.handle))
             return Unity(out[: features.size()], np.dtype("<f4"), gpu, self.device, features.size())
         finally:
@@ -336,6 +372,8 @@ class MatchFactory:
             P = (_lib.MatchParams * n)()
             Q, Tt, S, O = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_void_p * n)()
             outs, keep = [], []
+            pack_many(self.ctx, [u for _, qf, tf, _ in jobs for u in (qf, tf)])      # one launch for every view of the batch
+            self._select_engine()
             for i, (p, qf, tf, sd) in enumerate(jobs):
                 if sd is not None and sd.size() != qf.size():
                     raise MatchFactoryError("ERROR: seedDistances should have come from matching a seed image to queryFeatures")

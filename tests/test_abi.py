@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ssrlcv_b200_abi_version() == 1
+    assert lib.ssrlcv_b200_abi_version() == 2
 
 
 def test_params_struct_matches_header():
@@ -129,7 +129,7 @@ def test_header_is_plain_c_and_links(tmp_path):
     src.write_text('#include "ssrlcv_b200.h"\n'
                    "int main(void) {\n"
                    "  ssrlcv_b200_match_params p; ssrlcv_b200_ctx* ctx = 0; (void)p;\n"
-                   "  if (ssrlcv_b200_abi_version() != 1) return 1;\n"
+                   "  if (ssrlcv_b200_abi_version() != SSRLCV_B200_ABI_VERSION) return 1;\n"
                    "  if (ssrlcv_b200_create(0, 0, 0) == 0) return 2;          /* NULL out pointer: rejected */\n"
                    "  ssrlcv_b200_destroy(ctx);                                 /* NULL: no-op */\n"
                    "  return 0;\n}\n")

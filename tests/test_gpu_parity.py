@@ -28,7 +28,37 @@ def api():
 
     a = Api()
     a.O, a.Image, a.MatchFactory, a.Unity, a.cpu, a.gpu, a.both = O, Image, MatchFactory, Unity, cpu, gpu, both
+    _suite_default_knobs()
     return a
+
+
+def _suite_default_knobs():
+    """SSRLCV_TEST_FOLD=0|1 runs the whole suite under one forced matcher variant (tools/ab_fold.sh)."""
+    from ssrlcv_b200 import _lib
+    from ssrlcv_b200.match_factory import Context
+    f = os.environ.get("SSRLCV_TEST_FOLD")
+    Context.get(0).tune(_lib.TUNE_FOLD, int(f) if f not in (None, "") else -1)
+
+
+@pytest.fixture
+def knobs(api):
+    """ssrlcv_b200_tune for the duration of one test: knobs(fold=0, chunk_rows=512, ...); everything back to "library decides" afterwards."""
+    from ssrlcv_b200 import _lib
+    from ssrlcv_b200.match_factory import Context
+    names = {"fold": [_lib.TUNE_FOLD], "colmask": [_lib.TUNE_COLUMN_MASKS], "sorted": [_lib.TUNE_SORTED_TARGETS],
+             "chunk_rows": [_lib.TUNE_HOST_CHUNK_QUERY_ROWS, _lib.TUNE_HOST_CHUNK_TARGET_ROWS]}
+    ctx = Context.get(0)
+
+    def set_(**kw):
+        for k, v in kw.items():
+            for knob in names[k]:
+                ctx.tune(knob, -1 if v is None else int(v))
+
+    yield set_
+    for ks in names.values():
+        for knob in ks:
+            ctx.tune(knob, -1)
+    _suite_default_knobs()
 
 
 def _unity(api, arr, state=None):
@@ -232,11 +262,11 @@ def test_memory_states_restored(api):
 
 @pytest.mark.parametrize("fold", ["0", "1"])
 @pytest.mark.parametrize("thr", [FLT_MAX, 9.0e4])
-def test_forced_matcher_variants(api, everest, monkeypatch, fold, thr):
-    """SSRLCV_B200_FOLD forces the tensor-core kernel variant: five MMAs per tile with W folded into the contraction ("1"), or
+def test_forced_matcher_variants(api, everest, knobs, fold, thr):
+    """SSRLCV_B200_TUNE_FOLD forces the tensor-core kernel variant: five MMAs per tile with W folded into the contraction ("1"), or
     four MMAs with the window-bound test and W added in the epilogue ("0", otherwise only taken by sets whose norms do not
     fit the fold digits).  Both are exact, thresholded (column regime) and not (window regime), masked and unmasked."""
-    monkeypatch.setenv("SSRLCV_B200_FOLD", fold)
+    knobs(fold=fold)
     q, t = synth.make_pair(3000, 9000, seed=77)
     s = synth.make_seed(700)
     mf = api.MatchFactory(0.8, thr)
@@ -269,14 +299,11 @@ def _match_host(api, mf, p, q, t, s, elt_dtype):
 
 @pytest.mark.parametrize("chunk_rows", ["0", "256", "512", "1280", None])
 @pytest.mark.parametrize("nq,nt", [(3000, 3500), (700, 2049), (2049, 300), (1024, 1024)])
-def test_match_host_streamed_upload_equals_oracle(api, monkeypatch, chunk_rows, nq, nt):
+def test_match_host_streamed_upload_equals_oracle(api, knobs, chunk_rows, nq, nt):
     """match_host uploads large sets chunk by chunk and matches every chunk against what has already arrived (api.cu
     match_host_streamed); the chunk length is forced down here so that small cases take that path: every cut of the query
     and target sets gives the oracle's records.  "0" = never cut (the one-piece path), None = the library's own rule."""
-    if chunk_rows is None:
-        monkeypatch.delenv("SSRLCV_B200_HOST_CHUNK_ROWS", raising=False)
-    else:
-        monkeypatch.setenv("SSRLCV_B200_HOST_CHUNK_ROWS", chunk_rows)
+    knobs(chunk_rows=chunk_rows)
     q, t = synth.make_pair(nq, nt, seed=nq * 7 + nt)
     s = synth.make_seed(600)
     mf = api.MatchFactory(0.8, 1.1e5)
@@ -290,8 +317,8 @@ def test_match_host_streamed_upload_equals_oracle(api, monkeypatch, chunk_rows, 
             assert len(want) > 50 and T.fields_equal(got, want), (out_kind, seeded)
 
 
-def test_match_host_streamed_masked_and_unthresholded(api, everest, monkeypatch):
-    monkeypatch.setenv("SSRLCV_B200_HOST_CHUNK_ROWS", "768")
+def test_match_host_streamed_masked_and_unthresholded(api, everest, knobs):
+    knobs(chunk_rows=768)
     q, t = synth.make_pair(4000, 6000, seed=31)
     s = synth.make_seed(1000)
     sd_want = api.O.seed_distances(q, s)
@@ -317,10 +344,10 @@ def test_match_host_streamed_masked_and_unthresholded(api, everest, monkeypatch)
     assert np.array_equal(got3["keyPoints"]["loc"][v, 1], t["loc"][bi[v]])
 
 
-def test_match_host_streamed_large_norms_fall_back(api, monkeypatch):
+def test_match_host_streamed_large_norms_fall_back(api, knobs):
     """a target chunk whose norms do not fit the fold digits: the optimistic chunk launches are discarded and the pair is
     redone in one piece by the epilogue-add variant."""
-    monkeypatch.setenv("SSRLCV_B200_HOST_CHUNK_ROWS", "1024")
+    knobs(chunk_rows=1024)
     rng = np.random.default_rng(5)
     nq, nt = 1500, 5000
     qv = synth.sift_descriptors(rng, nq); tv = synth.sift_descriptors(rng, nt)
@@ -767,6 +794,182 @@ def test_do_feature_matching_two_view_golden(api, everest):
     assert ms.matches.size() == 0 and ms.keyPoints.size() == 0 and mx == 0.0
 
 
+def test_against_reference_cuda_featurematch(api):
+    """generateFeatureMatches[Constrained] (ref: src/MatchFactory.cu:654-750) against the reference's own kernels, with and without
+    seed distances.  The unconstrained form returns all numQuery entries uncompacted: the reference writes only `invalid` and
+    `distance` of an invalid entry (the rest of its local struct is uninitialised, :2325-2339), so those are compared on
+    `invalid` + `distance` and the valid ones field by field; the constrained form is compacted and compared in full."""
+    lib = _ref_lib()
+    q, t = synth.make_pair(2000, 3000, seed=72)
+    sd = api.O.seed_distances(q, synth.make_seed(500))
+    su = api.Unity(sd, np.dtype("<f4"), api.cpu)
+    mf = api.MatchFactory(0.8, 1.5e5)
+    F = np.array([[1e-6, 2e-6, 0.0015], [-3e-6, 1e-7, -1.0], [-0.0013, 1.0, 4.0]], np.float32)
+    for seed, seed_u in ((None, None), (sd, su)):
+        ref = _ref_match(lib, T.OUT_FEATUREMATCH, 0, 1.5e5, 0.8, q, t, seed)
+        got = mf.generateFeatureMatches(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t), seed_u).to_numpy()
+        assert len(ref) == len(got) == len(q)
+        assert np.array_equal(ref["invalid"] != 0, got["invalid"] != 0)
+        v = ref["invalid"] == 0
+        assert 50 < v.sum() < len(q)
+        assert T.fields_equal(got[v], ref[v]), seed is not None
+        if seed is None:        # no candidate / d2 >= abs: distance is the threshold itself; with seeds an entry that failed the ratio test keeps its d2
+            assert np.array_equal(got["distance"].view(np.uint32), ref["distance"].view(np.uint32))
+        else:
+            assert np.array_equal(got["distance"].view(np.uint32), ref["distance"].view(np.uint32))
+        ref = _ref_match(lib, T.OUT_FEATUREMATCH, 1, 1.5e5, 0.8, q, t, seed, eps=30.0, F=F)
+        got = mf.generateFeatureMatchesConstrained(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t), 30.0, F, seed_u).to_numpy()
+        assert len(ref) > 10 and T.fields_equal(got, ref), seed is not None
+
+
+def test_dropin_featurematch_equals_reference(api):
+    """the same two calls through the drop-in MatchFactory.cu (raw Unity<FeatureMatch>* API)"""
+    ref, drop = _load_harness("libssrlcv_ref.so"), _load_harness("libssrlcv_dropin.so")
+    q, t = synth.make_pair(1500, 2500, seed=73)
+    sd = api.O.seed_distances(q, synth.make_seed(400))
+    F = np.array([[1e-6, 2e-6, 0.0015], [-3e-6, 1e-7, -1.0], [-0.0013, 1.0, 4.0]], np.float32)
+    for seed in (None, sd):
+        a = _ref_match(ref, T.OUT_FEATUREMATCH, 0, 1.5e5, 0.8, q, t, seed)
+        b = _ref_match(drop, T.OUT_FEATUREMATCH, 0, 1.5e5, 0.8, q, t, seed)
+        assert len(a) == len(b) == len(q) and np.array_equal(a["invalid"] != 0, b["invalid"] != 0)
+        v = a["invalid"] == 0
+        assert v.sum() > 50 and T.fields_equal(a[v], b[v])
+        assert np.array_equal(a["distance"].view(np.uint32), b["distance"].view(np.uint32))
+        a = _ref_match(ref, T.OUT_FEATUREMATCH, 1, 1.5e5, 0.8, q, t, seed, eps=30.0, F=F)
+        b = _ref_match(drop, T.OUT_FEATUREMATCH, 1, 1.5e5, 0.8, q, t, seed, eps=30.0, F=F)
+        assert len(a) > 10 and T.fields_equal(a, b)
+
+
+@pytest.mark.parametrize("out_kind", [T.OUT_MATCH, T.OUT_DMATCH, T.OUT_PAIR, T.OUT_FEATUREMATCH])
+def test_validate_every_record_kind(api, out_kind):
+    """validateMatches x4 (ref: src/MatchFactory.cu:31-135): stable removal of invalid entries for Match / DMatch / uint2_pair (self
+    pair = invalid) / FeatureMatch, against numpy, against the reference's thrust::remove_if and through the drop-in."""
+    q, t = synth.make_pair(3000, 3000, seed=52 + out_kind)
+    p = api.O.make_params(out_kind=out_kind, query_id=3, target_id=8)
+    base = api.O.generate_matches(p, q, t)
+    assert len(base) == 3000
+    dirty = base.copy()
+    rng = np.random.default_rng(out_kind)
+    bad = rng.random(len(dirty)) < 0.37
+    if out_kind == T.OUT_PAIR:
+        dirty["b"][bad] = dirty["a"][bad]
+    else:
+        dirty["invalid"][bad] = 1
+    want = dirty[~bad]
+    mf = api.MatchFactory(1.0, FLT_MAX)
+    u = api.Unity(dirty.copy(), T.OUT_DTYPES[out_kind], api.cpu)
+    mf.validateMatches(u)
+    assert u.size() == len(want) and T.fields_equal(u.to_numpy(), want)
+    # all invalid: the reference's quirk leaves the caller's array as it was
+    allbad = base.copy()
+    if out_kind == T.OUT_PAIR:
+        allbad["b"] = allbad["a"]
+    else:
+        allbad["invalid"] = 1
+    u = api.Unity(allbad.copy(), T.OUT_DTYPES[out_kind], api.cpu)
+    mf.validateMatches(u)
+    assert u.size() == len(allbad)
+    for name in ("libssrlcv_ref.so", "libssrlcv_dropin.so"):
+        path = os.path.join(ROOT, "oracle", "_ref", name)
+        if not os.path.exists(path):
+            continue
+        lib = _load_harness(name)
+        lib.ref_validate.restype = C.c_long
+        rec = dirty.copy()
+        cwd = os.getcwd(); os.chdir("/tmp/ssrlcv_ref_run")
+        try:
+            n = lib.ref_validate(out_kind, rec.ctypes.data_as(C.c_void_p), C.c_ulong(len(rec)))
+        finally:
+            os.chdir(cwd)
+        assert n == len(want) and T.fields_equal(rec[:n], want), name
+
+
+def _exhaustive2(lib, ev, ordered, overlap):
+    n = 3
+    feats = (C.c_void_p * n)(*[v.ctypes.data for v in ev.views3])
+    nf = (C.c_ulong * n)(*[len(v) for v in ev.views3])
+    cam_bytes = [np.asarray(c).tobytes() for c in ev.cameras]
+    cams = (C.c_char_p * n)(*cam_bytes)
+    ids = (C.c_int * n)(*ev.img_ids)
+    mm = np.zeros(40000, T.MULTIMATCH); kp = np.zeros(120000, T.KEYPOINT)
+    nkp = C.c_ulong(0); ms = C.c_double(0)
+    lib.ref_exhaustive2.restype = C.c_long
+    cwd = os.getcwd(); os.chdir("/tmp/ssrlcv_ref_run")
+    try:
+        nmm = lib.ref_exhaustive2(n, feats, nf, C.cast(cams, C.POINTER(C.c_void_p)), ids, ev.seed3.ctypes.data_as(C.c_void_p), C.c_ulong(len(ev.seed3)),
+                                  C.c_float(ev.rel_threshold), C.c_float(ev.abs_threshold), C.c_float(ev.epsilon), C.c_float(ev.delta), 3,
+                                  int(ordered), C.c_float(overlap),
+                                  mm.ctypes.data_as(C.c_void_p), C.c_ulong(len(mm)), kp.ctypes.data_as(C.c_void_p), C.c_ulong(len(kp)), C.byref(nkp), C.byref(ms))
+    finally:
+        os.chdir(cwd)
+    assert nmm >= 0
+    return mm[:nmm], kp[: nkp.value]
+
+
+@pytest.mark.parametrize("ordered,overlap", [(True, 0.7), (True, 0.5), (False, 0.7)])
+def test_exhaustive_estimated_overlap_skip_rule(api, everest, ordered, overlap):
+    """The pair loop's skip rule for ordered image sets (ref: src/MatchFactory.cu:925-934; the counter is shared between the skip test
+    and the push): 3 views at overlap 0.7 run pairs 0:1 and 0:2, at 0.5 only 0:1, unordered all three.
+    The reference itself cannot run the ordered case: with `ordered && estimatedOverlap > 0` its `matchIndices[i++]` (:934) indexes
+    one past the vector it has just pushed to (i was already incremented by the skip test) -- undefined behaviour, a crash in
+    practice -- so the reference harness is driven only on the unordered case (no skip, same code path otherwise); the ordered
+    cases check the drop-in and the Python mirror against each other and against the oracle's fusion of exactly the expected pairs."""
+    from ssrlcv_b200.pair_scheduler import pair_order
+    want_pairs = {(True, 0.7): [(0, 1), (0, 2)], (True, 0.5): [(0, 1)], (False, 0.7): [(0, 1), (0, 2), (1, 2)]}[(ordered, overlap)]
+    assert pair_order(3, ordered, overlap) == want_pairs
+    ev = everest
+    drop = _load_harness("libssrlcv_dropin.so")
+    mm_d, kp_d = _exhaustive2(drop, ev, ordered, overlap)
+    assert len(mm_d) > 1000
+    if not ordered:
+        mm_r, kp_r = _exhaustive2(_load_harness("libssrlcv_ref.so"), ev, ordered, overlap)
+        assert T.fields_equal(mm_d, mm_r) and T.fields_equal(kp_d, kp_r)
+        assert T.fields_equal(mm_d, ev.g3_multimatch) and T.fields_equal(kp_d, ev.g3_keypoints)
+    mf = api.MatchFactory(ev.rel_threshold, ev.abs_threshold)
+    mf.setSeedFeatures(_unity(api, ev.seed3))
+    imgs = [api.Image(ev.img_ids[i], ev.cameras[i]) for i in range(3)]
+    ms = mf.generateMatchesExhaustive(imgs, [_unity(api, v) for v in ev.views3], ev.epsilon, ev.delta, ordered, overlap)
+    assert T.fields_equal(ms.matches.to_numpy(), mm_d) and T.fields_equal(ms.keyPoints.to_numpy(), kp_d)
+    # oracle: pair lists of exactly the expected pairs, fused
+    lists = []
+    for (a, b) in want_pairs:
+        sd = api.O.seed_distances(ev.views3[a], ev.seed3)
+        p = api.O.make_params(out_kind=T.OUT_PAIR, mask_kind=T.MASK_DOUBLE, has_seed=True, abs_threshold=ev.abs_threshold, rel_threshold=ev.rel_threshold,
+                              query_id=ev.img_ids[a], target_id=ev.img_ids[b], epsilon=ev.epsilon, delta=ev.delta,
+                              query_camera=ev.cameras[a], target_camera=ev.cameras[b])
+        lists.append(api.O.generate_matches(p, ev.views3[a], ev.views3[b], sd))
+    mm_o, kp_o = api.O.fuse_nview(ev.views3, lists)
+    assert T.fields_equal(mm_d, mm_o) and T.fields_equal(kp_d, kp_o)
+
+
+def test_exact_baseline_shapes_c2_and_c4_pair(api, everest):
+    """BASELINE.json's configs at their exact shapes against the CPU oracle: C2 = 16 384 x 16 384 + 8 192 seed features, seed-ratio test +
+    DoubleConstrained (the bench's parameters), and one pair of C4 = 32 768 x 32 768 generateMatchesIndexOnly."""
+    q, t = synth.make_pair(16384, 16384, seed=0x55524C43)
+    s = synth.make_seed(8192, seed=99)
+    mf = api.MatchFactory(0.6, 200.0 * 200.0)
+    mf.setSeedFeatures(_unity(api, s))
+    qu, tu = _unity(api, q), _unity(api, t)
+    qi, ti = api.Image(0, everest.cameras[0]), api.Image(1, everest.cameras[1])
+    sd = mf.getSeedDistances(qu)
+    sd_want = api.O.seed_distances(q, s)
+    assert np.array_equal(sd.to_numpy(), sd_want)
+    got = mf.generateDistanceMatchesDoubleConstrained(qi, qu, ti, tu, 25.0, 5.0, sd).to_numpy()
+    p = api.O.make_params(out_kind=T.OUT_DMATCH, mask_kind=T.MASK_DOUBLE, has_seed=True, abs_threshold=200.0 * 200.0, rel_threshold=0.6,
+                          query_id=0, target_id=1, epsilon=25.0, delta=5.0, query_camera=everest.cameras[0], target_camera=everest.cameras[1])
+    want = api.O.generate_matches(p, q, t, sd_want)
+    assert T.fields_equal(got, want)
+    # the same shape without the mask must find the planted correspondences (a non-empty answer at this exact shape)
+    got = mf.generateDistanceMatches(qi, qu, ti, tu, sd).to_numpy()
+    p.mask_kind = T.MASK_NONE
+    want = api.O.generate_matches(p, q, t, sd_want)
+    assert len(want) > 1000 and T.fields_equal(got, want)
+    q, t = synth.make_pair(32768, 32768, seed=0x55524C43 + 3)
+    got = mf.generateMatchesIndexOnly(api.Image(6), _unity(api, q), api.Image(7), _unity(api, t)).to_numpy()
+    want = api.O.generate_matches(api.O.make_params(out_kind=T.OUT_PAIR, abs_threshold=200.0 * 200.0, rel_threshold=0.6, query_id=6, target_id=7), q, t)
+    assert len(want) > 5000 and T.fields_equal(got, want)
+
+
 # ------------------------------------------------------------------------------------ size-independent properties at full size
 def test_c5_size_self_match_and_sharded_merge(api):
     """BASELINE C5 size (1 048 576 x 1 048 576), where the CPU oracle would take minutes: a set matched against ITSELF has a known
@@ -852,7 +1055,7 @@ def test_random_sweep_against_oracle(api, everest):
 
 
 @pytest.mark.parametrize("thr", [FLT_MAX, 1.2e5])
-def test_double_constrained_without_seeds_takes_the_x_sorted_targets(api, everest, monkeypatch, thr):
+def test_double_constrained_without_seeds_takes_the_x_sorted_targets(api, everest, knobs, thr):
     """DoubleConstrained searches without seed distances run on an x-sorted copy of the target set (api.cu sorted_of) so that whole
     32-target windows fall outside a query's epipolar segment: NaN / negative / repeated x coordinates, a ragged last window,
     both bookkeeping regimes -- same records as the oracle and as the unsorted path."""
@@ -869,11 +1072,11 @@ def test_double_constrained_without_seeds_takes_the_x_sorted_targets(api, everes
     assert len(want) > 50
     got = {}
     for so in ("1", "0"):
-        monkeypatch.setenv("SSRLCV_B200_SORTED", so)
+        knobs(sorted=so)
         mf = api.MatchFactory(1.0, thr)
         got[so] = mf.generateDistanceMatchesDoubleConstrained(qi, _unity(api, q), ti, _unity(api, t), 40.0, 5.0).to_numpy()
         assert T.fields_equal(got[so], want), so
-    monkeypatch.delenv("SSRLCV_B200_SORTED")
+    knobs(sorted=None)
     pr = api.MatchFactory(1.0, thr).generateMatchesDoubleConstrainedIndexOnly(qi, _unity(api, q), ti, _unity(api, t), 40.0, 5.0).to_numpy()
     p.out_kind = T.OUT_PAIR
     assert T.fields_equal(pr, api.O.generate_matches(p, q, t))

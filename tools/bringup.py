@@ -49,6 +49,12 @@ def compare(name, got, want):
     return ok
 
 
+def _fold(v):
+    from ssrlcv_b200 import _lib
+    from ssrlcv_b200.match_factory import Context
+    Context.get(0).tune(_lib.TUNE_FOLD, v)
+
+
 def run_engine_case(engine, nq, nt, tag, sift_like=True, seed=0):
     import numpy as np
     from oracle import oracle as O
@@ -70,17 +76,19 @@ def rung(name):
         for nq, nt in ((1, 1), (7, 33), (128, 256), (300, 1000)):
             ok &= run_engine_case(1, nq, nt, "simt")
     elif name == "tc_nofold":
-        os.environ["SSRLCV_B200_FOLD"] = "0"
+        _fold(0)
         for nq, nt in ((128, 256), (1, 1), (300, 1000), (1000, 5000)):
             ok &= run_engine_case(0, nq, nt, "tc_nofold")
+        _fold(-1)
     elif name == "tc_fold":
         for nq, nt in ((128, 256), (1, 1), (300, 1000), (1000, 5000)):
             ok &= run_engine_case(0, nq, nt, "tc_fold")
         ok &= run_engine_case(0, 500, 3000, "tc_fold_uniform_bytes", sift_like=False)
     elif name == "tc_big":
         ok &= run_engine_case(0, 16384, 16384, "tc_fold", seed=3)
-        os.environ["SSRLCV_B200_FOLD"] = "0"
+        _fold(0)
         ok &= run_engine_case(0, 8192, 20000, "tc_nofold", seed=4)
+        _fold(-1)
     elif name == "masked":
         from oracle import oracle as O
         from ssrlcv_b200 import types as T

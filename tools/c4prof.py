@@ -31,7 +31,7 @@ need = sorted({v for k in mine for v in pairs[k]})
 devbuf = {v: torch.from_numpy(views[v].view(np.uint8).reshape(-1)).cuda() for v in need}
 out = torch.zeros((len(mine), n, 4), dtype=torch.int32, device="cuda")
 p = _lib.MatchParams()
-p.absolute_threshold, p.relative_threshold, p.compact, p.engine = 4e4, 0.6, 1, 0
+p.absolute_threshold, p.relative_threshold, p.compact, p.reserved = 4e4, 0.6, 1, 0
 p.out_kind, p.mask_kind = T.OUT_PAIR, 0
 print(f"world {world}: {len(mine)} pairs, {len(need)} views on this rank")
 

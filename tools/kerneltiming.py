@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-role cycle breakdown of the matcher kernel (uses the SSRLCV_B200_TIMING diagnostics hook)."""
+"""Per-role cycle breakdown of the matcher kernel (ssrlcv_b200_tune(SSRLCV_B200_TUNE_TIMING_BUFFER): the instrumented build of the kernel)."""
 import ctypes as C
 import os
 import sys
@@ -50,7 +50,7 @@ ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=
 lib.ssrlcv_b200_set_profiling(h, 1)
 for it in range(6):
     if it == 5:
-        os.environ["SSRLCV_B200_TIMING"] = hex(tim.data_ptr())
+        lib.ssrlcv_b200_tune(h, 6, tim.data_ptr())
     lib.ssrlcv_b200_match(h, C.byref(p), hq, ht, None, 0, C.c_void_p(out.data_ptr()), C.byref(n_out))
     if it == 4:
         k_ms, k_n = C.c_double(0), C.c_uint64(0)
