@@ -667,6 +667,109 @@ def run_sharded(args, name, w, env, with_clocks=True, with_e2e=True):
     return line
 
 
+def run_c4_one_process(args, w, env):
+    """C4 through ssrlcv_b200_match_pairs_multi_gpu: ONE process (rank 0) drives every GPU of the job through the C ABI's own
+    pair scheduler (one context + host thread per device) -- the route the C++ drop-in's generateMatchesExhaustive takes.
+    View v lives on GPU v mod N (a multi-GPU feature-extraction stage leaves them spread like that); every pair list is
+    delivered to GPU 0.  The other ranks wait on the process group's store (host side: no NCCL kernel occupies their GPUs).
+    Timed per device with CUDA events inside the library (max over devices) and by the host clock around the call."""
+    torch = env.torch
+    from ssrlcv_b200 import _lib, types as T
+    from ssrlcv_b200.match_factory import MultiGpu
+    from ssrlcv_b200.pair_scheduler import pair_order
+    from tests import synth
+    rank, world = env.rank, env.world
+    store = None
+    if env.dist is not None:
+        from torch.distributed import distributed_c10d
+        store = distributed_c10d._get_default_store()
+    key = f"c4_one_process_done_{args.steps}"
+    if rank != 0:
+        env.torch.cuda.synchronize()
+        store.wait([key])
+        return None
+    line = None
+    try:
+        V, n = w["views"], w["n"]
+        views = []
+        for k in range(V // 2):
+            a, b = synth.make_pair(n, n, seed=0x55524C43 + k)
+            views += [a, b]
+        pairs = pair_order(V)
+        mg = MultiGpu.get(world)
+        lib = mg.lib
+        G = mg.device_count()
+        dev_views = [torch.from_numpy(views[v].view(np.uint8).reshape(-1)).to(f"cuda:{v % G}") for v in range(V)]
+        p = _lib.MatchParams()
+        p.absolute_threshold, p.relative_threshold, p.compact, p.reserved = ABS_THR, REL_THR, 1, 0
+        p.out_kind, p.mask_kind = T.OUT_PAIR, 0
+        m = len(pairs)
+        P = (_lib.MatchParams * m)()
+        for i, (a, b) in enumerate(pairs):
+            p.query_image_id, p.target_image_id = a, b
+            C.memmove(C.byref(P, i * C.sizeof(_lib.MatchParams)), C.byref(p), C.sizeof(_lib.MatchParams))
+        F = (C.c_void_p * V)(*[t.data_ptr() for t in dev_views])
+        N = (C.c_uint64 * V)(*([n] * V))
+        pq = (C.c_uint32 * m)(*[a for a, _ in pairs])
+        pt = (C.c_uint32 * m)(*[b for _, b in pairs])
+        out = torch.zeros((m, n, 4), dtype=torch.int32, device="cuda:0")
+        O = (C.c_void_p * m)(*[out[i].data_ptr() for i in range(m)])
+        n_out = (C.c_uint64 * m)()
+        for d in range(G):
+            torch.cuda.synchronize(d)
+
+        def step():
+            rc = lib.ssrlcv_b200_match_pairs_multi_gpu(mg.handle, V, F, N, None, 0, m, pq, pt, P, O, n_out)
+            if rc != 0:
+                raise RuntimeError(lib.ssrlcv_b200_multi_last_error(mg.handle))
+
+        for _ in range(max(args.warmup, 3)):
+            step()
+        flushes = [torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{d}") for d in range(G)]
+        dev_ms, wall_ms = [], []
+        for i in range(args.steps):
+            for d in range(G):
+                flushes[d].fill_(i & 0xFF)
+            for d in range(G):
+                torch.cuda.synchronize(d)
+            t0 = time.perf_counter()
+            step()
+            wall_ms.append((time.perf_counter() - t0) * 1e3)
+            dev_ms.append(max(lib.ssrlcv_b200_multi_device_ms(mg.handle, d) for d in range(G)))
+        counts = np.ctypeslib.as_array(n_out).copy()
+        # parity: every pair list == the single-GPU call on GPU 0
+        ctx = env.ctx
+        h = ctx.handle
+        allv = {v: (dev_views[v] if v % G == 0 else dev_views[v].to("cuda:0")) for v in range(V)}
+        solo = torch.zeros((n, 4), dtype=torch.int32, device="cuda:0")
+        ok, total, one = True, 0, C.c_uint64(0)
+        hq, ht = C.c_void_p(), C.c_void_p()
+        for k, (a, b) in enumerate(pairs):
+            ctx.check(ctx.lib.ssrlcv_b200_pack(h, C.c_void_p(allv[a].data_ptr()), n, C.byref(hq)))
+            ctx.check(ctx.lib.ssrlcv_b200_pack(h, C.c_void_p(allv[b].data_ptr()), n, C.byref(ht)))
+            p.query_image_id, p.target_image_id = a, b
+            ctx.check(ctx.lib.ssrlcv_b200_match(h, C.byref(p), hq, ht, None, 0, C.c_void_p(solo.data_ptr()), C.byref(one)))
+            ctx.lib.ssrlcv_b200_set_free(hq); ctx.lib.ssrlcv_b200_set_free(ht)
+            c = int(one.value)
+            total += c
+            ok = ok and c == int(counts[k]) and bool(torch.equal(solo[:c], out[k][:c]))
+        evals = evals_per_step(w)
+        t_dev, t_wall = sum(dev_ms) / len(dev_ms), sum(wall_ms) / len(wall_ms)
+        line = {"api": "ssrlcv_b200_match_pairs_multi_gpu (one process, one context + host thread per device)", "n_gpus": G,
+                "ms_per_step": t_dev, "wall_ms_per_step": t_wall, "scaling": "strong",
+                "value": evals / (t_dev * 1e-3), "value_wall": evals / (t_wall * 1e-3), "unit": "dist-evals/s",
+                "timing": "ms_per_step = max over devices of the CUDA-event time of each device's share (fetch ... delivery), mean over steps; "
+                          "wall_ms_per_step = host clock around the call (includes thread wake-up and the final joins)",
+                "inputs": f"view v resident on GPU v mod {G}; pair lists delivered to GPU 0", "matches_per_step": int(counts.sum()),
+                "parity": ok, "parity_note": f"every pair list == the single-GPU call on GPU 0 ({total} records)"}
+    except Exception as e:  # noqa: BLE001
+        line = {"error": repr(e)}
+    finally:
+        if store is not None:
+            store.set(key, "1")
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -704,6 +807,10 @@ def main():
                         r = {"error": repr(e)}
                     if rank == 0:
                         sub[name] = r
+                env.torch.cuda.empty_cache()
+                r = run_c4_one_process(sub_args, WORKLOADS["C4"], env)
+                if rank == 0:
+                    sub["C4_one_process"] = r
                 if line is not None:
                     line["sharded"] = sub
         env.close()

@@ -107,6 +107,8 @@ int  ssrlcv_b200_create(ssrlcv_b200_ctx** ctx, int device, void* stream);
 void ssrlcv_b200_destroy(ssrlcv_b200_ctx* ctx);
 const char* ssrlcv_b200_last_error(const ssrlcv_b200_ctx* ctx);
 int  ssrlcv_b200_synchronize(ssrlcv_b200_ctx* ctx);
+/* the cudaStream_t the context enqueues on (the one given to create(), or the library's own) */
+void* ssrlcv_b200_stream(const ssrlcv_b200_ctx* ctx);
 /* number of kernels this library has launched on the context so far (bench bookkeeping) */
 uint64_t ssrlcv_b200_launch_count(const ssrlcv_b200_ctx* ctx);
 /* bench instrumentation: when enabled, CUDA events bracket every launch of the tensor-core matcher kernel on the
@@ -153,6 +155,32 @@ int  ssrlcv_b200_match(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* par
 int  ssrlcv_b200_match_batch(ssrlcv_b200_ctx* ctx, uint32_t n_pairs, const ssrlcv_b200_match_params* params,
                              const ssrlcv_b200_set* const* queries, const ssrlcv_b200_set* const* targets,
                              const float* const* seed_dist_dev, void* const* out_dev, uint64_t* n_out);
+
+/* ---- the pair scheduler across the GPUs of one box ----------------------------------------------
+ * replaces: the pair loop of generateMatchesExhaustive (src/MatchFactory.cu:907-936) when more than one sm_100 device is
+ * visible.  One process, one context + persistent host thread per device.  multi_create: devices == NULL takes the first
+ * n_devices sm_100 devices (n_devices <= 0: all of them). */
+typedef struct ssrlcv_b200_multi ssrlcv_b200_multi;
+int  ssrlcv_b200_multi_create(ssrlcv_b200_multi** out, int n_devices, const int* devices);
+void ssrlcv_b200_multi_destroy(ssrlcv_b200_multi* m);
+int  ssrlcv_b200_multi_device_count(const ssrlcv_b200_multi* m);
+const char* ssrlcv_b200_multi_last_error(const ssrlcv_b200_multi* m);
+/* device time (ms, CUDA events on that device's stream) of the share device `index` ran in the last call: fetch of its views ...
+ * delivery of its last pair list (bench bookkeeping; the call's time is the maximum over the devices) */
+double ssrlcv_b200_multi_device_ms(const ssrlcv_b200_multi* m, int index);
+/* n_pairs independent matches (pair i: query view pair_query[i], target view pair_target[i], params[i]) dealt to the devices
+ * by cost with view affinity; every device fetches the views it needs (features[v]: n_features[v] Feature records behind ANY
+ * unified-address pointer -- host memory or any device's), packs them once, computes the seed distances of its query views
+ * (seed_features != NULL: every pair applies the seed-ratio test, like the reference's loop :915-917) and runs its pairs as
+ * one batch.  out[i]: any unified-address buffer with room for n_features[pair_query[i]] records of params[i].out_kind;
+ * n_out[i]: records written (ascending query index).  Returns when every device is done. */
+int  ssrlcv_b200_match_pairs_multi_gpu(ssrlcv_b200_multi* m, uint32_t n_views, const void* const* features,
+                                       const uint64_t* n_features, const void* seed_features, uint64_t n_seed,
+                                       uint32_t n_pairs, const uint32_t* pair_query, const uint32_t* pair_target,
+                                       const ssrlcv_b200_match_params* params, void* const* out, uint64_t* n_out);
+/* which device the scheduler gives each pair to (device_of_pair[n_pairs]); deterministic */
+int  ssrlcv_b200_multi_assignment(const ssrlcv_b200_multi* m, uint32_t n_views, const uint64_t* n_features, uint32_t n_pairs,
+                                  const uint32_t* pair_query, const uint32_t* pair_target, int32_t* device_of_pair);
 
 /* Whole reference call sequence with HOST buffers (what MatchFactory does when the Unity arrays are in
  * state `cpu`): H2D of both feature sets (+ seed set if seed_host != NULL), pack, seed distances, match,

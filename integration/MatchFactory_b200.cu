@@ -45,6 +45,29 @@ ssrlcv_b200_ctx* b200_context() {
   return ctx;
 }
 
+// More than one sm_100 device visible: generateMatchesExhaustive deals its pairs to all of them (one context + host thread per
+// device inside the library).  SSRLCV_B200_MAX_DEVICES (read once) caps the number of devices; 1 keeps everything on the
+// current device.
+ssrlcv_b200_multi* b200_multi() {
+  static ssrlcv_b200_multi* multi = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    int cap = 0;
+    if (const char* e = getenv("SSRLCV_B200_MAX_DEVICES")) cap = atoi(e);
+    int visible = 0;
+    cudaGetDeviceCount(&visible);
+    if (visible > 1 && cap != 1) {
+      ssrlcv_b200_multi* m = nullptr;
+      if (ssrlcv_b200_multi_create(&m, cap, nullptr) == 0) {
+        if (ssrlcv_b200_multi_device_count(m) > 1) multi = m;
+        else ssrlcv_b200_multi_destroy(m);
+      }
+    }
+  }
+  return multi;
+}
+
 void b200_check(int rc, const char* what) {
   if (rc == 0) return;
   logger.err.printf("ERROR: %s failed with code %d: %s", what, rc, ssrlcv_b200_last_error(b200_context()));
@@ -404,23 +427,20 @@ ssrlcv::MatchSet ssrlcv::MatchFactory<T>::generateMatchesExhaustive(std::vector<
   auto phase = [](const char*) {};
 #endif
   std::vector<MemoryState> origin(n);
-  std::vector<PackedSet*> packed;
+  std::vector<PackedSet*> packed(n, nullptr);
   PackedSet* seedPacked = nullptr;
-  {
+  ssrlcv_b200_multi* multi = n > 2 ? b200_multi() : nullptr;
+  for (size_t v = 0; v < n; ++v) {
+    origin[v] = features[v]->getMemoryState();
+    if (!b200_device_current(features[v])) features[v]->setMemoryState(gpu);
+  }
+  if (this->seedFeatures != nullptr && !b200_device_current(this->seedFeatures)) this->seedFeatures->setMemoryState(gpu);
+  if (!multi) {
     // every view (and the seed image's features) is packed once, all of them in ONE launch
     std::vector<const void*> dev;
     std::vector<uint64_t> cnt;
-    for (size_t v = 0; v < n; ++v) {
-      origin[v] = features[v]->getMemoryState();
-      if (!b200_device_current(features[v])) features[v]->setMemoryState(gpu);
-      dev.push_back(features[v]->device.get());
-      cnt.push_back(features[v]->size());
-    }
-    if (this->seedFeatures != nullptr) {
-      if (!b200_device_current(this->seedFeatures)) this->seedFeatures->setMemoryState(gpu);
-      dev.push_back(this->seedFeatures->device.get());
-      cnt.push_back(this->seedFeatures->size());
-    }
+    for (size_t v = 0; v < n; ++v) { dev.push_back(features[v]->device.get()); cnt.push_back(features[v]->size()); }
+    if (this->seedFeatures != nullptr) { dev.push_back(this->seedFeatures->device.get()); cnt.push_back(this->seedFeatures->size()); }
     b200_pack_all(dev, cnt, packed);
     if (this->seedFeatures != nullptr) { seedPacked = packed.back(); packed.pop_back(); }
   }
@@ -428,7 +448,8 @@ ssrlcv::MatchSet ssrlcv::MatchFactory<T>::generateMatchesExhaustive(std::vector<
   phase("states + pack");
   logger.info << "matching images";
   // The pair scheduler: seed distances once per query view, then every pair of the reference's loop (same order,
-  // same skip rule, ref: src/MatchFactory.cu:925-936) is handed to the library in ONE batch and synchronised once.
+  // same skip rule, ref: src/MatchFactory.cu:925-936) is handed to the library in ONE batch and synchronised once --
+  // on this device, or dealt to every sm_100 device of the box (ssrlcv_b200_match_pairs_multi_gpu).
   // The index pairs land in one grow-only device buffer (the reference cudaMallocs, compacts into a second allocation and
   // frees per pair, :909-936 via :853-905) and only the valid ones travel to the host.
 #if GEO_ORBIT == 1
@@ -469,9 +490,11 @@ ssrlcv::MatchSet ssrlcv::MatchFactory<T>::generateMatchesExhaustive(std::vector<
       memcpy(p.target_camera, &images[t]->camera, 80);
       p.compact = 1;
       params.push_back(p);
-      qsets.push_back(packed[q]->s);
-      tsets.push_back(packed[t]->s);
-      seeds.push_back(seedOfView[q] != nullptr ? seedOfView[q]->device.get() : nullptr);
+      if (!multi) {
+        qsets.push_back(packed[q]->s);
+        tsets.push_back(packed[t]->s);
+        seeds.push_back(seedOfView[q] != nullptr ? seedOfView[q]->device.get() : nullptr);
+      }
       outOffset.push_back(outRecords);
       outRecords += features[q]->size();
       pairOf.push_back(std::make_pair(q, t));
@@ -487,14 +510,32 @@ ssrlcv::MatchSet ssrlcv::MatchFactory<T>::generateMatchesExhaustive(std::vector<
   std::vector<void*> outs(params.size());
   for (size_t k = 0; k < params.size(); ++k) outs[k] = pairScratch + outOffset[k];
   std::vector<uint64_t> counts(params.size(), 0);
-  b200_check(ssrlcv_b200_match_batch(b200_context(), (uint32_t)params.size(), params.data(), qsets.data(), tsets.data(), seeds.data(),
-                                     outs.data(), counts.data()),
-             "ssrlcv_b200_match_batch");
+  if (multi) {
+    std::vector<const void*> dev(n);
+    std::vector<uint64_t> cnt(n);
+    std::vector<uint32_t> pq(params.size()), pt(params.size());
+    for (size_t v = 0; v < n; ++v) { dev[v] = features[v]->device.get(); cnt[v] = features[v]->size(); }
+    for (size_t k = 0; k < params.size(); ++k) { pq[k] = (uint32_t)pairOf[k].first; pt[k] = (uint32_t)pairOf[k].second; }
+    CudaSafeCall(cudaDeviceSynchronize());               // the workers' streams do not order themselves after the legacy stream
+    int rc = ssrlcv_b200_match_pairs_multi_gpu(multi, (uint32_t)n, dev.data(), cnt.data(),
+                                               this->seedFeatures != nullptr ? this->seedFeatures->device.get() : nullptr,
+                                               this->seedFeatures != nullptr ? this->seedFeatures->size() : 0, (uint32_t)params.size(), pq.data(),
+                                               pt.data(), params.data(), outs.data(), counts.data());
+    if (rc != 0) {
+      logger.err.printf("ERROR: ssrlcv_b200_match_pairs_multi_gpu failed with code %d: %s", rc, ssrlcv_b200_multi_last_error(multi));
+      exit(-1);
+    }
+  } else {
+    b200_check(ssrlcv_b200_match_batch(b200_context(), (uint32_t)params.size(), params.data(), qsets.data(), tsets.data(), seeds.data(),
+                                       outs.data(), counts.data()),
+               "ssrlcv_b200_match_batch");
+  }
   phase("seed distances + batch");
   std::vector<std::vector<uint2_pair>> matchIndices(params.size());
   for (size_t k = 0; k < params.size(); ++k) {
     if (counts[k] == 0) {
       // reference quirk (validateMatches, src/MatchFactory.cu:118-123): the caller keeps the uncompacted all-invalid array
+      if (this->seedFeatures != nullptr && seedOfView[pairOf[k].first] == nullptr) seedOfView[pairOf[k].first] = this->getSeedDistances(features[pairOf[k].first]);
       ptr::value<Unity<uint2_pair>> all = b200_generate<uint2_pair, T>(relativeThreshold, absoluteThreshold, SSRLCV_B200_OUT_PAIR, mask, true,
                                                                       images[pairOf[k].first], features[pairOf[k].first], images[pairOf[k].second],
                                                                       features[pairOf[k].second], epsilon, delta, nullptr, seedOfView[pairOf[k].first],
@@ -513,13 +554,15 @@ ssrlcv::MatchSet ssrlcv::MatchFactory<T>::generateMatchesExhaustive(std::vector<
     exit(0);
   }
   phase("records to host");
-  // Key-point locations: 8 bytes per feature from the packed sets instead of the whole 152-byte records the reference moves to
-  // the host (:966-967); the Unity arrays were forced to state gpu above, so none of them has a host copy right now.
+  // Key-point locations: 8 bytes per feature (a strided copy of `loc`, byte 8 of each 152-byte record) instead of the whole
+  // records the reference moves to the host (:966-967); the Unity arrays were forced to state gpu above, so none of them has a
+  // host copy right now.
   std::vector<std::vector<float2>> locOf(n);
   for (size_t v = 0; v < n; ++v) {
     locOf[v].resize(features[v]->size());
     if (!locOf[v].empty())
-      CudaSafeCall(cudaMemcpy(locOf[v].data(), ssrlcv_b200_set_loc(packed[v]->s), locOf[v].size() * sizeof(float2), cudaMemcpyDeviceToHost));
+      CudaSafeCall(cudaMemcpy2D(locOf[v].data(), sizeof(float2), (const char*)features[v]->device.get() + 8, sizeof(Feature<T>), sizeof(float2),
+                                locOf[v].size(), cudaMemcpyDeviceToHost));
   }
   for (size_t v = 0; v < n; ++v) delete packed[v];
   delete seedPacked;

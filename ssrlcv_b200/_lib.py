@@ -18,7 +18,9 @@ ERRORS = {-1: "EINVAL", -2: "ENODEVICE", -3: "ESEEDSIZE", -4: "ETHRESHOLD", -5: 
 # every symbol include/ssrlcv_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "ssrlcv_b200_abi_version", "ssrlcv_b200_create", "ssrlcv_b200_destroy", "ssrlcv_b200_last_error",
-    "ssrlcv_b200_synchronize", "ssrlcv_b200_launch_count", "ssrlcv_b200_tune", "ssrlcv_b200_set_profiling", "ssrlcv_b200_kernel_time",
+    "ssrlcv_b200_synchronize", "ssrlcv_b200_launch_count", "ssrlcv_b200_stream", "ssrlcv_b200_tune",
+    "ssrlcv_b200_multi_create", "ssrlcv_b200_multi_destroy", "ssrlcv_b200_multi_device_count", "ssrlcv_b200_multi_last_error", "ssrlcv_b200_multi_device_ms",
+    "ssrlcv_b200_match_pairs_multi_gpu", "ssrlcv_b200_multi_assignment", "ssrlcv_b200_set_profiling", "ssrlcv_b200_kernel_time",
     "ssrlcv_b200_pack", "ssrlcv_b200_pack_batch", "ssrlcv_b200_pack_host",
     "ssrlcv_b200_set_size", "ssrlcv_b200_set_free", "ssrlcv_b200_seed_distances", "ssrlcv_b200_match",
     "ssrlcv_b200_match_host", "ssrlcv_b200_match_batch", "ssrlcv_b200_match_candidates", "ssrlcv_b200_match_candidates_seeded", "ssrlcv_b200_finalize_candidates",
@@ -74,7 +76,20 @@ def load() -> C.CDLL:
     lib.ssrlcv_b200_synchronize.argtypes = [vp]
     lib.ssrlcv_b200_launch_count.argtypes = [vp]
     lib.ssrlcv_b200_launch_count.restype = u64
+    lib.ssrlcv_b200_stream.argtypes = [vp]
+    lib.ssrlcv_b200_stream.restype = vp
     lib.ssrlcv_b200_tune.argtypes = [vp, i32, C.c_int64]
+    pu32 = C.POINTER(C.c_uint32)
+    lib.ssrlcv_b200_multi_create.argtypes = [C.POINTER(vp), i32, C.POINTER(C.c_int)]
+    lib.ssrlcv_b200_multi_destroy.argtypes = [vp]
+    lib.ssrlcv_b200_multi_destroy.restype = None
+    lib.ssrlcv_b200_multi_device_count.argtypes = [vp]
+    lib.ssrlcv_b200_multi_last_error.argtypes = [vp]
+    lib.ssrlcv_b200_multi_last_error.restype = C.c_char_p
+    lib.ssrlcv_b200_multi_device_ms.argtypes = [vp, i32]
+    lib.ssrlcv_b200_multi_device_ms.restype = C.c_double
+    lib.ssrlcv_b200_match_pairs_multi_gpu.argtypes = [vp, u32, C.POINTER(vp), pu64, vp, u64, u32, pu32, pu32, pp, C.POINTER(vp), pu64]
+    lib.ssrlcv_b200_multi_assignment.argtypes = [vp, u32, pu64, u32, pu32, pu32, C.POINTER(C.c_int32)]
     lib.ssrlcv_b200_set_profiling.argtypes = [vp, i32]
     lib.ssrlcv_b200_kernel_time.argtypes = [vp, C.POINTER(C.c_double), pu64]
     lib.ssrlcv_b200_pack.argtypes = [vp, vp, u64, C.POINTER(vp)]

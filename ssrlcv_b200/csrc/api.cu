@@ -25,7 +25,7 @@ cudaError_t launch_sort_gather(cudaStream_t, const ssrlcv_b200_set_impl& src, ss
 cudaError_t launch_smax(cudaStream_t, const SmaxBatch&, int mask_kind, bool fold, bool colmask);
 // exact.cu
 void launch_exact(cudaStream_t, const SmaxArgs&, int mask_kind, int sm_count);
-void launch_exact_list(cudaStream_t, const SmaxBatch&, uint32_t* done, int mask_kind, int sm_count);
+void launch_exact_list(cudaStream_t, const SmaxBatch&, int mask_kind, int sm_count);
 void launch_endpoints(cudaStream_t, const MaskParams&, const float2*, uint64_t, float4*);
 void launch_query_masks(cudaStream_t, const MaskParams&, const float2*, uint64_t, float4*);
 void launch_sincos(cudaStream_t, const float*, uint64_t, float*, float*);
@@ -65,10 +65,12 @@ struct ssrlcv_b200_ctx {
   std::string err;
   uint64_t launches = 0;
   Workspace keys, flagged, counts, scratch, hostpin, qmask, sortws;
-  // zero-initialised once, left zero by the kernels that use them: tie counters ([0] = the tie kernel's `done` ticket),
-  // finalize tickets, finalize block states (stamped with `epoch`, so stale entries read as "not yet")
+  // zero-initialised once, left zero by the kernels that use them: tie counters (two banks: a matcher launch counts into
+  // one and clears the other for the next call), finalize tickets, finalize block states (stamped with `epoch`, so stale
+  // entries read as "not yet")
   Workspace nflag, tickets, fstate;
   uint32_t epoch = 0;
+  uint32_t flag_bank = 0;
   uint32_t* d_scalars = nullptr;   // small device scalars
   // job descriptors (SmaxJob / FinalizeArgs arrays) travel host -> device through a small ring of pinned buffers
   struct Staged { void* h = nullptr; void* d = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; bool pending = false; };
@@ -248,6 +250,7 @@ int ssrlcv_b200_tune(ssrlcv_b200_ctx* ctx, int knob, int64_t value) {
   return 0;
 }
 uint64_t ssrlcv_b200_launch_count(const ssrlcv_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* ssrlcv_b200_stream(const ssrlcv_b200_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
 
 int ssrlcv_b200_set_profiling(ssrlcv_b200_ctx* ctx, int enabled) {
   if (!ctx) return SSRLCV_B200_EINVAL;
@@ -315,11 +318,25 @@ static int set_alloc(ssrlcv_b200_ctx* ctx, uint64_t n, ssrlcv_b200_set** out, bo
   s->sigtheta = s->loc + np;
   s->wmax = reinterpret_cast<int32_t*>(s->sigtheta + np);
   s->orig = with_orig ? reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s->wmax) + wmax_bytes) : nullptr;
-  rc = encode_map(ctx, &s->map_a, s->desc, np, kDescBytes, kBM, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (!rc) rc = encode_map(ctx, &s->map_b, s->desc, np, kDescBytes, kBN, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (!rc) rc = encode_map(ctx, &s->map_ext, s->ext, np, kExtBytes, kBN, CU_TENSOR_MAP_SWIZZLE_32B);
-  if (rc) { ssrlcv_b200_set_free(s); return rc; }
+  s->has_map_a = s->has_map_bx = false;
   *out = s;
+  return 0;
+}
+// TMA descriptors of a set, encoded when the set is first used as a query (A tiles) / as a target (B + digit tiles)
+static int ensure_maps(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* cs, bool as_query, bool as_target) {
+  ssrlcv_b200_set* s = const_cast<ssrlcv_b200_set*>(cs);
+  int rc = 0;
+  if (as_query && !s->has_map_a) {
+    rc = encode_map(ctx, &s->map_a, s->desc, s->n_pad, kDescBytes, kBM, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    s->has_map_a = true;
+  }
+  if (as_target && !s->has_map_bx) {
+    rc = encode_map(ctx, &s->map_b, s->desc, s->n_pad, kDescBytes, kBN, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (!rc) rc = encode_map(ctx, &s->map_ext, s->ext, s->n_pad, kExtBytes, kBN, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (rc) return rc;
+    s->has_map_bx = true;
+  }
   return 0;
 }
 // After the last pack launch of a set: the event set_resolve waits for before it reads the verdict from the pinned word.
@@ -708,7 +725,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
   int rc = ws_reserve(ctx, ctx->keys, keys_total * sizeof(uint64_t));
   if (!rc) rc = ws_reserve(ctx, ctx->flagged, keys_total * sizeof(uint32_t));
   if (!rc && qmask_total) rc = ws_reserve(ctx, ctx->qmask, qmask_total * sizeof(float4));
-  if (!rc && n_tc) rc = ws_reserve_zero(ctx, ctx->nflag, (static_cast<size_t>(n_tc) + 1) * sizeof(uint32_t));
+  if (!rc && n_tc) rc = ws_reserve_zero(ctx, ctx->nflag, 2 * static_cast<size_t>(n_tc) * sizeof(uint32_t));
   if (rc) return rc;
   for (uint32_t i = 0; i < n; ++i) {
     SmaxArgs& a = w[i].a;
@@ -732,8 +749,12 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
   // ---- tensor-core launches: one per (mask kind, fold variant, bookkeeping regime) group
   if (n_tc) {
     // The job table of a single pair rides in the kernel's parameter block; several pairs are staged through a pinned ring
-    // (one small copy for the whole batch).  Tie counters: persistent zero words, [0] is the tie kernel's `done` ticket.
-    uint32_t* d_nflag = static_cast<uint32_t*>(ctx->nflag.p);
+    // (one small copy for the whole batch).  Tie counters: persistent words in two banks of the zero-initialised workspace;
+    // this call counts into one bank, its matcher launches clear the other for the call after it.
+    const uint32_t bank_len = static_cast<uint32_t>(ctx->nflag.cap / (2 * sizeof(uint32_t)));
+    ctx->flag_bank ^= 1u;
+    uint32_t* d_nflag = static_cast<uint32_t*>(ctx->nflag.p) + ctx->flag_bank * bank_len;
+    uint32_t* d_nflag_other = static_cast<uint32_t*>(ctx->nflag.p) + (ctx->flag_bank ^ 1u) * bank_len;
     ssrlcv_b200_ctx::Staged* st = nullptr;
     SmaxJob* hj = nullptr;
     SmaxJob single;
@@ -745,7 +766,10 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     uint32_t at = 0;
     for (Group& g : groups)
       for (uint32_t i : g.idx) {
-        w[i].a.n_flagged = d_nflag + 1 + at;
+        w[i].a.n_flagged = d_nflag + at;
+        rc = ensure_maps(ctx, w[i].q, true, false);
+        if (!rc) rc = ensure_maps(ctx, w[i].tt, false, true);
+        if (rc) return rc;
         SmaxJob& j = n_tc > 1 ? hj[at] : single;
         ++at;
         j.map_q = w[i].q->map_a; j.map_t = w[i].tt->map_b; j.map_text = w[i].tt->map_ext;
@@ -766,6 +790,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       b.n_jobs = static_cast<uint32_t>(g.idx.size());
       b.n_ctas = w[g.idx[0]].a.n_ctas;
       b.total_tiles = g.total;
+      b.clear = d_nflag_other; b.clear_n = bank_len;
       b.timing = ctx->knob[SSRLCV_B200_TUNE_TIMING_BUFFER] > 0 ? reinterpret_cast<unsigned long long*>(ctx->knob[SSRLCV_B200_TUNE_TIMING_BUFFER]) : nullptr;
       if (ctx->profiling) {
         if (ctx->prof_used == ctx->prof_events.size()) {
@@ -778,7 +803,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       cudaError_t e = launch_smax(ctx->stream, b, gi / 4, (gi & 2) != 0, (gi & 1) != 0);
       if (e != cudaSuccess) return fail(ctx, static_cast<int>(e), "smax launch: %s", cudaGetErrorString(e));
       if (ctx->profiling) { CU(cudaEventRecord(ctx->prof_events[ctx->prof_used].second, ctx->stream)); ctx->prof_used++; }
-      launch_exact_list(ctx->stream, b, d_nflag, gi / 4, ctx->sm_count);
+      launch_exact_list(ctx->stream, b, gi / 4, ctx->sm_count);
       ctx->launches += 2;
       at += b.n_jobs;
     }
@@ -1064,10 +1089,9 @@ static int make_view(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* parent, uint64
   v->norm += row0; v->wcol += row0; v->loc += row0; v->sigtheta += row0; v->wmax += row0 / kChunk;
   v->resolved = false;                                   // the parent's packs may still be in flight: optimistic fold launch
   v->is_view = true; v->sorted = nullptr;
-  int rc = encode_map(ctx, &v->map_a, v->desc, rows_pad, kDescBytes, kBM, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (!rc) rc = encode_map(ctx, &v->map_b, v->desc, rows_pad, kDescBytes, kBN, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (!rc) rc = encode_map(ctx, &v->map_ext, v->ext, rows_pad, kExtBytes, kBN, CU_TENSOR_MAP_SWIZZLE_32B);
-  return rc;
+  v->has_map_a = v->has_map_bx = false;                  // its own tensor maps, encoded on first use
+  (void)ctx;
+  return 0;
 }
 
 // How match_host cuts a set of n rows for the streamed upload: equal chunks (a multiple of kRowPad rows) of at least

@@ -91,24 +91,16 @@ __global__ void __launch_bounds__(256) exact_kernel(SmaxArgs a) {
   exact_items<kMask>(a, 0, s_min);
 }
 // tie fallback of the tensor-core engine: the flagged (slot, query) entries of every job of a launch.  The tie counters are
-// persistent device words that are zero between launches: the block that finishes last (`done` ticket) clears them again,
-// so nothing has to be zeroed or staged in front of the matcher.
+// persistent device words in two banks: a matcher launch counts into one bank and clears the other for the call after it
+// (smax_tc.cu), so nothing is zeroed or staged in front of the matcher and nothing is reset here.
 template <int kMask>
-__global__ void __launch_bounds__(256) exact_list_kernel(const __grid_constant__ SmaxBatch b, uint32_t* done) {
+__global__ void __launch_bounds__(256) exact_list_kernel(const __grid_constant__ SmaxBatch b) {
   __shared__ uint64_t s_min[8];
   const SmaxJob* jobs = b.jobs ? b.jobs : &b.inline_job;
   for (uint32_t j = 0; j < b.n_jobs; ++j) {
     if (*jobs[j].a.n_flagged == 0) continue;          // the common case: nothing to do for this job
     const SmaxArgs a = jobs[j].a;
     exact_items<kMask>(a, 1, s_min);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    if (atomicAdd(done, 1u) == gridDim.x - 1) {
-      for (uint32_t j = 0; j < b.n_jobs; ++j) *jobs[j].a.n_flagged = 0;
-      *done = 0;
-    }
   }
 }
 
@@ -120,12 +112,12 @@ void launch_exact(cudaStream_t st, const SmaxArgs& a, int mask_kind, int sm_coun
     default: exact_kernel<SSRLCV_B200_MASK_DOUBLE><<<blocks, 256, 0, st>>>(a); break;
   }
 }
-void launch_exact_list(cudaStream_t st, const SmaxBatch& b, uint32_t* done, int mask_kind, int sm_count) {
-  const int blocks = sm_count * 4;
+void launch_exact_list(cudaStream_t st, const SmaxBatch& b, int mask_kind, int sm_count) {
+  const int blocks = sm_count * 2;
   switch (mask_kind) {
-    case SSRLCV_B200_MASK_NONE: exact_list_kernel<SSRLCV_B200_MASK_NONE><<<blocks, 256, 0, st>>>(b, done); break;
-    case SSRLCV_B200_MASK_FUNDAMENTAL: exact_list_kernel<SSRLCV_B200_MASK_FUNDAMENTAL><<<blocks, 256, 0, st>>>(b, done); break;
-    default: exact_list_kernel<SSRLCV_B200_MASK_DOUBLE><<<blocks, 256, 0, st>>>(b, done); break;
+    case SSRLCV_B200_MASK_NONE: exact_list_kernel<SSRLCV_B200_MASK_NONE><<<blocks, 256, 0, st>>>(b); break;
+    case SSRLCV_B200_MASK_FUNDAMENTAL: exact_list_kernel<SSRLCV_B200_MASK_FUNDAMENTAL><<<blocks, 256, 0, st>>>(b); break;
+    default: exact_list_kernel<SSRLCV_B200_MASK_DOUBLE><<<blocks, 256, 0, st>>>(b); break;
   }
 }
 

@@ -80,6 +80,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   const bool emit = (i < nq) && (a.compact ? d.valid : true);
   const uint32_t bal = __ballot_sync(0xffffffffu, emit);
   if (lane == 0) s_warp[warp] = __popc(bal);
+  // the record's gathers are issued before the wait on the preceding blocks' counts
+  const float2 zero2 = make_float2(0.f, 0.f);
+  const float2 ql = d.valid ? a.q_loc[i] : zero2;
+  const float2 tl = (d.valid && a.t_loc) ? a.t_loc[d.f] : zero2;
   __syncthreads();
   uint32_t mine = 0;
 #pragma unroll
@@ -109,9 +113,6 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   for (int w = 0; w < warp; ++w) off += s_warp[w];
   off += __popc(bal & ((1u << lane) - 1u));
 
-  const float2 zero2 = make_float2(0.f, 0.f);
-  const float2 ql = d.valid ? a.q_loc[i] : zero2;
-  const float2 tl = (d.valid && a.t_loc) ? a.t_loc[d.f] : zero2;
   switch (a.out_kind) {
     case SSRLCV_B200_OUT_PAIR: {
       RefPair p;

@@ -150,6 +150,8 @@ struct SmaxBatch {
   uint32_t n_ctas;
   uint64_t total_tiles;
   unsigned long long* timing;    // optional [gridDim.x][16] cycle counters (diagnostics build), or nullptr
+  uint32_t* clear;               // the tie counters of the OTHER bank: zeroed by CTA 0 for the call after this one
+  uint32_t clear_n;
   SmaxJob inline_job;
 };
 
@@ -217,6 +219,7 @@ struct ssrlcv_b200_set : b200::ssrlcv_b200_set_impl {
   int32_t* h_mm;
   cudaEvent_t ready;
   bool resolved;
+  bool has_map_a, has_map_bx;    // tensor maps are encoded on first use as a query / as a target (api.cu ensure_maps)
   bool is_view;                  // rows of another set (match_host_streamed): borrowed memory
   ssrlcv_b200_set* sorted;       // cached x-sorted copy (owned), or nullptr
 };

@@ -35,72 +35,64 @@ __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackB
     const uint32_t win = w - b.jobs[j].win_begin;
     uint8_t* __restrict__ desc = b.jobs[j].desc;
     uint8_t* __restrict__ ext = b.jobs[j].ext;
-    int32_t* __restrict__ norm = b.jobs[j].norm;
-    int32_t* __restrict__ wcol = b.jobs[j].wcol;
-    float2* __restrict__ loc = b.jobs[j].loc;
-    float2* __restrict__ sigtheta = b.jobs[j].sigtheta;
     const uint64_t row0 = static_cast<uint64_t>(win) * kChunk;
-    int32_t wtop = 0;
-    bool bad = false;
-#pragma unroll 1
-    for (int it0 = 0; it0 < 16; it0 += 4) {
-      uint2 v[4];
+    // every load of the window first: 16 descriptor slices per lane (rows row0 + 2k + half) and the scalars of "its own" row
+    // row0 + 2 * sub + half, the row whose norm this lane will keep
+    uint2 v[16];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {                                   // four descriptor loads in flight per lane
-        const uint64_t i = row0 + (it0 + k) * 2 + half;
-        v[k] = make_uint2(0u, 0u);
-        if (i < n) v[k] = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(in + i) + 24 + sub * 8);
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint64_t i = row0 + (it0 + k) * 2 + half;               // < n_rows: windows are whole
-        *reinterpret_cast<uint2*>(desc + i * kDescBytes + sub * 8) = v[k];
-        uint32_t s = __dp4a(v[k].x, v[k].x, 0u);
-        s = __dp4a(v[k].y, v[k].y, s);
-#pragma unroll
-        for (int o = 8; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (sub == 0) {
-          // W = kFoldC - h as  digits[0] + 255 * sum(digits[1..31]),  every digit <= 255; zero on padding rows and on rows
-          // whose W does not fit (the whole set then takes the epilogue-add variant, which reads wcol = kNoFoldC - h)
-          uint32_t words[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          int32_t wn = 0;
-          if (i < n) {
-            const int32_t h = static_cast<int32_t>(s >> 1);
-            norm[i] = static_cast<int32_t>(s);
-            loc[i] = in[i].loc;
-            sigtheta[i] = make_float2(in[i].sigma, in[i].theta);
-            wn = kNoFoldC - h;                                         // >= 2
-            const int32_t W = kFoldC - h;
-            if (W >= 2) {
-              uint32_t rest = static_cast<uint32_t>(W) / 255u;        // <= 31 * 255, spread greedily over digits 1..31
-              words[0] = static_cast<uint32_t>(W) % 255u;
-#pragma unroll
-              for (int q = 1; q < 32; ++q) {
-                const uint32_t take = rest < 255u ? rest : 255u;
-                words[q >> 2] |= take << (8 * (q & 3));
-                rest -= take;
-              }
-            } else {
-              bad = true;
-            }
-          } else {
-            norm[i] = 0;
-            loc[i] = make_float2(0.f, 0.f);
-            sigtheta[i] = make_float2(0.f, 0.f);
-          }
-          wtop = max(wtop, wn);
-          wcol[i] = wn;
-          uint4* o = reinterpret_cast<uint4*>(ext + i * kExtBytes);
-          o[0] = make_uint4(words[0], words[1], words[2], words[3]);
-          o[1] = make_uint4(words[4], words[5], words[6], words[7]);
-        }
-      }
+    for (int k = 0; k < 16; ++k) {
+      const uint64_t i = row0 + 2 * k + half;
+      v[k] = make_uint2(0u, 0u);
+      if (i < n) v[k] = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(in + i) + 24 + sub * 8);
     }
-    wtop = max(wtop, __shfl_xor_sync(0xffffffffu, wtop, 16));          // lanes 0 and 16 hold the two halves' maxima
-    if (lane == 0) b.jobs[j].wmax[win] = wtop;                         // 0 for windows of padding only
+    const uint64_t own = row0 + 2 * sub + half;
+    uint2 own_loc = make_uint2(0u, 0u), own_st = make_uint2(0u, 0u);
+    if (own < n) {
+      own_loc = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(in + own) + 8);
+      own_st = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(in + own) + 16);
+    }
+    uint32_t own_s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const uint64_t i = row0 + 2 * k + half;                         // < n_rows: windows are whole
+      *reinterpret_cast<uint2*>(desc + i * kDescBytes + sub * 8) = v[k];
+      uint32_t s = __dp4a(v[k].x, v[k].x, 0u);
+      s = __dp4a(v[k].y, v[k].y, s);
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);   // every lane of the half-warp: |b|^2 of row i
+      own_s = k == sub ? s : own_s;
+      // W = kFoldC - h as  digits[0] + 255 * sum(digits[1..31]),  every digit <= 255, spread greedily over digits 1..31: the first
+      // nfull of them are 255, the next one holds the remainder.  Zero on padding rows and on rows whose W does not fit (the
+      // whole set then takes the epilogue-add variant, which reads wcol = kNoFoldC - h).  Lane `sub` writes digits 2 sub, 2 sub + 1.
+      const int32_t W = kFoldC - static_cast<int32_t>(s >> 1);
+      uint32_t pair16 = 0;
+      if (i < n && W >= 2) {
+        const uint32_t rest = static_cast<uint32_t>(W) / 255u, d0 = static_cast<uint32_t>(W) % 255u;
+        const uint32_t nfull = rest / 255u, rem = rest % 255u;       // rest <= 31 * 255
+        const uint32_t j0 = 2u * sub, j1 = j0 + 1u;
+        const uint32_t b0 = j0 == 0 ? d0 : (j0 <= nfull ? 255u : (j0 == nfull + 1 ? rem : 0u));
+        const uint32_t b1 = j1 <= nfull ? 255u : (j1 == nfull + 1 ? rem : 0u);
+        pair16 = b0 | (b1 << 8);
+      }
+      *reinterpret_cast<uint16_t*>(ext + i * kExtBytes + 2 * sub) = static_cast<uint16_t>(pair16);
+    }
+    // the window's scalars, one row per lane
+    int32_t wn = 0;
+    bool bad = false;
+    if (own < n) {
+      const int32_t h = static_cast<int32_t>(own_s >> 1);
+      wn = kNoFoldC - h;                                              // >= 2
+      bad = kFoldC - h < 2;
+    }
+    b.jobs[j].norm[own] = own < n ? static_cast<int32_t>(own_s) : 0;
+    b.jobs[j].wcol[own] = wn;
+    b.jobs[j].loc[own] = make_float2(__uint_as_float(own_loc.x), __uint_as_float(own_loc.y));
+    b.jobs[j].sigtheta[own] = make_float2(__uint_as_float(own_st.x), __uint_as_float(own_st.y));
+    const int32_t wtop = __reduce_max_sync(0xffffffffu, wn);
+    if (lane == 0) b.jobs[j].wmax[win] = wtop;                        // 0 for windows of padding only
     if (__any_sync(0xffffffffu, bad) && lane == 0) {
       atomicOr(b.jobs[j].meta, 1);
-      *reinterpret_cast<volatile int32_t*>(b.jobs[j].h_meta) = 1;      // pinned host word, read after the set's `ready` event
+      *reinterpret_cast<volatile int32_t*>(b.jobs[j].h_meta) = 1;     // pinned host word, read after the set's `ready` event
     }
   }
 }

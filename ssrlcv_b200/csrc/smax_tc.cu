@@ -391,6 +391,9 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  if (blockIdx.x == 0)                                 // tie counters of the other bank (the next call's): see exact.cu
+    for (uint32_t i = threadIdx.x; i < batch.clear_n; i += kThreads) batch.clear[i] = 0;
+
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kEpiWarps); }

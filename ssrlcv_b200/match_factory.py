@@ -132,6 +132,83 @@ def pack_many(ctx: Context, sets) -> list:
     return [pack(ctx, u) for u in sets]
 
 
+class MultiGpu:
+    """The pair scheduler across the sm_100 devices of the box (ssrlcv_b200_match_pairs_multi_gpu): one process, one library
+    context + host thread per device.  replaces: the pair loop of generateMatchesExhaustive (ref: src/MatchFactory.cu:907-936)."""
+    _instances: dict = {}
+
+    def __init__(self, n_devices: int = 0):
+        self.lib = _lib.load()
+        self.handle = C.c_void_p()
+        rc = self.lib.ssrlcv_b200_multi_create(C.byref(self.handle), int(n_devices), None)
+        if rc != 0:
+            raise _lib.B200Error(rc, "ssrlcv_b200_multi_create failed (needs sm_100 GPUs)")
+
+    @classmethod
+    def get(cls, n_devices: int = 0) -> "MultiGpu":
+        if n_devices not in cls._instances:
+            cls._instances[n_devices] = cls(n_devices)
+        return cls._instances[n_devices]
+
+    def device_count(self) -> int:
+        return int(self.lib.ssrlcv_b200_multi_device_count(self.handle))
+
+    @staticmethod
+    def _pointer(u):
+        """(address, rows) of a Feature array: Unity (device copy if it has one, else host), numpy array or torch tensor"""
+        if isinstance(u, Unity):
+            if u.getMemoryState() in (gpu, both) and u.device is not None:
+                return u.device_ptr() if u.size() else 0, u.size()
+            return (u.host.ctypes.data if u.size() else 0), u.size()
+        if isinstance(u, np.ndarray):
+            return (u.ctypes.data if len(u) else 0), len(u)
+        return (u.data_ptr() if u.numel() else 0), u.numel() // T.FEATURE.itemsize
+
+    def assignment(self, sizes, pairs):
+        n = len(pairs)
+        dev = (C.c_int32 * max(n, 1))()
+        pq = (C.c_uint32 * max(n, 1))(*[p[0] for p in pairs])
+        pt = (C.c_uint32 * max(n, 1))(*[p[1] for p in pairs])
+        rc = self.lib.ssrlcv_b200_multi_assignment(self.handle, len(sizes), (C.c_uint64 * len(sizes))(*sizes), n, pq, pt, dev)
+        if rc != 0:
+            raise _lib.B200Error(rc, "ssrlcv_b200_multi_assignment")
+        return [int(x) for x in dev[:n]]
+
+    def match_pairs(self, features, pairs, params, seed=None, out_device: int = 0):
+        """features: one Feature array per view; pairs: [(query view, target view)]; params: one MatchParams per pair.
+        Returns one Unity per pair (state gpu on `out_device`), exactly what the single-GPU generate* call returns."""
+        import torch
+
+        n_views, n = len(features), len(pairs)
+        ptrs, sizes = zip(*[self._pointer(f) for f in features]) if n_views else ((), ())
+        F = (C.c_void_p * max(n_views, 1))(*ptrs)
+        N = (C.c_uint64 * max(n_views, 1))(*sizes)
+        sp, sn = self._pointer(seed) if seed is not None else (None, 0)
+        P = (_lib.MatchParams * max(n, 1))()
+        for i, p in enumerate(params):
+            C.memmove(C.byref(P, i * C.sizeof(_lib.MatchParams)), C.byref(p), C.sizeof(_lib.MatchParams))
+        pq = (C.c_uint32 * max(n, 1))(*[p[0] for p in pairs])
+        pt = (C.c_uint32 * max(n, 1))(*[p[1] for p in pairs])
+        outs, O = [], (C.c_void_p * max(n, 1))()
+        for i, (q, _) in enumerate(pairs):
+            dt = T.OUT_DTYPES[params[i].out_kind]
+            o = torch.empty(max(sizes[q], 1) * dt.itemsize, dtype=torch.uint8, device=f"cuda:{out_device}")
+            outs.append(o)
+            O[i] = o.data_ptr()
+        torch.cuda.synchronize()                          # the workers' streams are not ordered after torch's
+        n_out = (C.c_uint64 * max(n, 1))()
+        rc = self.lib.ssrlcv_b200_match_pairs_multi_gpu(self.handle, n_views, F, N, C.c_void_p(sp) if sp else None, sn, n, pq, pt, P, O, n_out)
+        if rc != 0:
+            msg = self.lib.ssrlcv_b200_multi_last_error(self.handle)
+            raise _lib.B200Error(rc, msg.decode() if msg else "")
+        res = []
+        for i in range(n):
+            dt = T.OUT_DTYPES[params[i].out_kind]
+            k = int(n_out[i])
+            res.append(Unity(outs[i][: k * dt.itemsize], dt, gpu, out_device, k))
+        return res
+
+
 class MatchFactory:
     def __init__(self, relativeThreshold: float = 1.0, absoluteThreshold: float = FLT_MAX, device: int = 0,
                  engine: int = ENGINE_TCGEN05):

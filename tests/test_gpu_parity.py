@@ -803,21 +803,19 @@ def test_against_reference_cuda_featurematch(api):
     q, t = synth.make_pair(2000, 3000, seed=72)
     sd = api.O.seed_distances(q, synth.make_seed(500))
     su = api.Unity(sd, np.dtype("<f4"), api.cpu)
-    mf = api.MatchFactory(0.8, 1.5e5)
+    mf = api.MatchFactory(0.8, 6.0e4)
     F = np.array([[1e-6, 2e-6, 0.0015], [-3e-6, 1e-7, -1.0], [-0.0013, 1.0, 4.0]], np.float32)
     for seed, seed_u in ((None, None), (sd, su)):
-        ref = _ref_match(lib, T.OUT_FEATUREMATCH, 0, 1.5e5, 0.8, q, t, seed)
+        ref = _ref_match(lib, T.OUT_FEATUREMATCH, 0, 6.0e4, 0.8, q, t, seed)
         got = mf.generateFeatureMatches(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t), seed_u).to_numpy()
         assert len(ref) == len(got) == len(q)
         assert np.array_equal(ref["invalid"] != 0, got["invalid"] != 0)
         v = ref["invalid"] == 0
         assert 50 < v.sum() < len(q)
         assert T.fields_equal(got[v], ref[v]), seed is not None
-        if seed is None:        # no candidate / d2 >= abs: distance is the threshold itself; with seeds an entry that failed the ratio test keeps its d2
-            assert np.array_equal(got["distance"].view(np.uint32), ref["distance"].view(np.uint32))
-        else:
-            assert np.array_equal(got["distance"].view(np.uint32), ref["distance"].view(np.uint32))
-        ref = _ref_match(lib, T.OUT_FEATUREMATCH, 1, 1.5e5, 0.8, q, t, seed, eps=30.0, F=F)
+        # no candidate / d2 >= abs: distance is the threshold itself; an entry that failed the ratio test keeps its d2
+        assert np.array_equal(got["distance"].view(np.uint32), ref["distance"].view(np.uint32))
+        ref = _ref_match(lib, T.OUT_FEATUREMATCH, 1, 6.0e4, 0.8, q, t, seed, eps=30.0, F=F)
         got = mf.generateFeatureMatchesConstrained(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t), 30.0, F, seed_u).to_numpy()
         assert len(ref) > 10 and T.fields_equal(got, ref), seed is not None
 
@@ -829,14 +827,14 @@ def test_dropin_featurematch_equals_reference(api):
     sd = api.O.seed_distances(q, synth.make_seed(400))
     F = np.array([[1e-6, 2e-6, 0.0015], [-3e-6, 1e-7, -1.0], [-0.0013, 1.0, 4.0]], np.float32)
     for seed in (None, sd):
-        a = _ref_match(ref, T.OUT_FEATUREMATCH, 0, 1.5e5, 0.8, q, t, seed)
-        b = _ref_match(drop, T.OUT_FEATUREMATCH, 0, 1.5e5, 0.8, q, t, seed)
+        a = _ref_match(ref, T.OUT_FEATUREMATCH, 0, 6.0e4, 0.8, q, t, seed)
+        b = _ref_match(drop, T.OUT_FEATUREMATCH, 0, 6.0e4, 0.8, q, t, seed)
         assert len(a) == len(b) == len(q) and np.array_equal(a["invalid"] != 0, b["invalid"] != 0)
         v = a["invalid"] == 0
         assert v.sum() > 50 and T.fields_equal(a[v], b[v])
         assert np.array_equal(a["distance"].view(np.uint32), b["distance"].view(np.uint32))
-        a = _ref_match(ref, T.OUT_FEATUREMATCH, 1, 1.5e5, 0.8, q, t, seed, eps=30.0, F=F)
-        b = _ref_match(drop, T.OUT_FEATUREMATCH, 1, 1.5e5, 0.8, q, t, seed, eps=30.0, F=F)
+        a = _ref_match(ref, T.OUT_FEATUREMATCH, 1, 6.0e4, 0.8, q, t, seed, eps=30.0, F=F)
+        b = _ref_match(drop, T.OUT_FEATUREMATCH, 1, 6.0e4, 0.8, q, t, seed, eps=30.0, F=F)
         assert len(a) > 10 and T.fields_equal(a, b)
 
 
@@ -968,6 +966,59 @@ def test_exact_baseline_shapes_c2_and_c4_pair(api, everest):
     got = mf.generateMatchesIndexOnly(api.Image(6), _unity(api, q), api.Image(7), _unity(api, t)).to_numpy()
     want = api.O.generate_matches(api.O.make_params(out_kind=T.OUT_PAIR, abs_threshold=200.0 * 200.0, rel_threshold=0.6, query_id=6, target_id=7), q, t)
     assert len(want) > 5000 and T.fields_equal(got, want)
+
+
+# ------------------------------------------------------------------------------------ the pair scheduler across devices (C ABI)
+def _multi_gpu_case(api, everest, n_devices):
+    """ssrlcv_b200_match_pairs_multi_gpu: 5 views of different sizes, all 10 pairs, seed-ratio test + DoubleConstrained (what
+    generateMatchesExhaustive runs under GEO_ORBIT=1), views handed over as device arrays, pinned-free host arrays and a mix;
+    every pair list equals the single-GPU batch and the oracle."""
+    from ssrlcv_b200.match_factory import MultiGpu
+    from ssrlcv_b200.pair_scheduler import pair_order
+    mg = MultiGpu.get(n_devices)
+    sizes = (1500, 2300, 900, 3100, 1280)
+    views = [synth.make_pair(n, 16, seed=400 + i)[0] for i, n in enumerate(sizes)]
+    seed = synth.make_seed(500)
+    mf = api.MatchFactory(0.8, 9.0e4)
+    imgs = [api.Image(i, everest.cameras[i % 3]) for i in range(5)]
+    pairs = pair_order(5)
+    params = [mf._params(T.OUT_PAIR, T.MASK_DOUBLE, imgs[a], imgs[b], 2000.0, 5.0) for a, b in pairs]
+    dev_of = mg.assignment(list(sizes), pairs)
+    assert len(set(dev_of)) == mg.device_count() and len(dev_of) == 10
+    want = []
+    for (a, b), p in zip(pairs, params):
+        sd = api.O.seed_distances(views[a], seed)
+        po = api.O.make_params(out_kind=T.OUT_PAIR, mask_kind=T.MASK_DOUBLE, has_seed=True, abs_threshold=9.0e4, rel_threshold=0.8, query_id=a, target_id=b,
+                               epsilon=2000.0, delta=5.0, query_camera=everest.cameras[a % 3], target_camera=everest.cameras[b % 3])
+        want.append(api.O.generate_matches(po, views[a], views[b], sd))
+    assert sum(len(x) for x in want) > 500
+    on_dev = [_unity(api, v) for v in views]
+    for u in on_dev:
+        u.setMemoryState(api.gpu)
+    for feats, sd_in in ((on_dev, _unity(api, seed)), (views, seed), ([on_dev[0], views[1], on_dev[2], views[3], on_dev[4]], seed)):
+        got = mg.match_pairs(feats, pairs, params, seed=sd_in)
+        for g, w_ in zip(got, want):
+            if len(w_) == 0:
+                assert g.size() == 0
+            else:
+                assert T.fields_equal(g.to_numpy(), w_)
+    # unseeded, DMatch, unmasked: other record kind through the same entry
+    params2 = [mf._params(T.OUT_DMATCH, T.MASK_NONE, imgs[a], imgs[b]) for a, b in pairs]
+    got = mg.match_pairs(on_dev, pairs, params2)
+    for (a, b), g in zip(pairs, got):
+        w_ = api.O.generate_matches(api.O.make_params(out_kind=T.OUT_DMATCH, abs_threshold=9.0e4, query_id=a, target_id=b), views[a], views[b])
+        assert T.fields_equal(g.to_numpy(), w_)
+
+
+def test_multi_gpu_entry_on_one_device(api, everest):
+    _multi_gpu_case(api, everest, 1)
+
+
+def test_multi_gpu_entry_on_every_device(api, everest):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    _multi_gpu_case(api, everest, 0)
 
 
 # ------------------------------------------------------------------------------------ size-independent properties at full size
