@@ -70,8 +70,7 @@ enum {
   SSRLCV_B200_TUNE_CROSSCHECK_SIMT = 5,       /* 1: evaluate distances with the SIMT cross-check kernel instead of tcgen05     */
   SSRLCV_B200_TUNE_TIMING_BUFFER = 6,         /* device address of u64[148][16] cycle counters: runs the instrumented build of the
                                                  matcher kernel (tools/kerneltiming.py); 0 / -1 = off                           */
-  SSRLCV_B200_TUNE_SPLIT_N = 7,               /* 0 / 1: accumulator hand-off per 256-column tile / per 128-column half            */
-  SSRLCV_B200_TUNE_COUNT_ = 8
+  SSRLCV_B200_TUNE_COUNT_ = 7
 };
 /* internal engine ids (kept for the library's own use) */
 enum { SSRLCV_B200_ENGINE_TCGEN05 = 0, SSRLCV_B200_ENGINE_SIMT = 1 };

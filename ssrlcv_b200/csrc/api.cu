@@ -791,7 +791,6 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       b.n_ctas = w[g.idx[0]].a.n_ctas;
       b.total_tiles = g.total;
       b.clear = d_nflag_other; b.clear_n = bank_len;
-      b.split_n = ctx->knob[SSRLCV_B200_TUNE_SPLIT_N] > 0 ? 1u : 0u;
       b.timing = ctx->knob[SSRLCV_B200_TUNE_TIMING_BUFFER] > 0 ? reinterpret_cast<unsigned long long*>(ctx->knob[SSRLCV_B200_TUNE_TIMING_BUFFER]) : nullptr;
       if (ctx->profiling) {
         if (ctx->prof_used == ctx->prof_events.size()) {

@@ -152,7 +152,6 @@ struct SmaxBatch {
   unsigned long long* timing;    // optional [gridDim.x][16] cycle counters (diagnostics build), or nullptr
   uint32_t* clear;               // the tie counters of the OTHER bank: zeroed by CTA 0 for the call after this one
   uint32_t clear_n;
-  uint32_t split_n;              // accumulator hand-off per 128-column half instead of per 256-column tile (smax_tc.cu)
   SmaxJob inline_job;
 };
 

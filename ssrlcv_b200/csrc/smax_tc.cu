@@ -63,7 +63,7 @@ struct SmemLayout {
   static constexpr uint32_t col_w = bext;                                // kColStages x 1 KB   (no-fold variants)
   static constexpr uint32_t col_wmax = col_w + kColStages * kColWBytes;  // kColStages x 32 B   (8 window bounds per tile)
   static constexpr uint32_t bars = col_loc + kColStages * kColLocBytes;
-  static constexpr uint32_t n_bars = 2 * kStages + 4 + 8 + 2 * kColStages + 4;
+  static constexpr uint32_t n_bars = 2 * kStages + 4 + 4 + 2 * kColStages + 4;
   static constexpr uint32_t tmem_ptr = bars + n_bars * 8;
   static constexpr uint32_t xch = tmem_ptr + 16;                         // 2 (unit parity) x 2 (half) x 128 rows x 24 B
   static constexpr uint32_t total = xch + 2 * 2 * kBM * 24;
@@ -371,11 +371,7 @@ struct UnitIter {
 template <int kMask, bool kFold, bool kColMask, bool kTiming>
 __global__ void __launch_bounds__(kThreads, 1)
 smax_kernel(const __grid_constant__ SmaxBatch batch) {
-  // Unmasked no-fold: the epilogue reads the windows' W bounds (16 bytes per warp and tile) straight from global memory, two
-  // tiles ahead, and the 32 W values of a window only in the rare path -- no staging ring, no producer hand-shake per tile.
-  // Masked variants stage the target locations (and, no-fold, W and the bounds) through the shared-memory column ring.
-  constexpr bool kWGlobal = !kFold && kMask == SSRLCV_B200_MASK_NONE;
-  constexpr bool kCols = kMask != SSRLCV_B200_MASK_NONE;               // epilogue needs per-target data staged in shared memory
+  constexpr bool kCols = (kMask != SSRLCV_B200_MASK_NONE) || !kFold;   // epilogue needs per-target data (locations / W)
   constexpr int32_t kWOffset = kFold ? kFoldC : kNoFoldC;               // the C of W_b = C - h_b
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -385,12 +381,9 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
   uint64_t* empty = bars + kStages;              // [kStages]   MMA -> TMA
   uint64_t* a_full = bars + 2 * kStages;         // [2]
   uint64_t* a_empty = a_full + 2;                // [2]
-  // accumulator hand-off: [accumulator][128-column half].  Whole-tile mode uses [acc][0] only (one commit per 256-column tile,
-  // eight epilogue warps release it); split mode (SmaxBatch::split_n) commits and releases each 128-column half on its own, so the
-  // half-0 warps start while the tensor pipe still works on half 1 and the pipe may run up to four half-tiles ahead.
-  uint64_t* t_full = a_empty + 2;                // [4]         MMA -> epilogue (accumulator ready)
-  uint64_t* t_empty = t_full + 4;                // [4]         epilogue -> MMA (accumulator copied out of TMEM)
-  uint64_t* c_full = t_empty + 4;                // [kColStages] TMA -> epilogue (target columns data)
+  uint64_t* t_full = a_empty + 2;                // [2]         MMA -> epilogue (accumulator ready)
+  uint64_t* t_empty = t_full + 2;                // [2]         epilogue -> MMA (accumulator copied out of TMEM)
+  uint64_t* c_full = t_empty + 2;                // [kColStages] TMA -> epilogue (target columns data)
   uint64_t* c_empty = c_full + kColStages;       // [kColStages]
   uint64_t* x_full = c_empty + kColStages;       // [2] epilogue -> resolver warps (window states of a finished unit)
   uint64_t* x_empty = x_full + 2;                // [2] resolver -> epilogue
@@ -403,8 +396,7 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
 
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], batch.split_n ? kEpiWarps / 2 : kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kEpiWarps); }
     for (int i = 0; i < kColStages; ++i) { mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], kEpiWarps); }
     for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], kEpiWarps); mbar_init(&x_empty[i], 2); }
     fence_mbar_init();
@@ -480,8 +472,6 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
     // =============================== MMA issuer ===============================
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_i8(kBM, kBN, 0, 0);
-      constexpr uint32_t idesc_half = make_idesc_i8(kBM, kBN / 2, 0, 0);
-      const bool split = batch.split_n != 0;
       const uint64_t aext_desc = make_smem_desc(smem_u32(smem + SmemLayout::aext), 256, kSwizzle32B);
       uint32_t stage = 0, phase = 0, aslot = 0, aphase = 0, acc = 0, accphase = 0;
       long long tm_wait_acc = 0, tm_wait_full = 0, tm_total0 = 0;
@@ -493,37 +483,22 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
         for (uint32_t j = u.j0; j < u.j1; ++j) {
           long long c0 = 0, c1 = 0, c2 = 0;
           if (kTiming) c0 = clock64();
-          if (!split) mbar_wait(&t_empty[2 * acc], accphase ^ 1);
+          mbar_wait(&t_empty[acc], accphase ^ 1);
           if (kTiming) c1 = clock64();
           mbar_wait(&full[stage], phase);
           if (kTiming) { c2 = clock64(); tm_wait_acc += c1 - c0; tm_wait_full += c2 - c1; }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kBN;
           const uint64_t b_desc = make_smem_desc(smem_u32(smem + SmemLayout::b + stage * kBBytes), 1024, kSwizzle128B);
-          const uint64_t bext_desc = make_smem_desc(smem_u32(smem + SmemLayout::bext + stage * kBExtBytes), 256, kSwizzle32B);
-          if (!split) {
 #pragma unroll
-            for (uint32_t k = 0; k < 4; ++k)   // +32 bytes along K inside the 128-byte swizzle atom = +2 in the address field
-              mma_i8_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, k);
-            if (kFold) mma_i8_ss(d_tmem, aext_desc, bext_desc, idesc, 1);
-            mma_commit(&empty[stage]);
-            mma_commit(&t_full[2 * acc]);
-          } else {
-#pragma unroll
-            for (uint32_t h = 0; h < 2; ++h) {   // rows [128 h, 128 h + 128) of the B tile -> columns [128 h, ...) of the accumulator
-              long long w0 = 0;
-              if (kTiming) w0 = clock64();
-              mbar_wait(&t_empty[2 * acc + h], accphase ^ 1);
-              if (kTiming) tm_wait_acc += clock64() - w0;
-              tc_fence_after();
-              const uint64_t bh = b_desc + h * ((kBN / 2) * kDescBytes >> 4);
-#pragma unroll
-              for (uint32_t k = 0; k < 4; ++k) mma_i8_ss(d_tmem + h * (kBN / 2), a_desc + 2 * k, bh + 2 * k, idesc_half, k);
-              if (kFold) mma_i8_ss(d_tmem + h * (kBN / 2), aext_desc, bext_desc + h * ((kBN / 2) * kExtBytes >> 4), idesc_half, 1);
-              mma_commit(&t_full[2 * acc + h]);
-            }
-            mma_commit(&empty[stage]);
+          for (uint32_t k = 0; k < 4; ++k)   // +32 bytes along K inside the 128-byte swizzle atom = +2 in the address field
+            mma_i8_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, k);
+          if (kFold) {
+            const uint64_t bext_desc = make_smem_desc(smem_u32(smem + SmemLayout::bext + stage * kBExtBytes), 256, kSwizzle32B);
+            mma_i8_ss(d_tmem, aext_desc, bext_desc, idesc, 1);
           }
+          mma_commit(&empty[stage]);
+          mma_commit(&t_full[acc]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
           if (++acc == 2) { acc = 0; accphase ^= 1; }
         }
@@ -587,13 +562,6 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
       const uint32_t row_c = min(row, args.nq_pad - 1);
       const float eps = args.eps;
       const bool sorted = args.t_orig != nullptr;
-      const int32_t* g_wcol = args.t_wcol;
-      const int4* g_wmax = reinterpret_cast<const int4*>(args.t_wmax) + half;   // tile j: 8 bounds = two int4, this warp's half
-      int4 wb_pre0 = make_int4(0, 0, 0, 0), wb_pre1 = make_int4(0, 0, 0, 0);
-      if (kWGlobal) {
-        wb_pre0 = __ldg(g_wmax + 2 * static_cast<uint64_t>(u.j0));
-        if (u.j0 + 1 < u.j1) wb_pre1 = __ldg(g_wmax + 2 * static_cast<uint64_t>(u.j0 + 1));
-      }
       QueryMask qm;
       if (kMask != SSRLCV_B200_MASK_NONE) qm = load_query_mask<kMask>(args.q_mask + 2 * static_cast<uint64_t>(row_c));
 
@@ -628,17 +596,10 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
         if (kTiming) te_cwait += clock64() - cw0;
         int32_t wbound[kWinPerWarp] = {0, 0, 0, 0};                // no-fold: largest W of each of this warp's windows
         if (!kFold) {
-          int4 wb;
-          if (kWGlobal) {
-            wb = wb_pre0; wb_pre0 = wb_pre1;
-            if (j + 2 < u.j1) wb_pre1 = __ldg(g_wmax + 2 * static_cast<uint64_t>(j + 2));
-          } else {
-            wb = ld_shared_v4(smem_u32(smem + SmemLayout::col_wmax + cs * kColWmaxBytes + half * (kWinPerWarp * 4)));
-          }
+          const int4 wb = ld_shared_v4(smem_u32(smem + SmemLayout::col_wmax + cs * kColWmaxBytes + half * (kWinPerWarp * 4)));
           wbound[0] = wb.x; wbound[1] = wb.y; wbound[2] = wb.z; wbound[3] = wb.w;
         }
-        const uint32_t tb = 2 * acc + (batch.split_n ? half : 0u);
-        mbar_wait(&t_full[tb], accphase);
+        mbar_wait(&t_full[acc], accphase);
         if (kTiming) e1 = clock64();
         tc_fence_after();
         const float2* s_loc = reinterpret_cast<const float2*>(smem + SmemLayout::col_loc + cs * kColLocBytes);
@@ -652,7 +613,7 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[tb]);
+        if (lane == 0) mbar_arrive(&t_empty[acc]);
 
         // Window maxima of this warp's 4 windows, straight from the accumulator: one branch-free block (the four max trees
         // interleave).  Fold, unmasked: these ARE the windows' best scores.  Otherwise they are upper bounds of them:
@@ -688,10 +649,9 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
               if (kTiming) ++te_live;
               if (!kFold) {                                        // exact scores, as the fold variant gets them from the tensor pipe
                 const uint32_t wp = smem_u32(s_w + (c_begin + k) * kChunk);
-                const int4* wg = reinterpret_cast<const int4*>(g_wcol + static_cast<uint64_t>(j) * kBN + (c_begin + k) * kChunk);
 #pragma unroll
                 for (int e = 0; e < 32; e += 4) {
-                  const int4 w4 = kWGlobal ? __ldg(wg + (e >> 2)) : ld_shared_v4(wp + 4 * e);
+                  const int4 w4 = ld_shared_v4(wp + 4 * e);
                   x[e] += static_cast<uint32_t>(w4.x); x[e + 1] += static_cast<uint32_t>(w4.y);
                   x[e + 2] += static_cast<uint32_t>(w4.z); x[e + 3] += static_cast<uint32_t>(w4.w);
                 }

@@ -29,6 +29,12 @@ else:
 print("workload", w, "abs", abs_thr, "eps", eps)
 ctx = Context.get(0)
 lib, h = ctx.lib, ctx.handle
+# KT_FOLD / KT_SPLIT: force a matcher variant (ssrlcv_b200_tune)
+if os.environ.get("KT_FOLD"):
+    lib.ssrlcv_b200_tune(h, _lib.TUNE_FOLD, int(os.environ["KT_FOLD"]))
+if os.environ.get("KT_COLMASK"):
+    lib.ssrlcv_b200_tune(h, _lib.TUNE_COLUMN_MASKS, int(os.environ["KT_COLMASK"]))
+print("fold", os.environ.get("KT_FOLD", "auto"), "colmask", os.environ.get("KT_COLMASK", "auto"))
 q, t, s = synth_inputs(w, 0)
 qd = torch.from_numpy(q.view(np.uint8).reshape(-1)).cuda()
 td = torch.from_numpy(t.view(np.uint8).reshape(-1)).cuda()
