@@ -128,6 +128,21 @@ int  ssrlcv_b200_pack(ssrlcv_b200_ctx* ctx, const void* features_dev, uint64_t n
 int  ssrlcv_b200_pack_batch(ssrlcv_b200_ctx* ctx, uint32_t n_sets, const void* const* features_dev, const uint64_t* n,
                             ssrlcv_b200_set** out);
 int  ssrlcv_b200_pack_host(ssrlcv_b200_ctx* ctx, const void* features_host, uint64_t n, ssrlcv_b200_set** out);
+/* Producer hand-off (replaces: the 152-byte AoS stores at the end of fillDescriptors, src/SIFT_FeatureFactory.cu:533-548, and
+ * with them the whole pack pass): set_alloc reserves an EMPTY packed set of n rows; set_arrays_of returns the device arrays the
+ * producer's kernel writes in place -- desc[row][128] descriptor bytes, loc[row] = (x, y), sigma_theta[row] = (sigma, theta),
+ * rows [0, n) (device-side helpers: include/ssrlcv_b200_packed.cuh); set_commit (enqueue-only, one launch) then derives the
+ * norms, fold digits and window bounds and zero-fills the padding.  The producer's work must be ordered before the context's
+ * stream when set_commit is called (same stream, or an event wait). */
+typedef struct {
+  uint8_t* desc;         /* uint8[n_pad][128] */
+  float*   loc;          /* float2[n_pad]     */
+  float*   sigma_theta;  /* float2[n_pad]     */
+  uint64_t n, n_pad;
+} ssrlcv_b200_set_arrays;
+int  ssrlcv_b200_set_alloc(ssrlcv_b200_ctx* ctx, uint64_t n, ssrlcv_b200_set** out);
+int  ssrlcv_b200_set_arrays_of(const ssrlcv_b200_set* s, ssrlcv_b200_set_arrays* out);
+int  ssrlcv_b200_set_commit(ssrlcv_b200_ctx* ctx, ssrlcv_b200_set* s);
 uint64_t ssrlcv_b200_set_size(const ssrlcv_b200_set* s);
 void ssrlcv_b200_set_free(ssrlcv_b200_set* s);
 
@@ -235,6 +250,10 @@ int  ssrlcv_b200_match_set_2view(ssrlcv_b200_ctx* ctx, const void* dmatches_dev,
  * computes them (replaces getEpipolarEndpoints, src/MatchFactory.cu:1241-1277). out_dev: float4[n]. */
 int  ssrlcv_b200_epipolar_endpoints(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* params,
                                     const ssrlcv_b200_set* query, float* out_dev);
+/* one array of a packed set copied to the host: which = 0 desc, 1 fold digits, 2 norms, 3 W, 4 window bounds, 5 loc,
+ * 6 sigma/theta, 7 meta; *bytes = its size (host_out == NULL: size query only) */
+int  ssrlcv_b200_set_download(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* s, int which, void* host_out, uint64_t capacity,
+                              uint64_t* bytes);
 /* sinf/cosf of x[n] computed on the device (validates the oracle's libdevice restatement) */
 int  ssrlcv_b200_device_sincos(ssrlcv_b200_ctx* ctx, const float* x_dev, uint64_t n, float* sin_dev, float* cos_dev);
 

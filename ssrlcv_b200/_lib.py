@@ -21,11 +21,11 @@ EXPORTS = [
     "ssrlcv_b200_synchronize", "ssrlcv_b200_launch_count", "ssrlcv_b200_stream", "ssrlcv_b200_tune",
     "ssrlcv_b200_multi_create", "ssrlcv_b200_multi_destroy", "ssrlcv_b200_multi_device_count", "ssrlcv_b200_multi_last_error", "ssrlcv_b200_multi_device_ms",
     "ssrlcv_b200_match_pairs_multi_gpu", "ssrlcv_b200_multi_assignment", "ssrlcv_b200_set_profiling", "ssrlcv_b200_kernel_time",
-    "ssrlcv_b200_pack", "ssrlcv_b200_pack_batch", "ssrlcv_b200_pack_host",
+    "ssrlcv_b200_pack", "ssrlcv_b200_pack_batch", "ssrlcv_b200_pack_host", "ssrlcv_b200_set_alloc", "ssrlcv_b200_set_arrays_of", "ssrlcv_b200_set_commit",
     "ssrlcv_b200_set_size", "ssrlcv_b200_set_free", "ssrlcv_b200_seed_distances", "ssrlcv_b200_match",
     "ssrlcv_b200_match_host", "ssrlcv_b200_match_batch", "ssrlcv_b200_match_candidates", "ssrlcv_b200_match_candidates_seeded", "ssrlcv_b200_finalize_candidates",
     "ssrlcv_b200_set_loc", "ssrlcv_b200_validate", "ssrlcv_b200_refine", "ssrlcv_b200_sort",
-    "ssrlcv_b200_raw_matches", "ssrlcv_b200_match_set_2view", "ssrlcv_b200_epipolar_endpoints", "ssrlcv_b200_device_sincos",
+    "ssrlcv_b200_raw_matches", "ssrlcv_b200_match_set_2view", "ssrlcv_b200_epipolar_endpoints", "ssrlcv_b200_device_sincos", "ssrlcv_b200_set_download",
 ]
 
 
@@ -43,6 +43,10 @@ class MatchParams(C.Structure):
 
 # ssrlcv_b200_tune knobs (include/ssrlcv_b200.h)
 TUNE_FOLD, TUNE_COLUMN_MASKS, TUNE_SORTED_TARGETS, TUNE_HOST_CHUNK_QUERY_ROWS, TUNE_HOST_CHUNK_TARGET_ROWS, TUNE_CROSSCHECK_SIMT, TUNE_TIMING_BUFFER = range(7)
+
+
+class SetArrays(C.Structure):
+    _fields_ = [("desc", C.c_void_p), ("loc", C.c_void_p), ("sigma_theta", C.c_void_p), ("n", C.c_uint64), ("n_pad", C.c_uint64)]
 
 
 class B200Error(RuntimeError):
@@ -95,6 +99,9 @@ def load() -> C.CDLL:
     lib.ssrlcv_b200_pack.argtypes = [vp, vp, u64, C.POINTER(vp)]
     lib.ssrlcv_b200_pack_batch.argtypes = [vp, u32, C.POINTER(vp), pu64, C.POINTER(vp)]
     lib.ssrlcv_b200_pack_host.argtypes = [vp, vp, u64, C.POINTER(vp)]
+    lib.ssrlcv_b200_set_alloc.argtypes = [vp, u64, C.POINTER(vp)]
+    lib.ssrlcv_b200_set_arrays_of.argtypes = [vp, C.POINTER(SetArrays)]
+    lib.ssrlcv_b200_set_commit.argtypes = [vp, vp]
     lib.ssrlcv_b200_set_size.argtypes = [vp]
     lib.ssrlcv_b200_set_size.restype = u64
     lib.ssrlcv_b200_set_free.argtypes = [vp]
@@ -115,6 +122,7 @@ def load() -> C.CDLL:
     lib.ssrlcv_b200_match_set_2view.argtypes = [vp, vp, u64, vp, vp, C.POINTER(C.c_float)]
     lib.ssrlcv_b200_epipolar_endpoints.argtypes = [vp, pp, vp, vp]
     lib.ssrlcv_b200_device_sincos.argtypes = [vp, vp, u64, vp, vp]
+    lib.ssrlcv_b200_set_download.argtypes = [vp, vp, i32, vp, u64, pu64]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("ssrlcv_b200_abi_version",):

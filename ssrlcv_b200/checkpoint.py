@@ -103,13 +103,24 @@ def read_uty(path: str, expect: str | None = None) -> UnityFile:
     return UnityFile(kind, state, data)
 
 
+def checkpoint_path(directory: str, kind: str, id: int) -> str:
+    """getCheckpoint<T>(directory, id) of the stage loaders (ref: src/Pipeline.cu:4-6): directory + "/" + id + "_" + name + ".uty" """
+    return f"{directory}/{id}_{TYPE_NAMES[kind]}.uty"
+
+
+def image_checkpoint_path(directory: str, id: int) -> str:
+    """getImgCheckpoint (ref: src/Pipeline.cu:8-10)"""
+    return f"{directory}/{id}_N6ssrlcv5ImageE.cpimg"
+
+
 def write_uty(path_or_dir: str, kind: str, data: np.ndarray, state: int = STATE_CPU, id: int | None = None) -> str:
-    """Write `data` as a Unity<T> checkpoint. If `id` is given, `path_or_dir` is a directory
-    and the file is named `<id>_<mangled name>.uty` like Unity<T>::checkpoint(id, dir)."""
+    """Write `data` as a Unity<T> checkpoint.  If `id` is given the file name is `path_or_dir + "<id>_<mangled name>.uty"` --
+    plain string concatenation, exactly like Unity<T>::checkpoint(id, dirPath) (ref: include/Unity.cuh:933-935): a dirPath
+    without a trailing slash becomes a file-name prefix there, and does here."""
     name = TYPE_NAMES[kind]
     dt = TYPE_DTYPES[kind]
     data = np.ascontiguousarray(data, dtype=dt)
-    path = os.path.join(path_or_dir, f"{id}_{name}.uty") if id is not None else path_or_dir
+    path = f"{path_or_dir}{id}_{name}.uty" if id is not None else path_or_dir
     with open(path, "wb") as f:
         f.write(name.encode() + b"\n")
         f.write(struct.pack("<Q", libstdcxx_hash_bytes(name.encode())) + b"\n")
@@ -124,6 +135,8 @@ class ImageMeta:
     size: tuple
     colorDepth: int
     camera: np.ndarray  # shape (), dtype types.CAMERA
+    pushbroom: bytes = bytes(72)   # Image::PushbroomCamera @136 (the reference's reader copies it, src/Image.cu:55): carried through
+    isPushbroom: int = 0           # bool @208
 
 
 def read_cpimg(path: str) -> ImageMeta:
@@ -135,7 +148,7 @@ def read_cpimg(path: str) -> ImageMeta:
     size = struct.unpack_from("<II", raw, 40)
     (depth,) = struct.unpack_from("<I", raw, 48)
     cam = np.frombuffer(raw, dtype=T.CAMERA, count=1, offset=56)[0].copy()
-    return ImageMeta(img_id, size, depth, cam)
+    return ImageMeta(img_id, size, depth, cam, bytes(raw[136:208]), raw[208])
 
 
 def write_cpimg(path: str, meta: ImageMeta) -> None:
@@ -144,5 +157,7 @@ def write_cpimg(path: str, meta: ImageMeta) -> None:
     struct.pack_into("<II", buf, 40, *meta.size)
     struct.pack_into("<I", buf, 48, meta.colorDepth)
     buf[56:136] = np.asarray(meta.camera, dtype=T.CAMERA).tobytes()
+    buf[136:208] = bytes(meta.pushbroom)[:72].ljust(72, b"\0")
+    buf[208] = 1 if meta.isPushbroom else 0
     with open(path, "wb") as f:
         f.write(bytes(buf))

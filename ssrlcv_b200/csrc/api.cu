@@ -387,6 +387,29 @@ int ssrlcv_b200_pack_batch(ssrlcv_b200_ctx* ctx, uint32_t n_sets, const void* co
   return 0;
 }
 
+// ---- producer hand-off: the feature factory writes descriptors / locations straight into a packed set -------------
+int ssrlcv_b200_set_alloc(ssrlcv_b200_ctx* ctx, uint64_t n, ssrlcv_b200_set** out) {
+  if (!ctx || !out || n > 0x7fffffffull) return fail(ctx, SSRLCV_B200_EINVAL, "set_alloc: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  return set_alloc(ctx, n, out);
+}
+int ssrlcv_b200_set_arrays_of(const ssrlcv_b200_set* s, ssrlcv_b200_set_arrays* out) {
+  if (!s || !out) return SSRLCV_B200_EINVAL;
+  out->desc = s->desc; out->loc = reinterpret_cast<float*>(s->loc); out->sigma_theta = reinterpret_cast<float*>(s->sigtheta);
+  out->n = s->n; out->n_pad = s->n_pad;
+  return 0;
+}
+// Enqueue-only: one launch derives norms, fold digits, W and the window bounds from the rows the producer wrote and zero-fills
+// the padding; the producer's kernel must be ordered before the context's stream at this point.
+int ssrlcv_b200_set_commit(ssrlcv_b200_ctx* ctx, ssrlcv_b200_set* s) {
+  if (!ctx || !s || s->ctx != ctx || s->is_view) return fail(ctx, SSRLCV_B200_EINVAL, "set_commit: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  const PackJob j = pack_job(s, nullptr, s->n, s->n_pad, 0);
+  launch_pack(ctx->stream, &j, 1, ctx->sm_count, &ctx->launches);
+  s->resolved = false;
+  return set_finish(ctx, s);
+}
+
 int ssrlcv_b200_pack(ssrlcv_b200_ctx* ctx, const void* features_dev, uint64_t n, ssrlcv_b200_set** out) {
   if (!ctx || !out) return fail(ctx, SSRLCV_B200_EINVAL, "pack: bad arguments");
   return ssrlcv_b200_pack_batch(ctx, 1, &features_dev, &n, out);
@@ -1401,6 +1424,31 @@ int ssrlcv_b200_match_set_2view(ssrlcv_b200_ctx* ctx, const void* dmatches_dev, 
 }
 
 // ------------------------------------------------------------------------------------------- diagnostics
+// one array of a packed set to the host (parity tests: the producer hand-off must give byte-identical sets)
+int ssrlcv_b200_set_download(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* s, int which, void* host_out, uint64_t capacity, uint64_t* bytes) {
+  if (!ctx || !s || !bytes) return fail(ctx, SSRLCV_B200_EINVAL, "set_download: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  const void* src = nullptr;
+  uint64_t n = 0;
+  switch (which) {
+    case 0: src = s->desc; n = s->n_pad * kDescBytes; break;
+    case 1: src = s->ext; n = s->n_pad * kExtBytes; break;
+    case 2: src = s->norm; n = s->n_pad * 4; break;
+    case 3: src = s->wcol; n = s->n_pad * 4; break;
+    case 4: src = s->wmax; n = (s->n_pad / kChunk) * 4; break;
+    case 5: src = s->loc; n = s->n_pad * 8; break;
+    case 6: src = s->sigtheta; n = s->n_pad * 8; break;
+    case 7: src = s->meta; n = 4; break;
+    default: return fail(ctx, SSRLCV_B200_EINVAL, "set_download: unknown array");
+  }
+  *bytes = n;
+  if (!host_out) return 0;
+  if (capacity < n) return fail(ctx, SSRLCV_B200_EINVAL, "set_download: buffer too small");
+  CU(cudaMemcpyAsync(host_out, src, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 int ssrlcv_b200_epipolar_endpoints(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const ssrlcv_b200_set* query, float* out_dev) {
   if (!ctx || !p || !query || (query->n && !out_dev)) return fail(ctx, SSRLCV_B200_EINVAL, "epipolar_endpoints: bad arguments");
   CU(cudaSetDevice(ctx->device));

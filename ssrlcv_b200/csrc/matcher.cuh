@@ -157,7 +157,8 @@ struct SmaxBatch {
 
 // pack.cu: one set (or one row range of a set) of a pack launch
 struct PackJob {
-  const RefFeature* in;          // n records
+  const RefFeature* in;          // n records; nullptr = "commit": the producer already wrote desc / loc / sigtheta of rows [0, n) in
+                                 // place (include/ssrlcv_b200_packed.cuh) and only the derived arrays and the padding are written
   uint64_t n, n_rows;            // rows [0, n) are features, [n, n_rows) zero padding; n_rows % 32 == 0
   uint8_t* desc; uint8_t* ext; int32_t* norm; int32_t* wcol; int32_t* wmax; float2* loc; float2* sigtheta;   // at the range's first row
   int32_t* meta;                 // device scalars of the set (zero unless some W does not fit the fold digits)

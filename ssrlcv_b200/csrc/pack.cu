@@ -38,16 +38,19 @@ __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackB
     const uint64_t row0 = static_cast<uint64_t>(win) * kChunk;
     // every load of the window first: 16 descriptor slices per lane (rows row0 + 2k + half) and the scalars of "its own" row
     // row0 + 2 * sub + half, the row whose norm this lane will keep
+    const bool commit = in == nullptr;                                // rows [0, n) of desc / loc / sigtheta are already in place
     uint2 v[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const uint64_t i = row0 + 2 * k + half;
       v[k] = make_uint2(0u, 0u);
-      if (i < n) v[k] = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(in + i) + 24 + sub * 8);
+      if (i < n)
+        v[k] = commit ? *reinterpret_cast<const uint2*>(desc + i * kDescBytes + sub * 8)
+                      : *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(in + i) + 24 + sub * 8);
     }
     const uint64_t own = row0 + 2 * sub + half;
     uint2 own_loc = make_uint2(0u, 0u), own_st = make_uint2(0u, 0u);
-    if (own < n) {
+    if (own < n && !commit) {
       own_loc = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(in + own) + 8);
       own_st = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(in + own) + 16);
     }
@@ -55,7 +58,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackB
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const uint64_t i = row0 + 2 * k + half;                         // < n_rows: windows are whole
-      *reinterpret_cast<uint2*>(desc + i * kDescBytes + sub * 8) = v[k];
+      if (!commit || i >= n) *reinterpret_cast<uint2*>(desc + i * kDescBytes + sub * 8) = v[k];
       uint32_t s = __dp4a(v[k].x, v[k].x, 0u);
       s = __dp4a(v[k].y, v[k].y, s);
 #pragma unroll
@@ -86,8 +89,10 @@ __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackB
     }
     b.jobs[j].norm[own] = own < n ? static_cast<int32_t>(own_s) : 0;
     b.jobs[j].wcol[own] = wn;
-    b.jobs[j].loc[own] = make_float2(__uint_as_float(own_loc.x), __uint_as_float(own_loc.y));
-    b.jobs[j].sigtheta[own] = make_float2(__uint_as_float(own_st.x), __uint_as_float(own_st.y));
+    if (!commit || own >= n) {
+      b.jobs[j].loc[own] = make_float2(__uint_as_float(own_loc.x), __uint_as_float(own_loc.y));
+      b.jobs[j].sigtheta[own] = make_float2(__uint_as_float(own_st.x), __uint_as_float(own_st.y));
+    }
     const int32_t wtop = __reduce_max_sync(0xffffffffu, wn);
     if (lane == 0) b.jobs[j].wmax[win] = wtop;                        // 0 for windows of padding only
     if (__any_sync(0xffffffffu, bad) && lane == 0) {

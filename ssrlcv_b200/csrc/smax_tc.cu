@@ -33,6 +33,8 @@
 //   the pipe works on the next unit (one lane per query: a norm parity load and a 64-bit key each)
 // Masked variants (epipolar constraints) evaluate the reference's float mask per (query, target) in the
 // epilogue on target locations staged through a small shared-memory ring.
+#include <atomic>
+
 #include "geometry.cuh"
 #include "matcher.cuh"
 #include "ptx.cuh"
@@ -752,11 +754,14 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
 template <int kMask, bool kFold, bool kColMask, bool kTiming>
 static cudaError_t launch_one(cudaStream_t st, const SmaxBatch& b) {
   auto kern = smax_kernel<kMask, kFold, kColMask, kTiming>;
-  static bool configured = false;
-  if (!configured) {
+  // the dynamic shared-memory opt-in is a per-device attribute of the function (one context per device in multi-GPU jobs)
+  static std::atomic<uint64_t> configured{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 64 || !((configured.load(std::memory_order_acquire) >> dev) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes));
     if (e != cudaSuccess) return e;
-    configured = true;
+    if (dev < 64) configured.fetch_or(1ull << dev, std::memory_order_release);
   }
   kern<<<b.n_ctas, kThreads, kSmemBytes, st>>>(b);
   return cudaGetLastError();

@@ -60,8 +60,11 @@ def test_record_layouts():
 def test_uty_roundtrip_and_hash(tmp_path, everest):
     # the hash is libstdc++'s typeid(T).hash_code(); checked against the value stored in the reference's own fixtures
     assert ck.libstdcxx_hash_bytes(b"f") != 0
-    p = ck.write_uty(str(tmp_path), "keypoint", everest.g2_keypoints[:100], ck.STATE_CPU, id=7)
+    p = ck.write_uty(str(tmp_path) + "/", "keypoint", everest.g2_keypoints[:100], ck.STATE_CPU, id=7)
     assert os.path.basename(p) == "7_N6ssrlcv8KeyPointE.uty"
+    # Unity<T>::checkpoint concatenates dirPath and the file name (ref: include/Unity.cuh:933): no slash, no directory
+    p2 = ck.write_uty(str(tmp_path) + "/kp", "keypoint", everest.g2_keypoints[:3], ck.STATE_CPU, id=0)
+    assert os.path.basename(p2) == "kp0_N6ssrlcv8KeyPointE.uty"
     back = ck.read_uty(p, "keypoint")
     assert back.state == ck.STATE_CPU and T.fields_equal(back.data, everest.g2_keypoints[:100])
     with pytest.raises(ValueError):
@@ -80,10 +83,56 @@ def test_hash_matches_reference_fixture_header():
 
 
 def test_cpimg_roundtrip(tmp_path, everest):
-    m = ck.ImageMeta(3, (1024, 1024), 1, everest.cameras[1])
+    m = ck.ImageMeta(3, (1024, 1024), 1, everest.cameras[1], bytes(range(72)), 1)
     ck.write_cpimg(str(tmp_path / "3.cpimg"), m)
     b = ck.read_cpimg(str(tmp_path / "3.cpimg"))
     assert b.id == 3 and b.size == (1024, 1024) and b.camera.tobytes() == everest.cameras[1].tobytes()
+    assert b.pushbroom == bytes(range(72)) and b.isPushbroom == 1          # read-then-write is lossless
+
+
+def _write_stage_inputs(d, ev, n_views):
+    """a feature-generation checkpoint directory like the reference's fixtures (test/checkpoints/Pipeline{2,3}View)"""
+    views, seed = (ev.views2, ev.seed2) if n_views == 2 else (ev.views3, ev.seed3)
+    ck.write_uty(d + "/", "feature", seed, ck.STATE_CPU, id=-1)
+    for i in range(n_views):
+        ck.write_uty(d + "/", "feature", views[i], ck.STATE_CPU, id=i)
+        ck.write_cpimg(ck.image_checkpoint_path(d, i), ck.ImageMeta(ev.img_ids[i], (1024, 1024), 1, ev.cameras[i]))
+
+
+def test_stage_inputs_from_checkpoint(tmp_path, everest):
+    """FeatureMatchingInput::fromCheckpoint (ref: src/Pipeline.cu:144-163): seed image optional, one .cpimg + feature file per
+    image, the pose stage's seed distances only for 2 views and only if present."""
+    from ssrlcv_b200.pipeline import FeatureMatchingInput
+    d = str(tmp_path / "fg"); os.makedirs(d)
+    _write_stage_inputs(d, everest, 2)
+    inp = FeatureMatchingInput.fromCheckpoint(d, None, 2, 25.0, 5.0)
+    assert inp.seedDistances is None and len(inp.images) == 2 and [im.id for im in inp.images] == everest.img_ids[:2]
+    assert T.fields_equal(inp.seedFeatures.to_numpy(), everest.seed2)
+    for i in range(2):
+        assert T.fields_equal(inp.allFeatures[i].to_numpy(), everest.views2[i])
+        assert T.fields_equal(np.asarray(inp.images[i].camera).reshape(1), np.asarray(everest.cameras[i]).reshape(1))
+    pose = str(tmp_path / "pose"); os.makedirs(pose)
+    sd = np.arange(len(everest.views2[0]), dtype=np.float32)
+    ck.write_uty(pose + "/", "float", sd, ck.STATE_CPU, id=0)
+    inp = FeatureMatchingInput.fromCheckpoint(d, pose, 2, 25.0, 5.0)
+    assert np.array_equal(inp.seedDistances.to_numpy(), sd)
+    os.remove(ck.checkpoint_path(d, "feature", -1))
+    assert FeatureMatchingInput.fromCheckpoint(d, None, 2, 25.0, 5.0).seedFeatures is None
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/test/checkpoints"), reason="reference checkout not present")
+def test_checkpoint_writer_reproduces_reference_files(tmp_path, everest):
+    """the stage's output files as the reference wrote them (test/checkpoints/Pipeline2View/0_...KeyPointE.uty, ...MultiMatchE.uty):
+    same header bytes, same records (KeyPoint has 4 padding bytes the reference leaves uninitialised: compared field-wise)."""
+    d = "/root/reference/test/checkpoints/Pipeline2View/"
+    for kind, data in (("keypoint", everest.g2_keypoints), ("multimatch", everest.g2_multimatch)):
+        ours = ck.write_uty(str(tmp_path) + "/", kind, data, ck.STATE_CPU, id=0)
+        ref_raw, our_raw = open(d + os.path.basename(ours), "rb").read(), open(ours, "rb").read()
+        hdr = len(ck.TYPE_NAMES[kind]) + 1 + 9 + 13
+        assert len(ref_raw) == len(our_raw) and ref_raw[:hdr] == our_raw[:hdr]
+        assert T.fields_equal(ck.read_uty(d + os.path.basename(ours), kind).data, ck.read_uty(ours, kind).data)
+        if kind == "multimatch":
+            assert ref_raw == our_raw                       # no padding in MultiMatch: byte for byte
 
 
 def test_pair_order_and_assignment():

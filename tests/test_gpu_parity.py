@@ -982,6 +982,99 @@ def test_exact_baseline_shapes_c2_and_c4_pair(api, everest):
     assert len(want) > 5000 and T.fields_equal(got, want)
 
 
+# ------------------------------------------------------------------------------------ the stage, stand-alone, from checkpoints
+@pytest.mark.parametrize("n_views", [2, 3])
+def test_stage_runner_from_checkpoint_tree(api, everest, tmp_path, n_views):
+    """ref: src/Pipeline.cu:144-163 + src/SFM.cu:247-259 -- the matching stage from a feature-generation checkpoint directory (the
+    layout of the reference's own fixtures, test/checkpoints/Pipeline{2,3}View) to the stage's output checkpoints:
+    0_...KeyPointE.uty / 0_...MultiMatchE.uty hold the reference's golden MatchSet."""
+    from ssrlcv_b200 import checkpoint as ck
+    from ssrlcv_b200.pipeline import main as stage_main
+    from tests.test_abi import _write_stage_inputs
+    fg, out = str(tmp_path / "fg"), str(tmp_path / "fm")
+    os.makedirs(fg)
+    _write_stage_inputs(fg, everest, n_views)
+    assert stage_main(["--fg", fg, "--out", out, "-n", str(n_views), "--epsilon", "25", "--delta", "5"]) == 0
+    kp = ck.read_uty(ck.checkpoint_path(out, "keypoint", 0), "keypoint")
+    mm = ck.read_uty(ck.checkpoint_path(out, "multimatch", 0), "multimatch")
+    want_kp, want_mm = (everest.g2_keypoints, everest.g2_multimatch) if n_views == 2 else (everest.g3_keypoints, everest.g3_multimatch)
+    assert T.fields_equal(kp.data, want_kp) and T.fields_equal(mm.data, want_mm)
+    assert kp.state == ck.STATE_CPU and os.path.exists(os.path.join(out, "done"))
+
+
+def test_match_set_stays_on_the_device_for_the_consumer(api, everest):
+    """SURVEY 8f-4, consumer side: generateBundles moves matches and keyPoints to the GPU first thing (ref:
+    src/PointCloudFactory.cu:837-838); doFeatureMatching(device_resident=True) hands them over in state gpu (no D2H + H2D pair)."""
+    from ssrlcv_b200.pipeline import FeatureMatchingInput, doFeatureMatching
+    ev = everest
+    inp = FeatureMatchingInput(images=[api.Image(ev.img_ids[0], ev.cameras[0]), api.Image(ev.img_ids[1], ev.cameras[1])],
+                               allFeatures=[_unity(api, ev.views2[0]), _unity(api, ev.views2[1])], seedFeatures=_unity(api, ev.seed2),
+                               epsilon=ev.epsilon, delta=ev.delta)
+    out = doFeatureMatching(inp, device_resident=True)
+    assert out.matchSet.keyPoints.getMemoryState() == api.gpu and out.matchSet.matches.getMemoryState() == api.gpu
+    assert out.matchSet.keyPoints.host is None
+    assert T.fields_equal(out.matchSet.keyPoints.to_numpy(), ev.g2_keypoints) and T.fields_equal(out.matchSet.matches.to_numpy(), ev.g2_multimatch)
+
+
+# ------------------------------------------------------------------------------------ producer hand-off (SURVEY 8f-4)
+def test_producer_handoff_packed_writer(api):
+    """A feature factory that writes the packed layout itself (include/ssrlcv_b200_packed.cuh: the patched tail of fillDescriptors,
+    src/SIFT_FeatureFactory.cu:533-548) + ssrlcv_b200_set_commit gives sets that are byte-identical to what the pack kernel makes of
+    the 152-byte AoS records -- descriptors, fold digits, norms, W, window bounds, locations, sigma/theta, padding included -- and
+    the matcher returns the oracle's records on them.  No pack launch on that route."""
+    import torch
+    from ssrlcv_b200 import _lib
+    from ssrlcv_b200.match_factory import Context
+    path = os.path.join(ROOT, "tests", "native", "libpacked_writer_test.so")
+    if not os.path.exists(path):
+        pytest.skip("tests/native/libpacked_writer_test.so not built (__graft_entry__.build)")
+    helper = C.CDLL(path)
+    ctx = Context.get(0)
+    lib, h = ctx.lib, ctx.handle
+    stream = lib.ssrlcv_b200_stream(h)
+    q, t = synth.make_pair(3000 + 77, 5000 + 13, seed=1234)
+    rng = np.random.default_rng(3)
+    q["sigma"], q["theta"] = rng.uniform(1, 4, len(q)), rng.uniform(0, 6.28, len(q))
+    t["sigma"], t["theta"] = rng.uniform(1, 4, len(t)), rng.uniform(0, 6.28, len(t))
+    t["values"][17] = 255                      # one row whose norm does not fit the fold digits: the verdict must travel as well
+    handles = []
+
+    def download(hs, which):
+        nbytes = C.c_uint64(0)
+        ctx.check(lib.ssrlcv_b200_set_download(h, hs, which, None, 0, C.byref(nbytes)))
+        buf = np.zeros(nbytes.value, np.uint8)
+        ctx.check(lib.ssrlcv_b200_set_download(h, hs, which, C.c_void_p(buf.ctypes.data), nbytes.value, C.byref(nbytes)))
+        return buf
+
+    for feats in (q, t):
+        dev = torch.from_numpy(feats.view(np.uint8).reshape(-1)).cuda()
+        packed = C.c_void_p()
+        ctx.check(lib.ssrlcv_b200_pack(h, C.c_void_p(dev.data_ptr()), len(feats), C.byref(packed)))
+        direct = C.c_void_p()
+        launches0 = ctx.launch_count()
+        ctx.check(lib.ssrlcv_b200_set_alloc(h, len(feats), C.byref(direct)))
+        arrays = _lib.SetArrays()
+        ctx.check(lib.ssrlcv_b200_set_arrays_of(direct, C.byref(arrays)))
+        assert arrays.n == len(feats) and arrays.n_pad % 256 == 0
+        assert helper.packed_writer_fill(C.byref(arrays), C.c_void_p(dev.data_ptr()), C.c_ulong(len(feats)), C.c_void_p(stream)) == 0
+        ctx.check(lib.ssrlcv_b200_set_commit(h, direct))
+        assert ctx.launch_count() - launches0 == 1          # the commit launch only
+        for which in range(8):
+            assert np.array_equal(download(packed, which), download(direct, which)), which
+        lib.ssrlcv_b200_set_free(packed)
+        handles.append(direct)
+    mf = api.MatchFactory(1.0, 1.2e5)
+    p = mf._params(T.OUT_DMATCH, T.MASK_NONE, api.Image(0), api.Image(1))
+    out = torch.empty(len(q) * 48, dtype=torch.uint8, device="cuda")
+    n_out = C.c_uint64(0)
+    ctx.check(lib.ssrlcv_b200_match(h, C.byref(p), handles[0], handles[1], None, 0, C.c_void_p(out.data_ptr()), C.byref(n_out)))
+    got = out[: n_out.value * 48].cpu().numpy().view(T.DMATCH)
+    want = api.O.generate_matches(api.O.make_params(out_kind=T.OUT_DMATCH, abs_threshold=1.2e5), q, t)
+    assert len(want) > 500 and T.fields_equal(got, want)
+    for hs in handles:
+        lib.ssrlcv_b200_set_free(hs)
+
+
 # ------------------------------------------------------------------------------------ the pair scheduler across devices (C ABI)
 def _multi_gpu_case(api, everest, n_devices):
     """ssrlcv_b200_match_pairs_multi_gpu: 5 views of different sizes, all 10 pairs, seed-ratio test + DoubleConstrained (what
