@@ -813,6 +813,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       b.n_jobs = static_cast<uint32_t>(g.idx.size());
       b.n_ctas = w[g.idx[0]].a.n_ctas;
       b.total_tiles = g.total;
+      b.flags = d_nflag + at;
       b.clear = d_nflag_other; b.clear_n = bank_len;
       b.timing = ctx->knob[SSRLCV_B200_TUNE_TIMING_BUFFER] > 0 ? reinterpret_cast<unsigned long long*>(ctx->knob[SSRLCV_B200_TUNE_TIMING_BUFFER]) : nullptr;
       if (ctx->profiling) {

@@ -96,9 +96,16 @@ __global__ void __launch_bounds__(256) exact_kernel(SmaxArgs a) {
 template <int kMask>
 __global__ void __launch_bounds__(256) exact_list_kernel(const __grid_constant__ SmaxBatch b) {
   __shared__ uint64_t s_min[8];
+  __shared__ int s_any;
+  if (threadIdx.x == 0) s_any = 0;
+  __syncthreads();
+  for (uint32_t j = threadIdx.x; j < b.n_jobs; j += blockDim.x)
+    if (b.flags[j] != 0) s_any = 1;                   // the counters of the launch's jobs are contiguous: one parallel look
+  __syncthreads();
+  if (!s_any) return;                                 // the common case: no tie anywhere in the launch
   const SmaxJob* jobs = b.jobs ? b.jobs : &b.inline_job;
   for (uint32_t j = 0; j < b.n_jobs; ++j) {
-    if (*jobs[j].a.n_flagged == 0) continue;          // the common case: nothing to do for this job
+    if (b.flags[j] == 0) continue;
     const SmaxArgs a = jobs[j].a;
     exact_items<kMask>(a, 1, s_min);
   }

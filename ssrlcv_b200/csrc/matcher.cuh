@@ -150,6 +150,7 @@ struct SmaxBatch {
   uint32_t n_ctas;
   uint64_t total_tiles;
   unsigned long long* timing;    // optional [gridDim.x][16] cycle counters (diagnostics build), or nullptr
+  const uint32_t* flags;         // this launch's tie counters, one per job (job i counts into flags[i])
   uint32_t* clear;               // the tie counters of the OTHER bank: zeroed by CTA 0 for the call after this one
   uint32_t clear_n;
   SmaxJob inline_job;

@@ -51,6 +51,9 @@ class PairListExchange:
         for r, a in enumerate(assign):
             for s_i, k in enumerate(a):
                 self.where[k] = (r, s_i)
+        assert all(r >= 0 for r, _ in self.where), "every pair must be assigned to a rank"
+        self._rank_of = np.array([r for r, _ in self.where], np.int64)
+        self._slot_of = np.array([s_i for _, s_i in self.where], np.int64)
         pinned = str(device).startswith("cuda")
         self.counts_h = torch.zeros(self.slots, dtype=torch.int64, pin_memory=pinned)
         self.counts_d = torch.zeros(self.slots, dtype=torch.int64, device=device)
@@ -61,8 +64,7 @@ class PairListExchange:
 
     def run(self, out, counts):
         """out: int32[slots, capacity, 4] records of this rank's pairs (slot order = its assignment order);
-        counts: record count per owned pair (host).  Returns (counts per pair [n_pairs] on the host, lists) where lists[k]
-        is a device tensor int32[count_k.., 4] view of pair k's records."""
+        counts: record count per owned pair (host).  Returns (counts per pair [n_pairs] on the host, PairLists)."""
         torch = self.torch
         m = len(counts)
         self.counts_h.zero_()
@@ -86,15 +88,23 @@ class PairListExchange:
             self.dist.all_gather_into_tensor(recv, send.reshape(-1))
             view = recv.view(self.world, self.slots, cap, 4)
             self.last_bytes = recv.numel() * 4 + self.all_counts_d.numel() * 8
-        per_pair = np.zeros(self.n_pairs, np.int64)
-        lists = [None] * self.n_pairs
         ac = allc.numpy()
-        for k, (r, s_i) in enumerate(self.where):
-            if r < 0:
-                continue
-            per_pair[k] = ac[r, s_i]
-            lists[k] = view[r, s_i, : per_pair[k]]
-        return per_pair, lists
+        per_pair = ac[self._rank_of, self._slot_of]               # counts in pair order (one gather, no per-pair Python work)
+        return per_pair, PairLists(view, per_pair, self.where)
+
+
+class PairLists:
+    """every pair's records after the exchange, addressable in pair order: lists[k] is a device tensor int32[count_k, 4]"""
+
+    def __init__(self, view, counts, where):
+        self.view, self.counts, self.where = view, counts, where
+
+    def __len__(self):
+        return len(self.where)
+
+    def __getitem__(self, k):
+        r, s_i = self.where[k]
+        return self.view[r, s_i, : int(self.counts[k])]
 
 
 def exchange_pair_lists(n_pairs, assign, capacity, rank, world_size, dist, device="cpu") -> PairListExchange:
@@ -132,7 +142,7 @@ def gather_pair_lists(local: dict, n_pairs: int, rank: int, world_size: int, dis
     per_pair, lists = xch.run(out, [len(local[k]) for k in mine])
     res: List[np.ndarray] = []
     for k in range(n_pairs):
-        if lists[k] is None or per_pair[k] == 0:
+        if per_pair[k] == 0:
             res.append(np.zeros(0, T.UINT2_PAIR))
         else:
             res.append(np.ascontiguousarray(lists[k].cpu().numpy()).view(np.uint32).reshape(-1).view(T.UINT2_PAIR).copy())
