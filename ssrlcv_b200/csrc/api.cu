@@ -1118,26 +1118,25 @@ static int make_view(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* parent, uint64
   return 0;
 }
 
-// How match_host cuts a set of n rows for the streamed upload: equal chunks (a multiple of kRowPad rows) of at least
-// kMinChunkRows, at most kMaxChunks.  Every chunk costs a pack + matcher + tie-list + key-reduction launch (~25 us of
-// device time, ~30 us of host time), so few, large chunks win: measured at 65 536 x 65 536 (tools/e2e_chunks.sh,
-// profiles/r1f_e2e_chunks.txt): one piece 0.94 ms, 2 + 2 chunks 0.80 ms, 4 + 4 chunks 0.94 ms, 8 + 8 chunks 1.10 ms.
-// ssrlcv_b200_tune(SSRLCV_B200_TUNE_HOST_CHUNK_{QUERY,TARGET}_ROWS) overrides (0 = never cut; tests use tiny chunks).
-static uint64_t host_chunk_rows(const ssrlcv_b200_ctx* ctx, uint64_t n, int which) {
-  constexpr uint64_t kMinChunkRows = 16384, kMaxChunks = 2;
-  uint64_t rows;
+// How match_host cuts a set of n rows for the streamed upload: the first row of every chunk (multiples of kRowPad) + n.
+// Two equal chunks per set of at least 32 768 rows.  The available work grows with the SQUARE of the arrived fraction while
+// the transfer is linear, so the pipeline is transfer-bound early and compute-bound late whatever the cut: at 65 536 x 65 536
+// (0.40 ms of PCIe, 0.37 ms of matching) uneven schedules (small first / last chunks) and 4 + 4 chunks measure the same
+// 0.72 ms as 2 + 2 (profiles/r2_e2e_chunks.txt), every extra chunk costing a pack + matcher + tie-list + key-reduction launch.
+// ssrlcv_b200_tune(SSRLCV_B200_TUNE_HOST_CHUNK_{QUERY,TARGET}_ROWS) forces a chunk length (0 = never cut; tests use tiny ones).
+static std::vector<uint64_t> chunk_bounds(const ssrlcv_b200_ctx* ctx, uint64_t n, int which) {
+  std::vector<uint64_t> b{0};
   const int64_t knob = ctx->knob[which == 1 ? SSRLCV_B200_TUNE_HOST_CHUNK_TARGET_ROWS : SSRLCV_B200_TUNE_HOST_CHUNK_QUERY_ROWS];
-  if (knob >= 0) {
-    rows = static_cast<uint64_t>(knob);
-    if (rows == 0) return n ? ((n + kRowPad - 1) / kRowPad) * kRowPad : kRowPad;   // 0: never cut
-  } else {
-    uint64_t c = n / kMinChunkRows;
-    if (c < 1) c = 1;
-    if (c > kMaxChunks) c = kMaxChunks;
-    rows = (n + c - 1) / c;
+  auto round_rows = [](uint64_t r) { return ((r + kRowPad - 1) / kRowPad) * kRowPad; };
+  if (knob > 0) {
+    const uint64_t rows = round_rows(static_cast<uint64_t>(knob));
+    for (uint64_t r = rows; r < n; r += rows) b.push_back(r);
+  } else if (knob < 0 && n >= 32768) {
+    const uint64_t r = round_rows((n + 1) / 2);
+    if (r < n) b.push_back(r);
   }
-  rows = ((rows + kRowPad - 1) / kRowPad) * kRowPad;
-  return rows ? rows : kRowPad;
+  b.push_back(n);
+  return b;
 }
 
 // match_host for sets large enough that the PCIe transfer matters: both sets are uploaded chunk by chunk on a copy
@@ -1149,7 +1148,7 @@ static uint64_t host_chunk_rows(const ssrlcv_b200_ctx* ctx, uint64_t n, int whic
 // (keys carry the global target index, chunk boundaries are multiples of 32 so f mod 32 is unchanged), then one finalize.
 static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const void* query_host, uint64_t nq,
                                const void* target_host, uint64_t nt, const void* seed_host, uint64_t ns, void* out_host,
-                               uint64_t* n_out, uint64_t q_rows, uint64_t t_rows) {
+                               uint64_t* n_out, const std::vector<uint64_t>& qb, const std::vector<uint64_t>& tb) {
   CU(cudaSetDevice(ctx->device));
   if (!ctx->copy_stream) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   // Every exit after this point goes through cleanup(): on failure both streams are drained first, because copies from the
@@ -1165,7 +1164,7 @@ static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_par
     cudaError_t e_ = (call);                                                                                        \
     if (e_ != cudaSuccess) return cleanup(fail(ctx, static_cast<int>(e_), "%s: %s", #call, cudaGetErrorString(e_))); \
   } while (0)
-  const uint64_t n_qc = (nq + q_rows - 1) / q_rows, n_tc = (nt + t_rows - 1) / t_rows;
+  const uint64_t n_qc = qb.size() - 1, n_tc = tb.size() - 1;      // chunk i of a set = rows [b[i], b[i + 1])
   while (ctx->copy_events.size() < n_qc + n_tc + 2) {
     cudaEvent_t e;
     CUS(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1198,7 +1197,8 @@ static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_par
     // q_seed) exist once the last query has arrived, before the first (queries x target chunk) job is enqueued.
     uint64_t qi = 0, ti = 0;
     while (qi < n_qc || ti < n_tc) {
-      const bool take_q = ti >= n_tc || (qi < n_qc && (seed_host != nullptr || qi * n_tc <= ti * n_qc));
+      // the set whose arrived FRACTION is smaller goes next (query first on a tie): qb[qi] / nq <= tb[ti] / nt
+      const bool take_q = ti >= n_tc || (qi < n_qc && (seed_host != nullptr || qb[qi] * nt <= tb[ti] * nq));
       if (take_q) order.push_back(Up{true, qi++}); else order.push_back(Up{false, ti++});
     }
   }
@@ -1206,8 +1206,8 @@ static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_par
   if (seed_host) CUS(cudaEventRecord(ev_seed, ctx->copy_stream));
   for (size_t k = 0; k < order.size(); ++k) {
     const Up& u = order[k];
-    const uint64_t rows = u.is_q ? q_rows : t_rows, n = u.is_q ? nq : nt, r0 = u.idx * rows;
-    const uint64_t cnt = n - r0 < rows ? n - r0 : rows;
+    const std::vector<uint64_t>& bb = u.is_q ? qb : tb;
+    const uint64_t r0 = bb[u.idx], cnt = bb[u.idx + 1] - r0;
     const uint8_t* src = static_cast<const uint8_t*>(u.is_q ? query_host : target_host) + r0 * rec;
     CUS(cudaMemcpyAsync((u.is_q ? up_q : up_t) + r0 * rec, src, cnt * rec, cudaMemcpyHostToDevice, ctx->copy_stream));
     CUS(cudaEventRecord(ctx->copy_events[k], ctx->copy_stream));
@@ -1232,9 +1232,10 @@ static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_par
   for (size_t k = 0; k < order.size(); ++k) {
     const Up& u = order[k];
     ssrlcv_b200_set* set = u.is_q ? q : t;
-    const uint64_t rows = u.is_q ? q_rows : t_rows, r0 = u.idx * rows;
-    const bool last = r0 + rows >= set->n;
-    const uint64_t cnt = last ? set->n - r0 : rows, pad = last ? set->n_pad - r0 : rows;
+    const std::vector<uint64_t>& bb = u.is_q ? qb : tb;
+    const uint64_t r0 = bb[u.idx];
+    const bool last = u.idx + 2 == bb.size();
+    const uint64_t cnt = bb[u.idx + 1] - r0, pad = last ? set->n_pad - r0 : cnt;
     CUS(cudaStreamWaitEvent(ctx->stream, ctx->copy_events[k], 0));
     const PackJob pj = pack_job(set, (u.is_q ? up_q : up_t) + r0 * rec, cnt, pad, r0);
     launch_pack(ctx->stream, &pj, 1, ctx->sm_count, &ctx->launches);
@@ -1263,7 +1264,7 @@ static int match_host_streamed(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_par
         w.seed = (s && p->compact && q_arrived == q->n) ? seed_dev : nullptr;
         w.seed_ratio = ratio_threshold(p->out_kind, p->mask_kind, p->relative_threshold);
       }
-      t_arrived = r0 + cnt;                                    // a multiple of t_rows until the last chunk
+      t_arrived = r0 + cnt;                                    // a multiple of kRowPad until the last chunk
     }
     if (run) {
       w.q = &qv; w.t = &tv;
@@ -1316,12 +1317,12 @@ int ssrlcv_b200_match_host(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params*
   if ((n_query && !query_host) || (n_target && !target_host) || (seed_host == nullptr && n_seed)) return fail(ctx, SSRLCV_B200_EINVAL, "match_host: bad arguments");
   if (n_query > 0x7fffffffull || n_target > 0x7fffffffull || n_seed > 0x7fffffffull) return fail(ctx, SSRLCV_B200_EINVAL, "match_host: too many features");
   {
-    const uint64_t q_rows = host_chunk_rows(ctx, n_query, 0), t_rows = host_chunk_rows(ctx, n_target, 1);
+    const std::vector<uint64_t> qb = chunk_bounds(ctx, n_query, 0), tb = chunk_bounds(ctx, n_target, 1);
     // also for smaller seeded calls: the target set travels on the copy stream while the seed pass (queries x seed set) runs
     const bool overlap_seed_pass = seed_host != nullptr && n_seed != 0 && n_target >= 8192 &&
                                    ctx->knob[SSRLCV_B200_TUNE_HOST_CHUNK_QUERY_ROWS] < 0 && ctx->knob[SSRLCV_B200_TUNE_HOST_CHUNK_TARGET_ROWS] < 0;
-    if (n_query && n_target && engine_of(ctx) != SSRLCV_B200_ENGINE_SIMT && (q_rows < n_query || t_rows < n_target || overlap_seed_pass))
-      return match_host_streamed(ctx, p, query_host, n_query, target_host, n_target, seed_host, n_seed, out_host, n_out, q_rows, t_rows);
+    if (n_query && n_target && engine_of(ctx) != SSRLCV_B200_ENGINE_SIMT && (qb.size() > 2 || tb.size() > 2 || overlap_seed_pass))
+      return match_host_streamed(ctx, p, query_host, n_query, target_host, n_target, seed_host, n_seed, out_host, n_out, qb, tb);
   }
   rc = pack_host_async(ctx, query_host, n_query, &q);
   if (!rc) rc = pack_host_async(ctx, target_host, n_target, &t);
