@@ -348,21 +348,13 @@ def run_ours(args, w, env):
     p.target_camera = (C.c_uint8 * 80).from_buffer_copy(np.asarray(cam1).tobytes())
     p.compact, p.reserved = 1, 0
     n_out = C.c_uint64(0)
-    n_sets = 3 if s is not None else 2
-    ptrs = (C.c_void_p * n_sets)(qd.data_ptr(), td.data_ptr(), *([sd_feat.data_ptr()] if s is not None else []))
-    sizes = (C.c_uint64 * n_sets)(len(q), len(t), *([len(s)] if s is not None else []))
-    sets = (C.c_void_p * n_sets)()
+    seed_ptr = C.c_void_p(sd_feat.data_ptr()) if s is not None else None
+    seed_out = C.c_void_p(seed_dist.data_ptr()) if s is not None else None
 
     def step():
-        """pack every set (one launch), seed distances, match; inputs are device-resident AoS arrays."""
-        ctx.check(lib.ssrlcv_b200_pack_batch(h, n_sets, ptrs, sizes, sets))
-        seed_ptr, n_seed = None, 0
-        if s is not None:
-            ctx.check(lib.ssrlcv_b200_seed_distances(h, sets[0], sets[2], C.c_void_p(seed_dist.data_ptr())))
-            seed_ptr, n_seed = C.c_void_p(seed_dist.data_ptr()), len(q)
-        ctx.check(lib.ssrlcv_b200_match(h, C.byref(p), sets[0], sets[1], seed_ptr, n_seed, C.c_void_p(out.data_ptr()), C.byref(n_out)))
-        for x in sets:
-            lib.ssrlcv_b200_set_free(x)
+        """pack every set (one launch), seed distances, match, release; inputs are device-resident AoS arrays."""
+        ctx.check(lib.ssrlcv_b200_match_features(h, C.byref(p), C.c_void_p(qd.data_ptr()), len(q), C.c_void_p(td.data_ptr()), len(t),
+                                                 seed_ptr, len(s) if s is not None else 0, seed_out, C.c_void_p(out.data_ptr()), C.byref(n_out)))
         return int(n_out.value)
 
     # ---------------- device-resident timing ----------------
@@ -417,7 +409,7 @@ def run_ours(args, w, env):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": config_of(args.workload, w),
         "parallelism": f"pair-sharded x{world}: every rank matches its own image pair of this shape, no data-path collective",
-        "step": "pack(AoS->SoA, one launch) + [seed distances] + match + compaction, device-resident inputs",
+        "step": "ssrlcv_b200_match_features: pack(AoS->SoA, one launch) + [seed distances] + match + compaction, device-resident inputs",
         "matches_per_s": world * n_matches * args.steps / (total_ms * 1e-3), "queries_per_s": world * w["nq"] * args.steps / (total_ms * 1e-3),
         "matches_per_step": n_matches, "wall_ms_per_step": wall_ms / args.steps,
         "int8_tops": 256.0 * value / 1e12, "frac_of_int8_peak_step": 256.0 * value / 1e12 / (world * peak_tops),

@@ -163,6 +163,13 @@ int  ssrlcv_b200_match(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* par
                        const ssrlcv_b200_set* query, const ssrlcv_b200_set* target,
                        const float* seed_dist_dev, uint64_t n_seed_dist, void* out_dev, uint64_t* n_out);
 
+/* The same on DEVICE-resident Feature arrays in one call (pack of every set in one launch + [seed distances] + match +
+ * release): what getSeedDistances + generate* do on Unity arrays in state gpu (src/Pipeline.cu:176-197).  seed_dev == NULL:
+ * no seed-ratio test.  seed_dist_out_dev: float[n_query] that receives the seed distances, or NULL. */
+int  ssrlcv_b200_match_features(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* params, const void* query_dev,
+                                uint64_t n_query, const void* target_dev, uint64_t n_target, const void* seed_dev,
+                                uint64_t n_seed, float* seed_dist_out_dev, void* out_dev, uint64_t* n_out);
+
 /* replaces: the pair loop of generateMatchesExhaustive (src/MatchFactory.cu:907-936) -- the pair scheduler's device side.
  * n_pairs independent ssrlcv_b200_match calls (params[i], queries[i], targets[i], seed_dist_dev[i] or NULL, out_dev[i]) are
  * enqueued back to back and synchronised once; n_out[i] receives the record count of pair i.  seed_dist_dev may be NULL

@@ -64,7 +64,7 @@ struct ssrlcv_b200_ctx {
   EncodeTiledFn encode = nullptr;
   std::string err;
   uint64_t launches = 0;
-  Workspace keys, flagged, counts, scratch, hostpin, qmask, sortws;
+  Workspace keys, flagged, counts, scratch, hostpin, qmask, sortws, seedws;
   // zero-initialised once, left zero by the kernels that use them: tie counters (two banks: a matcher launch counts into
   // one and clears the other for the next call), finalize tickets, finalize block states (stamped with `epoch`, so stale
   // entries read as "not yet")
@@ -213,7 +213,7 @@ void ssrlcv_b200_destroy(ssrlcv_b200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (Workspace* w : {&ctx->keys, &ctx->flagged, &ctx->counts, &ctx->scratch, &ctx->qmask, &ctx->nflag, &ctx->tickets, &ctx->fstate, &ctx->sortws}) if (w->p) cudaFree(w->p);
+  for (Workspace* w : {&ctx->keys, &ctx->flagged, &ctx->counts, &ctx->scratch, &ctx->qmask, &ctx->nflag, &ctx->tickets, &ctx->fstate, &ctx->sortws, &ctx->seedws}) if (w->p) cudaFree(w->p);
   for (auto& st : ctx->staged) {
     if (st.h) cudaFreeHost(st.h);
     if (st.d) cudaFree(st.d);
@@ -1052,6 +1052,35 @@ int ssrlcv_b200_match(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, c
   const float* seeds[1] = {seed_dist_dev};
   void* outs[1] = {out_dev};
   return ssrlcv_b200_match_batch(ctx, 1, p, &query, &target, seed_dist_dev ? seeds : nullptr, outs, n_out);
+}
+
+// The whole 2-view call sequence on device-resident AoS arrays in ONE entry: pack (one launch for all sets), seed distances
+// (if a seed set is given), match, release of the packed sets.  What a caller of the reference does with
+// getSeedDistances + generate* on Unity arrays in state gpu (ref: src/Pipeline.cu:176-197).
+int ssrlcv_b200_match_features(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const void* query_dev, uint64_t n_query,
+                               const void* target_dev, uint64_t n_target, const void* seed_dev, uint64_t n_seed, float* seed_dist_out_dev,
+                               void* out_dev, uint64_t* n_out) {
+  if (!ctx || !n_out) return fail(ctx, SSRLCV_B200_EINVAL, "match_features: bad arguments");
+  int rc = check_params(ctx, p);
+  if (rc) return rc;
+  const bool seeded = seed_dev != nullptr;
+  const void* ptrs[3] = {query_dev, target_dev, seed_dev};
+  const uint64_t sizes[3] = {n_query, n_target, n_seed};
+  ssrlcv_b200_set* sets[3] = {nullptr, nullptr, nullptr};
+  rc = ssrlcv_b200_pack_batch(ctx, seeded ? 3 : 2, ptrs, sizes, sets);
+  if (rc) return rc;
+  float* sd = nullptr;
+  if (seeded) {
+    sd = seed_dist_out_dev;
+    if (!sd) {                                            // the caller does not want them back: context scratch
+      rc = ws_reserve(ctx, ctx->seedws, (n_query ? n_query : 1) * sizeof(float));
+      sd = static_cast<float*>(ctx->seedws.p);
+    }
+    if (!rc) rc = ssrlcv_b200_seed_distances(ctx, sets[0], sets[2], sd);
+  }
+  if (!rc) rc = ssrlcv_b200_match(ctx, p, sets[0], sets[1], sd, sd ? n_query : 0, out_dev, n_out);
+  for (ssrlcv_b200_set* s : sets) ssrlcv_b200_set_free(s);
+  return rc;
 }
 
 int ssrlcv_b200_match_candidates(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const ssrlcv_b200_set* query,

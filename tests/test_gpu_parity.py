@@ -982,6 +982,47 @@ def test_exact_baseline_shapes_c2_and_c4_pair(api, everest):
     assert len(want) > 5000 and T.fields_equal(got, want)
 
 
+def test_match_features_one_call(api, everest):
+    """ssrlcv_b200_match_features: pack + seed distances + match + release on device-resident AoS arrays in one entry (the bench's
+    step): seeded DoubleConstrained DMatch and unseeded Match, records and seed distances equal the oracle's; a target set whose
+    norms do not fit the fold digits (the seed pass and the match are first launched on the optimistic guess, then redone)."""
+    import torch
+    from ssrlcv_b200.match_factory import Context
+    ctx = Context.get(0)
+    lib, h = ctx.lib, ctx.handle
+    q, t = synth.make_pair(3000, 4100, seed=4242)
+    s = synth.make_seed(640)
+    dev = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1)).cuda()
+    mf = api.MatchFactory(0.8, 1.0e5)
+    qi, ti = api.Image(0, everest.cameras[0]), api.Image(1, everest.cameras[1])
+    for bright_seed in (False, True):
+        s2 = s.copy()
+        if bright_seed:
+            s2["values"][5] = 255
+        qd, td, sd_ = dev(q), dev(t), dev(s2)
+        sd_want = api.O.seed_distances(q, s2)
+        for out_kind, mask_kind, dt in ((T.OUT_DMATCH, T.MASK_DOUBLE, T.DMATCH), (T.OUT_MATCH, T.MASK_NONE, T.MATCH)):
+            p = mf._params(out_kind, mask_kind, qi, ti, 25.0, 5.0)
+            out = torch.empty(len(q) * dt.itemsize, dtype=torch.uint8, device="cuda")
+            seed_out = torch.zeros(len(q), dtype=torch.float32, device="cuda")
+            n_out = C.c_uint64(0)
+            ctx.check(lib.ssrlcv_b200_match_features(h, C.byref(p), C.c_void_p(qd.data_ptr()), len(q), C.c_void_p(td.data_ptr()), len(t),
+                                                     C.c_void_p(sd_.data_ptr()), len(s2), C.c_void_p(seed_out.data_ptr()), C.c_void_p(out.data_ptr()), C.byref(n_out)))
+            assert np.array_equal(seed_out.cpu().numpy(), sd_want)
+            po = api.O.make_params(out_kind=out_kind, mask_kind=mask_kind, has_seed=True, abs_threshold=1.0e5, rel_threshold=0.8, query_id=0, target_id=1,
+                                   epsilon=25.0, delta=5.0, query_camera=everest.cameras[0], target_camera=everest.cameras[1])
+            want = api.O.generate_matches(po, q, t, sd_want)
+            got = out[: n_out.value * dt.itemsize].cpu().numpy().view(dt)
+            assert len(want) >= 10 and T.fields_equal(got, want), (bright_seed, out_kind)
+    p = mf._params(T.OUT_PAIR, T.MASK_NONE, qi, ti)
+    out = torch.empty(len(q) * 16, dtype=torch.uint8, device="cuda")
+    n_out = C.c_uint64(0)
+    ctx.check(lib.ssrlcv_b200_match_features(h, C.byref(p), C.c_void_p(qd.data_ptr()), len(q), C.c_void_p(td.data_ptr()), len(t), None, 0, None,
+                                             C.c_void_p(out.data_ptr()), C.byref(n_out)))
+    want = api.O.generate_matches(api.O.make_params(out_kind=T.OUT_PAIR, abs_threshold=1.0e5, rel_threshold=0.8), q, t)
+    assert T.fields_equal(out[: n_out.value * 16].cpu().numpy().view(T.UINT2_PAIR), want)
+
+
 # ------------------------------------------------------------------------------------ the stage, stand-alone, from checkpoints
 @pytest.mark.parametrize("n_views", [2, 3])
 def test_stage_runner_from_checkpoint_tree(api, everest, tmp_path, n_views):
