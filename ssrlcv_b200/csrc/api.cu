@@ -28,6 +28,8 @@ void launch_exact(cudaStream_t, const SmaxArgs&, int mask_kind, int sm_count);
 void launch_exact_list(cudaStream_t, const SmaxBatch&, int mask_kind, int sm_count);
 void launch_endpoints(cudaStream_t, const MaskParams&, const float2*, uint64_t, float4*);
 void launch_query_masks(cudaStream_t, const MaskParams&, const float2*, uint64_t, float4*);
+void launch_cull(cudaStream_t, int mask_kind, const float4* q_mask, uint32_t nq, uint32_t n_qtiles, const float4* tbox, uint32_t n_ttiles,
+                 float eps, uint32_t* bits, uint32_t stride);
 void launch_sincos(cudaStream_t, const float*, uint64_t, float*, float*);
 // finalize.cu
 struct CompactArgs {
@@ -64,7 +66,7 @@ struct ssrlcv_b200_ctx {
   EncodeTiledFn encode = nullptr;
   std::string err;
   uint64_t launches = 0;
-  Workspace keys, flagged, counts, scratch, hostpin, qmask, sortws, seedws;
+  Workspace keys, flagged, counts, scratch, hostpin, qmask, sortws, seedws, cullws;
   // zero-initialised once, left zero by the kernels that use them: tie counters (two banks: a matcher launch counts into
   // one and clears the other for the next call), finalize tickets, finalize block states (stamped with `epoch`, so stale
   // entries read as "not yet")
@@ -213,7 +215,7 @@ void ssrlcv_b200_destroy(ssrlcv_b200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (Workspace* w : {&ctx->keys, &ctx->flagged, &ctx->counts, &ctx->scratch, &ctx->qmask, &ctx->nflag, &ctx->tickets, &ctx->fstate, &ctx->sortws, &ctx->seedws}) if (w->p) cudaFree(w->p);
+  for (Workspace* w : {&ctx->keys, &ctx->flagged, &ctx->counts, &ctx->scratch, &ctx->qmask, &ctx->nflag, &ctx->tickets, &ctx->fstate, &ctx->sortws, &ctx->seedws, &ctx->cullws}) if (w->p) cudaFree(w->p);
   for (auto& st : ctx->staged) {
     if (st.h) cudaFreeHost(st.h);
     if (st.d) cudaFree(st.d);
@@ -303,7 +305,8 @@ static int set_alloc(ssrlcv_b200_ctx* ctx, uint64_t n, ssrlcv_b200_set** out, bo
   // one allocation: desc | ext | norm | wcol | loc | sigtheta | wmax | [orig]   (all segments 32-byte aligned since n_pad % 256 == 0)
   const size_t np = s->n_pad;
   const size_t wmax_bytes = ((np / kChunk) * 4 + 255) / 256 * 256;
-  const size_t bytes = np * (kDescBytes + kExtBytes + 4 + 4 + 8 + 8 + (with_orig ? 4 : 0)) + wmax_bytes + 256;
+  const size_t box_bytes = with_orig ? ((np / kChunk + np / kRowPad) * sizeof(float4) + 255) / 256 * 256 : 0;
+  const size_t bytes = np * (kDescBytes + kExtBytes + 4 + 4 + 8 + 8 + (with_orig ? 4 : 0)) + wmax_bytes + box_bytes + 256;
   uint8_t* base = nullptr;
   cudaError_t e = cudaMallocAsync(&base, bytes, ctx->stream);
   if (e != cudaSuccess) {
@@ -318,6 +321,8 @@ static int set_alloc(ssrlcv_b200_ctx* ctx, uint64_t n, ssrlcv_b200_set** out, bo
   s->sigtheta = s->loc + np;
   s->wmax = reinterpret_cast<int32_t*>(s->sigtheta + np);
   s->orig = with_orig ? reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s->wmax) + wmax_bytes) : nullptr;
+  s->wbox = with_orig ? reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(s->orig) + np * 4) : nullptr;   // np * 4 is a multiple of 1024
+  s->tbox = with_orig ? s->wbox + np / kChunk : nullptr;
   s->has_map_a = s->has_map_bx = false;
   *out = s;
   return 0;
@@ -603,9 +608,10 @@ static int32_t d2_cap_of(float abs_thr) {
   return static_cast<int32_t>(c) - 1;
 }
 
-// The x-sorted copy of a packed set (cached on the set, built on first use; enqueue-only).  Rows are ordered by loc.x, padding
-// and NaN locations last; `orig` maps a row back to the caller's index.  Used as the target side of DoubleConstrained
-// searches that have no seed distances to bound their candidates (matcher.cuh t_orig).
+// The spatially sorted copy of a packed set (cached on the set, built on first use; enqueue-only).  Rows are ordered along a
+// Z-curve of loc (NaN locations last); `orig` maps a row back to the caller's index; wbox / tbox hold the bounding boxes of its
+// 32-row windows and 256-row tiles.  Used on BOTH sides of masked searches that have no seed distances to bound their
+// candidates (matcher.cuh t_orig / q_orig / live_bits).
 static int sorted_of(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* ct, const ssrlcv_b200_set** out) {
   ssrlcv_b200_set* t = const_cast<ssrlcv_b200_set*>(ct);
   if (t->sorted) { *out = t->sorted; return 0; }
@@ -628,7 +634,7 @@ static int sorted_of(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* ct, const ssrl
     s2->h_mm[0] = 1;
   }
   if (e != cudaSuccess) { ssrlcv_b200_set_free(s2); return fail(ctx, static_cast<int>(e), "sorted copy: %s", cudaGetErrorString(e)); }
-  ctx->launches += 3;
+  ctx->launches += 4;
   rc = set_finish(ctx, s2);
   if (rc) { ssrlcv_b200_set_free(s2); return rc; }
   s2->fold_ok = t->fold_ok; s2->resolved = true;
@@ -652,7 +658,8 @@ struct PairWork {
   const float* seed = nullptr;    // seed distances of the query set (device) when the ratio test will drop what exceeds it
   float seed_ratio = 0.f;
   bool optimistic_fold = false;   // out: the fold variant was launched before the target set's pack had reported back
-  const ssrlcv_b200_set* tt = nullptr;   // out: the set the kernel reads its targets from (t, or t's x-sorted copy)
+  const ssrlcv_b200_set* tt = nullptr;   // out: the set the kernel reads its targets from (t, or t's spatially sorted copy)
+  const ssrlcv_b200_set* qq = nullptr;   // out: the same for the queries
   SmaxArgs a;                     // out: a.keys, a.n_splits, a.nq_pad describe the pair's candidate keys
 };
 
@@ -682,19 +689,24 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     a.eps = p.mp.eps;
     a.d2_cap = d2_cap_of(p.abs_thr);
     a.q_seed = p.seed; a.seed_ratio = p.seed_ratio;
-    p.tt = p.t;
-    if (p.engine != SSRLCV_B200_ENGINE_SIMT && tiles != 0 && p.mp.kind == SSRLCV_B200_MASK_DOUBLE && p.seed == nullptr && !p.t->is_view) {
-      // worth its three launches (~40 us, once per target set) only for pairs whose matcher runs much longer than that
+    p.tt = p.t; p.qq = p.q;
+    if (p.engine != SSRLCV_B200_ENGINE_SIMT && tiles != 0 && p.mp.kind != SSRLCV_B200_MASK_NONE && p.seed == nullptr && !p.t->is_view && !p.q->is_view) {
+      // Masked search with nothing but the mask to prune it: both sets are matched in spatial (Z-curve) order, so that an
+      // epipolar band misses most 32-target windows and most (query tile, target tile) pairs outright.  Worth its launches
+      // (~4 per set, once per set) only for pairs whose matcher runs much longer than that.
       bool use_sorted = a.nt >= 16384 && static_cast<uint64_t>(a.nq) * a.nt >= (1ull << 28);
       if (ctx->knob[SSRLCV_B200_TUNE_SORTED_TARGETS] >= 0) use_sorted = ctx->knob[SSRLCV_B200_TUNE_SORTED_TARGETS] != 0;
       if (use_sorted) {
         int rc = sorted_of(ctx, p.t, &p.tt);
+        if (!rc) rc = sorted_of(ctx, p.q, &p.qq);
         if (rc) return rc;
       }
     }
     a.t_meta = p.tt->meta;
     a.t_orig = p.tt->orig;
-    a.q_desc = p.q->desc; a.q_norm = p.q->norm; a.q_loc = p.q->loc;
+    a.t_wbox = p.tt->wbox;
+    a.q_orig = p.qq->orig;
+    a.q_desc = p.qq->desc; a.q_norm = p.qq->norm; a.q_loc = p.qq->loc;
     a.t_desc = p.tt->desc; a.t_norm = p.tt->norm; a.t_loc = p.tt->loc; a.t_wcol = p.tt->wcol; a.t_wmax = p.tt->wmax;
     if (p.engine == SSRLCV_B200_ENGINE_SIMT || tiles == 0) {
       plan_simt(ctx, a);
@@ -738,17 +750,24 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     n_tc += static_cast<uint32_t>(g.idx.size());
   }
   // ---- workspaces: one region per pair in each
-  std::vector<size_t> keys_off(n), qmask_off(n);
+  std::vector<size_t> keys_off(n), qmask_off(n), cull_off(n);
+  size_t cull_total = 0;
   for (uint32_t i = 0; i < n; ++i) {
     keys_off[i] = keys_total;
     keys_total += static_cast<size_t>(w[i].a.n_splits) * w[i].a.nq_pad;
     qmask_off[i] = qmask_total;
     if (w[i].mp.kind != SSRLCV_B200_MASK_NONE && w[i].a.nq && w[i].a.nt) qmask_total += static_cast<size_t>(w[i].a.nq_pad) * 2;
+    cull_off[i] = cull_total;
+    if (w[i].tt->tbox != nullptr && w[i].qq->orig != nullptr) {     // both sides spatially sorted: dead tile pairs are worth finding
+      w[i].a.live_stride = (w[i].a.n_ttiles + 31) / 32;
+      cull_total += static_cast<size_t>(w[i].a.n_qtiles) * w[i].a.live_stride;
+    }
   }
   int rc = ws_reserve(ctx, ctx->keys, keys_total * sizeof(uint64_t));
   if (!rc) rc = ws_reserve(ctx, ctx->flagged, keys_total * sizeof(uint32_t));
   if (!rc && qmask_total) rc = ws_reserve(ctx, ctx->qmask, qmask_total * sizeof(float4));
   if (!rc && n_tc) rc = ws_reserve_zero(ctx, ctx->nflag, 2 * static_cast<size_t>(n_tc) * sizeof(uint32_t));
+  if (!rc && cull_total) rc = ws_reserve(ctx, ctx->cullws, cull_total * sizeof(uint32_t));
   if (rc) return rc;
   for (uint32_t i = 0; i < n; ++i) {
     SmaxArgs& a = w[i].a;
@@ -765,9 +784,15 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     PairWork& p = w[i];
     if (p.mp.kind == SSRLCV_B200_MASK_NONE || p.a.nq == 0 || p.a.nt == 0) continue;
     float4* qm = static_cast<float4*>(ctx->qmask.p) + qmask_off[i];
-    launch_query_masks(ctx->stream, p.mp, p.q->loc, p.a.nq_pad, qm);
+    launch_query_masks(ctx->stream, p.mp, p.qq->loc, p.a.nq_pad, qm);
     p.a.q_mask = qm;
     ctx->launches += 1;
+    if (p.a.live_stride) {                               // which (query tile, target tile) pairs can hold a match at all
+      uint32_t* bits = static_cast<uint32_t*>(ctx->cullws.p) + cull_off[i];
+      launch_cull(ctx->stream, p.mp.kind, qm, p.a.nq, p.a.n_qtiles, p.tt->tbox, p.a.n_ttiles, p.mp.eps, bits, p.a.live_stride);
+      p.a.live_bits = bits;
+      ctx->launches += 1;
+    }
   }
   // ---- tensor-core launches: one per (mask kind, fold variant, bookkeeping regime) group
   if (n_tc) {
@@ -790,12 +815,12 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     for (Group& g : groups)
       for (uint32_t i : g.idx) {
         w[i].a.n_flagged = d_nflag + at;
-        rc = ensure_maps(ctx, w[i].q, true, false);
+        rc = ensure_maps(ctx, w[i].qq, true, false);
         if (!rc) rc = ensure_maps(ctx, w[i].tt, false, true);
         if (rc) return rc;
         SmaxJob& j = n_tc > 1 ? hj[at] : single;
         ++at;
-        j.map_q = w[i].q->map_a; j.map_t = w[i].tt->map_b; j.map_text = w[i].tt->map_ext;
+        j.map_q = w[i].qq->map_a; j.map_t = w[i].tt->map_b; j.map_text = w[i].tt->map_ext;
         j.a = w[i].a;
       }
     if (n_tc > 1) {

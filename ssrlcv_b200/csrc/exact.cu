@@ -78,7 +78,7 @@ __device__ __forceinline__ void exact_items(const SmaxArgs& a, int use_list, uin
       uint64_t m = s_min[0];
 #pragma unroll
       for (int w = 1; w < 8; ++w) m = s_min[w] < m ? s_min[w] : m;
-      a.keys[static_cast<uint64_t>(split) * a.nq_pad + row] = m;
+      a.keys[static_cast<uint64_t>(split) * a.nq_pad + (a.q_orig ? a.q_orig[row] : row)] = m;   // row < nq here
     }
     __syncthreads();
   }
@@ -140,6 +140,34 @@ void launch_query_masks(cudaStream_t st, const MaskParams& mp, const float2* loc
   const unsigned blocks = static_cast<unsigned>((n + 127) / 128);
   if (mp.kind == SSRLCV_B200_MASK_DOUBLE) query_mask_kernel<SSRLCV_B200_MASK_DOUBLE><<<blocks, 128, 0, st>>>(mp, loc, n, out);
   else query_mask_kernel<SSRLCV_B200_MASK_FUNDAMENTAL><<<blocks, 128, 0, st>>>(mp, loc, n, out);
+}
+
+// ---- dead tile pairs of a masked search on spatially sorted sets --------------------------------------------
+// One block per query tile, one thread per query: bit j of row qt of `bits` is set iff some query of the tile can match some
+// target whose location lies in the box of target tile j (geometry.cuh box_skips: exact and conservative).  The matcher's
+// roles skip the dead pairs before the MMA.
+template <int kMask>
+__global__ void __launch_bounds__(kBM) cull_kernel(const float4* __restrict__ q_mask, uint32_t nq, const float4* __restrict__ tbox,
+                                                   uint32_t n_ttiles, float eps, uint32_t* __restrict__ bits, uint32_t stride) {
+  const uint32_t row = blockIdx.x * kBM + threadIdx.x;
+  const bool real = row < nq;
+  QueryMask qm;
+  qm = load_query_mask<kMask>(q_mask + 2 * static_cast<uint64_t>(real ? row : 0));
+  uint32_t word = 0;
+  for (uint32_t j = 0; j < n_ttiles; ++j) {
+    const bool live = real && !box_skips<kMask>(qm, __ldg(tbox + j), eps);
+    if (__syncthreads_or(live)) word |= 1u << (j & 31);
+    if ((j & 31) == 31 || j + 1 == n_ttiles) {
+      if (threadIdx.x == 0) bits[blockIdx.x * stride + (j >> 5)] = word;
+      word = 0;
+    }
+  }
+}
+void launch_cull(cudaStream_t st, int mask_kind, const float4* q_mask, uint32_t nq, uint32_t n_qtiles, const float4* tbox, uint32_t n_ttiles,
+                 float eps, uint32_t* bits, uint32_t stride) {
+  if (n_qtiles == 0 || n_ttiles == 0) return;
+  if (mask_kind == SSRLCV_B200_MASK_DOUBLE) cull_kernel<SSRLCV_B200_MASK_DOUBLE><<<n_qtiles, kBM, 0, st>>>(q_mask, nq, tbox, n_ttiles, eps, bits, stride);
+  else cull_kernel<SSRLCV_B200_MASK_FUNDAMENTAL><<<n_qtiles, kBM, 0, st>>>(q_mask, nq, tbox, n_ttiles, eps, bits, stride);
 }
 
 // ---- small diagnostics kernels -----------------------------------------------------------------

@@ -145,6 +145,34 @@ __device__ __forceinline__ bool mask_skips(const QueryMask& m, float tx, float t
   return false;
 }
 
+// true = EVERY target whose location lies in the box (x0, x1, y0, y1) = (b.x, b.y, b.z, b.w) is skipped by this query's mask,
+// decided from the box alone and exactly conservative -- no tolerance needed: every rounded operation of the per-target tests
+// above is monotone in the target's coordinates (tx - left_x, the fma, yl - ty; ex * tx + ez, the division, ty + pq), so over
+// the box the tested quantity ranges between its values at the box's corners.  Any NaN (in the box or in the query's state)
+// makes every comparison false: not culled, as a NaN target passes the per-target test.  An empty box (+inf, -inf, ...) culls.
+template <int kMask>
+__device__ __forceinline__ bool box_skips(const QueryMask& m, float4 b, float eps) {
+  if (kMask == SSRLCV_B200_MASK_DOUBLE) {
+    const Segment& s = m.seg;
+    if (b.y < s.lo_x || b.x > s.hi_x) return true;            // all of it left / right of the segment
+    if (s.vertical) return (s.top_lo > b.w) || (s.bot_hi < b.z);
+    const float yl0 = __fmaf_rn(__fadd_rn(b.x, -s.left_x), s.slope, s.left_y);
+    const float yl1 = __fmaf_rn(__fadd_rn(b.y, -s.left_x), s.slope, s.left_y);
+    if (yl0 != yl0 || yl1 != yl1) return false;
+    const float ya = fminf(yl0, yl1), yb = fmaxf(yl0, yl1);
+    return (__fadd_rn(ya, -b.w) > eps) || (__fadd_rn(yb, -b.z) < -eps);   // the band passes entirely below / above the box
+  }
+  if (kMask == SSRLCV_B200_MASK_FUNDAMENTAL) {
+    const EpiLine& e = m.line;
+    const float p0 = __fdiv_rn(__fmaf_rn(e.ex, b.x, e.ez), e.ey);
+    const float p1 = __fdiv_rn(__fmaf_rn(e.ex, b.y, e.ez), e.ey);
+    if (p0 != p0 || p1 != p1) return false;
+    const float pa = fminf(p0, p1), pb = fmaxf(p0, p1);
+    return (__fadd_rn(b.z, pa) > eps) || (__fadd_rn(b.w, pb) < -eps);
+  }
+  return false;
+}
+
 // the mask state of lane `src`, on every lane of the warp
 template <int kMask>
 __device__ __forceinline__ QueryMask shfl_query_mask(const QueryMask& m, int src) {

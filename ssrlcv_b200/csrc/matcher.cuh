@@ -88,7 +88,9 @@ struct ssrlcv_b200_set_impl {
   float2*  loc;       // [n_pad]
   float2*  sigtheta;  // [n_pad]
   int32_t* wmax;      // [n_pad / 32]  largest wcol of each 32-row window, 0 for windows of padding only
-  uint32_t* orig;     // [n_pad]       x-sorted copies of a set only (api.cu sorted_of): row -> index in the original set
+  uint32_t* orig;     // [n_pad]       spatially sorted copies of a set only (api.cu sorted_of): row -> index in the original set
+  float4*  wbox;      // [n_pad / 32]  sorted copies only: bounding box (x0, x1, y0, y1) of each 32-row window's locations
+  float4*  tbox;      // [n_pad / 256] sorted copies only: the same per 256-row tile
   int32_t* meta;      // [4] device scalars written by the pack kernel: [0] != 0 <=> some W does not fit the fold digits
   bool     fold_ok;      // every W fits the digit range -> fused extra-K-block path (host copy, valid after set_resolve)
   CUtensorMap map_a;     // desc, box 128 x kBM rows, SWIZZLE_128B
@@ -126,10 +128,16 @@ struct SmaxArgs {
   const float4* q_mask;          // [nq_pad][2] per-query epipolar mask state (geometry.cuh), masked modes only
   const uint8_t* t_desc; const int32_t* t_norm; const float2* t_loc; const int32_t* t_wcol;
   const int32_t* t_wmax;         // [n_ttiles * 8] per-window maximum of t_wcol (no-fold variant)
-  // Targets sorted by x (DoubleConstrained searches without seed distances, api.cu sorted_of): row r of the target arrays is
-  // feature t_orig[r] of the caller's set; keys carry the caller's index, so the winner rule is unchanged.  The rows of a
-  // 32-target window then span a narrow x range and a query whose epipolar segment lies outside it skips the window.
+  // Spatially sorted sets (masked searches without seed distances, api.cu sorted_of): row r of the target arrays is feature
+  // t_orig[r] of the caller's set and keys carry the caller's index, so the winner rule is unchanged; row r of the query arrays
+  // is query q_orig[r] and its key is stored at the caller's row.  A 32-target window then covers a small patch of the image
+  // (t_wbox) and a query whose epipolar band misses the patch skips the window; whole (query tile, target tile) pairs no query
+  // of which can match are marked dead beforehand (live_bits, cull_kernel) and skipped by every role before the MMA.
   const uint32_t* t_orig;        // nullptr: rows are in the caller's order
+  const uint32_t* q_orig;        // nullptr: rows are in the caller's order
+  const float4* t_wbox;          // [n_ttiles * 8] window boxes of the sorted target set, or nullptr
+  const uint32_t* live_bits;     // [n_qtiles][live_stride] bit j of row qt: tile pair (qt, j) may hold a match; nullptr: all live
+  uint32_t live_stride;
   uint64_t* keys;                // [n_splits][nq_pad]
   uint32_t* flagged;             // list of (slot * nq_pad + row) needing the exact kernel
   uint32_t* n_flagged;

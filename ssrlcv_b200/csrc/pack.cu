@@ -125,19 +125,73 @@ void launch_pack(cudaStream_t st, const PackJob* jobs, uint32_t n_jobs, int sm_c
   }
 }
 
-// ---------------------------------------------------------------- x-sorted copy of a packed set (masked searches, api.cu sorted_of)
-// key = loc.x as an order-preserving integer; every NaN sorts last (a NaN coordinate passes the reference's mask,
-// src/MatchFactory.cu:2241-2254, so the window that holds it must never be culled: it ends in a NaN, see smax_tc.cu)
-__global__ void sort_keys_x_kernel(const float2* __restrict__ loc, uint32_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+// ---------------------------------------------------------------- spatially sorted copy of a packed set (masked searches, api.cu sorted_of)
+// Rows are ordered along a Z-curve of their image location, so that the 32 rows of a candidate window and the 256 / 128 rows of a
+// target / query tile cover a compact patch of the image: an epipolar band then misses most windows and most tiles, and the
+// matcher skips them from their bounding boxes (smax_tc.cu, cull_kernel in exact.cu).  The key is only a locality heuristic --
+// correctness rests on the boxes, which are taken from the rows themselves: Morton code of the top 16 bits of the two
+// coordinates' order-preserving integer images (sign + exponent + 7 mantissa bits: cells of 4 px between 512 and 1024, finer
+// below).  A NaN coordinate passes the reference's mask (src/MatchFactory.cu:2241-2254, :1627): such rows sort last and make the
+// boxes of their window and tile NaN, which no test can cull.
+__device__ __forceinline__ uint32_t spread16(uint32_t v) {      // abcd -> 0a0b0c0d
+  v &= 0xFFFFu;
+  v = (v | (v << 8)) & 0x00FF00FFu;
+  v = (v | (v << 4)) & 0x0F0F0F0Fu;
+  v = (v | (v << 2)) & 0x33333333u;
+  v = (v | (v << 1)) & 0x55555555u;
+  return v;
+}
+__device__ __forceinline__ uint32_t orderable_f32(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__global__ void sort_keys_zcurve_kernel(const float2* __restrict__ loc, uint32_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float x = loc[i].x;
-  const uint32_t u = __float_as_uint(x);
-  keys[i] = (x != x) ? 0xFFFFFFFFu : ((u & 0x80000000u) ? ~u : (u | 0x80000000u));
+  const float2 l = loc[i];
+  keys[i] = (l.x != l.x || l.y != l.y) ? 0xFFFFFFFFu : ((spread16(orderable_f32(l.y) >> 16) << 1) | spread16(orderable_f32(l.x) >> 16));
   vals[i] = i;
 }
+// One block per 256-row tile, one warp per 32-row window: bounding box (x0, x1, y0, y1) of the window's real rows -- all NaN if
+// any coordinate is NaN, (+inf, -inf, +inf, -inf) if the window holds padding only -- then the tile's box from its 8 windows.
+__global__ void __launch_bounds__(256) boxes_kernel(const float2* __restrict__ loc, uint32_t n, float4* __restrict__ wbox, float4* __restrict__ tbox) {
+  __shared__ float4 s_box[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t r = blockIdx.x * 256u + threadIdx.x;
+  const float inf = __int_as_float(0x7f800000);
+  float x0 = inf, x1 = -inf, y0 = inf, y1 = -inf;
+  bool bad = false;
+  if (r < n) {
+    const float2 l = loc[r];
+    bad = (l.x != l.x) || (l.y != l.y);
+    if (!bad) { x0 = x1 = l.x; y0 = y1 = l.y; }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+    y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+  }
+  if (__any_sync(0xffffffffu, bad)) x0 = x1 = y0 = y1 = __uint_as_float(0x7fc00000u);
+  if (lane == 0) {
+    const float4 b4 = make_float4(x0, x1, y0, y1);
+    wbox[blockIdx.x * 8u + warp] = b4;
+    s_box[warp] = b4;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float4 t = s_box[0];
+    bool nan = t.x != t.x;
+    for (int w = 1; w < 8; ++w) {
+      const float4 b4 = s_box[w];
+      nan |= b4.x != b4.x;
+      t.x = fminf(t.x, b4.x); t.y = fmaxf(t.y, b4.y); t.z = fminf(t.z, b4.z); t.w = fmaxf(t.w, b4.w);
+    }
+    if (nan) t = make_float4(__uint_as_float(0x7fc00000u), __uint_as_float(0x7fc00000u), __uint_as_float(0x7fc00000u), __uint_as_float(0x7fc00000u));
+    tbox[blockIdx.x] = t;
+  }
+}
 // one warp per output row: row r of the sorted set = row perm[r] of the source; rows [n, n_rows) are padding (zero descriptor
-// and digits, W = 0, location NaN so that the last windows are never culled)
+// and digits, W = 0)
 __global__ void __launch_bounds__(256) gather_sorted_kernel(const uint32_t* __restrict__ perm, uint32_t n, uint32_t n_rows,
                                                             const uint8_t* __restrict__ s_desc, const uint8_t* __restrict__ s_ext,
                                                             const int32_t* __restrict__ s_norm, const int32_t* __restrict__ s_wcol,
@@ -168,7 +222,7 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(const uint32_t* __re
     if (lane < 8) e[lane] = 0u;
     if (lane == 0) {
       norm[r] = 0; wcol[r] = 0;
-      loc[r] = make_float2(__uint_as_float(0x7fc00000u), 0.f);
+      loc[r] = make_float2(0.f, 0.f);
       sigtheta[r] = make_float2(0.f, 0.f);
       orig[r] = 0u;
     }
@@ -185,12 +239,13 @@ cudaError_t launch_sort_gather(cudaStream_t st, const ssrlcv_b200_set_impl& src,
                                uint32_t* keys_out, uint32_t* vals_in, uint32_t* vals_out, void* temp, size_t temp_bytes) {
   const uint32_t n = static_cast<uint32_t>(src.n), n_rows = static_cast<uint32_t>(dst.n_pad);
   if (n) {
-    sort_keys_x_kernel<<<(n + 255) / 256, 256, 0, st>>>(src.loc, n, keys_in, vals_in);
+    sort_keys_zcurve_kernel<<<(n + 255) / 256, 256, 0, st>>>(src.loc, n, keys_in, vals_in);
     cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, static_cast<int>(n), 0, 32, st);
     if (e != cudaSuccess) return e;
   }
   gather_sorted_kernel<<<(n_rows + 7) / 8, 256, 0, st>>>(vals_out, n, n_rows, src.desc, src.ext, src.norm, src.wcol, src.loc, src.sigtheta,
                                                          dst.desc, dst.ext, dst.norm, dst.wcol, dst.wmax, dst.loc, dst.sigtheta, dst.orig);
+  boxes_kernel<<<n_rows / 256, 256, 0, st>>>(dst.loc, n, dst.wbox, dst.tbox);
   return cudaGetLastError();
 }
 

@@ -50,6 +50,7 @@ constexpr uint32_t kAExtBytes = kBM * kExtBytes;     // 4096
 constexpr uint32_t kColLocBytes = kBN * 8;           // float2 per target
 constexpr uint32_t kColWBytes = kBN * 4;             // int32 W per target
 constexpr uint32_t kColWmaxBytes = (kBN / kChunk) * 4;  // int32 largest W per 32-target window
+constexpr uint32_t kColBoxBytes = (kBN / kChunk) * 16;  // float4 bounding box per 32-target window (spatially sorted target sets)
 constexpr uint32_t kTmemCols = 512;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (4 + kEpiWarps) * 32;      // 384
@@ -64,7 +65,8 @@ struct SmemLayout {
   // the no-fold variants have no digit tiles: their per-target W ring and window-bound ring live in the bext region
   static constexpr uint32_t col_w = bext;                                // kColStages x 1 KB   (no-fold variants)
   static constexpr uint32_t col_wmax = col_w + kColStages * kColWBytes;  // kColStages x 32 B   (8 window bounds per tile)
-  static constexpr uint32_t bars = col_loc + kColStages * kColLocBytes;
+  static constexpr uint32_t col_box = col_loc + kColStages * kColLocBytes;   // kColStages x 128 B: the tile's 8 window boxes (sorted sets)
+  static constexpr uint32_t bars = col_box + kColStages * kColBoxBytes;
   static constexpr uint32_t n_bars = 2 * kStages + 4 + 4 + 2 * kColStages + 4;
   static constexpr uint32_t tmem_ptr = bars + n_bars * 8;
   static constexpr uint32_t xch = tmem_ptr + 16;                         // 2 (unit parity) x 2 (half) x 128 rows x 24 B
@@ -124,6 +126,16 @@ __device__ __forceinline__ uint32_t eq_mask32(const uint32_t (&x)[32], int32_t m
   return mask;
 }
 
+// Where query row `row` of the (possibly spatially sorted) query arrays keeps its key: the caller's row.  Padding rows of the
+// last tile keep their own (unused) row.
+__device__ __forceinline__ uint32_t key_row(const uint32_t* q_orig, uint32_t nq, uint32_t row) {
+  return (q_orig != nullptr && row < nq) ? __ldg(q_orig + row) : row;
+}
+// true: tile pair (qt, j) may hold a match (no dead-pair bitmap: every pair is live)
+__device__ __forceinline__ bool tile_live(const uint32_t* live_bits, uint32_t stride, uint32_t qt, uint32_t j) {
+  return live_bits == nullptr || ((__ldg(live_bits + static_cast<uint64_t>(qt) * stride + (j >> 5)) >> (j & 31)) & 1u);
+}
+
 // Turns the recorded states of query row r of tile qt (xa: the warp that saw columns [0,128) of every tile, xb: [128,256))
 // into the reference's winner key.  Every recorded column holds exactly the score `top`, so its distance follows from
 // the score and the parity of the target's norm; the minimum key over the recorded columns is the winner.
@@ -167,7 +179,7 @@ __device__ __forceinline__ void resolve_row(const SmaxArgs& job, const WinState&
       }
     }
   }
-  job.keys[static_cast<uint64_t>(slot) * job.nq_pad + row] = key;
+  job.keys[static_cast<uint64_t>(slot) * job.nq_pad + key_row(job.q_orig, job.nq, row)] = key;
 }
 
 // Key slots [slot + 1, fill_end) of a query tile whose last unit this is have no unit of their own (the tile is crossed by
@@ -177,8 +189,10 @@ __device__ __forceinline__ void fill_unused_slots(const SmaxArgs& job, uint32_t 
   if (slot + 1 >= fill_end) return;
   uint64_t* keys = job.keys;
   const uint64_t stride = job.nq_pad;
+  const uint32_t* q_orig = job.q_orig;
+  const uint32_t nq = job.nq;
   for (uint32_t s = slot + 1; s < fill_end; ++s)
-    for (uint32_t r = lane; r < r_count; r += 32) keys[s * stride + qt * kBM + r_begin + r] = kKeyNone;
+    for (uint32_t r = lane; r < r_count; r += 32) keys[s * stride + key_row(q_orig, nq, qt * kBM + r_begin + r)] = kKeyNone;
 }
 
 __device__ __forceinline__ uint32_t word_of(const uint4 (&v)[8], int w) {
@@ -199,10 +213,10 @@ __device__ __forceinline__ void resolve_rows_windows(const SmaxArgs& job, const 
   struct {
     uint32_t nq, nt, nq_pad; float eps; uint64_t target_offset;
     const uint8_t* q_desc; const int32_t* q_norm; const float4* q_mask;
-    const uint8_t* t_desc; const int32_t* t_norm; const float2* t_loc; const uint32_t* t_orig;
+    const uint8_t* t_desc; const int32_t* t_norm; const float2* t_loc; const uint32_t* t_orig; const uint32_t* q_orig;
     uint64_t* keys; uint32_t* flagged; uint32_t* n_flagged;
   } args = {job.nq, job.nt, job.nq_pad, job.eps, job.target_offset, job.q_desc, job.q_norm, job.q_mask,
-            job.t_desc, job.t_norm, job.t_loc, job.t_orig, job.keys, job.flagged, job.n_flagged};
+            job.t_desc, job.t_norm, job.t_loc, job.t_orig, job.q_orig, job.keys, job.flagged, job.n_flagged};
   for (uint32_t g = 0; g < r_count; g += kFly) {
     WinState ms[kFly];
     uint32_t qrow[kFly];
@@ -305,7 +319,7 @@ __device__ __forceinline__ void resolve_rows_windows(const SmaxArgs& job, const 
       uint64_t mine = res[0];
 #pragma unroll
       for (int k = 1; k < kFly; ++k) mine = lane == k ? res[k] : mine;
-      args.keys[static_cast<uint64_t>(slot) * args.nq_pad + qt * kBM + r_begin + g + lane] = mine;
+      args.keys[static_cast<uint64_t>(slot) * args.nq_pad + key_row(args.q_orig, args.nq, qt * kBM + r_begin + g + lane)] = mine;
     }
   }
 }
@@ -441,10 +455,14 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
         const float2* t_loc = u.J->a.t_loc;
         const int32_t* t_wcol = u.J->a.t_wcol;
         const int32_t* t_wmax = u.J->a.t_wmax;
+        const float4* t_wbox = u.J->a.t_wbox;
+        const uint32_t* live_bits = kMask != SSRLCV_B200_MASK_NONE ? u.J->a.live_bits : nullptr;
+        const uint32_t live_stride = u.J->a.live_stride;
         mbar_wait(&a_empty[aslot], aphase ^ 1);
         mbar_arrive_expect_tx(&a_full[aslot], kABytes);
         tma_load_2d(smem + SmemLayout::a + aslot * kABytes, map_q, &a_full[aslot], 0, static_cast<int32_t>(u.qt * kBM));
         for (uint32_t j = u.j0; j < u.j1; ++j) {
+          if (kMask != SSRLCV_B200_MASK_NONE && !tile_live(live_bits, live_stride, u.qt, j)) continue;   // dead pair: every role skips it
           long long p0 = 0;
           if (kTiming) p0 = clock64();
           mbar_wait(&empty[stage], phase ^ 1);
@@ -455,8 +473,11 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
           if (++stage == kStages) { stage = 0; phase ^= 1; }
           if (kCols) {
             mbar_wait(&c_empty[cs], cphase ^ 1);
-            const uint32_t bytes = (kMask != SSRLCV_B200_MASK_NONE ? kColLocBytes : 0) + (!kFold ? kColWBytes + kColWmaxBytes : 0);
+            const uint32_t bytes = (kMask != SSRLCV_B200_MASK_NONE ? kColLocBytes : 0) + (!kFold ? kColWBytes + kColWmaxBytes : 0) +
+                                   (t_wbox != nullptr ? kColBoxBytes : 0);
             mbar_arrive_expect_tx(&c_full[cs], bytes);
+            if (t_wbox != nullptr)
+              bulk_load_1d(smem + SmemLayout::col_box + cs * kColBoxBytes, t_wbox + static_cast<uint64_t>(j) * (kBN / kChunk), kColBoxBytes, &c_full[cs]);
             if (kMask != SSRLCV_B200_MASK_NONE)
               bulk_load_1d(smem + SmemLayout::col_loc + cs * kColLocBytes, t_loc + static_cast<uint64_t>(j) * kBN, kColLocBytes, &c_full[cs]);
             if (!kFold) {   // W of the tile's 256 targets and the largest W of each of its 8 windows (pack.cu wcol / wmax)
@@ -482,7 +503,10 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
       while (u.next(batch, blockIdx.x, kFold)) {
         mbar_wait(&a_full[aslot], aphase);
         const uint64_t a_desc = make_smem_desc(smem_u32(smem + SmemLayout::a + aslot * kABytes), 1024, kSwizzle128B);
+        const uint32_t* live_bits = kMask != SSRLCV_B200_MASK_NONE ? u.J->a.live_bits : nullptr;
+        const uint32_t live_stride = u.J->a.live_stride;
         for (uint32_t j = u.j0; j < u.j1; ++j) {
+          if (kMask != SSRLCV_B200_MASK_NONE && !tile_live(live_bits, live_stride, u.qt, j)) continue;
           long long c0 = 0, c1 = 0, c2 = 0;
           if (kTiming) c0 = clock64();
           mbar_wait(&t_empty[acc], accphase ^ 1);
@@ -563,7 +587,9 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
       const uint32_t row = u.qt * kBM + quarter * 32 + lane;       // this thread's query
       const uint32_t row_c = min(row, args.nq_pad - 1);
       const float eps = args.eps;
-      const bool sorted = args.t_orig != nullptr;
+      const bool boxed = args.t_wbox != nullptr;
+      const uint32_t* live_bits = kMask != SSRLCV_B200_MASK_NONE ? args.live_bits : nullptr;
+      const uint32_t live_stride = args.live_stride;
       QueryMask qm;
       if (kMask != SSRLCV_B200_MASK_NONE) qm = load_query_mask<kMask>(args.q_mask + 2 * static_cast<uint64_t>(row_c));
 
@@ -587,6 +613,7 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
         st.best = floor_s - 1; st.w1 = kNoWin; st.w2 = kNoWin; st.m1 = 0; st.m2 = 0; st.ovf = 0;
       }
       for (uint32_t j = u.j0; j < u.j1; ++j) {
+        if (kMask != SSRLCV_B200_MASK_NONE && !tile_live(live_bits, live_stride, u.qt, j)) continue;
         long long e0 = 0, e1 = 0;
         if (kTiming) e0 = clock64();
         const uint32_t acc = it & 1, accphase = (it >> 1) & 1, cs = it % kColStages, cphase = (it / kColStages) & 1;
@@ -625,16 +652,13 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
 #pragma unroll
         for (uint32_t k = 0; k < kWinPerWarp; ++k) wm[k] = max32(v[k]) + wbound[k];
         uint32_t culled = 0;                                       // bit k: this lane's query cannot match anything in window k
-        if (kMask == SSRLCV_B200_MASK_DOUBLE && sorted) {
-          // x-sorted targets: a window's rows span [first.x, last.x]; the mask rejects every target left of lo_x or right of hi_x
-          // (first test of the reference's mask, src/MatchFactory.cu:2241-2243), so a query whose segment lies outside that span
-          // skips the window without looking at it.  A window that ends in a NaN (NaN coordinates pass the mask; they and the
-          // padding sort last) is never skipped on its left edge.
+        if (kMask != SSRLCV_B200_MASK_NONE && boxed) {
+          // spatially sorted targets: a window's rows lie in a small box of the image; a query whose epipolar band misses the box
+          // (geometry.cuh box_skips: exact, NaN-safe) skips the window without looking at it
 #pragma unroll
           for (uint32_t k = 0; k < kWinPerWarp; ++k) {
-            const float x_first = ld_shared_f2(smem_u32(s_loc + (c_begin + k) * kChunk)).x;
-            const float x_last = ld_shared_f2(smem_u32(s_loc + (c_begin + k) * kChunk + kChunk - 1)).x;
-            const bool outside = (x_last < qm.seg.lo_x) | ((x_first > qm.seg.hi_x) & (x_last == x_last));
+            const int4 bx = ld_shared_v4(smem_u32(smem + SmemLayout::col_box + cs * kColBoxBytes + (c_begin + k) * 16));
+            const bool outside = box_skips<kMask>(qm, make_float4(__int_as_float(bx.x), __int_as_float(bx.y), __int_as_float(bx.z), __int_as_float(bx.w)), eps);
             wm[k] = outside ? 0 : wm[k];
             culled |= outside ? (1u << k) : 0u;
           }

@@ -1254,28 +1254,48 @@ def test_random_sweep_against_oracle(api, everest):
 
 
 @pytest.mark.parametrize("thr", [FLT_MAX, 1.2e5])
-def test_double_constrained_without_seeds_takes_the_x_sorted_targets(api, everest, knobs, thr):
-    """DoubleConstrained searches without seed distances run on an x-sorted copy of the target set (api.cu sorted_of) so that whole
-    32-target windows fall outside a query's epipolar segment: NaN / negative / repeated x coordinates, a ragged last window,
-    both bookkeeping regimes -- same records as the oracle and as the unsorted path."""
+def test_masked_without_seeds_on_spatially_sorted_sets(api, everest, knobs, thr):
+    """Masked searches without seed distances run on Z-curve-sorted copies of BOTH sets (api.cu sorted_of): 32-target windows and
+    (query tile, target tile) pairs whose boxes an epipolar band misses are skipped (geometry.cuh box_skips, exact.cu cull_kernel).
+    NaN / negative / repeated coordinates on both sides (a NaN coordinate passes the reference's mask and must never be culled), a
+    ragged last window, both bookkeeping regimes, both mask kinds -- same records as the oracle and as the unsorted path, in the
+    caller's query order."""
     q, t = synth.make_pair(2500, 8192 + 77, seed=123)
     rng = np.random.default_rng(9)
     t["loc"][rng.choice(len(t), 40, replace=False), 0] = np.nan          # NaN coordinates pass the reference's mask
     t["loc"][rng.choice(len(t), 40, replace=False), 0] = -5.0
     t["loc"][rng.choice(len(t), 300, replace=False), 0] = 512.0           # many equal keys
     t["loc"][rng.choice(len(t), 10, replace=False), 1] = np.nan
+    q["loc"][rng.choice(len(q), 12, replace=False), 0] = np.nan          # a query without a location: its mask state is NaN, nothing is masked
+    q["loc"][rng.choice(len(q), 12, replace=False), 1] = -40.0
     qi, ti = api.Image(0, everest.cameras[0]), api.Image(1, everest.cameras[1])
     p = api.O.make_params(out_kind=T.OUT_DMATCH, mask_kind=T.MASK_DOUBLE, abs_threshold=thr, query_id=0, target_id=1, epsilon=40, delta=5,
                           query_camera=everest.cameras[0], target_camera=everest.cameras[1])
     want = api.O.generate_matches(p, q, t)
     assert len(want) > 50
-    got = {}
+    F = np.array([[1e-6, 2e-6, 0.0015], [-3e-6, 1e-7, -1.0], [-0.0013, 1.0, 4.0]], np.float32)
+    pf = api.O.make_params(out_kind=T.OUT_DMATCH, mask_kind=T.MASK_FUNDAMENTAL, abs_threshold=thr, query_id=0, target_id=1, epsilon=30.0, fundamental=F)
+    want_f = api.O.generate_matches(pf, q, t)
+    assert len(want_f) > 50
     for so in ("1", "0"):
         knobs(sorted=so)
         mf = api.MatchFactory(1.0, thr)
-        got[so] = mf.generateDistanceMatchesDoubleConstrained(qi, _unity(api, q), ti, _unity(api, t), 40.0, 5.0).to_numpy()
-        assert T.fields_equal(got[so], want), so
+        got = mf.generateDistanceMatchesDoubleConstrained(qi, _unity(api, q), ti, _unity(api, t), 40.0, 5.0).to_numpy()
+        assert T.fields_equal(got, want), so
+        got = mf.generateDistanceMatchesConstrained(qi, _unity(api, q), ti, _unity(api, t), 30.0, F).to_numpy()
+        assert T.fields_equal(got, want_f), so
     knobs(sorted=None)
     pr = api.MatchFactory(1.0, thr).generateMatchesDoubleConstrainedIndexOnly(qi, _unity(api, q), ti, _unity(api, t), 40.0, 5.0).to_numpy()
     p.out_kind = T.OUT_PAIR
     assert T.fields_equal(pr, api.O.generate_matches(p, q, t))
+    # a batch of sorted and unsorted pairs in one launch, sets shared between pairs (the sorted copy is cached on the set)
+    knobs(sorted="1")
+    mf = api.MatchFactory(1.0, thr)
+    qu, tu = _unity(api, q), _unity(api, t)
+    jobs = [(mf._params(T.OUT_DMATCH, T.MASK_DOUBLE, qi, ti, 40.0, 5.0), qu, tu, None),
+            (mf._params(T.OUT_DMATCH, T.MASK_NONE, qi, ti), qu, tu, None),
+            (mf._params(T.OUT_DMATCH, T.MASK_FUNDAMENTAL, qi, ti, 30.0, 0.0, F), qu, tu, None)]
+    got = mf.matchBatch(jobs)
+    assert T.fields_equal(got[0].to_numpy(), want) and T.fields_equal(got[2].to_numpy(), want_f)
+    pn = api.O.make_params(out_kind=T.OUT_DMATCH, abs_threshold=thr, query_id=0, target_id=1)
+    assert T.fields_equal(got[1].to_numpy(), api.O.generate_matches(pn, q, t))
