@@ -82,6 +82,19 @@ inline bool b200_device_current(const U& u) {
   return st == ssrlcv::gpu || (st == ssrlcv::both && u->getFore() != ssrlcv::cpu);
 }
 
+// Device memory for the Unity arrays this file returns.  ptr::device<T>(n) is a cudaMalloc whose shared_ptr deleter cudaFrees
+// (include/Memory.cuh:183-216): milliseconds per call for megabyte blocks, more than the whole match.  The Unity only needs a
+// ptr::device<T> that owns its memory, so the block comes from the device's stream-ordered pool instead and the deleter hands it
+// back to the pool (both on the legacy default stream the reference runs on): microseconds, same ownership semantics.
+template <typename E>
+inline ssrlcv::ptr::device<E> b200_pool_device(size_t n) {
+  ssrlcv::ptr::device<E> d;
+  E* raw = nullptr;
+  CudaSafeCall(cudaMallocAsync((void**)&raw, (n ? n : 1) * sizeof(E), cudaStreamLegacy));
+  d.ptr.reset(raw, [](E* p) { cudaFreeAsync(p, cudaStreamLegacy); });
+  return d;
+}
+
 struct PackedSet {   // RAII over ssrlcv_b200_set
   ssrlcv_b200_set* s = nullptr;
   PackedSet(void* features_dev, unsigned long n) { b200_check(ssrlcv_b200_pack(b200_context(), features_dev, n, &s), "ssrlcv_b200_pack"); }
@@ -116,15 +129,10 @@ ssrlcv::ptr::value<ssrlcv::Unity<Out>> b200_generate(
   const unsigned long numPossibleMatches = queryFeatures->size();
   // The reference allocates numPossibleMatches records, compacts into a second allocation and frees the first
   // (src/MatchFactory.cu:31-60, :355-357): two cudaMalloc and a cudaFree of megabyte blocks cost milliseconds, more than the
-  // whole match.  Here the records land in a grow-only scratch buffer first and the Unity the caller gets is allocated once,
-  // at its final size.
-  static void* scratch = nullptr;
-  static size_t scratch_bytes = 0;
-  if (scratch_bytes < numPossibleMatches * sizeof(Out)) {
-    if (scratch) CudaSafeCall(cudaFree(scratch));
-    scratch_bytes = numPossibleMatches * sizeof(Out) + (numPossibleMatches * sizeof(Out)) / 2 + 256;
-    CudaSafeCall(cudaMalloc(&scratch, scratch_bytes));
-  }
+  // whole match.  Here the records are written once, compacted, into a pool block of that capacity, which the returned Unity
+  // then owns (its size is the number of valid matches).
+  ptr::device<Out> matches_device = b200_pool_device<Out>(numPossibleMatches);
+  void* scratch = (void*)matches_device.get();
   ptr::value<Unity<Out>> matches = nullptr;
 
   ssrlcv_b200_match_params p;
@@ -182,8 +190,6 @@ ssrlcv::ptr::value<ssrlcv::Unity<Out>> b200_generate(
         logger.info.printf("%d valid matches found out of %lu original matches", (int)n_out, numPossibleMatches);
       }
     }
-    ptr::device<Out> matches_device(n_out);
-    if (n_out) CudaSafeCall(cudaMemcpy(matches_device.get(), scratch, n_out * sizeof(Out), cudaMemcpyDeviceToDevice));
     matches = ptr::value<Unity<Out>>(matches_device, n_out, gpu);
     delete own_q;
     delete own_t;
@@ -211,8 +217,8 @@ void b200_compact_inplace(U matches, int out_kind, size_t elt, bool refine, floa
   if (refine) logger.info.printf("%lu matches have been refined to %u matches using a cutoff of %f", matches->size(), (unsigned)n_out, threshold);
   else logger.info.printf("%d valid matches found out of %lu original matches", (int)n_out, matches->size());
   typedef typename std::remove_reference<decltype(*matches->device.get())>::type Elt;
-  ptr::device<Elt> kept(n_out);
-  CudaSafeCall(cudaMemcpy(kept.get(), matches->device.get(), n_out * elt, cudaMemcpyDeviceToDevice));
+  ptr::device<Elt> kept = b200_pool_device<Elt>(n_out);
+  CudaSafeCall(cudaMemcpyAsync(kept.get(), matches->device.get(), n_out * elt, cudaMemcpyDeviceToDevice, cudaStreamLegacy));
   matches->setData(kept, n_out, gpu);
   if (origin != gpu) matches->setMemoryState(origin);
 }
@@ -314,7 +320,7 @@ void ssrlcv::MatchFactory<T>::sortMatches(Unity<FeatureMatch<T>>* matches) {
 template <typename T>
 ssrlcv::ptr::value<ssrlcv::Unity<ssrlcv::Match>> ssrlcv::MatchFactory<T>::getRawMatches(ssrlcv::ptr::value<ssrlcv::Unity<DMatch>> matches) {
   if (matches->getMemoryState() == gpu || matches->getFore() == gpu) {
-    ssrlcv::ptr::device<Match> rawMatches_device(matches->size());
+    ssrlcv::ptr::device<Match> rawMatches_device = b200_pool_device<Match>(matches->size());
     b200_check(ssrlcv_b200_raw_matches(b200_context(), matches->device.get(), matches->size(), rawMatches_device.get()), "ssrlcv_b200_raw_matches");
     return ssrlcv::ptr::value<Unity<Match>>(rawMatches_device, matches->size(), gpu);
   }
@@ -340,7 +346,7 @@ ssrlcv::ptr::value<ssrlcv::Unity<float>> ssrlcv::MatchFactory<T>::getSeedDistanc
   if (!b200_device_current(this->seedFeatures)) this->seedFeatures->setMemoryState(gpu);
   if (!b200_device_current(features)) features->setMemoryState(gpu);
   unsigned int numPossibleMatches = features->size();
-  ssrlcv::ptr::value<ssrlcv::Unity<float>> matchDistances = ssrlcv::ptr::value<ssrlcv::Unity<float>>(nullptr, numPossibleMatches, gpu);
+  ssrlcv::ptr::value<ssrlcv::Unity<float>> matchDistances = ssrlcv::ptr::value<ssrlcv::Unity<float>>(b200_pool_device<float>(numPossibleMatches), numPossibleMatches, gpu);
   clock_t timer = clock();
   {
     std::vector<PackedSet*> qs;
@@ -469,7 +475,7 @@ ssrlcv::MatchSet ssrlcv::MatchFactory<T>::generateMatchesExhaustive(std::vector<
     if (seedPacked != nullptr) {
       // getSeedDistances (ref: :915-917) on the sets that are packed already; stream-ordered before the batch below
       clock_t timer = clock();
-      seedOfView[q] = ssrlcv::ptr::value<ssrlcv::Unity<float>>(nullptr, features[q]->size(), gpu);
+      seedOfView[q] = ssrlcv::ptr::value<ssrlcv::Unity<float>>(b200_pool_device<float>(features[q]->size()), features[q]->size(), gpu);
       b200_check(ssrlcv_b200_seed_distances(b200_context(), packed[q]->s, seedPacked->s, seedOfView[q]->device.get()), "ssrlcv_b200_seed_distances");
       logger.info.printf("seed match distances computed in %f seconds.", ((float)clock() - timer) / CLOCKS_PER_SEC);
     }

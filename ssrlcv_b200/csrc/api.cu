@@ -758,7 +758,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     qmask_off[i] = qmask_total;
     if (w[i].mp.kind != SSRLCV_B200_MASK_NONE && w[i].a.nq && w[i].a.nt) qmask_total += static_cast<size_t>(w[i].a.nq_pad) * 2;
     cull_off[i] = cull_total;
-    if (w[i].tt->tbox != nullptr && w[i].qq->orig != nullptr) {     // both sides spatially sorted: dead tile pairs are worth finding
+    if (w[i].tt->tbox != nullptr && w[i].qq->orig != nullptr && w[i].a.n_ttiles <= 32 * 8192) {   // both sides spatially sorted: find the dead tile pairs (bitmap row <= 32 KB of shared memory)
       w[i].a.live_stride = (w[i].a.n_ttiles + 31) / 32;
       cull_total += static_cast<size_t>(w[i].a.n_qtiles) * w[i].a.live_stride;
     }

@@ -149,25 +149,29 @@ void launch_query_masks(cudaStream_t st, const MaskParams& mp, const float2* loc
 template <int kMask>
 __global__ void __launch_bounds__(kBM) cull_kernel(const float4* __restrict__ q_mask, uint32_t nq, const float4* __restrict__ tbox,
                                                    uint32_t n_ttiles, float eps, uint32_t* __restrict__ bits, uint32_t stride) {
+  extern __shared__ uint32_t s_words[];               // [stride]
   const uint32_t row = blockIdx.x * kBM + threadIdx.x;
   const bool real = row < nq;
-  QueryMask qm;
-  qm = load_query_mask<kMask>(q_mask + 2 * static_cast<uint64_t>(real ? row : 0));
-  uint32_t word = 0;
-  for (uint32_t j = 0; j < n_ttiles; ++j) {
-    const bool live = real && !box_skips<kMask>(qm, __ldg(tbox + j), eps);
-    if (__syncthreads_or(live)) word |= 1u << (j & 31);
-    if ((j & 31) == 31 || j + 1 == n_ttiles) {
-      if (threadIdx.x == 0) bits[blockIdx.x * stride + (j >> 5)] = word;
-      word = 0;
-    }
+  for (uint32_t w = threadIdx.x; w < stride; w += kBM) s_words[w] = 0;
+  __syncthreads();
+  const QueryMask qm = load_query_mask<kMask>(q_mask + 2 * static_cast<uint64_t>(real ? row : 0));
+  for (uint32_t w = 0; w < stride; ++w) {             // 32 target tiles per word: no barrier inside
+    uint32_t mine = 0;
+    const uint32_t j_end = min(n_ttiles - w * 32, 32u);
+    if (real)
+      for (uint32_t b = 0; b < j_end; ++b) mine |= box_skips<kMask>(qm, __ldg(tbox + w * 32 + b), eps) ? 0u : (1u << b);
+    mine = __reduce_or_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicOr(&s_words[w], mine);
   }
+  __syncthreads();
+  for (uint32_t w = threadIdx.x; w < stride; w += kBM) bits[blockIdx.x * stride + w] = s_words[w];
 }
 void launch_cull(cudaStream_t st, int mask_kind, const float4* q_mask, uint32_t nq, uint32_t n_qtiles, const float4* tbox, uint32_t n_ttiles,
                  float eps, uint32_t* bits, uint32_t stride) {
   if (n_qtiles == 0 || n_ttiles == 0) return;
-  if (mask_kind == SSRLCV_B200_MASK_DOUBLE) cull_kernel<SSRLCV_B200_MASK_DOUBLE><<<n_qtiles, kBM, 0, st>>>(q_mask, nq, tbox, n_ttiles, eps, bits, stride);
-  else cull_kernel<SSRLCV_B200_MASK_FUNDAMENTAL><<<n_qtiles, kBM, 0, st>>>(q_mask, nq, tbox, n_ttiles, eps, bits, stride);
+  const size_t smem = static_cast<size_t>(stride) * sizeof(uint32_t);   // <= 4 GiTiles / 32 words would not fit: stride is capped by the caller
+  if (mask_kind == SSRLCV_B200_MASK_DOUBLE) cull_kernel<SSRLCV_B200_MASK_DOUBLE><<<n_qtiles, kBM, smem, st>>>(q_mask, nq, tbox, n_ttiles, eps, bits, stride);
+  else cull_kernel<SSRLCV_B200_MASK_FUNDAMENTAL><<<n_qtiles, kBM, smem, st>>>(q_mask, nq, tbox, n_ttiles, eps, bits, stride);
 }
 
 // ---- small diagnostics kernels -----------------------------------------------------------------
