@@ -441,14 +441,15 @@ ssrlcv::MatchSet ssrlcv::MatchFactory<T>::generateMatchesExhaustive(std::vector<
     if (!b200_device_current(features[v])) features[v]->setMemoryState(gpu);
   }
   if (this->seedFeatures != nullptr && !b200_device_current(this->seedFeatures)) this->seedFeatures->setMemoryState(gpu);
-  if (!multi) {
-    // every view (and the seed image's features) is packed once, all of them in ONE launch
+  {
+    // every view (and the seed image's features) is packed once on this device, all of them in ONE launch (with several
+    // devices the pairs are matched elsewhere, but the key-point locations below still come from these packed sets)
     std::vector<const void*> dev;
     std::vector<uint64_t> cnt;
     for (size_t v = 0; v < n; ++v) { dev.push_back(features[v]->device.get()); cnt.push_back(features[v]->size()); }
-    if (this->seedFeatures != nullptr) { dev.push_back(this->seedFeatures->device.get()); cnt.push_back(this->seedFeatures->size()); }
+    if (this->seedFeatures != nullptr && !multi) { dev.push_back(this->seedFeatures->device.get()); cnt.push_back(this->seedFeatures->size()); }
     b200_pack_all(dev, cnt, packed);
-    if (this->seedFeatures != nullptr) { seedPacked = packed.back(); packed.pop_back(); }
+    if (this->seedFeatures != nullptr && !multi) { seedPacked = packed.back(); packed.pop_back(); }
   }
   unsigned long long totalMatches = 0;
   phase("states + pack");
@@ -560,15 +561,13 @@ ssrlcv::MatchSet ssrlcv::MatchFactory<T>::generateMatchesExhaustive(std::vector<
     exit(0);
   }
   phase("records to host");
-  // Key-point locations: 8 bytes per feature (a strided copy of `loc`, byte 8 of each 152-byte record) instead of the whole
-  // records the reference moves to the host (:966-967); the Unity arrays were forced to state gpu above, so none of them has a
-  // host copy right now.
+  // Key-point locations: 8 bytes per feature from the packed sets instead of the whole 152-byte records the reference moves to
+  // the host (:966-967); the Unity arrays were forced to state gpu above, so none of them has a host copy right now.
   std::vector<std::vector<float2>> locOf(n);
   for (size_t v = 0; v < n; ++v) {
     locOf[v].resize(features[v]->size());
     if (!locOf[v].empty())
-      CudaSafeCall(cudaMemcpy2D(locOf[v].data(), sizeof(float2), (const char*)features[v]->device.get() + 8, sizeof(Feature<T>), sizeof(float2),
-                                locOf[v].size(), cudaMemcpyDeviceToHost));
+      CudaSafeCall(cudaMemcpy(locOf[v].data(), ssrlcv_b200_set_loc(packed[v]->s), locOf[v].size() * sizeof(float2), cudaMemcpyDeviceToHost));
   }
   for (size_t v = 0; v < n; ++v) delete packed[v];
   delete seedPacked;
