@@ -274,7 +274,7 @@ class Env:
         self.ctx = Context.get(local_rank)
         # A/B timing of kernel variants: SSRLCV_BENCH_TUNE="fold=0,colmask=1,chunk_q=16384,chunk_t=16384" (tools/ab_fold.sh, e2e_chunks.sh)
         from ssrlcv_b200 import _lib
-        knob_ids = {"fold": _lib.TUNE_FOLD, "colmask": _lib.TUNE_COLUMN_MASKS, "sorted": _lib.TUNE_SORTED_TARGETS,
+        knob_ids = {"fold": _lib.TUNE_FOLD, "colmask": _lib.TUNE_COLUMN_MASKS, "sorted": _lib.TUNE_SORTED_TARGETS, "pair": _lib.TUNE_PAIR_UNITS,
                     "chunk_q": _lib.TUNE_HOST_CHUNK_QUERY_ROWS, "chunk_t": _lib.TUNE_HOST_CHUNK_TARGET_ROWS}
         for kv in filter(None, os.environ.get("SSRLCV_BENCH_TUNE", "").split(",")):
             k, v = kv.split("=")
@@ -320,7 +320,7 @@ def roofline_of(world, evals_per_launch_set, kern_ms, k_n, steps, kernel_note=""
     r = {"bound": "tensor", "achieved": achieved, "peak": peak_tops, "unit": "TFLOP/s", "frac": achieved / peak_tops,
          "frac_vs_nominal": achieved / 4500.0, "frac_vs_int8_mma_measured": (achieved / mma_meas) if mma_meas else None,
          "int8_mma_measured": mma_meas,
-         "kernel": "smax_kernel (tcgen05.mma kind::i8 + fused argmax epilogue)" + kernel_note, "kernel_ms": kern_ms, "launches_timed": int(k_n),
+         "kernel": "smax_pair_kernel / smax_kernel (tcgen05.mma kind::i8 + fused argmax epilogue; large unmasked searches take two query tiles per unit)" + kernel_note, "kernel_ms": kern_ms, "launches_timed": int(k_n),
          "ops": "int8 dense: 256 ops per distance evaluation (128 u8 x u8 MACs); the fold's extra K block is not counted",
          "peak_source": f"2 x bf16_tflops burst, {src}; nominal dense int8 is 4500; int8_mma_measured = MMA-only microbenchmark (tools/microbench.cu)"}
     return r, peak_tops

@@ -23,6 +23,7 @@ cudaError_t launch_sort_gather(cudaStream_t, const ssrlcv_b200_set_impl& src, ss
                                uint32_t* vals_in, uint32_t* vals_out, void* temp, size_t temp_bytes);
 // smax_tc.cu
 cudaError_t launch_smax(cudaStream_t, const SmaxBatch&, int mask_kind, bool fold, bool colmask);
+cudaError_t launch_smax_pair(cudaStream_t, const SmaxBatch&, bool fold, bool colmask);
 // exact.cu
 void launch_exact(cudaStream_t, const SmaxArgs&, int mask_kind, int sm_count);
 void launch_exact_list(cudaStream_t, const SmaxBatch&, int mask_kind, int sm_count);
@@ -670,7 +671,7 @@ struct PairWork {
 // those sets once the stream has been synchronised.  optimistic == NULL: wait for the sets' packs first.
 static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* optimistic) {
   struct Group { std::vector<uint32_t> idx; uint64_t total = 0; };
-  Group groups[12];                                       // [mask kind][fold][column-mask regime]
+  Group groups[24];                                       // [mask kind][fold][column-mask regime][one / two query tiles per unit]
   size_t keys_total = 0, qmask_total = 0;
   if (optimistic) *optimistic = false;
   for (uint32_t i = 0; i < n; ++i) {
@@ -680,8 +681,16 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     p.optimistic_fold = false;
     p.engine = engine_of(ctx);
     a.nq = static_cast<uint32_t>(p.q->n); a.nt = static_cast<uint32_t>(p.t->n); a.nq_pad = static_cast<uint32_t>(p.q->n_pad);
-    a.n_qtiles = (a.nq + kBM - 1) / kBM;
     a.n_ttiles = (a.nt + kBN - 1) / kBN;
+    // Large unmasked searches walk the score matrix two query tiles at a time (smax_pair.cu: every target tile is staged once
+    // per 256 queries -- half the L2 -> SM traffic -- and each accumulator has its own epilogue warps); everything else, and
+    // pairs too small to balance 256-row units over the SMs, one tile at a time (smax_tc.cu).
+    bool pair_units = p.engine != SSRLCV_B200_ENGINE_SIMT && p.mp.kind == SSRLCV_B200_MASK_NONE && a.nq_pad % (2 * kBM) == 0 &&
+                      static_cast<uint64_t>((a.nq + 2 * kBM - 1) / (2 * kBM)) * a.n_ttiles >= 8ull * static_cast<uint64_t>(ctx->sm_count);
+    if (ctx->knob[SSRLCV_B200_TUNE_PAIR_UNITS] >= 0)
+      pair_units = ctx->knob[SSRLCV_B200_TUNE_PAIR_UNITS] != 0 && p.engine != SSRLCV_B200_ENGINE_SIMT && p.mp.kind == SSRLCV_B200_MASK_NONE && a.nq_pad % (2 * kBM) == 0;
+    a.q_tile_rows = pair_units ? 2 * kBM : kBM;
+    a.n_qtiles = (a.nq + a.q_tile_rows - 1) / a.q_tile_rows;
     const uint64_t tiles = static_cast<uint64_t>(a.n_qtiles) * a.n_ttiles;
     if (tiles >= (1ull << 32))
       return fail(ctx, SSRLCV_B200_EINVAL, "%u x %u features is too large for one call: shard the target set (ssrlcv_b200_match_candidates)", a.nq, a.nt);
@@ -731,7 +740,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       // bookkeeping regime (smax_tc.cu): exact column masks for thresholded searches and short target sets
       bool colmask = a.d2_cap != 0x7fffffff || a.q_seed != nullptr || a.n_ttiles < 64;
       if (ctx->knob[SSRLCV_B200_TUNE_COLUMN_MASKS] >= 0) colmask = ctx->knob[SSRLCV_B200_TUNE_COLUMN_MASKS] != 0;   // A/B timing, tests
-      Group& g = groups[p.mp.kind * 4 + (fold ? 2 : 0) + (colmask ? 1 : 0)];
+      Group& g = groups[2 * (p.mp.kind * 4 + (fold ? 2 : 0) + (colmask ? 1 : 0)) + (pair_units ? 1 : 0)];
       a.tile_begin = g.total;
       g.total += tiles;
       a.tile_end = g.total;
@@ -828,8 +837,9 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       if (rc) return rc;
     }
     at = 0;
-    for (int gi = 0; gi < 12; ++gi) {
-      Group& g = groups[gi];
+    for (int gi2 = 0; gi2 < 24; ++gi2) {
+      Group& g = groups[gi2];
+      const int gi = gi2 >> 1;
       if (g.idx.empty()) continue;
       SmaxBatch b;
       memset(&b, 0, sizeof b);
@@ -840,6 +850,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       b.total_tiles = g.total;
       b.flags = d_nflag + at;
       b.clear = d_nflag_other; b.clear_n = bank_len;
+      b.diag = ctx->knob[SSRLCV_B200_TUNE_DIAG] > 0 ? static_cast<uint32_t>(ctx->knob[SSRLCV_B200_TUNE_DIAG]) : 0u;
       b.timing = ctx->knob[SSRLCV_B200_TUNE_TIMING_BUFFER] > 0 ? reinterpret_cast<unsigned long long*>(ctx->knob[SSRLCV_B200_TUNE_TIMING_BUFFER]) : nullptr;
       if (ctx->profiling) {
         if (ctx->prof_used == ctx->prof_events.size()) {
@@ -849,7 +860,8 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
         }
         CU(cudaEventRecord(ctx->prof_events[ctx->prof_used].first, ctx->stream));
       }
-      cudaError_t e = launch_smax(ctx->stream, b, gi / 4, (gi & 2) != 0, (gi & 1) != 0);
+      cudaError_t e = (gi2 & 1) ? launch_smax_pair(ctx->stream, b, (gi & 2) != 0, (gi & 1) != 0)
+                                : launch_smax(ctx->stream, b, gi / 4, (gi & 2) != 0, (gi & 1) != 0);
       if (e != cudaSuccess) return fail(ctx, static_cast<int>(e), "smax launch: %s", cudaGetErrorString(e));
       if (ctx->profiling) { CU(cudaEventRecord(ctx->prof_events[ctx->prof_used].second, ctx->stream)); ctx->prof_used++; }
       launch_exact_list(ctx->stream, b, gi / 4, ctx->sm_count);

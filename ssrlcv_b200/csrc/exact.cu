@@ -34,7 +34,7 @@ __device__ __forceinline__ void exact_items(const SmaxArgs& a, int use_list, uin
       // entry = key slot * nq_pad + row; the slot's target range is the tensor-core kernel's unit (matcher.cuh)
       const uint32_t e = a.flagged[item];
       split = e / a.nq_pad; row = e % a.nq_pad;
-      const uint32_t qt = row / kBM;
+      const uint32_t qt = row / a.q_tile_rows;
       const uint32_t cta = cta_of_tile(a.total_tiles, a.n_ctas, a.tile_begin + static_cast<uint64_t>(qt) * a.n_ttiles) + split;
       uint32_t j0, j1;
       unit_range(a, cta, qt, j0, j1);

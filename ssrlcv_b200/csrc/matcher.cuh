@@ -102,7 +102,8 @@ struct ssrlcv_b200_set_impl {
 struct SmaxArgs {
   uint32_t nq, nt;               // real sizes
   uint32_t nq_pad;
-  uint32_t n_qtiles;             // ceil(nq / kBM)
+  uint32_t q_tile_rows;          // query rows per work unit: kBM (smax_tc.cu) or 2 * kBM (smax_pair.cu: two A tiles per unit)
+  uint32_t n_qtiles;             // ceil(nq / q_tile_rows)
   uint32_t n_ttiles;             // ceil(nt / kBN)
   uint32_t n_splits;             // key slots per query: keys is [n_splits][nq_pad]
   uint32_t tiles_per_split;      // SIMT engine only: fixed-length target splits, slot = split
@@ -161,6 +162,7 @@ struct SmaxBatch {
   const uint32_t* flags;         // this launch's tie counters, one per job (job i counts into flags[i])
   uint32_t* clear;               // the tie counters of the OTHER bank: zeroed by CTA 0 for the call after this one
   uint32_t clear_n;
+  uint32_t diag;                 // what-if timing bits (SSRLCV_B200_TUNE_DIAG); 0 in every product launch
   SmaxJob inline_job;
 };
 

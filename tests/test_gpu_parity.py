@@ -33,13 +33,15 @@ def api():
 
 
 def _suite_default_knobs():
-    """SSRLCV_TEST_FOLD=0|1 / SSRLCV_TEST_COLMASK=0|1 run the whole suite under one forced matcher variant (tools/ab_kernel.sh)."""
+    """SSRLCV_TEST_FOLD=0|1 / SSRLCV_TEST_COLMASK=0|1 / SSRLCV_TEST_PAIR=0|1 run the whole suite under one forced matcher variant (tools/ab_kernel.sh)."""
     from ssrlcv_b200 import _lib
     from ssrlcv_b200.match_factory import Context
     f = os.environ.get("SSRLCV_TEST_FOLD")
     Context.get(0).tune(_lib.TUNE_FOLD, int(f) if f not in (None, "") else -1)
     cm = os.environ.get("SSRLCV_TEST_COLMASK")
     Context.get(0).tune(_lib.TUNE_COLUMN_MASKS, int(cm) if cm not in (None, "") else -1)
+    pu = os.environ.get("SSRLCV_TEST_PAIR")
+    Context.get(0).tune(_lib.TUNE_PAIR_UNITS, int(pu) if pu not in (None, "") else -1)
 
 
 @pytest.fixture
@@ -47,7 +49,7 @@ def knobs(api):
     """ssrlcv_b200_tune for the duration of one test: knobs(fold=0, chunk_rows=512, ...); everything back to "library decides" afterwards."""
     from ssrlcv_b200 import _lib
     from ssrlcv_b200.match_factory import Context
-    names = {"fold": [_lib.TUNE_FOLD], "colmask": [_lib.TUNE_COLUMN_MASKS], "sorted": [_lib.TUNE_SORTED_TARGETS],
+    names = {"fold": [_lib.TUNE_FOLD], "colmask": [_lib.TUNE_COLUMN_MASKS], "sorted": [_lib.TUNE_SORTED_TARGETS], "pair": [_lib.TUNE_PAIR_UNITS],
              "chunk_rows": [_lib.TUNE_HOST_CHUNK_QUERY_ROWS, _lib.TUNE_HOST_CHUNK_TARGET_ROWS]}
     ctx = Context.get(0)
 

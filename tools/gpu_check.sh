@@ -29,7 +29,7 @@ for w in $what; do
         ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_$c.csv \
             python bench.py --workload $c --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_bench_under_ncu_$c.log 2>&1
       done
-      ncu --set full --clock-control none --import-source on -k regex:smax_kernel -s 3 -c 1 -f -o gpurun_out/${tag}_smax_C3 \
+      ncu --set full --clock-control none --import-source on -k regex:smax_ -s 3 -c 1 -f -o gpurun_out/${tag}_smax_C3 \
           python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_ncu_full.log 2>&1 ;;
   esac
 done

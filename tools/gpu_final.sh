@@ -14,7 +14,7 @@ done
 for c in C3 C2 C1; do
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 150 --csv --log-file gpurun_out/${tag}_launches_$(echo $c | tr A-Z a-z).csv python bench.py --workload $c --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_under_ncu_$c.log 2>&1
 done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:smax_kernel -s 3 -c 1 -f -o gpurun_out/${tag}_smax_c3 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_ncu_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:smax_ -s 3 -c 1 -f -o gpurun_out/${tag}_smax_c3 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_ncu_full.log 2>&1
 ls -la gpurun_out/${tag}_smax_c3.ncu-rep
 python tools/kerneltiming.py C3 > gpurun_out/${tag}_kerneltiming_c3.txt 2>&1
 [ -x tools/microbench ] && ./tools/microbench > gpurun_out/${tag}_microbench.txt 2>&1
