@@ -360,12 +360,16 @@ def run_ours(args, w, env):
     # ---------------- device-resident timing ----------------
     for _ in range(max(args.warmup, 3)):
         step()
-    lib.ssrlcv_b200_set_profiling(h, 1)
     sampler = ClockSampler(env.local_rank) if rank == 0 else None      # one sampler per job, not per rank
     launches0 = ctx.launch_count()
     total_ms, n_matches, wall = env.timed(step, args.steps)
     launches = ctx.launch_count() - launches0
+    # The matcher's own duration (roofline): CUDA events around every matcher launch on the library's stream, over the same K
+    # steps run once more.  Not in the pass above: an event record between two kernels serialises them, and the chain's
+    # kernels are launched with programmatic stream serialisation (each sets itself up while its predecessor drains).
     k_ms, k_n = C.c_double(0), C.c_uint64(0)
+    lib.ssrlcv_b200_set_profiling(h, 1)
+    env.timed(step, args.steps)
     lib.ssrlcv_b200_kernel_time(h, C.byref(k_ms), C.byref(k_n))
     lib.ssrlcv_b200_set_profiling(h, 0)
     clocks = None

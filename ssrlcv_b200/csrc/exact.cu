@@ -7,6 +7,7 @@
 // 32-thread blocks (ref: src/MatchFactory.cu:1466-1492); the winner is the minimum of the key (d2, f%32, f).
 #include "geometry.cuh"
 #include "matcher.cuh"
+#include "ptx.cuh"
 
 namespace b200 {
 
@@ -97,6 +98,8 @@ template <int kMask>
 __global__ void __launch_bounds__(256) exact_list_kernel(const __grid_constant__ SmaxBatch b) {
   __shared__ uint64_t s_min[8];
   __shared__ int s_any;
+  pdl_launch_dependents();
+  pdl_wait();                                         // the matcher launch whose tie counters are read next
   if (threadIdx.x == 0) s_any = 0;
   __syncthreads();
   for (uint32_t j = threadIdx.x; j < b.n_jobs; j += blockDim.x)
@@ -122,15 +125,17 @@ void launch_exact(cudaStream_t st, const SmaxArgs& a, int mask_kind, int sm_coun
 void launch_exact_list(cudaStream_t st, const SmaxBatch& b, int mask_kind, int sm_count) {
   const int blocks = sm_count * 2;
   switch (mask_kind) {
-    case SSRLCV_B200_MASK_NONE: exact_list_kernel<SSRLCV_B200_MASK_NONE><<<blocks, 256, 0, st>>>(b); break;
-    case SSRLCV_B200_MASK_FUNDAMENTAL: exact_list_kernel<SSRLCV_B200_MASK_FUNDAMENTAL><<<blocks, 256, 0, st>>>(b); break;
-    default: exact_list_kernel<SSRLCV_B200_MASK_DOUBLE><<<blocks, 256, 0, st>>>(b); break;
+    case SSRLCV_B200_MASK_NONE: launch_pdl(exact_list_kernel<SSRLCV_B200_MASK_NONE>, dim3(blocks), dim3(256), 0, st, b); break;
+    case SSRLCV_B200_MASK_FUNDAMENTAL: launch_pdl(exact_list_kernel<SSRLCV_B200_MASK_FUNDAMENTAL>, dim3(blocks), dim3(256), 0, st, b); break;
+    default: launch_pdl(exact_list_kernel<SSRLCV_B200_MASK_DOUBLE>, dim3(blocks), dim3(256), 0, st, b); break;
   }
 }
 
 // ---- per-query mask prologue ---------------------------------------------------------------------
 template <int kMask>
 __global__ void __launch_bounds__(128) query_mask_kernel(MaskParams mp, const float2* __restrict__ loc, uint64_t n, float4* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();                                         // loc comes from the pack launch in front of this one
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   store_query_mask<kMask>(out + 2 * i, make_query_mask<kMask>(mp, loc[i]));
@@ -138,8 +143,8 @@ __global__ void __launch_bounds__(128) query_mask_kernel(MaskParams mp, const fl
 void launch_query_masks(cudaStream_t st, const MaskParams& mp, const float2* loc, uint64_t n, float4* out) {
   if (n == 0 || mp.kind == SSRLCV_B200_MASK_NONE) return;
   const unsigned blocks = static_cast<unsigned>((n + 127) / 128);
-  if (mp.kind == SSRLCV_B200_MASK_DOUBLE) query_mask_kernel<SSRLCV_B200_MASK_DOUBLE><<<blocks, 128, 0, st>>>(mp, loc, n, out);
-  else query_mask_kernel<SSRLCV_B200_MASK_FUNDAMENTAL><<<blocks, 128, 0, st>>>(mp, loc, n, out);
+  if (mp.kind == SSRLCV_B200_MASK_DOUBLE) launch_pdl(query_mask_kernel<SSRLCV_B200_MASK_DOUBLE>, dim3(blocks), dim3(128), 0, st, mp, loc, n, out);
+  else launch_pdl(query_mask_kernel<SSRLCV_B200_MASK_FUNDAMENTAL>, dim3(blocks), dim3(128), 0, st, mp, loc, n, out);
 }
 
 // ---- dead tile pairs of a masked search on spatially sorted sets --------------------------------------------

@@ -11,6 +11,7 @@
 #include <cub/cub.cuh>
 
 #include "matcher.cuh"
+#include "ptx.cuh"
 
 namespace b200 {
 
@@ -62,6 +63,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   __shared__ uint32_t s_warp[8];
   __shared__ uint32_t s_pre[8];
   __shared__ uint32_t s_ticket;
+  pdl_launch_dependents();
+  pdl_wait();                                         // keys (and a staged job table) come from the launches in front of this one
   const FinalizeArgs a = fb.jobs ? fb.jobs[blockIdx.y] : fb.inline_job;
   const uint32_t nq = a.nq, n_blocks = (nq + 255) / 256;
   if (blockIdx.x >= n_blocks) return;
@@ -163,11 +166,13 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
 void launch_finalize(cudaStream_t st, const FinalizeBatch& fb, uint32_t n_jobs, uint32_t max_nq) {
   if (n_jobs == 0 || max_nq == 0) return;
   const dim3 grid((max_nq + 255) / 256, n_jobs);
-  finalize_kernel<<<grid, 256, 0, st>>>(fb);
+  launch_pdl(finalize_kernel, grid, dim3(256), 0, st, fb);
 }
 
 // keys -> float seed distances (min over splits; FLT_MAX when there is no seed feature)
 __global__ void seed_from_keys_kernel(const uint64_t* keys, uint32_t nq, uint32_t nq_pad, uint32_t n_splits, float* out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   uint64_t key = kKeyNone;
@@ -178,10 +183,12 @@ __global__ void seed_from_keys_kernel(const uint64_t* keys, uint32_t nq, uint32_
   out[i] = key >= kKeyNeedsExact ? FLT_MAX : static_cast<float>(static_cast<uint32_t>(key >> 37));
 }
 void launch_seed_from_keys(cudaStream_t st, const uint64_t* keys, uint32_t nq, uint32_t nq_pad, uint32_t n_splits, float* out) {
-  if (nq) seed_from_keys_kernel<<<(nq + 255) / 256, 256, 0, st>>>(keys, nq, nq_pad, n_splits, out);
+  if (nq) launch_pdl(seed_from_keys_kernel, dim3((nq + 255) / 256), dim3(256), 0, st, keys, nq, nq_pad, n_splits, out);
 }
 
 __global__ void min_keys_kernel(const uint64_t* keys, uint32_t nq, uint32_t nq_pad, uint32_t n_splits, uint64_t* out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   uint64_t key = kKeyNone;
@@ -192,7 +199,7 @@ __global__ void min_keys_kernel(const uint64_t* keys, uint32_t nq, uint32_t nq_p
   out[i] = key;
 }
 void launch_min_keys(cudaStream_t st, const uint64_t* keys, uint32_t nq, uint32_t nq_pad, uint32_t n_splits, uint64_t* out) {
-  if (nq) min_keys_kernel<<<(nq + 255) / 256, 256, 0, st>>>(keys, nq, nq_pad, n_splits, out);
+  if (nq) launch_pdl(min_keys_kernel, dim3((nq + 255) / 256), dim3(256), 0, st, keys, nq, nq_pad, n_splits, out);
 }
 
 __global__ void fill_u64_kernel(uint64_t* p, uint64_t n, uint64_t v) {

@@ -222,6 +222,20 @@ __host__ __device__ __forceinline__ void unit_range(const SmaxArgs& a, uint32_t 
   j0 = static_cast<uint32_t>(b - base); j1 = static_cast<uint32_t>(e - base);
 }
 
+// Launch with programmatic stream serialisation: the kernel may be scheduled while the previous kernel of the stream drains
+// (ptx.cuh pdl_wait / pdl_launch_dependents).  The call chain of one match is 4-8 short kernels around the matcher; the
+// launch gaps between them were a fifth of the small configurations' step.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace b200
 
 struct ssrlcv_b200_set : b200::ssrlcv_b200_set_impl {

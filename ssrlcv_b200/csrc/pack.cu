@@ -10,6 +10,7 @@
 #include <cub/cub.cuh>
 
 #include "matcher.cuh"
+#include "ptx.cuh"
 
 namespace b200 {
 
@@ -24,6 +25,8 @@ namespace b200 {
 // cover one descriptor; the record base is only 8-byte aligned), so the window's largest W is a register maximum: no atomics
 // and nothing to zero beforehand.  Rows [n, n_rows) are the zero padding of the set and are written here too.
 __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackBatch b) {
+  pdl_wait();                  // the rows may be recycled memory a previous kernel of the stream still reads
+  pdl_launch_dependents();     // the matcher behind this launch sets itself up while the windows are packed
   const int lane = threadIdx.x & 31, half = lane >> 4, sub = lane & 15;
   const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -120,7 +123,7 @@ void launch_pack(cudaStream_t st, const PackJob* jobs, uint32_t n_jobs, int sm_c
     uint64_t blocks = (static_cast<uint64_t>(b.total_windows) + 7) / 8;
     const uint64_t cap = static_cast<uint64_t>(sm_count) * 8;
     if (blocks > cap) blocks = cap;
-    pack_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(b);
+    launch_pdl(pack_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, b);
     if (launches) *launches += 1;
   }
 }

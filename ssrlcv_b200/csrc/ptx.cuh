@@ -21,6 +21,15 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with launch_pdl (matcher.cuh) may begin while its predecessor in the stream is still running: pdl_wait()
+// returns once that grid has completed and its memory is visible (a no-op in a normally launched kernel); everything a kernel
+// does before it (barrier init, TMEM allocation, index arithmetic) overlaps the predecessor's tail and the launch latency.
+// EVERY path of such a kernel must pass pdl_wait() before it exits, so that completion stays transitive along the chain.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// lets the NEXT kernel of the stream be scheduled as soon as every CTA of this grid has got here (or exited)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

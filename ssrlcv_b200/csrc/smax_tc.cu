@@ -105,9 +105,6 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (blockIdx.x == 0)                                 // tie counters of the other bank (the next call's): see exact.cu
-    for (uint32_t i = threadIdx.x; i < batch.clear_n; i += kThreads) batch.clear[i] = 0;
-
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kEpiWarps); }
@@ -133,6 +130,11 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // everything above overlapped the tail of the previous kernel of the stream (the pack launch); its output is read from here on
+  pdl_launch_dependents();
+  pdl_wait();
+  if (blockIdx.x == 0)                                 // tie counters of the other bank (the next call's): see exact.cu.  After the
+    for (uint32_t i = threadIdx.x; i < batch.clear_n; i += kThreads) batch.clear[i] = 0;   // wait: the previous call's tie pass reads that bank
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -494,8 +496,7 @@ static cudaError_t launch_one(cudaStream_t st, const SmaxBatch& b) {
     if (e != cudaSuccess) return e;
     if (dev < 64) configured.fetch_or(1ull << dev, std::memory_order_release);
   }
-  kern<<<b.n_ctas, kThreads, kSmemBytes, st>>>(b);
-  return cudaGetLastError();
+  return launch_pdl(kern, dim3(b.n_ctas), dim3(kThreads), kSmemBytes, st, b);
 }
 
 template <int kMask>
