@@ -155,6 +155,8 @@ template <int kMask>
 __global__ void __launch_bounds__(kBM) cull_kernel(const float4* __restrict__ q_mask, uint32_t nq, const float4* __restrict__ tbox,
                                                    uint32_t n_ttiles, float eps, uint32_t* __restrict__ bits, uint32_t stride) {
   extern __shared__ uint32_t s_words[];               // [stride]
+  pdl_launch_dependents();
+  pdl_wait();                                         // q_mask comes from the launch in front of this one
   const uint32_t row = blockIdx.x * kBM + threadIdx.x;
   const bool real = row < nq;
   for (uint32_t w = threadIdx.x; w < stride; w += kBM) s_words[w] = 0;
@@ -175,8 +177,8 @@ void launch_cull(cudaStream_t st, int mask_kind, const float4* q_mask, uint32_t 
                  float eps, uint32_t* bits, uint32_t stride) {
   if (n_qtiles == 0 || n_ttiles == 0) return;
   const size_t smem = static_cast<size_t>(stride) * sizeof(uint32_t);   // <= 4 GiTiles / 32 words would not fit: stride is capped by the caller
-  if (mask_kind == SSRLCV_B200_MASK_DOUBLE) cull_kernel<SSRLCV_B200_MASK_DOUBLE><<<n_qtiles, kBM, smem, st>>>(q_mask, nq, tbox, n_ttiles, eps, bits, stride);
-  else cull_kernel<SSRLCV_B200_MASK_FUNDAMENTAL><<<n_qtiles, kBM, smem, st>>>(q_mask, nq, tbox, n_ttiles, eps, bits, stride);
+  if (mask_kind == SSRLCV_B200_MASK_DOUBLE) launch_pdl(cull_kernel<SSRLCV_B200_MASK_DOUBLE>, dim3(n_qtiles), dim3(kBM), smem, st, q_mask, nq, tbox, n_ttiles, eps, bits, stride);
+  else launch_pdl(cull_kernel<SSRLCV_B200_MASK_FUNDAMENTAL>, dim3(n_qtiles), dim3(kBM), smem, st, q_mask, nq, tbox, n_ttiles, eps, bits, stride);
 }
 
 // ---- small diagnostics kernels -----------------------------------------------------------------

@@ -1301,3 +1301,30 @@ def test_masked_without_seeds_on_spatially_sorted_sets(api, everest, knobs, thr)
     assert T.fields_equal(got[0].to_numpy(), want) and T.fields_equal(got[2].to_numpy(), want_f)
     pn = api.O.make_params(out_kind=T.OUT_DMATCH, abs_threshold=thr, query_id=0, target_id=1)
     assert T.fields_equal(got[1].to_numpy(), api.O.generate_matches(pn, q, t))
+
+
+@pytest.mark.parametrize("thr", [FLT_MAX, 3.0e5])
+def test_sorted_masked_search_with_ties_everywhere(api, everest, knobs, thr):
+    """Masked searches on spatially sorted sets when ties are the rule: few distinct descriptors repeated all over the target set, so
+    nearly every query ties in three or more windows of several units -- the tie pass (exact.cu, rows mapped back through q_orig /
+    t_orig) and the lane rule on the CALLER's indices decide the records.  Same as the oracle, under both bookkeeping regimes."""
+    rng = np.random.default_rng(77)
+    base = synth.sift_descriptors(rng, 6)
+    q, t = synth.make_pair(700, 4096 + 300, seed=5)
+    t["values"] = base[rng.integers(0, 6, len(t))]
+    q["values"][:500] = base[rng.integers(0, 6, 500)]
+    qi, ti = api.Image(0, everest.cameras[0]), api.Image(1, everest.cameras[1])
+    F = np.array([[1e-6, 2e-6, 0.0015], [-3e-6, 1e-7, -1.0], [-0.0013, 1.0, 4.0]], np.float32)
+    pf = api.O.make_params(out_kind=T.OUT_DMATCH, mask_kind=T.MASK_FUNDAMENTAL, abs_threshold=thr, query_id=0, target_id=1, epsilon=60.0, fundamental=F)
+    want_f = api.O.generate_matches(pf, q, t)
+    p = api.O.make_params(out_kind=T.OUT_DMATCH, mask_kind=T.MASK_DOUBLE, abs_threshold=thr, query_id=0, target_id=1, epsilon=80, delta=5,
+                          query_camera=everest.cameras[0], target_camera=everest.cameras[1])
+    want = api.O.generate_matches(p, q, t)
+    assert len(want_f) > 100 and len(want) > 100
+    for cm in ("1", "0"):
+        knobs(sorted="1", colmask=cm)
+        mf = api.MatchFactory(1.0, thr)
+        got = mf.generateDistanceMatchesConstrained(qi, _unity(api, q), ti, _unity(api, t), 60.0, F).to_numpy()
+        assert T.fields_equal(got, want_f), cm
+        got = mf.generateDistanceMatchesDoubleConstrained(qi, _unity(api, q), ti, _unity(api, t), 80.0, 5.0).to_numpy()
+        assert T.fields_equal(got, want), cm
