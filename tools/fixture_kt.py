@@ -40,7 +40,11 @@ lib.ssrlcv_b200_pack(h, C.c_void_p(td.data_ptr()), len(t), C.byref(ht))
 lib.ssrlcv_b200_set_profiling(h, 1)
 k_ms, k_n = C.c_double(0), C.c_uint64(0)
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for sorted_ in (1, 0):
+cm_env = os.environ.get("KT_COLMASK")
+if cm_env:
+    lib.ssrlcv_b200_tune(h, _lib.TUNE_COLUMN_MASKS, int(cm_env))
+print("colmask", cm_env or "auto")
+for sorted_ in ((1, 0) if mask else (1,)):
     lib.ssrlcv_b200_tune(h, _lib.TUNE_SORTED_TARGETS, sorted_)
     lib.ssrlcv_b200_tune(h, _lib.TUNE_TIMING_BUFFER, 0)
     for it in range(3):
