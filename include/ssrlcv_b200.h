@@ -229,6 +229,14 @@ int  ssrlcv_b200_match_candidates(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_
 int  ssrlcv_b200_match_candidates_seeded(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* params,
                                          const ssrlcv_b200_set* query, const ssrlcv_b200_set* target_shard,
                                          uint64_t target_offset, const float* seed_dist_dev, uint64_t* keys_dev);
+/* Runner-up ("top-2") -- an extension: the reference has NO second-best output (its ratio test divides by the SEED distance,
+ * src/MatchFactory.cu:1691-1697), so nothing in the MatchFactory API maps to this entry and the top-1 path does not
+ * depend on it.  For hosts that want a Lowe-style ratio: a second search of the same pair in which every query's winner is left out.
+ * winner_keys_dev: uint64[size(query)] keys of a previous ssrlcv_b200_match_candidates(..., target_offset = 0, ...) of this pair
+ * (all-ones = no winner: nothing is excluded); keys_dev: uint64[size(query)], the best REMAINING target of every query under the
+ * same winner rule (min of (d2, f mod 32, f) over the mask), all-ones = none below the absolute threshold.  Enqueue-only. */
+int  ssrlcv_b200_match_runner_up(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* params, const ssrlcv_b200_set* query,
+                                 const ssrlcv_b200_set* target, const uint64_t* winner_keys_dev, uint64_t* keys_dev);
 /* Merge n_shards candidate arrays (keys_dev: [n_shards][size(query)], e.g. the output of an all-gather),
  * then thresholds / ratio test / writers / compaction exactly as ssrlcv_b200_match.
  * target_loc_dev: float2[n_target_total] locations of the whole target set (index = global f);

@@ -23,7 +23,7 @@ EXPORTS = [
     "ssrlcv_b200_match_pairs_multi_gpu", "ssrlcv_b200_multi_assignment", "ssrlcv_b200_set_profiling", "ssrlcv_b200_kernel_time",
     "ssrlcv_b200_pack", "ssrlcv_b200_pack_batch", "ssrlcv_b200_pack_host", "ssrlcv_b200_set_alloc", "ssrlcv_b200_set_arrays_of", "ssrlcv_b200_set_commit",
     "ssrlcv_b200_set_size", "ssrlcv_b200_set_free", "ssrlcv_b200_seed_distances", "ssrlcv_b200_match",
-    "ssrlcv_b200_match_host", "ssrlcv_b200_match_features", "ssrlcv_b200_match_batch", "ssrlcv_b200_match_candidates", "ssrlcv_b200_match_candidates_seeded", "ssrlcv_b200_finalize_candidates",
+    "ssrlcv_b200_match_host", "ssrlcv_b200_match_features", "ssrlcv_b200_match_batch", "ssrlcv_b200_match_candidates", "ssrlcv_b200_match_candidates_seeded", "ssrlcv_b200_match_runner_up", "ssrlcv_b200_finalize_candidates",
     "ssrlcv_b200_set_loc", "ssrlcv_b200_validate", "ssrlcv_b200_refine", "ssrlcv_b200_sort",
     "ssrlcv_b200_raw_matches", "ssrlcv_b200_match_set_2view", "ssrlcv_b200_epipolar_endpoints", "ssrlcv_b200_device_sincos", "ssrlcv_b200_set_download",
 ]
@@ -115,6 +115,7 @@ def load() -> C.CDLL:
     lib.ssrlcv_b200_match_features.argtypes = [vp, pp, vp, u64, vp, u64, vp, u64, vp, vp, pu64]
     lib.ssrlcv_b200_match_candidates.argtypes = [vp, pp, vp, vp, u64, vp]
     lib.ssrlcv_b200_match_candidates_seeded.argtypes = [vp, pp, vp, vp, u64, vp, vp]
+    lib.ssrlcv_b200_match_runner_up.argtypes = [vp, pp, vp, vp, vp, vp]
     lib.ssrlcv_b200_finalize_candidates.argtypes = [vp, pp, vp, vp, u32, vp, vp, vp, pu64]
     lib.ssrlcv_b200_validate.argtypes = [vp, i32, vp, u64, pu64]
     lib.ssrlcv_b200_refine.argtypes = [vp, vp, u64, f32, pu64]

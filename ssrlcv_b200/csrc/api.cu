@@ -658,6 +658,7 @@ struct PairWork {
   float abs_thr = 0.f;
   const float* seed = nullptr;    // seed distances of the query set (device) when the ratio test will drop what exceeds it
   float seed_ratio = 0.f;
+  const uint64_t* exclude = nullptr;   // runner-up search: winner keys of a previous search of the same pair (matcher.cuh q_exclude)
   bool optimistic_fold = false;   // out: the fold variant was launched before the target set's pack had reported back
   const ssrlcv_b200_set* tt = nullptr;   // out: the set the kernel reads its targets from (t, or t's spatially sorted copy)
   const ssrlcv_b200_set* qq = nullptr;   // out: the same for the queries
@@ -685,10 +686,11 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     // Large unmasked searches walk the score matrix two query tiles at a time (smax_pair.cu: every target tile is staged once
     // per 256 queries -- half the L2 -> SM traffic -- and each accumulator has its own epilogue warps); everything else, and
     // pairs too small to balance 256-row units over the SMs, one tile at a time (smax_tc.cu).
-    bool pair_units = p.engine != SSRLCV_B200_ENGINE_SIMT && p.mp.kind == SSRLCV_B200_MASK_NONE && a.nq_pad % (2 * kBM) == 0 &&
+    bool pair_units = p.engine != SSRLCV_B200_ENGINE_SIMT && p.mp.kind == SSRLCV_B200_MASK_NONE && a.nq_pad % (2 * kBM) == 0 && p.exclude == nullptr &&
                       static_cast<uint64_t>((a.nq + 2 * kBM - 1) / (2 * kBM)) * a.n_ttiles >= 8ull * static_cast<uint64_t>(ctx->sm_count);
     if (ctx->knob[SSRLCV_B200_TUNE_PAIR_UNITS] >= 0)
-      pair_units = ctx->knob[SSRLCV_B200_TUNE_PAIR_UNITS] != 0 && p.engine != SSRLCV_B200_ENGINE_SIMT && p.mp.kind == SSRLCV_B200_MASK_NONE && a.nq_pad % (2 * kBM) == 0;
+      pair_units = ctx->knob[SSRLCV_B200_TUNE_PAIR_UNITS] != 0 && p.engine != SSRLCV_B200_ENGINE_SIMT && p.mp.kind == SSRLCV_B200_MASK_NONE &&
+                   a.nq_pad % (2 * kBM) == 0 && p.exclude == nullptr;
     a.q_tile_rows = pair_units ? 2 * kBM : kBM;
     a.n_qtiles = (a.nq + a.q_tile_rows - 1) / a.q_tile_rows;
     const uint64_t tiles = static_cast<uint64_t>(a.n_qtiles) * a.n_ttiles;
@@ -698,8 +700,10 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     a.eps = p.mp.eps;
     a.d2_cap = d2_cap_of(p.abs_thr);
     a.q_seed = p.seed; a.seed_ratio = p.seed_ratio;
+    a.q_exclude = p.exclude;
     p.tt = p.t; p.qq = p.q;
-    if (p.engine != SSRLCV_B200_ENGINE_SIMT && tiles != 0 && p.mp.kind != SSRLCV_B200_MASK_NONE && p.seed == nullptr && !p.t->is_view && !p.q->is_view) {
+    if (p.engine != SSRLCV_B200_ENGINE_SIMT && tiles != 0 && p.mp.kind != SSRLCV_B200_MASK_NONE && p.seed == nullptr && p.exclude == nullptr &&
+        !p.t->is_view && !p.q->is_view) {
       // Masked search with nothing but the mask to prune it: both sets are matched in spatial (Z-curve) order, so that an
       // epipolar band misses most 32-target windows and most (query tile, target tile) pairs outright.  Worth its launches
       // (~4 per set, once per set) only for pairs whose matcher runs much longer than that.
@@ -850,6 +854,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       b.total_tiles = g.total;
       b.flags = d_nflag + at;
       b.clear = d_nflag_other; b.clear_n = bank_len;
+      for (uint32_t i : g.idx) if (w[i].exclude != nullptr) b.has_exclude = 1;
       b.diag = ctx->knob[SSRLCV_B200_TUNE_DIAG] > 0 ? static_cast<uint32_t>(ctx->knob[SSRLCV_B200_TUNE_DIAG]) : 0u;
       b.timing = ctx->knob[SSRLCV_B200_TUNE_TIMING_BUFFER] > 0 ? reinterpret_cast<unsigned long long*>(ctx->knob[SSRLCV_B200_TUNE_TIMING_BUFFER]) : nullptr;
       if (ctx->profiling) {
@@ -1141,6 +1146,26 @@ int ssrlcv_b200_match_candidates_seeded(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_
   rc = engine_enqueue(ctx, &w, 1, nullptr);
   if (rc) return rc;
   if (w.a.nq) {                                            // reduce the local key slots to one key per query
+    launch_min_keys(ctx->stream, w.a.keys, w.a.nq, w.a.nq_pad, w.a.n_splits, keys_dev);
+    ctx->launches += 1;
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int ssrlcv_b200_match_runner_up(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_match_params* p, const ssrlcv_b200_set* query,
+                                const ssrlcv_b200_set* target, const uint64_t* winner_keys_dev, uint64_t* keys_dev) {
+  if (!ctx || !query || !target || (query->n && (!keys_dev || !winner_keys_dev))) return fail(ctx, SSRLCV_B200_EINVAL, "match_runner_up: bad arguments");
+  int rc = check_params(ctx, p);
+  if (rc) return rc;
+  CU(cudaSetDevice(ctx->device));
+  PairWork w;
+  fill_mask(p, w.mp);
+  w.q = query; w.t = target; w.abs_thr = p->absolute_threshold;
+  w.exclude = winner_keys_dev;
+  rc = engine_enqueue(ctx, &w, 1, nullptr);
+  if (rc) return rc;
+  if (w.a.nq) {
     launch_min_keys(ctx->stream, w.a.keys, w.a.nq, w.a.nq_pad, w.a.n_splits, keys_dev);
     ctx->launches += 1;
   }

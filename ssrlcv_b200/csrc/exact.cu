@@ -55,7 +55,9 @@ __device__ __forceinline__ void exact_items(const SmaxArgs& a, int use_list, uin
     QueryMask qm;
     if (kMask != SSRLCV_B200_MASK_NONE) qm = load_query_mask<kMask>(a.q_mask + 2 * static_cast<uint64_t>(row));
     uint64_t best = kKeyNone;
+    const uint64_t excluded = a.q_exclude ? (a.q_exclude[row] & 0xFFFFFFFFull) : ~0ull;   // runner-up search: one target row this query must not match
     for (uint64_t f = f_begin + threadIdx.x; f < f_end; f += 256) {     // f % 32 == lane for every f of this thread
+      if (f == excluded) continue;
       if (kMask != SSRLCV_B200_MASK_NONE) {
         const float2 tl = a.t_loc[f];
         if (mask_skips<kMask>(qm, tl.x, tl.y, eps)) continue;

@@ -124,6 +124,11 @@ struct SmaxArgs {
   // (everest fixture: 84 % of the (query, window) pairs reach d2 < 200^2, 0.04 % reach 0.36 * seed[q]).
   const float* q_seed;           // [nq] seed distances (exact integers as float, FLT_MAX = none) or nullptr
   float    seed_ratio;           // rel or rel^2 as the output kind prescribes (api.cu ratio_threshold)
+  // Runner-up search (ssrlcv_b200_match_runner_up): the low 32 bits of q_exclude[q] -- a winner key of a previous search of the
+  // same pair, all-ones = none -- name the row of the target set that query q must not match.  It scores 0, as a masked target
+  // would, wherever it could matter: in the epilogue's rare path, in the resolvers and in the exact kernels.  nullptr in every
+  // reference-API call.
+  const uint64_t* q_exclude;
   uint64_t target_offset;        // global index of target 0 of this set (sharded mode)
   const uint8_t* q_desc; const int32_t* q_norm; const float2* q_loc;
   const float4* q_mask;          // [nq_pad][2] per-query epipolar mask state (geometry.cuh), masked modes only
@@ -163,6 +168,8 @@ struct SmaxBatch {
   uint32_t* clear;               // the tie counters of the OTHER bank: zeroed by CTA 0 for the call after this one
   uint32_t clear_n;
   uint32_t diag;                 // what-if timing bits (SSRLCV_B200_TUNE_DIAG); 0 in every product launch
+  uint32_t has_exclude;          // some job of the launch is a runner-up search (SmaxArgs::q_exclude): read from the parameter bank,
+                                 // so the rare path of every other launch pays nothing for the feature
   SmaxJob inline_job;
 };
 

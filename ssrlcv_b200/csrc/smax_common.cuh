@@ -62,6 +62,37 @@ __device__ __forceinline__ uint32_t eq_mask32(const uint32_t (&x)[32], int32_t m
   return mask;
 }
 
+// The rare path's view of two job fields it alone needs: volatile loads, so that the compiler cannot hoist them into registers
+// that would live across the matcher's hot loop (the job lives in device memory or in the kernel's parameter block).
+__device__ __forceinline__ const uint64_t* load_exclude_ptr(const SmaxArgs& job) {
+  unsigned long long p;
+  asm volatile("ld.u64 %0, [%1];" : "=l"(p) : "l"(&job.q_exclude) : "memory");
+  return reinterpret_cast<const uint64_t*>(p);
+}
+__device__ __forceinline__ uint32_t excluded_row(const uint64_t* q_exclude, uint32_t row) { return static_cast<uint32_t>(__ldg(q_exclude + row)); }
+__device__ __forceinline__ uint32_t load_nq(const SmaxArgs& job) {
+  uint32_t v;
+  asm volatile("ld.u32 %0, [%1];" : "=r"(v) : "l"(&job.nq) : "memory");
+  return v;
+}
+// Runner-up searches: the excluded target of this lane's query (row `ex` of the target set) scores 0 in the windows that could
+// matter.  A window holding a query's excluded WINNER always reaches that query's running best, so the rare path -- the only
+// caller -- sees every case; the common path is untouched.  x holds exact scores here (fold, or W already added).
+template <int kWin>
+__device__ __forceinline__ void exclude_columns(uint32_t (&v)[kWin][32], int32_t (&wm)[kWin], int32_t best, uint32_t win0, uint32_t ex) {
+#pragma unroll
+  for (int k = 0; k < kWin; ++k) {
+    const bool hit = ((ex >> 5) == win0 + k) && (wm[k] >= best);
+    if (!__any_sync(0xffffffffu, hit)) continue;
+    uint32_t(&x)[32] = v[k];
+    const uint32_t col = ex & 31u;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = (hit && col == static_cast<uint32_t>(e)) ? 0u : x[e];
+    const int32_t m = max32(x);
+    wm[k] = hit ? m : wm[k];
+  }
+}
+
 // kWin 32-target windows of one query row, in registers (unmasked searches), in two steps: the window maxima (the common path:
 // max trees and nothing else) and -- only when some lane's maximum reaches its running best -- the bookkeeping.
 // Fold: the maxima ARE the windows' best scores.  No-fold: the accumulator holds a.b only; max(a.b) + wb[k] (the largest W of
@@ -84,7 +115,8 @@ __device__ __forceinline__ int32_t window_maxima(const uint32_t (&v)[kWin][32], 
 // added (s_w: shared-window address of the first window's 32 W values) and an exact maximum; the others stay bounds below every
 // lane's best.  win0: global index of the first window.
 template <int kWin, bool kFold, bool kColMask>
-__device__ __forceinline__ void window_bookkeeping(uint32_t (&v)[kWin][32], int32_t (&wm)[kWin], WinState& st, uint32_t win0, uint32_t s_w) {
+__device__ __forceinline__ void window_bookkeeping(uint32_t (&v)[kWin][32], int32_t (&wm)[kWin], WinState& st, uint32_t win0, uint32_t s_w,
+                                                   bool has_exclude, const SmaxArgs& job, uint32_t row) {
   if (!kFold) {
 #pragma unroll
     for (int k = 0; k < kWin; ++k) {
@@ -99,6 +131,10 @@ __device__ __forceinline__ void window_bookkeeping(uint32_t (&v)[kWin][32], int3
       }
       wm[k] = max32(x);
     }
+  }
+  if (has_exclude) {                                         // runner-up search (launch-uniform)
+    const uint64_t* q_exclude = load_exclude_ptr(job);
+    if (q_exclude != nullptr) exclude_columns<kWin>(v, wm, st.best, win0, row < load_nq(job) ? excluded_row(q_exclude, row) : 0xFFFFFFFFu);
   }
   if (kColMask) {
 #pragma unroll
@@ -201,9 +237,9 @@ __device__ __forceinline__ void resolve_rows_windows(const SmaxArgs& job, const 
     uint32_t nq, nt, nq_pad; float eps; uint64_t target_offset;
     const uint8_t* q_desc; const int32_t* q_norm; const float4* q_mask;
     const uint8_t* t_desc; const int32_t* t_norm; const float2* t_loc; const uint32_t* t_orig; const uint32_t* q_orig;
-    uint64_t* keys; uint32_t* flagged; uint32_t* n_flagged;
+    uint64_t* keys; uint32_t* flagged; uint32_t* n_flagged; const uint64_t* q_exclude;
   } args = {job.nq, job.nt, job.nq_pad, job.eps, job.target_offset, job.q_desc, job.q_norm, job.q_mask,
-            job.t_desc, job.t_norm, job.t_loc, job.t_orig, job.q_orig, job.keys, job.flagged, job.n_flagged};
+            job.t_desc, job.t_norm, job.t_loc, job.t_orig, job.q_orig, job.keys, job.flagged, job.n_flagged, job.q_exclude};
   for (uint32_t g = 0; g < r_count; g += kFly) {
     WinState ms[kFly];
     uint32_t qrow[kFly];
@@ -229,6 +265,7 @@ __device__ __forceinline__ void resolve_rows_windows(const SmaxArgs& job, const 
         const uint32_t w = ms[k].w1 == kNoWin ? 0u : ms[k].w1;
         const uint64_t f = static_cast<uint64_t>(w) * kChunk + lane;
         ok[k] = (f < args.nt) & (ms[k].w1 != kNoWin);
+        if (args.q_exclude != nullptr && qrow[k] < args.nq && f == excluded_row(args.q_exclude, qrow[k])) ok[k] = false;   // runner-up search
         fs[k] = ok[k] ? f : 0;
         const uint4* td = reinterpret_cast<const uint4*>(args.t_desc + fs[k] * kDescBytes);
 #pragma unroll
@@ -256,6 +293,7 @@ __device__ __forceinline__ void resolve_rows_windows(const SmaxArgs& job, const 
         if (ms[k].w1 != kNoWin && ms[k].w2 != kNoWin) {          // warp-uniform
           const uint64_t f = static_cast<uint64_t>(ms[k].w2) * kChunk + lane;
           bool ok2 = f < args.nt;
+          if (args.q_exclude != nullptr && qrow[k] < args.nq && f == excluded_row(args.q_exclude, qrow[k])) ok2 = false;
           const uint64_t f2 = ok2 ? f : 0;
           if (kMask != SSRLCV_B200_MASK_NONE) {
             const QueryMask qm = load_query_mask<kMask>(args.q_mask + 2 * static_cast<uint64_t>(qrow[k]));

@@ -311,7 +311,7 @@ smax_pair_kernel(const __grid_constant__ SmaxBatch batch) {
           const int32_t mt = window_maxima<4, kFold>(v, wb, wm, batch.diag);
           if (__any_sync(0xffffffffu, mt >= best[p])) {            // thresholded search: next to never
             WinState st = mine[p * kBM];
-            window_bookkeeping<4, kFold, kColMask>(v, wm, st, j * 8 + half * 4, s_w);
+            window_bookkeeping<4, kFold, kColMask>(v, wm, st, j * 8 + half * 4, s_w, /* runner-up searches take smax_tc.cu */ false, args, 0u);
             mine[p * kBM] = st;
             best[p] = st.best;
           }

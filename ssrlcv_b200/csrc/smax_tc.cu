@@ -427,6 +427,12 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
               }
             }
           }
+          if (batch.has_exclude) {                                 // runner-up search (launch-uniform): the excluded target scores 0
+            const uint64_t* q_exclude = load_exclude_ptr(args);
+            if (q_exclude != nullptr)
+              exclude_columns<static_cast<int>(kWinPerWarp)>(v, wm, st.best, j * kWinPerTile + c_begin,
+                                                             row < load_nq(args) ? excluded_row(q_exclude, row) : 0xFFFFFFFFu);
+          }
           // bookkeeping (branch-free body)
           if (kColMask) {
 #pragma unroll

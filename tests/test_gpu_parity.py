@@ -1328,3 +1328,58 @@ def test_sorted_masked_search_with_ties_everywhere(api, everest, knobs, thr):
         assert T.fields_equal(got, want_f), cm
         got = mf.generateDistanceMatchesDoubleConstrained(qi, _unity(api, q), ti, _unity(api, t), 80.0, 5.0).to_numpy()
         assert T.fields_equal(got, want), cm
+
+
+@pytest.mark.parametrize("thr", [FLT_MAX, 2.5e5])
+def test_runner_up_search_is_the_second_smallest_key(api, everest, knobs, thr):
+    """ssrlcv_b200_match_runner_up (an extension; the reference has no second-best output): a second search of the pair with every
+    query's winner left out returns the second-smallest key (d2, f mod 32, f) of the brute-force distance matrix -- duplicates,
+    ragged last window and all -- under every matcher variant; the winner keys themselves are what the plain search returns, so the
+    top-1 path is untouched.  Masked searches: the tensor-core path equals the independent SIMT engine."""
+    import torch
+    from ssrlcv_b200.match_factory import pack
+    q, t = synth.make_pair(1500, 5000 + 13, seed=31, dup=0.02)
+    qv, tv = q["values"].astype(np.int64), t["values"].astype(np.int64)
+    d2 = (qv * qv).sum(1)[:, None] + (tv * tv).sum(1)[None, :] - 2 * qv @ tv.T
+    f = np.arange(len(t), dtype=np.int64)[None, :]
+    key = (d2 << 37) | ((f & 31) << 32) | f
+    key = np.where(d2.astype(np.float32) < np.float32(thr), key, -1).astype(np.uint64)       # all-ones: not below the absolute threshold
+    two = np.sort(key, axis=1)[:, :2]
+    mf = api.MatchFactory(1.0, thr)
+    ctx = mf.ctx
+    qu, tu = _unity(api, q), _unity(api, t)
+    qu.setMemoryState(api.gpu); tu.setMemoryState(api.gpu)
+    p = mf._params(T.OUT_DMATCH, T.MASK_NONE, api.Image(0), api.Image(1))
+    k1 = torch.empty(len(q), dtype=torch.int64, device="cuda")
+    k2 = torch.empty(len(q), dtype=torch.int64, device="cuda")
+
+    def top2(pp):
+        ctx.check(ctx.lib.ssrlcv_b200_match_candidates(ctx.handle, C.byref(pp), pack(ctx, qu).handle, pack(ctx, tu).handle, 0, C.c_void_p(k1.data_ptr())))
+        ctx.check(ctx.lib.ssrlcv_b200_match_runner_up(ctx.handle, C.byref(pp), pack(ctx, qu).handle, pack(ctx, tu).handle,
+                                                      C.c_void_p(k1.data_ptr()), C.c_void_p(k2.data_ptr())))
+        ctx.check(ctx.lib.ssrlcv_b200_synchronize(ctx.handle))
+        return k1.cpu().numpy().view(np.uint64).copy(), k2.cpu().numpy().view(np.uint64).copy()
+
+    for fold, cm, pair in [(None, None, None), ("0", None, None), (None, "0", None), (None, "1", "1"), ("0", "0", "1"), (None, None, "0")]:
+        knobs(fold=fold, colmask=cm, pair=pair)
+        a, b = top2(p)
+        assert np.array_equal(a, two[:, 0]), (fold, cm, pair)
+        assert np.array_equal(b, two[:, 1]), (fold, cm, pair)
+    knobs(fold=None, colmask=None, pair=None)
+    # masked: tensor-core path == SIMT cross-check engine (two independent implementations of the exclusion)
+    qi, ti = api.Image(0, everest.cameras[0]), api.Image(1, everest.cameras[1])
+    F = np.array([[1e-6, 2e-6, 0.0015], [-3e-6, 1e-7, -1.0], [-0.0013, 1.0, 4.0]], np.float32)
+    for pm in (mf._params(T.OUT_DMATCH, T.MASK_DOUBLE, qi, ti, 60.0, 5.0), mf._params(T.OUT_DMATCH, T.MASK_FUNDAMENTAL, qi, ti, 40.0, 0.0, F)):
+        a, b = top2(pm)
+        ctx.tune(_lib_mod().TUNE_CROSSCHECK_SIMT, 1)
+        try:
+            a2, b2 = top2(pm)
+        finally:
+            ctx.tune(_lib_mod().TUNE_CROSSCHECK_SIMT, -1)
+        assert np.array_equal(a, a2) and np.array_equal(b, b2)
+        assert (b >= a).all() and (b[a != np.uint64(0xFFFFFFFFFFFFFFFF)] != a[a != np.uint64(0xFFFFFFFFFFFFFFFF)]).all()
+
+
+def _lib_mod():
+    from ssrlcv_b200 import _lib
+    return _lib
