@@ -248,7 +248,7 @@ smax_pair_kernel(const __grid_constant__ SmaxBatch batch) {
     const uint32_t my_r = quarter * 32 + lane;         // this thread's row of either query tile
     WinState* xch = reinterpret_cast<WinState*>(smem + Smem::xch);
     uint32_t it = 0, uiter = 0;                       // it: target tiles consumed so far -> phases of the accumulators and the column ring
-    long long te_wait = 0, te_work = 0, te_resolve = 0, te_total0 = 0, te_cwait = 0;
+    long long te_wait = 0, te_work = 0, te_resolve = 0, te_total0 = 0, te_cwait = 0, te_rare = 0, te_rare_n = 0;
     if (kTiming) te_total0 = clock64();
     UnitIter u(batch, blockIdx.x);
     while (u.next(batch, blockIdx.x, kFold)) {
@@ -310,10 +310,13 @@ smax_pair_kernel(const __grid_constant__ SmaxBatch batch) {
           int32_t wm[4];
           const int32_t mt = window_maxima<4, kFold>(v, wb, wm, batch.diag);
           if (__any_sync(0xffffffffu, mt >= best[p])) {            // thresholded search: next to never
+            long long r0 = 0;
+            if (kTiming) r0 = clock64();
             WinState st = mine[p * kBM];
             window_bookkeeping<4, kFold, kColMask>(v, wm, st, j * 8 + half * 4, s_w, /* runner-up searches take smax_tc.cu */ false, args, 0u);
             mine[p * kBM] = st;
             best[p] = st.best;
+            if (kTiming) { te_rare += clock64() - r0; ++te_rare_n; }
           }
           if (kTiming) { const long long e2 = clock64(); te_wait += e1 - e0; te_work += e2 - e1; }
         }
@@ -346,7 +349,7 @@ smax_pair_kernel(const __grid_constant__ SmaxBatch batch) {
       if (e == 0 || e == 5) {
         const uint32_t o = blockIdx.x * 16 + (e == 0 ? 4 : 8);
         batch.timing[o + 0] = te_wait; batch.timing[o + 1] = te_work; batch.timing[o + 2] = te_resolve; batch.timing[o + 3] = clock64() - te_total0;
-        if (e == 0) { batch.timing[blockIdx.x * 16 + 14] = 0; batch.timing[blockIdx.x * 16 + 15] = te_cwait; }
+        if (e == 0) { batch.timing[blockIdx.x * 16 + 14] = te_rare_n; batch.timing[blockIdx.x * 16 + 15] = kFold ? te_rare : te_cwait; }   // fold: cycles inside the rare path
       }
     }
   }

@@ -38,6 +38,8 @@ lib.ssrlcv_b200_pack(h, C.c_void_p(td.data_ptr()), len(t), C.byref(ht))
 lib.ssrlcv_b200_set_profiling(h, 1)
 k_ms, k_n = C.c_double(0), C.c_uint64(0)
 pairs = [int(x) for x in os.environ.get("DIAG_PAIR", "0,1").split(",")]
+if os.environ.get("DIAG_COLMASK"):
+    lib.ssrlcv_b200_tune(h, _lib.TUNE_COLUMN_MASKS, int(os.environ["DIAG_COLMASK"]))
 for fold, pair in [(f, pr) for f in (1, 0) for pr in pairs]:
     lib.ssrlcv_b200_tune(h, _lib.TUNE_FOLD, fold)
     lib.ssrlcv_b200_tune(h, _lib.TUNE_PAIR_UNITS, pair)
@@ -61,4 +63,4 @@ for fold, pair in [(f, pr) for f in (1, 0) for pr in pairs]:
         x = tim.cpu().numpy().reshape(148, 16)
         ims = k_ms.value / k_n.value
         print(f"fold={fold} pair={pair} diag={d}: kernel {1e3 * ms:8.2f} us  matches {n_out.value:6d} | instrumented {1e3 * ims:8.2f} us, mma cycles {x[:, 2].mean():9.0f} "
-              f"-> {x[:, 2].mean() / (1e3 * ims):6.1f} MHz, mma wait_t_empty {x[:, 0].mean():8.0f} wait_full {x[:, 1].mean():7.0f}, epi0 wait {x[:, 4].mean():8.0f} work {x[:, 5].mean():8.0f} cwait {x[:, 15].mean():7.0f}", flush=True)
+              f"-> {x[:, 2].mean() / (1e3 * ims):6.1f} MHz, mma wait_t_empty {x[:, 0].mean():8.0f} wait_full {x[:, 1].mean():7.0f}, epi0 wait {x[:, 4].mean():8.0f} work {x[:, 5].mean():8.0f} cwait|rare {x[:, 15].mean():7.0f} events {x[:, 14].mean():5.1f}", flush=True)
