@@ -64,8 +64,8 @@ for sorted_ in ((1, 0) if mask else (1,)):
     lib.ssrlcv_b200_kernel_time(h, C.byref(k_ms), C.byref(k_n))
     x = tim.cpu().numpy().reshape(148, 16)
     names = ["mma:wait_t_empty", "mma:wait_full", "mma:total", "tma:wait_empty", "epi0:wait_t_full", "epi0:work", "epi0:resolve", "epi0:total",
-             "epi5:wait_t_full", "epi5:work", "epi5:resolve", "epi5:total", "res0:wait", "res0:work", "epi0:live_windows", "epi0:wait_c_full"]
+             "epi5:wait_t_full", "epi5:work", "epi5:resolve", "epi5:total", "res0:wait", "res0:work", "epi0:live_windows (pair walk: rare-path entries)", "epi0:wait_c_full (pair walk, fold: cycles in the rare path)"]
     print(f"  instrumented kernel {1e3 * k_ms.value / k_n.value:.1f} us")
     for i, n in enumerate(names):
         col = x[:, i]
-        print(f"  {n:18s} mean {col.mean():12.0f}  min {col.min():12d}  max {col.max():12d}")
+        print(f"  {n:62s} mean {col.mean():12.0f}  min {col.min():12d}  max {col.max():12d}")
