@@ -62,6 +62,20 @@ static_assert(kColStages * (kColWBytes + kColWmaxBytes) <= kStages * kBExtBytes,
 constexpr uint32_t kSmemBytes = Smem::total + 1024;
 static_assert(kSmemBytes <= 232448, "227 KB of shared memory per CTA");
 
+// a row's window state in shared memory, by shared-window address (24 bytes, 8-byte aligned)
+__device__ __forceinline__ void ld_state(uint32_t addr, WinState& s) {
+  uint32_t a, b, c, d, e, f;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr) : "memory");
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(c), "=r"(d) : "r"(addr + 8) : "memory");
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e), "=r"(f) : "r"(addr + 16) : "memory");
+  s.best = static_cast<int32_t>(a); s.w1 = b; s.m1 = c; s.w2 = d; s.m2 = e; s.ovf = f;
+}
+__device__ __forceinline__ void st_state(uint32_t addr, const WinState& s) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(static_cast<uint32_t>(s.best)), "r"(s.w1) : "memory");
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + 8), "r"(s.m1), "r"(s.w2) : "memory");
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + 16), "r"(s.m2), "r"(s.ovf) : "memory");
+}
+
 template <bool kFold, bool kColMask, bool kTiming>
 __global__ void __launch_bounds__(kThreads, 1)
 smax_pair_kernel(const __grid_constant__ SmaxBatch batch) {
@@ -259,6 +273,7 @@ smax_pair_kernel(const __grid_constant__ SmaxBatch batch) {
       // resolvers of the unit before the previous one
       mbar_wait(&x_empty[uparity], ((uiter >> 1) & 1) ^ 1);
       WinState* mine = xch + (uparity * 2 + half) * kPairRows + my_r;   // row of query tile p: mine[p * kBM]
+      const uint32_t mine_addr = smem_u32(mine);
       int32_t best[2];
 #pragma unroll
       for (uint32_t p = 0; p < 2; ++p) {
@@ -310,11 +325,29 @@ smax_pair_kernel(const __grid_constant__ SmaxBatch batch) {
           int32_t wm[4];
           const int32_t mt = window_maxima<4, kFold>(v, wb, wm, batch.diag);
           if (__any_sync(0xffffffffu, mt >= best[p])) {            // thresholded search: next to never
+            // The warp that gets here reaches its next accumulator late, and every tile needs all eight warps: these ~180 entries
+            // per CTA cost the 65 536 x 65 536 launch 8 % (profiles/r2_kernel_experiments.txt), so the path is kept short.
             long long r0 = 0;
             if (kTiming) r0 = clock64();
-            WinState st = mine[p * kBM];
-            window_bookkeeping<4, kFold, kColMask>(v, wm, st, j * 8 + half * 4, s_w, /* runner-up searches take smax_tc.cu */ false, args, 0u);
-            mine[p * kBM] = st;
+            const uint32_t st_addr = mine_addr + p * (kBM * 24);
+            WinState st;
+            if (kFold && kColMask) {
+              // which windows matter is decided on the register copy of the running best (== st.best), in ONE warp reduction, so
+              // the state's load overlaps the equality masks; a window that stops mattering once an earlier one has raised the
+              // best is a no-op in win_update
+              uint32_t live = 0;
+#pragma unroll
+              for (uint32_t k = 0; k < 4; ++k) live |= (wm[k] >= best[p]) ? (1u << k) : 0u;
+              live = __reduce_or_sync(0xffffffffu, live);
+              ld_state(st_addr, st);
+#pragma unroll
+              for (uint32_t k = 0; k < 4; ++k)
+                if ((live >> k) & 1u) win_update(st, wm[k], j * 8 + half * 4 + k, eq_mask32(v[k], wm[k]));
+            } else {
+              ld_state(st_addr, st);
+              window_bookkeeping<4, kFold, kColMask>(v, wm, st, j * 8 + half * 4, s_w, /* runner-up searches take smax_tc.cu */ false, args, 0u);
+            }
+            st_state(st_addr, st);
             best[p] = st.best;
             if (kTiming) { te_rare += clock64() - r0; ++te_rare_n; }
           }
