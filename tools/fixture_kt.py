@@ -43,9 +43,7 @@ ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=
 cm_env = os.environ.get("KT_COLMASK")
 if cm_env:
     lib.ssrlcv_b200_tune(h, _lib.TUNE_COLUMN_MASKS, int(cm_env))
-if os.environ.get("KT_INTERLEAVE"):
-    lib.ssrlcv_b200_tune(h, _lib.TUNE_INTERLEAVE, int(os.environ["KT_INTERLEAVE"]))
-print("colmask", cm_env or "auto", "interleave", os.environ.get("KT_INTERLEAVE", "auto"))
+print("colmask", cm_env or "auto")
 for sorted_ in ((1, 0) if mask else (1,)):
     lib.ssrlcv_b200_tune(h, _lib.TUNE_SORTED_TARGETS, sorted_)
     lib.ssrlcv_b200_tune(h, _lib.TUNE_TIMING_BUFFER, 0)
