@@ -161,8 +161,9 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
         mbar_wait(&a_empty[aslot], aphase ^ 1);
         mbar_arrive_expect_tx(&a_full[aslot], kABytes);
         tma_load_2d(smem + SmemLayout::a + aslot * kABytes, map_q, &a_full[aslot], 0, static_cast<int32_t>(u.qt * kBM));
-        for (uint32_t j = u.j0; j < u.j1; ++j) {
-          if (kMask != SSRLCV_B200_MASK_NONE && !tile_live(live_bits, live_stride, u.qt, j)) continue;   // dead pair: every role skips it
+        LiveTiles tiles(live_bits, live_stride, u.qt, u.j0, u.j1);     // dead pairs: every role skips them
+        uint32_t j;
+        while (tiles.next(j)) {
           long long p0 = 0;
           if (kTiming) p0 = clock64();
           mbar_wait(&empty[stage], phase ^ 1);
@@ -209,8 +210,9 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
         const uint64_t a_desc = make_smem_desc(smem_u32(smem + SmemLayout::a + aslot * kABytes), 1024, kSwizzle128B);
         const uint32_t* live_bits = kMask != SSRLCV_B200_MASK_NONE ? u.J->a.live_bits : nullptr;
         const uint32_t live_stride = u.J->a.live_stride;
-        for (uint32_t j = u.j0; j < u.j1; ++j) {
-          if (kMask != SSRLCV_B200_MASK_NONE && !tile_live(live_bits, live_stride, u.qt, j)) continue;
+        LiveTiles tiles(live_bits, live_stride, u.qt, u.j0, u.j1);
+        uint32_t j;
+        while (tiles.next(j)) {
           long long c0 = 0, c1 = 0, c2 = 0;
           if (kTiming) c0 = clock64();
           mbar_wait(&t_empty[acc], accphase ^ 1);
@@ -316,8 +318,9 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
         }
         st.best = floor_s - 1; st.w1 = kNoWin; st.w2 = kNoWin; st.m1 = 0; st.m2 = 0; st.ovf = 0;
       }
-      for (uint32_t j = u.j0; j < u.j1; ++j) {
-        if (kMask != SSRLCV_B200_MASK_NONE && !tile_live(live_bits, live_stride, u.qt, j)) continue;
+      LiveTiles tiles(live_bits, live_stride, u.qt, u.j0, u.j1);
+      uint32_t j;
+      while (tiles.next(j)) {
         long long e0 = 0, e1 = 0;
         if (kTiming) e0 = clock64();
         const uint32_t acc = it & 1, accphase = (it >> 1) & 1, cs = it % kColStages, cphase = (it / kColStages) & 1;
