@@ -66,11 +66,6 @@ for sorted_ in ((1, 0) if mask else (1,)):
     names = ["mma:wait_t_empty", "mma:wait_full", "mma:total", "tma:wait_empty", "epi0:wait_t_full", "epi0:work", "epi0:resolve", "epi0:total",
              "epi5:wait_t_full", "epi5:work", "epi5:resolve", "epi5:total", "res0:wait", "res0:work", "epi0:live_windows (pair walk: rare-path entries)", "epi0:wait_c_full (pair walk, fold: cycles in the rare path)"]
     print(f"  instrumented kernel {1e3 * k_ms.value / k_n.value:.1f} us")
-    if os.environ.get("KT_PERCTA"):
-        order = np.argsort(x[:, 2])
-        for c in list(order[:6]) + list(order[-10:]):
-            print(f"    cta {c:3d}: mma total {x[c, 2]:8d}  live tiles {x[c, 1]:5d}  cycles/tile {x[c, 2] / max(x[c, 1], 1):8.0f}  epi0 work {x[c, 5]:8d} wait {x[c, 4]:8d} live_windows {x[c, 14]:5d}  epi5 work {x[c, 9]:8d}")
-        print("    corr(total, live tiles) =", np.corrcoef(x[:, 2], x[:, 1])[0, 1], " corr(total, epi0 live windows) =", np.corrcoef(x[:, 2], x[:, 14])[0, 1])
     for i, n in enumerate(names):
         col = x[:, i]
         print(f"  {n:62s} mean {col.mean():12.0f}  min {col.min():12d}  max {col.max():12d}")
