@@ -70,7 +70,8 @@ enum {
   SSRLCV_B200_TUNE_CROSSCHECK_SIMT = 5,       /* 1: evaluate distances with the SIMT cross-check kernel instead of tcgen05     */
   SSRLCV_B200_TUNE_TIMING_BUFFER = 6,         /* device address of u64[148][16] cycle counters: runs the instrumented build of the
                                                  matcher kernel (tools/kerneltiming.py); 0 / -1 = off                           */
-  SSRLCV_B200_TUNE_DIAG = 7,                  /* what-if timing of the matcher (tools/diag_ab.py), RESULTS ARE WRONG when non-zero:
+  SSRLCV_B200_TUNE_DIAG = 7,                  /* diagnostics builds of the library only (SSRLCV_B200_DIAG_BUILD; the product build rejects it):
+                                                 what-if timing of the matcher (tools/diag_ab.py), RESULTS ARE WRONG when non-zero:
                                                  bit 0 = load only every other target tile, bit 1 = skip the fold MMA,
                                                  bit 2 = skip the epilogue's max trees, bit 5 = no W ring (no-fold, smax_pair.cu);
                                                  0 / -1 = off                                                                    */

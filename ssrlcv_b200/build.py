@@ -17,7 +17,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O2,-fno-fast-math,-ffp-contract=off",
     "--fmad=true",          # explicit __f*_rn intrinsics pin every rounding that matters; never --use_fast_math
     "-Xptxas", "-v",
-]
+] + (["-DSSRLCV_B200_DIAG_BUILD"] if os.environ.get("SSRLCV_B200_DIAG_BUILD") else [])   # what-if timing hooks (tools/diag_ab.py): never in the product build
 
 
 def nvcc() -> str:

@@ -249,6 +249,8 @@ int ssrlcv_b200_synchronize(ssrlcv_b200_ctx* ctx) {
 }
 int ssrlcv_b200_tune(ssrlcv_b200_ctx* ctx, int knob, int64_t value) {
   if (!ctx || knob < 0 || knob >= SSRLCV_B200_TUNE_COUNT_) return fail(ctx, SSRLCV_B200_EINVAL, "tune: unknown knob");
+  if (knob == SSRLCV_B200_TUNE_DIAG && value > 0 && !kDiagBuild)
+    return fail(ctx, SSRLCV_B200_EINVAL, "tune: SSRLCV_B200_TUNE_DIAG needs a diagnostics build of the library (SSRLCV_B200_DIAG_BUILD=1 python -m ssrlcv_b200.build)");
   ctx->knob[knob] = value;
   return 0;
 }

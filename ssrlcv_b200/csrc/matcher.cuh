@@ -45,6 +45,15 @@ static_assert(sizeof(RefKeyPoint) == 16 && sizeof(RefMatch) == 40 && sizeof(RefD
 static_assert(sizeof(RefFeatureMatch) == 320 && offsetof(RefFeatureMatch, desc) == 44, "FeatureMatch layout");
 static_assert(sizeof(RefPair) == 16, "uint2_pair layout");
 
+// What-if timing hooks of the matcher (SSRLCV_B200_TUNE_DIAG, tools/diag_ab.py) exist only in a diagnostics build of the library
+// (SSRLCV_B200_DIAG_BUILD=1 python -m ssrlcv_b200.build): even one extra test in the epilogue's hot loop costs the 65 536 x 65 536
+// launch 2-3 %, so the product build compiles them out.
+#ifdef SSRLCV_B200_DIAG_BUILD
+constexpr bool kDiagBuild = true;
+#else
+constexpr bool kDiagBuild = false;
+#endif
+
 // ----- tiling -----
 constexpr int kBM = 128;          // query rows per CTA tile  (UMMA M, cta_group::1)
 constexpr int kBN = 256;          // target rows per pipeline stage (UMMA N)

@@ -99,7 +99,7 @@ __device__ __forceinline__ void exclude_columns(uint32_t (&v)[kWin][32], int32_t
 // window k, pack.cu wmax) bounds every score of the window.
 template <int kWin, bool kFold>
 __device__ __forceinline__ int32_t window_maxima(const uint32_t (&v)[kWin][32], const int32_t (&wb)[kWin], int32_t (&wm)[kWin], uint32_t diag) {
-  if (diag & 4u) {
+  if (kDiagBuild && (diag & 4u)) {
 #pragma unroll
     for (int k = 0; k < kWin; ++k) wm[k] = static_cast<int32_t>((v[k][0] | v[k][31]) >> 24);
   } else {

@@ -159,7 +159,7 @@ smax_pair_kernel(const __grid_constant__ SmaxBatch batch) {
           tma_load_2d(smem + Smem::b + stage * kBBytes, map_t, &full[stage], 0, static_cast<int32_t>(j * kBN));
           if (kFold) tma_load_2d(smem + Smem::bext + stage * kBExtBytes, map_text, &full[stage], 0, static_cast<int32_t>(j * kBN));
           if (++stage == kStages) { stage = 0; phase ^= 1; }
-          if (!kFold && !(batch.diag & 32u)) {   // W of the tile's 256 targets and the largest W of each of its 8 windows (pack.cu wcol / wmax)
+          if (!kFold && !(kDiagBuild && (batch.diag & 32u))) {   // W of the tile's 256 targets and the largest W of each of its 8 windows (pack.cu wcol / wmax)
             mbar_wait(&c_empty[cs], cphase ^ 1);
             mbar_arrive_expect_tx(&c_full[cs], kColWBytes + kColWmaxBytes);
             bulk_load_1d(smem + Smem::col_w + cs * kColWBytes, t_wcol + static_cast<uint64_t>(j) * kBN, kColWBytes, &c_full[cs]);
@@ -203,7 +203,7 @@ smax_pair_kernel(const __grid_constant__ SmaxBatch batch) {
 #pragma unroll
             for (uint32_t k = 0; k < 4; ++k)   // +32 bytes along K inside the 128-byte swizzle atom = +2 in the address field
               mma_i8_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, k);
-            if (kFold && !(batch.diag & 2u)) mma_i8_ss(d_tmem, aext_desc, bext_desc, idesc, 1);
+            if (kFold && !(kDiagBuild && (batch.diag & 2u))) mma_i8_ss(d_tmem, aext_desc, bext_desc, idesc, 1);
             mma_commit(&t_full[p]);
           }
           mma_commit(&empty[stage]);
@@ -299,7 +299,7 @@ smax_pair_kernel(const __grid_constant__ SmaxBatch batch) {
         const uint32_t accphase = it & 1, cs = it % kColStages, cphase = (it / kColStages) & 1;
         ++it;
         int32_t wb[4] = {0, 0, 0, 0};
-        if (!kFold && !(batch.diag & 32u)) {
+        if (!kFold && !(kDiagBuild && (batch.diag & 32u))) {
           long long c0 = 0;
           if (kTiming) c0 = clock64();
           mbar_wait(&c_full[cs], cphase);
@@ -353,7 +353,7 @@ smax_pair_kernel(const __grid_constant__ SmaxBatch batch) {
           }
           if (kTiming) { const long long e2 = clock64(); te_wait += e1 - e0; te_work += e2 - e1; }
         }
-        if (!kFold && !(batch.diag & 32u)) {
+        if (!kFold && !(kDiagBuild && (batch.diag & 32u))) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&c_empty[cs]);
         }

@@ -168,7 +168,7 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
           if (kTiming) p0 = clock64();
           mbar_wait(&empty[stage], phase ^ 1);
           if (kTiming) tp_wait += clock64() - p0;
-          if ((batch.diag & 1u) && (j & 1u)) {
+          if ((kDiagBuild && (batch.diag & 1u)) && (j & 1u)) {
             mbar_arrive(&full[stage]);
           } else {
           mbar_arrive_expect_tx(&full[stage], kBBytes + (kFold ? kBExtBytes : 0));
@@ -225,7 +225,7 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
 #pragma unroll
           for (uint32_t k = 0; k < 4; ++k)   // +32 bytes along K inside the 128-byte swizzle atom = +2 in the address field
             mma_i8_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, k);
-          if (kFold && !(batch.diag & 2u)) {
+          if (kFold && !(kDiagBuild && (batch.diag & 2u))) {
             const uint64_t bext_desc = make_smem_desc(smem_u32(smem + SmemLayout::bext + stage * kBExtBytes), 256, kSwizzle32B);
             mma_i8_ss(d_tmem, aext_desc, bext_desc, idesc, 1);
           }
@@ -356,7 +356,7 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
         //   no-fold: the accumulator holds a.b only; max(a.b) + (largest W of the window) bounds every score of the window
         //   masked : the unmasked maximum bounds the masked one
         int32_t wm[kWinPerWarp];
-        if (batch.diag & 4u) {
+        if (kDiagBuild && (batch.diag & 4u)) {
 #pragma unroll
           for (uint32_t k = 0; k < kWinPerWarp; ++k) wm[k] = static_cast<int32_t>((v[k][0] | v[k][31]) >> 24);
         } else {

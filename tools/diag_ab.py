@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """What-if timing of the matcher kernel at C3 (ssrlcv_b200_tune(SSRLCV_B200_TUNE_DIAG)): how fast would the launch be with
 half the L2->SM target-tile traffic / without the fold MMA / without the epilogue's max trees?  Results are wrong for every
-non-zero setting by construction; only the kernel time and the in-kernel clock are read."""
+non-zero setting by construction; only the kernel time and the in-kernel clock are read.  Needs a diagnostics build of the library
+(SSRLCV_B200_DIAG_BUILD=1 python -m ssrlcv_b200.build --force): the product build compiles the hooks out."""
 import ctypes as C
 import os
 import sys
@@ -44,7 +45,11 @@ for fold, pair in [(f, pr) for f in (1, 0) for pr in pairs]:
     lib.ssrlcv_b200_tune(h, _lib.TUNE_FOLD, fold)
     lib.ssrlcv_b200_tune(h, _lib.TUNE_PAIR_UNITS, pair)
     for d in settings:
-        lib.ssrlcv_b200_tune(h, _lib.TUNE_DIAG, d)
+        if d and lib.ssrlcv_b200_tune(h, _lib.TUNE_DIAG, d):
+            print(f"diag={d}: skipped (product build of the library)")
+            continue
+        if not d:
+            lib.ssrlcv_b200_tune(h, _lib.TUNE_DIAG, 0)
         lib.ssrlcv_b200_tune(h, _lib.TUNE_TIMING_BUFFER, 0)
         for it in range(3):
             lib.ssrlcv_b200_match(h, C.byref(p), hq, ht, None, 0, C.c_void_p(out.data_ptr()), C.byref(n_out))
