@@ -75,7 +75,9 @@ enum {
                                                  bit 0 = load only every other target tile, bit 1 = skip the fold MMA,
                                                  bit 2 = skip the epilogue's max trees, bit 5 = no W ring (no-fold, smax_pair.cu);
                                                  0 / -1 = off                                                                    */
-  SSRLCV_B200_TUNE_PAIR_UNITS = 8,            /* 0 / 1: unmasked searches one / two query tiles per work unit (smax_tc.cu / smax_pair.cu) */
+  SSRLCV_B200_TUNE_PAIR_UNITS = 8,            /* 0 / 1: unmasked searches one / two query tiles per work unit (smax_tc.cu / smax_pair.cu);
+                                                 2: four per CTA PAIR (smax_duo.cu, tcgen05 cta_group::2 on a cluster of two SMs) -- bit-exact,
+                                                 measured slower than 1, never chosen by the library (profiles/r2_kernel_experiments.txt 8) */
   SSRLCV_B200_TUNE_COUNT_ = 9
 };
 /* internal engine ids (kept for the library's own use) */

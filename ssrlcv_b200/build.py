@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libssrlcv_match_b200.so")
-SOURCES = ["api.cu", "pack.cu", "smax_tc.cu", "smax_pair.cu", "exact.cu", "finalize.cu", "multi.cu"]
+SOURCES = ["api.cu", "pack.cu", "smax_tc.cu", "smax_pair.cu", "smax_duo.cu", "exact.cu", "finalize.cu", "multi.cu"]
 HEADERS = ["matcher.cuh", "ptx.cuh", "geometry.cuh", "smax_common.cuh", os.path.join("..", "..", "include", "ssrlcv_b200.h")]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",

@@ -24,6 +24,8 @@ cudaError_t launch_sort_gather(cudaStream_t, const ssrlcv_b200_set_impl& src, ss
 // smax_tc.cu
 cudaError_t launch_smax(cudaStream_t, const SmaxBatch&, int mask_kind, bool fold, bool colmask);
 cudaError_t launch_smax_pair(cudaStream_t, const SmaxBatch&, bool fold, bool colmask);
+cudaError_t launch_smax_duo(cudaStream_t, const SmaxBatch&, bool fold, bool colmask);
+int smax_duo_max_pairs();
 // exact.cu
 void launch_exact(cudaStream_t, const SmaxArgs&, int mask_kind, int sm_count);
 void launch_exact_list(cudaStream_t, const SmaxBatch&, int mask_kind, int sm_count);
@@ -326,12 +328,12 @@ static int set_alloc(ssrlcv_b200_ctx* ctx, uint64_t n, ssrlcv_b200_set** out, bo
   s->orig = with_orig ? reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s->wmax) + wmax_bytes) : nullptr;
   s->wbox = with_orig ? reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(s->orig) + np * 4) : nullptr;   // np * 4 is a multiple of 1024
   s->tbox = with_orig ? s->wbox + np / kChunk : nullptr;
-  s->has_map_a = s->has_map_bx = false;
+  s->has_map_a = s->has_map_bx = s->has_map_exth = false;
   *out = s;
   return 0;
 }
 // TMA descriptors of a set, encoded when the set is first used as a query (A tiles) / as a target (B + digit tiles)
-static int ensure_maps(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* cs, bool as_query, bool as_target) {
+static int ensure_maps(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* cs, bool as_query, bool as_target, bool as_half_target = false) {
   ssrlcv_b200_set* s = const_cast<ssrlcv_b200_set*>(cs);
   int rc = 0;
   if (as_query && !s->has_map_a) {
@@ -344,6 +346,11 @@ static int ensure_maps(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* cs, bool as_
     if (!rc) rc = encode_map(ctx, &s->map_ext, s->ext, s->n_pad, kExtBytes, kBN, CU_TENSOR_MAP_SWIZZLE_32B);
     if (rc) return rc;
     s->has_map_bx = true;
+  }
+  if (as_half_target && !s->has_map_exth) {              // (its descriptor half-tiles go through map_a: same box)
+    rc = encode_map(ctx, &s->map_exth, s->ext, s->n_pad, kExtBytes, kBN / 2, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (rc) return rc;
+    s->has_map_exth = true;
   }
   return 0;
 }
@@ -578,11 +585,12 @@ static void plan_simt(const ssrlcv_b200_ctx* ctx, SmaxArgs& a) {
 // Tensor-core engine: the tile spaces (query tile x target tile) of all jobs of a launch are laid end to end and cut into
 // one contiguous, equally long range per CTA (matcher.cuh).  Every SM gets the same number of tiles (+-1) whatever the
 // shapes; a query tile is shared by the few CTAs whose ranges cross it, each writing its own key slot.
-static uint32_t launch_ctas(const ssrlcv_b200_ctx* ctx, uint64_t total_tiles) {
+static uint32_t launch_ctas(const ssrlcv_b200_ctx* ctx, uint64_t total_tiles, bool cta_pairs = false) {
   const uint64_t min_tiles = 4;                         // per-unit fixed cost (A tile, pipeline fill, resolve) ~ a few tiles
+  const uint64_t most = cta_pairs ? static_cast<uint64_t>(smax_duo_max_pairs()) : static_cast<uint64_t>(ctx->sm_count);
   uint64_t g = total_tiles / min_tiles;
+  if (g > most) g = most;
   if (g < 1) g = 1;
-  if (g > static_cast<uint64_t>(ctx->sm_count)) g = static_cast<uint64_t>(ctx->sm_count);
   return static_cast<uint32_t>(g);
 }
 // key slots of a job = the widest crossing of one of its query tiles (total_tiles, n_ctas, tile_begin already set)
@@ -674,7 +682,7 @@ struct PairWork {
 // those sets once the stream has been synchronised.  optimistic == NULL: wait for the sets' packs first.
 static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* optimistic) {
   struct Group { std::vector<uint32_t> idx; uint64_t total = 0; };
-  Group groups[24];                                       // [mask kind][fold][column-mask regime][one / two query tiles per unit]
+  Group groups[36];                                       // [mask kind][fold][column-mask regime][walk: one / two / two-per-CTA-of-a-pair query tiles per unit]
   size_t keys_total = 0, qmask_total = 0;
   if (optimistic) *optimistic = false;
   for (uint32_t i = 0; i < n; ++i) {
@@ -693,7 +701,12 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     if (ctx->knob[SSRLCV_B200_TUNE_PAIR_UNITS] >= 0)
       pair_units = ctx->knob[SSRLCV_B200_TUNE_PAIR_UNITS] != 0 && p.engine != SSRLCV_B200_ENGINE_SIMT && p.mp.kind == SSRLCV_B200_MASK_NONE &&
                    a.nq_pad % (2 * kBM) == 0 && p.exclude == nullptr;
-    a.q_tile_rows = pair_units ? 2 * kBM : kBM;
+    // ... and, on a CTA pair (smax_duo.cu, tcgen05 cta_group::2), four query tiles per unit with every target tile staged half in
+    // each SM of the pair: bit-exact, measured slower (the accumulator hand-off crosses the pair twice), only ever run by the knob
+    bool duo_units = false;
+    if (ctx->knob[SSRLCV_B200_TUNE_PAIR_UNITS] == 2) duo_units = pair_units && smax_duo_max_pairs() > 0;
+    const int walk = duo_units ? 2 : (pair_units ? 1 : 0);
+    a.q_tile_rows = duo_units ? 4 * kBM : (pair_units ? 2 * kBM : kBM);
     a.n_qtiles = (a.nq + a.q_tile_rows - 1) / a.q_tile_rows;
     const uint64_t tiles = static_cast<uint64_t>(a.n_qtiles) * a.n_ttiles;
     if (tiles >= (1ull << 32))
@@ -746,7 +759,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       // bookkeeping regime (smax_tc.cu): exact column masks for thresholded searches and short target sets
       bool colmask = a.d2_cap != 0x7fffffff || a.q_seed != nullptr || a.n_ttiles < 64;
       if (ctx->knob[SSRLCV_B200_TUNE_COLUMN_MASKS] >= 0) colmask = ctx->knob[SSRLCV_B200_TUNE_COLUMN_MASKS] != 0;   // A/B timing, tests
-      Group& g = groups[2 * (p.mp.kind * 4 + (fold ? 2 : 0) + (colmask ? 1 : 0)) + (pair_units ? 1 : 0)];
+      Group& g = groups[3 * (p.mp.kind * 4 + (fold ? 2 : 0) + (colmask ? 1 : 0)) + walk];
       a.tile_begin = g.total;
       g.total += tiles;
       a.tile_end = g.total;
@@ -754,9 +767,10 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     }
   }
   uint32_t n_tc = 0;
-  for (Group& g : groups) {
+  for (int gi2 = 0; gi2 < 36; ++gi2) {
+    Group& g = groups[gi2];
     if (g.idx.empty()) continue;
-    const uint32_t n_ctas = launch_ctas(ctx, g.total);
+    const uint32_t n_ctas = launch_ctas(ctx, g.total, gi2 % 3 == 2);
     for (uint32_t i : g.idx) {
       SmaxArgs& a = w[i].a;
       a.total_tiles = g.total; a.n_ctas = n_ctas; a.tiles_per_split = a.n_ttiles;
@@ -830,12 +844,15 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     for (Group& g : groups)
       for (uint32_t i : g.idx) {
         w[i].a.n_flagged = d_nflag + at;
+        const bool duo = w[i].a.q_tile_rows == 4 * kBM;
         rc = ensure_maps(ctx, w[i].qq, true, false);
-        if (!rc) rc = ensure_maps(ctx, w[i].tt, false, true);
+        if (!rc) rc = duo ? ensure_maps(ctx, w[i].tt, true, false, true) : ensure_maps(ctx, w[i].tt, false, true);
         if (rc) return rc;
         SmaxJob& j = n_tc > 1 ? hj[at] : single;
         ++at;
-        j.map_q = w[i].qq->map_a; j.map_t = w[i].tt->map_b; j.map_text = w[i].tt->map_ext;
+        j.map_q = w[i].qq->map_a;
+        j.map_t = duo ? w[i].tt->map_a : w[i].tt->map_b;
+        j.map_text = duo ? w[i].tt->map_exth : w[i].tt->map_ext;
         j.a = w[i].a;
       }
     if (n_tc > 1) {
@@ -843,9 +860,9 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       if (rc) return rc;
     }
     at = 0;
-    for (int gi2 = 0; gi2 < 24; ++gi2) {
+    for (int gi2 = 0; gi2 < 36; ++gi2) {
       Group& g = groups[gi2];
-      const int gi = gi2 >> 1;
+      const int gi = gi2 / 3, walk = gi2 % 3;
       if (g.idx.empty()) continue;
       SmaxBatch b;
       memset(&b, 0, sizeof b);
@@ -867,7 +884,8 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
         }
         CU(cudaEventRecord(ctx->prof_events[ctx->prof_used].first, ctx->stream));
       }
-      cudaError_t e = (gi2 & 1) ? launch_smax_pair(ctx->stream, b, (gi & 2) != 0, (gi & 1) != 0)
+      cudaError_t e = walk == 2 ? launch_smax_duo(ctx->stream, b, (gi & 2) != 0, (gi & 1) != 0)
+                    : walk == 1 ? launch_smax_pair(ctx->stream, b, (gi & 2) != 0, (gi & 1) != 0)
                                 : launch_smax(ctx->stream, b, gi / 4, (gi & 2) != 0, (gi & 1) != 0);
       if (e != cudaSuccess) return fail(ctx, static_cast<int>(e), "smax launch: %s", cudaGetErrorString(e));
       if (ctx->profiling) { CU(cudaEventRecord(ctx->prof_events[ctx->prof_used].second, ctx->stream)); ctx->prof_used++; }
@@ -1206,7 +1224,7 @@ static int make_view(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* parent, uint64
   v->norm += row0; v->wcol += row0; v->loc += row0; v->sigtheta += row0; v->wmax += row0 / kChunk;
   v->resolved = false;                                   // the parent's packs may still be in flight: optimistic fold launch
   v->is_view = true; v->sorted = nullptr;
-  v->has_map_a = v->has_map_bx = false;                  // its own tensor maps, encoded on first use
+  v->has_map_a = v->has_map_bx = v->has_map_exth = false;                  // its own tensor maps, encoded on first use
   (void)ctx;
   return 0;
 }

@@ -105,13 +105,16 @@ struct ssrlcv_b200_set_impl {
   CUtensorMap map_a;     // desc, box 128 x kBM rows, SWIZZLE_128B
   CUtensorMap map_b;     // desc, box 128 x kBN rows, SWIZZLE_128B
   CUtensorMap map_ext;   // ext,  box  32 x kBN rows, SWIZZLE_32B
+  CUtensorMap map_exth;  // ext,  box  32 x kBN / 2 rows, SWIZZLE_32B (smax_duo.cu: each CTA of a pair stages half a target tile; its
+                         // descriptor half is map_a's box)
 };
 
 // arguments of the fused tcgen05 kernel
 struct SmaxArgs {
   uint32_t nq, nt;               // real sizes
   uint32_t nq_pad;
-  uint32_t q_tile_rows;          // query rows per work unit: kBM (smax_tc.cu) or 2 * kBM (smax_pair.cu: two A tiles per unit)
+  uint32_t q_tile_rows;          // query rows per work unit: kBM (smax_tc.cu), 2 * kBM (smax_pair.cu: two A tiles per unit) or
+                                 // 4 * kBM (smax_duo.cu: two A tiles in each CTA of a pair)
   uint32_t n_qtiles;             // ceil(nq / q_tile_rows)
   uint32_t n_ttiles;             // ceil(nt / kBN)
   uint32_t n_splits;             // key slots per query: keys is [n_splits][nq_pad]
@@ -161,8 +164,8 @@ struct SmaxArgs {
 // One (query set, target set) pair of a launch; an array of these lives in device memory.
 struct alignas(128) SmaxJob {
   CUtensorMap map_q;             // query descriptors,  box 128 B x kBM rows
-  CUtensorMap map_t;             // target descriptors, box 128 B x kBN rows
-  CUtensorMap map_text;          // target fold digits, box  32 B x kBN rows
+  CUtensorMap map_t;             // target descriptors, box 128 B x kBN rows (smax_duo.cu jobs: kBN / 2 rows)
+  CUtensorMap map_text;          // target fold digits, box  32 B x kBN rows (smax_duo.cu jobs: kBN / 2 rows)
   SmaxArgs a;
 };
 // The launch's job table: device memory (many pairs, staged by the host) or, for a single pair, carried in the kernel's
@@ -170,7 +173,7 @@ struct alignas(128) SmaxJob {
 struct SmaxBatch {
   const SmaxJob* jobs;           // nullptr: the single job is `inline_job`
   uint32_t n_jobs;
-  uint32_t n_ctas;
+  uint32_t n_ctas;               // ranges the unit space is cut into: CTAs, or CTA pairs (smax_duo.cu)
   uint64_t total_tiles;
   unsigned long long* timing;    // optional [gridDim.x][16] cycle counters (diagnostics build), or nullptr
   const uint32_t* flags;         // this launch's tie counters, one per job (job i counts into flags[i])
@@ -261,7 +264,7 @@ struct ssrlcv_b200_set : b200::ssrlcv_b200_set_impl {
   int32_t* h_mm;
   cudaEvent_t ready;
   bool resolved;
-  bool has_map_a, has_map_bx;    // tensor maps are encoded on first use as a query / as a target (api.cu ensure_maps)
+  bool has_map_a, has_map_bx, has_map_exth;    // tensor maps are encoded on first use as a query / as a target (api.cu ensure_maps)
   bool is_view;                  // rows of another set (match_host_streamed): borrowed memory
   ssrlcv_b200_set* sorted;       // cached x-sorted copy (owned), or nullptr
 };

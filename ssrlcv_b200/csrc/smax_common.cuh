@@ -113,16 +113,18 @@ __device__ __forceinline__ int32_t window_maxima(const uint32_t (&v)[kWin][32], 
 }
 // The rare path (all lanes of the warp take it together).  No-fold: only windows whose bound reaches some lane's best get W
 // added (s_w: shared-window address of the first window's 32 W values) and an exact maximum; the others stay bounds below every
-// lane's best.  win0: global index of the first window.
-template <int kWin, bool kFold, bool kColMask>
+// lane's best.  win0: global index of the first window.  kSplit (smax_duo.cu, 128-column accumulators fed by both CTAs of a pair):
+// the four windows are two runs of two, four windows apart -- k -> win0 + (k >> 1) * 4 + (k & 1).
+template <int kWin, bool kFold, bool kColMask, bool kSplit = false>
 __device__ __forceinline__ void window_bookkeeping(uint32_t (&v)[kWin][32], int32_t (&wm)[kWin], WinState& st, uint32_t win0, uint32_t s_w,
                                                    bool has_exclude, const SmaxArgs& job, uint32_t row) {
+  auto wofs = [](int k) { return kSplit ? static_cast<uint32_t>((k >> 1) * 4 + (k & 1)) : static_cast<uint32_t>(k); };
   if (!kFold) {
 #pragma unroll
     for (int k = 0; k < kWin; ++k) {
       if (!__any_sync(0xffffffffu, wm[k] >= st.best)) continue;
       uint32_t(&x)[32] = v[k];
-      const uint32_t wp = s_w + k * (kChunk * 4);
+      const uint32_t wp = s_w + wofs(k) * (kChunk * 4);
 #pragma unroll
       for (int e = 0; e < 32; e += 4) {
         const int4 w4 = ld_shared_v4(wp + 4 * e);
@@ -140,11 +142,11 @@ __device__ __forceinline__ void window_bookkeeping(uint32_t (&v)[kWin][32], int3
 #pragma unroll
     for (int k = 0; k < kWin; ++k) {
       if (__any_sync(0xffffffffu, wm[k] >= st.best))         // which columns attained it: only for windows that matter
-        win_update(st, wm[k], win0 + k, eq_mask32(v[k], wm[k]));
+        win_update(st, wm[k], win0 + wofs(k), eq_mask32(v[k], wm[k]));
     }
   } else {
 #pragma unroll
-    for (int k = 0; k < kWin; ++k) win_update(st, wm[k], win0 + k, 0u);
+    for (int k = 0; k < kWin; ++k) win_update(st, wm[k], win0 + wofs(k), 0u);
   }
 }
 

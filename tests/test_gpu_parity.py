@@ -1380,6 +1380,20 @@ def test_runner_up_search_is_the_second_smallest_key(api, everest, knobs, thr):
         assert (b >= a).all() and (b[a != np.uint64(0xFFFFFFFFFFFFFFFF)] != a[a != np.uint64(0xFFFFFFFFFFFFFFFF)]).all()
 
 
+@pytest.mark.parametrize("nq,nt", [(300, 700), (513, 4097), (4096 + 77, 8192 + 5)])
+@pytest.mark.parametrize("thr", [FLT_MAX, 200.0 * 200.0])
+def test_cta_pair_walk_matches_oracle(api, knobs, nq, nt, thr):
+    """smax_duo.cu (tcgen05 cta_group::2 on a cluster of two SMs, ssrlcv_b200_tune(PAIR_UNITS, 2); measured slower than smax_pair.cu,
+    never selected automatically -- profiles/r2_kernel_experiments.txt section 8): every (fold, column-mask) variant gives the oracle's
+    records, including sets whose last 512-row unit leaves the peer CTA nothing but padding."""
+    q, t = synth.make_pair(nq, nt, seed=nq + nt, dup=0.02)
+    want = api.O.generate_matches(api.O.make_params(out_kind=T.OUT_DMATCH, abs_threshold=thr), q, t)
+    for fold, cm in [(None, None), ("0", None), (None, "0"), ("0", "0"), (None, "1")]:
+        knobs(fold=fold, colmask=cm, pair="2")
+        got = api.MatchFactory(1.0, thr).generateDistanceMatches(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t)).to_numpy()
+        assert len(got) == len(want) and T.fields_equal(got, want), (fold, cm)
+
+
 def _lib_mod():
     from ssrlcv_b200 import _lib
     return _lib

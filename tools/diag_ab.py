@@ -61,11 +61,14 @@ for fold, pair in [(f, pr) for f in (1, 0) for pr in pairs]:
         lib.ssrlcv_b200_kernel_time(h, C.byref(k_ms), C.byref(k_n))
         ms = k_ms.value / k_n.value
         # in-kernel clock: the instrumented build's MMA-warp cycle count over its event time
+        tim.zero_()
         lib.ssrlcv_b200_tune(h, _lib.TUNE_TIMING_BUFFER, tim.data_ptr())
         for it in range(3):
             lib.ssrlcv_b200_match(h, C.byref(p), hq, ht, None, 0, C.c_void_p(out.data_ptr()), C.byref(n_out))
         lib.ssrlcv_b200_kernel_time(h, C.byref(k_ms), C.byref(k_n))
         x = tim.cpu().numpy().reshape(148, 16)
+        if pair == 2:
+            x = x[0::2]                # the leader CTA of each pair
         ims = k_ms.value / k_n.value
         print(f"fold={fold} pair={pair} diag={d}: kernel {1e3 * ms:8.2f} us  matches {n_out.value:6d} | instrumented {1e3 * ims:8.2f} us, mma cycles {x[:, 2].mean():9.0f} "
-              f"-> {x[:, 2].mean() / (1e3 * ims):6.1f} MHz, mma wait_t_empty {x[:, 0].mean():8.0f} wait_full {x[:, 1].mean():7.0f}, epi0 wait {x[:, 4].mean():8.0f} work {x[:, 5].mean():8.0f} cwait|rare {x[:, 15].mean():7.0f} events {x[:, 14].mean():5.1f}", flush=True)
+              f"-> {x[:, 2].mean() / (1e3 * ims):6.1f} MHz, mma wait_t_empty {x[:, 0].mean():8.0f} wait_full {x[:, 1].mean():7.0f}, epi0 wait {x[:, 4].mean():8.0f} work {x[:, 5].mean():8.0f} cwait|rare {x[:, 15].mean():7.0f} events {x[:, 14].mean():5.1f}" + (f" | ld {x[:, 8].mean():8.0f} hand-back {x[:, 9].mean():7.0f} " if pair == 2 else ""), flush=True)
