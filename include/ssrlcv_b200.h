@@ -78,7 +78,10 @@ enum {
   SSRLCV_B200_TUNE_PAIR_UNITS = 8,            /* 0 / 1: unmasked searches one / two query tiles per work unit (smax_tc.cu / smax_pair.cu);
                                                  2: four per CTA PAIR (smax_duo.cu, tcgen05 cta_group::2 on a cluster of two SMs) -- bit-exact,
                                                  measured slower than 1, never chosen by the library (profiles/r2_kernel_experiments.txt 8) */
-  SSRLCV_B200_TUNE_COUNT_ = 9
+  SSRLCV_B200_TUNE_MASK_COOPERATIVE = 9,      /* masked searches: most live queries of a warp for which a window's mask is evaluated by the
+                                                 warp together (default 12); beyond, per row over its candidate columns (smax_tc.cu)   */
+  SSRLCV_B200_TUNE_MASK_WALK = 10,            /* ... unless some row has more candidate columns than this (default 32 = never): all 32 are tested */
+  SSRLCV_B200_TUNE_COUNT_ = 11
 };
 /* internal engine ids (kept for the library's own use) */
 enum { SSRLCV_B200_ENGINE_TCGEN05 = 0, SSRLCV_B200_ENGINE_SIMT = 1 };

@@ -874,6 +874,8 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       b.flags = d_nflag + at;
       b.clear = d_nflag_other; b.clear_n = bank_len;
       for (uint32_t i : g.idx) if (w[i].exclude != nullptr) b.has_exclude = 1;
+      b.mask_coop_max = ctx->knob[SSRLCV_B200_TUNE_MASK_COOPERATIVE] >= 0 ? static_cast<uint32_t>(ctx->knob[SSRLCV_B200_TUNE_MASK_COOPERATIVE]) : 12u;
+      b.mask_walk_max = ctx->knob[SSRLCV_B200_TUNE_MASK_WALK] >= 0 ? static_cast<uint32_t>(ctx->knob[SSRLCV_B200_TUNE_MASK_WALK]) : 32u;
       b.diag = ctx->knob[SSRLCV_B200_TUNE_DIAG] > 0 ? static_cast<uint32_t>(ctx->knob[SSRLCV_B200_TUNE_DIAG]) : 0u;
       b.timing = ctx->knob[SSRLCV_B200_TUNE_TIMING_BUFFER] > 0 ? reinterpret_cast<unsigned long long*>(ctx->knob[SSRLCV_B200_TUNE_TIMING_BUFFER]) : nullptr;
       if (ctx->profiling) {

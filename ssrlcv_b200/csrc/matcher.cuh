@@ -180,6 +180,10 @@ struct SmaxBatch {
   uint32_t* clear;               // the tie counters of the OTHER bank: zeroed by CTA 0 for the call after this one
   uint32_t clear_n;
   uint32_t diag;                 // what-if timing bits (SSRLCV_B200_TUNE_DIAG); 0 in every product launch
+  // masked searches, rare path (smax_tc.cu): a window that matters to at most mask_coop_max queries of a warp is tested by the warp
+  // together (one query at a time, lane l = target l); beyond that every lane walks the candidate columns of its own row unless
+  // some row has more than mask_walk_max of them (then all 32 columns are tested)
+  uint32_t mask_coop_max, mask_walk_max;
   uint32_t has_exclude;          // some job of the launch is a runner-up search (SmaxArgs::q_exclude): read from the parameter bank,
                                  // so the rare path of every other launch pays nothing for the feature
   SmaxJob inline_job;

@@ -403,7 +403,7 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
                 // score 0, below every floor (as do the rows past the end of the target set: zero padding with W = 0).
                 uint32_t todo = __ballot_sync(0xffffffffu, wm[k] >= st.best);
                 const bool mine = (todo >> lane) & 1u;             // this lane's query is one of the live ones
-                if (__popc(todo) <= 10) {
+                if (static_cast<uint32_t>(__popc(todo)) <= batch.mask_coop_max) {
                   uint32_t skip = 0;
                   const float2 tl = ld_shared_f2(smem_u32(s_loc + (c_begin + k) * kChunk + lane));
                   while (todo) {
@@ -416,13 +416,36 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
 #pragma unroll
                   for (int e = 0; e < 32; ++e) x[e] = (skip >> e) & 1u ? 0u : x[e];
                 } else {
-                  // many live queries (loose thresholds on real data): every lane tests the 32 targets of its own row
+                  // Many live queries (loose thresholds on real data).  Only a column whose score reaches its row's running best can
+                  // change anything, and once a query has seen a few masked-in targets that is one or two of a window's 32: every
+                  // lane walks the candidate columns of its own row (location by shared-memory address) and zeroes the masked-out
+                  // ones; the other columns stay unverified below the best.  A window in which some row has many candidates
+                  // (a query's first windows) is tested column by column as before.
                   const uint32_t lp = smem_u32(s_loc + (c_begin + k) * kChunk);
+                  uint32_t cand = 0;
+                  if (mine) {
 #pragma unroll
-                  for (int e = 0; e < 32; e += 2) {
-                    const int4 l2 = ld_shared_v4(lp + 8 * e);
-                    if (mask_skips<kMask>(qm, __int_as_float(l2.x), __int_as_float(l2.y), eps)) x[e] = 0;
-                    if (mask_skips<kMask>(qm, __int_as_float(l2.z), __int_as_float(l2.w), eps)) x[e + 1] = 0;
+                    for (int e = 0; e < 32; ++e) cand |= (static_cast<int32_t>(x[e]) >= st.best) ? (1u << e) : 0u;
+                  }
+                  if (__reduce_max_sync(0xffffffffu, static_cast<uint32_t>(__popc(cand))) <= batch.mask_walk_max) {
+                    uint32_t dead = 0;
+                    while (__any_sync(0xffffffffu, cand != 0u)) {
+                      if (cand) {
+                        const uint32_t e = __ffs(cand) - 1;
+                        cand &= cand - 1u;
+                        const float2 tl = ld_shared_f2(lp + 8 * e);
+                        dead |= mask_skips<kMask>(qm, tl.x, tl.y, eps) ? (1u << e) : 0u;
+                      }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) x[e] = (dead >> e) & 1u ? 0u : x[e];
+                  } else {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                      const int4 l2 = ld_shared_v4(lp + 8 * e);
+                      if (mask_skips<kMask>(qm, __int_as_float(l2.x), __int_as_float(l2.y), eps)) x[e] = 0;
+                      if (mask_skips<kMask>(qm, __int_as_float(l2.z), __int_as_float(l2.w), eps)) x[e + 1] = 0;
+                    }
                   }
                 }
                 // a lane that was not live keeps its bound (below its best; its row may not have been masked)
