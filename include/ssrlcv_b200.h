@@ -81,7 +81,9 @@ enum {
   SSRLCV_B200_TUNE_MASK_COOPERATIVE = 9,      /* masked searches: most live queries of a warp for which a window's mask is evaluated by the
                                                  warp together (default 12); beyond, per row over its candidate columns (smax_tc.cu)   */
   SSRLCV_B200_TUNE_MASK_WALK = 10,            /* ... unless some row has more candidate columns than this (default 32 = never): all 32 are tested */
-  SSRLCV_B200_TUNE_COUNT_ = 11
+  SSRLCV_B200_TUNE_CELL_SORT = 11,            /* 0: spatially sorted copies always by the radix sort of Morton keys; default: sets below 65 536
+                                                 rows by a one-block counting sort over image cells (pack.cu)                            */
+  SSRLCV_B200_TUNE_COUNT_ = 12
 };
 /* internal engine ids (kept for the library's own use) */
 enum { SSRLCV_B200_ENGINE_TCGEN05 = 0, SSRLCV_B200_ENGINE_SIMT = 1 };

@@ -19,6 +19,8 @@ namespace b200 {
 // pack.cu
 void launch_pack(cudaStream_t, const PackJob* jobs, uint32_t n_jobs, int sm_count, uint64_t* launches);
 size_t sort_x_temp_bytes(uint32_t n);
+bool cell_sort_serves(uint64_t n);
+cudaError_t launch_cell_sort_gather(cudaStream_t, const ssrlcv_b200_set_impl& src, ssrlcv_b200_set_impl& dst, uint32_t* perm, uint16_t* cell_of);
 cudaError_t launch_sort_gather(cudaStream_t, const ssrlcv_b200_set_impl& src, ssrlcv_b200_set_impl& dst, uint32_t* keys_in, uint32_t* keys_out,
                                uint32_t* vals_in, uint32_t* vals_out, void* temp, size_t temp_bytes);
 // smax_tc.cu
@@ -636,16 +638,24 @@ static int sorted_of(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* ct, const ssrl
   rc = ws_reserve(ctx, ctx->sortws, 4 * n4 + temp + 256);
   if (rc) { ssrlcv_b200_set_free(s2); return rc; }
   uint8_t* w = static_cast<uint8_t*>(ctx->sortws.p);
-  cudaError_t e = cudaMemsetAsync(s2->wmax, 0, (s2->n_pad / kChunk) * 4, ctx->stream);   // the gather accumulates the window bounds with atomicMax
-  if (e == cudaSuccess)
-    e = launch_sort_gather(ctx->stream, *t, *s2, reinterpret_cast<uint32_t*>(w), reinterpret_cast<uint32_t*>(w + n4),
-                           reinterpret_cast<uint32_t*>(w + 2 * n4), reinterpret_cast<uint32_t*>(w + 3 * n4), w + 4 * n4, temp);
+  cudaError_t e = cudaSuccess;
+  bool cells = cell_sort_serves(t->n);                     // one-block counting sort over image cells + one copy launch (pack.cu)
+  if (ctx->knob[SSRLCV_B200_TUNE_CELL_SORT] >= 0) cells = cells && ctx->knob[SSRLCV_B200_TUNE_CELL_SORT] != 0;
+  if (cells) {
+    e = launch_cell_sort_gather(ctx->stream, *t, *s2, reinterpret_cast<uint32_t*>(w), reinterpret_cast<uint16_t*>(w + n4));
+    ctx->launches += 2;
+  } else {
+    e = cudaMemsetAsync(s2->wmax, 0, (s2->n_pad / kChunk) * 4, ctx->stream);   // the gather accumulates the window bounds with atomicMax
+    if (e == cudaSuccess)
+      e = launch_sort_gather(ctx->stream, *t, *s2, reinterpret_cast<uint32_t*>(w), reinterpret_cast<uint32_t*>(w + n4),
+                             reinterpret_cast<uint32_t*>(w + 2 * n4), reinterpret_cast<uint32_t*>(w + 3 * n4), w + 4 * n4, temp);
+    ctx->launches += 4;
+  }
   if (e == cudaSuccess && !t->fold_ok) {
     e = cudaMemsetAsync(s2->meta, 1, sizeof(int32_t), ctx->stream);
     s2->h_mm[0] = 1;
   }
   if (e != cudaSuccess) { ssrlcv_b200_set_free(s2); return fail(ctx, static_cast<int>(e), "sorted copy: %s", cudaGetErrorString(e)); }
-  ctx->launches += 4;
   rc = set_finish(ctx, s2);
   if (rc) { ssrlcv_b200_set_free(s2); return rc; }
   s2->fold_ok = t->fold_ok; s2->resolved = true;

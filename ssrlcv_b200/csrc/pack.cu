@@ -7,6 +7,8 @@
 //                             no-fold variant tests before it adds W to a window's scores
 //   loc   float2[n_pad]       sigtheta float2[n_pad]
 // HBM-bound byte shuffling: 152 B read, 188 B written per feature (+ 4 B per 32 features).
+#include <atomic>
+
 #include <cub/cub.cuh>
 
 #include "matcher.cuh"
@@ -231,6 +233,212 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(const uint32_t* __re
     }
   }
 }
+// ---- small sets (n < 65 536: every set of the reference's fixtures): the whole ordering in ONE block, the copy in one more launch.
+// A radix sort of 32 k keys is ten launches of a few microseconds each (histogram, scan, four onesweep passes, ...), ~70 us per set
+// against a matcher launch of ~230; a counting sort over image cells needs no passes at all.  Cells: 128 x 128 over the bounding box
+// of the finite locations, in Z order (14-bit Morton code; one more bin for rows with a NaN coordinate, which sort last); rows of a
+// cell keep their original order, so the result is a stable sort by cell and does not depend on the order the atomics land in.
+constexpr int kCellBits = 7;                                   // per axis
+constexpr uint32_t kCellBins = (1u << (2 * kCellBits)) + 1;    // + the NaN bin
+constexpr int kCellThreads = 1024;
+constexpr uint32_t kCellSortMaxRows = 65535;                   // row indices travel as u16 in shared memory
+struct CellSortSmem {
+  uint32_t cursor[kCellBins + 3];        // histogram -> exclusive scan -> running cursor (ends at each bin's end)
+  uint32_t part[kCellThreads / 32];
+  float red[4][kCellThreads / 32];
+  float lim[4];
+  uint16_t perm[kCellSortMaxRows + 1];
+};
+__device__ __forceinline__ uint32_t spread7(uint32_t v) {     // 0000000 gfedcba -> 0g0f0e0d0c0b0a
+  v &= 0x7Fu;
+  v = (v | (v << 4)) & 0x070Fu;
+  v = (v | (v << 2)) & 0x1333u;
+  v = (v | (v << 1)) & 0x1555u;
+  return v;
+}
+__global__ void __launch_bounds__(kCellThreads, 1) cell_sort_kernel(const float2* __restrict__ loc, uint32_t n, uint16_t* __restrict__ cell_of,
+                                                                    uint32_t* __restrict__ perm_out) {
+  extern __shared__ __align__(16) uint8_t cs_raw[];
+  CellSortSmem& sm = *reinterpret_cast<CellSortSmem*>(cs_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (uint32_t b = tid; b < kCellBins + 3; b += kCellThreads) sm.cursor[b] = 0;
+  pdl_wait();                                                   // loc is the pack launch's output
+  pdl_launch_dependents();
+  // ---- bounding box of the finite locations
+  const float inf = __int_as_float(0x7f800000);
+  float x0 = inf, x1 = -inf, y0 = inf, y1 = -inf;
+  for (uint32_t i = tid; i < n; i += kCellThreads) {
+    const float2 l = loc[i];
+    if (fabsf(l.x) < inf && fabsf(l.y) < inf) { x0 = fminf(x0, l.x); x1 = fmaxf(x1, l.x); y0 = fminf(y0, l.y); y1 = fmaxf(y1, l.y); }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+    y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+  }
+  if (lane == 0) { sm.red[0][warp] = x0; sm.red[1][warp] = x1; sm.red[2][warp] = y0; sm.red[3][warp] = y1; }
+  __syncthreads();
+  if (warp == 0) {
+    x0 = sm.red[0][lane]; x1 = sm.red[1][lane]; y0 = sm.red[2][lane]; y1 = sm.red[3][lane];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+      y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    if (lane == 0) {
+      const float cells = static_cast<float>(1 << kCellBits);
+      sm.lim[0] = x0; sm.lim[1] = (x1 > x0) ? cells / (x1 - x0) : 0.0f;
+      sm.lim[2] = y0; sm.lim[3] = (y1 > y0) ? cells / (y1 - y0) : 0.0f;
+    }
+  }
+  __syncthreads();
+  const float ox = sm.lim[0], sx = sm.lim[1], oy = sm.lim[2], sy = sm.lim[3];
+  // ---- cell of every row, histogram
+  for (uint32_t i = tid; i < n; i += kCellThreads) {
+    const float2 l = loc[i];
+    uint32_t c = kCellBins - 1;                                 // a NaN / infinite coordinate: last
+    if (fabsf(l.x) < inf && fabsf(l.y) < inf) {
+      const int cx = min((1 << kCellBits) - 1, max(0, static_cast<int>((l.x - ox) * sx)));
+      const int cy = min((1 << kCellBits) - 1, max(0, static_cast<int>((l.y - oy) * sy)));
+      c = (spread7(static_cast<uint32_t>(cy)) << 1) | spread7(static_cast<uint32_t>(cx));
+    }
+    cell_of[i] = static_cast<uint16_t>(c);
+    atomicAdd(&sm.cursor[c], 1u);
+  }
+  __syncthreads();
+  // ---- exclusive scan of the bins: each thread a run of consecutive bins, then the block
+  constexpr uint32_t kRun = (kCellBins + kCellThreads - 1) / kCellThreads;   // 17
+  const uint32_t b0 = tid * kRun;
+  uint32_t sum = 0;
+  for (uint32_t k = 0; k < kRun; ++k) if (b0 + k < kCellBins) sum += sm.cursor[b0 + k];
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) sm.part[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t v = sm.part[lane], w = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += u; }
+    sm.part[lane] = w - v;
+  }
+  __syncthreads();
+  uint32_t run = sm.part[warp] + incl - sum;
+  for (uint32_t k = 0; k < kRun; ++k)
+    if (b0 + k < kCellBins) { const uint32_t c = sm.cursor[b0 + k]; sm.cursor[b0 + k] = run; run += c; }
+  __syncthreads();
+  // ---- scatter (order inside a cell: whatever the atomics give), then every cell's rows back into ascending order
+  for (uint32_t i = tid; i < n; i += kCellThreads) {
+    const uint32_t at = atomicAdd(&sm.cursor[cell_of[i]], 1u);
+    sm.perm[at] = static_cast<uint16_t>(i);
+  }
+  __syncthreads();
+  for (uint32_t k = 0; k < kRun; ++k) {
+    const uint32_t b = b0 + k;
+    if (b >= kCellBins) break;
+    const uint32_t end = sm.cursor[b], begin = b ? sm.cursor[b - 1] : 0u;   // cursor[b] now ends bin b = begins bin b + 1
+    for (uint32_t i = begin + 1; i < end; ++i) {                             // insertion sort: a cell holds a handful of rows
+      const uint16_t v = sm.perm[i];
+      uint32_t j = i;
+      while (j > begin && sm.perm[j - 1] > v) { sm.perm[j] = sm.perm[j - 1]; --j; }
+      sm.perm[j] = v;
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < n; i += kCellThreads) perm_out[i] = sm.perm[i];
+}
+
+// One block per 256-row tile of the sorted set, one warp per 32-row window: lane l takes the scalars of row l, the descriptor and
+// digit rows are copied one row per step by the whole warp; the window's largest W and its bounding box are warp reductions, the
+// tile's box comes from its 8 windows -- no atomics, nothing to zero beforehand, no separate box pass.
+__global__ void __launch_bounds__(256) gather_tiles_kernel(const uint32_t* __restrict__ perm, uint32_t n, uint32_t n_rows,
+                                                           const uint8_t* __restrict__ s_desc, const uint8_t* __restrict__ s_ext,
+                                                           const int32_t* __restrict__ s_norm, const int32_t* __restrict__ s_wcol,
+                                                           const float2* __restrict__ s_loc, const float2* __restrict__ s_sigtheta,
+                                                           uint8_t* __restrict__ desc, uint8_t* __restrict__ ext, int32_t* __restrict__ norm,
+                                                           int32_t* __restrict__ wcol, int32_t* __restrict__ wmax, float2* __restrict__ loc,
+                                                           float2* __restrict__ sigtheta, uint32_t* __restrict__ orig,
+                                                           float4* __restrict__ wbox, float4* __restrict__ tbox) {
+  __shared__ float4 s_box[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t r = blockIdx.x * 256u + threadIdx.x;          // this lane's row (n_rows % 256 == 0)
+  pdl_wait();
+  pdl_launch_dependents();
+  const bool real = r < n;
+  const uint32_t src = real ? perm[r] : 0u;
+  const float inf = __int_as_float(0x7f800000);
+  float x0 = inf, x1 = -inf, y0 = inf, y1 = -inf;
+  bool bad = false;
+  int32_t w = 0;
+  if (real) {
+    const float2 l = s_loc[src];
+    w = s_wcol[src];
+    norm[r] = s_norm[src]; wcol[r] = w; loc[r] = l; sigtheta[r] = s_sigtheta[src]; orig[r] = src;
+    bad = (l.x != l.x) || (l.y != l.y);
+    if (!bad) { x0 = x1 = l.x; y0 = y1 = l.y; }
+  } else {
+    norm[r] = 0; wcol[r] = 0; loc[r] = make_float2(0.f, 0.f); sigtheta[r] = make_float2(0.f, 0.f); orig[r] = 0u;
+  }
+  // descriptor + digit rows of the window, one row per step (128 + 32 contiguous bytes each)
+  const uint32_t row0 = blockIdx.x * 256u + warp * 32u;
+#pragma unroll 4
+  for (int k = 0; k < 32; ++k) {
+    const uint32_t sk = __shfl_sync(0xffffffffu, src, k);
+    const bool rk = row0 + k < n;
+    uint32_t d = 0u, e = 0u;
+    if (rk) {
+      d = reinterpret_cast<const uint32_t*>(s_desc + static_cast<uint64_t>(sk) * kDescBytes)[lane];
+      if (lane < 8) e = reinterpret_cast<const uint32_t*>(s_ext + static_cast<uint64_t>(sk) * kExtBytes)[lane];
+    }
+    reinterpret_cast<uint32_t*>(desc + static_cast<uint64_t>(row0 + k) * kDescBytes)[lane] = d;
+    if (lane < 8) reinterpret_cast<uint32_t*>(ext + static_cast<uint64_t>(row0 + k) * kExtBytes)[lane] = e;
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
+    x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+    y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+  }
+  if (__any_sync(0xffffffffu, bad)) x0 = x1 = y0 = y1 = __uint_as_float(0x7fc00000u);
+  if (lane == 0) {
+    const float4 b4 = make_float4(x0, x1, y0, y1);
+    wmax[row0 >> 5] = w;
+    wbox[row0 >> 5] = b4;
+    s_box[warp] = b4;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float4 t = s_box[0];
+    bool nan = t.x != t.x;
+    for (int k = 1; k < 8; ++k) {
+      const float4 b4 = s_box[k];
+      nan |= b4.x != b4.x;
+      t.x = fminf(t.x, b4.x); t.y = fmaxf(t.y, b4.y); t.z = fminf(t.z, b4.z); t.w = fmaxf(t.w, b4.w);
+    }
+    if (nan) t = make_float4(__uint_as_float(0x7fc00000u), __uint_as_float(0x7fc00000u), __uint_as_float(0x7fc00000u), __uint_as_float(0x7fc00000u));
+    tbox[blockIdx.x] = t;
+  }
+}
+bool cell_sort_serves(uint64_t n) { return n >= 1 && n <= kCellSortMaxRows; }
+// scratch: perm (n u32) then cell ids (n u16); two launches in the stream's dependent-launch chain
+cudaError_t launch_cell_sort_gather(cudaStream_t st, const ssrlcv_b200_set_impl& src, ssrlcv_b200_set_impl& dst, uint32_t* perm, uint16_t* cell_of) {
+  const uint32_t n = static_cast<uint32_t>(src.n), n_rows = static_cast<uint32_t>(dst.n_pad);
+  static std::atomic<uint64_t> configured{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 64 || !((configured.load(std::memory_order_acquire) >> dev) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(cell_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(CellSortSmem)));
+    if (e != cudaSuccess) return e;
+    if (dev < 64) configured.fetch_or(1ull << dev, std::memory_order_release);
+  }
+  cudaError_t e = launch_pdl(cell_sort_kernel, dim3(1), dim3(kCellThreads), sizeof(CellSortSmem), st, src.loc, n, cell_of, perm);
+  if (e != cudaSuccess) return e;
+  return launch_pdl(gather_tiles_kernel, dim3(n_rows / 256), dim3(256), 0, st, static_cast<const uint32_t*>(perm), n, n_rows,
+                    static_cast<const uint8_t*>(src.desc), static_cast<const uint8_t*>(src.ext), static_cast<const int32_t*>(src.norm),
+                    static_cast<const int32_t*>(src.wcol), static_cast<const float2*>(src.loc), static_cast<const float2*>(src.sigtheta),
+                    dst.desc, dst.ext, dst.norm, dst.wcol, dst.wmax, dst.loc, dst.sigtheta, dst.orig, dst.wbox, dst.tbox);
+}
+
 size_t sort_x_temp_bytes(uint32_t n) {
   size_t bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, bytes, static_cast<const uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),

@@ -50,6 +50,7 @@ def knobs(api):
     from ssrlcv_b200 import _lib
     from ssrlcv_b200.match_factory import Context
     names = {"fold": [_lib.TUNE_FOLD], "colmask": [_lib.TUNE_COLUMN_MASKS], "sorted": [_lib.TUNE_SORTED_TARGETS], "pair": [_lib.TUNE_PAIR_UNITS],
+             "cells": [_lib.TUNE_CELL_SORT], "mask_coop": [_lib.TUNE_MASK_COOPERATIVE], "mask_walk": [_lib.TUNE_MASK_WALK],
              "chunk_rows": [_lib.TUNE_HOST_CHUNK_QUERY_ROWS, _lib.TUNE_HOST_CHUNK_TARGET_ROWS]}
     ctx = Context.get(0)
 
@@ -1279,14 +1280,17 @@ def test_masked_without_seeds_on_spatially_sorted_sets(api, everest, knobs, thr)
     pf = api.O.make_params(out_kind=T.OUT_DMATCH, mask_kind=T.MASK_FUNDAMENTAL, abs_threshold=thr, query_id=0, target_id=1, epsilon=30.0, fundamental=F)
     want_f = api.O.generate_matches(pf, q, t)
     assert len(want_f) > 50
-    for so in ("1", "0"):
-        knobs(sorted=so)
+    # sorted by the one-block counting sort over image cells / by the radix sort of Morton keys / not at all; and every way the rare
+    # path evaluates the mask (warp-cooperative, candidate walk, all 32 columns)
+    for so, cells, coop, walk in (("1", None, None, None), ("1", "0", None, None), ("0", None, None, None), ("1", None, "0", "32"),
+                                  ("1", None, "0", "0"), ("1", None, "32", "0"), ("0", None, "2", "3")):
+        knobs(sorted=so, cells=cells, mask_coop=coop, mask_walk=walk)
         mf = api.MatchFactory(1.0, thr)
         got = mf.generateDistanceMatchesDoubleConstrained(qi, _unity(api, q), ti, _unity(api, t), 40.0, 5.0).to_numpy()
-        assert T.fields_equal(got, want), so
+        assert T.fields_equal(got, want), (so, cells, coop, walk)
         got = mf.generateDistanceMatchesConstrained(qi, _unity(api, q), ti, _unity(api, t), 30.0, F).to_numpy()
-        assert T.fields_equal(got, want_f), so
-    knobs(sorted=None)
+        assert T.fields_equal(got, want_f), (so, cells, coop, walk)
+    knobs(sorted=None, cells=None, mask_coop=None, mask_walk=None)
     pr = api.MatchFactory(1.0, thr).generateMatchesDoubleConstrainedIndexOnly(qi, _unity(api, q), ti, _unity(api, t), 40.0, 5.0).to_numpy()
     p.out_kind = T.OUT_PAIR
     assert T.fields_equal(pr, api.O.generate_matches(p, q, t))
