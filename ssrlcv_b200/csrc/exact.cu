@@ -150,37 +150,35 @@ void launch_query_masks(cudaStream_t st, const MaskParams& mp, const float2* loc
 }
 
 // ---- dead tile pairs of a masked search on spatially sorted sets --------------------------------------------
-// One block per query tile, one thread per query: bit j of row qt of `bits` is set iff some query of the tile can match some
-// target whose location lies in the box of target tile j (geometry.cuh box_skips: exact and conservative).  The matcher's
-// roles skip the dead pairs before the MMA.
+// One block per (query tile, word of 32 target tiles), one thread per query: bit j of row qt of `bits` is set iff some query of the
+// tile can match some target whose location lies in the box of target tile j (geometry.cuh box_skips: exact and conservative).
+// The matcher's roles skip the dead pairs before the MMA.
 template <int kMask>
 __global__ void __launch_bounds__(kBM) cull_kernel(const float4* __restrict__ q_mask, uint32_t nq, const float4* __restrict__ tbox,
                                                    uint32_t n_ttiles, float eps, uint32_t* __restrict__ bits, uint32_t stride) {
-  extern __shared__ uint32_t s_words[];               // [stride]
+  __shared__ uint32_t s_word;
   pdl_launch_dependents();
   pdl_wait();                                         // q_mask comes from the launch in front of this one
-  const uint32_t row = blockIdx.x * kBM + threadIdx.x;
+  const uint32_t row = blockIdx.x * kBM + threadIdx.x, w = blockIdx.y;
   const bool real = row < nq;
-  for (uint32_t w = threadIdx.x; w < stride; w += kBM) s_words[w] = 0;
+  if (threadIdx.x == 0) s_word = 0;
   __syncthreads();
   const QueryMask qm = load_query_mask<kMask>(q_mask + 2 * static_cast<uint64_t>(real ? row : 0));
-  for (uint32_t w = 0; w < stride; ++w) {             // 32 target tiles per word: no barrier inside
-    uint32_t mine = 0;
-    const uint32_t j_end = min(n_ttiles - w * 32, 32u);
-    if (real)
-      for (uint32_t b = 0; b < j_end; ++b) mine |= box_skips<kMask>(qm, __ldg(tbox + w * 32 + b), eps) ? 0u : (1u << b);
-    mine = __reduce_or_sync(0xffffffffu, mine);
-    if ((threadIdx.x & 31) == 0 && mine) atomicOr(&s_words[w], mine);
-  }
+  uint32_t mine = 0;
+  const uint32_t j_end = min(n_ttiles - w * 32, 32u);
+  if (real)
+    for (uint32_t b = 0; b < j_end; ++b) mine |= box_skips<kMask>(qm, __ldg(tbox + w * 32 + b), eps) ? 0u : (1u << b);
+  mine = __reduce_or_sync(0xffffffffu, mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicOr(&s_word, mine);
   __syncthreads();
-  for (uint32_t w = threadIdx.x; w < stride; w += kBM) bits[blockIdx.x * stride + w] = s_words[w];
+  if (threadIdx.x == 0) bits[blockIdx.x * stride + w] = s_word;
 }
 void launch_cull(cudaStream_t st, int mask_kind, const float4* q_mask, uint32_t nq, uint32_t n_qtiles, const float4* tbox, uint32_t n_ttiles,
                  float eps, uint32_t* bits, uint32_t stride) {
   if (n_qtiles == 0 || n_ttiles == 0) return;
-  const size_t smem = static_cast<size_t>(stride) * sizeof(uint32_t);   // <= 4 GiTiles / 32 words would not fit: stride is capped by the caller
-  if (mask_kind == SSRLCV_B200_MASK_DOUBLE) launch_pdl(cull_kernel<SSRLCV_B200_MASK_DOUBLE>, dim3(n_qtiles), dim3(kBM), smem, st, q_mask, nq, tbox, n_ttiles, eps, bits, stride);
-  else launch_pdl(cull_kernel<SSRLCV_B200_MASK_FUNDAMENTAL>, dim3(n_qtiles), dim3(kBM), smem, st, q_mask, nq, tbox, n_ttiles, eps, bits, stride);
+  const dim3 grid(n_qtiles, stride);                  // stride <= 8192 (capped by the caller)
+  if (mask_kind == SSRLCV_B200_MASK_DOUBLE) launch_pdl(cull_kernel<SSRLCV_B200_MASK_DOUBLE>, grid, dim3(kBM), 0, st, q_mask, nq, tbox, n_ttiles, eps, bits, stride);
+  else launch_pdl(cull_kernel<SSRLCV_B200_MASK_FUNDAMENTAL>, grid, dim3(kBM), 0, st, q_mask, nq, tbox, n_ttiles, eps, bits, stride);
 }
 
 // ---- small diagnostics kernels -----------------------------------------------------------------

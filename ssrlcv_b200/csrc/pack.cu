@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(const uint32_t* __re
 constexpr int kCellBits = 7;                                   // per axis
 constexpr uint32_t kCellBins = (1u << (2 * kCellBits)) + 1;    // + the NaN bin
 constexpr int kCellThreads = 1024;
+constexpr int kCellBatch = 8;
 constexpr uint32_t kCellSortMaxRows = 65535;                   // row indices travel as u16 in shared memory
 struct CellSortSmem {
   uint32_t cursor[kCellBins + 3];        // histogram -> exclusive scan -> running cursor (ends at each bin's end)
@@ -266,10 +267,15 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_sort_kernel(const float2
   pdl_launch_dependents();
   // ---- bounding box of the finite locations
   const float inf = __int_as_float(0x7f800000);
+  // (one block has to cover the memory latency by itself: every pass keeps kCellBatch independent loads per thread in flight)
   float x0 = inf, x1 = -inf, y0 = inf, y1 = -inf;
-  for (uint32_t i = tid; i < n; i += kCellThreads) {
-    const float2 l = loc[i];
-    if (fabsf(l.x) < inf && fabsf(l.y) < inf) { x0 = fminf(x0, l.x); x1 = fmaxf(x1, l.x); y0 = fminf(y0, l.y); y1 = fmaxf(y1, l.y); }
+  for (uint32_t base = tid; base < n; base += kCellBatch * kCellThreads) {
+    float2 l[kCellBatch];
+#pragma unroll
+    for (int k = 0; k < kCellBatch; ++k) { const uint32_t i = base + k * kCellThreads; l[k] = i < n ? loc[i] : make_float2(inf, inf); }
+#pragma unroll
+    for (int k = 0; k < kCellBatch; ++k)
+      if (fabsf(l[k].x) < inf && fabsf(l[k].y) < inf) { x0 = fminf(x0, l[k].x); x1 = fmaxf(x1, l[k].x); y0 = fminf(y0, l[k].y); y1 = fmaxf(y1, l[k].y); }
   }
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) {
@@ -294,16 +300,23 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_sort_kernel(const float2
   __syncthreads();
   const float ox = sm.lim[0], sx = sm.lim[1], oy = sm.lim[2], sy = sm.lim[3];
   // ---- cell of every row, histogram
-  for (uint32_t i = tid; i < n; i += kCellThreads) {
-    const float2 l = loc[i];
-    uint32_t c = kCellBins - 1;                                 // a NaN / infinite coordinate: last
-    if (fabsf(l.x) < inf && fabsf(l.y) < inf) {
-      const int cx = min((1 << kCellBits) - 1, max(0, static_cast<int>((l.x - ox) * sx)));
-      const int cy = min((1 << kCellBits) - 1, max(0, static_cast<int>((l.y - oy) * sy)));
-      c = (spread7(static_cast<uint32_t>(cy)) << 1) | spread7(static_cast<uint32_t>(cx));
+  for (uint32_t base = tid; base < n; base += kCellBatch * kCellThreads) {
+    float2 l[kCellBatch];
+#pragma unroll
+    for (int k = 0; k < kCellBatch; ++k) { const uint32_t i = base + k * kCellThreads; l[k] = i < n ? loc[i] : make_float2(inf, inf); }
+#pragma unroll
+    for (int k = 0; k < kCellBatch; ++k) {
+      const uint32_t i = base + k * kCellThreads;
+      if (i >= n) break;
+      uint32_t c = kCellBins - 1;                               // a NaN / infinite coordinate: last
+      if (fabsf(l[k].x) < inf && fabsf(l[k].y) < inf) {
+        const int cx = min((1 << kCellBits) - 1, max(0, static_cast<int>((l[k].x - ox) * sx)));
+        const int cy = min((1 << kCellBits) - 1, max(0, static_cast<int>((l[k].y - oy) * sy)));
+        c = (spread7(static_cast<uint32_t>(cy)) << 1) | spread7(static_cast<uint32_t>(cx));
+      }
+      cell_of[i] = static_cast<uint16_t>(c);
+      atomicAdd(&sm.cursor[c], 1u);
     }
-    cell_of[i] = static_cast<uint16_t>(c);
-    atomicAdd(&sm.cursor[c], 1u);
   }
   __syncthreads();
   // ---- exclusive scan of the bins: each thread a run of consecutive bins, then the block
@@ -328,9 +341,17 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_sort_kernel(const float2
     if (b0 + k < kCellBins) { const uint32_t c = sm.cursor[b0 + k]; sm.cursor[b0 + k] = run; run += c; }
   __syncthreads();
   // ---- scatter (order inside a cell: whatever the atomics give), then every cell's rows back into ascending order
-  for (uint32_t i = tid; i < n; i += kCellThreads) {
-    const uint32_t at = atomicAdd(&sm.cursor[cell_of[i]], 1u);
-    sm.perm[at] = static_cast<uint16_t>(i);
+  for (uint32_t base = tid; base < n; base += kCellBatch * kCellThreads) {
+    uint32_t c[kCellBatch];
+#pragma unroll
+    for (int k = 0; k < kCellBatch; ++k) { const uint32_t i = base + k * kCellThreads; c[k] = i < n ? cell_of[i] : 0u; }
+#pragma unroll
+    for (int k = 0; k < kCellBatch; ++k) {
+      const uint32_t i = base + k * kCellThreads;
+      if (i >= n) break;
+      const uint32_t at = atomicAdd(&sm.cursor[c[k]], 1u);
+      sm.perm[at] = static_cast<uint16_t>(i);
+    }
   }
   __syncthreads();
   for (uint32_t k = 0; k < kRun; ++k) {
@@ -381,7 +402,7 @@ __global__ void __launch_bounds__(256) gather_tiles_kernel(const uint32_t* __res
   }
   // descriptor + digit rows of the window, one row per step (128 + 32 contiguous bytes each)
   const uint32_t row0 = blockIdx.x * 256u + warp * 32u;
-#pragma unroll 4
+#pragma unroll 16
   for (int k = 0; k < 32; ++k) {
     const uint32_t sk = __shfl_sync(0xffffffffu, src, k);
     const bool rk = row0 + k < n;
