@@ -257,6 +257,22 @@ __device__ __forceinline__ uint32_t spread7(uint32_t v) {     // 0000000 gfedcba
   v = (v | (v << 1)) & 0x1555u;
   return v;
 }
+// position of cell (x, y) of the 128 x 128 grid along the Hilbert curve: consecutive positions are always neighbouring cells, so a
+// window of 32 consecutive rows never straddles one of the Z curve's jumps and its bounding box stays tight
+constexpr bool kCellHilbert = true;
+__device__ __forceinline__ uint32_t hilbert7(uint32_t x, uint32_t y) {
+  uint32_t d = 0;
+#pragma unroll
+  for (uint32_t s = 1u << (kCellBits - 1); s > 0; s >>= 1) {
+    const uint32_t rx = (x & s) ? 1u : 0u, ry = (y & s) ? 1u : 0u;
+    d += s * s * ((3u * rx) ^ ry);
+    if (ry == 0) {
+      if (rx == 1) { x = (1u << kCellBits) - 1 - x; y = (1u << kCellBits) - 1 - y; }
+      const uint32_t t = x; x = y; y = t;
+    }
+  }
+  return d;
+}
 __global__ void __launch_bounds__(kCellThreads, 1) cell_sort_kernel(const float2* __restrict__ loc, uint32_t n, uint16_t* __restrict__ cell_of,
                                                                     uint32_t* __restrict__ perm_out) {
   extern __shared__ __align__(16) uint8_t cs_raw[];
@@ -312,7 +328,8 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_sort_kernel(const float2
       if (fabsf(l[k].x) < inf && fabsf(l[k].y) < inf) {
         const int cx = min((1 << kCellBits) - 1, max(0, static_cast<int>((l[k].x - ox) * sx)));
         const int cy = min((1 << kCellBits) - 1, max(0, static_cast<int>((l[k].y - oy) * sy)));
-        c = (spread7(static_cast<uint32_t>(cy)) << 1) | spread7(static_cast<uint32_t>(cx));
+        c = kCellHilbert ? hilbert7(static_cast<uint32_t>(cx), static_cast<uint32_t>(cy))
+                         : ((spread7(static_cast<uint32_t>(cy)) << 1) | spread7(static_cast<uint32_t>(cx)));
       }
       cell_of[i] = static_cast<uint16_t>(c);
       atomicAdd(&sm.cursor[c], 1u);

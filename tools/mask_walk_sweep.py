@@ -30,7 +30,7 @@ lib.ssrlcv_b200_pack(h, C.c_void_p(qd.data_ptr()), len(q), C.byref(hq))
 lib.ssrlcv_b200_pack(h, C.c_void_p(td.data_ptr()), len(t), C.byref(ht))
 lib.ssrlcv_b200_set_profiling(h, 1)
 k_ms, k_n, n_out = C.c_double(0), C.c_uint64(0), C.c_uint64(0)
-settings = [(10, 0), (4, 32), (6, 32), (8, 32), (10, 32), (12, 32), (16, 32), (24, 32), (32, 32)]
+settings = [(12, 32)]
 for mask in (2, 1):
     p = _lib.MatchParams()
     p.out_kind, p.mask_kind, p.absolute_threshold, p.relative_threshold, p.compact = T.OUT_DMATCH, mask, ev.abs_threshold, ev.rel_threshold, 1
