@@ -274,7 +274,7 @@ class Env:
         self.ctx = Context.get(local_rank)
         # A/B timing of kernel variants: SSRLCV_BENCH_TUNE="fold=0,colmask=1,chunk_q=16384,chunk_t=16384" (tools/ab_fold.sh, e2e_chunks.sh)
         from ssrlcv_b200 import _lib
-        knob_ids = {"fold": _lib.TUNE_FOLD, "colmask": _lib.TUNE_COLUMN_MASKS, "sorted": _lib.TUNE_SORTED_TARGETS, "pair": _lib.TUNE_PAIR_UNITS,
+        knob_ids = {"fold": _lib.TUNE_FOLD, "colmask": _lib.TUNE_COLUMN_MASKS, "sorted": _lib.TUNE_SORTED_TARGETS, "pair": _lib.TUNE_PAIR_UNITS, "seedonly": _lib.TUNE_SEED_ONLY,
                     "chunk_q": _lib.TUNE_HOST_CHUNK_QUERY_ROWS, "chunk_t": _lib.TUNE_HOST_CHUNK_TARGET_ROWS}
         for kv in filter(None, os.environ.get("SSRLCV_BENCH_TUNE", "").split(",")):
             k, v = kv.split("=")

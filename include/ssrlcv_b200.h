@@ -83,7 +83,9 @@ enum {
   SSRLCV_B200_TUNE_MASK_WALK = 10,            /* ... unless some row has more candidate columns than this (default 32 = never): all 32 are tested */
   SSRLCV_B200_TUNE_CELL_SORT = 11,            /* 0: spatially sorted copies always by the radix sort of Morton keys; default: sets below 65 536
                                                  rows by a one-block counting sort over image cells (pack.cu)                            */
-  SSRLCV_B200_TUNE_COUNT_ = 12
+  SSRLCV_B200_TUNE_SEED_ONLY = 12,            /* 0: seed passes through the ordinary search (winner keys); default: large seed passes take the
+                                                 distances-only variant of smax_pair.cu (no bookkeeping, no resolvers)                    */
+  SSRLCV_B200_TUNE_COUNT_ = 13
 };
 /* internal engine ids (kept for the library's own use) */
 enum { SSRLCV_B200_ENGINE_TCGEN05 = 0, SSRLCV_B200_ENGINE_SIMT = 1 };

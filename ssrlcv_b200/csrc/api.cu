@@ -25,7 +25,7 @@ cudaError_t launch_sort_gather(cudaStream_t, const ssrlcv_b200_set_impl& src, ss
                                uint32_t* vals_in, uint32_t* vals_out, void* temp, size_t temp_bytes);
 // smax_tc.cu
 cudaError_t launch_smax(cudaStream_t, const SmaxBatch&, int mask_kind, bool fold, bool colmask);
-cudaError_t launch_smax_pair(cudaStream_t, const SmaxBatch&, bool fold, bool colmask);
+cudaError_t launch_smax_pair(cudaStream_t, const SmaxBatch&, bool fold, bool colmask, bool seed_only);
 cudaError_t launch_smax_duo(cudaStream_t, const SmaxBatch&, bool fold, bool colmask);
 int smax_duo_max_pairs();
 // exact.cu
@@ -679,6 +679,7 @@ struct PairWork {
   const float* seed = nullptr;    // seed distances of the query set (device) when the ratio test will drop what exceeds it
   float seed_ratio = 0.f;
   const uint64_t* exclude = nullptr;   // runner-up search: winner keys of a previous search of the same pair (matcher.cuh q_exclude)
+  bool seed_only = false;         // the caller wants each query's smallest d2 and nothing else (seed passes): keys may carry f = 0
   bool optimistic_fold = false;   // out: the fold variant was launched before the target set's pack had reported back
   const ssrlcv_b200_set* tt = nullptr;   // out: the set the kernel reads its targets from (t, or t's spatially sorted copy)
   const ssrlcv_b200_set* qq = nullptr;   // out: the same for the queries
@@ -692,7 +693,7 @@ struct PairWork {
 // those sets once the stream has been synchronised.  optimistic == NULL: wait for the sets' packs first.
 static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* optimistic) {
   struct Group { std::vector<uint32_t> idx; uint64_t total = 0; };
-  Group groups[36];                                       // [mask kind][fold][column-mask regime][walk: one / two / two-per-CTA-of-a-pair query tiles per unit]
+  Group groups[48];                                       // [mask kind][fold][column-mask regime][walk: one / two / two-per-CTA-of-a-pair query tiles per unit / two, distances only]
   size_t keys_total = 0, qmask_total = 0;
   if (optimistic) *optimistic = false;
   for (uint32_t i = 0; i < n; ++i) {
@@ -715,7 +716,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     // each SM of the pair: bit-exact, measured slower (the accumulator hand-off crosses the pair twice), only ever run by the knob
     bool duo_units = false;
     if (ctx->knob[SSRLCV_B200_TUNE_PAIR_UNITS] == 2) duo_units = pair_units && smax_duo_max_pairs() > 0;
-    const int walk = duo_units ? 2 : (pair_units ? 1 : 0);
+    int walk = duo_units ? 2 : (pair_units ? 1 : 0);
     a.q_tile_rows = duo_units ? 4 * kBM : (pair_units ? 2 * kBM : kBM);
     a.n_qtiles = (a.nq + a.q_tile_rows - 1) / a.q_tile_rows;
     const uint64_t tiles = static_cast<uint64_t>(a.n_qtiles) * a.n_ttiles;
@@ -769,7 +770,13 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       // bookkeeping regime (smax_tc.cu): exact column masks for thresholded searches and short target sets
       bool colmask = a.d2_cap != 0x7fffffff || a.q_seed != nullptr || a.n_ttiles < 64;
       if (ctx->knob[SSRLCV_B200_TUNE_COLUMN_MASKS] >= 0) colmask = ctx->knob[SSRLCV_B200_TUNE_COLUMN_MASKS] != 0;   // A/B timing, tests
-      Group& g = groups[3 * (p.mp.kind * 4 + (fold ? 2 : 0) + (colmask ? 1 : 0)) + walk];
+      // Seed passes on the pair walk (smax_pair.cu kSeedOnly): an uncapped search is bookkeeping-bound, a minimum distance needs no
+      // bookkeeping -- the fold variant maximises 2S - (parity of |b|^2) branch-free and writes keys without an index
+      if (walk == 1 && fold && p.seed_only && a.q_seed == nullptr && a.d2_cap == 0x7fffffff && ctx->knob[SSRLCV_B200_TUNE_SEED_ONLY] != 0) {
+        walk = 3;
+        colmask = false;
+      }
+      Group& g = groups[4 * (p.mp.kind * 4 + (fold ? 2 : 0) + (colmask ? 1 : 0)) + walk];
       a.tile_begin = g.total;
       g.total += tiles;
       a.tile_end = g.total;
@@ -777,10 +784,10 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     }
   }
   uint32_t n_tc = 0;
-  for (int gi2 = 0; gi2 < 36; ++gi2) {
+  for (int gi2 = 0; gi2 < 48; ++gi2) {
     Group& g = groups[gi2];
     if (g.idx.empty()) continue;
-    const uint32_t n_ctas = launch_ctas(ctx, g.total, gi2 % 3 == 2);
+    const uint32_t n_ctas = launch_ctas(ctx, g.total, gi2 % 4 == 2);
     for (uint32_t i : g.idx) {
       SmaxArgs& a = w[i].a;
       a.total_tiles = g.total; a.n_ctas = n_ctas; a.tiles_per_split = a.n_ttiles;
@@ -870,9 +877,9 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       if (rc) return rc;
     }
     at = 0;
-    for (int gi2 = 0; gi2 < 36; ++gi2) {
+    for (int gi2 = 0; gi2 < 48; ++gi2) {
       Group& g = groups[gi2];
-      const int gi = gi2 / 3, walk = gi2 % 3;
+      const int gi = gi2 / 4, walk = gi2 % 4;
       if (g.idx.empty()) continue;
       SmaxBatch b;
       memset(&b, 0, sizeof b);
@@ -897,7 +904,8 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
         CU(cudaEventRecord(ctx->prof_events[ctx->prof_used].first, ctx->stream));
       }
       cudaError_t e = walk == 2 ? launch_smax_duo(ctx->stream, b, (gi & 2) != 0, (gi & 1) != 0)
-                    : walk == 1 ? launch_smax_pair(ctx->stream, b, (gi & 2) != 0, (gi & 1) != 0)
+                    : walk == 3 ? launch_smax_pair(ctx->stream, b, true, false, true)
+                    : walk == 1 ? launch_smax_pair(ctx->stream, b, (gi & 2) != 0, (gi & 1) != 0, false)
                                 : launch_smax(ctx->stream, b, gi / 4, (gi & 2) != 0, (gi & 1) != 0);
       if (e != cudaSuccess) return fail(ctx, static_cast<int>(e), "smax launch: %s", cudaGetErrorString(e));
       if (ctx->profiling) { CU(cudaEventRecord(ctx->prof_events[ctx->prof_used].second, ctx->stream)); ctx->prof_used++; }
@@ -922,6 +930,7 @@ static int seed_pass_enqueue(ssrlcv_b200_ctx* ctx, const ssrlcv_b200_set* query,
   PairWork w;
   memset(&w.mp, 0, sizeof w.mp);
   w.q = query; w.t = seed; w.abs_thr = FLT_MAX;
+  w.seed_only = true;
   int rc = engine_enqueue(ctx, &w, 1, optimistic);
   if (rc) return rc;
   if (w.a.nq) { launch_seed_from_keys(ctx->stream, w.a.keys, w.a.nq, w.a.nq_pad, w.a.n_splits, out_dev); ctx->launches += 1; }

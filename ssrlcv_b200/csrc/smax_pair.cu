@@ -76,9 +76,20 @@ __device__ __forceinline__ void st_state(uint32_t addr, const WinState& s) {
   asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + 16), "r"(s.m2), "r"(s.ovf) : "memory");
 }
 
-template <bool kFold, bool kColMask, bool kTiming>
+// kSeedOnly (fold variant only): the search behind getSeedDistances (ref: src/MatchFactory.cu:349-394) wants each query's smallest
+// d2 and nothing else -- no index, no tie rule, no threshold.  An uncapped search is bookkeeping-bound (a running best keeps
+// improving, profiles/r2_fixture_regimes.txt), but a minimum needs no bookkeeping: with |b|^2 = 2h + p the score S = a.b + C - h
+// loses the parity bit p, and d2 = |a|^2 + 2C - (2S - p) exactly.  The epilogue therefore maximises T = 2S - p over ALL columns
+// branch-free (one add per score in front of the max trees) and keeps one register per row: no window records, no rare path, no
+// resolvers.  The resolver warps, idle in this mode, turn each target tile's norms into -p and stage them in shared memory a few
+// tiles ahead of the epilogue (the c_full / c_empty ring; the buffers live in the window-state region this mode does not use).
+constexpr uint32_t kNegParBytes = kBN * 4;              // one int32 (0 or -1) per target of a tile
+static_assert(kColStages * kNegParBytes + 2 * 2 * kPairRows * 4 <= 2 * 2 * kPairRows * 24, "seed-only buffers fit the window-state region");
+
+template <bool kFold, bool kColMask, bool kTiming, bool kSeedOnly = false>
 __global__ void __launch_bounds__(kThreads, 1)
 smax_pair_kernel(const __grid_constant__ SmaxBatch batch) {
+  static_assert(!kSeedOnly || (kFold && !kColMask && !kTiming), "seed-only: the fold variant, no bookkeeping regime, no instrumentation");
   constexpr int32_t kWOffset = kFold ? kFoldC : kNoFoldC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -101,7 +112,7 @@ smax_pair_kernel(const __grid_constant__ SmaxBatch batch) {
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kEpiWarps); }
-    for (int i = 0; i < kColStages; ++i) { mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], kEpiWarps); }
+    for (int i = 0; i < kColStages; ++i) { mbar_init(&c_full[i], kSeedOnly ? 2 : 1); mbar_init(&c_empty[i], kEpiWarps); }   // seed-only: filled by the two resolver warps
     for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], kEpiWarps); mbar_init(&x_empty[i], 2); }
     fence_mbar_init();
   }
@@ -228,6 +239,23 @@ smax_pair_kernel(const __grid_constant__ SmaxBatch batch) {
     uint32_t uparity = 0, uiter = 0;
     long long tr_wait = 0, tr_work = 0;
     UnitIter u(batch, blockIdx.x);
+    if (kSeedOnly) {
+      // -p of every target of every tile of this CTA's units, kColStages tiles ahead of the epilogue: warp rw takes columns
+      // [128 rw, +128) of the tile, lane l four of them
+      uint32_t cs = 0, cphase = 0;
+      while (u.next(batch, blockIdx.x, kFold)) {
+        const int32_t* t_norm = u.J->a.t_norm;
+        for (uint32_t j = u.j0; j < u.j1; ++j) {
+          const int4 n4 = __ldg(reinterpret_cast<const int4*>(t_norm + static_cast<uint64_t>(j) * kBN + rw * 128) + lane);
+          mbar_wait(&c_empty[cs], cphase ^ 1);
+          const uint32_t dst = smem_u32(smem + Smem::xch + cs * kNegParBytes) + (rw * 128 + lane * 4) * 4;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(-(n4.x & 1)), "r"(-(n4.y & 1)), "r"(-(n4.z & 1)), "r"(-(n4.w & 1)) : "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&c_full[cs]);
+          if (++cs == kColStages) { cs = 0; cphase ^= 1; }
+        }
+      }
+    } else
     while (u.next(batch, blockIdx.x, kFold)) {
       if (u.last) break;
       long long w0 = 0, w1 = 0;
@@ -265,6 +293,61 @@ smax_pair_kernel(const __grid_constant__ SmaxBatch batch) {
     long long te_wait = 0, te_work = 0, te_resolve = 0, te_total0 = 0, te_cwait = 0, te_rare = 0, te_rare_n = 0;
     if (kTiming) te_total0 = clock64();
     UnitIter u(batch, blockIdx.x);
+    if (kSeedOnly) {
+      int32_t* sbest = reinterpret_cast<int32_t*>(smem + Smem::xch + kColStages * kNegParBytes);   // [unit parity][column half][256 rows]
+      while (u.next(batch, blockIdx.x, kFold)) {
+        const SmaxArgs& args = u.J->a;
+        const uint32_t row_base = u.qt * kPairRows;
+        int32_t best[2] = {0, 0};                                  // T >= 3 for every real target; padding columns give 0
+        for (uint32_t j = u.j0; j < u.j1; ++j) {
+          const uint32_t accphase = it & 1, cs = it % kColStages, cphase = (it / kColStages) & 1;
+          ++it;
+          mbar_wait(&c_full[cs], cphase);
+          const uint32_t s_np = smem_u32(smem + Smem::xch + cs * kNegParBytes) + half * (128 * 4);
+#pragma unroll
+          for (uint32_t p = 0; p < 2; ++p) {
+            mbar_wait(&t_full[p], accphase);
+            tc_fence_after();
+            uint32_t v[4][32];
+            tmem_ld_32x128(taddr0 + p * kBN, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[p]);
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) {
+#pragma unroll
+              for (uint32_t e = 0; e < 32; e += 4) {
+                const int4 np4 = ld_shared_v4(s_np + (k * 32 + e) * 4);
+                v[k][e] = v[k][e] + v[k][e] + static_cast<uint32_t>(np4.x); v[k][e + 1] = v[k][e + 1] + v[k][e + 1] + static_cast<uint32_t>(np4.y);
+                v[k][e + 2] = v[k][e + 2] + v[k][e + 2] + static_cast<uint32_t>(np4.z); v[k][e + 3] = v[k][e + 3] + v[k][e + 3] + static_cast<uint32_t>(np4.w);
+              }
+            }
+            const int32_t m = max(max(max32(v[0]), max32(v[1])), max(max32(v[2]), max32(v[3])));
+            best[p] = max(best[p], m);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&c_empty[cs]);
+        }
+        // the two column halves of a row meet in shared memory; half 0 writes the unit's key: d2 = |a|^2 + 2C - T, no index
+        const uint32_t uparity = uiter & 1;
+        int32_t* mine = sbest + (uparity * 2 + half) * kPairRows;
+        mine[my_r] = best[0]; mine[kBM + my_r] = best[1];
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        if (half == 0) {
+          const int32_t* other = sbest + (uparity * 2 + 1) * kPairRows;
+#pragma unroll
+          for (uint32_t p = 0; p < 2; ++p) {
+            const uint32_t row = row_base + p * kBM + my_r;                 // < nq_pad: rows beyond nq land in the padding of the key array
+            const int32_t T = max(best[p], other[p * kBM + my_r]);
+            const uint32_t d2 = static_cast<uint32_t>(__ldg(args.q_norm + row) + 2 * kFoldC - T);
+            args.keys[static_cast<uint64_t>(u.slot) * args.nq_pad + key_row(args.q_orig, args.nq, row)] = T > 0 ? make_key(d2, 0) : kKeyNone;
+          }
+        }
+        fill_unused_slots(args, row_base, u.slot, u.fill_end, (warp - 4) * 32, 32, lane);
+        ++uiter;                                                   // (the next unit's halves meet in the other buffer)
+      }
+    } else
     while (u.next(batch, blockIdx.x, kFold)) {
       const SmaxArgs& args = u.J->a;                               // device memory: read what the unit needs up front
       const uint32_t row_base = u.qt * kPairRows;
@@ -392,9 +475,9 @@ smax_pair_kernel(const __grid_constant__ SmaxBatch batch) {
   if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
-template <bool kFold, bool kColMask, bool kTiming>
+template <bool kFold, bool kColMask, bool kTiming, bool kSeedOnly = false>
 static cudaError_t launch_one(cudaStream_t st, const SmaxBatch& b) {
-  auto kern = smax_pair_kernel<kFold, kColMask, kTiming>;
+  auto kern = smax_pair_kernel<kFold, kColMask, kTiming, kSeedOnly>;
   // the dynamic shared-memory opt-in is a per-device attribute of the function (one context per device in multi-GPU jobs)
   static std::atomic<uint64_t> configured{0};
   int dev = 0;
@@ -410,8 +493,9 @@ static cudaError_t launch_one(cudaStream_t st, const SmaxBatch& b) {
 }  // namespace pairk
 
 // one launch over all jobs of `b` (unmasked, same fold variant and bookkeeping regime, SmaxArgs::q_tile_rows == 256)
-cudaError_t launch_smax_pair(cudaStream_t st, const SmaxBatch& b, bool fold, bool colmask) {
+cudaError_t launch_smax_pair(cudaStream_t st, const SmaxBatch& b, bool fold, bool colmask, bool seed_only) {
   using namespace pairk;
+  if (seed_only) return launch_one<true, false, false, true>(st, b);   // (the host asks for it with the fold variant only)
   if (b.timing) {   // diagnostics build (tools/kerneltiming.py)
     if (fold) return colmask ? launch_one<true, true, true>(st, b) : launch_one<true, false, true>(st, b);
     return colmask ? launch_one<false, true, true>(st, b) : launch_one<false, false, true>(st, b);

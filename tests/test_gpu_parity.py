@@ -50,7 +50,7 @@ def knobs(api):
     from ssrlcv_b200 import _lib
     from ssrlcv_b200.match_factory import Context
     names = {"fold": [_lib.TUNE_FOLD], "colmask": [_lib.TUNE_COLUMN_MASKS], "sorted": [_lib.TUNE_SORTED_TARGETS], "pair": [_lib.TUNE_PAIR_UNITS],
-             "cells": [_lib.TUNE_CELL_SORT], "mask_coop": [_lib.TUNE_MASK_COOPERATIVE], "mask_walk": [_lib.TUNE_MASK_WALK],
+             "cells": [_lib.TUNE_CELL_SORT], "seedonly": [_lib.TUNE_SEED_ONLY], "mask_coop": [_lib.TUNE_MASK_COOPERATIVE], "mask_walk": [_lib.TUNE_MASK_WALK],
              "chunk_rows": [_lib.TUNE_HOST_CHUNK_QUERY_ROWS, _lib.TUNE_HOST_CHUNK_TARGET_ROWS]}
     ctx = Context.get(0)
 
@@ -1396,6 +1396,25 @@ def test_cta_pair_walk_matches_oracle(api, knobs, nq, nt, thr):
         knobs(fold=fold, colmask=cm, pair="2")
         got = api.MatchFactory(1.0, thr).generateDistanceMatches(api.Image(0), _unity(api, q), api.Image(1), _unity(api, t)).to_numpy()
         assert len(got) == len(want) and T.fields_equal(got, want), (fold, cm)
+
+
+@pytest.mark.parametrize("nq,ns", [(8192 + 77, 9600 + 5), (16384, 8192)])
+def test_seed_pass_distances_only_variant(api, knobs, nq, ns):
+    """Large seed passes take smax_pair.cu's distances-only variant (the epilogue maximises 2S - parity(|b|^2) branch-free: no window
+    records, no resolvers): the same float distances as the ordinary search of the same library and as the oracle (ref:
+    src/MatchFactory.cu:349-394), duplicates of a query among the seed features (distance 0) and odd / even norms included."""
+    q, s = synth.make_pair(nq, ns, seed=nq ^ ns, dup=0.01)
+    s["values"][::7] ^= 1                                              # flip the parity of every seventh seed feature's norm
+    want = api.O.seed_distances(q, s)
+    qu = _unity(api, q); qu.setMemoryState(api.gpu)
+    got = {}
+    for so in ("1", "0"):
+        knobs(seedonly=so)
+        mf = api.MatchFactory(0.6, 200.0 * 200.0)
+        mf.setSeedFeatures(_unity(api, s))
+        got[so] = mf.getSeedDistances(qu).to_numpy()
+        assert np.array_equal(got[so].view(np.uint32), want.view(np.uint32)), so
+    knobs(seedonly=None)
 
 
 def _lib_mod():
