@@ -772,7 +772,10 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       if (ctx->knob[SSRLCV_B200_TUNE_COLUMN_MASKS] >= 0) colmask = ctx->knob[SSRLCV_B200_TUNE_COLUMN_MASKS] != 0;   // A/B timing, tests
       // Seed passes on the pair walk (smax_pair.cu kSeedOnly): an uncapped search is bookkeeping-bound, a minimum distance needs no
       // bookkeeping -- the fold variant maximises 2S - (parity of |b|^2) branch-free and writes keys without an index
-      if (walk == 1 && fold && p.seed_only && a.q_seed == nullptr && a.d2_cap == 0x7fffffff && ctx->knob[SSRLCV_B200_TUNE_SEED_ONLY] != 0) {
+      // (up to 65 536 seed features: record updates thin out as 1 / position, and beyond that the ordinary search's common path beats an
+      // epilogue that is bound by its shared-memory loads, profiles/r2_seed_pass_scaling.txt)
+      const bool seed_variant = ctx->knob[SSRLCV_B200_TUNE_SEED_ONLY] >= 0 ? ctx->knob[SSRLCV_B200_TUNE_SEED_ONLY] != 0 : a.n_ttiles <= 256;
+      if (walk == 1 && fold && p.seed_only && a.q_seed == nullptr && a.d2_cap == 0x7fffffff && seed_variant) {
         walk = 3;
         colmask = false;
       }
