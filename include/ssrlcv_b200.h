@@ -85,7 +85,9 @@ enum {
                                                  rows by a one-block counting sort over image cells (pack.cu)                            */
   SSRLCV_B200_TUNE_SEED_ONLY = 12,            /* 0: seed passes through the ordinary search (winner keys); default: large seed passes take the
                                                  distances-only variant of smax_pair.cu (no bookkeeping, no resolvers)                    */
-  SSRLCV_B200_TUNE_COUNT_ = 13
+  SSRLCV_B200_TUNE_LEAN_MASKED = 13,          /* 0: seeded masked searches through the ordinary masked instantiation; default: the one with the
+                                                 unmasked hot loop (smax_tc.cu kLean)                                                     */
+  SSRLCV_B200_TUNE_COUNT_ = 14
 };
 /* internal engine ids (kept for the library's own use) */
 enum { SSRLCV_B200_ENGINE_TCGEN05 = 0, SSRLCV_B200_ENGINE_SIMT = 1 };

@@ -42,7 +42,7 @@ class MatchParams(C.Structure):
 
 
 # ssrlcv_b200_tune knobs (include/ssrlcv_b200.h)
-TUNE_FOLD, TUNE_COLUMN_MASKS, TUNE_SORTED_TARGETS, TUNE_HOST_CHUNK_QUERY_ROWS, TUNE_HOST_CHUNK_TARGET_ROWS, TUNE_CROSSCHECK_SIMT, TUNE_TIMING_BUFFER, TUNE_DIAG, TUNE_PAIR_UNITS, TUNE_MASK_COOPERATIVE, TUNE_MASK_WALK, TUNE_CELL_SORT, TUNE_SEED_ONLY = range(13)
+TUNE_FOLD, TUNE_COLUMN_MASKS, TUNE_SORTED_TARGETS, TUNE_HOST_CHUNK_QUERY_ROWS, TUNE_HOST_CHUNK_TARGET_ROWS, TUNE_CROSSCHECK_SIMT, TUNE_TIMING_BUFFER, TUNE_DIAG, TUNE_PAIR_UNITS, TUNE_MASK_COOPERATIVE, TUNE_MASK_WALK, TUNE_CELL_SORT, TUNE_SEED_ONLY, TUNE_LEAN_MASKED = range(14)
 
 
 class SetArrays(C.Structure):

@@ -24,7 +24,7 @@ cudaError_t launch_cell_sort_gather(cudaStream_t, const ssrlcv_b200_set_impl& sr
 cudaError_t launch_sort_gather(cudaStream_t, const ssrlcv_b200_set_impl& src, ssrlcv_b200_set_impl& dst, uint32_t* keys_in, uint32_t* keys_out,
                                uint32_t* vals_in, uint32_t* vals_out, void* temp, size_t temp_bytes);
 // smax_tc.cu
-cudaError_t launch_smax(cudaStream_t, const SmaxBatch&, int mask_kind, bool fold, bool colmask);
+cudaError_t launch_smax(cudaStream_t, const SmaxBatch&, int mask_kind, bool fold, bool colmask, bool lean);
 cudaError_t launch_smax_pair(cudaStream_t, const SmaxBatch&, bool fold, bool colmask, bool seed_only);
 cudaError_t launch_smax_duo(cudaStream_t, const SmaxBatch&, bool fold, bool colmask);
 int smax_duo_max_pairs();
@@ -693,7 +693,7 @@ struct PairWork {
 // those sets once the stream has been synchronised.  optimistic == NULL: wait for the sets' packs first.
 static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* optimistic) {
   struct Group { std::vector<uint32_t> idx; uint64_t total = 0; };
-  Group groups[48];                                       // [mask kind][fold][column-mask regime][walk: one / two / two-per-CTA-of-a-pair query tiles per unit / two, distances only]
+  Group groups[60];                                       // [mask kind][fold][column-mask regime][walk: one / two / two-per-CTA-of-a-pair query tiles per unit / two, distances only]
   size_t keys_total = 0, qmask_total = 0;
   if (optimistic) *optimistic = false;
   for (uint32_t i = 0; i < n; ++i) {
@@ -779,7 +779,12 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
         walk = 3;
         colmask = false;
       }
-      Group& g = groups[4 * (p.mp.kind * 4 + (fold ? 2 : 0) + (colmask ? 1 : 0)) + walk];
+      // Seeded masked searches (the reference pipeline's call): the bookkeeping path is next to never taken, so they run the
+      // instantiation with the unmasked hot loop (smax_tc.cu kLean: no column ring, no boxes, no dead-tile bitmap)
+      if (walk == 0 && p.mp.kind != SSRLCV_B200_MASK_NONE && fold && colmask && a.q_seed != nullptr && p.tt->orig == nullptr && p.qq->orig == nullptr &&
+          p.exclude == nullptr && ctx->knob[SSRLCV_B200_TUNE_LEAN_MASKED] != 0)
+        walk = 4;
+      Group& g = groups[5 * (p.mp.kind * 4 + (fold ? 2 : 0) + (colmask ? 1 : 0)) + walk];
       a.tile_begin = g.total;
       g.total += tiles;
       a.tile_end = g.total;
@@ -787,10 +792,10 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     }
   }
   uint32_t n_tc = 0;
-  for (int gi2 = 0; gi2 < 48; ++gi2) {
+  for (int gi2 = 0; gi2 < 60; ++gi2) {
     Group& g = groups[gi2];
     if (g.idx.empty()) continue;
-    const uint32_t n_ctas = launch_ctas(ctx, g.total, gi2 % 4 == 2);
+    const uint32_t n_ctas = launch_ctas(ctx, g.total, gi2 % 5 == 2);
     for (uint32_t i : g.idx) {
       SmaxArgs& a = w[i].a;
       a.total_tiles = g.total; a.n_ctas = n_ctas; a.tiles_per_split = a.n_ttiles;
@@ -880,9 +885,9 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       if (rc) return rc;
     }
     at = 0;
-    for (int gi2 = 0; gi2 < 48; ++gi2) {
+    for (int gi2 = 0; gi2 < 60; ++gi2) {
       Group& g = groups[gi2];
-      const int gi = gi2 / 4, walk = gi2 % 4;
+      const int gi = gi2 / 5, walk = gi2 % 5;
       if (g.idx.empty()) continue;
       SmaxBatch b;
       memset(&b, 0, sizeof b);
@@ -909,7 +914,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       cudaError_t e = walk == 2 ? launch_smax_duo(ctx->stream, b, (gi & 2) != 0, (gi & 1) != 0)
                     : walk == 3 ? launch_smax_pair(ctx->stream, b, true, false, true)
                     : walk == 1 ? launch_smax_pair(ctx->stream, b, (gi & 2) != 0, (gi & 1) != 0, false)
-                                : launch_smax(ctx->stream, b, gi / 4, (gi & 2) != 0, (gi & 1) != 0);
+                                : launch_smax(ctx->stream, b, gi / 4, (gi & 2) != 0, (gi & 1) != 0, walk == 4);
       if (e != cudaSuccess) return fail(ctx, static_cast<int>(e), "smax launch: %s", cudaGetErrorString(e));
       if (ctx->profiling) { CU(cudaEventRecord(ctx->prof_events[ctx->prof_used].second, ctx->stream)); ctx->prof_used++; }
       launch_exact_list(ctx->stream, b, gi / 4, ctx->sm_count);

@@ -217,4 +217,20 @@ __device__ __forceinline__ QueryMask load_query_mask(const float4* src) {
   return m;
 }
 
+// The same load for a bookkeeping path that must not keep the state in registers across the matcher's hot loop (smax_tc.cu kLean):
+// volatile, so that the compiler cannot hoist it.
+template <int kMask>
+__device__ __forceinline__ QueryMask load_query_mask_rare(const float4* src) {
+  QueryMask m;
+  float4 a, b;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(src) : "memory");
+  if (kMask == SSRLCV_B200_MASK_DOUBLE) {
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(src + 1) : "memory");
+    m.seg.lo_x = a.x; m.seg.hi_x = a.y; m.seg.left_x = a.z; m.seg.left_y = a.w;
+    m.seg.slope = b.x; m.seg.top_lo = b.y; m.seg.bot_hi = b.z; m.seg.vertical = __float_as_int(b.w);
+  }
+  if (kMask == SSRLCV_B200_MASK_FUNDAMENTAL) { m.line.ex = a.x; m.line.ey = a.y; m.line.ez = a.z; }
+  return m;
+}
+
 }  // namespace b200

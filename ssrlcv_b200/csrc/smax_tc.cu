@@ -82,10 +82,19 @@ constexpr uint32_t kSmemBytes = SmemLayout::total + 1024;   // + slack for manua
 // kColMask: record WHICH columns of a window attained its maximum (true) or only the window (false), see above
 //        unit_records_columns(); chosen per job by the host (job_records_columns).
 // kTiming: per-role cycle counters (diagnostics build of the same kernel; never used by the product path).
-template <int kMask, bool kFold, bool kColMask, bool kTiming>
+// kLean (masked, fold): for searches whose bookkeeping path is next to never taken -- SEEDED masked searches, the reference
+//        pipeline's own call: the per-query seed cap leaves 0.04 % of the (query, window) pairs on real data.  The masked
+//        instantiations carry a column-data ring (target locations / window boxes staged per tile, two more barrier operations per
+//        tile in the epilogue), the dead-tile iterator and the query's mask state through the hot loop; ptxas, capped at 168
+//        registers beside a 128-register accumulator slice, answers with local-memory traffic on the hand-off chain: 168 us for the
+//        fixture's seeded DoubleConstrained search against 108 us unmasked (profiles/r2_kernel_experiments.txt section 9).  The lean
+//        instantiation has the UNMASKED hot loop: no ring, no boxes, no dead-tile bitmap (sorted copies exist for unseeded searches
+//        only); the bookkeeping path reads the mask state and the 32 target locations of a window from global memory.
+template <int kMask, bool kFold, bool kColMask, bool kTiming, bool kLean = false>
 __global__ void __launch_bounds__(kThreads, 1)
 smax_kernel(const __grid_constant__ SmaxBatch batch) {
-  constexpr bool kCols = (kMask != SSRLCV_B200_MASK_NONE) || !kFold;   // epilogue needs per-target data (locations / W)
+  static_assert(!kLean || (kMask != SSRLCV_B200_MASK_NONE && kFold && !kTiming), "lean: masked fold variants");
+  constexpr bool kCols = ((kMask != SSRLCV_B200_MASK_NONE) && !kLean) || !kFold;   // epilogue needs staged per-target data (locations / W)
   constexpr int32_t kWOffset = kFold ? kFoldC : kNoFoldC;               // the C of W_b = C - h_b
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -156,7 +165,7 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
         const int32_t* t_wcol = u.J->a.t_wcol;
         const int32_t* t_wmax = u.J->a.t_wmax;
         const float4* t_wbox = u.J->a.t_wbox;
-        const uint32_t* live_bits = kMask != SSRLCV_B200_MASK_NONE ? u.J->a.live_bits : nullptr;
+        const uint32_t* live_bits = (kMask != SSRLCV_B200_MASK_NONE && !kLean) ? u.J->a.live_bits : nullptr;
         const uint32_t live_stride = u.J->a.live_stride;
         mbar_wait(&a_empty[aslot], aphase ^ 1);
         mbar_arrive_expect_tx(&a_full[aslot], kABytes);
@@ -208,7 +217,7 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
       while (u.next(batch, blockIdx.x, kFold)) {
         mbar_wait(&a_full[aslot], aphase);
         const uint64_t a_desc = make_smem_desc(smem_u32(smem + SmemLayout::a + aslot * kABytes), 1024, kSwizzle128B);
-        const uint32_t* live_bits = kMask != SSRLCV_B200_MASK_NONE ? u.J->a.live_bits : nullptr;
+        const uint32_t* live_bits = (kMask != SSRLCV_B200_MASK_NONE && !kLean) ? u.J->a.live_bits : nullptr;
         const uint32_t live_stride = u.J->a.live_stride;
         LiveTiles tiles(live_bits, live_stride, u.qt, u.j0, u.j1);
         uint32_t j;
@@ -293,11 +302,11 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
       const uint32_t row = u.qt * kBM + quarter * 32 + lane;       // this thread's query
       const uint32_t row_c = min(row, args.nq_pad - 1);
       const float eps = args.eps;
-      const bool boxed = args.t_wbox != nullptr;
-      const uint32_t* live_bits = kMask != SSRLCV_B200_MASK_NONE ? args.live_bits : nullptr;
+      const bool boxed = !kLean && args.t_wbox != nullptr;
+      const uint32_t* live_bits = (kMask != SSRLCV_B200_MASK_NONE && !kLean) ? args.live_bits : nullptr;
       const uint32_t live_stride = args.live_stride;
       QueryMask qm;
-      if (kMask != SSRLCV_B200_MASK_NONE) qm = load_query_mask<kMask>(args.q_mask + 2 * static_cast<uint64_t>(row_c));
+      if (kMask != SSRLCV_B200_MASK_NONE && !kLean) qm = load_query_mask<kMask>(args.q_mask + 2 * static_cast<uint64_t>(row_c));
 
       // Lowest score that can still pass the absolute threshold: d2 = |a|^2 - 2 (S - C) + p <= d2_cap
       // <=> S >= C + ceil((|a|^2 - d2_cap) / 2)  (p = 0 is the permissive case).  Real scores are >= 2,
@@ -397,6 +406,8 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
                 if (kMask != SSRLCV_B200_MASK_NONE && !__any_sync(0xffffffffu, wm[k] >= st.best)) continue;
               }
               if (kMask != SSRLCV_B200_MASK_NONE) {
+                if (kLean) qm = load_query_mask_rare<kMask>(args.q_mask + 2 * static_cast<uint64_t>(row_c));   // (rare: not kept across the hot loop)
+                const float2* g_loc = args.t_loc + (static_cast<uint64_t>(j) * kBN + (c_begin + k) * kChunk);   // lean: the window's locations, global
                 // The reference's float mask (ref: src/MatchFactory.cu:2241-2254, :1613-1627) for the queries (lanes) this window
                 // matters to -- usually one.  The warp evaluates it together: the live query's mask state is broadcast, lane l
                 // tests target l of the window, the ballot comes back to the query's lane as a column mask.  Masked entries
@@ -405,7 +416,7 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
                 const bool mine = (todo >> lane) & 1u;             // this lane's query is one of the live ones
                 if (static_cast<uint32_t>(__popc(todo)) <= batch.mask_coop_max) {
                   uint32_t skip = 0;
-                  const float2 tl = ld_shared_f2(smem_u32(s_loc + (c_begin + k) * kChunk + lane));
+                  const float2 tl = kLean ? __ldg(g_loc + lane) : ld_shared_f2(smem_u32(s_loc + (c_begin + k) * kChunk + lane));
                   while (todo) {
                     const int src = __ffs(todo) - 1;
                     todo &= todo - 1;
@@ -433,7 +444,7 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
                       if (cand) {
                         const uint32_t e = __ffs(cand) - 1;
                         cand &= cand - 1u;
-                        const float2 tl = ld_shared_f2(lp + 8 * e);
+                        const float2 tl = kLean ? __ldg(g_loc + e) : ld_shared_f2(lp + 8 * e);
                         dead |= mask_skips<kMask>(qm, tl.x, tl.y, eps) ? (1u << e) : 0u;
                       }
                     }
@@ -442,7 +453,7 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
                   } else {
 #pragma unroll
                     for (int e = 0; e < 32; e += 2) {
-                      const int4 l2 = ld_shared_v4(lp + 8 * e);
+                      const int4 l2 = kLean ? __ldg(reinterpret_cast<const int4*>(g_loc + e)) : ld_shared_v4(lp + 8 * e);
                       if (mask_skips<kMask>(qm, __int_as_float(l2.x), __int_as_float(l2.y), eps)) x[e] = 0;
                       if (mask_skips<kMask>(qm, __int_as_float(l2.z), __int_as_float(l2.w), eps)) x[e + 1] = 0;
                     }
@@ -516,9 +527,9 @@ smax_kernel(const __grid_constant__ SmaxBatch batch) {
   if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
-template <int kMask, bool kFold, bool kColMask, bool kTiming>
+template <int kMask, bool kFold, bool kColMask, bool kTiming, bool kLean = false>
 static cudaError_t launch_one(cudaStream_t st, const SmaxBatch& b) {
-  auto kern = smax_kernel<kMask, kFold, kColMask, kTiming>;
+  auto kern = smax_kernel<kMask, kFold, kColMask, kTiming, kLean>;
   // the dynamic shared-memory opt-in is a per-device attribute of the function (one context per device in multi-GPU jobs)
   static std::atomic<uint64_t> configured{0};
   int dev = 0;
@@ -532,7 +543,10 @@ static cudaError_t launch_one(cudaStream_t st, const SmaxBatch& b) {
 }
 
 template <int kMask>
-static cudaError_t launch_mask(cudaStream_t st, const SmaxBatch& b, bool fold, bool colmask) {
+static cudaError_t launch_mask(cudaStream_t st, const SmaxBatch& b, bool fold, bool colmask, bool lean) {
+  if constexpr (kMask != SSRLCV_B200_MASK_NONE) {
+    if (lean && fold && colmask && !b.timing) return launch_one<kMask, true, true, false, true>(st, b);
+  }
   if (b.timing) {   // diagnostics build (tools/kerneltiming.py); fold variants of the unconstrained and DoubleConstrained kernels
     if (kMask != SSRLCV_B200_MASK_FUNDAMENTAL && fold)
       return colmask ? launch_one<kMask == SSRLCV_B200_MASK_FUNDAMENTAL ? 0 : kMask, true, true, true>(st, b)
@@ -545,11 +559,11 @@ static cudaError_t launch_mask(cudaStream_t st, const SmaxBatch& b, bool fold, b
 }
 
 // one launch over all jobs of `b` (same mask kind, fold variant and bookkeeping regime); b.jobs is device memory
-cudaError_t launch_smax(cudaStream_t st, const SmaxBatch& b, int mask_kind, bool fold, bool colmask) {
+cudaError_t launch_smax(cudaStream_t st, const SmaxBatch& b, int mask_kind, bool fold, bool colmask, bool lean) {
   switch (mask_kind) {
-    case SSRLCV_B200_MASK_NONE: return launch_mask<SSRLCV_B200_MASK_NONE>(st, b, fold, colmask);
-    case SSRLCV_B200_MASK_FUNDAMENTAL: return launch_mask<SSRLCV_B200_MASK_FUNDAMENTAL>(st, b, fold, colmask);
-    default: return launch_mask<SSRLCV_B200_MASK_DOUBLE>(st, b, fold, colmask);
+    case SSRLCV_B200_MASK_NONE: return launch_mask<SSRLCV_B200_MASK_NONE>(st, b, fold, colmask, false);
+    case SSRLCV_B200_MASK_FUNDAMENTAL: return launch_mask<SSRLCV_B200_MASK_FUNDAMENTAL>(st, b, fold, colmask, lean);
+    default: return launch_mask<SSRLCV_B200_MASK_DOUBLE>(st, b, fold, colmask, lean);
   }
 }
 

@@ -50,7 +50,7 @@ def knobs(api):
     from ssrlcv_b200 import _lib
     from ssrlcv_b200.match_factory import Context
     names = {"fold": [_lib.TUNE_FOLD], "colmask": [_lib.TUNE_COLUMN_MASKS], "sorted": [_lib.TUNE_SORTED_TARGETS], "pair": [_lib.TUNE_PAIR_UNITS],
-             "cells": [_lib.TUNE_CELL_SORT], "seedonly": [_lib.TUNE_SEED_ONLY], "mask_coop": [_lib.TUNE_MASK_COOPERATIVE], "mask_walk": [_lib.TUNE_MASK_WALK],
+             "cells": [_lib.TUNE_CELL_SORT], "seedonly": [_lib.TUNE_SEED_ONLY], "lean": [_lib.TUNE_LEAN_MASKED], "mask_coop": [_lib.TUNE_MASK_COOPERATIVE], "mask_walk": [_lib.TUNE_MASK_WALK],
              "chunk_rows": [_lib.TUNE_HOST_CHUNK_QUERY_ROWS, _lib.TUNE_HOST_CHUNK_TARGET_ROWS]}
     ctx = Context.get(0)
 
@@ -1415,6 +1415,33 @@ def test_seed_pass_distances_only_variant(api, knobs, nq, ns):
         got[so] = mf.getSeedDistances(qu).to_numpy()
         assert np.array_equal(got[so].view(np.uint32), want.view(np.uint32)), so
     knobs(seedonly=None)
+
+
+@pytest.mark.parametrize("ratio,thr", [(0.8, 1.5e5), (1.0, FLT_MAX)])
+def test_seeded_masked_searches_lean_instantiation(api, everest, knobs, ratio, thr):
+    """Seeded masked searches run smax_tc.cu's lean instantiation (the unmasked hot loop; mask state and target locations read from
+    global memory in the bookkeeping path): same records as the ordinary masked instantiation and as the oracle -- tight seed
+    distances (bookkeeping rare) and a loose ratio (bookkeeping frequent), duplicates and a ragged last tile included."""
+    q, t = synth.make_pair(3000 + 7, 5000 + 13, seed=83, dup=0.02)
+    sd = api.O.seed_distances(q, synth.make_seed(700))
+    su = api.Unity(sd, np.dtype("<f4"), api.cpu)
+    qi, ti = api.Image(0, everest.cameras[0]), api.Image(1, everest.cameras[1])
+    F = np.array([[1e-6, 2e-6, 0.0015], [-3e-6, 1e-7, -1.0], [-0.0013, 1.0, 4.0]], np.float32)
+    p = api.O.make_params(out_kind=T.OUT_DMATCH, mask_kind=T.MASK_DOUBLE, has_seed=True, abs_threshold=thr, rel_threshold=ratio, query_id=0, target_id=1,
+                          epsilon=25, delta=5, query_camera=everest.cameras[0], target_camera=everest.cameras[1])
+    want = api.O.generate_matches(p, q, t, sd)
+    pf = api.O.make_params(out_kind=T.OUT_DMATCH, mask_kind=T.MASK_FUNDAMENTAL, has_seed=True, abs_threshold=thr, rel_threshold=ratio, query_id=0,
+                           target_id=1, epsilon=30.0, fundamental=F)
+    want_f = api.O.generate_matches(pf, q, t, sd)
+    assert len(want) > 10 and len(want_f) > 10
+    for lean in ("1", "0"):
+        knobs(lean=lean)
+        mf = api.MatchFactory(ratio, thr)
+        got = mf.generateDistanceMatchesDoubleConstrained(qi, _unity(api, q), ti, _unity(api, t), 25.0, 5.0, su).to_numpy()
+        assert T.fields_equal(got, want), lean
+        got = mf.generateDistanceMatchesConstrained(qi, _unity(api, q), ti, _unity(api, t), 30.0, F, su).to_numpy()
+        assert T.fields_equal(got, want_f), lean
+    knobs(lean=None)
 
 
 def _lib_mod():

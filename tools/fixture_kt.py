@@ -50,6 +50,8 @@ if seeded:
 lib.ssrlcv_b200_set_profiling(h, 1)
 k_ms, k_n = C.c_double(0), C.c_uint64(0)
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+if os.environ.get("KT_LEAN"):
+    lib.ssrlcv_b200_tune(h, _lib.TUNE_LEAN_MASKED, int(os.environ["KT_LEAN"]))
 if os.environ.get("KT_PAIR"):
     lib.ssrlcv_b200_tune(h, _lib.TUNE_PAIR_UNITS, int(os.environ["KT_PAIR"]))
 cm_env = os.environ.get("KT_COLMASK")
