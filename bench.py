@@ -82,11 +82,13 @@ def big_pair(nq, nt, seed):
     return np.concatenate(qs)[:nq], np.concatenate(ts)[:nt]
 
 
-def bind_to_gpu_numa(index):
+def bind_to_gpu_numa(index, local_world=1):
     """Run this process on the CPUs local to GPU `index` (NVML's ideal CPU affinity) so that the pinned host buffers of the
     e2e leg are allocated, and their copies issued, on the NUMA node the GPU hangs off; a pinned buffer on the far socket
-    costs up to 3x in H2D time (profiles/r1f_e2eprof_c3.txt).  Returns the previous mask (restore before the CPU baseline,
-    which wants every core), or None when NVML is not available."""
+    costs up to 3x in H2D time (profiles/r1f_e2eprof_c3.txt).  With several ranks on one host whose GPUs share a CPU set (all
+    eight GPUs of this pool's boxes report CPUs 0-31), every rank takes its own slice of it: the launch chain of a step is a handful
+    of host calls a few microseconds apart, and eight ranks' threads migrating over the same cores show up as launch gaps.
+    Returns the previous mask (restore before the CPU baseline, which wants every core), or None when NVML is not available."""
     try:
         import pynvml
         import torch
@@ -98,6 +100,12 @@ def bind_to_gpu_numa(index):
         prev = os.sched_getaffinity(0)
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(prev) + 64) // 64)
         cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1} & prev
+        if cpus and local_world > 1:
+            order = sorted(cpus)
+            per = len(order) // local_world
+            if per >= 2:
+                mine = set(order[(index % local_world) * per:(index % local_world + 1) * per])
+                cpus = mine or cpus
         if cpus:
             os.sched_setaffinity(0, cpus)
         return prev
@@ -265,7 +273,7 @@ class Env:
         from ssrlcv_b200.match_factory import Context
         self.torch, self.rank, self.world, self.local_rank = torch, rank, world, local_rank
         torch.cuda.set_device(local_rank)
-        self.prev_affinity = bind_to_gpu_numa(local_rank)
+        self.prev_affinity = bind_to_gpu_numa(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
         self.dist = None
         if world > 1:
             import torch.distributed as dist
@@ -685,6 +693,9 @@ def run_c4_one_process(args, w, env):
         store.wait([key])
         return None
     line = None
+    mask_here = os.sched_getaffinity(0)
+    if env.prev_affinity:
+        os.sched_setaffinity(0, env.prev_affinity)   # this ONE process drives every GPU with a host thread per device: all the CPUs, not rank 0's slice
     try:
         V, n = w["views"], w["n"]
         views = []
@@ -761,6 +772,7 @@ def run_c4_one_process(args, w, env):
     except Exception as e:  # noqa: BLE001
         line = {"error": repr(e)}
     finally:
+        os.sched_setaffinity(0, mask_here)
         if store is not None:
             store.set(key, "1")
     return line
