@@ -693,7 +693,15 @@ struct PairWork {
 // those sets once the stream has been synchronised.  optimistic == NULL: wait for the sets' packs first.
 static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* optimistic) {
   struct Group { std::vector<uint32_t> idx; uint64_t total = 0; };
-  Group groups[60];                                       // [mask kind][fold][column-mask regime][walk: one / two / two-per-CTA-of-a-pair query tiles per unit / two, distances only]
+  // how a job walks the score matrix = which kernel family / instantiation serves it (one launch per non-empty group)
+  enum Walk { kWalkTile = 0,       // smax_tc.cu: one query tile per unit (every mask kind, any size)
+              kWalkPair = 1,       // smax_pair.cu: two query tiles per unit (large unmasked searches)
+              kWalkDuo = 2,        // smax_duo.cu: four per CTA pair, tcgen05 cta_group::2 (knob only: measured slower)
+              kWalkPairSeed = 3,   // smax_pair.cu kSeedOnly: seed passes, distances only
+              kWalkTileLean = 4,   // smax_tc.cu kLean: seeded masked searches, unmasked hot loop
+              kWalks = 5 };
+  constexpr int kGroups = 3 * 4 * kWalks;                 // [mask kind][fold][column-mask regime][walk]
+  Group groups[kGroups];
   size_t keys_total = 0, qmask_total = 0;
   if (optimistic) *optimistic = false;
   for (uint32_t i = 0; i < n; ++i) {
@@ -716,7 +724,7 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     // each SM of the pair: bit-exact, measured slower (the accumulator hand-off crosses the pair twice), only ever run by the knob
     bool duo_units = false;
     if (ctx->knob[SSRLCV_B200_TUNE_PAIR_UNITS] == 2) duo_units = pair_units && smax_duo_max_pairs() > 0;
-    int walk = duo_units ? 2 : (pair_units ? 1 : 0);
+    int walk = duo_units ? kWalkDuo : (pair_units ? kWalkPair : kWalkTile);
     a.q_tile_rows = duo_units ? 4 * kBM : (pair_units ? 2 * kBM : kBM);
     a.n_qtiles = (a.nq + a.q_tile_rows - 1) / a.q_tile_rows;
     const uint64_t tiles = static_cast<uint64_t>(a.n_qtiles) * a.n_ttiles;
@@ -775,16 +783,16 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       // (up to 65 536 seed features: record updates thin out as 1 / position, and beyond that the ordinary search's common path beats an
       // epilogue that is bound by its shared-memory loads, profiles/r2_seed_pass_scaling.txt)
       const bool seed_variant = ctx->knob[SSRLCV_B200_TUNE_SEED_ONLY] >= 0 ? ctx->knob[SSRLCV_B200_TUNE_SEED_ONLY] != 0 : a.n_ttiles <= 256;
-      if (walk == 1 && fold && p.seed_only && a.q_seed == nullptr && a.d2_cap == 0x7fffffff && seed_variant) {
-        walk = 3;
+      if (walk == kWalkPair && fold && p.seed_only && a.q_seed == nullptr && a.d2_cap == 0x7fffffff && seed_variant) {
+        walk = kWalkPairSeed;
         colmask = false;
       }
       // Seeded masked searches (the reference pipeline's call): the bookkeeping path is next to never taken, so they run the
       // instantiation with the unmasked hot loop (smax_tc.cu kLean: no column ring, no boxes, no dead-tile bitmap)
-      if (walk == 0 && p.mp.kind != SSRLCV_B200_MASK_NONE && fold && colmask && a.q_seed != nullptr && p.tt->orig == nullptr && p.qq->orig == nullptr &&
+      if (walk == kWalkTile && p.mp.kind != SSRLCV_B200_MASK_NONE && fold && colmask && a.q_seed != nullptr && p.tt->orig == nullptr && p.qq->orig == nullptr &&
           p.exclude == nullptr && ctx->knob[SSRLCV_B200_TUNE_LEAN_MASKED] != 0)
-        walk = 4;
-      Group& g = groups[5 * (p.mp.kind * 4 + (fold ? 2 : 0) + (colmask ? 1 : 0)) + walk];
+        walk = kWalkTileLean;
+      Group& g = groups[kWalks * (p.mp.kind * 4 + (fold ? 2 : 0) + (colmask ? 1 : 0)) + walk];
       a.tile_begin = g.total;
       g.total += tiles;
       a.tile_end = g.total;
@@ -792,10 +800,10 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
     }
   }
   uint32_t n_tc = 0;
-  for (int gi2 = 0; gi2 < 60; ++gi2) {
+  for (int gi2 = 0; gi2 < kGroups; ++gi2) {
     Group& g = groups[gi2];
     if (g.idx.empty()) continue;
-    const uint32_t n_ctas = launch_ctas(ctx, g.total, gi2 % 5 == 2);
+    const uint32_t n_ctas = launch_ctas(ctx, g.total, gi2 % kWalks == kWalkDuo);
     for (uint32_t i : g.idx) {
       SmaxArgs& a = w[i].a;
       a.total_tiles = g.total; a.n_ctas = n_ctas; a.tiles_per_split = a.n_ttiles;
@@ -885,9 +893,9 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
       if (rc) return rc;
     }
     at = 0;
-    for (int gi2 = 0; gi2 < 60; ++gi2) {
+    for (int gi2 = 0; gi2 < kGroups; ++gi2) {
       Group& g = groups[gi2];
-      const int gi = gi2 / 5, walk = gi2 % 5;
+      const int gi = gi2 / kWalks, walk = gi2 % kWalks;     // gi = mask kind * 4 + fold * 2 + column masks
       if (g.idx.empty()) continue;
       SmaxBatch b;
       memset(&b, 0, sizeof b);
@@ -911,10 +919,10 @@ static int engine_enqueue(ssrlcv_b200_ctx* ctx, PairWork* w, uint32_t n, bool* o
         }
         CU(cudaEventRecord(ctx->prof_events[ctx->prof_used].first, ctx->stream));
       }
-      cudaError_t e = walk == 2 ? launch_smax_duo(ctx->stream, b, (gi & 2) != 0, (gi & 1) != 0)
-                    : walk == 3 ? launch_smax_pair(ctx->stream, b, true, false, true)
-                    : walk == 1 ? launch_smax_pair(ctx->stream, b, (gi & 2) != 0, (gi & 1) != 0, false)
-                                : launch_smax(ctx->stream, b, gi / 4, (gi & 2) != 0, (gi & 1) != 0, walk == 4);
+      cudaError_t e = walk == kWalkDuo      ? launch_smax_duo(ctx->stream, b, (gi & 2) != 0, (gi & 1) != 0)
+                    : walk == kWalkPairSeed ? launch_smax_pair(ctx->stream, b, true, false, true)
+                    : walk == kWalkPair     ? launch_smax_pair(ctx->stream, b, (gi & 2) != 0, (gi & 1) != 0, false)
+                                            : launch_smax(ctx->stream, b, gi / 4, (gi & 2) != 0, (gi & 1) != 0, walk == kWalkTileLean);
       if (e != cudaSuccess) return fail(ctx, static_cast<int>(e), "smax launch: %s", cudaGetErrorString(e));
       if (ctx->profiling) { CU(cudaEventRecord(ctx->prof_events[ctx->prof_used].second, ctx->stream)); ctx->prof_used++; }
       launch_exact_list(ctx->stream, b, gi / 4, ctx->sm_count);
