@@ -82,6 +82,17 @@ def big_pair(nq, nt, seed):
     return np.concatenate(qs)[:nq], np.concatenate(ts)[:nt]
 
 
+def cpu_slice(cpus, index, local_world):
+    """The part of the CPU set `cpus` that local rank `index` of `local_world` ranks keeps for itself: equal contiguous slices in
+    ascending CPU order; the whole set when the ranks would get fewer than two CPUs each."""
+    order = sorted(cpus)
+    per = len(order) // max(local_world, 1)
+    if local_world <= 1 or per < 2:
+        return set(order)
+    r = index % local_world
+    return set(order[r * per:(r + 1) * per])
+
+
 def bind_to_gpu_numa(index, local_world=1):
     """Run this process on the CPUs local to GPU `index` (NVML's ideal CPU affinity) so that the pinned host buffers of the
     e2e leg are allocated, and their copies issued, on the NUMA node the GPU hangs off; a pinned buffer on the far socket
@@ -100,12 +111,8 @@ def bind_to_gpu_numa(index, local_world=1):
         prev = os.sched_getaffinity(0)
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(prev) + 64) // 64)
         cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1} & prev
-        if cpus and local_world > 1:
-            order = sorted(cpus)
-            per = len(order) // local_world
-            if per >= 2:
-                mine = set(order[(index % local_world) * per:(index % local_world + 1) * per])
-                cpus = mine or cpus
+        if cpus:
+            cpus = cpu_slice(cpus, index, local_world)
         if cpus:
             os.sched_setaffinity(0, cpus)
         return prev

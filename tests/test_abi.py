@@ -190,3 +190,15 @@ def test_header_is_plain_c_and_links(tmp_path):
     exe = tmp_path / "abi"
     subprocess.check_call(["gcc", str(tmp_path / "abi.o"), "-L", libdir, "-lssrlcv_match_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)])
     assert subprocess.call([str(exe)]) == 0
+
+
+def test_bench_gives_every_local_rank_its_own_cpus():
+    """bench.py: the ranks of one host split the GPU-local CPU set (this pool's eight GPUs all report CPUs 0-31) into disjoint slices."""
+    import bench
+    cpus = set(range(32))
+    slices = [bench.cpu_slice(cpus, r, 8) for r in range(8)]
+    assert all(len(s) == 4 for s in slices) and set().union(*slices) == cpus
+    assert all(slices[a].isdisjoint(slices[b]) for a in range(8) for b in range(a))
+    assert bench.cpu_slice(cpus, 0, 1) == cpus
+    assert bench.cpu_slice(set(range(6)), 3, 8) == set(range(6))          # fewer than two CPUs per rank: no slicing
+    assert bench.cpu_slice({3, 9, 4, 8}, 1, 2) == {8, 9}
